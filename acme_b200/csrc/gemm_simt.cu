@@ -1,0 +1,332 @@
+// K6, fp32 parity mode: one tiled SIMT GEMM (FFMA, fp32 accumulate) with pluggable operand
+// loaders, used for every dense contraction of the Q-network / critic / policy:
+//   linear fwd / dgrad / wgrad           (acme/tf/networks/duelling.py:37-59, continuous.py:37-68)
+//   conv2d fwd / wgrad / dgrad (NHWC, TF-SAME asymmetric padding, implicit im2col -- no col buffer)
+//                                        (acme/tf/networks/atari.py:36-52)
+// This mode exists to meet the 1e-5 parity bar against the fp32 oracle; the speed mode is the
+// tcgen05 path in gemm_tc.cu.  C[row, col] = sum_red A(row, red) * B(red, col).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace b200rl {
+
+constexpr int BM = 64, BN = 64, BK = 16, GEMM_THREADS = 256;
+
+// ---- loaders.  load(outer, red) returns 4 values:
+//   kRedContig  : (outer, red .. red+3)          -- 4 consecutive reduction indices
+//   !kRedContig : (outer .. outer+3, red)        -- 4 consecutive outer indices
+// Out-of-range elements read as zero.  `outer` is the row index for A and the column index for B.
+struct DenseRed {   // element (outer, red) at p[outer * ld + red]
+  static constexpr bool kRedContig = true;
+  const float* p; int ld; int n_outer; int n_red;
+  __device__ __forceinline__ float4 load(int outer, int red) const {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (outer >= n_outer || red >= n_red) return v;
+    const float* q = p + (size_t)outer * ld + red;
+    if (red + 3 < n_red && ((((uintptr_t)q) & 15) == 0)) return __ldg(reinterpret_cast<const float4*>(q));
+    v.x = __ldg(q);
+    if (red + 1 < n_red) v.y = __ldg(q + 1);
+    if (red + 2 < n_red) v.z = __ldg(q + 2);
+    if (red + 3 < n_red) v.w = __ldg(q + 3);
+    return v;
+  }
+};
+struct DenseOuter { // element (outer, red) at p[red * ld + outer]
+  static constexpr bool kRedContig = false;
+  const float* p; int ld; int n_outer; int n_red;
+  __device__ __forceinline__ float4 load(int outer, int red) const {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (outer >= n_outer || red >= n_red) return v;
+    const float* q = p + (size_t)red * ld + outer;
+    if (outer + 3 < n_outer && ((((uintptr_t)q) & 15) == 0)) return __ldg(reinterpret_cast<const float4*>(q));
+    v.x = __ldg(q);
+    if (outer + 1 < n_outer) v.y = __ldg(q + 1);
+    if (outer + 2 < n_outer) v.z = __ldg(q + 2);
+    if (outer + 3 < n_outer) v.w = __ldg(q + 3);
+    return v;
+  }
+};
+
+// implicit im2col of an NHWC tensor: pixel m = (b, oy, ox), patch index k = (ky, kx, ci); C % 4 == 0
+struct Im2colBase {
+  const void* x; int u8; b200rl_conv_geom g; int Mtot; int Ktot;
+  __device__ __forceinline__ float4 fetch(int m, int k) const {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m >= Mtot || k >= Ktot) return v;
+    const int ox = m % g.OW; int t = m / g.OW; const int oy = t % g.OH; const int b = t / g.OH;
+    const int ci = k % g.C; int t2 = k / g.C; const int kx = t2 % g.kw; const int ky = t2 / g.kw;
+    const int iy = oy * g.stride - g.pad_top + ky, ix = ox * g.stride - g.pad_left + kx;
+    if (iy < 0 || iy >= g.H || ix < 0 || ix >= g.W) return v;
+    const size_t off = (((size_t)b * g.H + iy) * g.W + ix) * g.C + ci;
+    if (u8) {
+      uchar4 q = __ldg(reinterpret_cast<const uchar4*>((const uint8_t*)x + off));
+      // float32(u8)/255 with a true division: equals np.float32(u/255.0) for all 256 values
+      v.x = __fdiv_rn((float)q.x, 255.f); v.y = __fdiv_rn((float)q.y, 255.f);
+      v.z = __fdiv_rn((float)q.z, 255.f); v.w = __fdiv_rn((float)q.w, 255.f);
+    } else {
+      v = __ldg(reinterpret_cast<const float4*>((const float*)x + off));
+    }
+    return v;
+  }
+};
+struct Im2colRows : Im2colBase {   // A of conv fwd: (outer = pixel m, red = k)
+  static constexpr bool kRedContig = true;
+  __device__ __forceinline__ float4 load(int outer, int red) const { return fetch(outer, red); }
+};
+struct Im2colCols : Im2colBase {   // B of conv wgrad: (outer = k, red = pixel m): 4 consecutive k
+  static constexpr bool kRedContig = false;
+  __device__ __forceinline__ float4 load(int outer, int red) const { return fetch(red, outer); }
+};
+
+// conv dgrad in gather form: row m' = input pixel (b, iy, ix); red = (ky, kx, co); Cout % 4 == 0
+struct DgradRows {
+  static constexpr bool kRedContig = true;
+  const float* dy; b200rl_conv_geom g; int Mtot; int Rtot;
+  __device__ __forceinline__ float4 load(int m, int r) const {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m >= Mtot || r >= Rtot) return v;
+    const int ix = m % g.W; int t = m / g.W; const int iy = t % g.H; const int b = t / g.H;
+    const int co = r % g.Cout; int t2 = r / g.Cout; const int kx = t2 % g.kw; const int ky = t2 / g.kw;
+    const int ny = iy + g.pad_top - ky, nx = ix + g.pad_left - kx;
+    if (ny < 0 || nx < 0 || ny % g.stride || nx % g.stride) return v;
+    const int oy = ny / g.stride, ox = nx / g.stride;
+    if (oy >= g.OH || ox >= g.OW) return v;
+    return __ldg(reinterpret_cast<const float4*>(dy + (((size_t)b * g.OH + oy) * g.OW + ox) * g.Cout + co));
+  }
+};
+struct DgradWeights {  // B(red = (ky,kx,co), outer = ci) = w[co][ky][kx][ci]; 4 consecutive ci
+  static constexpr bool kRedContig = false;
+  const float* w; b200rl_conv_geom g; int Rtot;
+  __device__ __forceinline__ float4 load(int ci, int r) const {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ci >= g.C || r >= Rtot) return v;
+    const int co = r % g.Cout; int t2 = r / g.Cout; const int kx = t2 % g.kw; const int ky = t2 / g.kw;
+    return __ldg(reinterpret_cast<const float4*>(w + (((size_t)co * g.kh + ky) * g.kw + kx) * g.C + ci));
+  }
+};
+
+// ---- epilogue
+struct Epilogue {
+  float* out; int ldo;
+  const float* bias;   // per column, nullable
+  int act;             // applied after bias
+  const float* mask;   // nullable: multiply by act'(mask[row, col])
+  int ldmask; int mask_act;
+  float* partial;      // non-null: split-K partial sums [split][M][N], epilogue deferred
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case B200RL_ACT_RELU: return fmaxf(v, 0.f);
+    case B200RL_ACT_ELU: return v > 0.f ? v : expm1f(v);
+    case B200RL_ACT_TANH: return tanhf(v);
+    default: return v;
+  }
+}
+__device__ __forceinline__ float act_grad_out(float y, int act) {
+  switch (act) {
+    case B200RL_ACT_RELU: return y > 0.f ? 1.f : 0.f;
+    case B200RL_ACT_ELU: return y > 0.f ? 1.f : y + 1.f;
+    case B200RL_ACT_TANH: return 1.f - y * y;
+    default: return 1.f;
+  }
+}
+__device__ __forceinline__ void finish(const Epilogue& e, int row, int col, float acc) {
+  if (e.bias) acc += e.bias[col];
+  acc = apply_act(acc, e.act);
+  if (e.mask) acc *= act_grad_out(e.mask[(size_t)row * e.ldmask + col], e.mask_act);
+  e.out[(size_t)row * e.ldo + col] = acc;
+}
+
+template <class AL, class BL>
+__global__ void __launch_bounds__(GEMM_THREADS)
+gemm_kernel(AL a, BL b, Epilogue epi, int M, int N, int K, int k_per_split) {
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int row0 = blockIdx.y * BM, col0 = blockIdx.x * BN;
+  const int k_begin = blockIdx.z * k_per_split;
+  const int k_end = min(K, k_begin + k_per_split);
+  const int tx = tid & 15, ty = tid >> 4;
+
+  // per-thread load coordinates inside a tile (each thread moves one float4 of A and one of B)
+  const int a_outer = AL::kRedContig ? (tid >> 2) : ((tid & 15) << 2);
+  const int a_red = AL::kRedContig ? ((tid & 3) << 2) : (tid >> 4);
+  const int b_outer = BL::kRedContig ? (tid >> 2) : ((tid & 15) << 2);
+  const int b_red = BL::kRedContig ? ((tid & 3) << 2) : (tid >> 4);
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  auto stash = [&](int buf, float4 av, float4 bv) {
+    if (AL::kRedContig) {
+      As[buf][a_red + 0][a_outer] = av.x; As[buf][a_red + 1][a_outer] = av.y;
+      As[buf][a_red + 2][a_outer] = av.z; As[buf][a_red + 3][a_outer] = av.w;
+    } else {
+      *reinterpret_cast<float4*>(&As[buf][a_red][a_outer]) = av;
+    }
+    if (BL::kRedContig) {
+      Bs[buf][b_red + 0][b_outer] = bv.x; Bs[buf][b_red + 1][b_outer] = bv.y;
+      Bs[buf][b_red + 2][b_outer] = bv.z; Bs[buf][b_red + 3][b_outer] = bv.w;
+    } else {
+      *reinterpret_cast<float4*>(&Bs[buf][b_red][b_outer]) = bv;
+    }
+  };
+
+  int buf = 0;
+  {
+    float4 av = a.load(row0 + a_outer, k_begin + a_red);
+    float4 bv = b.load(col0 + b_outer, k_begin + b_red);
+    stash(0, av, bv);
+  }
+  __syncthreads();
+  for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+    const bool more = k0 + BK < k_end;
+    float4 av, bv;
+    if (more) {
+      av = a.load(row0 + a_outer, k0 + BK + a_red);
+      bv = b.load(col0 + b_outer, k0 + BK + b_red);
+    }
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 ar = *reinterpret_cast<const float4*>(&As[buf][kk][ty << 2]);
+      const float4 br = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx << 2]);
+      const float af[4] = {ar.x, ar.y, ar.z, ar.w}, bf[4] = {br.x, br.y, br.z, br.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(af[i], bf[j], acc[i][j]);
+    }
+    if (more) stash(buf ^ 1, av, bv);
+    __syncthreads();
+    buf ^= 1;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = row0 + (ty << 2) + i;
+    if (row >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = col0 + (tx << 2) + j;
+      if (col >= N) continue;
+      if (epi.partial) epi.partial[((size_t)blockIdx.z * M + row) * N + col] = acc[i][j];
+      else finish(epi, row, col, acc[i][j]);
+    }
+  }
+}
+
+__global__ void splitk_finish_kernel(Epilogue epi, int M, int N, int splits) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)M * N) return;
+  const int row = (int)(i / N), col = (int)(i % N);
+  float acc = 0.f;
+  for (int s = 0; s < splits; ++s) acc += epi.partial[((size_t)s * M + row) * N + col];  // fixed order
+  finish(epi, row, col, acc);
+}
+
+__global__ void colsum_kernel(int M, int N, const float* __restrict__ x, int ld, float* __restrict__ out) {
+  // out[n] = sum_m x[m, n]; block = 32 columns x 8 row-lanes, fixed-order tree over the 8 lanes
+  __shared__ float part[8][33];
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f;
+  if (col < N)
+    for (int m = threadIdx.y; m < M; m += 8) s += x[(size_t)m * ld + col];
+  part[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < N) {
+    float t = 0.f;
+    for (int r = 0; r < 8; ++r) t += part[r][threadIdx.x];
+    out[col] = t;
+  }
+}
+
+template <class AL, class BL>
+static int launch_gemm(const AL& a, const BL& b, Epilogue epi, int M, int N, int K, void* ws, int64_t ws_bytes,
+                       cudaStream_t stream) {
+  const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
+  int splits = 1;
+  if (tiles < 2 * kNumSMs && K >= 4 * BK) {
+    splits = ceil_div(2 * kNumSMs, tiles);
+    splits = std::min(splits, K / (2 * BK));
+    splits = std::min(splits, 64);
+    const int64_t cap = ws ? ws_bytes / ((int64_t)M * N * 4) : 0;
+    splits = (int)std::min<int64_t>(splits, cap);
+    if (splits < 1) splits = 1;
+  }
+  int k_per_split = ceil_div(ceil_div(K, splits), BK) * BK;
+  splits = ceil_div(K, k_per_split);
+  dim3 grid(ceil_div(N, BN), ceil_div(M, BM), splits);
+  if (splits > 1) epi.partial = (float*)ws; else epi.partial = nullptr;
+  gemm_kernel<AL, BL><<<grid, GEMM_THREADS, 0, stream>>>(a, b, epi, M, N, K, k_per_split);
+  B200RL_LAUNCH_OK();
+  if (splits > 1) {
+    splitk_finish_kernel<<<(int)ceil_div<long long>((long long)M * N, 256), 256, 0, stream>>>(epi, M, N, splits);
+    B200RL_LAUNCH_OK();
+  }
+  return B200RL_OK;
+}
+
+static int launch_colsum(int M, int N, const float* x, int ld, float* out, cudaStream_t stream) {
+  colsum_kernel<<<ceil_div(N, 32), dim3(32, 8), 0, stream>>>(M, N, x, ld, out);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+
+// ---------------------------------------------------------------- fp32 entry points (precision 0)
+int simt_linear_fwd(int M, int N, int K, const float* x, int ldx, const float* w, const float* bias, float* y,
+                    int ldy, int act, void* ws, int64_t wsb, cudaStream_t s) {
+  DenseRed a{x, ldx, M, K};
+  DenseRed b{w, K, N, K};
+  Epilogue e{y, ldy, bias, act, nullptr, 0, 0, nullptr};
+  return launch_gemm(a, b, e, M, N, K, ws, wsb, s);
+}
+int simt_linear_dgrad(int M, int N, int K, const float* dy, int lddy, const float* w, float* dx, int lddx,
+                      const float* mask, int ldmask, int mask_act, void* ws, int64_t wsb, cudaStream_t s) {
+  DenseRed a{dy, lddy, M, N};        // rows m, red n
+  DenseOuter b{w, K, K, N};          // (outer = k, red = n) at w[n*K + k]
+  Epilogue e{dx, lddx, nullptr, 0, mask, ldmask, mask_act, nullptr};
+  return launch_gemm(a, b, e, M, K, N, ws, wsb, s);
+}
+int simt_linear_wgrad(int M, int N, int K, const float* dy, int lddy, const float* x, int ldx, float* dw, float* db,
+                      void* ws, int64_t wsb, cudaStream_t s) {
+  DenseOuter a{dy, lddy, N, M};      // (outer = n, red = m) at dy[m*ld + n]
+  DenseOuter b{x, ldx, K, M};        // (outer = k, red = m) at x[m*ld + k]
+  Epilogue e{dw, K, nullptr, 0, nullptr, 0, 0, nullptr};
+  int rc = launch_gemm(a, b, e, N, K, M, ws, wsb, s);
+  if (rc) return rc;
+  if (db) return launch_colsum(M, N, dy, lddy, db, s);
+  return B200RL_OK;
+}
+int simt_conv_fwd(const void* x, int x_u8, const float* w, const float* bias, float* y, const b200rl_conv_geom& g,
+                  int act, void* ws, int64_t wsb, cudaStream_t s) {
+  const int M = g.B * g.OH * g.OW, K = g.kh * g.kw * g.C;
+  Im2colRows a; a.x = x; a.u8 = x_u8; a.g = g; a.Mtot = M; a.Ktot = K;
+  DenseRed b{w, K, g.Cout, K};
+  Epilogue e{y, g.Cout, bias, act, nullptr, 0, 0, nullptr};
+  return launch_gemm(a, b, e, M, g.Cout, K, ws, wsb, s);
+}
+int simt_conv_wgrad(const void* x, int x_u8, const float* dy, float* dw, float* db, const b200rl_conv_geom& g,
+                    void* ws, int64_t wsb, cudaStream_t s) {
+  const int M = g.B * g.OH * g.OW, K = g.kh * g.kw * g.C;
+  DenseOuter a{dy, g.Cout, g.Cout, M};                 // (outer = co, red = m)
+  Im2colCols b; b.x = x; b.u8 = x_u8; b.g = g; b.Mtot = M; b.Ktot = K;
+  Epilogue e{dw, K, nullptr, 0, nullptr, 0, 0, nullptr};
+  int rc = launch_gemm(a, b, e, g.Cout, K, M, ws, wsb, s);
+  if (rc) return rc;
+  if (db) return launch_colsum(M, g.Cout, dy, g.Cout, db, s);
+  return B200RL_OK;
+}
+int simt_conv_dgrad(const float* dy, const float* w, float* dx, const b200rl_conv_geom& g, const float* mask,
+                    int mask_act, void* ws, int64_t wsb, cudaStream_t s) {
+  const int Min = g.B * g.H * g.W, R = g.kh * g.kw * g.Cout;
+  DgradRows a{dy, g, Min, R};
+  DgradWeights b{w, g, R};
+  Epilogue e{dx, g.C, nullptr, 0, mask, g.C, mask_act, nullptr};
+  return launch_gemm(a, b, e, Min, g.C, R, ws, wsb, s);
+}
+
+}  // namespace b200rl

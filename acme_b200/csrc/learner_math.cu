@@ -1,0 +1,654 @@
+// K4 (double-Q TD / Huber / importance weights / priorities), K5 (C51 projection + cross-entropy),
+// K7 (Adam, global-norm clip, target copy) and the small element-wise pieces of the networks.
+// Each kernel cites the reference lines it restates; all are HBM-bound and deterministic
+// (fixed-order reductions, no atomics).
+#include "common.cuh"
+
+#include <cuda_bf16.h>
+
+namespace b200rl {
+
+// ------------------------------------------------------------------------------ Philox4x32-10
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+
+__global__ void uniform_kernel(float* __restrict__ out, int n, unsigned long long seed,
+                               const long long* __restrict__ step_dev, long long step_offset) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long step = (unsigned long long)((step_dev ? *step_dev : 0) + step_offset);
+  uint32_t c[4] = {(uint32_t)i, 0u, (uint32_t)step, (uint32_t)(step >> 32)};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[i] = (float)(c[0] >> 8) * (1.0f / 16777216.0f);  // 24 bits -> [0,1), exact in fp32
+}
+
+// ------------------------------------------------------------------------------ block reductions
+template <typename T, typename Op>
+__device__ __forceinline__ T block_reduce(T v, Op op, T identity, T* scratch /* >= 32 */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, d));
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  v = (threadIdx.x < nw) ? scratch[threadIdx.x] : identity;
+  if (warp == 0) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, d));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) scratch[0] = v;
+  __syncthreads();
+  v = scratch[0];
+  return v;
+}
+
+struct MaxD { __device__ double operator()(double a, double b) const { return a > b ? a : b; } };
+struct SumF { __device__ float operator()(float a, float b) const { return a + b; } };
+struct MaxF { __device__ float operator()(float a, float c) const { return fmaxf(a, c); } };
+struct SumD { __device__ double operator()(double a, double b) const { return a + b; } };
+
+// ------------------------------------------------------------------------------------------ K4
+// acme/agents/tf/dqn/learning.py:127-154; trfl.double_qlearning; acme/tf/losses/huber.py:48-57.
+__global__ void __launch_bounds__(1024)
+is_weight_max_kernel(int B, const float* __restrict__ prob, double beta, double* __restrict__ out) {
+  __shared__ double scratch[32];
+  double m = 0.0;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) m = fmax(m, pow(1.0 / (double)prob[b], beta));
+  m = block_reduce(m, MaxD(), 0.0, scratch);
+  if (threadIdx.x == 0) *out = m;
+}
+
+__global__ void __launch_bounds__(1024)
+dqn_td_kernel(int B, int A, const float* __restrict__ q_tm1, const float* __restrict__ q_tv,
+              const float* __restrict__ q_ts, const int* __restrict__ a_tm1,
+              const float* __restrict__ R, const float* __restrict__ D, const float* __restrict__ prob,
+              float gamma, float delta, double beta, float max_abs_r, const double* __restrict__ wmax_dev,
+              float grad_scale, float* __restrict__ td_out, float* __restrict__ loss_ps,
+              float* __restrict__ weight, float* __restrict__ priority, float* __restrict__ dq,
+              float* __restrict__ loss_mean) {
+  __shared__ double scratch_d[32];
+  __shared__ float scratch_f[32];
+  double wmax = 0.0;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) wmax = fmax(wmax, pow(1.0 / (double)prob[b], beta));
+  if (wmax_dev) wmax = *wmax_dev;                          // global max (data-parallel learners)
+  else wmax = block_reduce(wmax, MaxD(), 0.0, scratch_d);  // tf.reduce_max, learning.py:140
+  float lsum = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float* sel = q_ts + (size_t)b * A;
+    int best = 0;
+    float bv = sel[0];
+    for (int a = 1; a < A; ++a) {
+      float v = sel[a];
+      if (v > bv) { bv = v; best = a; }   // first maximum wins
+    }
+    float r = fminf(fmaxf(R[b], -max_abs_r), max_abs_r);          // learning.py:129
+    float d = __fmul_rn(D[b], gamma);                             // learning.py:130
+    float target = __fadd_rn(r, __fmul_rn(d, q_tv[(size_t)b * A + best]));
+    const int act = a_tm1[b];
+    float td = __fsub_rn(target, q_tm1[(size_t)b * A + act]);
+    float absx = fabsf(td);
+    float quad = fminf(absx, delta);
+    float lin = __fsub_rn(absx, quad);
+    float hub = __fadd_rn(__fmul_rn(__fmul_rn(0.5f, quad), quad), __fmul_rn(delta, lin));
+    float w = (float)(pow(1.0 / (double)prob[b], beta) / wmax);   // f64 then cast, learning.py:138-143
+    float l = __fmul_rn(hub, w);
+    td_out[b] = td;
+    loss_ps[b] = l;
+    weight[b] = w;
+    priority[b] = absx;                                           // learning.py:152 (no epsilon)
+    float g = -(w * grad_scale) * fminf(fmaxf(td, -delta), delta);
+    for (int a = 0; a < A; ++a) dq[(size_t)b * A + a] = (a == act) ? g : 0.f;
+    lsum += l;
+  }
+  lsum = block_reduce(lsum, SumF(), 0.f, scratch_f);
+  if (threadIdx.x == 0 && loss_mean) *loss_mean = lsum / (float)B;
+}
+
+// ------------------------------------------------------------------------------------------ K5
+// acme/tf/losses/distributional.py:22-83.  One CTA per sample; thread i owns atom i and evaluates
+// the dense projection row sum_j clip(1 - |clip(z'_j) - z_i| / delta_i, 0, 1) * p_j with p, z' in
+// shared memory -- the reference's arithmetic without materialising [B,K,K].
+__device__ __forceinline__ float atom_value(int i, int K, float vmin, float vmax) {
+  if (i == K - 1) return vmax;
+  double step = ((double)vmax - (double)vmin) / (double)(K - 1);
+  return (float)((double)vmin + (double)i * step);   // np.linspace(..., dtype=float32)
+}
+
+__global__ void c51_loss_kernel(int K, float vmin, float vmax, const float* __restrict__ logits_tm1,
+                                const float* __restrict__ logits_t, const float* __restrict__ R,
+                                const float* __restrict__ D, float gamma, float grad_scale,
+                                float* __restrict__ target_out, float* __restrict__ loss_ps,
+                                float* __restrict__ dlogits) {
+  extern __shared__ float sm[];
+  float* p = sm;          // softmax(logits_t)          [K]
+  float* zc = sm + K;     // clip(R + Dg * z_j)         [K]
+  float* zq = sm + 2 * K; // support                    [K]
+  __shared__ float scratch[32];
+  const int b = blockIdx.x, i = threadIdx.x;
+  const bool on = i < K;
+  const float lt = on ? logits_t[(size_t)b * K + i] : -INFINITY;
+  float mx = block_reduce(lt, MaxF(), -INFINITY, scratch);
+  float e = on ? expf(lt - mx) : 0.f;
+  float se = block_reduce(e, SumF(), 0.f, scratch);
+  const float zi = on ? atom_value(i, K, vmin, vmax) : 0.f;
+  if (on) {
+    p[i] = e / se;
+    float dg = __fmul_rn(gamma, D[b]);                            // discount * d_t, learning.py:202
+    float z = __fadd_rn(R[b], __fmul_rn(dg, zi));                 // distributional.py:27
+    zc[i] = fminf(fmaxf(z, vmin), vmax);
+    zq[i] = zi;
+  }
+  __syncthreads();
+  float tgt = 0.f;
+  if (on) {
+    // distributional.py:66-76: d_pos = z_{i+1}-z_i (vmin-z_i at the top), d_neg = z_i-z_{i-1} (z_0-vmax at 0)
+    const float d_pos = (i + 1 < K ? zq[i + 1] : vmin) - zi;
+    const float d_neg = zi - (i > 0 ? zq[i - 1] : vmax);
+    for (int j = 0; j < K; ++j) {
+      float delta = zc[j] - zi;
+      float dh = (delta >= 0.f) ? (delta / d_pos) : -(delta / d_neg);
+      float wgt = fminf(fmaxf(1.f - dh, 0.f), 1.f);
+      tgt = __fadd_rn(tgt, __fmul_rn(wgt, p[j]));
+    }
+    if (target_out) target_out[(size_t)b * K + i] = tgt;
+  }
+  // softmax cross-entropy of logits_tm1 against the (stop-gradient) target
+  const float l1 = on ? logits_tm1[(size_t)b * K + i] : -INFINITY;
+  float m1 = block_reduce(l1, MaxF(), -INFINITY, scratch);
+  float e1 = on ? expf(l1 - m1) : 0.f;
+  float s1 = block_reduce(e1, SumF(), 0.f, scratch);
+  float lse = m1 + logf(s1);
+  float contrib = on ? -tgt * (l1 - lse) : 0.f;
+  float loss = block_reduce(contrib, SumF(), 0.f, scratch);
+  float tsum = block_reduce(tgt, SumF(), 0.f, scratch);
+  if (on && dlogits) dlogits[(size_t)b * K + i] = ((e1 / s1) * tsum - tgt) * grad_scale;
+  if (i == 0 && loss_ps) loss_ps[b] = loss;
+}
+
+__global__ void __launch_bounds__(1024) mean_kernel(const float* __restrict__ x, int n, float* __restrict__ out) {
+  __shared__ float scratch[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
+  s = block_reduce(s, SumF(), 0.f, scratch);
+  if (threadIdx.x == 0) *out = s / (float)n;
+}
+
+// distributions.py:64-66: q = sum_i softmax(l)_i z_i ; warp per row
+__global__ void c51_mean_kernel(int B, int K, float vmin, float vmax, const float* __restrict__ logits,
+                                const float* __restrict__ dq, float* __restrict__ q, float* __restrict__ dlogits) {
+  const int lane = threadIdx.x & 31;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= B) return;
+  const float* l = logits + (size_t)b * K;
+  float mx = -INFINITY;
+  for (int i = lane; i < K; i += 32) mx = fmaxf(mx, l[i]);
+  for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+  float se = 0.f, sz = 0.f;
+  for (int i = lane; i < K; i += 32) {
+    float e = expf(l[i] - mx);
+    se += e;
+    sz += e * atom_value(i, K, vmin, vmax);
+  }
+  for (int d = 16; d > 0; d >>= 1) {
+    se += __shfl_xor_sync(0xffffffffu, se, d);
+    sz += __shfl_xor_sync(0xffffffffu, sz, d);
+  }
+  const float mean = sz / se;
+  if (q && lane == 0) q[b] = mean;
+  if (dlogits) {
+    const float g = dq ? dq[b] : 1.f;
+    for (int i = lane; i < K; i += 32)
+      dlogits[(size_t)b * K + i] = (expf(l[i] - mx) / se) * (atom_value(i, K, vmin, vmax) - mean) * g;
+  }
+}
+
+// acme/tf/losses/dpg.py:41-57 (tf.clip_by_norm: t * clip / max(||t||, clip)); warp per row
+__global__ void dpg_kernel(int B, int A, const float* __restrict__ dqda, float clip, int clip_norm,
+                           float grad_scale, float* __restrict__ da, float* __restrict__ loss_ps) {
+  const int lane = threadIdx.x & 31;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= B) return;
+  const float* g = dqda + (size_t)b * A;
+  float ss = 0.f;
+  for (int i = lane; i < A; i += 32) ss += g[i] * g[i];
+  for (int d = 16; d > 0; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
+  const float nrm = sqrtf(ss);
+  float l = 0.f;
+  for (int i = lane; i < A; i += 32) {
+    float v = g[i];
+    if (clip > 0.f) v = clip_norm ? (v * clip) / fmaxf(nrm, clip) : fminf(fmaxf(v, -clip), clip);
+    da[(size_t)b * A + i] = -v * grad_scale;
+    l += v * v;
+  }
+  for (int d = 16; d > 0; d >>= 1) l += __shfl_xor_sync(0xffffffffu, l, d);
+  if (lane == 0 && loss_ps) loss_ps[b] = 0.5f * l;
+}
+
+// ------------------------------------------------------------------------------------------ K7
+// snt.optimizers.Adam.apply as recalled in SURVEY App. A.5 (source not in the reference tree).
+__global__ void __launch_bounds__(256)
+adam_kernel(long long n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+            float* __restrict__ v, const long long* __restrict__ step_dev, float lr, double b1,
+            double b2, float eps, int eps_mode, const float* __restrict__ gscale_dev,
+            __nv_bfloat16* __restrict__ shadow) {
+  const double t = (double)(*step_dev + 1);
+  const float bc1 = (float)(1.0 - pow(b1, t)), bc2 = (float)(1.0 - pow(b2, t));
+  const float b1f = (float)b1, b2f = (float)b2, omb1 = (float)(1.0 - b1), omb2 = (float)(1.0 - b2);
+  const float gs = gscale_dev ? *gscale_dev : 1.f;
+  const float k1 = sqrtf(bc2) / bc1;
+  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  for (; i < n; i += stride) {
+    float pv[4], gv[4], mv[4], vv[4];
+    const int cnt = (n - i >= 4) ? 4 : (int)(n - i);
+    if (cnt == 4) {
+      *reinterpret_cast<float4*>(pv) = *reinterpret_cast<const float4*>(p + i);
+      *reinterpret_cast<float4*>(gv) = __ldg(reinterpret_cast<const float4*>(g + i));
+      *reinterpret_cast<float4*>(mv) = *reinterpret_cast<const float4*>(m + i);
+      *reinterpret_cast<float4*>(vv) = *reinterpret_cast<const float4*>(v + i);
+    } else {
+      for (int j = 0; j < cnt; ++j) { pv[j] = p[i + j]; gv[j] = g[i + j]; mv[j] = m[i + j]; vv[j] = v[i + j]; }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float gj = gs == 1.f ? gv[j] : __fmul_rn(gv[j], gs);
+      mv[j] = __fadd_rn(__fmul_rn(b1f, mv[j]), __fmul_rn(omb1, gj));
+      vv[j] = __fadd_rn(__fmul_rn(b2f, vv[j]), __fmul_rn(omb2, __fmul_rn(gj, gj)));
+      float upd;
+      if (eps_mode == 0) upd = __fdiv_rn(__fdiv_rn(mv[j], bc1), __fadd_rn(__fsqrt_rn(__fdiv_rn(vv[j], bc2)), eps));
+      else upd = __fdiv_rn(__fmul_rn(k1, mv[j]), __fadd_rn(__fsqrt_rn(vv[j]), eps));
+      pv[j] = __fsub_rn(pv[j], __fmul_rn(lr, upd));
+    }
+    if (cnt == 4) {
+      *reinterpret_cast<float4*>(p + i) = *reinterpret_cast<float4*>(pv);
+      *reinterpret_cast<float4*>(m + i) = *reinterpret_cast<float4*>(mv);
+      *reinterpret_cast<float4*>(v + i) = *reinterpret_cast<float4*>(vv);
+      if (shadow) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(pv[0], pv[1]), hi = __floats2bfloat162_rn(pv[2], pv[3]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(shadow + i) = pk;
+      }
+    } else {
+      for (int j = 0; j < cnt; ++j) {
+        p[i + j] = pv[j]; m[i + j] = mv[j]; v[i + j] = vv[j];
+        if (shadow) shadow[i + j] = __float2bfloat16_rn(pv[j]);
+      }
+    }
+  }
+}
+
+// tf.clip_by_global_norm (acme/agents/tf/d4pg/learning.py:235-237), two fixed-order stages
+__global__ void __launch_bounds__(256) sumsq_partial_kernel(long long n, const float* __restrict__ g, float* __restrict__ partial) {
+  __shared__ double scratch[32];
+  double s = 0.0;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) { double x = g[i]; s += x * x; }
+  s = block_reduce(s, SumD(), 0.0, scratch);
+  if (threadIdx.x == 0) partial[blockIdx.x] = (float)s;
+}
+__global__ void __launch_bounds__(256) norm_finish_kernel(int nparts, const float* __restrict__ partial, float clip,
+                                                         float* __restrict__ scale_out, float* __restrict__ norm_out) {
+  __shared__ double scratch[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += (double)partial[i];
+  s = block_reduce(s, SumD(), 0.0, scratch);
+  if (threadIdx.x == 0) {
+    float nrm = (float)sqrt(s);
+    if (norm_out) *norm_out = nrm;
+    *scale_out = clip / fmaxf(nrm, clip);
+  }
+}
+
+__global__ void copy_if_period_kernel(long long n16, int4* __restrict__ dst, const int4* __restrict__ src,
+                                      const long long* __restrict__ step_dev, long long period, long long phase) {
+  if (((*step_dev) + phase) % period != 0) return;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n16; i += stride) dst[i] = __ldg(src + i);
+}
+__global__ void step_increment_kernel(long long* step) { *step += 1; }
+
+// ------------------------------------------------------------------------------ element-wise
+__device__ __forceinline__ float act_grad_from_output(float y, int act) {
+  switch (act) {
+    case B200RL_ACT_RELU: return y > 0.f ? 1.f : 0.f;
+    case B200RL_ACT_ELU: return y > 0.f ? 1.f : y + 1.f;
+    case B200RL_ACT_TANH: return 1.f - y * y;
+    default: return 1.f;
+  }
+}
+__global__ void act_bwd_kernel(long long n, float* __restrict__ dy, const float* __restrict__ y, int act) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dy[i] *= act_grad_from_output(y[i], act);
+}
+
+// acme/tf/networks/duelling.py:51-59
+__global__ void duelling_fwd_kernel(int B, int A, const float* __restrict__ value, const float* __restrict__ adv, float* __restrict__ q) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float s = 0.f;
+  for (int a = 0; a < A; ++a) s += adv[(size_t)b * A + a];
+  const float mean = s / (float)A, v = value[b];
+  for (int a = 0; a < A; ++a) q[(size_t)b * A + a] = v + (adv[(size_t)b * A + a] - mean);
+}
+__global__ void duelling_bwd_kernel(int B, int A, const float* __restrict__ dq, float* __restrict__ dvalue, float* __restrict__ dadv) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float s = 0.f;
+  for (int a = 0; a < A; ++a) s += dq[(size_t)b * A + a];
+  dvalue[b] = s;
+  const float mean = s / (float)A;
+  for (int a = 0; a < A; ++a) dadv[(size_t)b * A + a] = dq[(size_t)b * A + a] - mean;
+}
+
+// snt.LayerNorm(axis=slice(1,None), scale, offset) + tanh (acme/tf/networks/continuous.py:55-58); CTA per row
+__global__ void __launch_bounds__(256)
+layernorm_tanh_fwd_kernel(int N, const float* __restrict__ x, const float* __restrict__ scale,
+                          const float* __restrict__ offset, float eps, float* __restrict__ y,
+                          float* __restrict__ xhat, float* __restrict__ rstd) {
+  __shared__ float scratch[32];
+  const int b = blockIdx.x;
+  const float* xr = x + (size_t)b * N;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) s += xr[i];
+  const float mean = block_reduce(s, SumF(), 0.f, scratch) / (float)N;
+  float vs = 0.f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) { float d = xr[i] - mean; vs += d * d; }
+  const float var = block_reduce(vs, SumF(), 0.f, scratch) / (float)N;
+  const float rs = rsqrtf(var + eps);
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    float xh = (xr[i] - mean) * rs;
+    xhat[(size_t)b * N + i] = xh;
+    y[(size_t)b * N + i] = tanhf(xh * scale[i] + offset[i]);
+  }
+  if (threadIdx.x == 0) rstd[b] = rs;
+}
+__global__ void __launch_bounds__(256)
+layernorm_tanh_bwd_kernel(int N, const float* __restrict__ dy, const float* __restrict__ y,
+                          const float* __restrict__ xhat, const float* __restrict__ rstd,
+                          const float* __restrict__ scale, float* __restrict__ dx) {
+  __shared__ float scratch[32];
+  const int b = blockIdx.x;
+  const size_t o = (size_t)b * N;
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    float dz = dy[o + i] * (1.f - y[o + i] * y[o + i]);
+    float dxh = dz * scale[i];
+    s1 += dxh;
+    s2 += dxh * xhat[o + i];
+  }
+  const float m1 = block_reduce(s1, SumF(), 0.f, scratch) / (float)N;
+  const float m2 = block_reduce(s2, SumF(), 0.f, scratch) / (float)N;
+  const float rs = rstd[b];
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    float dz = dy[o + i] * (1.f - y[o + i] * y[o + i]);
+    float dxh = dz * scale[i];
+    dx[o + i] = rs * (dxh - m1 - xhat[o + i] * m2);
+  }
+}
+__global__ void layernorm_param_grad_kernel(int B, int N, const float* __restrict__ dy, const float* __restrict__ y,
+                                            const float* __restrict__ xhat, float* __restrict__ dscale, float* __restrict__ doffset) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  float ds = 0.f, dof = 0.f;
+  for (int b = 0; b < B; ++b) {
+    size_t o = (size_t)b * N + i;
+    float dz = dy[o] * (1.f - y[o] * y[o]);
+    ds += dz * xhat[o];
+    dof += dz;
+  }
+  dscale[i] = ds;
+  doffset[i] = dof;
+}
+
+// acme/tf/networks/rescaling.py:63-74
+__global__ void tanh_to_spec_fwd_kernel(long long n, int A, const float* __restrict__ x, const float* __restrict__ scale,
+                                        const float* __restrict__ offset, float* __restrict__ a) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int c = (int)(i % A);
+  float t = tanhf(x[i]);
+  t = 0.5f * (t + 1.0f);
+  a[i] = t * scale[c] + offset[c];
+}
+__global__ void tanh_to_spec_bwd_kernel(long long n, int A, const float* __restrict__ da, const float* __restrict__ x,
+                                        const float* __restrict__ scale, float* __restrict__ dx) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int c = (int)(i % A);
+  float t = tanhf(x[i]);
+  dx[i] = da[i] * 0.5f * scale[c] * (1.f - t * t);
+}
+
+// acme/tf/utils.py:39-54 batch_concat of two flat tensors, and the slice of its gradient
+__global__ void concat2_kernel(int B, int n0, int n1, const float* __restrict__ x0, const float* __restrict__ x1, float* __restrict__ y) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = n0 + n1;
+  if (i >= (long long)B * n) return;
+  int b = (int)(i / n), c = (int)(i % n);
+  y[i] = c < n0 ? x0[(size_t)b * n0 + c] : x1[(size_t)b * n1 + (c - n0)];
+}
+__global__ void split_second_kernel(int B, int n0, int n1, const float* __restrict__ dy, float* __restrict__ dx1) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * n1) return;
+  int b = (int)(i / n1), c = (int)(i % n1);
+  dx1[i] = dy[(size_t)b * (n0 + n1) + n0 + c];
+}
+
+}  // namespace b200rl
+
+using namespace b200rl;
+
+static inline int grid1d(long long n, int threads, int cap = kNumSMs * 16) {
+  long long b = (n + threads - 1) / threads;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+extern "C" int b200rl_uniform(float* out, int32_t n, uint64_t seed, const int64_t* step_dev,
+                              int64_t step_offset, void* stream) {
+  B200RL_REQUIRE(out && n >= 0, "bad argument");
+  if (n == 0) return B200RL_OK;
+  uniform_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(out, n, seed, (const long long*)step_dev, step_offset);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_is_weight_max(int32_t B, const float* prob, double beta, double* out, void* stream) {
+  B200RL_REQUIRE(prob && out && B >= 1, "bad argument");
+  is_weight_max_kernel<<<1, B >= 1024 ? 1024 : ((B + 31) / 32) * 32, 0, as_stream(stream)>>>(B, prob, beta, out);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_dqn_td(int32_t B, int32_t A, const float* q_tm1, const float* q_tv, const float* q_ts,
+                             const int32_t* a_tm1, const float* R, const float* D, const float* prob,
+                             float gamma, float delta, double beta, float max_abs_reward,
+                             const double* wmax_dev, float grad_scale, float* td, float* loss_ps,
+                             float* weight, float* priority, float* dq, float* loss_mean, void* stream) {
+  B200RL_REQUIRE(q_tm1 && q_tv && q_ts && a_tm1 && R && D && prob && td && loss_ps && weight && priority && dq,
+                 "null argument");
+  B200RL_REQUIRE(B >= 1 && A >= 1, "bad shape");
+  B200RL_REQUIRE(delta >= 0.f, "quadratic_linear_boundary must be >= 0");  // huber.py:45-46
+  int threads = B >= 1024 ? 1024 : ((B + 31) / 32) * 32;
+  dqn_td_kernel<<<1, threads, 0, as_stream(stream)>>>(B, A, q_tm1, q_tv, q_ts, a_tm1, R, D, prob, gamma, delta, beta,
+                                                     max_abs_reward, wmax_dev, grad_scale, td, loss_ps, weight,
+                                                     priority, dq, loss_mean);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_c51_loss(int32_t B, int32_t K, float vmin, float vmax, const float* logits_tm1,
+                               const float* logits_t, const float* R, const float* D, float gamma,
+                               float grad_scale, float* target, float* loss_ps, float* dlogits,
+                               float* loss_mean, void* stream) {
+  B200RL_REQUIRE(logits_tm1 && logits_t && R && D && loss_ps, "null argument");
+  B200RL_REQUIRE(B >= 1 && K >= 2 && K <= 1024, "bad shape");
+  int threads = ((K + 31) / 32) * 32;
+  c51_loss_kernel<<<B, threads, 3 * K * sizeof(float), as_stream(stream)>>>(K, vmin, vmax, logits_tm1, logits_t, R, D, gamma,
+                                                                           grad_scale, target, loss_ps, dlogits);
+  B200RL_LAUNCH_OK();
+  if (loss_mean) {
+    mean_kernel<<<1, 256, 0, as_stream(stream)>>>(loss_ps, B, loss_mean);
+    B200RL_LAUNCH_OK();
+  }
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_c51_mean_fwd(int32_t B, int32_t K, float vmin, float vmax, const float* logits, float* q, void* stream) {
+  B200RL_REQUIRE(logits && q && B >= 1 && K >= 2, "bad argument");
+  c51_mean_kernel<<<ceil_div(B * 32, 128), 128, 0, as_stream(stream)>>>(B, K, vmin, vmax, logits, nullptr, q, nullptr);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+extern "C" int b200rl_c51_mean_bwd(int32_t B, int32_t K, float vmin, float vmax, const float* logits, const float* dq,
+                                   float* dlogits, void* stream) {
+  B200RL_REQUIRE(logits && dlogits && B >= 1 && K >= 2, "bad argument");
+  c51_mean_kernel<<<ceil_div(B * 32, 128), 128, 0, as_stream(stream)>>>(B, K, vmin, vmax, logits, dq, nullptr, dlogits);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_dpg_action_grad(int32_t B, int32_t A, const float* dqda, float clip, int clip_norm,
+                                      float grad_scale, float* da, float* loss_ps, float* loss_mean, void* stream) {
+  B200RL_REQUIRE(dqda && da && B >= 1 && A >= 1, "bad argument");
+  B200RL_REQUIRE(!loss_mean || loss_ps, "loss_mean needs a loss_per_sample buffer");
+  dpg_kernel<<<ceil_div(B * 32, 128), 128, 0, as_stream(stream)>>>(B, A, dqda, clip, clip_norm, grad_scale, da, loss_ps);
+  B200RL_LAUNCH_OK();
+  if (loss_mean) {
+    mean_kernel<<<1, 256, 0, as_stream(stream)>>>(loss_ps, B, loss_mean);
+    B200RL_LAUNCH_OK();
+  }
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_adam(int64_t n, float* param, const float* grad, float* m, float* v, const int64_t* step_dev,
+                           float lr, double b1, double b2, float eps, int eps_mode, const float* grad_scale_dev,
+                           void* bf16_shadow, void* stream) {
+  B200RL_REQUIRE(param && grad && m && v && step_dev, "null argument");
+  B200RL_REQUIRE(n >= 0 && (eps_mode == 0 || eps_mode == 1), "bad argument");
+  B200RL_REQUIRE((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "buffers must be 16-byte aligned");
+  if (n == 0) return B200RL_OK;
+  int blocks = grid1d((n + 3) / 4, 256, kNumSMs * 8);
+  adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(n, param, grad, m, v, (const long long*)step_dev, lr, b1, b2, eps,
+                                                    eps_mode, grad_scale_dev, (__nv_bfloat16*)bf16_shadow);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_global_norm_scale(int64_t n, const float* grad, float clip, float* partial_ws, float* scale_out,
+                                        float* norm_out, void* stream) {
+  B200RL_REQUIRE(grad && partial_ws && scale_out && n >= 1, "bad argument");
+  int blocks = grid1d(n, 256, 1024);
+  sumsq_partial_kernel<<<blocks, 256, 0, as_stream(stream)>>>(n, grad, partial_ws);
+  B200RL_LAUNCH_OK();
+  norm_finish_kernel<<<1, 256, 0, as_stream(stream)>>>(blocks, partial_ws, clip, scale_out, norm_out);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_copy_if_period(int64_t n_bytes, void* dst, const void* src, const int64_t* step_dev, int64_t period,
+                                     int64_t phase, void* stream) {
+  B200RL_REQUIRE(dst && src && step_dev && period >= 1, "bad argument");
+  B200RL_REQUIRE(n_bytes % 16 == 0 && (((uintptr_t)dst | (uintptr_t)src) & 15) == 0, "copy must be 16-byte aligned/sized");
+  copy_if_period_kernel<<<grid1d(n_bytes / 16, 256, kNumSMs * 8), 256, 0, as_stream(stream)>>>(
+      n_bytes / 16, (int4*)dst, (const int4*)src, (const long long*)step_dev, period, phase);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_step_increment(int64_t* step_dev, void* stream) {
+  B200RL_REQUIRE(step_dev, "null argument");
+  step_increment_kernel<<<1, 1, 0, as_stream(stream)>>>((long long*)step_dev);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_act_bwd(int64_t n, float* dy, const float* y, int act, void* stream) {
+  B200RL_REQUIRE(dy && y && n >= 0, "bad argument");
+  if (n == 0 || act == B200RL_ACT_NONE) return B200RL_OK;
+  act_bwd_kernel<<<grid1d(n, 256), 256, 0, as_stream(stream)>>>(n, dy, y, act);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_duelling_fwd(int32_t B, int32_t A, const float* value, const float* adv, float* q, void* stream) {
+  B200RL_REQUIRE(value && adv && q && B >= 1 && A >= 1, "bad argument");
+  duelling_fwd_kernel<<<ceil_div(B, 128), 128, 0, as_stream(stream)>>>(B, A, value, adv, q);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+extern "C" int b200rl_duelling_bwd(int32_t B, int32_t A, const float* dq, float* dvalue, float* dadv, void* stream) {
+  B200RL_REQUIRE(dq && dvalue && dadv && B >= 1 && A >= 1, "bad argument");
+  duelling_bwd_kernel<<<ceil_div(B, 128), 128, 0, as_stream(stream)>>>(B, A, dq, dvalue, dadv);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_layernorm_tanh_fwd(int32_t B, int32_t N, const float* x, const float* scale, const float* offset,
+                                         float eps, float* y, float* xhat, float* rstd, void* stream) {
+  B200RL_REQUIRE(x && scale && offset && y && xhat && rstd && B >= 1 && N >= 1, "bad argument");
+  layernorm_tanh_fwd_kernel<<<B, 256, 0, as_stream(stream)>>>(N, x, scale, offset, eps, y, xhat, rstd);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+extern "C" int b200rl_layernorm_tanh_bwd(int32_t B, int32_t N, const float* dy, const float* y, const float* xhat,
+                                         const float* rstd, const float* scale, float* dx, float* dscale,
+                                         float* doffset, void* stream) {
+  B200RL_REQUIRE(dy && y && xhat && rstd && scale && dx && B >= 1 && N >= 1, "bad argument");
+  layernorm_tanh_bwd_kernel<<<B, 256, 0, as_stream(stream)>>>(N, dy, y, xhat, rstd, scale, dx);
+  B200RL_LAUNCH_OK();
+  if (dscale && doffset) {
+    layernorm_param_grad_kernel<<<ceil_div(N, 128), 128, 0, as_stream(stream)>>>(B, N, dy, y, xhat, dscale, doffset);
+    B200RL_LAUNCH_OK();
+  }
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_tanh_to_spec_fwd(int32_t B, int32_t A, const float* x, const float* scale, const float* offset,
+                                       float* a, void* stream) {
+  B200RL_REQUIRE(x && scale && offset && a && B >= 1 && A >= 1, "bad argument");
+  long long n = (long long)B * A;
+  tanh_to_spec_fwd_kernel<<<(int)ceil_div<long long>(n, 256), 256, 0, as_stream(stream)>>>(n, A, x, scale, offset, a);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+extern "C" int b200rl_tanh_to_spec_bwd(int32_t B, int32_t A, const float* da, const float* x, const float* scale,
+                                       float* dx, void* stream) {
+  B200RL_REQUIRE(da && x && scale && dx && B >= 1 && A >= 1, "bad argument");
+  long long n = (long long)B * A;
+  tanh_to_spec_bwd_kernel<<<(int)ceil_div<long long>(n, 256), 256, 0, as_stream(stream)>>>(n, A, da, x, scale, dx);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_concat2(int32_t B, int32_t n0, int32_t n1, const float* x0, const float* x1, float* y, void* stream) {
+  B200RL_REQUIRE(x0 && x1 && y && B >= 1 && n0 >= 1 && n1 >= 1, "bad argument");
+  long long n = (long long)B * (n0 + n1);
+  concat2_kernel<<<(int)ceil_div<long long>(n, 256), 256, 0, as_stream(stream)>>>(B, n0, n1, x0, x1, y);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+extern "C" int b200rl_split_second(int32_t B, int32_t n0, int32_t n1, const float* dy, float* dx1, void* stream) {
+  B200RL_REQUIRE(dy && dx1 && B >= 1 && n0 >= 1 && n1 >= 1, "bad argument");
+  long long n = (long long)B * n1;
+  split_second_kernel<<<(int)ceil_div<long long>(n, 256), 256, 0, as_stream(stream)>>>(B, n0, n1, dy, dx1);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}

@@ -1,0 +1,799 @@
+// Replay shard runtime: HBM ring of observation slots + ring of items + sum tree, the pinned
+// staging that feeds it, and K3 (gather + n-step build).
+//
+// Stands in for the Reverb table/writer/sampler the reference builds at
+// acme/agents/tf/dqn/agent.py:95-116 and drives from acme/adders/reverb/{base,transition}.py.
+// The host half of this file is the native counterpart of Reverb's C++ table bookkeeping (FIFO
+// remover, key allocation, writer history); the arithmetic lives in the kernels.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <deque>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b200rl {
+
+static thread_local std::string g_last_error;
+
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+}
+
+// from sumtree.cu
+int tree_staged_levels(const TreeView& t, int64_t budget_bytes);
+int tree_sample(const TreeView& t, const ReplayState* st_dev, int64_t M, int B, const float* u,
+                int stratified, int shard_count, int64_t* idx, uint64_t* keys, float* prob,
+                cudaStream_t stream, int* staged_out);
+int tree_rebuild(const TreeView& t, cudaStream_t stream);
+int tree_scatter_positions(const TreeView& t, int64_t M, int n, const int64_t* pos_dev,
+                           const float* w_dev, const ReplayState* st_dev, unsigned long long* stamp,
+                           unsigned long long* epoch_dev, cudaStream_t stream);
+int tree_scatter_keys(const TreeView& t, int64_t M, int n, const uint64_t* keys_dev,
+                      const float* prio_dev, double alpha, const ReplayState* st_dev,
+                      unsigned long long* stamp, unsigned long long* epoch_dev, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------ device side
+struct SlotFill {   // scalars of one finished step, scattered into the slot arrays at flush
+  int32_t slot;
+  int32_t next;
+  float rew;
+  float disc;
+};
+struct ItemRec {    // one new item (len > 0) or a tree-only update (len == 0, e.g. eviction)
+  int64_t pos;
+  int32_t start;
+  int32_t end;
+  int32_t len;
+  float weight;
+};
+
+struct RingView {
+  uint8_t* obs;
+  uint8_t* act;
+  float* rew;
+  float* disc;
+  int32_t* next;
+  int32_t* item_start;
+  int32_t* item_end;
+  int32_t* item_len;
+  int64_t obs_stride;
+  int32_t obs_bytes;
+  int32_t act_stride;
+  int32_t act_bytes;
+  float gamma;
+};
+
+__global__ void scatter_fills_kernel(RingView r, const SlotFill* __restrict__ fills,
+                                     const uint8_t* __restrict__ acts, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  SlotFill f = fills[i];
+  r.rew[f.slot] = f.rew;
+  r.disc[f.slot] = f.disc;
+  r.next[f.slot] = f.next;
+  const uint8_t* src = acts + (size_t)i * r.act_stride;
+  uint8_t* dst = r.act + (size_t)f.slot * r.act_stride;
+  for (int b = 0; b < r.act_bytes; ++b) dst[b] = src[b];
+}
+
+__global__ void scatter_items_kernel(RingView r, const ItemRec* __restrict__ recs, int n,
+                                     long long* __restrict__ pos_out, float* __restrict__ w_out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ItemRec it = recs[i];
+  if (it.len > 0) {
+    r.item_start[it.pos] = it.start;
+    r.item_end[it.pos] = it.end;
+    r.item_len[it.pos] = it.len;
+  }
+  pos_out[i] = it.pos;
+  w_out[i] = it.weight;
+}
+
+// K3.  grid = (B, 2): y = 0 copies o_tm1 (+ action, n-step R/D by thread 0), y = 1 copies o_t.
+// Observation rows are moved with 16-byte vectors (ring rows are 16-byte aligned; batch rows are
+// when obs_bytes % 16 == 0, otherwise the 4-byte or byte path is taken).
+template <int VEC>
+__global__ void __launch_bounds__(256)
+gather_kernel(RingView r, const long long* __restrict__ idx, uint8_t* __restrict__ o_tm1,
+              uint8_t* __restrict__ a_tm1, float* __restrict__ R, float* __restrict__ D,
+              uint8_t* __restrict__ o_t) {
+  const int b = blockIdx.x;
+  const long long pos = idx[b];
+  const int which = blockIdx.y;
+  const int slot = which == 0 ? r.item_start[pos] : r.item_end[pos];
+  const uint8_t* src = r.obs + (size_t)slot * r.obs_stride;
+  uint8_t* dst = (which == 0 ? o_tm1 : o_t) + (size_t)b * r.obs_bytes;
+  if (VEC == 16) {
+    const int4* s4 = reinterpret_cast<const int4*>(src);
+    int4* d4 = reinterpret_cast<int4*>(dst);
+    const int nv = r.obs_bytes >> 4;
+    // 4 independent 16-byte loads in flight per thread before the stores
+    int i = threadIdx.x;
+    for (; i + 3 * 256 < nv; i += 4 * 256) {
+      int4 v0 = __ldg(s4 + i), v1 = __ldg(s4 + i + 256), v2 = __ldg(s4 + i + 512), v3 = __ldg(s4 + i + 768);
+      d4[i] = v0; d4[i + 256] = v1; d4[i + 512] = v2; d4[i + 768] = v3;
+    }
+    for (; i < nv; i += 256) d4[i] = __ldg(s4 + i);
+  } else if (VEC == 4) {
+    const int* s1 = reinterpret_cast<const int*>(src);
+    int* d1 = reinterpret_cast<int*>(dst);
+    for (int i = threadIdx.x; i < (r.obs_bytes >> 2); i += 256) d1[i] = __ldg(s1 + i);
+  } else {
+    for (int i = threadIdx.x; i < r.obs_bytes; i += 256) dst[i] = src[i];
+  }
+  if (which == 0) {
+    const uint8_t* as = r.act + (size_t)slot * r.act_stride;
+    uint8_t* ad = a_tm1 + (size_t)b * r.act_bytes;
+    for (int i = threadIdx.x; i < r.act_bytes; i += 256) ad[i] = as[i];
+    if (threadIdx.x == 0) {
+      // acme/adders/reverb/transition.py:135-145, fp32, every op rounded separately (no FMA)
+      int cur = slot;
+      const int len = r.item_len[pos];
+      float Rv = r.rew[cur], Dv = r.disc[cur];
+      cur = r.next[cur];
+      for (int j = 1; j < len; ++j) {
+        Dv = __fmul_rn(Dv, r.gamma);
+        Rv = __fadd_rn(Rv, __fmul_rn(r.rew[cur], Dv));
+        Dv = __fmul_rn(Dv, r.disc[cur]);
+        cur = r.next[cur];
+      }
+      R[b] = Rv;
+      D[b] = Dv;
+    }
+  }
+}
+
+__global__ void fill_float_kernel(float* p, long long n, float v) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = v;
+}
+
+}  // namespace b200rl
+
+// ------------------------------------------------------------------------------ host side
+using namespace b200rl;
+
+struct Writer {
+  std::deque<uint64_t> hist;  // slot seqs of this episode, newest (the open slot) last
+  bool in_use = false;
+  int64_t k = 0;              // steps appended in the current episode
+  bool has_pending = false;   // stream form: act/rew/disc of the open slot wait for the next obs
+  std::vector<uint8_t> pending_act;
+  float pending_rew = 0.f, pending_disc = 0.f;
+};
+
+struct Stage {   // one pinned staging set + its device mirror; two sets alternate
+  uint8_t* h_obs = nullptr;
+  SlotFill* h_fill = nullptr;
+  uint8_t* h_act = nullptr;
+  ItemRec* h_item = nullptr;
+  ReplayState* h_state = nullptr;
+  SlotFill* d_fill = nullptr;
+  uint8_t* d_act = nullptr;
+  ItemRec* d_item = nullptr;
+  long long* d_pos = nullptr;
+  float* d_w = nullptr;
+  cudaEvent_t done = nullptr;
+  bool in_flight = false;
+};
+
+struct b200rl_replay {
+  b200rl_replay_cfg cfg;
+  int64_t M = 0, S = 0;
+  int64_t obs_stride = 0;
+  int32_t act_stride = 0;
+  RingView ring{};
+  float* d_tree = nullptr;
+  TreeView tree{};
+  unsigned long long* d_stamp = nullptr;
+  unsigned long long* d_epoch = nullptr;
+  ReplayState* d_state = nullptr;
+  int staged_levels = 0;
+
+  uint64_t slot_head = 0, item_head = 0, item_tail = 0;
+  std::vector<uint64_t> item_start_seq;
+  std::vector<Writer> writers;
+
+  Stage stage[2];
+  int cur = 0;
+  int64_t stage_slots = 0, stage_items = 0;
+  int64_t n_obs = 0, n_fill = 0, n_item = 0;
+  uint64_t obs_first_seq = 0;
+  bool state_dirty = false;
+  cudaStream_t last_flush_stream = nullptr;  // flushes on different streams are chained by event
+  cudaEvent_t last_flush_event = nullptr;
+};
+
+static int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+static int ensure_device(b200rl_replay* h) {
+  B200RL_CUDA_OK(cudaSetDevice(h->cfg.device));
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_version(void) { return B200RL_VERSION; }
+extern "C" const char* b200rl_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int b200rl_device_check(int device) {
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) {
+    set_error("no usable CUDA device %d: %s (this library has no CPU fallback)", device,
+              cudaGetErrorString(e));
+    return B200RL_ECUDA;
+  }
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+              prop.major, prop.minor);
+    return B200RL_EARCH;
+  }
+  return B200RL_OK;
+}
+
+static void free_stage(Stage& s) {
+  cudaFreeHost(s.h_obs); cudaFreeHost(s.h_fill); cudaFreeHost(s.h_act); cudaFreeHost(s.h_item);
+  cudaFreeHost(s.h_state);
+  cudaFree(s.d_fill); cudaFree(s.d_act); cudaFree(s.d_item); cudaFree(s.d_pos); cudaFree(s.d_w);
+  if (s.done) cudaEventDestroy(s.done);
+  s = Stage{};
+}
+
+extern "C" int b200rl_replay_destroy(b200rl_replay* h) {
+  if (!h) return B200RL_OK;
+  cudaSetDevice(h->cfg.device);
+  cudaFree(h->ring.obs); cudaFree(h->ring.act); cudaFree(h->ring.rew); cudaFree(h->ring.disc);
+  cudaFree(h->ring.next); cudaFree(h->ring.item_start); cudaFree(h->ring.item_end);
+  cudaFree(h->ring.item_len); cudaFree(h->d_tree); cudaFree(h->d_stamp); cudaFree(h->d_epoch);
+  cudaFree(h->d_state);
+  free_stage(h->stage[0]);
+  free_stage(h->stage[1]);
+  delete h;
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_replay_create(b200rl_replay** out, const b200rl_replay_cfg* cfg) {
+  B200RL_REQUIRE(out && cfg, "null argument");
+  B200RL_REQUIRE(cfg->max_items >= 1 && cfg->max_items < (1ll << 31), "max_items out of range");
+  B200RL_REQUIRE(cfg->obs_bytes >= 0 && cfg->act_bytes >= 0, "negative payload size");
+  B200RL_REQUIRE(cfg->max_window >= 1 && cfg->max_window <= 64, "max_window must be in [1,64]");
+  B200RL_REQUIRE(cfg->shard_count >= 1, "shard_count must be >= 1");
+  const bool payload = cfg->obs_bytes > 0;
+  B200RL_REQUIRE(!payload || (cfg->slot_capacity >= cfg->max_window + 2 && cfg->slot_capacity < (1ll << 31)),
+                 "slot_capacity must be >= max_window + 2");
+  int rc = b200rl_device_check(cfg->device);
+  if (rc) return rc;
+  B200RL_CUDA_OK(cudaSetDevice(cfg->device));
+
+  b200rl_replay* h = new b200rl_replay();
+  h->cfg = *cfg;
+  h->M = cfg->max_items;
+  h->S = payload ? cfg->slot_capacity : 0;
+  h->obs_stride = round_up(cfg->obs_bytes, 16);
+  h->act_stride = (int32_t)round_up(std::max(cfg->act_bytes, 1), 4);
+  RingView& r = h->ring;
+  r.obs_stride = h->obs_stride;
+  r.obs_bytes = cfg->obs_bytes;
+  r.act_stride = h->act_stride;
+  r.act_bytes = cfg->act_bytes;
+  r.gamma = cfg->gamma;
+
+#define ALLOC(ptr, bytes)                                                        \
+  do {                                                                           \
+    cudaError_t _e = cudaMalloc((void**)&(ptr), (size_t)std::max<int64_t>((bytes), 16)); \
+    if (_e != cudaSuccess) {                                                     \
+      set_error("cudaMalloc(%lld bytes) failed: %s", (long long)(bytes), cudaGetErrorString(_e)); \
+      b200rl_replay_destroy(h);                                                  \
+      return B200RL_ECUDA;                                                       \
+    }                                                                            \
+  } while (0)
+
+  if (payload) {
+    ALLOC(r.obs, h->S * h->obs_stride);
+    ALLOC(r.act, h->S * (int64_t)h->act_stride);
+    ALLOC(r.rew, h->S * 4);
+    ALLOC(r.disc, h->S * 4);
+    ALLOC(r.next, h->S * 4);
+    ALLOC(r.item_start, h->M * 4);
+    ALLOC(r.item_end, h->M * 4);
+    ALLOC(r.item_len, h->M * 4);
+    cudaMemset(r.next, 0xff, h->S * 4);
+    cudaMemset(r.item_len, 0, h->M * 4);
+  }
+  // tree geometry (oracle/sumtree.py::num_levels / level_width)
+  TreeView& t = h->tree;
+  int L = 1;
+  {
+    int64_t span = kFanout;
+    while (span < h->M) { span *= kFanout; ++L; }
+  }
+  B200RL_REQUIRE(L < kMaxLevels, "tree too deep");
+  t.L = L;
+  int64_t total = 32;  // root padded
+  for (int l = 1; l <= L; ++l) {
+    int64_t span = 1;
+    for (int i = 0; i < L - l; ++i) span *= kFanout;
+    t.width[l] = round_up(ceil_div<int64_t>(h->M, span), kFanout);
+    total += t.width[l];
+  }
+  t.width[0] = 1;
+  ALLOC(h->d_tree, total * 4);
+  cudaMemset(h->d_tree, 0, total * 4);
+  {
+    float* p = h->d_tree;
+    t.lvl[0] = p;
+    p += 32;
+    for (int l = 1; l <= L; ++l) { t.lvl[l] = p; p += t.width[l]; }
+  }
+  ALLOC(h->d_stamp, t.width[L] * 8);
+  cudaMemset(h->d_stamp, 0, t.width[L] * 8);
+  ALLOC(h->d_epoch, 8);
+  {
+    unsigned long long one = 1;
+    cudaMemcpy(h->d_epoch, &one, 8, cudaMemcpyHostToDevice);
+  }
+  ALLOC(h->d_state, sizeof(ReplayState));
+  cudaMemset(h->d_state, 0, sizeof(ReplayState));
+  h->staged_levels = tree_staged_levels(t, 16 * 1024);
+
+  h->stage_slots = cfg->stage_slots > 0 ? cfg->stage_slots : 256;
+  h->stage_items = h->stage_slots * 2 + 2 * cfg->max_window + 8;
+  for (int i = 0; i < 2; ++i) {
+    Stage& s = h->stage[i];
+    bool ok = true;
+    if (payload) {
+      ok = ok && cudaMallocHost((void**)&s.h_obs, (size_t)(h->stage_slots * std::max<int64_t>(cfg->obs_bytes, 1))) == cudaSuccess;
+      ok = ok && cudaMallocHost((void**)&s.h_fill, h->stage_slots * sizeof(SlotFill)) == cudaSuccess;
+      ok = ok && cudaMallocHost((void**)&s.h_act, h->stage_slots * (size_t)h->act_stride) == cudaSuccess;
+      ok = ok && cudaMalloc((void**)&s.d_fill, h->stage_slots * sizeof(SlotFill)) == cudaSuccess;
+      ok = ok && cudaMalloc((void**)&s.d_act, h->stage_slots * (size_t)h->act_stride) == cudaSuccess;
+    }
+    ok = ok && cudaMallocHost((void**)&s.h_item, h->stage_items * sizeof(ItemRec)) == cudaSuccess;
+    ok = ok && cudaMallocHost((void**)&s.h_state, sizeof(ReplayState)) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&s.d_item, h->stage_items * sizeof(ItemRec)) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&s.d_pos, h->stage_items * 8) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&s.d_w, h->stage_items * 4) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+      set_error("staging allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+      b200rl_replay_destroy(h);
+      return B200RL_ECUDA;
+    }
+  }
+#undef ALLOC
+  B200RL_CUDA_OK(cudaDeviceSynchronize());
+  *out = h;
+  return B200RL_OK;
+}
+
+// ----------------------------------------------------------------------------------- flush
+static int flush_impl(b200rl_replay* h, cudaStream_t stream) {
+  if (h->n_obs == 0 && h->n_fill == 0 && h->n_item == 0 && !h->state_dirty) return B200RL_OK;
+  Stage& s = h->stage[h->cur];
+  RingView& r = h->ring;
+  if (h->last_flush_event && h->last_flush_stream != stream)
+    B200RL_CUDA_OK(cudaStreamWaitEvent(stream, h->last_flush_event, 0));
+  if (h->n_obs > 0) {
+    // staged observations occupy consecutive slot sequence numbers -> at most two runs in the ring
+    int64_t first = (int64_t)(h->obs_first_seq % (uint64_t)h->S);
+    int64_t run0 = std::min<int64_t>(h->n_obs, h->S - first);
+    B200RL_CUDA_OK(cudaMemcpy2DAsync(r.obs + first * r.obs_stride, r.obs_stride, s.h_obs, r.obs_bytes,
+                                     r.obs_bytes, run0, cudaMemcpyHostToDevice, stream));
+    if (run0 < h->n_obs)
+      B200RL_CUDA_OK(cudaMemcpy2DAsync(r.obs, r.obs_stride, s.h_obs + run0 * (int64_t)r.obs_bytes,
+                                       r.obs_bytes, r.obs_bytes, h->n_obs - run0,
+                                       cudaMemcpyHostToDevice, stream));
+  }
+  if (h->n_fill > 0) {
+    B200RL_CUDA_OK(cudaMemcpyAsync(s.d_fill, s.h_fill, h->n_fill * sizeof(SlotFill), cudaMemcpyHostToDevice, stream));
+    B200RL_CUDA_OK(cudaMemcpyAsync(s.d_act, s.h_act, h->n_fill * (size_t)r.act_stride, cudaMemcpyHostToDevice, stream));
+    scatter_fills_kernel<<<(int)ceil_div<int64_t>(h->n_fill, 128), 128, 0, stream>>>(r, s.d_fill, s.d_act, (int)h->n_fill);
+    B200RL_LAUNCH_OK();
+  }
+  // publish the key range BEFORE the tree update so that its kernels see the new tail/head
+  s.h_state->item_head = h->item_head;
+  s.h_state->item_tail = h->item_tail;
+  B200RL_CUDA_OK(cudaMemcpyAsync(h->d_state, s.h_state, sizeof(ReplayState), cudaMemcpyHostToDevice, stream));
+  if (h->n_item > 0) {
+    B200RL_CUDA_OK(cudaMemcpyAsync(s.d_item, s.h_item, h->n_item * sizeof(ItemRec), cudaMemcpyHostToDevice, stream));
+    scatter_items_kernel<<<(int)ceil_div<int64_t>(h->n_item, 128), 128, 0, stream>>>(r, s.d_item, (int)h->n_item, s.d_pos, s.d_w);
+    B200RL_LAUNCH_OK();
+    // large flushes go through the stamp path in <=1024-entry pieces? no: one call, any size
+    int rc = tree_scatter_positions(h->tree, h->M, (int)h->n_item, (const int64_t*)s.d_pos, s.d_w,
+                                    h->d_state, h->d_stamp, h->d_epoch, stream);
+    if (rc) return rc;
+  }
+  B200RL_CUDA_OK(cudaEventRecord(s.done, stream));
+  s.in_flight = true;
+  h->last_flush_event = s.done;
+  h->last_flush_stream = stream;
+  h->n_obs = h->n_fill = h->n_item = 0;
+  h->state_dirty = false;
+  h->cur ^= 1;
+  Stage& nxt = h->stage[h->cur];
+  if (nxt.in_flight) {  // the set we are about to overwrite: wait for its copies (2 flushes ago)
+    B200RL_CUDA_OK(cudaEventSynchronize(nxt.done));
+    nxt.in_flight = false;
+  }
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_replay_flush(b200rl_replay* h, void* stream) {
+  B200RL_REQUIRE(h, "null handle");
+  int rc = ensure_device(h);
+  if (rc) return rc;
+  return flush_impl(h, as_stream(stream));
+}
+
+// the stream used by implicit flushes triggered from the host-only writer calls
+static cudaStream_t g_implicit_stream = nullptr;
+
+static int stage_tree_only(b200rl_replay* h, int64_t pos, float w) {
+  if (h->n_item >= h->stage_items) {
+    int rc = flush_impl(h, g_implicit_stream);
+    if (rc) return rc;
+  }
+  ItemRec& it = h->stage[h->cur].h_item[h->n_item++];
+  it.pos = pos; it.start = 0; it.end = 0; it.len = 0; it.weight = w;
+  return B200RL_OK;
+}
+
+// Allocate the next slot; evict items whose first slot is about to be overwritten.
+static int alloc_slot(b200rl_replay* h, const void* obs_host, uint64_t* seq_out) {
+  if (obs_host && h->n_obs >= h->stage_slots) {
+    int rc = flush_impl(h, g_implicit_stream);
+    if (rc) return rc;
+  }
+  uint64_t seq = h->slot_head++;
+  if (obs_host) {
+    if (h->n_obs == 0) h->obs_first_seq = seq;
+    memcpy(h->stage[h->cur].h_obs + h->n_obs * (int64_t)h->cfg.obs_bytes, obs_host, h->cfg.obs_bytes);
+    h->n_obs++;
+  }
+  if (h->slot_head > (uint64_t)h->S) {
+    uint64_t floor_seq = h->slot_head - (uint64_t)h->S;
+    while (h->item_tail < h->item_head && h->item_start_seq[h->item_tail % h->M] < floor_seq) {
+      int rc = stage_tree_only(h, (int64_t)(h->item_tail % h->M), 0.f);
+      if (rc) return rc;
+      h->item_tail++;
+      h->state_dirty = true;
+    }
+  }
+  *seq_out = seq;
+  return B200RL_OK;
+}
+
+static int stage_fill(b200rl_replay* h, uint64_t slot_seq, const void* act, float rew, float disc,
+                      uint64_t next_seq) {
+  if (h->n_fill >= h->stage_slots) {
+    int rc = flush_impl(h, g_implicit_stream);
+    if (rc) return rc;
+  }
+  Stage& s = h->stage[h->cur];
+  SlotFill& f = s.h_fill[h->n_fill];
+  f.slot = (int32_t)(slot_seq % (uint64_t)h->S);
+  f.next = (int32_t)(next_seq % (uint64_t)h->S);
+  f.rew = rew;
+  f.disc = disc;
+  uint8_t* a = s.h_act + h->n_fill * (int64_t)h->act_stride;
+  memset(a, 0, h->act_stride);
+  if (act) memcpy(a, act, h->cfg.act_bytes);
+  h->n_fill++;
+  return B200RL_OK;
+}
+
+static int make_item(b200rl_replay* h, Writer& w, int32_t num_timesteps, double priority, uint64_t* key_out) {
+  B200RL_REQUIRE(num_timesteps >= 1 && (int64_t)w.hist.size() >= (int64_t)num_timesteps + 1,
+                 "create_item(%d): only %d steps appended in this episode", num_timesteps,
+                 (int)w.hist.size() - 1);
+  uint64_t start_seq = w.hist[w.hist.size() - 1 - num_timesteps];
+  uint64_t end_seq = w.hist.back();
+  B200RL_REQUIRE(h->slot_head <= (uint64_t)h->S || start_seq >= h->slot_head - (uint64_t)h->S,
+                 "item window was already overwritten in the slot ring (slot_capacity too small)");
+  if (h->item_start_seq.empty()) h->item_start_seq.assign(h->M, 0);
+  // never stage two records for one tree position (tiny tables): cap the window at M items
+  if (h->n_item >= std::min<int64_t>(h->stage_items, h->M)) {
+    int rc = flush_impl(h, g_implicit_stream);
+    if (rc) return rc;
+  }
+  uint64_t key = h->item_head++;
+  if (h->item_head - h->item_tail > (uint64_t)h->M) h->item_tail++;  // Fifo remover: same tree position
+  int64_t pos = (int64_t)(key % (uint64_t)h->M);
+  h->item_start_seq[pos] = start_seq;
+  ItemRec& it = h->stage[h->cur].h_item[h->n_item++];
+  it.pos = pos;
+  it.start = (int32_t)(start_seq % (uint64_t)h->S);
+  it.end = (int32_t)(end_seq % (uint64_t)h->S);
+  it.len = num_timesteps;
+  float wt = (float)std::pow(priority, h->cfg.alpha);
+  it.weight = (wt > 0.f && wt < 3.0e38f) ? wt : 0.f;
+  h->state_dirty = true;
+  if (key_out) *key_out = key;  // keys are shard-local; the owning rank is implied by the handle
+  return B200RL_OK;
+}
+
+static Writer* get_writer(b200rl_replay* h, int32_t id) {
+  if (id < 0 || id >= (int32_t)h->writers.size() || !h->writers[id].in_use) {
+    set_error("unknown writer id %d", id);
+    return nullptr;
+  }
+  return &h->writers[id];
+}
+
+extern "C" int b200rl_writer_open(b200rl_replay* h, int32_t* writer_id) {
+  B200RL_REQUIRE(h && writer_id, "null argument");
+  B200RL_REQUIRE(h->cfg.obs_bytes > 0, "this replay was created without payload storage");
+  for (size_t i = 0; i < h->writers.size(); ++i)
+    if (!h->writers[i].in_use) {
+      h->writers[i] = Writer();
+      h->writers[i].in_use = true;
+      *writer_id = (int32_t)i;
+      return B200RL_OK;
+    }
+  h->writers.emplace_back();
+  h->writers.back().in_use = true;
+  *writer_id = (int32_t)h->writers.size() - 1;
+  return B200RL_OK;
+}
+
+static void push_hist(b200rl_replay* h, Writer& w, uint64_t seq) {
+  w.hist.push_back(seq);
+  while ((int64_t)w.hist.size() > h->cfg.max_window + 1) w.hist.pop_front();
+}
+
+extern "C" int b200rl_writer_append(b200rl_replay* h, int32_t writer, const void* obs, const void* act,
+                                    float rew, float disc, const void* next_obs) {
+  B200RL_REQUIRE(h && next_obs, "null argument");
+  Writer* w = get_writer(h, writer);
+  if (!w) return B200RL_EINVAL;
+  int rc = ensure_device(h);
+  if (rc) return rc;
+  if (w->hist.empty()) {
+    B200RL_REQUIRE(obs, "first append of an episode needs the initial observation");
+    uint64_t s0;
+    rc = alloc_slot(h, obs, &s0);
+    if (rc) return rc;
+    push_hist(h, *w, s0);
+    w->k = 0;
+  }
+  uint64_t cur = w->hist.back(), nxt;
+  rc = alloc_slot(h, next_obs, &nxt);
+  if (rc) return rc;
+  rc = stage_fill(h, cur, act, rew, disc, nxt);
+  if (rc) return rc;
+  push_hist(h, *w, nxt);
+  w->k++;
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_writer_create_item(b200rl_replay* h, int32_t writer, int32_t num_timesteps,
+                                         double priority, uint64_t* key_out) {
+  B200RL_REQUIRE(h, "null handle");
+  Writer* w = get_writer(h, writer);
+  if (!w) return B200RL_EINVAL;
+  int rc = ensure_device(h);
+  if (rc) return rc;
+  return make_item(h, *w, num_timesteps, priority, key_out);
+}
+
+extern "C" int b200rl_writer_close(b200rl_replay* h, int32_t writer) {
+  B200RL_REQUIRE(h, "null handle");
+  Writer* w = get_writer(h, writer);
+  if (!w) return B200RL_EINVAL;
+  w->in_use = false;
+  w->hist.clear();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_writer_append_stream(b200rl_replay* h, int32_t writer, int64_t n, const void* obs,
+                                           int obs_on_device, const void* act, const float* rew,
+                                           const float* disc, const uint8_t* first,
+                                           const uint8_t* last, int32_t n_step, double priority,
+                                           void* stream_) {
+  B200RL_REQUIRE(h && obs && rew && disc && first && last, "null argument");
+  B200RL_REQUIRE(n_step >= 1 && n_step <= h->cfg.max_window, "n_step must be in [1, max_window]");
+  B200RL_REQUIRE(n >= 0 && n <= h->S, "a stream chunk cannot exceed slot_capacity");
+  Writer* w = get_writer(h, writer);
+  if (!w) return B200RL_EINVAL;
+  int rc = ensure_device(h);
+  if (rc) return rc;
+  cudaStream_t stream = as_stream(stream_);
+  cudaStream_t saved = g_implicit_stream;
+  g_implicit_stream = stream;
+  const int32_t ob = h->cfg.obs_bytes;
+  if (obs_on_device) {
+    // pending host-staged observations must land first (slot order), then one or two D2D runs
+    rc = flush_impl(h, stream);
+    if (rc) { g_implicit_stream = saved; return rc; }
+    int64_t firsti = (int64_t)(h->slot_head % (uint64_t)h->S);
+    int64_t run0 = std::min<int64_t>(n, h->S - firsti);
+    RingView& r = h->ring;
+    if (run0 > 0)
+      B200RL_CUDA_OK(cudaMemcpy2DAsync(r.obs + firsti * r.obs_stride, r.obs_stride, obs, ob, ob, run0,
+                                       cudaMemcpyDeviceToDevice, stream));
+    if (run0 < n)
+      B200RL_CUDA_OK(cudaMemcpy2DAsync(r.obs, r.obs_stride, (const uint8_t*)obs + run0 * (int64_t)ob, ob, ob,
+                                       n - run0, cudaMemcpyDeviceToDevice, stream));
+  }
+  const uint8_t* acts = (const uint8_t*)act;
+  for (int64_t i = 0; i < n && rc == 0; ++i) {
+    if (first[i]) {  // a FIRST timestep: any unfinished episode of this writer is abandoned
+      w->hist.clear();
+      w->k = 0;
+      w->has_pending = false;
+    } else {
+      if (w->hist.empty()) {
+        set_error("stream element %lld is not FIRST but the writer has no open episode", (long long)i);
+        rc = B200RL_EINVAL;
+        break;
+      }
+    }
+    uint64_t seq;
+    rc = alloc_slot(h, obs_on_device ? nullptr : (const uint8_t*)obs + i * (int64_t)ob, &seq);
+    if (rc) break;
+    if (!first[i]) {
+      rc = stage_fill(h, w->hist.back(), w->pending_act.data(), w->pending_rew, w->pending_disc, seq);
+      if (rc) break;
+    }
+    push_hist(h, *w, seq);
+    if (!first[i]) {
+      w->k++;
+      // NStepTransitionAdder._write after the k-th add: window = whole deque (transition.py:120-124)
+      int32_t m = (int32_t)std::min<int64_t>(w->k, n_step);
+      rc = make_item(h, *w, m, priority, nullptr);
+      if (rc) break;
+      if (last[i]) {  // _write_last drain (transition.py:167-172)
+        for (int32_t j = 1; j < m && rc == 0; ++j) rc = make_item(h, *w, m - j, priority, nullptr);
+        w->hist.clear();
+        w->k = 0;
+        w->has_pending = false;
+        continue;
+      }
+    }
+    if (!last[i]) {
+      w->pending_act.assign(h->act_stride, 0);
+      if (acts) memcpy(w->pending_act.data(), acts + i * (int64_t)h->cfg.act_bytes, h->cfg.act_bytes);
+      w->pending_rew = rew[i];
+      w->pending_disc = disc[i];
+      w->has_pending = true;
+    } else {  // FIRST and LAST at once: a one-observation episode yields nothing
+      w->hist.clear();
+      w->k = 0;
+    }
+  }
+  if (rc == 0) rc = flush_impl(h, stream);
+  g_implicit_stream = saved;
+  return rc;
+}
+
+extern "C" int b200rl_replay_reset(b200rl_replay* h, void* stream_) {
+  B200RL_REQUIRE(h, "null handle");
+  int rc = ensure_device(h);
+  if (rc) return rc;
+  cudaStream_t stream = as_stream(stream_);
+  h->n_obs = h->n_fill = h->n_item = 0;
+  h->item_tail = h->item_head;  // every key issued so far is dead
+  for (auto& w : h->writers) { w.hist.clear(); w.k = 0; w.has_pending = false; }
+  int64_t total = 32;
+  for (int l = 1; l <= h->tree.L; ++l) total += h->tree.width[l];
+  B200RL_CUDA_OK(cudaMemsetAsync(h->d_tree, 0, total * 4, stream));
+  h->state_dirty = true;
+  return flush_impl(h, stream);
+}
+
+// ----------------------------------------------------------------------------- sample path
+extern "C" int b200rl_replay_sample(b200rl_replay* h, int32_t B, const float* u_dev, int stratified,
+                                    int64_t* idx_dev, uint64_t* keys_dev, float* prob_dev, void* stream) {
+  B200RL_REQUIRE(h && u_dev && idx_dev && prob_dev, "null argument");
+  B200RL_REQUIRE(B >= 1, "batch must be >= 1");
+  if (h->item_head == h->item_tail) {
+    set_error("replay is empty (MinSize(1) not met)");
+    return B200RL_EAGAIN;
+  }
+  int rc = ensure_device(h);
+  if (rc) return rc;
+  return tree_sample(h->tree, h->d_state, h->M, B, u_dev, stratified, h->cfg.shard_count, idx_dev,
+                     keys_dev, prob_dev, as_stream(stream), nullptr);
+}
+
+extern "C" int b200rl_replay_gather(b200rl_replay* h, int32_t B, const int64_t* idx_dev, void* o_tm1,
+                                    void* a_tm1, float* R, float* D, void* o_t, void* stream) {
+  B200RL_REQUIRE(h && idx_dev && o_tm1 && a_tm1 && R && D && o_t, "null argument");
+  B200RL_REQUIRE(h->cfg.obs_bytes > 0, "this replay was created without payload storage");
+  B200RL_REQUIRE(B >= 1, "batch must be >= 1");
+  int rc = ensure_device(h);
+  if (rc) return rc;
+  dim3 grid(B, 2);
+  const bool a16 = (h->cfg.obs_bytes % 16 == 0) && (((uintptr_t)o_tm1 | (uintptr_t)o_t) % 16 == 0);
+  const bool a4 = (h->cfg.obs_bytes % 4 == 0) && (((uintptr_t)o_tm1 | (uintptr_t)o_t) % 4 == 0);
+  if (a16)
+    gather_kernel<16><<<grid, 256, 0, as_stream(stream)>>>(h->ring, (const long long*)idx_dev, (uint8_t*)o_tm1, (uint8_t*)a_tm1, R, D, (uint8_t*)o_t);
+  else if (a4)
+    gather_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(h->ring, (const long long*)idx_dev, (uint8_t*)o_tm1, (uint8_t*)a_tm1, R, D, (uint8_t*)o_t);
+  else
+    gather_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(h->ring, (const long long*)idx_dev, (uint8_t*)o_tm1, (uint8_t*)a_tm1, R, D, (uint8_t*)o_t);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_replay_update_priorities(b200rl_replay* h, int32_t B, const uint64_t* keys_dev,
+                                               const float* priority_dev, void* stream) {
+  B200RL_REQUIRE(h && keys_dev && priority_dev, "null argument");
+  B200RL_REQUIRE(B >= 0, "negative batch");
+  int rc = ensure_device(h);
+  if (rc) return rc;
+  return tree_scatter_keys(h->tree, h->M, B, keys_dev, priority_dev, h->cfg.alpha, h->d_state,
+                           h->d_stamp, h->d_epoch, as_stream(stream));
+}
+
+extern "C" int b200rl_replay_info(b200rl_replay* h, int64_t* size, uint64_t* head_key, uint64_t* tail_key,
+                                  float* total_mass, void* stream) {
+  B200RL_REQUIRE(h, "null handle");
+  if (size) *size = (int64_t)(h->item_head - h->item_tail);
+  if (head_key) *head_key = h->item_head;
+  if (tail_key) *tail_key = h->item_tail;
+  if (total_mass) {
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    B200RL_CUDA_OK(cudaMemcpyAsync(total_mass, h->tree.lvl[0], 4, cudaMemcpyDeviceToHost, as_stream(stream)));
+    B200RL_CUDA_OK(cudaStreamSynchronize(as_stream(stream)));
+  }
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_replay_tree_levels(b200rl_replay* h, int32_t* num_levels, int32_t* fanout, int32_t* staged) {
+  B200RL_REQUIRE(h, "null handle");
+  if (num_levels) *num_levels = h->tree.L;
+  if (fanout) *fanout = kFanout;
+  if (staged) *staged = h->staged_levels;
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_replay_tree_level_width(b200rl_replay* h, int32_t level, int64_t* width) {
+  B200RL_REQUIRE(h && width && level >= 0 && level <= h->tree.L, "bad level");
+  *width = h->tree.width[level];
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_replay_tree_read(b200rl_replay* h, int32_t level, float* host_out, int64_t n, void* stream) {
+  B200RL_REQUIRE(h && host_out && level >= 0 && level <= h->tree.L, "bad argument");
+  B200RL_REQUIRE(n >= 0 && n <= h->tree.width[level], "n exceeds level width");
+  int rc = ensure_device(h);
+  if (rc) return rc;
+  B200RL_CUDA_OK(cudaMemcpyAsync(host_out, h->tree.lvl[level], n * 4, cudaMemcpyDeviceToHost, as_stream(stream)));
+  B200RL_CUDA_OK(cudaStreamSynchronize(as_stream(stream)));
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_replay_mass_ptr(b200rl_replay* h, float** mass_dev) {
+  B200RL_REQUIRE(h && mass_dev, "null argument");
+  *mass_dev = h->tree.lvl[0];
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_replay_set_weights(b200rl_replay* h, int64_t n, const float* weights_dev, void* stream_) {
+  B200RL_REQUIRE(h && weights_dev, "null argument");
+  B200RL_REQUIRE(n >= 1 && n <= h->M, "n must be in [1, max_items]");
+  int rc = ensure_device(h);
+  if (rc) return rc;
+  cudaStream_t stream = as_stream(stream_);
+  const int L = h->tree.L;
+  B200RL_CUDA_OK(cudaMemcpyAsync(h->tree.lvl[L], weights_dev, n * 4, cudaMemcpyDeviceToDevice, stream));
+  if (n < h->tree.width[L])
+    B200RL_CUDA_OK(cudaMemsetAsync(h->tree.lvl[L] + n, 0, (h->tree.width[L] - n) * 4, stream));
+  rc = tree_rebuild(h->tree, stream);
+  if (rc) return rc;
+  h->item_tail = 0;
+  h->item_head = (uint64_t)n;
+  h->state_dirty = true;
+  return flush_impl(h, stream);
+}

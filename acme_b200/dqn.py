@@ -1,0 +1,235 @@
+"""DQN learner + agent on the B200 hot path.
+
+`DQNLearner` keeps the constructor and `step()/get_variables()/state` surface of
+`acme/agents/tf/dqn/learning.py:35-199`; one `step()` is:
+  K1 sample -> K3 gather/n-step -> K6 three forwards -> K4 TD/Huber/IS/priorities ->
+  K6 backward -> [NCCL all-reduce when data-parallel] -> K7 Adam -> K2 priority write-back ->
+  conditional target copy -> step counter,
+all on one stream, recorded once into a CUDA graph and replayed.  `DQN` builds the table, adder,
+dataset, actor and learner like `acme/agents/tf/dqn/agent.py:45-162`.
+"""
+
+from __future__ import annotations
+
+import time
+from typing import List, Optional
+
+import numpy as np
+
+from acme_b200 import _capi, actors, adders, agent, core, counting, loggers, networks, replay, specs
+
+
+class DQNLearner(core.Learner, core.Saveable):
+
+  def __init__(self, network, target_network, discount: float, importance_sampling_exponent: float,
+               learning_rate: float, target_update_period: int, dataset: replay.ReplayDataset,
+               huber_loss_parameter: float = 1., replay_client: Optional[replay.Client] = None,
+               counter: counting.Counter = None, logger: loggers.Logger = None, checkpoint: bool = True,
+               max_abs_reward: float = 1., eps_mode: int = 0, use_cuda_graph: bool = True,
+               process_group=None, adam_eps: float = 1e-8):
+    import torch
+    if huber_loss_parameter < 0:
+      raise ValueError('quadratic_linear_boundary must be >= 0.')   # huber.py:45-46
+    self._torch = torch
+    self._net, self._tgt = network, target_network
+    self._dataset = dataset
+    self._replay_client = replay_client
+    self._discount = float(np.float32(discount))
+    self._beta = float(importance_sampling_exponent)
+    self._delta = float(huber_loss_parameter)
+    self._lr = float(np.float32(learning_rate))
+    self._period = int(target_update_period)
+    self._max_abs_reward = float(max_abs_reward)
+    self._eps_mode, self._adam_eps = int(eps_mode), float(adam_eps)
+    self._counter = counter or counting.Counter()
+    self._logger = logger or loggers.TerminalLogger('learner', time_delta=1.)
+    self._timestamp = None
+    self._pg = process_group
+    self._world = 1
+    if process_group is not None:
+      import torch.distributed as dist
+      self._world = dist.get_world_size(process_group)
+
+    dev = torch.device('cuda', network.device)
+    B, A = dataset.B, network.A
+    self.B = B
+    f32 = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
+    self._bufs_train = network.make_buffers(B)
+    self._bufs_sel = network.make_buffers(B)
+    self._bufs_tgt = target_network.make_buffers(B)
+    self._gbufs = network.make_grad_buffers(B)
+    self.td, self.loss_ps, self.weight, self.priority = f32(B), f32(B), f32(B), f32(B)
+    self.dq = f32(B, A)
+    self.loss = f32(1)
+    self._m = torch.zeros_like(network.params.flat)
+    self._v = torch.zeros_like(network.params.flat)
+    self._num_steps = torch.zeros(1, dtype=torch.int64, device=dev)
+    self._wmax = torch.zeros(1, dtype=torch.float64, device=dev)
+    self._gscale = torch.full((1,), 1.0 / self._world, dtype=torch.float32, device=dev)
+    self._loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+    self._graphs = None
+    self._use_graph = bool(use_cuda_graph)
+    self._steps_done = 0
+    self.kernel_launches_per_step = None
+
+    t = dataset.table
+    obs_spec = t.signature[0]
+    self._obs_shape = tuple(obs_spec.shape)
+    self._obs_dtype = np.dtype(obs_spec.dtype)
+    self._act_dtype = np.dtype(t.signature[1].dtype)
+
+  # ------------------------------------------------------------------ one update on the device
+  def _obs_view(self, rows):
+    torch = self._torch
+    if self._obs_dtype == np.uint8:
+      return rows.view((self.B,) + self._obs_shape)
+    return rows.view(getattr(torch, self._obs_dtype.name)).view((self.B,) + self._obs_shape)
+
+  def _actions_i32(self):
+    torch = self._torch
+    a = self._dataset.a_tm1
+    if self._act_dtype == np.int32:
+      return a.view(torch.int32).view(self.B)
+    return a.view(getattr(torch, self._act_dtype.name)).view(self.B).to(torch.int32)
+
+  def _forward_loss(self):
+    ds, net, tgt = self._dataset, self._net, self._tgt
+    st = _capi.current_stream()
+    o_tm1, o_t = self._obs_view(ds.o_tm1), self._obs_view(ds.o_t)
+    q_tm1 = net.forward(o_tm1, self._bufs_train)               # learning.py:123
+    q_t_value = tgt.forward(o_t, self._bufs_tgt)               # learning.py:124
+    q_t_selector = net.forward(o_t, self._bufs_sel)            # learning.py:125
+    wmax = None
+    if self._world > 1:   # global max importance weight: allreduce(MAX) of one f64
+      import torch.distributed as dist
+      _capi.call('b200rl_is_weight_max', self.B, _capi.ptr(ds.prob), self._beta, _capi.ptr(self._wmax), st)
+      dist.all_reduce(self._wmax, op=dist.ReduceOp.MAX, group=self._pg)
+      wmax = _capi.ptr(self._wmax)
+    _capi.call('b200rl_dqn_td', self.B, net.A, _capi.ptr(q_tm1), _capi.ptr(q_t_value), _capi.ptr(q_t_selector),
+               _capi.ptr(self._actions_i32()), _capi.ptr(ds.R), _capi.ptr(ds.D), _capi.ptr(ds.prob),
+               self._discount, self._delta, self._beta, self._max_abs_reward, wmax, 1.0 / self.B,
+               _capi.ptr(self.td), _capi.ptr(self.loss_ps), _capi.ptr(self.weight), _capi.ptr(self.priority),
+               _capi.ptr(self.dq), _capi.ptr(self.loss), st)
+    net.backward(o_tm1, self._bufs_train, self._gbufs, self.dq)
+
+  def _apply(self):
+    net, tgt, st = self._net, self._tgt, _capi.current_stream()
+    P = net.params
+    _capi.call('b200rl_adam', P.size, _capi.ptr(P.flat), _capi.ptr(P.grad), _capi.ptr(self._m), _capi.ptr(self._v),
+               _capi.ptr(self._num_steps), self._lr, 0.9, 0.999, self._adam_eps, self._eps_mode,
+               _capi.ptr(self._gscale) if self._world > 1 else None, None, st)
+    if self._replay_client is not None:                         # learning.py:151-154
+      self._dataset.table.update_priorities_device(self._dataset.keys, self.priority)
+    # learning.py:157-161: copy when num_steps % period == 0, evaluated before the increment
+    _capi.call('b200rl_copy_if_period', P.size * 4, _capi.ptr(tgt.params.flat), _capi.ptr(P.flat),
+               _capi.ptr(self._num_steps), self._period, 0, st)
+    _capi.call('b200rl_step_increment', _capi.ptr(self._num_steps), st)
+
+  def _device_step(self, uniforms=None):
+    torch = self._torch
+    if self._world > 1:
+      import torch.distributed as dist
+      self._dataset.sample_raw(uniforms)
+      self._forward_loss()
+      dist.all_reduce(self._net.params.grad, op=dist.ReduceOp.SUM, group=self._pg)  # then x 1/R in Adam
+      self._apply()
+      return
+    if not self._use_graph or uniforms is not None:
+      self._dataset.sample_raw(uniforms)
+      self._forward_loss()
+      self._apply()
+      return
+    if self._graphs is None:
+      if self._steps_done < 2:          # warm-up un-captured (one-time attribute setup inside the library)
+        self._dataset.sample_raw()
+        self._forward_loss()
+        self._apply()
+        return
+      g = torch.cuda.CUDAGraph()
+      torch.cuda.synchronize()
+      with torch.cuda.graph(g):
+        self._dataset.sample_raw()
+        self._forward_loss()
+        self._apply()
+      self._graphs = g
+    self._graphs.replay()
+
+  # ------------------------------------------------------------------ acme.core.Learner
+  def step(self, uniforms=None, fetch_loss: bool = True):
+    table = self._dataset.table
+    table.flush()
+    if table.size < 1:
+      raise RuntimeError('replay is empty: MinSize(1) rate limiter would block')
+    self._device_step(uniforms)
+    self._steps_done += 1
+    result = {}
+    if fetch_loss:
+      self._loss_host.copy_(self.loss, non_blocking=True)
+      self._torch.cuda.current_stream().synchronize()
+      result['loss'] = float(self._loss_host[0])
+    timestamp = time.time()
+    elapsed = timestamp - self._timestamp if self._timestamp else 0
+    self._timestamp = timestamp
+    result.update(self._counter.increment(steps=1, walltime=elapsed))
+    self._logger.write(result)
+    return None
+
+  def get_variables(self, names: List[str]) -> List[List[np.ndarray]]:
+    return [list(self._net.variables().values())]
+
+  @property
+  def num_steps(self) -> int:
+    return int(self._num_steps.item())
+
+  @property
+  def state(self):
+    return {'network': self._net, 'target_network': self._tgt, 'optimizer': (self._m, self._v),
+            'num_steps': self._num_steps}
+
+  def save(self):
+    return {'network': self._net.params.flat.cpu().numpy(), 'target_network': self._tgt.params.flat.cpu().numpy(),
+            'adam_m': self._m.cpu().numpy(), 'adam_v': self._v.cpu().numpy(), 'num_steps': self.num_steps}
+
+  def restore(self, state):
+    torch = self._torch
+    self._net.params.flat.copy_(torch.as_tensor(state['network']))
+    self._tgt.params.flat.copy_(torch.as_tensor(state['target_network']))
+    self._m.copy_(torch.as_tensor(state['adam_m']))
+    self._v.copy_(torch.as_tensor(state['adam_v']))
+    self._num_steps.fill_(int(state['num_steps']))
+
+
+class DQN(agent.Agent):
+  """`acme/agents/tf/dqn/agent.py:36-167` with the replay, adder, dataset and learner of this package."""
+
+  def __init__(self, environment_spec: specs.EnvironmentSpec, network, batch_size: int = 256,
+               prefetch_size: int = 4, target_update_period: int = 100, samples_per_insert: float = 32.0,
+               min_replay_size: int = 1000, max_replay_size: int = 1000000,
+               importance_sampling_exponent: float = 0.2, priority_exponent: float = 0.6, n_step: int = 5,
+               epsilon: Optional[float] = None, learning_rate: float = 1e-3, discount: float = 0.99,
+               logger: loggers.Logger = None, checkpoint: bool = False, checkpoint_subpath: str = '~/acme/',
+               seed: int = 0, use_cuda_graph: bool = True, slot_capacity: Optional[int] = None):
+    table = replay.Table(
+        name=replay.DEFAULT_PRIORITY_TABLE, sampler=replay.selectors.Prioritized(priority_exponent),
+        remover=replay.selectors.Fifo(), max_size=max_replay_size,
+        rate_limiter=replay.rate_limiters.MinSize(1),
+        signature=adders.NStepTransitionAdder.signature(environment_spec),
+        max_window=max(n_step, 1), discount=discount, device=network.device, slot_capacity=slot_capacity)
+    self._server = replay.Server([table], port=None)
+    address = f'localhost:{self._server.port}'
+    adder = adders.NStepTransitionAdder(client=replay.Client(address), n_step=n_step, discount=discount)
+    replay_client = replay.TFClient(address)
+    dataset = replay.make_reverb_dataset(server_address=address, batch_size=batch_size,
+                                         prefetch_size=prefetch_size, seed=seed)
+    policy = actors.EpsilonGreedyPolicy(network, 0.05 if epsilon is None else epsilon, seed=seed)
+    target_network = network.clone()                 # deep-copied parameters (agent.py:127)
+    actor = actors.FeedForwardActor(policy, adder)
+    learner = DQNLearner(network=network, target_network=target_network, discount=discount,
+                         importance_sampling_exponent=importance_sampling_exponent,
+                         learning_rate=learning_rate, target_update_period=target_update_period,
+                         dataset=dataset, replay_client=replay_client, logger=logger, checkpoint=checkpoint,
+                         use_cuda_graph=use_cuda_graph)
+    self._learner_obj = learner
+    self._table = table
+    super().__init__(actor=actor, learner=learner, min_observations=max(batch_size, min_replay_size),
+                     observations_per_step=float(batch_size) / samples_per_insert)

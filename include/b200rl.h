@@ -1,0 +1,243 @@
+/*
+ * b200rl.h — C ABI of the B200-native off-policy learner hot path.
+ *
+ * The reference (tmtlakmal/acme v0.1.8) is pure Python and has no FFI layer of its own; its
+ * seams for this path are Python ABCs and the Reverb client surface.  Each entry
+ * point below names the reference call site it stands in for.  Host code (acme_b200/*.py) binds
+ * these with ctypes; signatures carry only plain pointers and sizes.
+ *
+ * Conventions
+ *   - return 0 on success; <0 on failure: -1 invalid argument, -2 CUDA error, -3 would block /
+ *     not enough items, -4 unsupported device (compute capability != 10.0; there is NO CPU
+ *     fallback).  b200rl_last_error() gives the message (thread-local).
+ *   - `*_dev` pointers are device pointers on the handle's device; `stream` is a cudaStream_t
+ *     passed as void* (NULL = legacy default stream).  Hot calls never allocate, never
+ *     synchronise and never create streams, so they can be captured into CUDA graphs.
+ *   - buffers are caller-owned; the library allocates only in *_create and frees in *_destroy.
+ *   - one writer thread + one learner thread per handle; a handle is not re-entrant.
+ */
+#ifndef B200RL_H_
+#define B200RL_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200RL_VERSION 100
+
+#define B200RL_OK 0
+#define B200RL_EINVAL (-1)
+#define B200RL_ECUDA (-2)
+#define B200RL_EAGAIN (-3)
+#define B200RL_EARCH (-4)
+
+int b200rl_version(void);
+const char* b200rl_last_error(void);
+/* 0 iff `device` is an sm_100 part this library was built for. */
+int b200rl_device_check(int device);
+
+/* ------------------------------------------------------------------------------------------
+ * Replay shard: ring of observation slots + ring of items + fan-out-32 fp32 sum-tree.
+ * Stands in for reverb.Table(sampler=Prioritized(alpha), remover=Fifo(), max_size,
+ * rate_limiter=MinSize(1))  — acme/agents/tf/dqn/agent.py:95-102, d4pg/agent.py:96-103.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct b200rl_replay b200rl_replay;
+
+typedef struct b200rl_replay_cfg {
+  int64_t max_items;     /* Table max_size (items)                                         */
+  int64_t slot_capacity; /* observation slots in the HBM ring (>= max_window + 2)           */
+  int32_t obs_bytes;     /* bytes of one observation                                        */
+  int32_t act_bytes;     /* bytes of one action                                             */
+  int32_t max_window;    /* largest n_step any writer will use                              */
+  int32_t shard_count;   /* R replay shards (one per rank); probability = w / (R * mass_r)  */
+  int32_t shard_rank;
+  int32_t device;
+  int32_t stage_slots;   /* pinned-host staging capacity in slots (0 = default)             */
+  int32_t reserved;
+  float gamma;           /* agent discount, np.float32(discount): transition.py:111         */
+  float reserved_f;
+  double alpha;          /* priority exponent: stored weight = priority^alpha               */
+} b200rl_replay_cfg;
+
+int b200rl_replay_create(b200rl_replay** out, const b200rl_replay_cfg* cfg);
+int b200rl_replay_destroy(b200rl_replay* h);
+/* reverb.Client.reset(table) (acme/datasets/reverb_test.py:70): drop every item. */
+int b200rl_replay_reset(b200rl_replay* h, void* stream);
+
+/* --- insert path: reverb.Client.writer(...) / Writer.append / create_item / close
+ *     (acme/adders/reverb/base.py:111-132, transition.py:162-165).  Host pointers. --- */
+int b200rl_writer_open(b200rl_replay* h, int32_t* writer_id);
+/* One environment step: (obs, act, rew, disc) then the observation that followed.  `obs` is read
+ * only when the writer has no open episode (first step after open/close). */
+int b200rl_writer_append(b200rl_replay* h, int32_t writer, const void* obs, const void* act,
+                         float rew, float disc, const void* next_obs);
+/* Item over the last `num_timesteps` appended steps (Reverb's meaning), priority raw. */
+int b200rl_writer_create_item(b200rl_replay* h, int32_t writer, int32_t num_timesteps,
+                              double priority, uint64_t* key_out);
+/* End of episode (ReverbAdder.reset, base.py:126-132): forget the step history. */
+int b200rl_writer_close(b200rl_replay* h, int32_t writer);
+/* Bulk form used by feeders and benchmarks: `n` consecutive timesteps of ONE stream.  Element i is
+ * an observation slot; first[i] marks an episode start, last[i] a terminal observation (its
+ * act/rew/disc are ignored).  Items are enumerated exactly as NStepTransitionAdder does
+ * (transition.py:119-172) with window `n_step` and raw priority `priority`.
+ * `obs` may be a device pointer (obs_on_device != 0); the other arrays are host arrays. */
+int b200rl_writer_append_stream(b200rl_replay* h, int32_t writer, int64_t n, const void* obs,
+                                int obs_on_device, const void* act, const float* rew,
+                                const float* disc, const uint8_t* first, const uint8_t* last,
+                                int32_t n_step, double priority, void* stream);
+/* Make everything appended so far visible to sample/gather (H2D of staged slots + tree insert). */
+int b200rl_replay_flush(b200rl_replay* h, void* stream);
+
+/* --- sample path: what reverb.ReplayDataset yields per item (acme/datasets/reverb.py:91-139):
+ *     SampleInfo(key, probability, table_size, priority) + data.                       --- */
+/* K1.  u_dev: B uniforms in [0,1).  stratified: target_b = (b+u_b)/B*mass, else u_b*mass.
+ * idx = tree position (item slot), keys = Reverb-style opaque key, prob = w/(R*mass). */
+int b200rl_replay_sample(b200rl_replay* h, int32_t B, const float* u_dev, int stratified,
+                         int64_t* idx_dev, uint64_t* keys_dev, float* prob_dev, void* stream);
+/* K3.  Gather (o_tm1, a_tm1, R, D, o_t) for B tree positions; R, D built from the ring with the
+ * arithmetic of transition.py:135-145 (fp32, unfused). */
+int b200rl_replay_gather(b200rl_replay* h, int32_t B, const int64_t* idx_dev, void* o_tm1_dev,
+                         void* a_tm1_dev, float* R_dev, float* D_dev, void* o_t_dev, void* stream);
+/* K2.  TFClient.update_priorities(table, keys, priorities) (dqn/learning.py:151-154): weight =
+ * priority^alpha for every still-live key, duplicates: last wins, dead keys ignored. */
+int b200rl_replay_update_priorities(b200rl_replay* h, int32_t B, const uint64_t* keys_dev,
+                                    const float* priority_dev, void* stream);
+/* Host view of the table (synchronises `stream`): live items, key range, total mass. */
+int b200rl_replay_info(b200rl_replay* h, int64_t* size, uint64_t* head_key, uint64_t* tail_key,
+                       float* total_mass, void* stream);
+/* Tree geometry + raw level access (tests, checkpointing).  level 0 = root .. L = leaves. */
+int b200rl_replay_tree_levels(b200rl_replay* h, int32_t* num_levels, int32_t* fanout,
+                              int32_t* staged_levels);
+int b200rl_replay_tree_level_width(b200rl_replay* h, int32_t level, int64_t* width);
+int b200rl_replay_tree_read(b200rl_replay* h, int32_t level, float* host_out, int64_t n, void* stream);
+/* Device address of the root mass (one float) for cross-shard normalisation. */
+int b200rl_replay_mass_ptr(b200rl_replay* h, float** mass_dev);
+
+/* Stand-alone sum-tree (priorities only) for the sampling/update sweep (BASELINE config 4). */
+int b200rl_replay_set_weights(b200rl_replay* h, int64_t n, const float* weights_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Learner math (stateless kernels; parameters live in caller-owned device buffers).
+ * ------------------------------------------------------------------------------------------ */
+/* Philox4x32-10 uniforms in [0,1): out[i] = f(seed, *step_dev + step_offset, i). */
+int b200rl_uniform(float* out_dev, int32_t n, uint64_t seed, const int64_t* step_dev,
+                   int64_t step_offset, void* stream);
+
+/* K4.  dqn/learning.py:127-154 + trfl.double_qlearning + losses/huber.py:48-57.
+ * wmax_dev (nullable): device scalar (f64) holding the GLOBAL max importance weight for data-parallel
+ * learners; NULL = batch max (the reference's tf.reduce_max).  If wmax_out_dev != NULL the local
+ * max is written there instead and no normalisation happens (two-pass DP form). */
+int b200rl_dqn_td(int32_t B, int32_t A, const float* q_tm1, const float* q_t_value,
+                  const float* q_t_selector, const int32_t* a_tm1, const float* R, const float* D,
+                  const float* prob, float gamma, float huber_delta, double is_exponent,
+                  float max_abs_reward, const double* wmax_dev, float grad_scale, float* td,
+                  float* loss_per_sample, float* weight, float* priority, float* dq_tm1,
+                  float* loss_mean, void* stream);
+int b200rl_is_weight_max(int32_t B, const float* prob, double is_exponent, double* wmax_out_dev,
+                         void* stream);
+
+/* K5.  losses/distributional.py:22-83: target = l2_project(R + Dg*z, softmax(logits_t), z); loss =
+ * CE(logits_tm1, target); dlogits = (softmax(logits_tm1)*sum(target) - target) * grad_scale. */
+int b200rl_c51_loss(int32_t B, int32_t K, float vmin, float vmax, const float* logits_tm1,
+                    const float* logits_t, const float* R, const float* D, float gamma,
+                    float grad_scale, float* target, float* loss_per_sample, float* dlogits_tm1,
+                    float* loss_mean, void* stream);
+/* mean of a discrete-valued distribution and its logit gradient (distributions.py:64-66):
+ * q = sum softmax(l)_i z_i;  dlogits_i = p_i (z_i - q) * dq. */
+int b200rl_c51_mean_fwd(int32_t B, int32_t K, float vmin, float vmax, const float* logits, float* q,
+                        void* stream);
+int b200rl_c51_mean_bwd(int32_t B, int32_t K, float vmin, float vmax, const float* logits,
+                        const float* dq /*nullable => 1*/, float* dlogits, void* stream);
+/* losses/dpg.py:41-57: da = -clip_by_norm(dqda, clip) * grad_scale; loss = mean 0.5*||clipped||^2 */
+int b200rl_dpg_action_grad(int32_t B, int32_t A, const float* dqda, float clip, int clip_norm,
+                           float grad_scale, float* da, float* loss_per_sample /*nullable*/,
+                           float* loss_mean /*nullable, needs loss_per_sample*/, void* stream);
+
+/* K7.  snt.optimizers.Adam.apply (dqn/learning.py:148); step/bias corrections live on device so the
+ * call is graph-replayable: t = *step_dev + 1.  eps_mode 0 = m^/(sqrt(v^)+eps), 1 = Keras form.
+ * grad_scale_dev (nullable): device scalar multiplied into every gradient (global-norm clip, 1/R).
+ * bf16_shadow (nullable): also writes the updated parameter rounded to bf16. */
+int b200rl_adam(int64_t n, float* param, const float* grad, float* m, float* v,
+                const int64_t* step_dev, float lr, double b1, double b2, float eps, int eps_mode,
+                const float* grad_scale_dev, void* bf16_shadow, void* stream);
+/* tf.clip_by_global_norm (d4pg/learning.py:235-237): *scale_out = clip / max(||g||, clip). */
+int b200rl_global_norm_scale(int64_t n, const float* grad, float clip, float* partial_ws,
+                             float* scale_out_dev, float* norm_out_dev, void* stream);
+/* if (*step_dev % period == 0) dst <- src   (dqn/learning.py:157-160; d4pg/learning.py:171-174) */
+int b200rl_copy_if_period(int64_t n_bytes, void* dst, const void* src, const int64_t* step_dev,
+                          int64_t period, int64_t phase, void* stream);
+int b200rl_step_increment(int64_t* step_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K6.  Network layers (acme/tf/networks/atari.py:36-69, duelling.py:37-59, continuous.py:37-68).
+ * Activations NHWC / row-major fp32; weights [out][in] (conv: [Cout][kh][kw][Cin]) fp32.
+ * precision: 0 = fp32 SIMT (parity mode, 1e-5), 1 = bf16 operands on tcgen05 tensor cores with
+ * fp32 accumulation (speed mode; stated tolerance in DESIGN.md).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct b200rl_conv_geom {
+  int32_t B, H, W, C;       /* input NHWC                         */
+  int32_t kh, kw, stride;   /* filter                             */
+  int32_t pad_top, pad_left;/* TF SAME: before = total/2          */
+  int32_t OH, OW, Cout;
+} b200rl_conv_geom;
+
+#define B200RL_ACT_NONE 0
+#define B200RL_ACT_RELU 1
+#define B200RL_ACT_ELU 2
+#define B200RL_ACT_TANH 3
+
+/* y = act(conv(x, w) + b).  x_u8 != 0: x is uint8 and is read as float(x)/255 (atari_wrapper.py:303). */
+int b200rl_conv2d_fwd(const void* x, int x_u8, const float* w, const float* bias, float* y,
+                      const b200rl_conv_geom* g, int act, int precision, void* ws, int64_t ws_bytes,
+                      void* stream);
+/* dw[Cout][kh][kw][Cin] = sum_m dy[m,co] * col(x)[m,k];  db = colsum(dy).  dy is d(pre-activation). */
+int b200rl_conv2d_wgrad(const void* x, int x_u8, const float* dy, float* dw, float* db,
+                        const b200rl_conv_geom* g, int precision, void* ws, int64_t ws_bytes,
+                        void* stream);
+/* dx = conv_transpose(dy, w) [* act'(x_out)]: if mask_y != NULL multiplies by d act / d pre evaluated
+ * from the producer layer's *output* mask_y (ReLU: y>0). */
+int b200rl_conv2d_dgrad(const float* dy, const float* w, float* dx, const b200rl_conv_geom* g,
+                        const float* mask_y, int mask_act, int precision, void* ws,
+                        int64_t ws_bytes, void* stream);
+/* y[M,N] = act(x[M,K] @ w[N,K]^T + b); ldx / ldy are row strides in elements (>= K / >= N) */
+int b200rl_linear_fwd(int32_t M, int32_t N, int32_t K, const float* x, int32_t ldx, const float* w,
+                      const float* bias, float* y, int32_t ldy, int act, int precision, void* ws,
+                      int64_t ws_bytes, void* stream);
+/* dx[M,K] = dy[M,N] @ w[N,K]  [* act'(mask_y)]; mask_y shares dx's row stride */
+int b200rl_linear_dgrad(int32_t M, int32_t N, int32_t K, const float* dy, int32_t lddy,
+                        const float* w, float* dx, int32_t lddx, const float* mask_y, int mask_act,
+                        int precision, void* ws, int64_t ws_bytes, void* stream);
+/* dw[N,K] = dy[M,N]^T @ x[M,K];  db[N] = colsum(dy) (nullable) */
+int b200rl_linear_wgrad(int32_t M, int32_t N, int32_t K, const float* dy, int32_t lddy,
+                        const float* x, int32_t ldx, float* dw, float* db, int precision, void* ws,
+                        int64_t ws_bytes, void* stream);
+/* in-place dy *= act'(y) for outputs that feed a loss directly */
+int b200rl_act_bwd(int64_t n, float* dy, const float* y, int act, void* stream);
+/* duelling head (duelling.py:51-59): q = v + (adv - mean(adv)); bwd: dv = sum dq, dadv = dq - mean(dq) */
+int b200rl_duelling_fwd(int32_t B, int32_t A, const float* value, const float* adv, float* q, void* stream);
+int b200rl_duelling_bwd(int32_t B, int32_t A, const float* dq, float* dvalue, float* dadv, void* stream);
+/* snt.LayerNorm(axis=1:, scale, offset, eps=1e-5) followed by tanh (continuous.py:55-58) */
+int b200rl_layernorm_tanh_fwd(int32_t B, int32_t N, const float* x, const float* scale,
+                              const float* offset, float eps, float* y, float* xhat, float* rstd,
+                              void* stream);
+int b200rl_layernorm_tanh_bwd(int32_t B, int32_t N, const float* dy, const float* y, const float* xhat,
+                              const float* rstd, const float* scale, float* dx, float* dscale,
+                              float* doffset, void* stream);
+/* TanhToSpec (rescaling.py:63-74): a = 0.5*(tanh(x)+1)*scale + offset; bwd: dx = da*0.5*scale*(1-tanh^2) */
+int b200rl_tanh_to_spec_fwd(int32_t B, int32_t A, const float* x, const float* scale,
+                            const float* offset, float* a, void* stream);
+int b200rl_tanh_to_spec_bwd(int32_t B, int32_t A, const float* da, const float* x, const float* scale,
+                            float* dx, void* stream);
+/* batch_concat([obs, act]) (tf/utils.py:39-54) and its split for the backward */
+int b200rl_concat2(int32_t B, int32_t n0, int32_t n1, const float* x0, const float* x1, float* y, void* stream);
+int b200rl_split_second(int32_t B, int32_t n0, int32_t n1, const float* dy, float* dx1, void* stream);
+/* bytes of split-K workspace that lets every layer call on outputs of up to max_out_elems
+ * elements use its preferred split count (smaller workspaces only reduce the split count) */
+int64_t b200rl_workspace_bytes(int64_t max_out_elems);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RL_H_ */

@@ -1,0 +1,375 @@
+"""GPU parity of the learner math (K4 TD/Huber/IS, K5 C51, K6 layers fwd/bwd, K7 Adam) through the
+C ABI against the fp32 oracle.  Tolerance: 1e-5 relative (north_star) with an absolute floor that
+scales with the magnitude of the tensor (different fp32 summation orders)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def close(got, want, rtol=RTOL, atol_scale=1e-6, name=''):
+  got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+  atol = atol_scale * max(float(np.abs(want).max()), 1e-30)
+  np.testing.assert_allclose(got, want, rtol=rtol, atol=atol, err_msg=name)
+
+
+def dev(x):
+  import torch
+  return torch.as_tensor(np.ascontiguousarray(x)).cuda()
+
+
+def empty(*shape, dtype=None):
+  import torch
+  return torch.empty(shape, dtype=dtype or torch.float32, device='cuda')
+
+
+@pytest.mark.parametrize('B,A,wmax', [(256, 18, None), (10, 3, None), (2048, 18, None), (256, 18, 7.5)])
+def test_dqn_td_kernel(B, A, wmax):
+  import torch
+  from acme_b200 import _capi
+  from oracle import losses
+  rng = np.random.default_rng(B + A)
+  q_tm1, q_tv, q_ts = (rng.standard_normal((B, A)).astype(np.float32) * 3 for _ in range(3))
+  q_ts[0, :] = 1.0                                          # ties -> first index
+  a = rng.integers(0, A, B).astype(np.int32)
+  R = (rng.standard_normal(B) * 2).astype(np.float32)
+  D = rng.choice([0., 0.9801, 1.0], B).astype(np.float32)
+  prob = rng.uniform(1e-7, 1e-3, B).astype(np.float32)
+  ref = losses.dqn_loss(q_tm1, q_tv, q_ts, a, R, D, prob, 0.99, 1.0, 0.2, 1.0, global_wmax=wmax)
+  td, lps, w, pr, dq, lm = empty(B), empty(B), empty(B), empty(B), empty(B, A), empty(1)
+  wm = dev(np.array([wmax], np.float64)) if wmax else None
+  _capi.call('b200rl_dqn_td', B, A, dev(q_tm1).data_ptr(), dev(q_tv).data_ptr(), dev(q_ts).data_ptr(), dev(a).data_ptr(),
+             dev(R).data_ptr(), dev(D).data_ptr(), dev(prob).data_ptr(), 0.99, 1.0, 0.2, 1.0, _capi.ptr(wm), 1.0 / B,
+             td.data_ptr(), lps.data_ptr(), w.data_ptr(), pr.data_ptr(), dq.data_ptr(), lm.data_ptr(), _capi.current_stream())
+  torch.cuda.synchronize()
+  np.testing.assert_array_equal(td.cpu().numpy(), ref['td'])          # same fp32 op order: bit-exact
+  np.testing.assert_array_equal(pr.cpu().numpy(), np.abs(ref['td']))
+  close(w.cpu().numpy(), ref['weight'], name='weight')
+  close(lps.cpu().numpy(), ref['per_sample'], name='per-sample loss')
+  close(lm.cpu().numpy()[0], ref['loss'], name='loss')
+  close(dq.cpu().numpy(), ref['dq_tm1'], name='dq')
+  if wmax is None:
+    out = dev(np.zeros(1, np.float64))
+    _capi.call('b200rl_is_weight_max', B, dev(prob).data_ptr(), 0.2, out.data_ptr(), _capi.current_stream())
+    close(out.cpu().numpy()[0], ref['wmax64'], rtol=1e-12)
+
+
+@pytest.mark.parametrize('B,K,vmin,vmax', [(256, 51, -150., 150.), (7, 51, -10., 10.), (64, 11, 0., 5.)])
+def test_c51_projection_and_loss(B, K, vmin, vmax):
+  import torch
+  from acme_b200 import _capi
+  from oracle import losses
+  rng = np.random.default_rng(K + B)
+  lt1, lt = rng.standard_normal((B, K)).astype(np.float32) * 2, rng.standard_normal((B, K)).astype(np.float32) * 2
+  R = rng.uniform(-1, 1, B).astype(np.float32) * (vmax - vmin) / 4
+  D = rng.choice([0., 0.96, 1.0], B).astype(np.float32)
+  R[0], D[0] = 0.0, 1.0   # gamma=1 below for this row would land on atoms; keep generic + explicit case
+  values = np.linspace(vmin, vmax, K, dtype=np.float32)
+  gamma = 0.99
+  ref = losses.categorical(lt1, lt, values, R, (np.float32(gamma) * D).astype(np.float32))
+  tgt, lps, dl, lm = empty(B, K), empty(B), empty(B, K), empty(1)
+  _capi.call('b200rl_c51_loss', B, K, vmin, vmax, dev(lt1).data_ptr(), dev(lt).data_ptr(), dev(R).data_ptr(),
+             dev(D).data_ptr(), gamma, 1.0 / B, tgt.data_ptr(), lps.data_ptr(), dl.data_ptr(), lm.data_ptr(),
+             _capi.current_stream())
+  torch.cuda.synchronize()
+  close(tgt.cpu().numpy(), ref['target'], name='projected distribution')
+  close(lps.cpu().numpy(), ref['loss'], name='CE loss')
+  close(dl.cpu().numpy(), ref['dlogits_tm1'], atol_scale=1e-5, name='dlogits')
+  close(lm.cpu().numpy()[0], ref['loss'].mean())
+  np.testing.assert_allclose(tgt.cpu().numpy().sum(-1), 1.0, atol=1e-5)   # projection conserves mass
+
+
+def test_c51_atoms_landing_exactly_on_support():
+  import torch
+  from acme_b200 import _capi
+  from oracle import losses
+  B, K, vmin, vmax = 4, 51, -150., 150.
+  values = np.linspace(vmin, vmax, K, dtype=np.float32)
+  lt = np.random.default_rng(0).standard_normal((B, K)).astype(np.float32)
+  R = np.array([0., 6., -12., 400.], np.float32)     # shifts by whole atoms; last row clips to vmax
+  D = np.ones(B, np.float32)
+  ref = losses.categorical(lt, lt, values, R, D)
+  tgt, lps = empty(B, K), empty(B)
+  _capi.call('b200rl_c51_loss', B, K, vmin, vmax, dev(lt).data_ptr(), dev(lt).data_ptr(), dev(R).data_ptr(), dev(D).data_ptr(),
+             1.0, 1.0, tgt.data_ptr(), lps.data_ptr(), None, None, _capi.current_stream())
+  torch.cuda.synchronize()
+  close(tgt.cpu().numpy(), ref['target'])
+  p = losses.softmax(lt)
+  close(tgt.cpu().numpy()[0], p[0])                   # identity shift reproduces the distribution
+  assert abs(tgt.cpu().numpy()[3, -1] - 1.0) < 1e-5   # everything clipped onto vmax
+
+
+def test_c51_mean_and_dpg():
+  import torch
+  from acme_b200 import _capi
+  from oracle import losses
+  rng = np.random.default_rng(3)
+  B, K, A = 33, 51, 21
+  logits = rng.standard_normal((B, K)).astype(np.float32)
+  values = np.linspace(-150, 150, K, dtype=np.float32)
+  p = losses.softmax(logits)
+  q_ref = (p * values).sum(-1)
+  q, dl = empty(B), empty(B, K)
+  _capi.call('b200rl_c51_mean_fwd', B, K, -150., 150., dev(logits).data_ptr(), q.data_ptr(), _capi.current_stream())
+  _capi.call('b200rl_c51_mean_bwd', B, K, -150., 150., dev(logits).data_ptr(), None, dl.data_ptr(), _capi.current_stream())
+  close(q.cpu().numpy(), q_ref, atol_scale=1e-5)
+  close(dl.cpu().numpy(), p * (values[None] - q_ref[:, None]), atol_scale=1e-5)
+  dqda = rng.standard_normal((B, A)).astype(np.float32) * np.linspace(0.01, 3, B, dtype=np.float32)[:, None]
+  da_ref, clipped = losses.dpg_action_grad(dqda, 1.0, True)
+  da, lps, lm = empty(B, A), empty(B), empty(1)
+  _capi.call('b200rl_dpg_action_grad', B, A, dev(dqda).data_ptr(), 1.0, 1, 1.0 / B, da.data_ptr(), lps.data_ptr(),
+             lm.data_ptr(), _capi.current_stream())
+  close(da.cpu().numpy(), da_ref)
+  close(lm.cpu().numpy()[0], 0.5 * (clipped**2).sum(-1).mean())
+
+
+@pytest.mark.parametrize('eps_mode', [0, 1])
+def test_adam_and_global_norm(eps_mode):
+  import torch
+  from acme_b200 import _capi
+  from oracle import learner as olearner
+  from oracle import losses
+  rng = np.random.default_rng(eps_mode)
+  n = 100_003
+  p0 = rng.standard_normal(n).astype(np.float32)
+  opt = olearner.Adam(1e-3, eps_mode=eps_mode)
+  params = {'p': p0.copy()}
+  P = torch.zeros(n + 1, device='cuda')[:n]
+  P.copy_(dev(p0))
+  m, v = torch.zeros_like(P), torch.zeros_like(P)
+  step = torch.zeros(1, dtype=torch.int64, device='cuda')
+  shadow = torch.zeros(n, dtype=torch.bfloat16, device='cuda')
+  for t in range(3):
+    g = (rng.standard_normal(n) * 10.0**rng.integers(-6, 1, n)).astype(np.float32)
+    params = opt.apply({'p': g}, params)
+    _capi.call('b200rl_adam', n, P.data_ptr(), dev(g).data_ptr(), m.data_ptr(), v.data_ptr(), step.data_ptr(), 1e-3, 0.9,
+               0.999, 1e-8, eps_mode, None, shadow.data_ptr(), _capi.current_stream())
+    _capi.call('b200rl_step_increment', step.data_ptr(), _capi.current_stream())
+    close(P.cpu().numpy(), params['p'], name=f'params after step {t}')
+    close(m.cpu().numpy(), opt.m['p'])
+    close(v.cpu().numpy(), opt.v['p'], atol_scale=1e-9)
+  np.testing.assert_array_equal(shadow.float().cpu().numpy(), P.to(torch.bfloat16).float().cpu().numpy())
+  # clip_by_global_norm
+  g = (rng.standard_normal(n) * 3).astype(np.float32)
+  ref, norm = losses.clip_by_global_norm([g], 40.)
+  part, scale, nrm = empty(1024), empty(1), empty(1)
+  _capi.call('b200rl_global_norm_scale', n, dev(g).data_ptr(), 40., part.data_ptr(), scale.data_ptr(), nrm.data_ptr(),
+             _capi.current_stream())
+  close(nrm.cpu().numpy()[0], norm)
+  close(scale.cpu().numpy()[0], 40. / max(norm, 40.))
+
+
+def test_copy_if_period_and_step_counter():
+  import torch
+  from acme_b200 import _capi
+  src, dst = torch.arange(1024, dtype=torch.float32, device='cuda'), torch.zeros(1024, device='cuda')
+  step = torch.zeros(1, dtype=torch.int64, device='cuda')
+  for t in range(7):
+    src += 1
+    _capi.call('b200rl_copy_if_period', 4096, dst.data_ptr(), src.data_ptr(), step.data_ptr(), 3, 0, _capi.current_stream())
+    _capi.call('b200rl_step_increment', step.data_ptr(), _capi.current_stream())
+    expect = (t // 3) * 3 + 1     # copies at steps 0, 3, 6 (dqn/learning.py:157-161)
+    assert float(dst[0]) == expect, (t, float(dst[0]))
+  assert int(step) == 7
+
+
+# ------------------------------------------------------------------------------------ K6 layers
+@pytest.mark.parametrize('H,C,k,s,Cout,u8', [(84, 4, 8, 4, 32, True), (21, 32, 4, 2, 64, False), (11, 64, 3, 1, 64, False),
+                                             (12, 8, 3, 2, 12, False)])
+def test_conv_fwd_wgrad_dgrad_vs_torch_cpu(H, C, k, s, Cout, u8):
+  import torch
+  from acme_b200 import _capi, networks
+  from oracle import nets as onets
+  rng = np.random.default_rng(H + C)
+  B = 5
+  OH, pad = networks.tf_same_pad(H, k, s)
+  g = _capi.ConvGeom(B=B, H=H, W=H, C=C, kh=k, kw=k, stride=s, pad_top=pad, pad_left=pad, OH=OH, OW=OH, Cout=Cout)
+  x_raw = rng.integers(0, 256, (B, H, H, C), dtype=np.uint8) if u8 else rng.standard_normal((B, H, H, C)).astype(np.float32)
+  x_f = (x_raw.astype(np.float32) / np.float32(255)) if u8 else x_raw
+  w_hwio = (rng.standard_normal((k, k, C, Cout)) / np.sqrt(k * k * C)).astype(np.float32)
+  bias = rng.standard_normal(Cout).astype(np.float32)
+  xt = torch.tensor(x_f, requires_grad=True)
+  wt = torch.tensor(w_hwio, requires_grad=True)
+  bt = torch.tensor(bias, requires_grad=True)
+  y_ref = torch.relu(onets._conv_same(xt, wt, bt, s))
+  dy_post = rng.standard_normal(tuple(y_ref.shape)).astype(np.float32)
+  y_ref.backward(torch.tensor(dy_post))
+  ws = empty(64 << 20, dtype=torch.uint8)
+  w_ohwi = dev(w_hwio.transpose(3, 0, 1, 2))
+  y = empty(B, OH, OH, Cout)
+  xd = dev(x_raw)
+  _capi.call('b200rl_conv2d_fwd', xd.data_ptr(), int(u8), w_ohwi.data_ptr(), dev(bias).data_ptr(), y.data_ptr(), g,
+             _capi.ACT_RELU, 0, ws.data_ptr(), ws.numel(), _capi.current_stream())
+  close(y.cpu().numpy(), y_ref.detach().numpy(), name='conv fwd')
+  dy_pre = dev(dy_post * (y_ref.detach().numpy() > 0))
+  dw, db = empty(Cout, k, k, C), empty(Cout)
+  _capi.call('b200rl_conv2d_wgrad', xd.data_ptr(), int(u8), dy_pre.data_ptr(), dw.data_ptr(), db.data_ptr(), g, 0,
+             ws.data_ptr(), ws.numel(), _capi.current_stream())
+  close(dw.cpu().numpy().transpose(1, 2, 3, 0), wt.grad.numpy(), atol_scale=2e-6, name='conv wgrad')
+  close(db.cpu().numpy(), bt.grad.numpy(), atol_scale=2e-6, name='conv bias grad')
+  if C % 4 == 0 and not u8:
+    dx = empty(B, H, H, C)
+    _capi.call('b200rl_conv2d_dgrad', dy_pre.data_ptr(), w_ohwi.data_ptr(), dx.data_ptr(), g, None, 0, 0, ws.data_ptr(),
+               ws.numel(), _capi.current_stream())
+    close(dx.cpu().numpy(), xt.grad.numpy(), atol_scale=2e-6, name='conv dgrad')
+
+
+@pytest.mark.parametrize('M,N,K', [(256, 1024, 7744), (10, 50, 50), (256, 18, 512), (256, 1, 512), (33, 51, 256)])
+def test_linear_fwd_dgrad_wgrad(M, N, K):
+  import torch
+  from acme_b200 import _capi
+  rng = np.random.default_rng(M + N)
+  x = rng.standard_normal((M, K)).astype(np.float32)
+  w = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+  b = rng.standard_normal(N).astype(np.float32)
+  xt, wt, bt = torch.tensor(x, requires_grad=True), torch.tensor(w, requires_grad=True), torch.tensor(b, requires_grad=True)
+  y_ref = torch.nn.functional.elu(xt @ wt.T + bt)
+  dy_post = rng.standard_normal((M, N)).astype(np.float32)
+  y_ref.backward(torch.tensor(dy_post))
+  ws = empty(64 << 20, dtype=torch.uint8)
+  y = empty(M, N)
+  st = _capi.current_stream()
+  _capi.call('b200rl_linear_fwd', M, N, K, dev(x).data_ptr(), K, dev(w).data_ptr(), dev(b).data_ptr(), y.data_ptr(), N,
+             _capi.ACT_ELU, 0, ws.data_ptr(), ws.numel(), st)
+  close(y.cpu().numpy(), y_ref.detach().numpy(), name='linear fwd')
+  dy = dev(dy_post)
+  _capi.call('b200rl_act_bwd', M * N, dy.data_ptr(), y.data_ptr(), _capi.ACT_ELU, st)
+  dx, dw, db = empty(M, K), empty(N, K), empty(N)
+  _capi.call('b200rl_linear_dgrad', M, N, K, dy.data_ptr(), N, dev(w).data_ptr(), dx.data_ptr(), K, None, 0, 0,
+             ws.data_ptr(), ws.numel(), st)
+  _capi.call('b200rl_linear_wgrad', M, N, K, dy.data_ptr(), N, dev(x).data_ptr(), K, dw.data_ptr(), db.data_ptr(), 0,
+             ws.data_ptr(), ws.numel(), st)
+  close(dx.cpu().numpy(), xt.grad.numpy(), atol_scale=2e-6, name='linear dgrad')
+  close(dw.cpu().numpy(), wt.grad.numpy(), atol_scale=2e-6, name='linear wgrad')
+  close(db.cpu().numpy(), bt.grad.numpy(), atol_scale=2e-6, name='linear bias grad')
+
+
+def test_layernorm_tanh_and_small_ops():
+  import torch
+  from acme_b200 import _capi
+  rng = np.random.default_rng(9)
+  B, N = 17, 512
+  x = (rng.standard_normal((B, N)) * 3 + 1).astype(np.float32)
+  sc, of = rng.uniform(0.5, 1.5, N).astype(np.float32), rng.standard_normal(N).astype(np.float32) * 0.1
+  xt, st_, ot = torch.tensor(x, requires_grad=True), torch.tensor(sc, requires_grad=True), torch.tensor(of, requires_grad=True)
+  y_ref = torch.tanh(torch.nn.functional.layer_norm(xt, (N,), st_, ot, eps=1e-5))
+  dy = rng.standard_normal((B, N)).astype(np.float32)
+  y_ref.backward(torch.tensor(dy))
+  y, xh, rs, dx, ds, do = empty(B, N), empty(B, N), empty(B), empty(B, N), empty(N), empty(N)
+  s = _capi.current_stream()
+  _capi.call('b200rl_layernorm_tanh_fwd', B, N, dev(x).data_ptr(), dev(sc).data_ptr(), dev(of).data_ptr(), 1e-5, y.data_ptr(),
+             xh.data_ptr(), rs.data_ptr(), s)
+  _capi.call('b200rl_layernorm_tanh_bwd', B, N, dev(dy).data_ptr(), y.data_ptr(), xh.data_ptr(), rs.data_ptr(),
+             dev(sc).data_ptr(), dx.data_ptr(), ds.data_ptr(), do.data_ptr(), s)
+  close(y.cpu().numpy(), y_ref.detach().numpy(), atol_scale=2e-6)
+  close(dx.cpu().numpy(), xt.grad.numpy(), atol_scale=1e-5)
+  close(ds.cpu().numpy(), st_.grad.numpy(), atol_scale=1e-5)
+  close(do.cpu().numpy(), ot.grad.numpy(), atol_scale=1e-5)
+  # duelling head
+  A = 18
+  val, adv = rng.standard_normal((B, 1)).astype(np.float32), rng.standard_normal((B, A)).astype(np.float32)
+  q = empty(B, A)
+  _capi.call('b200rl_duelling_fwd', B, A, dev(val).data_ptr(), dev(adv).data_ptr(), q.data_ptr(), s)
+  close(q.cpu().numpy(), val + (adv - adv.mean(-1, keepdims=True)))
+  dq = rng.standard_normal((B, A)).astype(np.float32)
+  dv, da = empty(B), empty(B, A)
+  _capi.call('b200rl_duelling_bwd', B, A, dev(dq).data_ptr(), dv.data_ptr(), da.data_ptr(), s)
+  close(dv.cpu().numpy(), dq.sum(-1))
+  close(da.cpu().numpy(), dq - dq.mean(-1, keepdims=True))
+
+
+# ------------------------------------------------------------------------------------ whole nets
+def _dqn_pair(A=18, seed=0):
+  from acme_b200 import networks
+  from oracle import nets as onets
+  net = networks.DQNAtariNetwork(A, seed=seed)
+  onet = onets.DQNAtariNetwork(A)
+  onet.load(net.variables())
+  return net, onet
+
+
+def test_dqn_atari_network_forward_backward():
+  import torch
+  net, onet = _dqn_pair()
+  rng = np.random.default_rng(0)
+  B = 6
+  obs = rng.integers(0, 256, (B, 84, 84, 4), dtype=np.uint8)
+  bufs, gbufs = net.make_buffers(B), net.make_grad_buffers(B)
+  q = net.forward(dev(obs), bufs)
+  q_ref = onet(torch.tensor(obs.astype(np.float32) / np.float32(255)))
+  close(q.cpu().numpy(), q_ref.detach().numpy(), atol_scale=5e-6, name='q values')
+  dq = rng.standard_normal((B, 18)).astype(np.float32)
+  q_ref.backward(torch.tensor(dq))
+  net.backward(dev(obs), bufs, gbufs, dev(dq))
+  got = net.variables(grad=True)
+  for k, v in onet.vars.items():
+    close(got[k], v.grad.numpy(), atol_scale=1e-5, name=f'grad {k}')
+
+
+def test_variable_export_roundtrip():
+  net, onet = _dqn_pair(A=5, seed=3)
+  v = net.variables()
+  assert v['conv2/w'].shape == (4, 4, 32, 64) and v['value/l0/w'].shape == (7744, 512) and v['adv/l1/w'].shape == (512, 5)
+  assert sum(x.size for x in v.values()) == 8_018_611 - (18 - 5) * 513
+  net2 = type(net)(5, seed=99)
+  net2.load_variables(v)
+  for k, x in net2.variables().items():
+    np.testing.assert_array_equal(x, v[k])
+
+
+@pytest.mark.parametrize('use_graph', [False, True])
+def test_dqn_learner_steps_match_oracle(use_graph):
+  """Full update (sample -> gather -> 3 forwards -> TD -> backward -> Adam -> priorities -> target copy)
+  against oracle.learner.DQNOracleLearner fed by oracle.replay on the same uniform draws."""
+  import torch
+  import helpers
+  from acme_b200 import dqn, networks, replay
+  from oracle import learner as olearner
+  from oracle import nets as onets
+  rng = np.random.default_rng(1)
+  shape, A, n, B = (84, 84, 4), 6, 3, 16
+  spec, table, server, adder, oracle = helpers.make_pair(shape, np.uint8, A, n, 0.99, 0.6, max_size=300)
+  for ep in range(8):
+    helpers.feed_episode(rng, adder, oracle, int(rng.integers(5, 30)), n, shape, np.uint8, A)
+  table.flush()
+  helpers.sync_oracle_leaves(table, oracle)
+  net = networks.DQNAtariNetwork(A, seed=5)
+  tgt = net.clone()
+  onet, otgt = onets.DQNAtariNetwork(A), onets.DQNAtariNetwork(A)
+  onet.load(net.variables())
+  otgt.load(net.variables())
+  ds = replay.ReplayDataset(table, B, seed=7)
+  client = replay.Client(server)
+  learner = dqn.DQNLearner(net, tgt, 0.99, 0.2, 1e-3, target_update_period=2, dataset=ds, replay_client=client,
+                           logger=__import__('acme_b200.loggers', fromlist=['x']).NoOpLogger(), use_cuda_graph=use_graph)
+  ol = olearner.DQNOracleLearner(onet, otgt, 0.99, 0.2, 1e-3, 2)
+  counter = torch.zeros(1, dtype=torch.int64, device='cuda')
+  u_dev = torch.empty(B, device='cuda')
+  from acme_b200 import _capi
+  for step in range(5):
+    # the uniforms the learner is about to draw (device Philox keyed by (seed, call counter))
+    _capi.call('b200rl_uniform', u_dev.data_ptr(), B, 7, counter.data_ptr(), step, _capi.current_stream())
+    u = u_dev.cpu().numpy()
+    keys, pos, prob = oracle.sample(u, True)
+    o0, a, R, D, o1 = oracle.gather(pos)
+    ref = ol.step(o0, a, R, D, o1, prob)
+    oracle.update_priorities(keys, ref['priority'])
+    learner.step()
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(ds.idx.cpu().numpy(), pos)
+    np.testing.assert_array_equal(ds.keys.cpu().numpy().view(np.uint64), keys)
+    close(learner.td.cpu().numpy(), ref['td'], atol_scale=2e-5, name=f'td step {step}')
+    close(learner.priority.cpu().numpy(), ref['priority'], atol_scale=2e-5)
+    close(learner.loss.cpu().numpy()[0], ref['loss'], rtol=1e-4)
+    close(learner.weight.cpu().numpy(), ref['weight'])
+    got = net.variables()
+    for k, v in onet.numpy().items():
+      close(got[k], v, rtol=1e-4, atol_scale=2e-5, name=f'param {k} step {step}')
+    gt = tgt.variables()
+    for k, v in otgt.numpy().items():
+      close(gt[k], v, rtol=1e-4, atol_scale=2e-5, name=f'target {k} step {step}')
+    helpers.sync_oracle_leaves_loose(table, oracle)
+  assert learner.num_steps == 5
+  server.stop()
