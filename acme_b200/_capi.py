@@ -31,6 +31,7 @@ class ConvGeom(C.Structure):
 # name -> (restype, argtypes); every symbol declared in include/b200rl.h
 PROTOTYPES = {
     'b200rl_version': (c_int, []),
+    'b200rl_launch_count': (c_u64, []),
     'b200rl_last_error': (C.c_char_p, []),
     'b200rl_device_check': (c_int, [c_int]),
     'b200rl_replay_create': (c_int, [C.POINTER(c_vp), C.POINTER(ReplayCfg)]),

@@ -12,6 +12,7 @@
 namespace b200rl {
 
 void set_error(const char* fmt, ...);
+void count_launch();
 
 #define B200RL_CUDA_OK(expr)                                                              \
   do {                                                                                    \
@@ -32,6 +33,7 @@ void set_error(const char* fmt, ...);
 
 #define B200RL_LAUNCH_OK()                                                                 \
   do {                                                                                     \
+ ::b200rl::count_launch();                                                                \
     cudaError_t _e = cudaGetLastError();                                                   \
     if (_e != cudaSuccess) {                                                               \
       ::b200rl::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \

@@ -17,6 +17,8 @@
 namespace b200rl {
 
 static thread_local std::string g_last_error;
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED); }
 
 void set_error(const char* fmt, ...) {
   char buf[1024];
@@ -222,6 +224,7 @@ static int ensure_device(b200rl_replay* h) {
 }
 
 extern "C" int b200rl_version(void) { return B200RL_VERSION; }
+extern "C" uint64_t b200rl_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 extern "C" const char* b200rl_last_error(void) { return g_last_error.c_str(); }
 
 extern "C" int b200rl_device_check(int device) {
@@ -351,7 +354,6 @@ extern "C" int b200rl_replay_create(b200rl_replay** out, const b200rl_replay_cfg
     Stage& s = h->stage[i];
     bool ok = true;
     if (payload) {
-      ok = ok && cudaMallocHost((void**)&s.h_obs, (size_t)(h->stage_slots * std::max<int64_t>(cfg->obs_bytes, 1))) == cudaSuccess;
       ok = ok && cudaMallocHost((void**)&s.h_fill, h->stage_slots * sizeof(SlotFill)) == cudaSuccess;
       ok = ok && cudaMallocHost((void**)&s.h_act, h->stage_slots * (size_t)h->act_stride) == cudaSuccess;
       ok = ok && cudaMalloc((void**)&s.d_fill, h->stage_slots * sizeof(SlotFill)) == cudaSuccess;
@@ -452,6 +454,11 @@ static int alloc_slot(b200rl_replay* h, const void* obs_host, uint64_t* seq_out)
   if (obs_host && h->n_obs >= h->stage_slots) {
     int rc = flush_impl(h, g_implicit_stream);
     if (rc) return rc;
+  }
+  if (obs_host && !h->stage[h->cur].h_obs) {  // host-observation staging is allocated on first use
+    for (int i = 0; i < 2; ++i)
+      B200RL_CUDA_OK(cudaMallocHost((void**)&h->stage[i].h_obs,
+                                    (size_t)(h->stage_slots * std::max<int64_t>(h->cfg.obs_bytes, 1))));
   }
   uint64_t seq = h->slot_head++;
   if (obs_host) {

@@ -125,25 +125,28 @@ class DQNLearner(core.Learner, core.Saveable):
                _capi.ptr(self._num_steps), self._period, 0, st)
     _capi.call('b200rl_step_increment', _capi.ptr(self._num_steps), st)
 
+  def _eager_step(self, uniforms):
+    lib = _capi.load()
+    n0 = lib.b200rl_launch_count()
+    self._dataset.sample_raw(uniforms)
+    self._forward_loss()
+    if self._world > 1:
+      import torch.distributed as dist
+      dist.all_reduce(self._net.params.grad, op=dist.ReduceOp.SUM, group=self._pg)  # then x 1/R in Adam
+    self._apply()
+    self.kernel_launches_per_step = int(lib.b200rl_launch_count() - n0)
+
   def _device_step(self, uniforms=None):
     torch = self._torch
     if self._world > 1:
-      import torch.distributed as dist
-      self._dataset.sample_raw(uniforms)
-      self._forward_loss()
-      dist.all_reduce(self._net.params.grad, op=dist.ReduceOp.SUM, group=self._pg)  # then x 1/R in Adam
-      self._apply()
+      self._eager_step(uniforms)
       return
     if not self._use_graph or uniforms is not None:
-      self._dataset.sample_raw(uniforms)
-      self._forward_loss()
-      self._apply()
+      self._eager_step(uniforms)
       return
     if self._graphs is None:
       if self._steps_done < 2:          # warm-up un-captured (one-time attribute setup inside the library)
-        self._dataset.sample_raw()
-        self._forward_loss()
-        self._apply()
+        self._eager_step(None)
         return
       g = torch.cuda.CUDAGraph()
       torch.cuda.synchronize()

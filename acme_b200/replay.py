@@ -86,10 +86,10 @@ class _Packer:
     if len(vals) != len(self.leaves):
       raise ValueError('value does not match the table signature')
     for v, (shape, dt, off, n) in zip(vals, self.leaves):
-      a = np.ascontiguousarray(np.asarray(v, dtype=dt))
+      a = np.asarray(v, dtype=dt)
       if a.shape != shape:
         raise ValueError(f'expected shape {shape}, got {a.shape}')
-      row[off:off + n] = a.reshape(-1).view(np.uint8)
+      row[off:off + n] = np.frombuffer(a.tobytes(), np.uint8)
     return row
 
   def unpack_batch(self, rows):

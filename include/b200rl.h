@@ -34,6 +34,8 @@ extern "C" {
 #define B200RL_EARCH (-4)
 
 int b200rl_version(void);
+/* Number of CUDA kernels this library has launched (or recorded into a graph capture) so far. */
+uint64_t b200rl_launch_count(void);
 const char* b200rl_last_error(void);
 /* 0 iff `device` is an sm_100 part this library was built for. */
 int b200rl_device_check(int device);

@@ -15,9 +15,25 @@ def close(got, want, rtol=RTOL, atol_scale=1e-6, name=''):
   np.testing.assert_allclose(got, want, rtol=rtol, atol=atol, err_msg=name)
 
 
+_KEEP = []
+
+
 def dev(x):
+  """Host array -> device tensor that stays alive until the end of the test (raw pointers are passed
+  to the C ABI, so a temporary would be recycled by the caching allocator)."""
   import torch
-  return torch.as_tensor(np.ascontiguousarray(x)).cuda()
+  t = torch.as_tensor(np.ascontiguousarray(x)).cuda()
+  _KEEP.append(t)
+  return t
+
+
+@pytest.fixture(autouse=True)
+def _release_device_tensors():
+  yield
+  import torch
+  if torch.cuda.is_available():
+    torch.cuda.synchronize()
+  _KEEP.clear()
 
 
 def empty(*shape, dtype=None):
@@ -329,7 +345,7 @@ def test_dqn_learner_steps_match_oracle(use_graph):
   from oracle import learner as olearner
   from oracle import nets as onets
   rng = np.random.default_rng(1)
-  shape, A, n, B = (84, 84, 4), 6, 3, 16
+  shape, A, n, B, lr = (84, 84, 4), 6, 3, 16, 1e-3
   spec, table, server, adder, oracle = helpers.make_pair(shape, np.uint8, A, n, 0.99, 0.6, max_size=300)
   for ep in range(8):
     helpers.feed_episode(rng, adder, oracle, int(rng.integers(5, 30)), n, shape, np.uint8, A)
@@ -364,12 +380,18 @@ def test_dqn_learner_steps_match_oracle(use_graph):
     close(learner.priority.cpu().numpy(), ref['priority'], atol_scale=2e-5)
     close(learner.loss.cpu().numpy()[0], ref['loss'], rtol=1e-4)
     close(learner.weight.cpu().numpy(), ref['weight'])
-    got = net.variables()
-    for k, v in onet.numpy().items():
-      close(got[k], v, rtol=1e-4, atol_scale=2e-5, name=f'param {k} step {step}')
-    gt = tgt.variables()
-    for k, v in otgt.numpy().items():
-      close(gt[k], v, rtol=1e-4, atol_scale=2e-5, name=f'target {k} step {step}')
+    # Parameters: Adam's update is lr * m^/(sqrt(v^)+eps) ~ +-lr whenever |g| >> eps, so an element whose
+    # gradient is ~1e-8 turns a 1e-5-relative gradient difference into a visible fraction of lr.  The Adam
+    # kernel itself is pinned to 1e-5 in test_adam_and_global_norm and the gradients in
+    # test_dqn_atari_network_forward_backward; here all but <1e-5 of the parameters must agree to 2% of one
+    # learning-rate step and every one of them to half a step.
+    def params_close(got, want, what):
+      for k, v in want.items():
+        bad = ~np.isclose(got[k], v, rtol=1e-4, atol=0.02 * lr)
+        assert bad.mean() < 1e-5, f'{what} {k} step {step}: {bad.sum()} of {bad.size} outside 2% of lr'
+        np.testing.assert_allclose(got[k], v, rtol=1e-4, atol=0.5 * lr, err_msg=f'{what} {k} step {step}')
+    params_close(net.variables(), onet.numpy(), 'param')
+    params_close(tgt.variables(), otgt.numpy(), 'target')
     helpers.sync_oracle_leaves_loose(table, oracle)
   assert learner.num_steps == 5
   server.stop()
