@@ -8,6 +8,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "gemm_common.cuh"
 
 namespace b200rl {
 
@@ -106,39 +107,6 @@ struct DgradWeights {  // B(red = (ky,kx,co), outer = ci) = w[co][ky][kx][ci]; 4
   }
 };
 
-// ---- epilogue
-struct Epilogue {
-  float* out; int ldo;
-  const float* bias;   // per column, nullable
-  int act;             // applied after bias
-  const float* mask;   // nullable: multiply by act'(mask[row, col])
-  int ldmask; int mask_act;
-  float* partial;      // non-null: split-K partial sums [split][M][N], epilogue deferred
-};
-
-__device__ __forceinline__ float apply_act(float v, int act) {
-  switch (act) {
-    case B200RL_ACT_RELU: return fmaxf(v, 0.f);
-    case B200RL_ACT_ELU: return v > 0.f ? v : expm1f(v);
-    case B200RL_ACT_TANH: return tanhf(v);
-    default: return v;
-  }
-}
-__device__ __forceinline__ float act_grad_out(float y, int act) {
-  switch (act) {
-    case B200RL_ACT_RELU: return y > 0.f ? 1.f : 0.f;
-    case B200RL_ACT_ELU: return y > 0.f ? 1.f : y + 1.f;
-    case B200RL_ACT_TANH: return 1.f - y * y;
-    default: return 1.f;
-  }
-}
-__device__ __forceinline__ void finish(const Epilogue& e, int row, int col, float acc) {
-  if (e.bias) acc += e.bias[col];
-  acc = apply_act(acc, e.act);
-  if (e.mask) acc *= act_grad_out(e.mask[(size_t)row * e.ldmask + col], e.mask_act);
-  e.out[(size_t)row * e.ldo + col] = acc;
-}
-
 template <class AL, class BL>
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_kernel(AL a, BL b, Epilogue epi, int M, int N, int K, int k_per_split) {
@@ -228,20 +196,37 @@ __global__ void splitk_finish_kernel(Epilogue epi, int M, int N, int splits) {
   finish(epi, row, col, acc);
 }
 
-__global__ void colsum_kernel(int M, int N, const float* __restrict__ x, int ld, float* __restrict__ out) {
-  // out[n] = sum_m x[m, n]; block = 32 columns x 8 row-lanes, fixed-order tree over the 8 lanes
+// out[n] = sum_m x[m, n].  Rows are split over gridDim.y CTAs (each a 32-column x 8-row-lane tile with a
+// fixed-order tree), partial sums go to `partial` [gridDim.y][N] and a second pass adds them in
+// order: deterministic and parallel over the (long) row dimension.
+__global__ void colsum_partial_kernel(int M, int N, const float* __restrict__ x, int ld, int rows_per_block,
+                                      float* __restrict__ partial) {
   __shared__ float part[8][33];
   const int col = blockIdx.x * 32 + threadIdx.x;
+  const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
   float s = 0.f;
   if (col < N)
-    for (int m = threadIdx.y; m < M; m += 8) s += x[(size_t)m * ld + col];
+    for (int m = m0 + threadIdx.y; m < m1; m += 8) s += x[(size_t)m * ld + col];
   part[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && col < N) {
     float t = 0.f;
     for (int r = 0; r < 8; ++r) t += part[r][threadIdx.x];
-    out[col] = t;
+    partial[(size_t)blockIdx.y * N + col] = t;
   }
+}
+__global__ void colsum_finish_kernel(int N, int splits, const float* __restrict__ partial, float* __restrict__ out) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= N) return;
+  float t = 0.f;
+  for (int s = 0; s < splits; ++s) t += partial[(size_t)s * N + col];
+  out[col] = t;
+}
+
+int launch_splitk_finish(const Epilogue& epi, int M, int N, int splits, cudaStream_t stream) {
+  splitk_finish_kernel<<<(int)ceil_div<long long>((long long)M * N, 256), 256, 0, stream>>>(epi, M, N, splits);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
 }
 
 template <class AL, class BL>
@@ -270,8 +255,20 @@ static int launch_gemm(const AL& a, const BL& b, Epilogue epi, int M, int N, int
   return B200RL_OK;
 }
 
-static int launch_colsum(int M, int N, const float* x, int ld, float* out, cudaStream_t stream) {
-  colsum_kernel<<<ceil_div(N, 32), dim3(32, 8), 0, stream>>>(M, N, x, ld, out);
+int launch_colsum(int M, int N, const float* x, int ld, float* out, void* ws, int64_t ws_bytes, cudaStream_t stream) {
+  const int col_blocks = ceil_div(N, 32);
+  int splits = std::max(1, std::min(ceil_div(M, 64), (2 * kNumSMs) / col_blocks));
+  splits = (int)std::min<int64_t>(splits, ws ? ws_bytes / ((int64_t)N * 4) : 1);
+  if (splits <= 1) {
+    colsum_partial_kernel<<<dim3(col_blocks, 1), dim3(32, 8), 0, stream>>>(M, N, x, ld, M, out);
+    B200RL_LAUNCH_OK();
+    return B200RL_OK;
+  }
+  const int rpb = ceil_div(M, splits);
+  splits = ceil_div(M, rpb);
+  colsum_partial_kernel<<<dim3(col_blocks, splits), dim3(32, 8), 0, stream>>>(M, N, x, ld, rpb, (float*)ws);
+  B200RL_LAUNCH_OK();
+  colsum_finish_kernel<<<ceil_div(N, 128), 128, 0, stream>>>(N, splits, (const float*)ws, out);
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }
@@ -281,24 +278,24 @@ int simt_linear_fwd(int M, int N, int K, const float* x, int ldx, const float* w
                     int ldy, int act, void* ws, int64_t wsb, cudaStream_t s) {
   DenseRed a{x, ldx, M, K};
   DenseRed b{w, K, N, K};
-  Epilogue e{y, ldy, bias, act, nullptr, 0, 0, nullptr};
+  Epilogue e{y, ldy, bias, act, nullptr, 0, 0, nullptr, 0};
   return launch_gemm(a, b, e, M, N, K, ws, wsb, s);
 }
 int simt_linear_dgrad(int M, int N, int K, const float* dy, int lddy, const float* w, float* dx, int lddx,
                       const float* mask, int ldmask, int mask_act, void* ws, int64_t wsb, cudaStream_t s) {
   DenseRed a{dy, lddy, M, N};        // rows m, red n
   DenseOuter b{w, K, K, N};          // (outer = k, red = n) at w[n*K + k]
-  Epilogue e{dx, lddx, nullptr, 0, mask, ldmask, mask_act, nullptr};
+  Epilogue e{dx, lddx, nullptr, 0, mask, ldmask, mask_act, nullptr, 0};
   return launch_gemm(a, b, e, M, K, N, ws, wsb, s);
 }
 int simt_linear_wgrad(int M, int N, int K, const float* dy, int lddy, const float* x, int ldx, float* dw, float* db,
                       void* ws, int64_t wsb, cudaStream_t s) {
   DenseOuter a{dy, lddy, N, M};      // (outer = n, red = m) at dy[m*ld + n]
   DenseOuter b{x, ldx, K, M};        // (outer = k, red = m) at x[m*ld + k]
-  Epilogue e{dw, K, nullptr, 0, nullptr, 0, 0, nullptr};
+  Epilogue e{dw, K, nullptr, 0, nullptr, 0, 0, nullptr, 0};
   int rc = launch_gemm(a, b, e, N, K, M, ws, wsb, s);
   if (rc) return rc;
-  if (db) return launch_colsum(M, N, dy, lddy, db, s);
+  if (db) return launch_colsum(M, N, dy, lddy, db, ws, wsb, s);
   return B200RL_OK;
 }
 int simt_conv_fwd(const void* x, int x_u8, const float* w, const float* bias, float* y, const b200rl_conv_geom& g,
@@ -306,7 +303,7 @@ int simt_conv_fwd(const void* x, int x_u8, const float* w, const float* bias, fl
   const int M = g.B * g.OH * g.OW, K = g.kh * g.kw * g.C;
   Im2colRows a; a.x = x; a.u8 = x_u8; a.g = g; a.Mtot = M; a.Ktot = K;
   DenseRed b{w, K, g.Cout, K};
-  Epilogue e{y, g.Cout, bias, act, nullptr, 0, 0, nullptr};
+  Epilogue e{y, g.Cout, bias, act, nullptr, 0, 0, nullptr, 0};
   return launch_gemm(a, b, e, M, g.Cout, K, ws, wsb, s);
 }
 int simt_conv_wgrad(const void* x, int x_u8, const float* dy, float* dw, float* db, const b200rl_conv_geom& g,
@@ -314,10 +311,10 @@ int simt_conv_wgrad(const void* x, int x_u8, const float* dy, float* dw, float* 
   const int M = g.B * g.OH * g.OW, K = g.kh * g.kw * g.C;
   DenseOuter a{dy, g.Cout, g.Cout, M};                 // (outer = co, red = m)
   Im2colCols b; b.x = x; b.u8 = x_u8; b.g = g; b.Mtot = M; b.Ktot = K;
-  Epilogue e{dw, K, nullptr, 0, nullptr, 0, 0, nullptr};
+  Epilogue e{dw, K, nullptr, 0, nullptr, 0, 0, nullptr, 0};
   int rc = launch_gemm(a, b, e, g.Cout, K, M, ws, wsb, s);
   if (rc) return rc;
-  if (db) return launch_colsum(M, g.Cout, dy, g.Cout, db, s);
+  if (db) return launch_colsum(M, g.Cout, dy, g.Cout, db, ws, wsb, s);
   return B200RL_OK;
 }
 int simt_conv_dgrad(const float* dy, const float* w, float* dx, const b200rl_conv_geom& g, const float* mask,
@@ -325,7 +322,7 @@ int simt_conv_dgrad(const float* dy, const float* w, float* dx, const b200rl_con
   const int Min = g.B * g.H * g.W, R = g.kh * g.kw * g.Cout;
   DgradRows a{dy, g, Min, R};
   DgradWeights b{w, g, R};
-  Epilogue e{dx, g.C, nullptr, 0, mask, g.C, mask_act, nullptr};
+  Epilogue e{dx, g.C, nullptr, 0, mask, g.C, mask_act, nullptr, 0};
   return launch_gemm(a, b, e, Min, g.C, R, ws, wsb, s);
 }
 

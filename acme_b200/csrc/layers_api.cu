@@ -16,6 +16,18 @@ int simt_conv_wgrad(const void* x, int x_u8, const float* dy, float* dw, float* 
                     void* ws, int64_t wsb, cudaStream_t s);
 int simt_conv_dgrad(const float* dy, const float* w, float* dx, const b200rl_conv_geom& g, const float* mask,
                     int mask_act, void* ws, int64_t wsb, cudaStream_t s);
+int tc_linear_fwd(int M, int N, int K, const float* x, int ldx, const float* w, const float* bias, float* y,
+                  int ldy, int act, void* ws, int64_t wsb, cudaStream_t s);
+int tc_linear_dgrad(int M, int N, int K, const float* dy, int lddy, const float* w, float* dx, int lddx,
+                    const float* mask, int ldmask, int mask_act, void* ws, int64_t wsb, cudaStream_t s);
+int tc_linear_wgrad(int M, int N, int K, const float* dy, int lddy, const float* x, int ldx, float* dw, float* db,
+                    void* ws, int64_t wsb, cudaStream_t s);
+int tc_conv_fwd(const void* x, int x_u8, const float* w, const float* bias, float* y, const b200rl_conv_geom& g,
+                int act, void* ws, int64_t wsb, cudaStream_t s);
+int tc_conv_wgrad(const void* x, int x_u8, const float* dy, float* dw, float* db, const b200rl_conv_geom& g,
+                  void* ws, int64_t wsb, cudaStream_t s);
+int tc_conv_dgrad(const float* dy, const float* w, float* dx, const b200rl_conv_geom& g, const float* mask,
+                  int mask_act, void* ws, int64_t wsb, cudaStream_t s);
 }  // namespace b200rl
 
 using namespace b200rl;
@@ -29,44 +41,52 @@ static int check_geom(const b200rl_conv_geom* g) {
   return B200RL_OK;
 }
 
-#define PRECISION_SWITCH(simt_call)                                                            \
+#define PRECISION_SWITCH(simt_call, tc_call)                                                   \
   if (precision == 0) return simt_call;                                                        \
-  set_error("precision %d is not available for this call in this build (0 = fp32 SIMT)", precision); \
+  if (precision == 1) return tc_call;                                                          \
+  set_error("unknown precision %d (0 = fp32 SIMT, 1 = bf16 tcgen05)", precision);             \
   return B200RL_EINVAL;
 
 extern "C" int b200rl_conv2d_fwd(const void* x, int x_u8, const float* w, const float* bias, float* y,
                                  const b200rl_conv_geom* g, int act, int precision, void* ws, int64_t wsb, void* stream) {
   B200RL_REQUIRE(x && w && y, "null argument");
   if (int rc = check_geom(g)) return rc;
-  PRECISION_SWITCH(simt_conv_fwd(x, x_u8, w, bias, y, *g, act, ws, wsb, as_stream(stream)));
+  PRECISION_SWITCH(simt_conv_fwd(x, x_u8, w, bias, y, *g, act, ws, wsb, as_stream(stream)),
+                   tc_conv_fwd(x, x_u8, w, bias, y, *g, act, ws, wsb, as_stream(stream)));
 }
 extern "C" int b200rl_conv2d_wgrad(const void* x, int x_u8, const float* dy, float* dw, float* db,
                                    const b200rl_conv_geom* g, int precision, void* ws, int64_t wsb, void* stream) {
   B200RL_REQUIRE(x && dy && dw, "null argument");
   if (int rc = check_geom(g)) return rc;
-  PRECISION_SWITCH(simt_conv_wgrad(x, x_u8, dy, dw, db, *g, ws, wsb, as_stream(stream)));
+  PRECISION_SWITCH(simt_conv_wgrad(x, x_u8, dy, dw, db, *g, ws, wsb, as_stream(stream)),
+                   tc_conv_wgrad(x, x_u8, dy, dw, db, *g, ws, wsb, as_stream(stream)));
 }
 extern "C" int b200rl_conv2d_dgrad(const float* dy, const float* w, float* dx, const b200rl_conv_geom* g,
                                    const float* mask_y, int mask_act, int precision, void* ws, int64_t wsb, void* stream) {
   B200RL_REQUIRE(dy && w && dx, "null argument");
   if (int rc = check_geom(g)) return rc;
-  PRECISION_SWITCH(simt_conv_dgrad(dy, w, dx, *g, mask_y, mask_act, ws, wsb, as_stream(stream)));
+  B200RL_REQUIRE(precision != 1 || (g->Cout % 8 == 0 && g->C % 8 == 0), "bf16 conv dgrad needs C %% 8 == 0 and Cout %% 8 == 0");
+  PRECISION_SWITCH(simt_conv_dgrad(dy, w, dx, *g, mask_y, mask_act, ws, wsb, as_stream(stream)),
+                   tc_conv_dgrad(dy, w, dx, *g, mask_y, mask_act, ws, wsb, as_stream(stream)));
 }
 extern "C" int b200rl_linear_fwd(int32_t M, int32_t N, int32_t K, const float* x, int32_t ldx, const float* w,
                                  const float* bias, float* y, int32_t ldy, int act, int precision, void* ws,
                                  int64_t wsb, void* stream) {
   B200RL_REQUIRE(x && w && y && M >= 1 && N >= 1 && K >= 1 && ldx >= K && ldy >= N, "bad argument");
-  PRECISION_SWITCH(simt_linear_fwd(M, N, K, x, ldx, w, bias, y, ldy, act, ws, wsb, as_stream(stream)));
+  PRECISION_SWITCH(simt_linear_fwd(M, N, K, x, ldx, w, bias, y, ldy, act, ws, wsb, as_stream(stream)),
+                   tc_linear_fwd(M, N, K, x, ldx, w, bias, y, ldy, act, ws, wsb, as_stream(stream)));
 }
 extern "C" int b200rl_linear_dgrad(int32_t M, int32_t N, int32_t K, const float* dy, int32_t lddy, const float* w,
                                    float* dx, int32_t lddx, const float* mask_y, int mask_act, int precision,
                                    void* ws, int64_t wsb, void* stream) {
   B200RL_REQUIRE(dy && w && dx && M >= 1 && N >= 1 && K >= 1 && lddy >= N && lddx >= K, "bad argument");
-  PRECISION_SWITCH(simt_linear_dgrad(M, N, K, dy, lddy, w, dx, lddx, mask_y, lddx, mask_act, ws, wsb, as_stream(stream)));
+  PRECISION_SWITCH(simt_linear_dgrad(M, N, K, dy, lddy, w, dx, lddx, mask_y, lddx, mask_act, ws, wsb, as_stream(stream)),
+                   tc_linear_dgrad(M, N, K, dy, lddy, w, dx, lddx, mask_y, lddx, mask_act, ws, wsb, as_stream(stream)));
 }
 extern "C" int b200rl_linear_wgrad(int32_t M, int32_t N, int32_t K, const float* dy, int32_t lddy, const float* x,
                                    int32_t ldx, float* dw, float* db, int precision, void* ws, int64_t wsb, void* stream) {
   B200RL_REQUIRE(dy && x && dw && M >= 1 && N >= 1 && K >= 1 && lddy >= N && ldx >= K, "bad argument");
-  PRECISION_SWITCH(simt_linear_wgrad(M, N, K, dy, lddy, x, ldx, dw, db, ws, wsb, as_stream(stream)));
+  PRECISION_SWITCH(simt_linear_wgrad(M, N, K, dy, lddy, x, ldx, dw, db, ws, wsb, as_stream(stream)),
+                   tc_linear_wgrad(M, N, K, dy, lddy, x, ldx, dw, db, ws, wsb, as_stream(stream)));
 }
 extern "C" int64_t b200rl_workspace_bytes(int64_t max_out_elems) { return 64 * max_out_elems * 4; }

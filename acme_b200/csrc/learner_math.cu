@@ -356,6 +356,88 @@ __global__ void duelling_bwd_kernel(int B, int A, const float* __restrict__ dq, 
   for (int a = 0; a < A; ++a) dadv[(size_t)b * A + a] = dq[(size_t)b * A + a] - mean;
 }
 
+
+// Fused duelling head (acme/tf/networks/duelling.py:37-59): value = h[:, :H] . wv + bv, adv = h[:, H:] . wa^T + ba,
+// q = value + (adv - mean(adv)).  One warp per sample; the 2H-wide hidden row is read once.
+__global__ void __launch_bounds__(256)
+duelling_head_fwd_kernel(int B, int A, int H, const float* __restrict__ h, int ldh, const float* __restrict__ wv,
+                         const float* __restrict__ bv, const float* __restrict__ wa, const float* __restrict__ ba,
+                         float* __restrict__ val, float* __restrict__ adv, float* __restrict__ q) {
+  const int lane = threadIdx.x & 31;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= B) return;
+  const float* hv = h + (size_t)b * ldh;
+  const float* ha = hv + H;
+  float sv = 0.f;
+  for (int k = lane; k < H; k += 32) sv = fmaf(hv[k], __ldg(wv + k), sv);
+  for (int d = 16; d > 0; d >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, d);
+  sv += bv[0];
+  float mine = 0.f, total = 0.f;   // lane a keeps advantage a (A <= 32 handled per chunk of 32)
+  for (int a0 = 0; a0 < A; a0 += 32) {
+    for (int a = a0; a < min(A, a0 + 32); ++a) {
+      float s = 0.f;
+      const float* w = wa + (size_t)a * H;
+      for (int k = lane; k < H; k += 32) s = fmaf(ha[k], __ldg(w + k), s);
+      for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+      s += ba[a];
+      total += s;
+      if (lane == (a & 31)) { mine = s; adv[(size_t)b * A + a] = s; }
+    }
+  }
+  const float mean = total / (float)A;
+  if (lane == 0) val[b] = sv;
+  if (A <= 32) {
+    if (lane < A) q[(size_t)b * A + lane] = sv + (mine - mean);
+  } else {
+    __syncwarp();
+    for (int a = lane; a < A; a += 32) q[(size_t)b * A + a] = sv + (adv[(size_t)b * A + a] - mean);
+  }
+}
+
+// backward, part 1 (warp per sample): dval = sum_a dq, dadv = dq - mean(dq), and
+// dh = [dval * wv, dadv @ wa] * relu'(h)
+__global__ void __launch_bounds__(256)
+duelling_head_bwd_dh_kernel(int B, int A, int H, const float* __restrict__ dq, const float* __restrict__ h, int ldh,
+                            const float* __restrict__ wv, const float* __restrict__ wa, float* __restrict__ dval,
+                            float* __restrict__ dadv, float* __restrict__ dh, int lddh) {
+  const int lane = threadIdx.x & 31;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= B) return;
+  float s = 0.f;
+  for (int a = lane; a < A; a += 32) s += dq[(size_t)b * A + a];
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  const float mean = s / (float)A;
+  for (int a = lane; a < A; a += 32) dadv[(size_t)b * A + a] = dq[(size_t)b * A + a] - mean;
+  if (lane == 0) dval[b] = s;
+  const float* hr = h + (size_t)b * ldh;
+  float* dr = dh + (size_t)b * lddh;
+  for (int k = lane; k < H; k += 32) {
+    dr[k] = hr[k] > 0.f ? s * __ldg(wv + k) : 0.f;
+    float acc = 0.f;
+    for (int a = 0; a < A; ++a) acc = fmaf(dq[(size_t)b * A + a] - mean, __ldg(wa + (size_t)a * H + k), acc);
+    dr[H + k] = hr[H + k] > 0.f ? acc : 0.f;
+  }
+}
+// backward, part 2 (thread per weight): dwv[k] = sum_b dval[b] h[b,k], dwa[a,k] = sum_b dadv[b,a] h[b,H+k], biases
+__global__ void __launch_bounds__(128)
+duelling_head_bwd_dw_kernel(int B, int A, int H, const float* __restrict__ dval, const float* __restrict__ dadv,
+                            const float* __restrict__ h, int ldh, float* __restrict__ dwv, float* __restrict__ dbv,
+                            float* __restrict__ dwa, float* __restrict__ dba) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int a = (int)blockIdx.y - 1;   // -1 = value stream
+  if (k >= H) return;
+  float acc = 0.f, bsum = 0.f;
+  if (a < 0) {
+    for (int b = 0; b < B; ++b) { const float g = dval[b]; acc = fmaf(g, h[(size_t)b * ldh + k], acc); bsum += g; }
+    dwv[k] = acc;
+    if (k == 0) dbv[0] = bsum;
+  } else {
+    for (int b = 0; b < B; ++b) { const float g = dadv[(size_t)b * A + a]; acc = fmaf(g, h[(size_t)b * ldh + H + k], acc); bsum += g; }
+    dwa[(size_t)a * H + k] = acc;
+    if (k == 0) dba[a] = bsum;
+  }
+}
+
 // snt.LayerNorm(axis=slice(1,None), scale, offset) + tanh (acme/tf/networks/continuous.py:55-58); CTA per row
 __global__ void __launch_bounds__(256)
 layernorm_tanh_fwd_kernel(int N, const float* __restrict__ x, const float* __restrict__ scale,
@@ -597,6 +679,27 @@ extern "C" int b200rl_duelling_fwd(int32_t B, int32_t A, const float* value, con
 extern "C" int b200rl_duelling_bwd(int32_t B, int32_t A, const float* dq, float* dvalue, float* dadv, void* stream) {
   B200RL_REQUIRE(dq && dvalue && dadv && B >= 1 && A >= 1, "bad argument");
   duelling_bwd_kernel<<<ceil_div(B, 128), 128, 0, as_stream(stream)>>>(B, A, dq, dvalue, dadv);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+
+
+extern "C" int b200rl_duelling_head_fwd(int32_t B, int32_t A, int32_t H, const float* h, int32_t ldh, const float* wv,
+                                        const float* bv, const float* wa, const float* ba, float* value, float* adv,
+                                        float* q, void* stream) {
+  B200RL_REQUIRE(h && wv && bv && wa && ba && value && adv && q && B >= 1 && A >= 1 && H >= 1 && ldh >= 2 * H, "bad argument");
+  duelling_head_fwd_kernel<<<ceil_div(B * 32, 256), 256, 0, as_stream(stream)>>>(B, A, H, h, ldh, wv, bv, wa, ba, value, adv, q);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+extern "C" int b200rl_duelling_head_bwd(int32_t B, int32_t A, int32_t H, const float* dq, const float* h, int32_t ldh,
+                                        const float* wv, const float* wa, float* dvalue, float* dadv, float* dh,
+                                        int32_t lddh, float* dwv, float* dbv, float* dwa, float* dba, void* stream) {
+  B200RL_REQUIRE(dq && h && wv && wa && dvalue && dadv && dh && dwv && dbv && dwa && dba, "null argument");
+  B200RL_REQUIRE(B >= 1 && A >= 1 && H >= 1 && ldh >= 2 * H && lddh >= 2 * H, "bad shape");
+  duelling_head_bwd_dh_kernel<<<ceil_div(B * 32, 256), 256, 0, as_stream(stream)>>>(B, A, H, dq, h, ldh, wv, wa, dvalue, dadv, dh, lddh);
+  B200RL_LAUNCH_OK();
+  duelling_head_bwd_dw_kernel<<<dim3(ceil_div(H, 128), A + 1), 128, 0, as_stream(stream)>>>(B, A, H, dvalue, dadv, h, ldh, dwv, dbv, dwa, dba);
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }

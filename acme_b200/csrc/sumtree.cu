@@ -209,10 +209,24 @@ scatter_small_kernel(TreeView t, ScatterSrc src, const ReplayState* __restrict__
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int l = t.L; l >= 1; --l) {
     const int shift = 5 * (t.L - l + 1);
-    for (int e = warp; e < n; e += nwarps) {
-      int p = spos[e];
-      if (p < 0) continue;
-      recompute_parent(t, l, (long long)p >> shift, lane);
+    // each warp owns entries warp, warp + nwarps, ...; the (independent) node loads of up to 8 entries
+    // are issued before the first scan so that their latencies overlap
+    for (int e0 = warp; e0 < n; e0 += nwarps * 8) {
+      float c[8];
+      long long g[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int e = e0 + j * nwarps;
+        const int p = e < n ? spos[e] : -1;
+        g[j] = p < 0 ? -1 : ((long long)p >> shift);
+        c[j] = g[j] < 0 ? 0.f : t.lvl[l][g[j] * kFanout + lane];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (g[j] < 0) continue;
+        float p = warp_ks_scan(c[j], lane);
+        if (lane == 31) t.lvl[l - 1][l == 1 ? 0 : g[j]] = p;
+      }
     }
     __syncthreads();
   }
@@ -287,9 +301,7 @@ static int tree_scatter_impl(const TreeView& t, const ScatterSrc& src, const Rep
                              cudaStream_t stream) {
   if (n <= 0) return B200RL_OK;
   if (n <= 1024) {
-    int threads = ((n + 31) / 32) * 32;
-    if (threads < 128) threads = 128;
-    scatter_small_kernel<<<1, threads, 0, stream>>>(t, src, st_dev, n);
+    scatter_small_kernel<<<1, 1024, 0, stream>>>(t, src, st_dev, n);   // 32 warps share the per-level node recomputes
     B200RL_LAUNCH_OK();
     return B200RL_OK;
   }

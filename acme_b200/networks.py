@@ -250,11 +250,8 @@ class DQNAtariNetwork(Network):
       x, x_u8 = y.data_ptr(), 0
     h = bufs['h']
     _linear(B, 1024, self.flat_dim, x, self.flat_dim, P.p('fc1.w'), P.p('fc1.b'), h.data_ptr(), 1024, ACT_RELU, self)
-    _linear(B, 1, 512, h.data_ptr(), 1024, P.p('v2.w'), P.p('v2.b'), bufs['val'].data_ptr(), 1, ACT_NONE, self)
-    _linear(B, self.A, 512, h.data_ptr() + 512 * 4, 1024, P.p('a2.w'), P.p('a2.b'), bufs['adv'].data_ptr(),
-            self.A, ACT_NONE, self)
-    _capi.call('b200rl_duelling_fwd', B, self.A, bufs['val'].data_ptr(), bufs['adv'].data_ptr(),
-               bufs['q'].data_ptr(), st)
+    _capi.call('b200rl_duelling_head_fwd', B, self.A, 512, h.data_ptr(), 1024, P.p('v2.w'), P.p('v2.b'), P.p('a2.w'),
+               P.p('a2.b'), bufs['val'].data_ptr(), bufs['adv'].data_ptr(), bufs['q'].data_ptr(), st)
     return bufs['q']
 
   def backward(self, obs, bufs, gbufs, dq):
@@ -263,13 +260,10 @@ class DQNAtariNetwork(Network):
     B, P, st = bufs['B'], self.params, _capi.current_stream()
     ws, wsb = self.ws
     h = bufs['h']
-    _capi.call('b200rl_duelling_bwd', B, self.A, dq.data_ptr(), gbufs['dval'].data_ptr(),
-               gbufs['dadv'].data_ptr(), st)
-    dval, dadv, dh = gbufs['dval'].data_ptr(), gbufs['dadv'].data_ptr(), gbufs['dh'].data_ptr()
-    _linear_wgrad(B, 1, 512, dval, 1, h.data_ptr(), 1024, P.g('v2.w'), P.g('v2.b'), self)
-    _linear_wgrad(B, self.A, 512, dadv, self.A, h.data_ptr() + 2048, 1024, P.g('a2.w'), P.g('a2.b'), self)
-    _linear_dgrad(B, 1, 512, dval, 1, P.p('v2.w'), dh, 1024, h.data_ptr(), ACT_RELU, self)
-    _linear_dgrad(B, self.A, 512, dadv, self.A, P.p('a2.w'), dh + 2048, 1024, h.data_ptr() + 2048, ACT_RELU, self)
+    dh = gbufs['dh'].data_ptr()
+    _capi.call('b200rl_duelling_head_bwd', B, self.A, 512, dq.data_ptr(), h.data_ptr(), 1024, P.p('v2.w'), P.p('a2.w'),
+               gbufs['dval'].data_ptr(), gbufs['dadv'].data_ptr(), dh, 1024, P.g('v2.w'), P.g('v2.b'), P.g('a2.w'),
+               P.g('a2.b'), st)
     y3 = bufs['y3']
     _linear_wgrad(B, 1024, self.flat_dim, dh, 1024, y3.data_ptr(), self.flat_dim, P.g('fc1.w'), P.g('fc1.b'), self)
     _linear_dgrad(B, 1024, self.flat_dim, dh, 1024, P.p('fc1.w'), gbufs['dy3'].data_ptr(), self.flat_dim,

@@ -220,6 +220,15 @@ int b200rl_act_bwd(int64_t n, float* dy, const float* y, int act, void* stream);
 /* duelling head (duelling.py:51-59): q = v + (adv - mean(adv)); bwd: dv = sum dq, dadv = dq - mean(dq) */
 int b200rl_duelling_fwd(int32_t B, int32_t A, const float* value, const float* adv, float* q, void* stream);
 int b200rl_duelling_bwd(int32_t B, int32_t A, const float* dq, float* dvalue, float* dadv, void* stream);
+/* whole duelling head in one pass over the hidden row h[B, 2H] (value stream = first H columns):
+ * value = h[:, :H].wv + bv, adv = h[:, H:] @ wa^T + ba, q as above (duelling.py:37-59); the backward
+ * also applies relu'(h) to dh and produces the four parameter gradients. */
+int b200rl_duelling_head_fwd(int32_t B, int32_t A, int32_t H, const float* h, int32_t ldh, const float* wv,
+                             const float* bv, const float* wa, const float* ba, float* value, float* adv,
+                             float* q, void* stream);
+int b200rl_duelling_head_bwd(int32_t B, int32_t A, int32_t H, const float* dq, const float* h, int32_t ldh,
+                             const float* wv, const float* wa, float* dvalue, float* dadv, float* dh,
+                             int32_t lddh, float* dwv, float* dbv, float* dwa, float* dba, void* stream);
 /* snt.LayerNorm(axis=1:, scale, offset, eps=1e-5) followed by tanh (continuous.py:55-58) */
 int b200rl_layernorm_tanh_fwd(int32_t B, int32_t N, const float* x, const float* scale,
                               const float* offset, float eps, float* y, float* xhat, float* rstd,
