@@ -85,7 +85,7 @@ PROTOTYPES = {
     'b200rl_duelling_bwd': (c_int, [c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     'b200rl_duelling_head_fwd': (c_int, [c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'b200rl_duelling_head_bwd': (c_int, [c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp,
-                                          c_vp, c_vp, c_vp]),
+                                          c_vp, c_vp, c_vp, c_i64, c_vp]),
     'b200rl_layernorm_tanh_fwd': (c_int, [c_i32, c_i32, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp]),
     'b200rl_layernorm_tanh_bwd': (c_int, [c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'b200rl_tanh_to_spec_fwd': (c_int, [c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),

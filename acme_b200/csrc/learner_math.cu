@@ -2,6 +2,8 @@
 // K7 (Adam, global-norm clip, target copy) and the small element-wise pieces of the networks.
 // Each kernel cites the reference lines it restates; all are HBM-bound and deterministic
 // (fixed-order reductions, no atomics).
+#include <algorithm>
+
 #include "common.cuh"
 
 #include <cuda_bf16.h>
@@ -358,36 +360,56 @@ __global__ void duelling_bwd_kernel(int B, int A, const float* __restrict__ dq, 
 
 
 // Fused duelling head (acme/tf/networks/duelling.py:37-59): value = h[:, :H] . wv + bv, adv = h[:, H:] . wa^T + ba,
-// q = value + (adv - mean(adv)).  One warp per sample; the 2H-wide hidden row is read once.
+// q = value + (adv - mean(adv)).  One warp per sample: the 2H-wide hidden row sits in registers (H = 32 * HPL),
+// the weight rows stream through with HPL independent loads in flight per dot product.
+// The (A+1) x H weight rows are staged in shared memory once per CTA (one coalesced sweep, all loads
+// independent) so that the per-sample dot products never wait on L2.
+__device__ __forceinline__ void stage_head_weights(float* sw, const float* __restrict__ wv, const float* __restrict__ wa,
+                                                   int A, int H) {
+  const int nv = H / 4, na = A * H / 4;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) reinterpret_cast<float4*>(sw)[i] = __ldg(reinterpret_cast<const float4*>(wv) + i);
+  for (int i = threadIdx.x; i < na; i += blockDim.x) reinterpret_cast<float4*>(sw + H)[i] = __ldg(reinterpret_cast<const float4*>(wa) + i);
+  __syncthreads();
+}
+
+template <int HPL>
 __global__ void __launch_bounds__(256)
-duelling_head_fwd_kernel(int B, int A, int H, const float* __restrict__ h, int ldh, const float* __restrict__ wv,
+duelling_head_fwd_kernel(int B, int A, const float* __restrict__ h, int ldh, const float* __restrict__ wv,
                          const float* __restrict__ bv, const float* __restrict__ wa, const float* __restrict__ ba,
                          float* __restrict__ val, float* __restrict__ adv, float* __restrict__ q) {
+  constexpr int H = 32 * HPL;
+  extern __shared__ __align__(16) float sw[];   // [A + 1][H]: value row, then advantage rows
+  stage_head_weights(sw, wv, wa, A, H);
   const int lane = threadIdx.x & 31;
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (b >= B) return;
-  const float* hv = h + (size_t)b * ldh;
-  const float* ha = hv + H;
+  float hv[HPL], ha[HPL];
+#pragma unroll
+  for (int j = 0; j < HPL; ++j) {
+    hv[j] = h[(size_t)b * ldh + lane + 32 * j];
+    ha[j] = h[(size_t)b * ldh + H + lane + 32 * j];
+  }
   float sv = 0.f;
-  for (int k = lane; k < H; k += 32) sv = fmaf(hv[k], __ldg(wv + k), sv);
+#pragma unroll
+  for (int j = 0; j < HPL; ++j) sv = fmaf(hv[j], sw[lane + 32 * j], sv);
   for (int d = 16; d > 0; d >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, d);
   sv += bv[0];
-  float mine = 0.f, total = 0.f;   // lane a keeps advantage a (A <= 32 handled per chunk of 32)
-  for (int a0 = 0; a0 < A; a0 += 32) {
-    for (int a = a0; a < min(A, a0 + 32); ++a) {
-      float s = 0.f;
-      const float* w = wa + (size_t)a * H;
-      for (int k = lane; k < H; k += 32) s = fmaf(ha[k], __ldg(w + k), s);
-      for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-      s += ba[a];
-      total += s;
-      if (lane == (a & 31)) { mine = s; adv[(size_t)b * A + a] = s; }
-    }
+  float total = 0.f, mine = 0.f;
+  for (int a = 0; a < A; ++a) {
+    const float* w = sw + (size_t)(a + 1) * H;
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < HPL; ++j) s = fmaf(ha[j], w[lane + 32 * j], s);
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    s += ba[a];
+    total += s;
+    if (lane == (a & 31)) mine = s;
+    if (A > 32 && lane == 0) adv[(size_t)b * A + a] = s;
   }
   const float mean = total / (float)A;
   if (lane == 0) val[b] = sv;
   if (A <= 32) {
-    if (lane < A) q[(size_t)b * A + lane] = sv + (mine - mean);
+    if (lane < A) { adv[(size_t)b * A + lane] = mine; q[(size_t)b * A + lane] = sv + (mine - mean); }
   } else {
     __syncwarp();
     for (int a = lane; a < A; a += 32) q[(size_t)b * A + a] = sv + (adv[(size_t)b * A + a] - mean);
@@ -395,11 +417,13 @@ duelling_head_fwd_kernel(int B, int A, int H, const float* __restrict__ h, int l
 }
 
 // backward, part 1 (warp per sample): dval = sum_a dq, dadv = dq - mean(dq), and
-// dh = [dval * wv, dadv @ wa] * relu'(h)
+// dh = [dval * wv, dadv @ wa] * relu'(h); weights from shared memory, dadv row broadcast by shuffles
 __global__ void __launch_bounds__(256)
 duelling_head_bwd_dh_kernel(int B, int A, int H, const float* __restrict__ dq, const float* __restrict__ h, int ldh,
                             const float* __restrict__ wv, const float* __restrict__ wa, float* __restrict__ dval,
                             float* __restrict__ dadv, float* __restrict__ dh, int lddh) {
+  extern __shared__ __align__(16) float sw[];
+  stage_head_weights(sw, wv, wa, A, H);
   const int lane = threadIdx.x & 31;
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (b >= B) return;
@@ -409,33 +433,59 @@ duelling_head_bwd_dh_kernel(int B, int A, int H, const float* __restrict__ dq, c
   const float mean = s / (float)A;
   for (int a = lane; a < A; a += 32) dadv[(size_t)b * A + a] = dq[(size_t)b * A + a] - mean;
   if (lane == 0) dval[b] = s;
+  __syncwarp();
   const float* hr = h + (size_t)b * ldh;
   float* dr = dh + (size_t)b * lddh;
+  const float* gr = dadv + (size_t)b * A;
   for (int k = lane; k < H; k += 32) {
-    dr[k] = hr[k] > 0.f ? s * __ldg(wv + k) : 0.f;
+    dr[k] = hr[k] > 0.f ? s * sw[k] : 0.f;
     float acc = 0.f;
-    for (int a = 0; a < A; ++a) acc = fmaf(dq[(size_t)b * A + a] - mean, __ldg(wa + (size_t)a * H + k), acc);
+    for (int a = 0; a < A; ++a) acc = fmaf(gr[a], sw[(size_t)(a + 1) * H + k], acc);
     dr[H + k] = hr[H + k] > 0.f ? acc : 0.f;
   }
 }
-// backward, part 2 (thread per weight): dwv[k] = sum_b dval[b] h[b,k], dwa[a,k] = sum_b dadv[b,a] h[b,H+k], biases
+// backward, part 2: dwv[k] = sum_b dval[b] h[b,k], dwa[a,k] = sum_b dadv[b,a] h[b,H+k] and the bias sums.
+// The batch is cut into gridDim.z segments (partial sums, then a fixed-order add) so that enough
+// threads are in flight; 8 independent accumulators keep 8 loads per thread outstanding.
 __global__ void __launch_bounds__(128)
 duelling_head_bwd_dw_kernel(int B, int A, int H, const float* __restrict__ dval, const float* __restrict__ dadv,
-                            const float* __restrict__ h, int ldh, float* __restrict__ dwv, float* __restrict__ dbv,
-                            float* __restrict__ dwa, float* __restrict__ dba) {
+                            const float* __restrict__ h, int ldh, float* __restrict__ partial) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int a = (int)blockIdx.y - 1;   // -1 = value stream
   if (k >= H) return;
-  float acc = 0.f, bsum = 0.f;
-  if (a < 0) {
-    for (int b = 0; b < B; ++b) { const float g = dval[b]; acc = fmaf(g, h[(size_t)b * ldh + k], acc); bsum += g; }
-    dwv[k] = acc;
-    if (k == 0) dbv[0] = bsum;
-  } else {
-    for (int b = 0; b < B; ++b) { const float g = dadv[(size_t)b * A + a]; acc = fmaf(g, h[(size_t)b * ldh + H + k], acc); bsum += g; }
-    dwa[(size_t)a * H + k] = acc;
-    if (k == 0) dba[a] = bsum;
+  const int seg = (B + gridDim.z - 1) / gridDim.z;
+  const int b0 = blockIdx.z * seg, b1 = min(B, b0 + seg);
+  const float* g = a < 0 ? dval : dadv + a;
+  const int gs = a < 0 ? 1 : A;
+  const float* hc = h + (a < 0 ? 0 : H) + k;
+  float acc[8], bs = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  int b = b0;
+  for (; b + 8 <= b1; b += 8) {
+    float gv[8], hv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { gv[j] = g[(size_t)(b + j) * gs]; hv[j] = hc[(size_t)(b + j) * ldh]; }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc[j] = fmaf(gv[j], hv[j], acc[j]); bs += gv[j]; }
   }
+  for (; b < b1; ++b) { const float gv = g[(size_t)b * gs]; acc[0] = fmaf(gv, hc[(size_t)b * ldh], acc[0]); bs += gv; }
+  const float t = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+  // partial layout: [seg][A+1][H + 1] (last column = bias partial, written by k == 0)
+  float* row = partial + ((size_t)blockIdx.z * (A + 1) + (a + 1)) * (H + 1);
+  row[k] = t;
+  if (k == 0) row[H] = bs;
+}
+__global__ void duelling_head_bwd_finish_kernel(int A, int H, int segs, const float* __restrict__ partial,
+                                                float* __restrict__ dwv, float* __restrict__ dbv,
+                                                float* __restrict__ dwa, float* __restrict__ dba) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over (A+1) * (H+1)
+  if (i >= (A + 1) * (H + 1)) return;
+  float t = 0.f;
+  for (int s = 0; s < segs; ++s) t += partial[(size_t)s * (A + 1) * (H + 1) + i];
+  const int r = i / (H + 1), k = i % (H + 1);
+  if (r == 0) { if (k < H) dwv[k] = t; else dbv[0] = t; }
+  else { if (k < H) dwa[(size_t)(r - 1) * H + k] = t; else dba[r - 1] = t; }
 }
 
 // snt.LayerNorm(axis=slice(1,None), scale, offset) + tanh (acme/tf/networks/continuous.py:55-58); CTA per row
@@ -684,22 +734,56 @@ extern "C" int b200rl_duelling_bwd(int32_t B, int32_t A, const float* dq, float*
 }
 
 
+static int ensure_head_attrs() {
+  static bool attr = false;
+  if (!attr) {
+    B200RL_CUDA_OK(cudaFuncSetAttribute(duelling_head_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    B200RL_CUDA_OK(cudaFuncSetAttribute(duelling_head_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    B200RL_CUDA_OK(cudaFuncSetAttribute(duelling_head_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    B200RL_CUDA_OK(cudaFuncSetAttribute(duelling_head_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    B200RL_CUDA_OK(cudaFuncSetAttribute(duelling_head_bwd_dh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  return B200RL_OK;
+}
+
 extern "C" int b200rl_duelling_head_fwd(int32_t B, int32_t A, int32_t H, const float* h, int32_t ldh, const float* wv,
                                         const float* bv, const float* wa, const float* ba, float* value, float* adv,
                                         float* q, void* stream) {
-  B200RL_REQUIRE(h && wv && bv && wa && ba && value && adv && q && B >= 1 && A >= 1 && H >= 1 && ldh >= 2 * H, "bad argument");
-  duelling_head_fwd_kernel<<<ceil_div(B * 32, 256), 256, 0, as_stream(stream)>>>(B, A, H, h, ldh, wv, bv, wa, ba, value, adv, q);
+  B200RL_REQUIRE(h && wv && bv && wa && ba && value && adv && q && B >= 1 && A >= 1 && ldh >= 2 * H, "bad argument");
+  const int blocks = ceil_div(B * 32, 256);
+  cudaStream_t st = as_stream(stream);
+  const size_t smem = (size_t)(A + 1) * H * 4;
+  B200RL_REQUIRE(smem <= 200 * 1024 && H % 4 == 0, "duelling head weights do not fit in shared memory");
+  if (int rc = ensure_head_attrs()) return rc;
+  switch (H) {
+    case 512: duelling_head_fwd_kernel<16><<<blocks, 256, smem, st>>>(B, A, h, ldh, wv, bv, wa, ba, value, adv, q); break;
+    case 256: duelling_head_fwd_kernel<8><<<blocks, 256, smem, st>>>(B, A, h, ldh, wv, bv, wa, ba, value, adv, q); break;
+    case 128: duelling_head_fwd_kernel<4><<<blocks, 256, smem, st>>>(B, A, h, ldh, wv, bv, wa, ba, value, adv, q); break;
+    case 64: duelling_head_fwd_kernel<2><<<blocks, 256, smem, st>>>(B, A, h, ldh, wv, bv, wa, ba, value, adv, q); break;
+    default: set_error("duelling head: hidden size %d not in {64,128,256,512}", H); return B200RL_EINVAL;
+  }
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }
 extern "C" int b200rl_duelling_head_bwd(int32_t B, int32_t A, int32_t H, const float* dq, const float* h, int32_t ldh,
                                         const float* wv, const float* wa, float* dvalue, float* dadv, float* dh,
-                                        int32_t lddh, float* dwv, float* dbv, float* dwa, float* dba, void* stream) {
-  B200RL_REQUIRE(dq && h && wv && wa && dvalue && dadv && dh && dwv && dbv && dwa && dba, "null argument");
+                                        int32_t lddh, float* dwv, float* dbv, float* dwa, float* dba, void* ws,
+                                        int64_t ws_bytes, void* stream) {
+  B200RL_REQUIRE(dq && h && wv && wa && dvalue && dadv && dh && dwv && dbv && dwa && dba && ws, "null argument");
   B200RL_REQUIRE(B >= 1 && A >= 1 && H >= 1 && ldh >= 2 * H && lddh >= 2 * H, "bad shape");
-  duelling_head_bwd_dh_kernel<<<ceil_div(B * 32, 256), 256, 0, as_stream(stream)>>>(B, A, H, dq, h, ldh, wv, wa, dvalue, dadv, dh, lddh);
+  cudaStream_t st = as_stream(stream);
+  const size_t smem = (size_t)(A + 1) * H * 4;
+  B200RL_REQUIRE(smem <= 200 * 1024 && H % 4 == 0, "duelling head weights do not fit in shared memory");
+  if (int rc = ensure_head_attrs()) return rc;
+  duelling_head_bwd_dh_kernel<<<ceil_div(B * 32, 256), 256, smem, st>>>(B, A, H, dq, h, ldh, wv, wa, dvalue, dadv, dh, lddh);
   B200RL_LAUNCH_OK();
-  duelling_head_bwd_dw_kernel<<<dim3(ceil_div(H, 128), A + 1), 128, 0, as_stream(stream)>>>(B, A, H, dvalue, dadv, h, ldh, dwv, dbv, dwa, dba);
+  int segs = std::max(1, std::min(B / 32, 8));
+  const int64_t per = (int64_t)(A + 1) * (H + 1) * 4;
+  segs = (int)std::max<int64_t>(1, std::min<int64_t>(segs, ws_bytes / per));
+  duelling_head_bwd_dw_kernel<<<dim3(ceil_div(H, 128), A + 1, segs), 128, 0, st>>>(B, A, H, dvalue, dadv, h, ldh, (float*)ws);
+  B200RL_LAUNCH_OK();
+  duelling_head_bwd_finish_kernel<<<ceil_div((A + 1) * (H + 1), 256), 256, 0, st>>>(A, H, segs, (const float*)ws, dwv, dbv, dwa, dba);
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }

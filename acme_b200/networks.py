@@ -263,7 +263,7 @@ class DQNAtariNetwork(Network):
     dh = gbufs['dh'].data_ptr()
     _capi.call('b200rl_duelling_head_bwd', B, self.A, 512, dq.data_ptr(), h.data_ptr(), 1024, P.p('v2.w'), P.p('a2.w'),
                gbufs['dval'].data_ptr(), gbufs['dadv'].data_ptr(), dh, 1024, P.g('v2.w'), P.g('v2.b'), P.g('a2.w'),
-               P.g('a2.b'), st)
+               P.g('a2.b'), ws, wsb, st)
     y3 = bufs['y3']
     _linear_wgrad(B, 1024, self.flat_dim, dh, 1024, y3.data_ptr(), self.flat_dim, P.g('fc1.w'), P.g('fc1.b'), self)
     _linear_dgrad(B, 1024, self.flat_dim, dh, 1024, P.p('fc1.w'), gbufs['dy3'].data_ptr(), self.flat_dim,

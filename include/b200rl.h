@@ -228,7 +228,8 @@ int b200rl_duelling_head_fwd(int32_t B, int32_t A, int32_t H, const float* h, in
                              float* q, void* stream);
 int b200rl_duelling_head_bwd(int32_t B, int32_t A, int32_t H, const float* dq, const float* h, int32_t ldh,
                              const float* wv, const float* wa, float* dvalue, float* dadv, float* dh,
-                             int32_t lddh, float* dwv, float* dbv, float* dwa, float* dba, void* stream);
+                             int32_t lddh, float* dwv, float* dbv, float* dwa, float* dba, void* ws,
+                             int64_t ws_bytes, void* stream);
 /* snt.LayerNorm(axis=1:, scale, offset, eps=1e-5) followed by tanh (continuous.py:55-58) */
 int b200rl_layernorm_tanh_fwd(int32_t B, int32_t N, const float* x, const float* scale,
                               const float* offset, float eps, float* y, float* xhat, float* rstd,

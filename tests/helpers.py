@@ -8,8 +8,11 @@ from oracle import replay as oreplay
 
 
 def make_pair(obs_shape=(8, 8, 4), obs_dtype=np.uint8, num_actions=4, n_step=3, discount=0.99, alpha=0.6,
-              max_size=500, slot_capacity=None, stage_slots=0):
-  spec = specs.EnvironmentSpec(specs.Array(obs_shape, obs_dtype), specs.DiscreteArray(num_actions),
+              max_size=500, slot_capacity=None, stage_slots=0, act_dim=None):
+  """num_actions discrete actions, or (act_dim given) a float32 action vector in [-1, 1]."""
+  aspec = (specs.DiscreteArray(num_actions) if act_dim is None else
+           specs.BoundedArray((act_dim,), np.float32, -1., 1.))
+  spec = specs.EnvironmentSpec(specs.Array(obs_shape, obs_dtype), aspec,
                                specs.Array((), np.float32), specs.BoundedArray((), np.float32, 0., 1.))
   table = replay.Table(replay.DEFAULT_PRIORITY_TABLE, replay.selectors.Prioritized(alpha), replay.selectors.Fifo(),
                        max_size=max_size, rate_limiter=replay.rate_limiters.MinSize(1),
@@ -17,8 +20,8 @@ def make_pair(obs_shape=(8, 8, 4), obs_dtype=np.uint8, num_actions=4, n_step=3, 
                        discount=discount, slot_capacity=slot_capacity, stage_slots=stage_slots)
   server = replay.Server([table])
   adder = adders.NStepTransitionAdder(replay.Client(server), n_step=n_step, discount=discount)
-  oracle = oreplay.Table(max_size, table.slot_capacity, obs_shape, obs_dtype, (), np.int32, discount, alpha,
-                         max_window=n_step)
+  oracle = oreplay.Table(max_size, table.slot_capacity, obs_shape, obs_dtype, () if act_dim is None else (act_dim,),
+                         np.int32 if act_dim is None else np.float32, discount, alpha, max_window=n_step)
   return spec, table, server, adder, oracle
 
 
@@ -28,13 +31,13 @@ def random_obs(rng, shape, dtype):
   return rng.standard_normal(shape).astype(dtype)
 
 
-def feed_episode(rng, adder, oracle, T, n_step, obs_shape, obs_dtype, num_actions, terminal=True):
+def feed_episode(rng, adder, oracle, T, n_step, obs_shape, obs_dtype, num_actions, terminal=True, act_dim=None):
   """One episode of T steps into both stores (oracle items follow SURVEY App. A.1)."""
   o = random_obs(rng, obs_shape, obs_dtype)
   adder.add_first(dm_env.restart(o))
   w = oracle.writer()
   for k in range(1, T + 1):
-    a = np.int32(rng.integers(num_actions))
+    a = np.int32(rng.integers(num_actions)) if act_dim is None else rng.uniform(-1, 1, act_dim).astype(np.float32)
     r = np.float32(rng.choice([-1., 0., 1., 0.5, 2.5]))
     last = k == T
     d = np.float32(0. if (last and terminal) else rng.choice([1., 1., 0.9]))

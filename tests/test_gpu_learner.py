@@ -418,3 +418,70 @@ def test_dqn_learner_steps_match_oracle(use_graph):
     helpers.sync_oracle_leaves_loose(table, oracle)
   assert learner.num_steps == 5
   server.stop()
+
+
+@pytest.mark.parametrize('use_graph', [False, True])
+def test_d4pg_learner_steps_match_oracle(use_graph):
+  """acme/agents/tf/d4pg/learning.py:156-247 end to end (humanoid-shaped: 67-d obs, 21-d act, C51 critic)
+  against oracle.learner.D4PGOracleLearner on the same uniform draws."""
+  import torch
+  import helpers
+  from acme_b200 import _capi, d4pg, loggers, networks, replay
+  from oracle import learner as olearner
+  from oracle import nets as onets
+  rng = np.random.default_rng(2)
+  OBS, ACT, n, B = 67, 21, 5, 32
+  spec, table, server, adder, oracle = helpers.make_pair((OBS,), np.float32, 0, n, 0.99, 0.0, max_size=400, act_dim=ACT)
+  for ep in range(10):
+    helpers.feed_episode(rng, adder, oracle, int(rng.integers(3, 40)), n, (OBS,), np.float32, 0, act_dim=ACT)
+  table.flush()
+  helpers.sync_oracle_leaves(table, oracle)
+  policy = networks.D4PGPolicy(OBS, ACT, seed=1)
+  critic = networks.D4PGCritic(OBS, ACT, seed=2)
+  # make the near-zero-initialised policy head non-trivial so that the actor path is exercised
+  pv = policy.variables()
+  pv['out/w'] = (np.random.default_rng(3).standard_normal(pv['out/w'].shape) * 0.05).astype(np.float32)
+  policy.load_variables(pv)
+  tpolicy, tcritic = policy.clone(), critic.clone()
+  opol, ocri = onets.D4PGPolicy(OBS, ACT), onets.D4PGCritic(OBS, ACT)
+  otp, otc = onets.D4PGPolicy(OBS, ACT), onets.D4PGCritic(OBS, ACT)
+  for o, n_ in ((opol, policy), (otp, policy), (ocri, critic), (otc, critic)):
+    o.load(n_.variables())
+  ds = replay.ReplayDataset(table, B, seed=11, stratified=False)
+  learner = d4pg.D4PGLearner(policy, critic, tpolicy, tcritic, 0.99, target_update_period=2, dataset=ds,
+                             logger=loggers.NoOpLogger(), use_cuda_graph=use_graph)
+  ol = olearner.D4PGOracleLearner(opol, ocri, otp, otc, 0.99, 2)
+  counter = torch.zeros(1, dtype=torch.int64, device='cuda')
+  u_dev = torch.empty(B, device='cuda')
+  lr = 1e-4
+  for step in range(4):
+    _capi.call('b200rl_uniform', u_dev.data_ptr(), B, 11, counter.data_ptr(), step, _capi.current_stream())
+    u = u_dev.cpu().numpy()
+    keys, pos, prob = oracle.sample(u, False)
+    ref = ol.step(*oracle.gather(pos))
+    learner.step()
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(ds.idx.cpu().numpy(), pos)
+    close(learner.target.cpu().numpy(), ref['target'], atol_scale=2e-5, name=f'projected distribution step {step}')
+    close(learner.critic_loss_ps.cpu().numpy(), ref['per_sample'], rtol=1e-4, atol_scale=2e-5, name='critic CE')
+    close(learner.critic_loss.cpu().numpy()[0], ref['critic_loss'], rtol=1e-4)
+    close(learner.dqda.cpu().numpy(), ref['dqda'], rtol=1e-3, atol_scale=1e-4, name='dq/da')
+    close(learner.policy_loss.cpu().numpy()[0], ref['policy_loss'], rtol=1e-3)
+    if ref['critic_norm'] is not None:
+      close(learner.critic_norm.cpu().numpy()[0], ref['critic_norm'], rtol=1e-4)
+      close(learner.policy_norm.cpu().numpy()[0], ref['policy_norm'], rtol=1e-3)
+    if step < 2:
+      for net, onet, what in ((critic, ocri, 'critic'), (policy, opol, 'policy')):
+        got = net.variables()
+        for k, v in onet.numpy().items():
+          bad = ~np.isclose(got[k], v, rtol=1e-4, atol=0.02 * lr)
+          assert bad.mean() < 2e-3, f'{what} {k} step {step}: {bad.sum()} of {bad.size} outside 2% of lr'
+    # target copy happens BEFORE the update when num_steps % period == 0 (learning.py:171-174)
+    if step % 2 == 0:
+      pass   # copied at the start of this step from the pre-update online networks
+    else:
+      frozen_c, frozen_p = critic.params.flat.clone(), policy.params.flat.clone()
+    if step in (2,):
+      assert torch.equal(tcritic.params.flat, frozen_c) and torch.equal(tpolicy.params.flat, frozen_p)
+  assert learner.num_steps == 4
+  server.stop()

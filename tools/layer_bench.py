@@ -45,10 +45,11 @@ def main():
     r['fc1.fwd'] = t(lambda: _capi.call('b200rl_linear_fwd', B, 1024, F, x, F, P.p('fc1.w'), P.p('fc1.b'), h, 1024, 1, prec, ws, wsb, st))
     r['fc1.wgrad'] = t(lambda: _capi.call('b200rl_linear_wgrad', B, 1024, F, dh, 1024, x, F, P.g('fc1.w'), P.g('fc1.b'), prec, ws, wsb, st))
     r['fc1.dgrad'] = t(lambda: _capi.call('b200rl_linear_dgrad', B, 1024, F, dh, 1024, P.p('fc1.w'), g['dy3'].data_ptr(), F, x, 1, prec, ws, wsb, st))
-    r['heads.fwd(v2+a2+duel)'] = t(lambda: (
-        _capi.call('b200rl_linear_fwd', B, 1, 512, h, 1024, P.p('v2.w'), P.p('v2.b'), bufs['val'].data_ptr(), 1, 0, prec, ws, wsb, st),
-        _capi.call('b200rl_linear_fwd', B, 18, 512, h + 2048, 1024, P.p('a2.w'), P.p('a2.b'), bufs['adv'].data_ptr(), 18, 0, prec, ws, wsb, st),
-        _capi.call('b200rl_duelling_fwd', B, 18, bufs['val'].data_ptr(), bufs['adv'].data_ptr(), bufs['q'].data_ptr(), st)))
+    r['head.fwd'] = t(lambda: _capi.call('b200rl_duelling_head_fwd', B, 18, 512, h, 1024, P.p('v2.w'), P.p('v2.b'), P.p('a2.w'),
+                                         P.p('a2.b'), bufs['val'].data_ptr(), bufs['adv'].data_ptr(), bufs['q'].data_ptr(), st))
+    r['head.bwd'] = t(lambda: _capi.call('b200rl_duelling_head_bwd', B, 18, 512, dq.data_ptr(), h, 1024, P.p('v2.w'), P.p('a2.w'),
+                                         g['dval'].data_ptr(), g['dadv'].data_ptr(), dh, 1024, P.g('v2.w'), P.g('v2.b'),
+                                         P.g('a2.w'), P.g('a2.b'), ws, wsb, st))
     r['forward'] = t(lambda: net.forward(obs, bufs))
     r['backward'] = t(lambda: net.backward(obs, bufs, g, dq))
     out['fp32' if prec == 0 else 'bf16'] = r
