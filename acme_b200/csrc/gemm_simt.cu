@@ -191,9 +191,24 @@ __global__ void splitk_finish_kernel(Epilogue epi, int M, int N, int splits) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)M * N) return;
   const int row = (int)(i / N), col = (int)(i % N);
-  float acc = 0.f;
-  for (int s = 0; s < splits; ++s) acc += epi.partial[((size_t)s * M + row) * N + col];  // fixed order
-  finish(epi, row, col, acc);
+  // fixed order: four interleaved accumulators (s % 4), combined pairwise; the loads of a group of 8
+  // splits are independent and issue together
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  const float* p = epi.partial + (size_t)row * N + col;
+  const size_t stride = (size_t)M * N;
+  int s = 0;
+  for (; s + 8 <= splits; s += 8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = p[(size_t)(s + j) * stride];
+    a0 += v[0]; a1 += v[1]; a2 += v[2]; a3 += v[3];
+    a0 += v[4]; a1 += v[5]; a2 += v[6]; a3 += v[7];
+  }
+  for (; s < splits; ++s) {
+    const float v = p[(size_t)s * stride];
+    switch (s & 3) { case 0: a0 += v; break; case 1: a1 += v; break; case 2: a2 += v; break; default: a3 += v; }
+  }
+  finish(epi, row, col, (a0 + a1) + (a2 + a3));
 }
 
 // out[n] = sum_m x[m, n].  Rows are split over gridDim.y CTAs (each a 32-column x 8-row-lane tile with a
@@ -218,9 +233,20 @@ __global__ void colsum_partial_kernel(int M, int N, const float* __restrict__ x,
 __global__ void colsum_finish_kernel(int N, int splits, const float* __restrict__ partial, float* __restrict__ out) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= N) return;
-  float t = 0.f;
-  for (int s = 0; s < splits; ++s) t += partial[(size_t)s * N + col];
-  out[col] = t;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int s = 0;
+  for (; s + 8 <= splits; s += 8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = partial[(size_t)(s + j) * N + col];
+    a0 += v[0]; a1 += v[1]; a2 += v[2]; a3 += v[3];
+    a0 += v[4]; a1 += v[5]; a2 += v[6]; a3 += v[7];
+  }
+  for (; s < splits; ++s) {
+    const float v = partial[(size_t)s * N + col];
+    switch (s & 3) { case 0: a0 += v; break; case 1: a1 += v; break; case 2: a2 += v; break; default: a3 += v; }
+  }
+  out[col] = (a0 + a1) + (a2 + a3);
 }
 
 int launch_splitk_finish(const Epilogue& epi, int M, int N, int splits, cudaStream_t stream) {
@@ -257,7 +283,7 @@ static int launch_gemm(const AL& a, const BL& b, Epilogue epi, int M, int N, int
 
 int launch_colsum(int M, int N, const float* x, int ld, float* out, void* ws, int64_t ws_bytes, cudaStream_t stream) {
   const int col_blocks = ceil_div(N, 32);
-  int splits = std::max(1, std::min(ceil_div(M, 64), (2 * kNumSMs) / col_blocks));
+  int splits = std::max(1, std::min(std::min(ceil_div(M, 64), (2 * kNumSMs) / col_blocks), 96));
   splits = (int)std::min<int64_t>(splits, ws ? ws_bytes / ((int64_t)N * 4) : 1);
   if (splits <= 1) {
     colsum_partial_kernel<<<dim3(col_blocks, 1), dim3(32, 8), 0, stream>>>(M, N, x, ld, M, out);

@@ -239,56 +239,67 @@ __global__ void dpg_kernel(int B, int A, const float* __restrict__ dqda, float c
 
 // ------------------------------------------------------------------------------------------ K7
 // snt.optimizers.Adam.apply as recalled in SURVEY App. A.5 (source not in the reference tree).
+struct AdamConsts { float bc1, bc2, b1f, b2f, omb1, omb2, gs, k1, lr, eps; int eps_mode; };
+__device__ __forceinline__ float adam_one(float& p, float g, float& m, float& v, const AdamConsts& c) {
+  const float gj = c.gs == 1.f ? g : __fmul_rn(g, c.gs);
+  m = __fadd_rn(__fmul_rn(c.b1f, m), __fmul_rn(c.omb1, gj));
+  v = __fadd_rn(__fmul_rn(c.b2f, v), __fmul_rn(c.omb2, __fmul_rn(gj, gj)));
+  float upd;
+  if (c.eps_mode == 0) upd = __fdiv_rn(__fdiv_rn(m, c.bc1), __fadd_rn(__fsqrt_rn(__fdiv_rn(v, c.bc2)), c.eps));
+  else upd = __fdiv_rn(__fmul_rn(c.k1, m), __fadd_rn(__fsqrt_rn(v), c.eps));
+  p = __fsub_rn(p, __fmul_rn(c.lr, upd));
+  return p;
+}
+// 8 elements (two float4 per array = 8 independent 16-byte loads) per thread per iteration: enough bytes in
+// flight to run at HBM speed; p/m/v are read-modify-write, g is read once (streamed through the read-only path).
 __global__ void __launch_bounds__(256)
 adam_kernel(long long n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
             float* __restrict__ v, const long long* __restrict__ step_dev, float lr, double b1,
             double b2, float eps, int eps_mode, const float* __restrict__ gscale_dev,
             __nv_bfloat16* __restrict__ shadow) {
   const double t = (double)(*step_dev + 1);
-  const float bc1 = (float)(1.0 - pow(b1, t)), bc2 = (float)(1.0 - pow(b2, t));
-  const float b1f = (float)b1, b2f = (float)b2, omb1 = (float)(1.0 - b1), omb2 = (float)(1.0 - b2);
-  const float gs = gscale_dev ? *gscale_dev : 1.f;
-  const float k1 = sqrtf(bc2) / bc1;
-  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  const long long stride = (long long)gridDim.x * blockDim.x * 4;
-  for (; i < n; i += stride) {
-    float pv[4], gv[4], mv[4], vv[4];
-    const int cnt = (n - i >= 4) ? 4 : (int)(n - i);
-    if (cnt == 4) {
-      *reinterpret_cast<float4*>(pv) = *reinterpret_cast<const float4*>(p + i);
-      *reinterpret_cast<float4*>(gv) = __ldg(reinterpret_cast<const float4*>(g + i));
-      *reinterpret_cast<float4*>(mv) = *reinterpret_cast<const float4*>(m + i);
-      *reinterpret_cast<float4*>(vv) = *reinterpret_cast<const float4*>(v + i);
-    } else {
-      for (int j = 0; j < cnt; ++j) { pv[j] = p[i + j]; gv[j] = g[i + j]; mv[j] = m[i + j]; vv[j] = v[i + j]; }
+  AdamConsts c;
+  c.bc1 = (float)(1.0 - pow(b1, t)); c.bc2 = (float)(1.0 - pow(b2, t));
+  c.b1f = (float)b1; c.b2f = (float)b2; c.omb1 = (float)(1.0 - b1); c.omb2 = (float)(1.0 - b2);
+  c.gs = gscale_dev ? *gscale_dev : 1.f;
+  c.k1 = sqrtf(c.bc2) / c.bc1; c.lr = lr; c.eps = eps; c.eps_mode = eps_mode;
+  const long long n8 = n & ~7ll;
+  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  const long long stride = (long long)gridDim.x * blockDim.x * 8;
+  for (; i < n8; i += stride) {
+    float4 pq[2], gq[2], mq[2], vq[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      pq[h] = *reinterpret_cast<const float4*>(p + i + 4 * h);
+      gq[h] = __ldg(reinterpret_cast<const float4*>(g + i + 4 * h));
+      mq[h] = *reinterpret_cast<const float4*>(m + i + 4 * h);
+      vq[h] = *reinterpret_cast<const float4*>(v + i + 4 * h);
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float gj = gs == 1.f ? gv[j] : __fmul_rn(gv[j], gs);
-      mv[j] = __fadd_rn(__fmul_rn(b1f, mv[j]), __fmul_rn(omb1, gj));
-      vv[j] = __fadd_rn(__fmul_rn(b2f, vv[j]), __fmul_rn(omb2, __fmul_rn(gj, gj)));
-      float upd;
-      if (eps_mode == 0) upd = __fdiv_rn(__fdiv_rn(mv[j], bc1), __fadd_rn(__fsqrt_rn(__fdiv_rn(vv[j], bc2)), eps));
-      else upd = __fdiv_rn(__fmul_rn(k1, mv[j]), __fadd_rn(__fsqrt_rn(vv[j]), eps));
-      pv[j] = __fsub_rn(pv[j], __fmul_rn(lr, upd));
+    for (int h = 0; h < 2; ++h) {
+      adam_one(pq[h].x, gq[h].x, mq[h].x, vq[h].x, c);
+      adam_one(pq[h].y, gq[h].y, mq[h].y, vq[h].y, c);
+      adam_one(pq[h].z, gq[h].z, mq[h].z, vq[h].z, c);
+      adam_one(pq[h].w, gq[h].w, mq[h].w, vq[h].w, c);
+      *reinterpret_cast<float4*>(p + i + 4 * h) = pq[h];
+      *reinterpret_cast<float4*>(m + i + 4 * h) = mq[h];
+      *reinterpret_cast<float4*>(v + i + 4 * h) = vq[h];
     }
-    if (cnt == 4) {
-      *reinterpret_cast<float4*>(p + i) = *reinterpret_cast<float4*>(pv);
-      *reinterpret_cast<float4*>(m + i) = *reinterpret_cast<float4*>(mv);
-      *reinterpret_cast<float4*>(v + i) = *reinterpret_cast<float4*>(vv);
-      if (shadow) {
-        __nv_bfloat162 lo = __floats2bfloat162_rn(pv[0], pv[1]), hi = __floats2bfloat162_rn(pv[2], pv[3]);
-        uint2 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&lo);
-        pk.y = *reinterpret_cast<uint32_t*>(&hi);
-        *reinterpret_cast<uint2*>(shadow + i) = pk;
-      }
-    } else {
-      for (int j = 0; j < cnt; ++j) {
-        p[i + j] = pv[j]; m[i + j] = mv[j]; v[i + j] = vv[j];
-        if (shadow) shadow[i + j] = __float2bfloat16_rn(pv[j]);
-      }
+    if (shadow) {
+      uint4 pk;
+      __nv_bfloat162 t0 = __floats2bfloat162_rn(pq[0].x, pq[0].y), t1 = __floats2bfloat162_rn(pq[0].z, pq[0].w);
+      __nv_bfloat162 t2 = __floats2bfloat162_rn(pq[1].x, pq[1].y), t3 = __floats2bfloat162_rn(pq[1].z, pq[1].w);
+      pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+      pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+      *reinterpret_cast<uint4*>(shadow + i) = pk;
     }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (int)(n - n8)) {   // ragged tail (< 8 elements)
+    const long long j = n8 + threadIdx.x;
+    float pv = p[j], mv = m[j], vv = v[j];
+    adam_one(pv, g[j], mv, vv, c);
+    p[j] = pv; m[j] = mv; v[j] = vv;
+    if (shadow) shadow[j] = __float2bfloat16_rn(pv);
   }
 }
 
@@ -677,7 +688,7 @@ extern "C" int b200rl_adam(int64_t n, float* param, const float* grad, float* m,
   B200RL_REQUIRE(n >= 0 && (eps_mode == 0 || eps_mode == 1), "bad argument");
   B200RL_REQUIRE((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "buffers must be 16-byte aligned");
   if (n == 0) return B200RL_OK;
-  int blocks = grid1d((n + 3) / 4, 256, kNumSMs * 8);
+  int blocks = grid1d((n + 7) / 8, 256, kNumSMs * 8);
   adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(n, param, grad, m, v, (const long long*)step_dev, lr, b1, b2, eps,
                                                     eps_mode, grad_scale_dev, (__nv_bfloat16*)bf16_shadow);
   B200RL_LAUNCH_OK();

@@ -16,7 +16,7 @@ from typing import List, Optional
 
 import numpy as np
 
-from acme_b200 import _capi, actors, adders, agent, core, counting, loggers, networks, replay, specs
+from acme_b200 import _capi, actors, adders, agent, core, counting, loggers, networks, parallel, replay, specs
 
 
 class DQNLearner(core.Learner, core.Saveable):
@@ -26,7 +26,7 @@ class DQNLearner(core.Learner, core.Saveable):
                huber_loss_parameter: float = 1., replay_client: Optional[replay.Client] = None,
                counter: counting.Counter = None, logger: loggers.Logger = None, checkpoint: bool = True,
                max_abs_reward: float = 1., eps_mode: int = 0, use_cuda_graph: bool = True,
-               process_group=None, adam_eps: float = 1e-8):
+               process_group=None, adam_eps: float = 1e-8, concurrent_streams: bool = True):
     import torch
     if huber_loss_parameter < 0:
       raise ValueError('quadratic_linear_boundary must be >= 0.')   # huber.py:45-46
@@ -44,11 +44,8 @@ class DQNLearner(core.Learner, core.Saveable):
     self._counter = counter or counting.Counter()
     self._logger = logger or loggers.TerminalLogger('learner', time_delta=1.)
     self._timestamp = None
-    self._pg = process_group
-    self._world = 1
-    if process_group is not None:
-      import torch.distributed as dist
-      self._world = dist.get_world_size(process_group)
+    self._dp = parallel.DataParallel(process_group)
+    self._world = self._dp.world
 
     dev = torch.device('cuda', network.device)
     B, A = dataset.B, network.A
@@ -69,6 +66,10 @@ class DQNLearner(core.Learner, core.Saveable):
     self._loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
     self._graphs = None
     self._use_graph = bool(use_cuda_graph)
+    # the three forward passes are independent, and so are a layer's weight- and data-gradient: run them on
+    # parallel streams (fork/join with events, also inside the captured graph)
+    self._concurrent = bool(concurrent_streams) and hasattr(network, '_backward_two_streams')
+    self._side = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)] if self._concurrent else None
     self._steps_done = 0
     self.kernel_launches_per_step = None
 
@@ -96,21 +97,41 @@ class DQNLearner(core.Learner, core.Saveable):
     ds, net, tgt = self._dataset, self._net, self._tgt
     st = _capi.current_stream()
     o_tm1, o_t = self._obs_view(ds.o_tm1), self._obs_view(ds.o_t)
-    q_tm1 = net.forward(o_tm1, self._bufs_train)               # learning.py:123
-    q_t_value = tgt.forward(o_t, self._bufs_tgt)               # learning.py:124
-    q_t_selector = net.forward(o_t, self._bufs_sel)            # learning.py:125
+    if self._concurrent:
+      torch = self._torch
+      main = torch.cuda.current_stream()
+      start = torch.cuda.Event()
+      start.record(main)
+      for s in self._side:
+        s.wait_event(start)
+      with torch.cuda.stream(self._side[0]):
+        q_t_value = tgt.lane(1).forward(o_t, self._bufs_tgt)     # learning.py:124
+      tgt.lane(0)
+      with torch.cuda.stream(self._side[1]):
+        q_t_selector = net.lane(2).forward(o_t, self._bufs_sel)  # learning.py:125
+      q_tm1 = net.lane(0).forward(o_tm1, self._bufs_train)       # learning.py:123
+      for s in self._side:
+        done = torch.cuda.Event()
+        done.record(s)
+        main.wait_event(done)
+    else:
+      q_tm1 = net.forward(o_tm1, self._bufs_train)               # learning.py:123
+      q_t_value = tgt.forward(o_t, self._bufs_tgt)               # learning.py:124
+      q_t_selector = net.forward(o_t, self._bufs_sel)            # learning.py:125
     wmax = None
     if self._world > 1:   # global max importance weight: allreduce(MAX) of one f64
-      import torch.distributed as dist
       _capi.call('b200rl_is_weight_max', self.B, _capi.ptr(ds.prob), self._beta, _capi.ptr(self._wmax), st)
-      dist.all_reduce(self._wmax, op=dist.ReduceOp.MAX, group=self._pg)
+      self._dp.global_max_(self._wmax)
       wmax = _capi.ptr(self._wmax)
     _capi.call('b200rl_dqn_td', self.B, net.A, _capi.ptr(q_tm1), _capi.ptr(q_t_value), _capi.ptr(q_t_selector),
                _capi.ptr(self._actions_i32()), _capi.ptr(ds.R), _capi.ptr(ds.D), _capi.ptr(ds.prob),
                self._discount, self._delta, self._beta, self._max_abs_reward, wmax, 1.0 / self.B,
                _capi.ptr(self.td), _capi.ptr(self.loss_ps), _capi.ptr(self.weight), _capi.ptr(self.priority),
                _capi.ptr(self.dq), _capi.ptr(self.loss), st)
-    net.backward(o_tm1, self._bufs_train, self._gbufs, self.dq)
+    if self._concurrent:
+      net.backward(o_tm1, self._bufs_train, self._gbufs, self.dq, side_stream=self._side[0])
+    else:
+      net.backward(o_tm1, self._bufs_train, self._gbufs, self.dq)
 
   def _apply(self):
     net, tgt, st = self._net, self._tgt, _capi.current_stream()
@@ -130,9 +151,7 @@ class DQNLearner(core.Learner, core.Saveable):
     n0 = lib.b200rl_launch_count()
     self._dataset.sample_raw(uniforms)
     self._forward_loss()
-    if self._world > 1:
-      import torch.distributed as dist
-      dist.all_reduce(self._net.params.grad, op=dist.ReduceOp.SUM, group=self._pg)  # then x 1/R in Adam
+    self._dp.sum_(self._net.params.grad)   # all-reduce(SUM); Adam multiplies by 1/R (mean), then applies
     self._apply()
     self.kernel_launches_per_step = int(lib.b200rl_launch_count() - n0)
 

@@ -93,11 +93,20 @@ class Network:
     import torch
     _capi.require_device(self.device)
     self.params.allocate()
-    self._ws = torch.empty(64 << 20, dtype=torch.uint8, device=torch.device('cuda', self.device))
+    # one split-K / partial-sum workspace per concurrent stream (see Network.lanes)
+    self._ws_all = [torch.empty(64 << 20, dtype=torch.uint8, device=torch.device('cuda', self.device)) for _ in range(3)]
+    self._lane = 0
 
   @property
   def ws(self):
-    return self._ws.data_ptr(), self._ws.numel()
+    w = self._ws_all[self._lane]
+    return w.data_ptr(), w.numel()
+
+  def lane(self, i: int):
+    """Selects the workspace used by the following calls; kernels issued on different streams must use
+    different lanes (0..2)."""
+    self._lane = i
+    return self
 
   def copy_params_from(self, other: 'Network'):
     self.params.flat.copy_(other.params.flat)
@@ -254,9 +263,15 @@ class DQNAtariNetwork(Network):
                P.p('a2.b'), bufs['val'].data_ptr(), bufs['adv'].data_ptr(), bufs['q'].data_ptr(), st)
     return bufs['q']
 
-  def backward(self, obs, bufs, gbufs, dq):
-    """Accumulates nothing: overwrites params.grad with d(loss)/d(params) given dq [B, A]."""
+  def backward(self, obs, bufs, gbufs, dq, side_stream=None):
+    """Accumulates nothing: overwrites params.grad with d(loss)/d(params) given dq [B, A].
+
+    With `side_stream`, the weight-gradient GEMMs of fc1 / conv3 / conv2 run on it (workspace lane 1)
+    concurrently with the data-gradient chain on the current stream: the two are independent once a
+    layer's dy exists, and each kernel alone is too latency-bound to fill the machine."""
     import torch
+    if side_stream is not None:
+      return self._backward_two_streams(obs, bufs, gbufs, dq, side_stream)
     B, P, st = bufs['B'], self.params, _capi.current_stream()
     ws, wsb = self.ws
     h = bufs['h']
@@ -280,6 +295,58 @@ class DQNAtariNetwork(Network):
       if i > 0:
         _capi.call('b200rl_conv2d_dgrad', dy, P.p(f'conv{i + 1}.w'), gbufs[f'dy{i}'].data_ptr(), g,
                    bufs[f'y{i}'].data_ptr(), ACT_RELU, self.precision, ws, wsb, st)
+
+
+  def _backward_two_streams(self, obs, bufs, gbufs, dq, side):
+    import torch
+    B, P = bufs['B'], self.params
+    main = torch.cuda.current_stream()
+    h, y3 = bufs['h'], bufs['y3']
+    dh = gbufs['dh'].data_ptr()
+
+    def fork():           # side waits for everything issued on main so far
+      ev = torch.cuda.Event()
+      ev.record(main)
+      side.wait_event(ev)
+
+    self.lane(0)
+    ws, wsb = self.ws
+    _capi.call('b200rl_duelling_head_bwd', B, self.A, 512, dq.data_ptr(), h.data_ptr(), 1024, P.p('v2.w'), P.p('a2.w'),
+               gbufs['dval'].data_ptr(), gbufs['dadv'].data_ptr(), dh, 1024, P.g('v2.w'), P.g('v2.b'), P.g('a2.w'),
+               P.g('a2.b'), ws, wsb, _capi.current_stream())
+    fork()
+    with torch.cuda.stream(side):
+      self.lane(1)
+      _linear_wgrad(B, 1024, self.flat_dim, dh, 1024, y3.data_ptr(), self.flat_dim, P.g('fc1.w'), P.g('fc1.b'), self)
+    self.lane(0)
+    _linear_dgrad(B, 1024, self.flat_dim, dh, 1024, P.p('fc1.w'), gbufs['dy3'].data_ptr(), self.flat_dim,
+                  y3.data_ptr(), ACT_RELU, self)
+    for i in (2, 1, 0):
+      g = self.geom(i, B)
+      dy = gbufs[f'dy{i + 1}'].data_ptr()
+      if i > 0:
+        x, x_u8 = bufs[f'y{i}'].data_ptr(), 0
+      else:
+        x, x_u8 = obs.data_ptr(), int(obs.dtype == torch.uint8)
+      if i > 0:
+        fork()
+        with torch.cuda.stream(side):
+          self.lane(1)
+          ws1, wsb1 = self.ws
+          _capi.call('b200rl_conv2d_wgrad', x, x_u8, dy, P.g(f'conv{i + 1}.w'), P.g(f'conv{i + 1}.b'), g,
+                     self.precision, ws1, wsb1, _capi.current_stream())
+        self.lane(0)
+        ws, wsb = self.ws
+        _capi.call('b200rl_conv2d_dgrad', dy, P.p(f'conv{i + 1}.w'), gbufs[f'dy{i}'].data_ptr(), g,
+                   bufs[f'y{i}'].data_ptr(), ACT_RELU, self.precision, ws, wsb, _capi.current_stream())
+      else:   # conv1 has no data gradient: its weight gradient finishes the main chain
+        ws, wsb = self.ws
+        _capi.call('b200rl_conv2d_wgrad', x, x_u8, dy, P.g('conv1.w'), P.g('conv1.b'), g, self.precision, ws, wsb,
+                   _capi.current_stream())
+    ev = torch.cuda.Event()
+    ev.record(side)
+    main.wait_event(ev)
+    self.lane(0)
 
 
 # =============================================================================== plain MLP Q-net

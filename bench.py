@@ -291,6 +291,14 @@ def run_ours(args):
   ms_per_step = dev_s / args.steps * 1e3
   value = world * args.steps / dev_s
 
+  if args.profile:
+    if rank == 0:
+      print(json.dumps({'metric': METRIC, 'value': value, 'ms_per_step': ms_per_step, 'profile_run': True}))
+    server.stop()
+    if world > 1:
+      dist.destroy_process_group()
+    return
+
   # ---- end to end through the public API with host buffers: the reference loop's cadence is 8
   #      environment steps inserted per learner step (batch 256 / samples_per_insert 32, dqn/agent.py:158-162)
   rng = np.random.default_rng(99 + rank)
@@ -414,6 +422,8 @@ def run_ours(args):
         'setup_s': t_setup,
     }
     print(json.dumps(out))
+  if world > 1:   # replicas must not have diverged (identical Adam on identical averaged gradients)
+    learner._dp.assert_replicated(net.params.flat, 'online parameters')
   server.stop()
   if world > 1:
     dist.destroy_process_group()
@@ -429,6 +439,7 @@ def main():
   ap.add_argument('--items', type=int, default=1_000_000)
   ap.add_argument('--no-graph', action='store_true')
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--profile', action='store_true', help='only warm-up + timed steps (for ncu captures)')
   args = ap.parse_args()
   if args.impl == 'reference':
     if args.steps == 100 and args.warmup == 10:      # defaults sized for the GPU arm; bound the CPU run

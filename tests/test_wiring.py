@@ -1,0 +1,76 @@
+"""Host wiring without a GPU: EnvironmentLoop counts (acme/environment_loop_test.py:36-51), Agent
+learner-step cadence (acme/agents/agent.py:45-89), Counter (acme/utils/counting_test.py)."""
+import pytest
+
+from acme_b200 import agent, counting, environment_loop, loggers, specs, testing
+
+EPISODE_LENGTH = 10
+
+
+def make_loop():
+  env = testing.DiscreteEnvironment(episode_length=EPISODE_LENGTH)
+  actor = testing.Actor(specs.make_environment_spec(env))
+  return environment_loop.EnvironmentLoop(env, actor, logger=loggers.NoOpLogger()), actor
+
+
+def test_one_episode():
+  loop, _ = make_loop()
+  result = loop.run_episode()
+  assert result['episode_length'] == EPISODE_LENGTH and 'episode_return' in result and 'steps_per_second' in result
+
+
+def test_run_episodes_and_steps():
+  loop, actor = make_loop()
+  loop.run(num_episodes=10)
+  assert actor.num_updates == 10 * EPISODE_LENGTH
+  loop, actor = make_loop()
+  loop.run(num_steps=EPISODE_LENGTH + 5)
+  assert actor.num_updates == 2 * EPISODE_LENGTH
+  with pytest.raises(ValueError):
+    loop.run(num_episodes=1, num_steps=1)
+
+
+class CountingLearner:
+
+  def __init__(self):
+    self.steps = 0
+
+  def step(self):
+    self.steps += 1
+
+  def get_variables(self, names):
+    return []
+
+
+@pytest.mark.parametrize('ops,min_obs,observations,expected', [
+    (8.0, 1000, 1000, 1),      # DQN defaults: first update right after the 1000th observation (agent.py:161)
+    (8.0, 1000, 1016, 3),      # ... then one every 8 observations
+    (8.0, 1000, 999, 0),
+    (0.25, 10, 12, 12),        # observations_per_step < 1 -> int(1/ops) learner steps per observation
+])
+def test_agent_cadence(ops, min_obs, observations, expected):
+  env = testing.DiscreteEnvironment(episode_length=10**9)
+  actor = testing.Actor(specs.make_environment_spec(env))
+  learner = CountingLearner()
+  a = agent.Agent(actor, learner, min_observations=min_obs, observations_per_step=ops)
+  ts = env.reset()
+  a.observe_first(ts)
+  for _ in range(observations):
+    action = a.select_action(ts.observation)
+    ts = env.step(action)
+    a.observe(action, ts)
+    a.update()
+  assert learner.steps == expected
+
+
+def test_counter_hierarchy():
+  parent = counting.Counter()
+  child = counting.Counter(parent, prefix='learner', time_delta=0.)
+  child.increment(steps=2)
+  counts = child.increment(steps=3, walltime=1.5)
+  assert counts['learner_steps'] == 5 and counts['learner_walltime'] == 1.5
+  assert parent.get_counts()['learner_steps'] == 5
+  state = parent.save()
+  fresh = counting.Counter()
+  fresh.restore(state)
+  assert fresh.get_counts() == parent.get_counts()
