@@ -52,6 +52,7 @@ PROTOTYPES = {
     'b200rl_replay_tree_levels': (c_int, [c_vp, C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i32)]),
     'b200rl_replay_tree_level_width': (c_int, [c_vp, c_i32, C.POINTER(c_i64)]),
     'b200rl_replay_tree_read': (c_int, [c_vp, c_i32, c_vp, c_i64, c_vp]),
+    'b200rl_replay_tree_read_prefix': (c_int, [c_vp, c_i32, c_vp, c_i64, c_vp]),
     'b200rl_replay_mass_ptr': (c_int, [c_vp, C.POINTER(c_vp)]),
     'b200rl_replay_set_weights': (c_int, [c_vp, c_i64, c_vp, c_vp]),
     'b200rl_uniform': (c_int, [c_vp, c_i32, c_u64, c_vp, c_i64, c_vp]),

@@ -45,9 +45,11 @@ constexpr int kFanout = 32;
 constexpr int kMaxLevels = 8;
 constexpr int kNumSMs = 148;
 
-// Device view of the fan-out-32 sum tree: lvl[0] = root (1 float) .. lvl[L] = leaves.
+// Device view of the fan-out-32 sum tree: lvl[0] = root (1 float) .. lvl[L] = leaf weights (raw child
+// values); pre[l] = sequential fp32 inclusive prefixes of every node's 32 children at level l.
 struct TreeView {
   float* lvl[kMaxLevels];
+  float* pre[kMaxLevels];
   int64_t width[kMaxLevels];
   int32_t L;
 };
@@ -63,17 +65,6 @@ static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStre
 template <typename T>
 static inline T ceil_div(T a, T b) {
   return (a + b - 1) / b;
-}
-
-// Kogge-Stone inclusive scan over the 32 lanes, fp32 round-to-nearest adds in a fixed order
-// (shared bit-for-bit with oracle/sumtree.py::ks_scan).
-__device__ __forceinline__ float warp_ks_scan(float x, int lane) {
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    float y = __shfl_up_sync(0xffffffffu, x, d);
-    if (lane >= d) x = __fadd_rn(x, y);
-  }
-  return x;
 }
 
 }  // namespace b200rl

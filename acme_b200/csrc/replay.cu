@@ -196,6 +196,7 @@ struct b200rl_replay {
   int32_t act_stride = 0;
   RingView ring{};
   float* d_tree = nullptr;
+  int64_t tree_floats = 0;
   TreeView tree{};
   unsigned long long* d_stamp = nullptr;
   unsigned long long* d_epoch = nullptr;
@@ -329,13 +330,15 @@ extern "C" int b200rl_replay_create(b200rl_replay** out, const b200rl_replay_cfg
     total += t.width[l];
   }
   t.width[0] = 1;
-  ALLOC(h->d_tree, total * 4);
-  cudaMemset(h->d_tree, 0, total * 4);
+  h->tree_floats = 2 * total;   // raw values + prefix lines
+  ALLOC(h->d_tree, h->tree_floats * 4);
+  cudaMemset(h->d_tree, 0, h->tree_floats * 4);
   {
     float* p = h->d_tree;
     t.lvl[0] = p;
+    t.pre[0] = p + total;
     p += 32;
-    for (int l = 1; l <= L; ++l) { t.lvl[l] = p; p += t.width[l]; }
+    for (int l = 1; l <= L; ++l) { t.lvl[l] = p; t.pre[l] = p + total; p += t.width[l]; }
   }
   ALLOC(h->d_stamp, t.width[L] * 8);
   cudaMemset(h->d_stamp, 0, t.width[L] * 8);
@@ -690,9 +693,7 @@ extern "C" int b200rl_replay_reset(b200rl_replay* h, void* stream_) {
   h->n_obs = h->n_fill = h->n_item = 0;
   h->item_tail = h->item_head;  // every key issued so far is dead
   for (auto& w : h->writers) { w.hist.clear(); w.k = 0; w.has_pending = false; }
-  int64_t total = 32;
-  for (int l = 1; l <= h->tree.L; ++l) total += h->tree.width[l];
-  B200RL_CUDA_OK(cudaMemsetAsync(h->d_tree, 0, total * 4, stream));
+  B200RL_CUDA_OK(cudaMemsetAsync(h->d_tree, 0, h->tree_floats * 4, stream));
   h->state_dirty = true;
   return flush_impl(h, stream);
 }
@@ -777,6 +778,16 @@ extern "C" int b200rl_replay_tree_read(b200rl_replay* h, int32_t level, float* h
   int rc = ensure_device(h);
   if (rc) return rc;
   B200RL_CUDA_OK(cudaMemcpyAsync(host_out, h->tree.lvl[level], n * 4, cudaMemcpyDeviceToHost, as_stream(stream)));
+  B200RL_CUDA_OK(cudaStreamSynchronize(as_stream(stream)));
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_replay_tree_read_prefix(b200rl_replay* h, int32_t level, float* host_out, int64_t n, void* stream) {
+  B200RL_REQUIRE(h && host_out && level >= 1 && level <= h->tree.L, "bad argument");
+  B200RL_REQUIRE(n >= 0 && n <= h->tree.width[level], "n exceeds level width");
+  int rc = ensure_device(h);
+  if (rc) return rc;
+  B200RL_CUDA_OK(cudaMemcpyAsync(host_out, h->tree.pre[level], n * 4, cudaMemcpyDeviceToHost, as_stream(stream)));
   B200RL_CUDA_OK(cudaStreamSynchronize(as_stream(stream)));
   return B200RL_OK;
 }

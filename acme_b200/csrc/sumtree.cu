@@ -4,11 +4,19 @@
 // Stands in for Reverb's Prioritized selector as configured at acme/agents/tf/dqn/agent.py:95-101
 // (sampling) and for TFClient.update_priorities at acme/agents/tf/dqn/learning.py:151-154.
 //
-// Layout: level l (1..L) is a dense float array; the 32 children of node g are lvl[l][32g..32g+31]
-// = one 128-byte line, so a warp fetches a node with ONE coalesced load, scans it with shuffles
-// and descends.  The top levels are staged in shared memory once per CTA.  Every internal node is
-// lane 31 of the Kogge-Stone scan of its children, so sampling and update share one summation
-// order and the CPU oracle (oracle/sumtree.py) reproduces both bit for bit.
+// Layout.  Level l (1..L, L = leaves) keeps two dense float arrays of the same width:
+//   raw[l][32 g + j]  value of child j of node g (leaf level: the stored weight priority^alpha)
+//   pre[l][32 g + j]  SEQUENTIAL fp32 inclusive prefix  p_j = fl(p_{j-1} + raw_j)  over the 32 children
+// and raw[l-1][g] = pre[l][32 g + 31] (the root mass for l = 1).  A node's 32 prefixes are one
+// 128-byte line.  Sequential prefixes are monotone, so "first child with target < prefix" is just the
+// COUNT of prefixes <= target, and a child that is picked always has raw > 0:
+//   sampling needs no scan at all -- a group of 4 lanes reads the line (32 bytes each), counts, takes
+//   the largest prefix <= target as the exclusive prefix (two shuffles each) and descends; 8 samples per
+//   warp, the top levels staged in shared memory once per CTA;
+//   updates write leaves (last occurrence wins) and then recompute, level by level, the prefix line
+//   of every touched node with ONE THREAD PER NODE (32 dependent adds, no atomics).
+// The CPU oracle (oracle/sumtree.py) states the same arithmetic with np.cumsum(float32), so nodes,
+// sampled indices and probabilities are bit-exact.
 #include "common.cuh"
 
 namespace b200rl {
@@ -16,13 +24,55 @@ namespace b200rl {
 // ------------------------------------------------------------------------------------------ K1
 constexpr int kSampleThreads = 1024;
 
-template <int SPW>
+__device__ __forceinline__ void group_descend(const float* __restrict__ line, int gl, float& t, long long& node) {
+  // line: the 32 prefixes of the current node; this lane owns entries 8*gl .. 8*gl+7
+  const float4 a = *reinterpret_cast<const float4*>(line + gl * 8);
+  const float4 b = *reinterpret_cast<const float4*>(line + gl * 8 + 4);
+  const float p[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  int cnt = 0;
+  float mx = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool le = !(t < p[i]);       // prefix <= target
+    cnt += le ? 1 : 0;
+    mx = le ? fmaxf(mx, p[i]) : mx;    // prefixes are monotone: the largest one <= target is p[j-1]
+  }
+  cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+  cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+  int j = cnt;
+  if (__any_sync(0xffffffffu, j == 32)) {
+    // target >= node mass (fp rounding on the way down, or u*mass == mass): clamp to the last child
+    // whose prefix increased, i.e. the last child with a non-empty subtree
+    float prev = __shfl_up_sync(0xffffffffu, p[7], 1);
+    if (gl == 0) prev = 0.f;
+    int last = -1;
+    float before = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (p[i] > prev) { last = gl * 8 + i; before = prev; }
+      prev = p[i];
+    }
+#pragma unroll
+    for (int d = 1; d <= 2; d <<= 1) {
+      const int ol = __shfl_xor_sync(0xffffffffu, last, d);
+      const float ob = __shfl_xor_sync(0xffffffffu, before, d);
+      if (ol > last) { last = ol; before = ob; }
+    }
+    if (j == 32) { j = last < 0 ? 0 : last; mx = last < 0 ? 0.f : before; }
+  }
+  t = __fsub_rn(t, mx);
+  node = node * kFanout + j;
+}
+
+template <int SPG>   // samples interleaved per 4-lane group (memory-level parallelism for large batches)
 __global__ void __launch_bounds__(kSampleThreads)
 sample_kernel(TreeView t, int S, const ReplayState* __restrict__ st, long long M, int B,
               const float* __restrict__ u, int stratified, float shards_f,
               long long* __restrict__ idx, unsigned long long* __restrict__ keys,
               float* __restrict__ prob) {
-  extern __shared__ float staged[];
+  extern __shared__ __align__(16) float staged[];
   __shared__ int off[kMaxLevels];
   if (threadIdx.x == 0) {
     int o = 0;
@@ -33,75 +83,48 @@ sample_kernel(TreeView t, int S, const ReplayState* __restrict__ st, long long M
   }
   __syncthreads();
   for (int l = 1; l <= S; ++l) {
-    const float* src = t.lvl[l];
-    float* dst = staged + off[l];
-    for (int i = threadIdx.x; i < (int)t.width[l]; i += blockDim.x) dst[i] = src[i];
+    const float4* src = reinterpret_cast<const float4*>(t.pre[l]);
+    float4* dst = reinterpret_cast<float4*>(staged + off[l]);
+    for (int i = threadIdx.x; i < (int)(t.width[l] / 4); i += blockDim.x) dst[i] = src[i];
   }
   __syncthreads();
 
-  const int lane = threadIdx.x & 31;
-  const int warps_per_block = blockDim.x >> 5;
-  const long long warp_global = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-  const long long total_warps = (long long)gridDim.x * warps_per_block;
+  const int gl = threadIdx.x & 3;
+  const long long group_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  const long long total_groups = ((long long)gridDim.x * blockDim.x) >> 2;
   const float mass = t.lvl[0][0];
   const float denom = __fmul_rn(shards_f, mass);
   const unsigned long long tail = st->item_tail;
   const unsigned long long key_base = tail - tail % (unsigned long long)M;
+  const long long rounds = ((long long)B + total_groups * SPG - 1) / (total_groups * SPG);
 
-  for (long long base = warp_global * SPW; base < B; base += total_warps * SPW) {
-    float tg[SPW];
-    long long node[SPW];
-    float leaf[SPW];
+  for (long long r = 0; r < rounds; ++r) {     // every lane runs every round: the shuffles are warp-wide
+    float tg[SPG];
+    long long node[SPG], b[SPG];
 #pragma unroll
-    for (int s = 0; s < SPW; ++s) {
-      long long b = base + s;
-      float ub = (b < B) ? __ldg(u + b) : 0.f;
-      tg[s] = stratified ? __fmul_rn(__fdiv_rn(__fadd_rn((float)b, ub), (float)B), mass)
-                         : __fmul_rn(ub, mass);
+    for (int s = 0; s < SPG; ++s) {
+      b[s] = (r * SPG + s) * total_groups + group_global;
+      const float ub = (b[s] < B) ? __ldg(u + b[s]) : 0.f;
+      tg[s] = stratified ? __fmul_rn(__fdiv_rn(__fadd_rn((float)b[s], ub), (float)B), mass) : __fmul_rn(ub, mass);
       node[s] = 0;
-      leaf[s] = 0.f;
     }
 #pragma unroll 1
     for (int l = 1; l <= t.L; ++l) {
-      float c[SPW];
-      if (l <= S) {
-        const float* src = staged + off[l];
+      const float* base = (l <= S) ? staged + off[l] : t.pre[l];
 #pragma unroll
-        for (int s = 0; s < SPW; ++s) c[s] = src[node[s] * kFanout + lane];
-      } else {
-        const float* src = t.lvl[l];
-#pragma unroll
-        for (int s = 0; s < SPW; ++s) c[s] = __ldg(src + node[s] * kFanout + lane);
-      }
-#pragma unroll
-      for (int s = 0; s < SPW; ++s) {
-        float p = warp_ks_scan(c[s], lane);
-        unsigned ok = __ballot_sync(0xffffffffu, (tg[s] < p) && (c[s] > 0.f));
-        int j;
-        if (ok) {
-          j = __ffs(ok) - 1;
-        } else {
-          unsigned nz = __ballot_sync(0xffffffffu, c[s] > 0.f);
-          j = nz ? 31 - __clz(nz) : 0;
-        }
-        float pm1 = __shfl_sync(0xffffffffu, p, j > 0 ? j - 1 : 0);
-        tg[s] = __fsub_rn(tg[s], j > 0 ? pm1 : 0.f);
-        node[s] = node[s] * kFanout + j;
-        leaf[s] = __shfl_sync(0xffffffffu, c[s], j);
-      }
+      for (int s = 0; s < SPG; ++s) group_descend(base + node[s] * kFanout, gl, tg[s], node[s]);
     }
-    if (lane == 0) {
+    if (gl == 0) {
 #pragma unroll
-      for (int s = 0; s < SPW; ++s) {
-        long long b = base + s;
-        if (b < B) {
-          idx[b] = node[s];
+      for (int s = 0; s < SPG; ++s) {
+        if (b[s] < B) {
+          idx[b[s]] = node[s];
           if (keys) {
             unsigned long long k = key_base + (unsigned long long)node[s];
             if (k < tail) k += (unsigned long long)M;
-            keys[b] = k;
+            keys[b[s]] = k;
           }
-          prob[b] = __fdiv_rn(leaf[s], denom);
+          prob[b[s]] = __fdiv_rn(__ldg(t.lvl[t.L] + node[s]), denom);
         }
       }
     }
@@ -131,7 +154,7 @@ int tree_sample(const TreeView& t, const ReplayState* st_dev, int64_t M, int B, 
   static bool attr_set = false;
   if (!attr_set) {
     B200RL_CUDA_OK(cudaFuncSetAttribute(sample_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    B200RL_CUDA_OK(cudaFuncSetAttribute(sample_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    B200RL_CUDA_OK(cudaFuncSetAttribute(sample_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   const bool large = B >= 16384;
@@ -140,18 +163,17 @@ int tree_sample(const TreeView& t, const ReplayState* st_dev, int64_t M, int B, 
   size_t smem = (size_t)staged_bytes(t, S);
   if (staged_out) *staged_out = S;
   if (!large) {
-    int warps = B;
-    int blocks = (int)ceil_div<int64_t>(warps, 4);
-    sample_kernel<1><<<blocks, 128, smem, stream>>>(t, S, st_dev, M, B, u, stratified,
-                                                    (float)shard_count, (long long*)idx,
-                                                    (unsigned long long*)keys, prob);
+    const int threads = 128;                                    // 32 samples per CTA
+    int blocks = (int)ceil_div<int64_t>((int64_t)B * 4, threads);
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    sample_kernel<1><<<blocks, threads, smem, stream>>>(t, S, st_dev, M, B, u, stratified, (float)shard_count,
+                                                        (long long*)idx, (unsigned long long*)keys, prob);
   } else {
-    const bool fat = smem > 100 * 1024;  // one 1024-thread CTA per SM, else two 512-thread CTAs
+    const bool fat = smem > 100 * 1024;   // one 1024-thread CTA per SM when the staged levels are big
     int threads = fat ? 1024 : 512;
-    int blocks = kNumSMs * (fat ? 1 : 2);
-    sample_kernel<4><<<blocks, threads, smem, stream>>>(
-        t, S, st_dev, M, B, u, stratified, (float)shard_count, (long long*)idx,
-        (unsigned long long*)keys, prob);
+    int blocks = kNumSMs * (fat ? 1 : 4);
+    sample_kernel<2><<<blocks, threads, smem, stream>>>(t, S, st_dev, M, B, u, stratified, (float)shard_count,
+                                                        (long long*)idx, (unsigned long long*)keys, prob);
   }
   B200RL_LAUNCH_OK();
   return B200RL_OK;
@@ -182,15 +204,30 @@ __device__ __forceinline__ void load_entry(const ScatterSrc& s, const ReplayStat
   }
 }
 
-// recompute the parent of group g at level l: parent = lane 31 of the scan of its 32 children
-__device__ __forceinline__ void recompute_parent(const TreeView& t, int l, long long g, int lane) {
-  float c = t.lvl[l][g * kFanout + lane];
-  float p = warp_ks_scan(c, lane);
-  if (lane == 31) t.lvl[l - 1][l == 1 ? 0 : g] = p;
+// One thread recomputes the prefix line of node g at level l from its 32 children and the node's own
+// value one level up: p_j = fl(p_{j-1} + raw_j), sequential in fp32 (np.cumsum(float32) on the CPU).
+__device__ __forceinline__ void recompute_node(const TreeView& t, int l, long long g) {
+  const float4* src = reinterpret_cast<const float4*>(t.lvl[l] + g * kFanout);
+  float4* dst = reinterpret_cast<float4*>(t.pre[l] + g * kFanout);
+  float4 c[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) c[q] = src[q];
+  float acc = 0.f;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    float4 o;
+    acc = __fadd_rn(acc, c[q].x); o.x = acc;
+    acc = __fadd_rn(acc, c[q].y); o.y = acc;
+    acc = __fadd_rn(acc, c[q].z); o.z = acc;
+    acc = __fadd_rn(acc, c[q].w); o.w = acc;
+    dst[q] = o;
+  }
+  t.lvl[l - 1][l == 1 ? 0 : g] = acc;
 }
 
 // One CTA does the whole update for n <= 1024: leaf scatter with "last occurrence wins", then one
-// pass per level; only __syncthreads between levels, no atomics anywhere.
+// pass per level (thread e recomputes the ancestor of entry e);
+// only __syncthreads between levels, no atomics anywhere.
 __global__ void __launch_bounds__(1024)
 scatter_small_kernel(TreeView t, ScatterSrc src, const ReplayState* __restrict__ st, int n) {
   __shared__ int spos[1024];
@@ -206,28 +243,11 @@ scatter_small_kernel(TreeView t, ScatterSrc src, const ReplayState* __restrict__
     if (winner) t.lvl[t.L][pos] = w;
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int l = t.L; l >= 1; --l) {
     const int shift = 5 * (t.L - l + 1);
-    // each warp owns entries warp, warp + nwarps, ...; the (independent) node loads of up to 8 entries
-    // are issued before the first scan so that their latencies overlap
-    for (int e0 = warp; e0 < n; e0 += nwarps * 8) {
-      float c[8];
-      long long g[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int e = e0 + j * nwarps;
-        const int p = e < n ? spos[e] : -1;
-        g[j] = p < 0 ? -1 : ((long long)p >> shift);
-        c[j] = g[j] < 0 ? 0.f : t.lvl[l][g[j] * kFanout + lane];
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (g[j] < 0) continue;
-        float p = warp_ks_scan(c[j], lane);
-        if (lane == 31) t.lvl[l - 1][l == 1 ? 0 : g[j]] = p;
-      }
-    }
+    // entries that share a node recompute it redundantly and write identical values (cheaper than
+    // electing one of them: the whole level is one load latency + 32 adds)
+    if (pos >= 0) recompute_node(t, l, pos >> shift);
     __syncthreads();
   }
 }
@@ -256,34 +276,32 @@ __global__ void scatter_leaf_kernel(TreeView t, ScatterSrc src, const ReplayStat
   if (pos >= 0 && stamp[pos] == ((*epoch << 32) | (unsigned long long)(unsigned)i)) t.lvl[t.L][pos] = w;
 }
 
-// sparse level pass: one warp per entry recomputes that entry's ancestor at level l-1
+// sparse level pass: thread e recomputes the ancestor (at level l-1) of entry e
 __global__ void scatter_level_sparse_kernel(TreeView t, ScatterSrc src,
                                             const ReplayState* __restrict__ st, int n, int l) {
-  const int lane = threadIdx.x & 31;
-  long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
   long long pos;
   float w;
-  load_entry(src, st, (int)e, pos, w);
+  load_entry(src, st, e, pos, w);
   if (pos < 0) return;
-  recompute_parent(t, l, pos >> (5 * (t.L - l + 1)), lane);
+  recompute_node(t, l, pos >> (5 * (t.L - l + 1)));
 }
 
 // dense level pass: recompute every node of level l-1 from level l
 __global__ void level_dense_kernel(TreeView t, int l, long long groups) {
-  const int lane = threadIdx.x & 31;
-  long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long stride = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (; g < groups; g += stride) recompute_parent(t, l, g, lane);
+  long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; g < groups; g += stride) recompute_node(t, l, g);
 }
 
 __global__ void epoch_bump_kernel(unsigned long long* epoch) { *epoch += 1; }
 
 static int launch_dense_level(const TreeView& t, int l, cudaStream_t stream) {
   long long groups = t.width[l] / kFanout;
-  long long blocks = ceil_div<long long>(groups * 32, 256);
-  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  level_dense_kernel<<<(int)blocks, 256, 0, stream>>>(t, l, groups);
+  long long blocks = ceil_div<long long>(groups, 128);
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  level_dense_kernel<<<(int)blocks, 128, 0, stream>>>(t, l, groups);
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }
@@ -301,7 +319,8 @@ static int tree_scatter_impl(const TreeView& t, const ScatterSrc& src, const Rep
                              cudaStream_t stream) {
   if (n <= 0) return B200RL_OK;
   if (n <= 1024) {
-    scatter_small_kernel<<<1, 1024, 0, stream>>>(t, src, st_dev, n);   // 32 warps share the per-level node recomputes
+    int threads = ((n + 31) / 32) * 32;
+    scatter_small_kernel<<<1, threads, 0, stream>>>(t, src, st_dev, n);
     B200RL_LAUNCH_OK();
     return B200RL_OK;
   }
@@ -318,8 +337,7 @@ static int tree_scatter_impl(const TreeView& t, const ScatterSrc& src, const Rep
       int rc = launch_dense_level(t, l, stream);
       if (rc) return rc;
     } else {
-      long long b = ceil_div<long long>((long long)n * 32, 256);
-      scatter_level_sparse_kernel<<<(int)b, 256, 0, stream>>>(t, src, st_dev, n, l);
+      scatter_level_sparse_kernel<<<ceil_div(n, 128), 128, 0, stream>>>(t, src, st_dev, n, l);
       B200RL_LAUNCH_OK();
     }
   }

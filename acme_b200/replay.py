@@ -217,6 +217,14 @@ class Table:
                _capi.current_stream())
     return out
 
+  def read_tree_prefix(self, level: int) -> np.ndarray:
+    w = C.c_int64()
+    _capi.call('b200rl_replay_tree_level_width', self.handle, level, C.byref(w))
+    out = np.empty(w.value, np.float32)
+    _capi.call('b200rl_replay_tree_read_prefix', self.handle, level, out.ctypes.data, w.value,
+               _capi.current_stream())
+    return out
+
   def mass_ptr(self) -> int:
     p = C.c_void_p()
     _capi.call('b200rl_replay_mass_ptr', self.handle, C.byref(p))

@@ -109,11 +109,13 @@ int b200rl_replay_update_priorities(b200rl_replay* h, int32_t B, const uint64_t*
 /* Host view of the table (synchronises `stream`): live items, key range, total mass. */
 int b200rl_replay_info(b200rl_replay* h, int64_t* size, uint64_t* head_key, uint64_t* tail_key,
                        float* total_mass, void* stream);
-/* Tree geometry + raw level access (tests, checkpointing).  level 0 = root .. L = leaves. */
+/* Tree geometry + raw level access (tests, checkpointing).  level 0 = root .. L = leaves (child values). */
 int b200rl_replay_tree_levels(b200rl_replay* h, int32_t* num_levels, int32_t* fanout,
                               int32_t* staged_levels);
 int b200rl_replay_tree_level_width(b200rl_replay* h, int32_t level, int64_t* width);
 int b200rl_replay_tree_read(b200rl_replay* h, int32_t level, float* host_out, int64_t n, void* stream);
+/* the sequential-prefix lines of level 1..L (what the sampler reads) */
+int b200rl_replay_tree_read_prefix(b200rl_replay* h, int32_t level, float* host_out, int64_t n, void* stream);
 /* Device address of the root mass (one float) for cross-shard normalisation. */
 int b200rl_replay_mass_ptr(b200rl_replay* h, float** mass_dev);
 

@@ -7,12 +7,12 @@ items with zero weight are never drawn, updates are applied in order (last wins)
 
 The *arithmetic order* is this project's own and is shared bit-for-bit with the CUDA
 kernels in `acme_b200/csrc/sumtree.cu`:
-  * every internal node = element 31 of the Kogge-Stone inclusive scan of its 32 children
-    (`x[i] += x[i-d]` for d = 1,2,4,8,16, fp32 round-to-nearest each add) -- this is what a
-    warp computes with `__shfl_up_sync`;
+  * every node keeps the SEQUENTIAL fp32 inclusive prefixes of its 32 children,
+    p_j = fl(p_{j-1} + c_j) (= np.cumsum on float32), and the node's own value is p_31;
   * stratified target  t_b = ((b + u_b) / B) * M, plain draw t_b = u_b * M  (fp32 ops);
-  * descent: in a node pick the first child c with  t < scan[c]  and  child[c] > 0; if none,
-    the last child with child[c] > 0; then t -= scan[c-1] (0 for c = 0);
+  * descent: j = number of prefixes <= t (prefixes are monotone, so this is the first child
+    with t < p_j, and such a child always has c_j > 0); if j == 32 (t >= node mass after
+    rounding) j = last child whose prefix increased (0 if none); then t -= p_{j-1} (0 for j = 0);
   * probability = leaf / M (fp32 IEEE division).
 """
 
@@ -38,12 +38,15 @@ def level_width(capacity: int, L: int, lvl: int) -> int:
   return -(-w // F) * F
 
 
-def ks_scan(x: np.ndarray) -> np.ndarray:
-  """Kogge-Stone inclusive scan along the last axis (length 32), fp32."""
-  x = np.array(x, dtype=_f32, copy=True)
-  for d in (1, 2, 4, 8, 16):
-    x[..., d:] = x[..., d:] + x[..., :-d].copy()
-  return x
+def seq_scan(x: np.ndarray) -> np.ndarray:
+  """Sequential fp32 inclusive prefix along the last axis (length 32): p_j = fl(p_{j-1} + x_j)."""
+  x = np.asarray(x, dtype=_f32)
+  out = np.empty_like(x)
+  acc = np.zeros(x.shape[:-1], _f32)
+  for j in range(x.shape[-1]):
+    acc = (acc + x[..., j]).astype(_f32)
+    out[..., j] = acc
+  return out
 
 
 def weight_from_priority(p, alpha) -> np.ndarray:
@@ -72,7 +75,7 @@ class SumTree:
   def rebuild(self):
     for l in range(self.L, 0, -1):
       child = self.levels[l].reshape(-1, F)
-      sums = ks_scan(child)[:, F - 1]
+      sums = seq_scan(child)[:, F - 1]
       if l == 1:
         self.levels[0][0] = sums[0]
       else:
@@ -87,7 +90,7 @@ class SumTree:
     touched = np.unique(positions)
     for l in range(self.L, 0, -1):
       touched = np.unique(touched // F)
-      sums = ks_scan(self.levels[l].reshape(-1, F)[touched])[:, F - 1]
+      sums = seq_scan(self.levels[l].reshape(-1, F)[touched])[:, F - 1]
       if l == 1:
         self.levels[0][0] = sums[0]
       else:
@@ -110,16 +113,16 @@ class SumTree:
     rows = np.arange(B)
     for l in range(1, self.L + 1):
       child = self.levels[l].reshape(-1, F)[node]            # [B, 32]
-      scan = ks_scan(child)
-      ok = (t[:, None] < scan) & (child > 0)
-      any_ok = ok.any(axis=1)
-      first = np.argmax(ok, axis=1)
-      nz = child > 0
-      last_nz = np.where(nz.any(axis=1), (F - 1) - np.argmax(nz[:, ::-1], axis=1), 0)
-      c = np.where(any_ok, first, last_nz)
-      excl = np.where(c > 0, scan[rows, np.maximum(c - 1, 0)], _f32(0)).astype(_f32)
+      scan = seq_scan(child)
+      j = (scan <= t[:, None]).sum(axis=1)                   # first child with t < prefix
+      prev = np.concatenate([np.zeros((B, 1), _f32), scan[:, :-1]], axis=1)
+      inc = scan > prev
+      last_inc = np.where(inc.any(axis=1), (F - 1) - np.argmax(inc[:, ::-1], axis=1), 0)
+      j = np.where(j == F, last_inc, j)
+      excl = prev[rows, j]
+      excl = np.where((j == 0), _f32(0), excl).astype(_f32)
       t = (t - excl).astype(_f32)
-      node = node * F + c
+      node = node * F + j
     leaf = self.levels[self.L][node]
     with np.errstate(divide='ignore', invalid='ignore'):
       prob = (leaf / self.total).astype(_f32)

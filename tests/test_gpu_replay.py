@@ -78,6 +78,10 @@ def test_lockstep_with_oracle(n_step, alpha, max_size):
   helpers.sync_oracle_leaves(table, oracle)
   for l in range(oracle.tree.L + 1):
     np.testing.assert_array_equal(table.read_tree_level(l)[:oracle.tree.levels[l].shape[0]], oracle.tree.levels[l])
+  from oracle import sumtree as ost
+  for l in range(1, oracle.tree.L + 1):   # the prefix lines the sampler reads = sequential fp32 scan of the children
+    want = ost.seq_scan(oracle.tree.levels[l].reshape(-1, 32)).reshape(-1)
+    np.testing.assert_array_equal(table.read_tree_prefix(l)[:want.shape[0]], want)
   B = 128
   ds = replay.ReplayDataset(table, B)
   for stratified in (True, False):
