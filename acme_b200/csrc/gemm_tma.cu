@@ -1,0 +1,279 @@
+// K6, speed mode, dense layers: TMA-fed tf32 GEMM on tcgen05 (fp32 operands straight from HBM, no
+// register staging, no conversion pass, no bf16 copies).
+//
+//   producer (1 thread)  cp.async.bulk.tensor.2d (TMA, 128-byte swizzle) -> 4-stage shared-memory ring,
+//                        completion by mbarrier transaction bytes
+//   MMA      (1 thread)  tcgen05.mma.cta_group::1.kind::tf32  (M = 128, N = BN, K = 8 per instruction),
+//                        accumulator in TMEM; tcgen05.commit frees the stage / signals the epilogue
+//   epilogue (4 warps)   tcgen05.ld -> bias / activation / activation-derivative mask -> float4 stores
+//                        (or split-K partials)
+// An operand whose memory-contiguous direction is the reduction index is loaded K-major (box = 32 k x
+// rows); otherwise MN-major (boxes of 32 rows/columns x 32 k, the smem image is the same 128-byte
+// swizzled rows, only the instruction descriptor's major bit and the LBO/SBO strides differ), so the
+// data-gradient and weight-gradient products need no transposed copies.
+// Used for linear fwd / dgrad / wgrad whenever the matrices satisfy TMA's 16-byte stride rule; the
+// accessor-fed kernel in gemm_tc.cu covers the convolutions and everything else.
+#include <algorithm>
+
+#include <cuda.h>
+
+#include "common.cuh"
+#include "gemm_common.cuh"
+#include "tc_common.cuh"
+
+namespace b200rl {
+
+__device__ unsigned long long* g_tma_timeline = nullptr;   // tools/tc_timeline.py
+__device__ __forceinline__ void tm_mark(int slot) {
+  if (g_tma_timeline && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_tma_timeline[slot] = t;
+  }
+}
+
+constexpr int GBM = 128, GBK = 32 /* fp32 elements = 128 bytes */, G_STAGES = 3, G_THREADS = 192;
+
+// ---- tensor maps (driver entry point fetched at run time: no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// fp32 matrix X[lines][pos] (pos contiguous, row stride ld floats); box = box_pos x box_lines
+static bool make_map(CUtensorMap* m, const float* p, int64_t lines, int64_t pos, int64_t ld, int box_pos, int box_lines,
+                     bool mn_major) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)pos, (cuuint64_t)lines};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_pos, (cuuint32_t)box_lines};
+  cuuint32_t es[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)p, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             // MN-major tf32 operands only exist in the 32-byte-atom flavour of the 128-byte swizzle
+             mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+static bool tma_ok(const float* p, int64_t ld) { return (((uintptr_t)p) & 15) == 0 && (ld * 4) % 16 == 0; }
+
+// ---- device helpers
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 128-byte-swizzled tile: start address, LBO, SBO (bytes), version 1, layout type 2 (SWIZZLE_128B, 16-byte
+// atoms: K-major operands) or 1 (SWIZZLE_128B_BASE32B, 32-byte atoms: the only layout for MN-major tf32)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint64_t layout) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (layout << 61);
+}
+// kind::tf32: D = f32 (bits 4-5 = 1), A = B = tf32 (format 2 at bits 7-9 / 10-12), major bits 15 / 16
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// C[row, col] = sum_k A(row, k) B(k, col).  Tile coordinates for the maps:
+//   K-major operand : one box {32 k, R rows}       at (k0, row0)
+//   MN-major operand: R/32 boxes {32 rows, 32 k}   at (row0 + 32 j, k0), stacked 4 KB apart
+template <bool AMN, bool BMN, int BN>
+__global__ void __launch_bounds__(G_THREADS)
+tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, Epilogue epi,
+                int M, int N, int K, int kblocks_per_split) {
+  constexpr int A_BYTES = GBM * 128, B_BYTES = BN * 128, STAGE = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // 128-byte swizzle atoms are 1 KB
+  __shared__ __align__(8) uint64_t bar_full[G_STAGES], bar_empty[G_STAGES], bar_done;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row0 = blockIdx.y * GBM, col0 = blockIdx.x * BN;
+  const int total_kblocks = (K + GBK - 1) / GBK;
+  const int kb_begin = blockIdx.z * kblocks_per_split;
+  const int nkb = min(total_kblocks, kb_begin + kblocks_per_split) - kb_begin;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < G_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+    mbar_init(&bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_smem;
+  if (tid == 0) tm_mark(0);
+
+  if (warp == 0 && lane == 0) {
+    // ---------------- TMA producer
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % G_STAGES;
+      if (i >= G_STAGES) mbar_wait(&bar_empty[s], ((i / G_STAGES) - 1) & 1);
+      mbar_expect_tx(&bar_full[s], STAGE);
+      const uint32_t sa = base + s * STAGE, sb = sa + A_BYTES;
+      const int k0 = (kb_begin + i) * GBK;
+      if (AMN) {
+#pragma unroll
+        for (int j = 0; j < GBM / 32; ++j) tma_load_2d(sa + j * 4096, &map_a, row0 + 32 * j, k0, &bar_full[s]);
+      } else {
+        tma_load_2d(sa, &map_a, k0, row0, &bar_full[s]);
+      }
+      if (BMN) {
+#pragma unroll
+        for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * 4096, &map_b, col0 + 32 * j, k0, &bar_full[s]);
+      } else {
+        tma_load_2d(sb, &map_b, k0, col0, &bar_full[s]);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---------------- MMA issuer
+    constexpr uint32_t idesc = umma_idesc_tf32(GBM, BN, AMN, BMN);
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % G_STAGES;
+      mbar_wait(&bar_full[s], (i / G_STAGES) & 1);
+      if (i < 8) tm_mark(1 + i);
+      tc_fence_after();
+      const uint32_t sa = base + s * STAGE, sb = sa + A_BYTES;
+#pragma unroll
+      for (int kk = 0; kk < GBK / 8; ++kk) {
+        // K-major : 8 k = 32 bytes inside the swizzled 128-byte row; 8-row groups 1 KB apart (SBO)
+        // MN-major: 8 k = 8 rows of 128 bytes = two 4-row swizzle atoms 512 B apart (SBO); 32-wide row/column
+        //           blocks 4 KB apart (LBO)
+        const uint64_t da = AMN ? umma_desc_sw128(sa + kk * 1024, 4096, 512, 1) : umma_desc_sw128(sa + kk * 32, 16, 1024, 2);
+        const uint64_t db = BMN ? umma_desc_sw128(sb + kk * 1024, 4096, 512, 1) : umma_desc_sw128(sb + kk * 32, 16, 1024, 2);
+        umma_tf32(tmem_d, da, db, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+      }
+      umma_commit(&bar_empty[s]);
+      if (i == nkb - 1) umma_commit(&bar_done);
+    }
+  } else if (warp >= 2) {
+    // ---------------- epilogue: warp w may read TMEM lanes 32 * (w % 4) ..
+    if (nkb > 0) {
+      mbar_wait(&bar_done, 0);
+      tc_fence_after();
+    }
+    if (tid == 64) tm_mark(10);
+    const int lane_base = (warp & 3) * 32;
+    const int row = row0 + lane_base + lane;
+#pragma unroll 1
+    for (int cc = 0; cc < BN; cc += 16) {
+      float v[16];
+      if (nkb > 0) tmem_ld16(tmem_d + ((uint32_t)lane_base << 16) + (uint32_t)cc, v);
+      else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+      }
+      if (row < M) finish16(epi, row, col0 + cc, N, M, v);
+    }
+  }
+  if (tid == 64) tm_mark(11);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_d, TMEM_COLS);
+  if (tid == 32) tm_mark(12);
+}
+
+template <bool AMN, bool BMN, int BN>
+static int launch_tma_bn(const CUtensorMap& ma, const CUtensorMap& mb, Epilogue epi, int M, int N, int K, void* ws,
+                         int64_t ws_bytes, cudaStream_t stream) {
+  constexpr int smem = G_STAGES * (GBM * 128 + BN * 128) + 1024;
+  static bool attr = false;
+  if (!attr) {
+    B200RL_CUDA_OK(cudaFuncSetAttribute(tma_gemm_kernel<AMN, BMN, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  const int tiles = ceil_div(M, GBM) * ceil_div(N, BN);
+  const int kblocks = ceil_div(K, GBK);
+  int splits = 1;
+  if (tiles < kNumSMs && kblocks >= 16) {
+    splits = std::min(ceil_div(kNumSMs, tiles), kblocks / 8);
+    splits = std::min(splits, 64);
+    const int64_t cap = ws ? ws_bytes / ((int64_t)M * N * 4) : 0;
+    splits = (int)std::max<int64_t>(1, std::min<int64_t>(splits, cap));
+  }
+  const int kps = ceil_div(kblocks, splits);
+  splits = ceil_div(kblocks, kps);
+  epi.partial = splits > 1 ? (float*)ws : nullptr;
+  dim3 grid(ceil_div(N, BN), ceil_div(M, GBM), splits);
+  tma_gemm_kernel<AMN, BMN, BN><<<grid, G_THREADS, smem, stream>>>(ma, mb, epi, M, N, K, kps);
+  B200RL_LAUNCH_OK();
+  if (splits > 1) return launch_splitk_finish(epi, M, N, splits, stream);
+  return B200RL_OK;
+}
+
+template <bool AMN, bool BMN>
+static int launch_tma(const CUtensorMap& ma, const CUtensorMap& mb, const Epilogue& epi, int M, int N, int K, int BN,
+                      void* ws, int64_t wsb, cudaStream_t s) {
+  if (BN == 32) return launch_tma_bn<AMN, BMN, 32>(ma, mb, epi, M, N, K, ws, wsb, s);
+  if (BN == 64) return launch_tma_bn<AMN, BMN, 64>(ma, mb, epi, M, N, K, ws, wsb, s);
+  return launch_tma_bn<AMN, BMN, 128>(ma, mb, epi, M, N, K, ws, wsb, s);
+}
+static int pick_bn(int N) { return N <= 32 ? 32 : (N <= 64 ? 64 : 128); }
+
+// ---- entry points; return 1 when the shapes do not satisfy TMA's rules (caller falls back to gemm_tc.cu)
+int tma_linear_fwd(int M, int N, int K, const float* x, int ldx, const float* w, const float* bias, float* y,
+                   int ldy, int act, void* ws, int64_t wsb, cudaStream_t s) {
+  if (!tma_ok(x, ldx) || !tma_ok(w, K) || K < GBK) return 1;
+  const int BN = pick_bn(N);
+  CUtensorMap ma, mb;
+  if (!make_map(&ma, x, M, K, ldx, GBK, GBM, false) || !make_map(&mb, w, N, K, K, GBK, BN, false)) return 1;
+  Epilogue e{y, ldy, bias, act, nullptr, 0, 0, nullptr, 0};
+  return launch_tma<false, false>(ma, mb, e, M, N, K, BN, ws, wsb, s);
+}
+int tma_linear_dgrad(int M, int N, int K, const float* dy, int lddy, const float* w, float* dx, int lddx,
+                     const float* mask, int ldmask, int mask_act, void* ws, int64_t wsb, cudaStream_t s) {
+  // dx[m, k] = sum_n dy[m, n] w[n, k]: A = dy K-major (reduction n contiguous), B = w MN-major (line = n, pos = k)
+  if (!tma_ok(dy, lddy) || !tma_ok(w, K) || N < GBK) return 1;
+  const int BN = pick_bn(K);
+  CUtensorMap ma, mb;
+  if (!make_map(&ma, dy, M, N, lddy, GBK, GBM, false) || !make_map(&mb, w, N, K, K, 32, GBK, true)) return 1;
+  Epilogue e{dx, lddx, nullptr, 0, mask, ldmask, mask_act, nullptr, 0};
+  return launch_tma<false, true>(ma, mb, e, M, K, N, BN, ws, wsb, s);
+}
+int tma_linear_wgrad(int M, int N, int K, const float* dy, int lddy, const float* x, int ldx, float* dw, float* db,
+                     void* ws, int64_t wsb, cudaStream_t s) {
+  // dw[n, k] = sum_m dy[m, n] x[m, k]: both operands MN-major (line = reduction m)
+  if (!tma_ok(dy, lddy) || !tma_ok(x, ldx) || M < GBK) return 1;
+  const int BN = pick_bn(K);
+  CUtensorMap ma, mb;
+  if (!make_map(&ma, dy, M, N, lddy, 32, GBK, true) || !make_map(&mb, x, M, K, ldx, 32, GBK, true)) return 1;
+  Epilogue e{dw, K, nullptr, 0, nullptr, 0, 0, nullptr, 0};
+  int rc = launch_tma<true, true>(ma, mb, e, N, K, M, BN, ws, wsb, s);
+  if (rc) return rc;
+  if (db) return launch_colsum(M, N, dy, lddy, db, ws, wsb, s);
+  return B200RL_OK;
+}
+
+}  // namespace b200rl
+
+extern "C" int b200rl_debug_tma_timeline(unsigned long long* buf_dev) {
+  cudaError_t e = cudaMemcpyToSymbol(b200rl::g_tma_timeline, &buf_dev, sizeof(buf_dev));
+  return e == cudaSuccess ? 0 : -2;
+}

@@ -28,9 +28,19 @@ int tc_conv_wgrad(const void* x, int x_u8, const float* dy, float* dw, float* db
                   void* ws, int64_t wsb, cudaStream_t s);
 int tc_conv_dgrad(const float* dy, const float* w, float* dx, const b200rl_conv_geom& g, const float* mask,
                   int mask_act, void* ws, int64_t wsb, cudaStream_t s);
+// gemm_tma.cu: return 1 = shapes not eligible for TMA (fall back to the accessor-fed kernel)
+int tma_linear_fwd(int M, int N, int K, const float* x, int ldx, const float* w, const float* bias, float* y,
+                   int ldy, int act, void* ws, int64_t wsb, cudaStream_t s);
+int tma_linear_dgrad(int M, int N, int K, const float* dy, int lddy, const float* w, float* dx, int lddx,
+                     const float* mask, int ldmask, int mask_act, void* ws, int64_t wsb, cudaStream_t s);
+int tma_linear_wgrad(int M, int N, int K, const float* dy, int lddy, const float* x, int ldx, float* dw, float* db,
+                     void* ws, int64_t wsb, cudaStream_t s);
 }  // namespace b200rl
 
 using namespace b200rl;
+
+static bool g_use_tma = true;
+extern "C" int b200rl_debug_set_tma(int on) { g_use_tma = on != 0; return 0; }
 
 static int check_geom(const b200rl_conv_geom* g) {
   B200RL_REQUIRE(g, "null geometry");
@@ -73,6 +83,10 @@ extern "C" int b200rl_linear_fwd(int32_t M, int32_t N, int32_t K, const float* x
                                  const float* bias, float* y, int32_t ldy, int act, int precision, void* ws,
                                  int64_t wsb, void* stream) {
   B200RL_REQUIRE(x && w && y && M >= 1 && N >= 1 && K >= 1 && ldx >= K && ldy >= N, "bad argument");
+  if (precision == 1 && g_use_tma) {
+    int rc = tma_linear_fwd(M, N, K, x, ldx, w, bias, y, ldy, act, ws, wsb, as_stream(stream));
+    if (rc != 1) return rc;
+  }
   PRECISION_SWITCH(simt_linear_fwd(M, N, K, x, ldx, w, bias, y, ldy, act, ws, wsb, as_stream(stream)),
                    tc_linear_fwd(M, N, K, x, ldx, w, bias, y, ldy, act, ws, wsb, as_stream(stream)));
 }
@@ -80,12 +94,20 @@ extern "C" int b200rl_linear_dgrad(int32_t M, int32_t N, int32_t K, const float*
                                    float* dx, int32_t lddx, const float* mask_y, int mask_act, int precision,
                                    void* ws, int64_t wsb, void* stream) {
   B200RL_REQUIRE(dy && w && dx && M >= 1 && N >= 1 && K >= 1 && lddy >= N && lddx >= K, "bad argument");
+  if (precision == 1 && g_use_tma && (!mask_y || (((uintptr_t)mask_y | (uintptr_t)dx) & 15) == 0)) {
+    int rc = tma_linear_dgrad(M, N, K, dy, lddy, w, dx, lddx, mask_y, lddx, mask_act, ws, wsb, as_stream(stream));
+    if (rc != 1) return rc;
+  }
   PRECISION_SWITCH(simt_linear_dgrad(M, N, K, dy, lddy, w, dx, lddx, mask_y, lddx, mask_act, ws, wsb, as_stream(stream)),
                    tc_linear_dgrad(M, N, K, dy, lddy, w, dx, lddx, mask_y, lddx, mask_act, ws, wsb, as_stream(stream)));
 }
 extern "C" int b200rl_linear_wgrad(int32_t M, int32_t N, int32_t K, const float* dy, int32_t lddy, const float* x,
                                    int32_t ldx, float* dw, float* db, int precision, void* ws, int64_t wsb, void* stream) {
   B200RL_REQUIRE(dy && x && dw && M >= 1 && N >= 1 && K >= 1 && lddy >= N && ldx >= K, "bad argument");
+  if (precision == 1 && g_use_tma) {
+    int rc = tma_linear_wgrad(M, N, K, dy, lddy, x, ldx, dw, db, ws, wsb, as_stream(stream));
+    if (rc != 1) return rc;
+  }
   PRECISION_SWITCH(simt_linear_wgrad(M, N, K, dy, lddy, x, ldx, dw, db, ws, wsb, as_stream(stream)),
                    tc_linear_wgrad(M, N, K, dy, lddy, x, ldx, dw, db, ws, wsb, as_stream(stream)));
 }
