@@ -93,7 +93,8 @@ class DQNLearner(core.Learner, core.Saveable):
       return a.view(torch.int32).view(self.B)
     return a.view(getattr(torch, self._act_dtype.name)).view(self.B).to(torch.int32)
 
-  def _forward_loss(self):
+  def _forwards(self):
+    """K1 sample, K3 gather, the three forward passes (learning.py:117-125) [+ local IS-weight max]."""
     ds, net, tgt = self._dataset, self._net, self._tgt
     st = _capi.current_stream()
     o_tm1, o_t = self._obs_view(ds.o_tm1), self._obs_view(ds.o_t)
@@ -105,33 +106,43 @@ class DQNLearner(core.Learner, core.Saveable):
       for s in self._side:
         s.wait_event(start)
       with torch.cuda.stream(self._side[0]):
-        q_t_value = tgt.lane(1).forward(o_t, self._bufs_tgt)     # learning.py:124
+        tgt.lane(1).forward(o_t, self._bufs_tgt)                 # learning.py:124
       tgt.lane(0)
       with torch.cuda.stream(self._side[1]):
-        q_t_selector = net.lane(2).forward(o_t, self._bufs_sel)  # learning.py:125
-      q_tm1 = net.lane(0).forward(o_tm1, self._bufs_train)       # learning.py:123
+        net.lane(2).forward(o_t, self._bufs_sel)                 # learning.py:125
+      net.lane(0).forward(o_tm1, self._bufs_train)               # learning.py:123
       for s in self._side:
         done = torch.cuda.Event()
         done.record(s)
         main.wait_event(done)
     else:
-      q_tm1 = net.forward(o_tm1, self._bufs_train)               # learning.py:123
-      q_t_value = tgt.forward(o_t, self._bufs_tgt)               # learning.py:124
-      q_t_selector = net.forward(o_t, self._bufs_sel)            # learning.py:125
-    wmax = None
-    if self._world > 1:   # global max importance weight: allreduce(MAX) of one f64
+      net.forward(o_tm1, self._bufs_train)                       # learning.py:123
+      tgt.forward(o_t, self._bufs_tgt)                           # learning.py:124
+      net.forward(o_t, self._bufs_sel)                           # learning.py:125
+    if self._world > 1:   # local max importance weight; the all-reduce(MAX) of this one f64 follows
       _capi.call('b200rl_is_weight_max', self.B, _capi.ptr(ds.prob), self._beta, _capi.ptr(self._wmax), st)
-      self._dp.global_max_(self._wmax)
-      wmax = _capi.ptr(self._wmax)
-    _capi.call('b200rl_dqn_td', self.B, net.A, _capi.ptr(q_tm1), _capi.ptr(q_t_value), _capi.ptr(q_t_selector),
-               _capi.ptr(self._actions_i32()), _capi.ptr(ds.R), _capi.ptr(ds.D), _capi.ptr(ds.prob),
-               self._discount, self._delta, self._beta, self._max_abs_reward, wmax, 1.0 / self.B,
+
+  def _loss_backward(self):
+    """K4 (learning.py:127-154) and the backward pass through net(o_tm1)."""
+    ds, net = self._dataset, self._net
+    st = _capi.current_stream()
+    o_tm1 = self._obs_view(ds.o_tm1)
+    wmax = _capi.ptr(self._wmax) if self._world > 1 else None
+    _capi.call('b200rl_dqn_td', self.B, net.A, _capi.ptr(self._bufs_train['q']), _capi.ptr(self._bufs_tgt['q']),
+               _capi.ptr(self._bufs_sel['q']), _capi.ptr(self._actions_i32()), _capi.ptr(ds.R), _capi.ptr(ds.D),
+               _capi.ptr(ds.prob), self._discount, self._delta, self._beta, self._max_abs_reward, wmax, 1.0 / self.B,
                _capi.ptr(self.td), _capi.ptr(self.loss_ps), _capi.ptr(self.weight), _capi.ptr(self.priority),
                _capi.ptr(self.dq), _capi.ptr(self.loss), st)
     if self._concurrent:
       net.backward(o_tm1, self._bufs_train, self._gbufs, self.dq, side_stream=self._side[0])
     else:
       net.backward(o_tm1, self._bufs_train, self._gbufs, self.dq)
+
+  def _forward_loss(self):
+    self._forwards()
+    if self._world > 1:
+      self._dp.global_max_(self._wmax)
+    self._loss_backward()
 
   def _apply(self):
     net, tgt, st = self._net, self._tgt, _capi.current_stream()
@@ -155,26 +166,41 @@ class DQNLearner(core.Learner, core.Saveable):
     self._apply()
     self.kernel_launches_per_step = int(lib.b200rl_launch_count() - n0)
 
-  def _device_step(self, uniforms=None):
+  def _capture(self, fn):
     torch = self._torch
-    if self._world > 1:
-      self._eager_step(uniforms)
-      return
-    if not self._use_graph or uniforms is not None:
-      self._eager_step(uniforms)
+    g = torch.cuda.CUDAGraph()
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+      fn()
+    return g
+
+  def _device_step(self, uniforms=None):
+    """One update on the device.  Single GPU: the whole step is one CUDA graph.  Data parallel: three graphs
+    (forwards | loss + backward | apply) with the two NCCL all-reduces issued between them, so the host
+    does 5 launches per step instead of ~50."""
+    if not self._use_graph or uniforms is not None or self._steps_done < 2:
+      self._eager_step(uniforms)      # also the un-captured warm-up (one-time attribute setup inside the library)
       return
     if self._graphs is None:
-      if self._steps_done < 2:          # warm-up un-captured (one-time attribute setup inside the library)
-        self._eager_step(None)
-        return
-      g = torch.cuda.CUDAGraph()
-      torch.cuda.synchronize()
-      with torch.cuda.graph(g):
-        self._dataset.sample_raw()
-        self._forward_loss()
-        self._apply()
-      self._graphs = g
-    self._graphs.replay()
+      if self._world == 1:
+        def whole():
+          self._dataset.sample_raw()
+          self._forward_loss()
+          self._apply()
+        self._graphs = [self._capture(whole)]
+      else:
+        def first():
+          self._dataset.sample_raw()
+          self._forwards()
+        self._graphs = [self._capture(first), self._capture(self._loss_backward), self._capture(self._apply)]
+    if self._world == 1:
+      self._graphs[0].replay()
+    else:
+      self._graphs[0].replay()
+      self._dp.global_max_(self._wmax)            # 1 scalar: the global importance-weight normaliser
+      self._graphs[1].replay()
+      self._dp.sum_(self._net.params.grad)        # 32 MB of gradients over NVLink; Adam applies the 1/R
+      self._graphs[2].replay()
 
   # ------------------------------------------------------------------ acme.core.Learner
   def step(self, uniforms=None, fetch_loss: bool = True):
