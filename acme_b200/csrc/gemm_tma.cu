@@ -52,6 +52,42 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeIm2colFn get_encode_im2col() {
+  static EncodeIm2colFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeIm2colFn)p;
+  }
+  return fn;
+}
+// NHWC fp32 activation tensor viewed through TMA's im2col mode: one instruction loads `pixels` consecutive
+// output pixels (b, oy, ox order) x `channels` input channels of ONE filter tap; padding reads as zero.
+// Corners as in CUTLASS (conv/collective/detail.hpp): lower = -pad_before, upper = pad_after - (k - 1).
+static bool make_im2col_map(CUtensorMap* m, const float* x, const b200rl_conv_geom& g, int channels, int pixels,
+                            bool mn_major) {
+  EncodeIm2colFn enc = get_encode_im2col();
+  if (!enc) return false;
+  const int pad_bottom = (g.OH - 1) * g.stride + g.kh - g.H - g.pad_top;
+  const int pad_right = (g.OW - 1) * g.stride + g.kw - g.W - g.pad_left;
+  cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.B};
+  cuuint64_t strides[3] = {(cuuint64_t)g.C * 4, (cuuint64_t)g.W * g.C * 4, (cuuint64_t)g.H * g.W * g.C * 4};
+  int lower[2] = {-g.pad_left, -g.pad_top};
+  int upper[2] = {pad_right - (g.kw - 1), pad_bottom - (g.kh - 1)};
+  cuuint32_t es[4] = {1, (cuuint32_t)g.stride, (cuuint32_t)g.stride, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x, dims, strides, lower, upper, (cuuint32_t)channels,
+             (cuuint32_t)pixels, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // fp32 matrix X[lines][pos] (pos contiguous, row stride ld floats); box = box_pos x box_lines
 static bool make_map(CUtensorMap* m, const float* p, int64_t lines, int64_t pos, int64_t ld, int box_pos, int box_lines,
                      bool mn_major) {
@@ -74,6 +110,19 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
 }
+__device__ __forceinline__ void tma_load_im2col(uint32_t smem_dst, const CUtensorMap* map, int c, int w, int h, int n,
+                                                uint16_t off_w, uint16_t off_h, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w),
+      "h"(off_h)
+      : "memory");
+}
+// When A is the implicit im2col of a convolution input: k-block i = (filter tap, block of 32 channels)
+struct ConvA {
+  int enabled;
+  int C, kw, OW, OH, stride, pad_left, pad_top, taps;
+};
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -104,7 +153,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, bool a_mn, 
 template <bool AMN, bool BMN, int BN>
 __global__ void __launch_bounds__(G_THREADS)
 tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, Epilogue epi,
-                int M, int N, int K, int kblocks_per_split) {
+                int M, int N, int K, int kblocks_per_split, ConvA conv) {
   constexpr int A_BYTES = GBM * 128, B_BYTES = BN * 128, STAGE = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
   extern __shared__ uint8_t smem_raw[];
@@ -133,13 +182,44 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
   if (warp == 0 && lane == 0) {
     // ---------------- TMA producer
+    int ax = 0, ay = 0, an = 0;   // im2col anchor of the tile's first pixel (input coordinates)
+    if (conv.enabled) {
+      const int ox = row0 % conv.OW, t = row0 / conv.OW;
+      ax = ox * conv.stride - conv.pad_left;
+      ay = (t % conv.OH) * conv.stride - conv.pad_top;
+      an = t / conv.OH;
+    }
     for (int i = 0; i < nkb; ++i) {
       const int s = i % G_STAGES;
       if (i >= G_STAGES) mbar_wait(&bar_empty[s], ((i / G_STAGES) - 1) & 1);
-      mbar_expect_tx(&bar_full[s], STAGE);
       const uint32_t sa = base + s * STAGE, sb = sa + A_BYTES;
       const int k0 = (kb_begin + i) * GBK;
-      if (AMN) {
+      if (AMN && conv.enabled) {
+        // conv weight gradient: rows = patch indices (tap, channel), reduction = pixels.  Row block j of the tile
+        // is 32 channels of one tap for the 32 pixels of this k-block; blocks past the last tap are skipped
+        // (their accumulator rows are never stored).
+        const int ox = k0 % conv.OW, t = k0 / conv.OW;
+        const int px = ox * conv.stride - conv.pad_left, py = (t % conv.OH) * conv.stride - conv.pad_top, pn = t / conv.OH;
+        int nblk = 0;
+#pragma unroll
+        for (int j = 0; j < GBM / 32; ++j) nblk += ((row0 + 32 * j) / conv.C < conv.taps) ? 1 : 0;
+        mbar_expect_tx(&bar_full[s], nblk * 4096 + B_BYTES);
+#pragma unroll
+        for (int j = 0; j < GBM / 32; ++j) {
+          const int r = row0 + 32 * j, tap = r / conv.C;
+          if (tap < conv.taps)
+            tma_load_im2col(sa + j * 4096, &map_a, r % conv.C, px, py, pn, (uint16_t)(tap % conv.kw), (uint16_t)(tap / conv.kw),
+                            &bar_full[s]);
+        }
+      } else {
+        mbar_expect_tx(&bar_full[s], STAGE);
+      }
+      if (AMN && conv.enabled) {
+      } else if (!AMN && conv.enabled) {   // conv forward: 128 pixels x 32 channels of one tap
+        const int cb = conv.C / GBK, kb = kb_begin + i;
+        const int tap = kb / cb, c0 = (kb % cb) * GBK;
+        tma_load_im2col(sa, &map_a, c0, ax, ay, an, (uint16_t)(tap % conv.kw), (uint16_t)(tap / conv.kw), &bar_full[s]);
+      } else if (AMN) {
 #pragma unroll
         for (int j = 0; j < GBM / 32; ++j) tma_load_2d(sa + j * 4096, &map_a, row0 + 32 * j, k0, &bar_full[s]);
       } else {
@@ -202,7 +282,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
 template <bool AMN, bool BMN, int BN>
 static int launch_tma_bn(const CUtensorMap& ma, const CUtensorMap& mb, Epilogue epi, int M, int N, int K, void* ws,
-                         int64_t ws_bytes, cudaStream_t stream) {
+                         int64_t ws_bytes, cudaStream_t stream, const ConvA& conv) {
   constexpr int smem = G_STAGES * (GBM * 128 + BN * 128) + 1024;
   static bool attr = false;
   if (!attr) {
@@ -222,7 +302,7 @@ static int launch_tma_bn(const CUtensorMap& ma, const CUtensorMap& mb, Epilogue 
   splits = ceil_div(kblocks, kps);
   epi.partial = splits > 1 ? (float*)ws : nullptr;
   dim3 grid(ceil_div(N, BN), ceil_div(M, GBM), splits);
-  tma_gemm_kernel<AMN, BMN, BN><<<grid, G_THREADS, smem, stream>>>(ma, mb, epi, M, N, K, kps);
+  tma_gemm_kernel<AMN, BMN, BN><<<grid, G_THREADS, smem, stream>>>(ma, mb, epi, M, N, K, kps, conv);
   B200RL_LAUNCH_OK();
   if (splits > 1) return launch_splitk_finish(epi, M, N, splits, stream);
   return B200RL_OK;
@@ -230,10 +310,10 @@ static int launch_tma_bn(const CUtensorMap& ma, const CUtensorMap& mb, Epilogue 
 
 template <bool AMN, bool BMN>
 static int launch_tma(const CUtensorMap& ma, const CUtensorMap& mb, const Epilogue& epi, int M, int N, int K, int BN,
-                      void* ws, int64_t wsb, cudaStream_t s) {
-  if (BN == 32) return launch_tma_bn<AMN, BMN, 32>(ma, mb, epi, M, N, K, ws, wsb, s);
-  if (BN == 64) return launch_tma_bn<AMN, BMN, 64>(ma, mb, epi, M, N, K, ws, wsb, s);
-  return launch_tma_bn<AMN, BMN, 128>(ma, mb, epi, M, N, K, ws, wsb, s);
+                      void* ws, int64_t wsb, cudaStream_t s, const ConvA& conv = ConvA{0, 0, 0, 0, 0, 0, 0, 0, 0}) {
+  if (BN == 32) return launch_tma_bn<AMN, BMN, 32>(ma, mb, epi, M, N, K, ws, wsb, s, conv);
+  if (BN == 64) return launch_tma_bn<AMN, BMN, 64>(ma, mb, epi, M, N, K, ws, wsb, s, conv);
+  return launch_tma_bn<AMN, BMN, 128>(ma, mb, epi, M, N, K, ws, wsb, s, conv);
 }
 static int pick_bn(int N) { return N <= 32 ? 32 : (N <= 64 ? 64 : 128); }
 
@@ -268,6 +348,35 @@ int tma_linear_wgrad(int M, int N, int K, const float* dy, int lddy, const float
   int rc = launch_tma<true, true>(ma, mb, e, N, K, M, BN, ws, wsb, s);
   if (rc) return rc;
   if (db) return launch_colsum(M, N, dy, lddy, db, ws, wsb, s);
+  return B200RL_OK;
+}
+
+// conv forward with an fp32 NHWC input whose channel count is a multiple of 32: A = TMA im2col, B = weights
+int tma_conv_fwd(const float* x, const float* w, const float* bias, float* y, const b200rl_conv_geom& g, int act,
+                 void* ws, int64_t wsb, cudaStream_t s) {
+  const int M = g.B * g.OH * g.OW, K = g.kh * g.kw * g.C;
+  if (g.C % GBK != 0 || !tma_ok(x, g.C) || !tma_ok(w, K) || (int64_t)g.B * g.H * g.W * g.C * 4 < 131072) return 1;
+  const int BN = pick_bn(g.Cout);
+  CUtensorMap ma, mb;
+  if (!make_im2col_map(&ma, x, g, GBK, GBM, false) || !make_map(&mb, w, g.Cout, K, K, GBK, BN, false)) return 1;
+  Epilogue e{y, g.Cout, bias, act, nullptr, 0, 0, nullptr, 0};
+  ConvA conv{1, g.C, g.kw, g.OW, g.OH, g.stride, g.pad_left, g.pad_top, g.kh * g.kw};
+  return launch_tma<false, false>(ma, mb, e, M, g.Cout, K, BN, ws, wsb, s, conv);
+}
+
+// conv weight gradient, fp32 NHWC input with C % 32 == 0: dW^T[k, co] = sum_pixel col[pixel, k] dy[pixel, co]
+int tma_conv_wgrad(const float* x, const float* dy, float* dw, float* db, const b200rl_conv_geom& g, void* ws, int64_t wsb,
+                   cudaStream_t s) {
+  const int M = g.B * g.OH * g.OW, K = g.kh * g.kw * g.C;
+  if (g.C % GBK != 0 || !tma_ok(x, g.C) || !tma_ok(dy, g.Cout) || (int64_t)g.B * g.H * g.W * g.C * 4 < 131072 || M < GBK) return 1;
+  const int BN = pick_bn(g.Cout);
+  CUtensorMap ma, mb;
+  if (!make_im2col_map(&ma, x, g, 32, GBK, true) || !make_map(&mb, dy, M, g.Cout, g.Cout, 32, GBK, true)) return 1;
+  Epilogue e{dw, K, nullptr, 0, nullptr, 0, 0, nullptr, 1};   // stored transposed: dw[co][k]
+  ConvA conv{1, g.C, g.kw, g.OW, g.OH, g.stride, g.pad_left, g.pad_top, g.kh * g.kw};
+  int rc = launch_tma<true, true>(ma, mb, e, K, g.Cout, M, BN, ws, wsb, s, conv);
+  if (rc) return rc;
+  if (db) return launch_colsum(M, g.Cout, dy, g.Cout, db, ws, wsb, s);
   return B200RL_OK;
 }
 

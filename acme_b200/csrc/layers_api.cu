@@ -35,6 +35,10 @@ int tma_linear_dgrad(int M, int N, int K, const float* dy, int lddy, const float
                      const float* mask, int ldmask, int mask_act, void* ws, int64_t wsb, cudaStream_t s);
 int tma_linear_wgrad(int M, int N, int K, const float* dy, int lddy, const float* x, int ldx, float* dw, float* db,
                      void* ws, int64_t wsb, cudaStream_t s);
+int tma_conv_fwd(const float* x, const float* w, const float* bias, float* y, const b200rl_conv_geom& g, int act,
+                 void* ws, int64_t wsb, cudaStream_t s);
+int tma_conv_wgrad(const float* x, const float* dy, float* dw, float* db, const b200rl_conv_geom& g, void* ws, int64_t wsb,
+                   cudaStream_t s);
 }  // namespace b200rl
 
 using namespace b200rl;
@@ -61,6 +65,10 @@ extern "C" int b200rl_conv2d_fwd(const void* x, int x_u8, const float* w, const 
                                  const b200rl_conv_geom* g, int act, int precision, void* ws, int64_t wsb, void* stream) {
   B200RL_REQUIRE(x && w && y, "null argument");
   if (int rc = check_geom(g)) return rc;
+  if (precision == 1 && g_use_tma && !x_u8) {
+    int rc = tma_conv_fwd((const float*)x, w, bias, y, *g, act, ws, wsb, as_stream(stream));
+    if (rc != 1) return rc;
+  }
   PRECISION_SWITCH(simt_conv_fwd(x, x_u8, w, bias, y, *g, act, ws, wsb, as_stream(stream)),
                    tc_conv_fwd(x, x_u8, w, bias, y, *g, act, ws, wsb, as_stream(stream)));
 }
@@ -68,6 +76,10 @@ extern "C" int b200rl_conv2d_wgrad(const void* x, int x_u8, const float* dy, flo
                                    const b200rl_conv_geom* g, int precision, void* ws, int64_t wsb, void* stream) {
   B200RL_REQUIRE(x && dy && dw, "null argument");
   if (int rc = check_geom(g)) return rc;
+  if (precision == 1 && g_use_tma && !x_u8) {
+    int rc = tma_conv_wgrad((const float*)x, dy, dw, db, *g, ws, wsb, as_stream(stream));
+    if (rc != 1) return rc;
+  }
   PRECISION_SWITCH(simt_conv_wgrad(x, x_u8, dy, dw, db, *g, ws, wsb, as_stream(stream)),
                    tc_conv_wgrad(x, x_u8, dy, dw, db, *g, ws, wsb, as_stream(stream)));
 }

@@ -122,9 +122,14 @@ class DQNLearner(core.Learner, core.Saveable):
     if self._world > 1:   # local max importance weight; the all-reduce(MAX) of this one f64 follows
       _capi.call('b200rl_is_weight_max', self.B, _capi.ptr(ds.prob), self._beta, _capi.ptr(self._wmax), st)
 
-  def _loss_backward(self):
-    """K4 (learning.py:127-154) and the backward pass through net(o_tm1)."""
+  def _loss_backward(self, part: str = 'all'):
+    """K4 (learning.py:127-154) and the backward pass through net(o_tm1).  `part` lets the data-parallel
+    step cut the backward in two ('dense' = loss + head + fc1, 'conv' = the torso) so that the all-reduce
+    of the fc1/head gradients (99% of the bytes) overlaps the convolution backward."""
     ds, net = self._dataset, self._net
+    if part == 'conv':
+      net.backward_conv_part(self._obs_view(ds.o_tm1), self._bufs_train, self._gbufs, self._side[0])
+      return
     st = _capi.current_stream()
     o_tm1 = self._obs_view(ds.o_tm1)
     wmax = _capi.ptr(self._wmax) if self._world > 1 else None
@@ -133,7 +138,9 @@ class DQNLearner(core.Learner, core.Saveable):
                _capi.ptr(ds.prob), self._discount, self._delta, self._beta, self._max_abs_reward, wmax, 1.0 / self.B,
                _capi.ptr(self.td), _capi.ptr(self.loss_ps), _capi.ptr(self.weight), _capi.ptr(self.priority),
                _capi.ptr(self.dq), _capi.ptr(self.loss), st)
-    if self._concurrent:
+    if part == 'dense':
+      net.backward_dense_part(self._bufs_train, self._gbufs, self.dq, self._side[0])
+    elif self._concurrent:
       net.backward(o_tm1, self._bufs_train, self._gbufs, self.dq, side_stream=self._side[0])
     else:
       net.backward(o_tm1, self._bufs_train, self._gbufs, self.dq)
@@ -192,15 +199,31 @@ class DQNLearner(core.Learner, core.Saveable):
         def first():
           self._dataset.sample_raw()
           self._forwards()
-        self._graphs = [self._capture(first), self._capture(self._loss_backward), self._capture(self._apply)]
+        if self._concurrent and hasattr(self._net, 'grad_buckets'):
+          self._graphs = [self._capture(first), self._capture(lambda: self._loss_backward('dense')),
+                          self._capture(lambda: self._loss_backward('conv')), self._capture(self._apply)]
+        else:
+          self._graphs = [self._capture(first), self._capture(self._loss_backward), self._capture(self._apply)]
     if self._world == 1:
       self._graphs[0].replay()
-    else:
+    elif len(self._graphs) == 3:
       self._graphs[0].replay()
       self._dp.global_max_(self._wmax)            # 1 scalar: the global importance-weight normaliser
       self._graphs[1].replay()
       self._dp.sum_(self._net.params.grad)        # 32 MB of gradients over NVLink; Adam applies the 1/R
       self._graphs[2].replay()
+    else:
+      import torch.distributed as dist
+      g = self._net.params.grad
+      (o1, n1), (o0, n0) = self._net.grad_buckets()
+      self._graphs[0].replay()
+      self._dp.global_max_(self._wmax)
+      self._graphs[1].replay()                    # loss, head and fc1 backward: the tail of the gradient buffer is final
+      work = dist.all_reduce(g[o1:o1 + n1], op=dist.ReduceOp.SUM, group=self._dp.group, async_op=True)
+      self._graphs[2].replay()                    # convolution backward runs while NCCL moves fc1's 31.7 MB
+      self._dp.sum_(g[o0:o0 + n0])                # the convolutions' 0.3 MB
+      work.wait()
+      self._graphs[3].replay()
 
   # ------------------------------------------------------------------ acme.core.Learner
   def step(self, uniforms=None, fetch_loss: bool = True):

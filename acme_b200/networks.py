@@ -298,38 +298,53 @@ class DQNAtariNetwork(Network):
 
 
   def _backward_two_streams(self, obs, bufs, gbufs, dq, side):
+    self.backward_dense_part(bufs, gbufs, dq, side)
+    self.backward_conv_part(obs, bufs, gbufs, side)
+
+  def grad_buckets(self):
+    """(offset, count) in floats of the gradient regions that become final after backward_dense_part
+    (fc1 + heads: the tail of the flat buffer, 99% of the bytes) and after backward_conv_part (the convs)."""
+    split = self.params.entries['fc1.w'][0]
+    return (split, self.params.size - split), (0, split)
+
+  def backward_dense_part(self, bufs, gbufs, dq, side):
+    """Duelling head + fc1: parameter gradients of everything after the torso, and dy3."""
     import torch
     B, P = bufs['B'], self.params
     main = torch.cuda.current_stream()
     h, y3 = bufs['h'], bufs['y3']
     dh = gbufs['dh'].data_ptr()
-
-    def fork():           # side waits for everything issued on main so far
-      ev = torch.cuda.Event()
-      ev.record(main)
-      side.wait_event(ev)
-
     self.lane(0)
     ws, wsb = self.ws
     _capi.call('b200rl_duelling_head_bwd', B, self.A, 512, dq.data_ptr(), h.data_ptr(), 1024, P.p('v2.w'), P.p('a2.w'),
                gbufs['dval'].data_ptr(), gbufs['dadv'].data_ptr(), dh, 1024, P.g('v2.w'), P.g('v2.b'), P.g('a2.w'),
                P.g('a2.b'), ws, wsb, _capi.current_stream())
-    fork()
+    ev = torch.cuda.Event()
+    ev.record(main)
+    side.wait_event(ev)
     with torch.cuda.stream(side):
       self.lane(1)
       _linear_wgrad(B, 1024, self.flat_dim, dh, 1024, y3.data_ptr(), self.flat_dim, P.g('fc1.w'), P.g('fc1.b'), self)
     self.lane(0)
     _linear_dgrad(B, 1024, self.flat_dim, dh, 1024, P.p('fc1.w'), gbufs['dy3'].data_ptr(), self.flat_dim,
                   y3.data_ptr(), ACT_RELU, self)
+    ev = torch.cuda.Event()
+    ev.record(side)
+    main.wait_event(ev)
+
+  def backward_conv_part(self, obs, bufs, gbufs, side):
+    """The three convolutions: weight gradients on `side`, data gradients on the current stream."""
+    import torch
+    B, P = bufs['B'], self.params
+    main = torch.cuda.current_stream()
     for i in (2, 1, 0):
       g = self.geom(i, B)
       dy = gbufs[f'dy{i + 1}'].data_ptr()
       if i > 0:
         x, x_u8 = bufs[f'y{i}'].data_ptr(), 0
-      else:
-        x, x_u8 = obs.data_ptr(), int(obs.dtype == torch.uint8)
-      if i > 0:
-        fork()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        side.wait_event(ev)
         with torch.cuda.stream(side):
           self.lane(1)
           ws1, wsb1 = self.ws
@@ -340,6 +355,7 @@ class DQNAtariNetwork(Network):
         _capi.call('b200rl_conv2d_dgrad', dy, P.p(f'conv{i + 1}.w'), gbufs[f'dy{i}'].data_ptr(), g,
                    bufs[f'y{i}'].data_ptr(), ACT_RELU, self.precision, ws, wsb, _capi.current_stream())
       else:   # conv1 has no data gradient: its weight gradient finishes the main chain
+        x, x_u8 = obs.data_ptr(), int(obs.dtype == torch.uint8)
         ws, wsb = self.ws
         _capi.call('b200rl_conv2d_wgrad', x, x_u8, dy, P.g('conv1.w'), P.g('conv1.b'), g, self.precision, ws, wsb,
                    _capi.current_stream())

@@ -108,41 +108,56 @@ def fill_replay(table, steps, n_step, seed, chunk=32768):
 
 # ------------------------------------------------------------------------------ clocks sampler
 class ClockSampler:
-  Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+  """nvidia-smi sampler (the recipe's clocks line).  It is started before the warm-up and samples every 50 ms;
+  `mark()` brackets the timed region so only samples taken inside it are summarised (if the region is shorter
+  than the sampling period, the samples nearest to it are used)."""
+  Q = ('timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
        'clocks_event_reasons.sw_power_cap')
 
   def __init__(self, gpu_index=0):
     self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
     self.p = None
+    self.t0 = self.t1 = None
     try:
-      self.p = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+      self.p = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '50',
                                  '-i', str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
     except Exception:  # noqa: BLE001
       self.p = None
 
+  def mark(self):
+    if self.t0 is None:
+      self.t0 = time.time()
+    else:
+      self.t1 = time.time()
+
   def stop(self):
+    import datetime
     if self.p is None:
       return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-    time.sleep(0.15)
+    time.sleep(0.12)
     self.p.terminate()
     self.p.wait()
     self.f.flush()
     rows = [r.strip().split(', ') for r in open(self.f.name) if r.strip()]
     os.unlink(self.f.name)
-    sm, smax, reasons = [], [], set()
+    samples = []
     for r in rows:
       try:
-        sm.append(float(r[1])); smax.append(float(r[2]))
+        ts = datetime.datetime.strptime(r[0].strip(), '%Y/%m/%d %H:%M:%S.%f').timestamp()
+        samples.append((ts, float(r[2]), float(r[3]), [v.strip().lower().startswith('active') for v in r[6:10]]))
       except Exception:  # noqa: BLE001
         continue
-      for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
-        if v.strip().lower().startswith('active'):
-          reasons.add(name)
-    if not sm:
+    if not samples:
       return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
-    return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(smax)), 'reasons': sorted(reasons),
-            'samples': len(sm)}
+    t0, t1 = self.t0 or samples[0][0], self.t1 or samples[-1][0]
+    inside = [x for x in samples if t0 - 0.05 <= x[0] <= t1 + 0.05]
+    if not inside:   # region shorter than the sampling period: take the two samples nearest to it
+      inside = sorted(samples, key=lambda x: abs(x[0] - 0.5 * (t0 + t1)))[:2]
+    names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+    reasons = sorted({n for x in inside for n, on in zip(names, x[3]) if on})
+    return {'sm_mhz': float(np.median([x[1] for x in inside])), 'sm_max_mhz': float(max(x[2] for x in inside)),
+            'reasons': reasons, 'samples': len(inside)}
 
 
 # ------------------------------------------------------------------------------ CPU baseline / reference arm
@@ -269,19 +284,20 @@ def run_ours(args):
     torch.cuda.synchronize()
 
   # ---- device-resident timing (value)
+  clocks = ClockSampler(local)
   for _ in range(max(args.warmup, 3)):
     learner.step(fetch_loss=False)
   barrier()
   launches0 = lib.b200rl_launch_count()
-  learner_launches_per_step = None
-  clocks = ClockSampler(local)
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   barrier()
+  clocks.mark()
   e0.record()
   for _ in range(args.steps):
     learner.step(fetch_loss=False)
   e1.record()
   barrier()
+  clocks.mark()
   dev_s = e0.elapsed_time(e1) * 1e-3
   clk = clocks.stop()
   if world > 1:
