@@ -380,6 +380,173 @@ int tma_conv_wgrad(const float* x, const float* dy, float* dw, float* db, const 
   return B200RL_OK;
 }
 
+// ---- conv data gradient as an implicit GEMM over dy, one sub-problem per stride phase.
+// With n = i + pad and n = s q + p (p = phase, 0 <= p < s) an input pixel i only meets the taps k = p + s t:
+//     dx[i, ci] = sum_{t, co} dy[q - t, co] w[co, p + s t, ci]        (separately in y and x)
+// i.e. every phase is a stride-1 correlation of dy with a T_y x T_x sub-filter, T = ceil((k - p) / s).  A = TMA im2col
+// over dy (one map per phase: the bounding box selects that phase's q range, out-of-range dy reads as zero),
+// B = 32 x C boxes of the untransposed weight matrix [Cout][kh kw C] (MN-major), accumulator rows are scattered
+// to the phase's pixels of dx with the producer layer's activation derivative applied.
+struct DgradPhase {
+  int tile_begin;            // first CTA of this phase
+  int cnt_x, cnt_y;          // q range sizes
+  int lower_x, lower_y;      // im2col base coordinate of q = qmin (qmin - (T - 1))
+  int Tx, Ty, px, py;
+  int ix0, iy0;              // input coordinate of q = qmin
+};
+struct DgradParams {
+  DgradPhase ph[4];
+  int nphase, stride, kw, C, Cout, W, H, B;
+};
+struct DgradMaps { CUtensorMap m[4]; };
+
+template <int BN>
+__global__ void __launch_bounds__(G_THREADS)
+tma_conv_dgrad_kernel(const __grid_constant__ DgradMaps maps, const __grid_constant__ CUtensorMap map_w, DgradParams P,
+                      float* __restrict__ dx, const float* __restrict__ mask, int mask_act) {
+  constexpr int A_BYTES = GBM * 128, B_BYTES = BN * 128, STAGE = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ __align__(8) uint64_t bar_full[G_STAGES], bar_empty[G_STAGES], bar_done;
+  __shared__ uint32_t tmem_base_smem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  int phase = 0;
+#pragma unroll
+  for (int i = 1; i < 4; ++i) if (i < P.nphase && (int)blockIdx.x >= P.ph[i].tile_begin) phase = i;
+  const DgradPhase ph = P.ph[phase];
+  const int row0 = ((int)blockIdx.x - ph.tile_begin) * GBM;
+  const int Mp = P.B * ph.cnt_y * ph.cnt_x;
+  const int cb = P.Cout / GBK;
+  const int nkb = ph.Ty * ph.Tx * cb;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < G_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+    mbar_init(&bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_smem;
+
+  if (warp == 0 && lane == 0) {
+    const int jx = row0 % ph.cnt_x, t = row0 / ph.cnt_x;
+    const int ax = ph.lower_x + jx, ay = ph.lower_y + t % ph.cnt_y, an = t / ph.cnt_y;
+    const int K = P.kw * P.C;   // weight row: tap (ky, kx) starts at (ky kw + kx) C; rows are kh*K long
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % G_STAGES;
+      if (i >= G_STAGES) mbar_wait(&bar_empty[s], ((i / G_STAGES) - 1) & 1);
+      const uint32_t sa = base + s * STAGE, sb = sa + A_BYTES;
+      const int tap = i / cb, co0 = (i % cb) * GBK;
+      const int off_y = tap / ph.Tx, off_x = tap % ph.Tx;
+      const int ky = ph.py + P.stride * (ph.Ty - 1 - off_y), kx = ph.px + P.stride * (ph.Tx - 1 - off_x);
+      mbar_expect_tx(&bar_full[s], STAGE);
+      tma_load_im2col(sa, &maps.m[phase], co0, ax, ay, an, (uint16_t)off_x, (uint16_t)off_y, &bar_full[s]);
+#pragma unroll
+      for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * 4096, &map_w, ky * K + kx * P.C + 32 * j, co0, &bar_full[s]);
+    }
+  } else if (warp == 1 && lane == 0) {
+    constexpr uint32_t idesc = umma_idesc_tf32(GBM, BN, false, true);
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % G_STAGES;
+      mbar_wait(&bar_full[s], (i / G_STAGES) & 1);
+      tc_fence_after();
+      const uint32_t sa = base + s * STAGE, sb = sa + A_BYTES;
+#pragma unroll
+      for (int kk = 0; kk < GBK / 8; ++kk)
+        umma_tf32(tmem_d, umma_desc_sw128(sa + kk * 32, 16, 1024, 2), umma_desc_sw128(sb + kk * 1024, 4096, 512, 1), idesc,
+                  (i > 0 || kk > 0) ? 1u : 0u);
+      umma_commit(&bar_empty[s]);
+      if (i == nkb - 1) umma_commit(&bar_done);
+    }
+  } else if (warp >= 2) {
+    mbar_wait(&bar_done, 0);
+    tc_fence_after();
+    const int lane_base = (warp & 3) * 32;
+    const int row = row0 + lane_base + lane;
+    size_t orow = 0;
+    if (row < Mp) {
+      const int jx = row % ph.cnt_x, t = row / ph.cnt_x;
+      const int jy = t % ph.cnt_y, b = t / ph.cnt_y;
+      orow = ((size_t)b * P.H + (ph.iy0 + P.stride * jy)) * P.W + (ph.ix0 + P.stride * jx);
+    }
+    Epilogue e{dx, P.C, nullptr, 0, mask, P.C, mask_act, nullptr, 0};
+#pragma unroll 1
+    for (int cc = 0; cc < BN; cc += 16) {
+      float v[16];
+      tmem_ld16(tmem_d + ((uint32_t)lane_base << 16) + (uint32_t)cc, v);
+      if (row < Mp) finish16(e, (int)orow, cc, P.C, 0, v);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_d, TMEM_COLS);
+}
+
+template <int BN>
+static int launch_dgrad(const DgradMaps& maps, const CUtensorMap& mw, const DgradParams& P, int tiles, float* dx,
+                        const float* mask, int mask_act, cudaStream_t s) {
+  constexpr int smem = G_STAGES * (GBM * 128 + BN * 128) + 1024;
+  static bool attr = false;
+  if (!attr) {
+    B200RL_CUDA_OK(cudaFuncSetAttribute(tma_conv_dgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  tma_conv_dgrad_kernel<BN><<<tiles, G_THREADS, smem, s>>>(maps, mw, P, dx, mask, mask_act);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+
+int tma_conv_dgrad(const float* dy, const float* w, float* dx, const b200rl_conv_geom& g, const float* mask, int mask_act,
+                   void* ws, int64_t wsb, cudaStream_t s) {
+  (void)ws; (void)wsb;
+  const int K = g.kh * g.kw * g.C, st = g.stride;
+  if (st > 2 || g.kh < st || g.kw < st || g.Cout % GBK != 0 || (g.C != 32 && g.C != 64 && g.C != 128) || !tma_ok(dy, g.Cout) ||
+      !tma_ok(w, K) || !tma_ok(dx, g.C) || (mask && !tma_ok(mask, g.C)) || (int64_t)g.B * g.OH * g.OW * g.Cout * 4 < 131072 ||
+      (int64_t)g.B * g.H * g.W >= (1ll << 31) / g.C)
+    return 1;
+  EncodeIm2colFn enc = get_encode_im2col();
+  if (!enc) return 1;
+  DgradMaps maps;
+  DgradParams P;
+  P.nphase = st * st; P.stride = st; P.kw = g.kw; P.C = g.C; P.Cout = g.Cout; P.W = g.W; P.H = g.H; P.B = g.B;
+  auto fdiv = [](int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); };
+  int tiles = 0;
+  for (int py = 0; py < st; ++py)
+    for (int px = 0; px < st; ++px) {
+      DgradPhase& ph = P.ph[py * st + px];
+      const int Ty = (g.kh - py + st - 1) / st, Tx = (g.kw - px + st - 1) / st;
+      const int qy0 = -fdiv(-(g.pad_top - py), st) , qx0 = -fdiv(-(g.pad_left - px), st);          // ceil
+      const int qy1 = fdiv(g.H - 1 + g.pad_top - py, st), qx1 = fdiv(g.W - 1 + g.pad_left - px, st);  // floor
+      ph.tile_begin = tiles;
+      ph.cnt_x = qx1 - qx0 + 1; ph.cnt_y = qy1 - qy0 + 1;
+      ph.Tx = Tx; ph.Ty = Ty; ph.px = px; ph.py = py;
+      ph.lower_x = qx0 - (Tx - 1); ph.lower_y = qy0 - (Ty - 1);
+      ph.ix0 = st * qx0 + px - g.pad_left; ph.iy0 = st * qy0 + py - g.pad_top;
+      if (ph.cnt_x <= 0 || ph.cnt_y <= 0) return 1;
+      tiles += ceil_div(g.B * ph.cnt_x * ph.cnt_y, GBM);
+      cuuint64_t dims[4] = {(cuuint64_t)g.Cout, (cuuint64_t)g.OW, (cuuint64_t)g.OH, (cuuint64_t)g.B};
+      cuuint64_t strides[3] = {(cuuint64_t)g.Cout * 4, (cuuint64_t)g.OW * g.Cout * 4, (cuuint64_t)g.OH * g.OW * g.Cout * 4};
+      int lower[2] = {ph.lower_x, ph.lower_y};
+      int upper[2] = {(qx1 - (Tx - 1)) - (g.OW - 1), (qy1 - (Ty - 1)) - (g.OH - 1)};
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      if (enc(&maps.m[py * st + px], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)dy, dims, strides, lower, upper, GBK, GBM, es,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return 1;
+    }
+  for (int i = P.nphase; i < 4; ++i) { P.ph[i] = P.ph[0]; maps.m[i] = maps.m[0]; }
+  CUtensorMap mw;
+  if (!make_map(&mw, w, g.Cout, K, K, 32, GBK, true)) return 1;
+  if (g.C == 32) return launch_dgrad<32>(maps, mw, P, tiles, dx, mask, mask_act, s);
+  if (g.C == 64) return launch_dgrad<64>(maps, mw, P, tiles, dx, mask, mask_act, s);
+  return launch_dgrad<128>(maps, mw, P, tiles, dx, mask, mask_act, s);
+}
+
 }  // namespace b200rl
 
 extern "C" int b200rl_debug_tma_timeline(unsigned long long* buf_dev) {

@@ -39,6 +39,8 @@ int tma_conv_fwd(const float* x, const float* w, const float* bias, float* y, co
                  void* ws, int64_t wsb, cudaStream_t s);
 int tma_conv_wgrad(const float* x, const float* dy, float* dw, float* db, const b200rl_conv_geom& g, void* ws, int64_t wsb,
                    cudaStream_t s);
+int tma_conv_dgrad(const float* dy, const float* w, float* dx, const b200rl_conv_geom& g, const float* mask, int mask_act,
+                   void* ws, int64_t wsb, cudaStream_t s);
 }  // namespace b200rl
 
 using namespace b200rl;
@@ -87,6 +89,10 @@ extern "C" int b200rl_conv2d_dgrad(const float* dy, const float* w, float* dx, c
                                    const float* mask_y, int mask_act, int precision, void* ws, int64_t wsb, void* stream) {
   B200RL_REQUIRE(dy && w && dx, "null argument");
   if (int rc = check_geom(g)) return rc;
+  if (precision == 1 && g_use_tma) {
+    int rc = tma_conv_dgrad(dy, w, dx, *g, mask_y, mask_act, ws, wsb, as_stream(stream));
+    if (rc != 1) return rc;
+  }
   B200RL_REQUIRE(precision != 1 || (g->Cout % 8 == 0 && g->C % 8 == 0), "bf16 conv dgrad needs C %% 8 == 0 and Cout %% 8 == 0");
   PRECISION_SWITCH(simt_conv_dgrad(dy, w, dx, *g, mask_y, mask_act, ws, wsb, as_stream(stream)),
                    tc_conv_dgrad(dy, w, dx, *g, mask_y, mask_act, ws, wsb, as_stream(stream)));

@@ -94,7 +94,7 @@ class Network:
     _capi.require_device(self.device)
     self.params.allocate()
     # one split-K / partial-sum workspace per concurrent stream (see Network.lanes)
-    self._ws_all = [torch.empty(64 << 20, dtype=torch.uint8, device=torch.device('cuda', self.device)) for _ in range(3)]
+    self._ws_all = [torch.empty(96 << 20, dtype=torch.uint8, device=torch.device('cuda', self.device)) for _ in range(3)]
     self._lane = 0
 
   @property

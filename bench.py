@@ -257,7 +257,7 @@ def run_ours(args):
     pg = dist.group.WORLD
   P = peaks()
   B, n_step, items = 256, 3, args.items
-  precision = {'fp32': _capi.PRECISION_FP32, 'bf16': _capi.PRECISION_BF16}[args.precision]
+  precision = {'fp32': _capi.PRECISION_FP32, 'tc': _capi.PRECISION_BF16, 'bf16': _capi.PRECISION_BF16}[args.precision]
 
   spec = specs.EnvironmentSpec(specs.Array(OBS_SHAPE, np.uint8), specs.DiscreteArray(NUM_ACTIONS),
                                specs.Array((), np.float32), specs.BoundedArray((), np.float32, 0., 1.))
@@ -404,12 +404,12 @@ def run_ours(args):
     if not gpu_launches:
       gpu_launches = int(lib.b200rl_launch_count() - launches0)
     kname = 'k6_network_gemm_conv (3 forwards + 1 backward, fp32 SIMT FFMA)' if precision == 0 else \
-            'k6_network_gemm_conv (3 forwards + 1 backward, bf16 tcgen05)'
+            'k6_network_gemm_conv (3 forwards + 1 backward; tcgen05: TMA-fed kind::tf32 for conv2/conv3/fc1, kind::f16 bf16 for conv1)'
     achieved = STEP_FLOPS / net_s / 1e12 if net_s > 0 else None
     out = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f32' if precision == 0 else 'bf16 operands, f32 accumulate/master',
+        'dtype': 'f32' if precision == 0 else 'tf32/bf16 tensor-core operands, f32 accumulate, f32 master weights and optimizer',
         'data': 'synthetic',
         'config': {'workload': 'DQN Atari-shaped 84x84x4 uint8, PER 1M items, batch 256, n=3 (BASELINE configs[1])',
                    'items_per_rank': info['size'], 'batch_per_rank': B, 'n_step': n_step, 'alpha': 0.6, 'beta': 0.2,
@@ -448,10 +448,12 @@ def run_ours(args):
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
-  ap.add_argument('--steps', type=int, default=100)
-  ap.add_argument('--warmup', type=int, default=10)
+  ap.add_argument('--steps', type=int, default=500)
+  ap.add_argument('--warmup', type=int, default=20)
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-  ap.add_argument('--precision', default=os.environ.get('B200RL_PRECISION', 'fp32'), choices=['fp32', 'bf16'])
+  ap.add_argument('--precision', default=os.environ.get('B200RL_PRECISION', 'tc'), choices=['fp32', 'tc', 'bf16'],
+                  help="'tc' (default; 'bf16' is an alias): tcgen05 tensor cores with tf32/bf16 operands, stated tolerance in "
+                       "tests/test_gpu_learner.py; 'fp32': SIMT FFMA, 1e-5 parity with the oracle")
   ap.add_argument('--items', type=int, default=1_000_000)
   ap.add_argument('--no-graph', action='store_true')
   ap.add_argument('--no-cpu-baseline', action='store_true')

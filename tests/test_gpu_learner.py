@@ -200,14 +200,14 @@ def test_copy_if_period_and_step_counter():
 
 # ------------------------------------------------------------------------------------ K6 layers
 @pytest.mark.parametrize('precision', [0, 1])
-@pytest.mark.parametrize('H,C,k,s,Cout,u8', [(84, 4, 8, 4, 32, True), (21, 32, 4, 2, 64, False), (11, 64, 3, 1, 64, False),
-                                             (12, 8, 3, 2, 16, False)])
-def test_conv_fwd_wgrad_dgrad_vs_torch_cpu(H, C, k, s, Cout, u8, precision):
+@pytest.mark.parametrize('H,C,k,s,Cout,u8,B', [(84, 4, 8, 4, 32, True, 5), (21, 32, 4, 2, 64, False, 5),
+                                               (11, 64, 3, 1, 64, False, 5), (12, 8, 3, 2, 16, False, 5),
+                                               (20, 32, 5, 2, 32, False, 13), (17, 64, 3, 2, 96, False, 11)])
+def test_conv_fwd_wgrad_dgrad_vs_torch_cpu(H, C, k, s, Cout, u8, B, precision):
   import torch
   from acme_b200 import _capi, networks
   from oracle import nets as onets
   rng = np.random.default_rng(H + C)
-  B = 5
   OH, pad = networks.tf_same_pad(H, k, s)
   g = _capi.ConvGeom(B=B, H=H, W=H, C=C, kh=k, kw=k, stride=s, pad_top=pad, pad_left=pad, OH=OH, OW=OH, Cout=Cout)
   x_raw = rng.integers(0, 256, (B, H, H, C), dtype=np.uint8) if u8 else rng.standard_normal((B, H, H, C)).astype(np.float32)
@@ -238,6 +238,11 @@ def test_conv_fwd_wgrad_dgrad_vs_torch_cpu(H, C, k, s, Cout, u8, precision):
     _capi.call('b200rl_conv2d_dgrad', dy_pre.data_ptr(), w_ohwi.data_ptr(), dx.data_ptr(), g, None, 0, precision,
                ws.data_ptr(), ws.numel(), _capi.current_stream())
     close(dx.cpu().numpy(), xt.grad.numpy(), name='conv dgrad', **tol(precision, atol_scale=2e-6))
+    # with the producer layer's ReLU derivative fused (mask = that layer's output)
+    prev = rng.standard_normal((B, H, H, C)).astype(np.float32)
+    _capi.call('b200rl_conv2d_dgrad', dy_pre.data_ptr(), w_ohwi.data_ptr(), dx.data_ptr(), g, dev(prev).data_ptr(),
+               _capi.ACT_RELU, precision, ws.data_ptr(), ws.numel(), _capi.current_stream())
+    close(dx.cpu().numpy(), xt.grad.numpy() * (prev > 0), name='conv dgrad masked', **tol(precision, atol_scale=2e-6))
 
 
 @pytest.mark.parametrize('precision', [0, 1])
