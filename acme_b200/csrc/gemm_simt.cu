@@ -6,6 +6,8 @@
 // This mode exists to meet the 1e-5 parity bar against the fp32 oracle; the speed mode is the
 // tcgen05 path in gemm_tc.cu.  C[row, col] = sum_red A(row, red) * B(red, col).
 #include <algorithm>
+#include <mutex>
+#include <vector>
 
 #include "common.cuh"
 #include "gemm_common.cuh"
@@ -281,7 +283,91 @@ static int launch_gemm(const AL& a, const BL& b, Epilogue epi, int M, int N, int
   return B200RL_OK;
 }
 
+// Vectorised column sum in ONE launch: a CTA of 256 threads is a (256 / (N/4)) x (N/4) grid of float4 lanes that
+// walks its slice of rows with fully coalesced 16-byte loads, reduces its row-lanes in a fixed order through shared
+// memory and writes one partial row; the CTA that finishes last (a per-stream ticket in g_tail_tickets, reset on
+// the way out, so the kernel is CUDA-graph safe) reduces the partial rows with the same routine.  The order of
+// every addition is fixed by indices, never by arrival, so the result is deterministic.
+__device__ unsigned int g_tail_tickets[64];
+
+__device__ __forceinline__ float4 block_colsum(const float* __restrict__ x, int ld, int m0, int m1, int cpr, float4* red,
+                                               bool through_l2) {
+  const int rl = threadIdx.x / cpr, c = threadIdx.x % cpr, rpi = 256 / cpr;
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+  int m = m0 + rl;
+  for (; m + rpi < m1; m += 2 * rpi) {
+    const float4* p0 = reinterpret_cast<const float4*>(x + (size_t)m * ld) + c;
+    const float4* p1 = reinterpret_cast<const float4*>(x + (size_t)(m + rpi) * ld) + c;
+    const float4 v0 = through_l2 ? __ldcg(p0) : __ldg(p0), v1 = through_l2 ? __ldcg(p1) : __ldg(p1);
+    a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+    a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+  }
+  if (m < m1) {
+    const float4* p0 = reinterpret_cast<const float4*>(x + (size_t)m * ld) + c;
+    const float4 v0 = through_l2 ? __ldcg(p0) : __ldg(p0);
+    a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+  }
+  red[threadIdx.x] = make_float4(a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w);
+  __syncthreads();
+  float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (threadIdx.x < cpr)
+    for (int j = 0; j < rpi; ++j) {
+      const float4 v = red[j * cpr + threadIdx.x];
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+  __syncthreads();
+  return t;   // valid in threads < cpr
+}
+
+__global__ void __launch_bounds__(256)
+colsum_vec_kernel(int M, int N, const float* __restrict__ x, int ld, int rows_per_block, float* __restrict__ partial,
+                  float* __restrict__ out, int ticket) {
+  __shared__ float4 red[256];
+  __shared__ bool last;
+  const int cpr = N >> 2;
+  const int m0 = blockIdx.x * rows_per_block, m1 = min(M, m0 + rows_per_block);
+  float4 t = block_colsum(x, ld, m0, m1, cpr, red, false);
+  if (gridDim.x == 1) {
+    if (threadIdx.x < cpr) reinterpret_cast<float4*>(out)[threadIdx.x] = t;
+    return;
+  }
+  if (threadIdx.x < cpr) reinterpret_cast<float4*>(partial + (size_t)blockIdx.x * N)[threadIdx.x] = t;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(&g_tail_tickets[ticket], 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  t = block_colsum(partial, N, 0, (int)gridDim.x, cpr, red, true);
+  if (threadIdx.x < cpr) reinterpret_cast<float4*>(out)[threadIdx.x] = t;
+  if (threadIdx.x == 0) g_tail_tickets[ticket] = 0;
+}
+
+// kernels on one stream never overlap, so a ticket per stream is race-free (also inside a captured graph, whose
+// nodes keep the capture-time stream order)
+static int ticket_for(cudaStream_t s) {
+  static std::mutex mu;
+  static std::vector<cudaStream_t> seen;
+  std::lock_guard<std::mutex> lk(mu);
+  for (size_t i = 0; i < seen.size(); ++i) if (seen[i] == s) return (int)i;
+  if (seen.size() >= 64) return -1;
+  seen.push_back(s);
+  return (int)seen.size() - 1;
+}
+
 int launch_colsum(int M, int N, const float* x, int ld, float* out, void* ws, int64_t ws_bytes, cudaStream_t stream) {
+  const bool vec = N >= 4 && N <= 1024 && (N & (N - 1)) == 0 && ld % 4 == 0 && ((((uintptr_t)x) | ((uintptr_t)out) | ((uintptr_t)ws)) & 15) == 0;
+  const int ticket = vec ? ticket_for(stream) : -1;
+  if (vec && ticket >= 0) {
+    const int rpi = 256 / (N / 4);
+    int blocks = std::max(1, std::min(ceil_div(M, 4 * rpi), 2 * kNumSMs));
+    blocks = (int)std::max<int64_t>(1, std::min<int64_t>(blocks, ws ? ws_bytes / ((int64_t)N * 4) : 1));
+    const int rpb = ceil_div(M, blocks);
+    blocks = ceil_div(M, rpb);
+    colsum_vec_kernel<<<blocks, 256, 0, stream>>>(M, N, x, ld, rpb, (float*)ws, out, ticket);
+    B200RL_LAUNCH_OK();
+    return B200RL_OK;
+  }
   const int col_blocks = ceil_div(N, 32);
   int splits = std::max(1, std::min(std::min(ceil_div(M, 64), (2 * kNumSMs) / col_blocks), 96));
   splits = (int)std::min<int64_t>(splits, ws ? ws_bytes / ((int64_t)N * 4) : 1);

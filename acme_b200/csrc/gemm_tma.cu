@@ -33,6 +33,7 @@ __device__ __forceinline__ void tm_mark(int slot) {
 }
 
 constexpr int GBM = 128, GBK = 32 /* fp32 elements = 128 bytes */, G_STAGES = 3, G_THREADS = 192;
+int g_tma_stage_mode = 0;   // 0 = heuristic, 1 = always shallow, 2 = always deep (tools/layer_bench.py)
 
 // ---- tensor maps (driver entry point fetched at run time: no link-time dependency on libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -150,7 +151,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, bool a_mn, 
 // C[row, col] = sum_k A(row, k) B(k, col).  Tile coordinates for the maps:
 //   K-major operand : one box {32 k, R rows}       at (k0, row0)
 //   MN-major operand: R/32 boxes {32 rows, 32 k}   at (row0 + 32 j, k0), stacked 4 KB apart
-template <bool AMN, bool BMN, int BN>
+template <bool AMN, bool BMN, int BN, int STAGES>
 __global__ void __launch_bounds__(G_THREADS)
 tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, Epilogue epi,
                 int M, int N, int K, int kblocks_per_split, ConvA conv) {
@@ -158,7 +159,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // 128-byte swizzle atoms are 1 KB
-  __shared__ __align__(8) uint64_t bar_full[G_STAGES], bar_empty[G_STAGES], bar_done;
+  __shared__ __align__(8) uint64_t bar_full[STAGES], bar_empty[STAGES], bar_done;
   __shared__ uint32_t tmem_base_smem;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -169,7 +170,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < G_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
     mbar_init(&bar_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -190,8 +191,8 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       an = t / conv.OH;
     }
     for (int i = 0; i < nkb; ++i) {
-      const int s = i % G_STAGES;
-      if (i >= G_STAGES) mbar_wait(&bar_empty[s], ((i / G_STAGES) - 1) & 1);
+      const int s = i % STAGES;
+      if (i >= STAGES) mbar_wait(&bar_empty[s], ((i / STAGES) - 1) & 1);
       const uint32_t sa = base + s * STAGE, sb = sa + A_BYTES;
       const int k0 = (kb_begin + i) * GBK;
       if (AMN && conv.enabled) {
@@ -236,8 +237,8 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     // ---------------- MMA issuer
     constexpr uint32_t idesc = umma_idesc_tf32(GBM, BN, AMN, BMN);
     for (int i = 0; i < nkb; ++i) {
-      const int s = i % G_STAGES;
-      mbar_wait(&bar_full[s], (i / G_STAGES) & 1);
+      const int s = i % STAGES;
+      mbar_wait(&bar_full[s], (i / STAGES) & 1);
       if (i < 8) tm_mark(1 + i);
       tc_fence_after();
       const uint32_t sa = base + s * STAGE, sb = sa + A_BYTES;
@@ -261,16 +262,26 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
     if (tid == 64) tm_mark(10);
     const int lane_base = (warp & 3) * 32;
-    const int row = row0 + lane_base + lane;
+    if (epi.transpose_out) {
+      // C^T is wanted: lanes (= rows) are already the contiguous direction of the destination
+      const int row = row0 + lane_base + lane;
 #pragma unroll 1
-    for (int cc = 0; cc < BN; cc += 16) {
-      float v[16];
-      if (nkb > 0) tmem_ld16(tmem_d + ((uint32_t)lane_base << 16) + (uint32_t)cc, v);
-      else {
+      for (int cc = 0; cc < BN; cc += 16) {
+        float v[16];
+        if (nkb > 0) tmem_ld16(tmem_d + ((uint32_t)lane_base << 16) + (uint32_t)cc, v);
+        else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+          for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        }
+        if (row < M) finish16(epi, row, col0 + cc, N, M, v);
       }
-      if (row < M) finish16(epi, row, col0 + cc, N, M, v);
+    } else {
+      // transpose through shared memory (the drained pipeline stages) so that every store instruction of a warp
+      // covers whole rows: 32 / (BN / 4) rows x BN floats
+      float* slab = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw))) + (warp & 3) * 32 * BN;
+      stage_accumulator<BN>(tmem_d + ((uint32_t)lane_base << 16), slab, lane, nkb > 0);
+      const int first = row0 + lane_base;
+      store_staged_rows<BN>(epi, slab, lane, col0, N, M, [&](int r) -> long long { return first + r < M ? first + r : -1; });
     }
   }
   if (tid == 64) tm_mark(11);
@@ -283,16 +294,10 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 template <bool AMN, bool BMN, int BN>
 static int launch_tma_bn(const CUtensorMap& ma, const CUtensorMap& mb, Epilogue epi, int M, int N, int K, void* ws,
                          int64_t ws_bytes, cudaStream_t stream, const ConvA& conv) {
-  constexpr int smem = G_STAGES * (GBM * 128 + BN * 128) + 1024;
-  static bool attr = false;
-  if (!attr) {
-    B200RL_CUDA_OK(cudaFuncSetAttribute(tma_gemm_kernel<AMN, BMN, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
-  }
   const int tiles = ceil_div(M, GBM) * ceil_div(N, BN);
   const int kblocks = ceil_div(K, GBK);
   int splits = 1;
-  if (tiles < kNumSMs && kblocks >= 16) {
+  if (2 * tiles <= kNumSMs && kblocks >= 16) {   // a partial pass + finish launch costs more than a part-filled wave
     splits = std::min(ceil_div(kNumSMs, tiles), kblocks / 8);
     splits = std::min(splits, 64);
     const int64_t cap = ws ? ws_bytes / ((int64_t)M * N * 4) : 0;
@@ -302,7 +307,27 @@ static int launch_tma_bn(const CUtensorMap& ma, const CUtensorMap& mb, Epilogue 
   splits = ceil_div(kblocks, kps);
   epi.partial = splits > 1 ? (float*)ws : nullptr;
   dim3 grid(ceil_div(N, BN), ceil_div(M, GBM), splits);
-  tma_gemm_kernel<AMN, BMN, BN><<<grid, G_THREADS, smem, stream>>>(ma, mb, epi, M, N, K, kps, conv);
+  // one CTA per SM anyway -> spend the shared memory on a deeper TMA ring (the loads are latency-bound);
+  // more CTAs than SMs -> keep stages shallow so 2-3 CTAs co-reside and one's epilogue overlaps another's loads
+  const bool deep = g_tma_stage_mode == 2 || (false);
+  if (deep) {
+    constexpr int DS = BN == 128 ? 6 : 8;
+    constexpr int smem = DS * (GBM * 128 + BN * 128) + 1024;
+    static bool attr = false;
+    if (!attr) {
+      B200RL_CUDA_OK(cudaFuncSetAttribute(tma_gemm_kernel<AMN, BMN, BN, DS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attr = true;
+    }
+    tma_gemm_kernel<AMN, BMN, BN, DS><<<grid, G_THREADS, smem, stream>>>(ma, mb, epi, M, N, K, kps, conv);
+  } else {
+    constexpr int smem = G_STAGES * (GBM * 128 + BN * 128) + 1024;
+    static bool attr = false;
+    if (!attr) {
+      B200RL_CUDA_OK(cudaFuncSetAttribute(tma_gemm_kernel<AMN, BMN, BN, G_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attr = true;
+    }
+    tma_gemm_kernel<AMN, BMN, BN, G_STAGES><<<grid, G_THREADS, smem, stream>>>(ma, mb, epi, M, N, K, kps, conv);
+  }
   B200RL_LAUNCH_OK();
   if (splits > 1) return launch_splitk_finish(epi, M, N, splits, stream);
   return B200RL_OK;
@@ -468,19 +493,16 @@ tma_conv_dgrad_kernel(const __grid_constant__ DgradMaps maps, const __grid_const
     tc_fence_after();
     const int lane_base = (warp & 3) * 32;
     const int row = row0 + lane_base + lane;
-    size_t orow = 0;
+    long long orow = -1;   // destination pixel of this lane's accumulator row
     if (row < Mp) {
       const int jx = row % ph.cnt_x, t = row / ph.cnt_x;
       const int jy = t % ph.cnt_y, b = t / ph.cnt_y;
-      orow = ((size_t)b * P.H + (ph.iy0 + P.stride * jy)) * P.W + (ph.ix0 + P.stride * jx);
+      orow = ((long long)b * P.H + (ph.iy0 + P.stride * jy)) * P.W + (ph.ix0 + P.stride * jx);
     }
     Epilogue e{dx, P.C, nullptr, 0, mask, P.C, mask_act, nullptr, 0};
-#pragma unroll 1
-    for (int cc = 0; cc < BN; cc += 16) {
-      float v[16];
-      tmem_ld16(tmem_d + ((uint32_t)lane_base << 16) + (uint32_t)cc, v);
-      if (row < Mp) finish16(e, (int)orow, cc, P.C, 0, v);
-    }
+    float* slab = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw))) + (warp & 3) * 32 * BN;
+    stage_accumulator<BN>(tmem_d + ((uint32_t)lane_base << 16), slab, lane, true);
+    store_staged_rows<BN>(e, slab, lane, 0, P.C, 0, [&](int r) -> long long { return __shfl_sync(0xffffffffu, orow, r); });
   }
   tc_fence_before();
   __syncthreads();
@@ -549,6 +571,7 @@ int tma_conv_dgrad(const float* dy, const float* w, float* dx, const b200rl_conv
 
 }  // namespace b200rl
 
+extern "C" int b200rl_debug_tma_stage_mode(int mode) { b200rl::g_tma_stage_mode = mode; return 0; }
 extern "C" int b200rl_debug_tma_timeline(unsigned long long* buf_dev) {
   cudaError_t e = cudaMemcpyToSymbol(b200rl::g_tma_timeline, &buf_dev, sizeof(buf_dev));
   return e == cudaSuccess ? 0 : -2;

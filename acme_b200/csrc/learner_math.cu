@@ -427,33 +427,38 @@ duelling_head_fwd_kernel(int B, int A, const float* __restrict__ h, int ldh, con
   }
 }
 
-// backward, part 1 (warp per sample): dval = sum_a dq, dadv = dq - mean(dq), and
-// dh = [dval * wv, dadv @ wa] * relu'(h); weights from shared memory, dadv row broadcast by shuffles
+// backward, part 1 (thread per sample x 4 hidden units): dval = sum_a dq, dadv = dq - mean(dq), and
+// dh = [dval * wv, dadv @ wa] * relu'(h).  The (A+1) x H weights are 40 KB: they stay in L1/L2, the dq row is a
+// warp-wide broadcast load.
 __global__ void __launch_bounds__(256)
 duelling_head_bwd_dh_kernel(int B, int A, int H, const float* __restrict__ dq, const float* __restrict__ h, int ldh,
                             const float* __restrict__ wv, const float* __restrict__ wa, float* __restrict__ dval,
                             float* __restrict__ dadv, float* __restrict__ dh, int lddh) {
-  extern __shared__ __align__(16) float sw[];
-  stage_head_weights(sw, wv, wa, A, H);
-  const int lane = threadIdx.x & 31;
-  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (b >= B) return;
+  const int per = H >> 2;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * per) return;
+  const int b = (int)(i / per), k = (int)(i % per) * 4;
+  const float* q = dq + (size_t)b * A;
   float s = 0.f;
-  for (int a = lane; a < A; a += 32) s += dq[(size_t)b * A + a];
-  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  for (int a = 0; a < A; ++a) s += __ldg(q + a);
   const float mean = s / (float)A;
-  for (int a = lane; a < A; a += 32) dadv[(size_t)b * A + a] = dq[(size_t)b * A + a] - mean;
-  if (lane == 0) dval[b] = s;
-  __syncwarp();
-  const float* hr = h + (size_t)b * ldh;
-  float* dr = dh + (size_t)b * lddh;
-  const float* gr = dadv + (size_t)b * A;
-  for (int k = lane; k < H; k += 32) {
-    dr[k] = hr[k] > 0.f ? s * sw[k] : 0.f;
-    float acc = 0.f;
-    for (int a = 0; a < A; ++a) acc = fmaf(gr[a], sw[(size_t)(a + 1) * H + k], acc);
-    dr[H + k] = hr[H + k] > 0.f ? acc : 0.f;
+  if (k == 0) {
+    dval[b] = s;
+    for (int a = 0; a < A; ++a) dadv[(size_t)b * A + a] = __ldg(q + a) - mean;
   }
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int a = 0; a < A; ++a) {
+    const float g = __ldg(q + a) - mean;
+    const float4 w = __ldg(reinterpret_cast<const float4*>(wa + (size_t)a * H + k));
+    acc.x = fmaf(g, w.x, acc.x); acc.y = fmaf(g, w.y, acc.y); acc.z = fmaf(g, w.z, acc.z); acc.w = fmaf(g, w.w, acc.w);
+  }
+  const float4 v = __ldg(reinterpret_cast<const float4*>(wv + k));
+  const float4 hv = __ldg(reinterpret_cast<const float4*>(h + (size_t)b * ldh + k));
+  const float4 ha = __ldg(reinterpret_cast<const float4*>(h + (size_t)b * ldh + H + k));
+  *reinterpret_cast<float4*>(dh + (size_t)b * lddh + k) =
+      make_float4(hv.x > 0.f ? s * v.x : 0.f, hv.y > 0.f ? s * v.y : 0.f, hv.z > 0.f ? s * v.z : 0.f, hv.w > 0.f ? s * v.w : 0.f);
+  *reinterpret_cast<float4*>(dh + (size_t)b * lddh + H + k) =
+      make_float4(ha.x > 0.f ? acc.x : 0.f, ha.y > 0.f ? acc.y : 0.f, ha.z > 0.f ? acc.z : 0.f, ha.w > 0.f ? acc.w : 0.f);
 }
 // backward, part 2: dwv[k] = sum_b dval[b] h[b,k], dwa[a,k] = sum_b dadv[b,a] h[b,H+k] and the bias sums.
 // The batch is cut into gridDim.z segments (partial sums, then a fixed-order add) so that enough
@@ -752,7 +757,6 @@ static int ensure_head_attrs() {
     B200RL_CUDA_OK(cudaFuncSetAttribute(duelling_head_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     B200RL_CUDA_OK(cudaFuncSetAttribute(duelling_head_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     B200RL_CUDA_OK(cudaFuncSetAttribute(duelling_head_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    B200RL_CUDA_OK(cudaFuncSetAttribute(duelling_head_bwd_dh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
   return B200RL_OK;
@@ -787,7 +791,11 @@ extern "C" int b200rl_duelling_head_bwd(int32_t B, int32_t A, int32_t H, const f
   const size_t smem = (size_t)(A + 1) * H * 4;
   B200RL_REQUIRE(smem <= 200 * 1024 && H % 4 == 0, "duelling head weights do not fit in shared memory");
   if (int rc = ensure_head_attrs()) return rc;
-  duelling_head_bwd_dh_kernel<<<ceil_div(B * 32, 256), 256, smem, st>>>(B, A, H, dq, h, ldh, wv, wa, dvalue, dadv, dh, lddh);
+  B200RL_REQUIRE(ldh % 4 == 0 && lddh % 4 == 0 &&
+                     (((uintptr_t)h | (uintptr_t)dh | (uintptr_t)wv | (uintptr_t)wa) & 15) == 0,
+                 "duelling head: rows must be 16-byte aligned");
+  duelling_head_bwd_dh_kernel<<<(int)ceil_div<long long>((long long)B * (H / 4), 256), 256, 0, st>>>(B, A, H, dq, h, ldh, wv, wa,
+                                                                                                     dvalue, dadv, dh, lddh);
   B200RL_LAUNCH_OK();
   int segs = std::max(1, std::min(B / 32, 8));
   const int64_t per = (int64_t)(A + 1) * (H + 1) * 4;

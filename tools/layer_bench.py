@@ -19,7 +19,9 @@ def t(fn, it=20):
 def main():
   B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
   out = {}
-  for prec in (0, 1):
+  mode = int(os.environ.get('B200RL_STAGE_MODE', '0'))
+  _capi.load().b200rl_debug_tma_stage_mode(mode)
+  for prec in ((1,) if mode else (0, 1)):
     net = networks.DQNAtariNetwork(18, precision=prec)
     P = net.params
     bufs, g = net.make_buffers(B), net.make_grad_buffers(B)
@@ -53,6 +55,9 @@ def main():
     r['forward'] = t(lambda: net.forward(obs, bufs))
     r['backward'] = t(lambda: net.backward(obs, bufs, g, dq))
     out['fp32' if prec == 0 else 'bf16'] = r
+  if mode:
+    print(json.dumps({k: round(v, 1) for k, v in out['bf16'].items()}))
+    return
   for k in out['fp32']:
     print(f"{k:26s} fp32 {out['fp32'][k]:9.1f} us   bf16 {out['bf16'][k]:9.1f} us")
   json.dump(out, open('gpurun_out/layer_bench.json', 'w'), indent=1)
