@@ -122,7 +122,7 @@ __device__ __forceinline__ void tma_load_im2col(uint32_t smem_dst, const CUtenso
 // When A is the implicit im2col of a convolution input: k-block i = (filter tap, block of 32 channels)
 struct ConvA {
   int enabled;
-  int C, kw, OW, OH, stride, pad_left, pad_top, taps;
+  int C, kw, OW, OH, stride_w, stride_h, pad_left, pad_top, taps;
 };
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -186,9 +186,28 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     int ax = 0, ay = 0, an = 0;   // im2col anchor of the tile's first pixel (input coordinates)
     if (conv.enabled) {
       const int ox = row0 % conv.OW, t = row0 / conv.OW;
-      ax = ox * conv.stride - conv.pad_left;
-      ay = (t % conv.OH) * conv.stride - conv.pad_top;
+      ax = ox * conv.stride_w - conv.pad_left;
+      ay = (t % conv.OH) * conv.stride_h - conv.pad_top;
       an = t / conv.OH;
+    }
+    // all per-k-block coordinates advance incrementally: the producer is a single thread and run-time integer
+    // divisions (dozens of instructions each) would bound the rate at which it can issue loads
+    int f_c0 = 0, f_tx = 0, f_ty = 0;          // conv forward: channel block / filter tap of the current k-block
+    int w_ox = 0, w_oy = 0, w_n = 0;           // conv weight gradient: first pixel of the current k-block
+    int w_c[GBM / 32], w_tx[GBM / 32], w_ty[GBM / 32], w_nblk = 0;   // ... and its (loop-invariant) row blocks
+    if (conv.enabled && !AMN) {
+      const int cb = conv.C / GBK, tap = kb_begin / cb;
+      f_c0 = (kb_begin % cb) * GBK; f_tx = tap % conv.kw; f_ty = tap / conv.kw;
+    }
+    if (conv.enabled && AMN) {
+      const int p0 = kb_begin * GBK, t = p0 / conv.OW;
+      w_ox = p0 % conv.OW; w_oy = t % conv.OH; w_n = t / conv.OH;
+#pragma unroll
+      for (int j = 0; j < GBM / 32; ++j) {
+        const int r = row0 + 32 * j, tap = r / conv.C;
+        w_c[j] = r % conv.C; w_tx[j] = tap % conv.kw; w_ty[j] = tap / conv.kw;
+        if (tap < conv.taps) w_nblk = j + 1;   // taps are ascending in j: blocks past the last tap are skipped
+      }
     }
     for (int i = 0; i < nkb; ++i) {
       const int s = i % STAGES;
@@ -199,27 +218,28 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         // conv weight gradient: rows = patch indices (tap, channel), reduction = pixels.  Row block j of the tile
         // is 32 channels of one tap for the 32 pixels of this k-block; blocks past the last tap are skipped
         // (their accumulator rows are never stored).
-        const int ox = k0 % conv.OW, t = k0 / conv.OW;
-        const int px = ox * conv.stride - conv.pad_left, py = (t % conv.OH) * conv.stride - conv.pad_top, pn = t / conv.OH;
-        int nblk = 0;
+        const int px = w_ox * conv.stride_w - conv.pad_left, py = w_oy * conv.stride_h - conv.pad_top;
+        mbar_expect_tx(&bar_full[s], w_nblk * 4096 + B_BYTES);
 #pragma unroll
-        for (int j = 0; j < GBM / 32; ++j) nblk += ((row0 + 32 * j) / conv.C < conv.taps) ? 1 : 0;
-        mbar_expect_tx(&bar_full[s], nblk * 4096 + B_BYTES);
-#pragma unroll
-        for (int j = 0; j < GBM / 32; ++j) {
-          const int r = row0 + 32 * j, tap = r / conv.C;
-          if (tap < conv.taps)
-            tma_load_im2col(sa + j * 4096, &map_a, r % conv.C, px, py, pn, (uint16_t)(tap % conv.kw), (uint16_t)(tap / conv.kw),
-                            &bar_full[s]);
+        for (int j = 0; j < GBM / 32; ++j)
+          if (j < w_nblk)
+            tma_load_im2col(sa + j * 4096, &map_a, w_c[j], px, py, w_n, (uint16_t)w_tx[j], (uint16_t)w_ty[j], &bar_full[s]);
+        w_ox += GBK;
+        while (w_ox >= conv.OW) {
+          w_ox -= conv.OW;
+          if (++w_oy == conv.OH) { w_oy = 0; ++w_n; }
         }
       } else {
         mbar_expect_tx(&bar_full[s], STAGE);
       }
       if (AMN && conv.enabled) {
       } else if (!AMN && conv.enabled) {   // conv forward: 128 pixels x 32 channels of one tap
-        const int cb = conv.C / GBK, kb = kb_begin + i;
-        const int tap = kb / cb, c0 = (kb % cb) * GBK;
-        tma_load_im2col(sa, &map_a, c0, ax, ay, an, (uint16_t)(tap % conv.kw), (uint16_t)(tap / conv.kw), &bar_full[s]);
+        tma_load_im2col(sa, &map_a, f_c0, ax, ay, an, (uint16_t)f_tx, (uint16_t)f_ty, &bar_full[s]);
+        f_c0 += GBK;
+        if (f_c0 == conv.C) {
+          f_c0 = 0;
+          if (++f_tx == conv.kw) { f_tx = 0; ++f_ty; }
+        }
       } else if (AMN) {
 #pragma unroll
         for (int j = 0; j < GBM / 32; ++j) tma_load_2d(sa + j * 4096, &map_a, row0 + 32 * j, k0, &bar_full[s]);
@@ -262,7 +282,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
     if (tid == 64) tm_mark(10);
     const int lane_base = (warp & 3) * 32;
-    if (epi.transpose_out) {
+    if (epi.transpose_out && !epi.partial) {
       // C^T is wanted: lanes (= rows) are already the contiguous direction of the destination
       const int row = row0 + lane_base + lane;
 #pragma unroll 1
@@ -335,7 +355,7 @@ static int launch_tma_bn(const CUtensorMap& ma, const CUtensorMap& mb, Epilogue 
 
 template <bool AMN, bool BMN>
 static int launch_tma(const CUtensorMap& ma, const CUtensorMap& mb, const Epilogue& epi, int M, int N, int K, int BN,
-                      void* ws, int64_t wsb, cudaStream_t s, const ConvA& conv = ConvA{0, 0, 0, 0, 0, 0, 0, 0, 0}) {
+                      void* ws, int64_t wsb, cudaStream_t s, const ConvA& conv = ConvA{0, 0, 0, 0, 0, 0, 0, 0, 0, 0}) {
   if (BN == 32) return launch_tma_bn<AMN, BMN, 32>(ma, mb, epi, M, N, K, ws, wsb, s, conv);
   if (BN == 64) return launch_tma_bn<AMN, BMN, 64>(ma, mb, epi, M, N, K, ws, wsb, s, conv);
   return launch_tma_bn<AMN, BMN, 128>(ma, mb, epi, M, N, K, ws, wsb, s, conv);
@@ -385,7 +405,7 @@ int tma_conv_fwd(const float* x, const float* w, const float* bias, float* y, co
   CUtensorMap ma, mb;
   if (!make_im2col_map(&ma, x, g, GBK, GBM, false) || !make_map(&mb, w, g.Cout, K, K, GBK, BN, false)) return 1;
   Epilogue e{y, g.Cout, bias, act, nullptr, 0, 0, nullptr, 0};
-  ConvA conv{1, g.C, g.kw, g.OW, g.OH, g.stride, g.pad_left, g.pad_top, g.kh * g.kw};
+  ConvA conv{1, g.C, g.kw, g.OW, g.OH, g.stride, g.stride, g.pad_left, g.pad_top, g.kh * g.kw};
   return launch_tma<false, false>(ma, mb, e, M, g.Cout, K, BN, ws, wsb, s, conv);
 }
 
@@ -398,10 +418,126 @@ int tma_conv_wgrad(const float* x, const float* dy, float* dw, float* db, const 
   CUtensorMap ma, mb;
   if (!make_im2col_map(&ma, x, g, 32, GBK, true) || !make_map(&mb, dy, M, g.Cout, g.Cout, 32, GBK, true)) return 1;
   Epilogue e{dw, K, nullptr, 0, nullptr, 0, 0, nullptr, 1};   // stored transposed: dw[co][k]
-  ConvA conv{1, g.C, g.kw, g.OW, g.OH, g.stride, g.pad_left, g.pad_top, g.kh * g.kw};
+  ConvA conv{1, g.C, g.kw, g.OW, g.OH, g.stride, g.stride, g.pad_left, g.pad_top, g.kh * g.kw};
   int rc = launch_tma<true, true>(ma, mb, e, K, g.Cout, M, BN, ws, wsb, s, conv);
   if (rc) return rc;
   if (db) return launch_colsum(M, g.Cout, dy, g.Cout, db, ws, wsb, s);
+  return B200RL_OK;
+}
+
+// ---- first-layer convolutions on uint8 frames (DQN conv1: 84x84x4, 8x8 stride 4).  Four channels are far too
+// few for TMA's im2col mode, but one filter ROW (kw * C = 32 values) is contiguous in an NHWC image.  The frames are
+// therefore rewritten once per call as zero-padded fp32 rows, float(x) / 255 (`atari_wrapper.py:303-304`), and the
+// convolution becomes a kh x 1 filter over "wide pixels" of 32 channels: wide pixel ox of an image row starts at
+// float offset ox * stride * C, i.e. neighbouring wide pixels OVERLAP in memory (TMA strides need not be >= the
+// extent of the inner dimension).  If the driver refuses the overlapping view the rows are materialised without
+// overlap instead ([.., OW, 32], twice the bytes).
+__global__ void __launch_bounds__(256)
+u8_rows_to_f32_kernel(const uint8_t* __restrict__ x, float* __restrict__ out, int B, int H, int W, int C, int Hp, int row_floats,
+                      int wide_stride /* floats between wide pixels */, int src_step /* source pixels between wide pixels */,
+                      int pad_left, int pad_top, long long total4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one float4 = C (== 4) channels of one pixel
+  if (i >= total4) return;
+  const int per_row = row_floats >> 2;
+  const int q = (int)(i % per_row);
+  long long t = i / per_row;
+  const int hp = (int)(t % Hp);
+  const int b = (int)(t / Hp);
+  // position q of the row belongs to wide pixel q / (wide_stride / 4) at pixel offset q % (wide_stride / 4)
+  const int wq = wide_stride >> 2;
+  const int xs = (q / wq) * src_step + (q % wq) - pad_left, ys = hp - pad_top;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (xs >= 0 && xs < W && ys >= 0 && ys < H) {
+    const uchar4 p = __ldg(reinterpret_cast<const uchar4*>(x + (((size_t)b * H + ys) * W + xs) * 4));
+    v = make_float4(__fdiv_rn((float)p.x, 255.f), __fdiv_rn((float)p.y, 255.f), __fdiv_rn((float)p.z, 255.f), __fdiv_rn((float)p.w, 255.f));
+  }
+  reinterpret_cast<float4*>(out)[i] = v;
+}
+
+struct WideView {
+  int Hp, row_floats, wide_stride;   // padded rows, floats per row, floats between wide pixels
+  int64_t bytes;
+};
+static int g_wide_overlap = 1;   // 1 = try the overlapping view first, 0 = driver refused it once
+static bool wide_eligible(const b200rl_conv_geom& g) {
+  return g.C == 4 && g.kw * g.C == GBK && g.Cout % 8 == 0 && g.Cout <= 128 && (g.stride * g.C * 4) % 16 == 0;
+}
+static WideView wide_view(const b200rl_conv_geom& g, bool overlap) {
+  WideView v;
+  const int pad_bottom = (g.OH - 1) * g.stride + g.kh - g.H - g.pad_top;
+  const int pad_right = (g.OW - 1) * g.stride + g.kw - g.W - g.pad_left;
+  v.Hp = g.H + g.pad_top + std::max(pad_bottom, 0);
+  if (overlap) { v.row_floats = (g.W + g.pad_left + std::max(pad_right, 0)) * g.C; v.wide_stride = g.stride * g.C; }
+  else { v.row_floats = g.OW * GBK; v.wide_stride = GBK; }
+  v.bytes = (int64_t)g.B * v.Hp * v.row_floats * 4;
+  return v;
+}
+static int wide_convert(const uint8_t* x, float* out, const b200rl_conv_geom& g, const WideView& v, bool overlap, cudaStream_t s) {
+  const long long total4 = (long long)g.B * v.Hp * (v.row_floats / 4);
+  // overlapping view: the row is the padded image itself, "wide pixel" granularity = one source pixel
+  const int ws_ = overlap ? 4 : v.wide_stride, step = overlap ? 1 : g.stride;
+  u8_rows_to_f32_kernel<<<(int)ceil_div<long long>(total4, 256), 256, 0, s>>>(x, out, g.B, g.H, g.W, g.C, v.Hp, v.row_floats, ws_, step,
+                                                                          g.pad_left, g.pad_top, total4);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+static bool make_wide_map(CUtensorMap* m, const float* xw, const b200rl_conv_geom& g, const WideView& v, int pixels, bool mn_major) {
+  EncodeIm2colFn enc = get_encode_im2col();
+  if (!enc) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)GBK, (cuuint64_t)g.OW, (cuuint64_t)v.Hp, (cuuint64_t)g.B};
+  cuuint64_t strides[3] = {(cuuint64_t)v.wide_stride * 4, (cuuint64_t)v.row_floats * 4, (cuuint64_t)v.Hp * v.row_floats * 4};
+  int lower[2] = {0, 0};
+  int upper[2] = {0, -(g.kh - 1)};
+  cuuint32_t es[4] = {1, 1, (cuuint32_t)g.stride, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)xw, dims, strides, lower, upper, GBK, (cuuint32_t)pixels, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// picks the view (overlapping first), converts the frames into ws and builds the A map; *used = bytes of ws taken
+static int wide_prepare(const uint8_t* x, const b200rl_conv_geom& g, void* ws, int64_t wsb, int pixels, bool mn_major,
+                        CUtensorMap* ma, int64_t* used, cudaStream_t s) {
+  if (!wide_eligible(g) || !ws || (((uintptr_t)ws) & 127) != 0) return 1;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    const bool overlap = g_wide_overlap != 0;
+    const WideView v = wide_view(g, overlap);
+    if (v.bytes > wsb) return 1;
+    if (make_wide_map(ma, (const float*)ws, g, v, pixels, mn_major)) {
+      *used = (v.bytes + 1023) & ~(int64_t)1023;
+      return wide_convert(x, (float*)ws, g, v, overlap, s);
+    }
+    if (!overlap) return 1;
+    g_wide_overlap = 0;
+  }
+  return 1;
+}
+
+int tma_conv_fwd_u8(const uint8_t* x, const float* w, const float* bias, float* y, const b200rl_conv_geom& g, int act,
+                    void* ws, int64_t wsb, cudaStream_t s) {
+  const int M = g.B * g.OH * g.OW, K = g.kh * g.kw * g.C;
+  if (!tma_ok(w, K) || (int64_t)M * g.Cout * 4 < 131072) return 1;
+  CUtensorMap ma, mb;
+  int64_t used = 0;
+  const int BN = pick_bn(g.Cout);
+  if (!make_map(&mb, w, g.Cout, K, K, GBK, BN, false)) return 1;
+  if (int rc = wide_prepare(x, g, ws, wsb, GBM, false, &ma, &used, s)) return rc;
+  Epilogue e{y, g.Cout, bias, act, nullptr, 0, 0, nullptr, 0};
+  ConvA conv{1, GBK, 1, g.OW, g.OH, 1, g.stride, 0, 0, g.kh};
+  return launch_tma<false, false>(ma, mb, e, M, g.Cout, K, BN, (char*)ws + used, wsb - used, s, conv);
+}
+int tma_conv_wgrad_u8(const uint8_t* x, const float* dy, float* dw, float* db, const b200rl_conv_geom& g, void* ws, int64_t wsb,
+                      cudaStream_t s) {
+  const int M = g.B * g.OH * g.OW, K = g.kh * g.kw * g.C;
+  if (!tma_ok(dy, g.Cout) || g.Cout % 32 != 0 || (int64_t)M * g.Cout * 4 < 131072 || M < GBK) return 1;
+  CUtensorMap ma, mb;
+  int64_t used = 0;
+  const int BN = pick_bn(g.Cout);
+  if (!make_map(&mb, dy, M, g.Cout, g.Cout, 32, GBK, true)) return 1;
+  if (int rc = wide_prepare(x, g, ws, wsb, GBK, true, &ma, &used, s)) return rc;
+  Epilogue e{dw, K, nullptr, 0, nullptr, 0, 0, nullptr, 1};
+  ConvA conv{1, GBK, 1, g.OW, g.OH, 1, g.stride, 0, 0, g.kh};
+  int rc = launch_tma<true, true>(ma, mb, e, K, g.Cout, M, BN, (char*)ws + used, wsb - used, s, conv);
+  if (rc) return rc;
+  if (db) return launch_colsum(M, g.Cout, dy, g.Cout, db, (char*)ws + used, wsb - used, s);
   return B200RL_OK;
 }
 
@@ -462,17 +598,21 @@ tma_conv_dgrad_kernel(const __grid_constant__ DgradMaps maps, const __grid_const
     const int jx = row0 % ph.cnt_x, t = row0 / ph.cnt_x;
     const int ax = ph.lower_x + jx, ay = ph.lower_y + t % ph.cnt_y, an = t / ph.cnt_y;
     const int K = P.kw * P.C;   // weight row: tap (ky, kx) starts at (ky kw + kx) C; rows are kh*K long
+    int co0 = 0, off_x = 0, off_y = 0;   // advanced incrementally (no divisions in the issue loop)
     for (int i = 0; i < nkb; ++i) {
       const int s = i % G_STAGES;
       if (i >= G_STAGES) mbar_wait(&bar_empty[s], ((i / G_STAGES) - 1) & 1);
       const uint32_t sa = base + s * STAGE, sb = sa + A_BYTES;
-      const int tap = i / cb, co0 = (i % cb) * GBK;
-      const int off_y = tap / ph.Tx, off_x = tap % ph.Tx;
       const int ky = ph.py + P.stride * (ph.Ty - 1 - off_y), kx = ph.px + P.stride * (ph.Tx - 1 - off_x);
       mbar_expect_tx(&bar_full[s], STAGE);
       tma_load_im2col(sa, &maps.m[phase], co0, ax, ay, an, (uint16_t)off_x, (uint16_t)off_y, &bar_full[s]);
 #pragma unroll
       for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * 4096, &map_w, ky * K + kx * P.C + 32 * j, co0, &bar_full[s]);
+      co0 += GBK;
+      if (co0 == P.Cout) {
+        co0 = 0;
+        if (++off_x == ph.Tx) { off_x = 0; ++off_y; }
+      }
     }
   } else if (warp == 1 && lane == 0) {
     constexpr uint32_t idesc = umma_idesc_tf32(GBM, BN, false, true);

@@ -41,6 +41,10 @@ int tma_conv_wgrad(const float* x, const float* dy, float* dw, float* db, const 
                    cudaStream_t s);
 int tma_conv_dgrad(const float* dy, const float* w, float* dx, const b200rl_conv_geom& g, const float* mask, int mask_act,
                    void* ws, int64_t wsb, cudaStream_t s);
+int tma_conv_fwd_u8(const uint8_t* x, const float* w, const float* bias, float* y, const b200rl_conv_geom& g, int act,
+                    void* ws, int64_t wsb, cudaStream_t s);
+int tma_conv_wgrad_u8(const uint8_t* x, const float* dy, float* dw, float* db, const b200rl_conv_geom& g, void* ws, int64_t wsb,
+                      cudaStream_t s);
 }  // namespace b200rl
 
 using namespace b200rl;
@@ -67,8 +71,9 @@ extern "C" int b200rl_conv2d_fwd(const void* x, int x_u8, const float* w, const 
                                  const b200rl_conv_geom* g, int act, int precision, void* ws, int64_t wsb, void* stream) {
   B200RL_REQUIRE(x && w && y, "null argument");
   if (int rc = check_geom(g)) return rc;
-  if (precision == 1 && g_use_tma && !x_u8) {
-    int rc = tma_conv_fwd((const float*)x, w, bias, y, *g, act, ws, wsb, as_stream(stream));
+  if (precision == 1 && g_use_tma) {
+    int rc = x_u8 ? tma_conv_fwd_u8((const uint8_t*)x, w, bias, y, *g, act, ws, wsb, as_stream(stream))
+                  : tma_conv_fwd((const float*)x, w, bias, y, *g, act, ws, wsb, as_stream(stream));
     if (rc != 1) return rc;
   }
   PRECISION_SWITCH(simt_conv_fwd(x, x_u8, w, bias, y, *g, act, ws, wsb, as_stream(stream)),
@@ -78,8 +83,9 @@ extern "C" int b200rl_conv2d_wgrad(const void* x, int x_u8, const float* dy, flo
                                    const b200rl_conv_geom* g, int precision, void* ws, int64_t wsb, void* stream) {
   B200RL_REQUIRE(x && dy && dw, "null argument");
   if (int rc = check_geom(g)) return rc;
-  if (precision == 1 && g_use_tma && !x_u8) {
-    int rc = tma_conv_wgrad((const float*)x, dy, dw, db, *g, ws, wsb, as_stream(stream));
+  if (precision == 1 && g_use_tma) {
+    int rc = x_u8 ? tma_conv_wgrad_u8((const uint8_t*)x, dy, dw, db, *g, ws, wsb, as_stream(stream))
+                  : tma_conv_wgrad((const float*)x, dy, dw, db, *g, ws, wsb, as_stream(stream));
     if (rc != 1) return rc;
   }
   PRECISION_SWITCH(simt_conv_wgrad(x, x_u8, dy, dw, db, *g, ws, wsb, as_stream(stream)),
