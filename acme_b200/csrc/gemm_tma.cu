@@ -433,25 +433,23 @@ int tma_conv_wgrad(const float* x, const float* dy, float* dw, float* db, const 
 // extent of the inner dimension).  If the driver refuses the overlapping view the rows are materialised without
 // overlap instead ([.., OW, 32], twice the bytes).
 __global__ void __launch_bounds__(256)
-u8_rows_to_f32_kernel(const uint8_t* __restrict__ x, float* __restrict__ out, int B, int H, int W, int C, int Hp, int row_floats,
-                      int wide_stride /* floats between wide pixels */, int src_step /* source pixels between wide pixels */,
-                      int pad_left, int pad_top, long long total4) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one float4 = C (== 4) channels of one pixel
-  if (i >= total4) return;
-  const int per_row = row_floats >> 2;
-  const int q = (int)(i % per_row);
-  long long t = i / per_row;
-  const int hp = (int)(t % Hp);
-  const int b = (int)(t / Hp);
-  // position q of the row belongs to wide pixel q / (wide_stride / 4) at pixel offset q % (wide_stride / 4)
-  const int wq = wide_stride >> 2;
-  const int xs = (q / wq) * src_step + (q % wq) - pad_left, ys = hp - pad_top;
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (xs >= 0 && xs < W && ys >= 0 && ys < H) {
-    const uchar4 p = __ldg(reinterpret_cast<const uchar4*>(x + (((size_t)b * H + ys) * W + xs) * 4));
-    v = make_float4(__fdiv_rn((float)p.x, 255.f), __fdiv_rn((float)p.y, 255.f), __fdiv_rn((float)p.z, 255.f), __fdiv_rn((float)p.w, 255.f));
+u8_rows_to_f32_kernel(const uint8_t* __restrict__ x, float* __restrict__ out, int H, int W, int Hp, int per_row /* float4s */,
+                      int wq /* float4s per wide pixel */, int src_step /* source pixels between wide pixels */, int pad_left,
+                      int pad_top) {
+  // blockIdx.x = padded row (b, hp); threads = the row's float4s (one float4 = the 4 channels of one pixel)
+  const int row = blockIdx.x, b = row / Hp, hp = row - b * Hp, ys = hp - pad_top;
+  float4* dst = reinterpret_cast<float4*>(out) + (size_t)row * per_row;
+  const bool live = ys >= 0 && ys < H;
+  const uchar4* src = reinterpret_cast<const uchar4*>(x) + ((size_t)b * H + (live ? ys : 0)) * W;
+  for (int q = blockIdx.y * blockDim.x + threadIdx.x; q < per_row; q += gridDim.y * blockDim.x) {
+    const int xs = wq == 1 ? q - pad_left : (q / wq) * src_step + (q % wq) - pad_left;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live && xs >= 0 && xs < W) {
+      const uchar4 p = __ldg(src + xs);
+      v = make_float4(__fdiv_rn((float)p.x, 255.f), __fdiv_rn((float)p.y, 255.f), __fdiv_rn((float)p.z, 255.f), __fdiv_rn((float)p.w, 255.f));
+    }
+    dst[q] = v;
   }
-  reinterpret_cast<float4*>(out)[i] = v;
 }
 
 struct WideView {
@@ -473,11 +471,11 @@ static WideView wide_view(const b200rl_conv_geom& g, bool overlap) {
   return v;
 }
 static int wide_convert(const uint8_t* x, float* out, const b200rl_conv_geom& g, const WideView& v, bool overlap, cudaStream_t s) {
-  const long long total4 = (long long)g.B * v.Hp * (v.row_floats / 4);
   // overlapping view: the row is the padded image itself, "wide pixel" granularity = one source pixel
-  const int ws_ = overlap ? 4 : v.wide_stride, step = overlap ? 1 : g.stride;
-  u8_rows_to_f32_kernel<<<(int)ceil_div<long long>(total4, 256), 256, 0, s>>>(x, out, g.B, g.H, g.W, g.C, v.Hp, v.row_floats, ws_, step,
-                                                                          g.pad_left, g.pad_top, total4);
+  const int per_row = v.row_floats / 4, wq = overlap ? 1 : v.wide_stride / 4, step = overlap ? 1 : g.stride;
+  const int threads = per_row <= 96 ? 96 : 256;
+  u8_rows_to_f32_kernel<<<dim3(g.B * v.Hp, ceil_div(per_row, threads)), threads, 0, s>>>(x, out, g.H, g.W, v.Hp, per_row, wq, step,
+                                                                                        g.pad_left, g.pad_top);
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }

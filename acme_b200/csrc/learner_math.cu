@@ -257,9 +257,16 @@ adam_kernel(long long n, float* __restrict__ p, const float* __restrict__ g, flo
             float* __restrict__ v, const long long* __restrict__ step_dev, float lr, double b1,
             double b2, float eps, int eps_mode, const float* __restrict__ gscale_dev,
             __nv_bfloat16* __restrict__ shadow) {
-  const double t = (double)(*step_dev + 1);
+  // the double-precision powers cost a few hundred FP64 instructions: one thread per CTA evaluates them
+  __shared__ float bc_sh[2];
+  if (threadIdx.x == 0) {
+    const double t = (double)(*step_dev + 1);
+    bc_sh[0] = (float)(1.0 - pow(b1, t));
+    bc_sh[1] = (float)(1.0 - pow(b2, t));
+  }
+  __syncthreads();
   AdamConsts c;
-  c.bc1 = (float)(1.0 - pow(b1, t)); c.bc2 = (float)(1.0 - pow(b2, t));
+  c.bc1 = bc_sh[0]; c.bc2 = bc_sh[1];
   c.b1f = (float)b1; c.b2f = (float)b2; c.omb1 = (float)(1.0 - b1); c.omb2 = (float)(1.0 - b2);
   c.gs = gscale_dev ? *gscale_dev : 1.f;
   c.k1 = sqrtf(c.bc2) / c.bc1; c.lr = lr; c.eps = eps; c.eps_mode = eps_mode;

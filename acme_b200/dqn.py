@@ -64,6 +64,10 @@ class DQNLearner(core.Learner, core.Saveable):
     self._wmax = torch.zeros(1, dtype=torch.float64, device=dev)
     self._gscale = torch.full((1,), 1.0 / self._world, dtype=torch.float32, device=dev)
     self._loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+    # fetch_loss='async': two pinned slots + events, the loss of step i is logged when step i+1 is issued
+    self._loss_ring = torch.zeros(2, dtype=torch.float32).pin_memory()
+    self._loss_events = [torch.cuda.Event(), torch.cuda.Event()]
+    self._loss_pending = None
     self._graphs = None
     self._use_graph = bool(use_cuda_graph)
     # the three forward passes are independent, and so are a layer's weight- and data-gradient: run them on
@@ -226,7 +230,10 @@ class DQNLearner(core.Learner, core.Saveable):
       self._graphs[3].replay()
 
   # ------------------------------------------------------------------ acme.core.Learner
-  def step(self, uniforms=None, fetch_loss: bool = True):
+  def step(self, uniforms=None, fetch_loss=True):
+    """One learner update (`dqn/learning.py:143-163`).  `fetch_loss`: True = read the loss back and log it before
+    returning (the reference behaviour); 'async' = copy it to pinned memory without stalling and log it when the NEXT
+    step is issued (or at `drain()`), so host-side inserts overlap the device step; False = leave it on the device."""
     table = self._dataset.table
     table.flush()
     if table.size < 1:
@@ -234,7 +241,16 @@ class DQNLearner(core.Learner, core.Saveable):
     self._device_step(uniforms)
     self._steps_done += 1
     result = {}
-    if fetch_loss:
+    if fetch_loss == 'async':
+      slot = self._steps_done & 1
+      self._loss_ring[slot:slot + 1].copy_(self.loss, non_blocking=True)
+      self._loss_events[slot].record()
+      previous, self._loss_pending = self._loss_pending, slot
+      if previous is not None:
+        self._loss_events[previous].synchronize()
+        result['loss'] = float(self._loss_ring[previous])
+    elif fetch_loss:
+      self.drain()
       self._loss_host.copy_(self.loss, non_blocking=True)
       self._torch.cuda.current_stream().synchronize()
       result['loss'] = float(self._loss_host[0])
@@ -244,6 +260,16 @@ class DQNLearner(core.Learner, core.Saveable):
     result.update(self._counter.increment(steps=1, walltime=elapsed))
     self._logger.write(result)
     return None
+
+  def drain(self):
+    """Logs the loss still in flight from a `fetch_loss='async'` step; returns it (or None)."""
+    if self._loss_pending is None:
+      return None
+    slot, self._loss_pending = self._loss_pending, None
+    self._loss_events[slot].synchronize()
+    loss = float(self._loss_ring[slot])
+    self._logger.write({'loss': loss})
+    return loss
 
   def get_variables(self, names: List[str]) -> List[List[np.ndarray]]:
     return [list(self._net.variables().values())]
