@@ -693,6 +693,17 @@ extern "C" int b200rl_dpg_action_grad(int32_t B, int32_t A, const float* dqda, f
   return B200RL_OK;
 }
 
+// tools/step_phases.py: a one-thread kernel that writes the global timer, placed between the phases of a captured step
+__global__ void stamp_kernel(unsigned long long* buf, int slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  buf[slot] = t;
+}
+extern "C" int b200rl_debug_stamp(unsigned long long* buf, int slot, void* stream) {
+  stamp_kernel<<<1, 1, 0, as_stream(stream)>>>(buf, slot);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
 extern "C" int b200rl_adam(int64_t n, float* param, const float* grad, float* m, float* v, const int64_t* step_dev,
                            float lr, double b1, double b2, float eps, int eps_mode, const float* grad_scale_dev,
                            void* bf16_shadow, void* stream) {

@@ -11,6 +11,8 @@ dataset, actor and learner like `acme/agents/tf/dqn/agent.py:45-162`.
 
 from __future__ import annotations
 
+import ctypes
+import os
 import time
 from typing import List, Optional
 
@@ -68,6 +70,7 @@ class DQNLearner(core.Learner, core.Saveable):
     self._loss_ring = torch.zeros(2, dtype=torch.float32).pin_memory()
     self._loss_events = [torch.cuda.Event(), torch.cuda.Event()]
     self._loss_pending = None
+    self._stamps = torch.zeros(8, dtype=torch.int64, device='cuda') if os.environ.get('B200RL_STAMPS') else None
     self._graphs = None
     self._use_graph = bool(use_cuda_graph)
     # the three forward passes are independent, and so are a layer's weight- and data-gradient: run them on
@@ -97,10 +100,16 @@ class DQNLearner(core.Learner, core.Saveable):
       return a.view(torch.int32).view(self.B)
     return a.view(getattr(torch, self._act_dtype.name)).view(self.B).to(torch.int32)
 
+  def _stamp(self, slot: int):
+    """tools/step_phases.py: global-timer stamps between the phases of the (captured) step; off by default."""
+    if self._stamps is not None:
+      _capi.load().b200rl_debug_stamp(ctypes.c_void_p(self._stamps.data_ptr()), slot, ctypes.c_void_p(_capi.current_stream()))
+
   def _forwards(self):
     """K1 sample, K3 gather, the three forward passes (learning.py:117-125) [+ local IS-weight max]."""
     ds, net, tgt = self._dataset, self._net, self._tgt
     st = _capi.current_stream()
+    self._stamp(1)
     o_tm1, o_t = self._obs_view(ds.o_tm1), self._obs_view(ds.o_t)
     if self._concurrent:
       torch = self._torch
@@ -123,6 +132,7 @@ class DQNLearner(core.Learner, core.Saveable):
       net.forward(o_tm1, self._bufs_train)                       # learning.py:123
       tgt.forward(o_t, self._bufs_tgt)                           # learning.py:124
       net.forward(o_t, self._bufs_sel)                           # learning.py:125
+    self._stamp(2)
     if self._world > 1:   # local max importance weight; the all-reduce(MAX) of this one f64 follows
       _capi.call('b200rl_is_weight_max', self.B, _capi.ptr(ds.prob), self._beta, _capi.ptr(self._wmax), st)
 
@@ -142,6 +152,7 @@ class DQNLearner(core.Learner, core.Saveable):
                _capi.ptr(ds.prob), self._discount, self._delta, self._beta, self._max_abs_reward, wmax, 1.0 / self.B,
                _capi.ptr(self.td), _capi.ptr(self.loss_ps), _capi.ptr(self.weight), _capi.ptr(self.priority),
                _capi.ptr(self.dq), _capi.ptr(self.loss), st)
+    self._stamp(3)
     if part == 'dense':
       net.backward_dense_part(self._bufs_train, self._gbufs, self.dq, self._side[0])
     elif self._concurrent:
@@ -154,6 +165,7 @@ class DQNLearner(core.Learner, core.Saveable):
     if self._world > 1:
       self._dp.global_max_(self._wmax)
     self._loss_backward()
+    self._stamp(4)
 
   def _apply(self):
     net, tgt, st = self._net, self._tgt, _capi.current_stream()
@@ -161,12 +173,14 @@ class DQNLearner(core.Learner, core.Saveable):
     _capi.call('b200rl_adam', P.size, _capi.ptr(P.flat), _capi.ptr(P.grad), _capi.ptr(self._m), _capi.ptr(self._v),
                _capi.ptr(self._num_steps), self._lr, 0.9, 0.999, self._adam_eps, self._eps_mode,
                _capi.ptr(self._gscale) if self._world > 1 else None, None, st)
+    self._stamp(5)
     if self._replay_client is not None:                         # learning.py:151-154
       self._dataset.table.update_priorities_device(self._dataset.keys, self.priority)
     # learning.py:157-161: copy when num_steps % period == 0, evaluated before the increment
     _capi.call('b200rl_copy_if_period', P.size * 4, _capi.ptr(tgt.params.flat), _capi.ptr(P.flat),
                _capi.ptr(self._num_steps), self._period, 0, st)
     _capi.call('b200rl_step_increment', _capi.ptr(self._num_steps), st)
+    self._stamp(6)
 
   def _eager_step(self, uniforms):
     lib = _capi.load()
@@ -195,6 +209,7 @@ class DQNLearner(core.Learner, core.Saveable):
     if self._graphs is None:
       if self._world == 1:
         def whole():
+          self._stamp(0)
           self._dataset.sample_raw()
           self._forward_loss()
           self._apply()
