@@ -76,6 +76,8 @@ class DQNLearner(core.Learner, core.Saveable):
     # the three forward passes are independent, and so are a layer's weight- and data-gradient: run them on
     # parallel streams (fork/join with events, also inside the captured graph)
     self._concurrent = bool(concurrent_streams) and hasattr(network, '_backward_two_streams')
+    self._split_adam = self._concurrent and hasattr(network, 'grad_buckets')
+    self._tail_done = None
     self._side = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)] if self._concurrent else None
     self._steps_done = 0
     self.kernel_launches_per_step = None
@@ -133,8 +135,14 @@ class DQNLearner(core.Learner, core.Saveable):
       tgt.forward(o_t, self._bufs_tgt)                           # learning.py:124
       net.forward(o_t, self._bufs_sel)                           # learning.py:125
     self._stamp(2)
-    if self._world > 1:   # local max importance weight; the all-reduce(MAX) of this one f64 follows
-      _capi.call('b200rl_is_weight_max', self.B, _capi.ptr(ds.prob), self._beta, _capi.ptr(self._wmax), st)
+
+  def _sample(self, uniforms=None):
+    """K1, and in data-parallel mode the local max importance weight: its all-reduce(MAX) (one f64) is issued right
+    after this and hides behind the gather and the forward passes."""
+    ds = self._dataset
+    ds.sample_only(uniforms)
+    if self._world > 1:
+      _capi.call('b200rl_is_weight_max', self.B, _capi.ptr(ds.prob), self._beta, _capi.ptr(self._wmax), _capi.current_stream())
 
   def _loss_backward(self, part: str = 'all'):
     """K4 (learning.py:127-154) and the backward pass through net(o_tm1).  `part` lets the data-parallel
@@ -155,6 +163,12 @@ class DQNLearner(core.Learner, core.Saveable):
     self._stamp(3)
     if part == 'dense':
       net.backward_dense_part(self._bufs_train, self._gbufs, self.dq, self._side[0])
+    elif self._concurrent and self._split_adam and self._world == 1:
+      # fc1 + heads (99% of the parameters) are final after the dense part: their Adam update streams 200 MB and
+      # runs on a third stream underneath the latency-bound convolution backward
+      net.backward_dense_part(self._bufs_train, self._gbufs, self.dq, self._side[0])
+      self._adam_tail_async()
+      net.backward_conv_part(o_tm1, self._bufs_train, self._gbufs, self._side[0])
     elif self._concurrent:
       net.backward(o_tm1, self._bufs_train, self._gbufs, self.dq, side_stream=self._side[0])
     else:
@@ -167,12 +181,42 @@ class DQNLearner(core.Learner, core.Saveable):
     self._loss_backward()
     self._stamp(4)
 
-  def _apply(self):
+  def _adam(self, off: int, n: int):
+    """K7 over params[off : off + n] (snt.optimizers.Adam.apply, dqn/learning.py:147-149)."""
+    P, b = self._net.params, 4 * off
+    _capi.call('b200rl_adam', n, _capi.ptr(P.flat) + b, _capi.ptr(P.grad) + b, _capi.ptr(self._m) + b, _capi.ptr(self._v) + b,
+               _capi.ptr(self._num_steps), self._lr, 0.9, 0.999, self._adam_eps, self._eps_mode,
+               _capi.ptr(self._gscale) if self._world > 1 else None, None, _capi.current_stream())
+
+  def _adam_tail_async(self, after=None):
+    """Adam on the fc1 + head bucket on side stream 1; `after` = the bucket's pending all-reduce (data parallel)."""
+    torch = self._torch
+    (o1, n1), _ = self._net.grad_buckets()
+    main, side = torch.cuda.current_stream(), self._side[1]
+    ev = torch.cuda.Event()
+    ev.record(main)
+    side.wait_event(ev)
+    with torch.cuda.stream(side):
+      if after is not None:
+        after.wait()
+      self._adam(o1, n1)
+      self._tail_done = torch.cuda.Event()
+      self._tail_done.record(side)
+
+  def _apply(self, adam: str = 'auto'):
+    """Adam, priority update, periodic target copy, step counter.  adam = 'all' | 'conv+join' (the fc1 + head bucket
+    was updated by _adam_tail_async inside this capture: join it) | 'conv' (the caller has joined it)."""
     net, tgt, st = self._net, self._tgt, _capi.current_stream()
     P = net.params
-    _capi.call('b200rl_adam', P.size, _capi.ptr(P.flat), _capi.ptr(P.grad), _capi.ptr(self._m), _capi.ptr(self._v),
-               _capi.ptr(self._num_steps), self._lr, 0.9, 0.999, self._adam_eps, self._eps_mode,
-               _capi.ptr(self._gscale) if self._world > 1 else None, None, st)
+    if adam == 'auto':
+      adam = 'conv+join' if (self._concurrent and self._split_adam and self._world == 1) else 'all'
+    if adam == 'all':
+      self._adam(0, P.size)
+    else:
+      if adam == 'conv+join':
+        self._torch.cuda.current_stream().wait_event(self._tail_done)
+      _, (o0, n0) = net.grad_buckets()
+      self._adam(o0, n0)
     self._stamp(5)
     if self._replay_client is not None:                         # learning.py:151-154
       self._dataset.table.update_priorities_device(self._dataset.keys, self.priority)
@@ -185,7 +229,8 @@ class DQNLearner(core.Learner, core.Saveable):
   def _eager_step(self, uniforms):
     lib = _capi.load()
     n0 = lib.b200rl_launch_count()
-    self._dataset.sample_raw(uniforms)
+    self._sample(uniforms)
+    self._dataset.gather_only()
     self._forward_loss()
     self._dp.sum_(self._net.params.grad)   # all-reduce(SUM); Adam multiplies by 1/R (mean), then applies
     self._apply()
@@ -210,39 +255,45 @@ class DQNLearner(core.Learner, core.Saveable):
       if self._world == 1:
         def whole():
           self._stamp(0)
-          self._dataset.sample_raw()
+          self._sample()
+          self._dataset.gather_only()
           self._forward_loss()
           self._apply()
         self._graphs = [self._capture(whole)]
       else:
-        def first():
-          self._dataset.sample_raw()
+        def second():
+          self._dataset.gather_only()
           self._forwards()
-        if self._concurrent and hasattr(self._net, 'grad_buckets'):
-          self._graphs = [self._capture(first), self._capture(lambda: self._loss_backward('dense')),
-                          self._capture(lambda: self._loss_backward('conv')), self._capture(self._apply)]
+        if self._concurrent and self._split_adam:
+          self._graphs = [self._capture(self._sample), self._capture(second),
+                          self._capture(lambda: self._loss_backward('dense')),
+                          self._capture(lambda: self._loss_backward('conv')), self._capture(lambda: self._apply('conv'))]
         else:
-          self._graphs = [self._capture(first), self._capture(self._loss_backward), self._capture(self._apply)]
+          self._graphs = [self._capture(self._sample), self._capture(second), self._capture(self._loss_backward),
+                          self._capture(lambda: self._apply('all'))]
     if self._world == 1:
       self._graphs[0].replay()
-    elif len(self._graphs) == 3:
-      self._graphs[0].replay()
-      self._dp.global_max_(self._wmax)            # 1 scalar: the global importance-weight normaliser
-      self._graphs[1].replay()
-      self._dp.sum_(self._net.params.grad)        # 32 MB of gradients over NVLink; Adam applies the 1/R
+      return
+    import torch.distributed as dist
+    torch, grp = self._torch, self._dp.group
+    g = self._net.params.grad
+    self._graphs[0].replay()                      # K1 + local max importance weight
+    wmax = dist.all_reduce(self._wmax, op=dist.ReduceOp.MAX, group=grp, async_op=True)   # 1 scalar, hidden behind ...
+    self._graphs[1].replay()                      # ... K3 and the three forward passes
+    wmax.wait()
+    if len(self._graphs) == 4:
       self._graphs[2].replay()
-    else:
-      import torch.distributed as dist
-      g = self._net.params.grad
-      (o1, n1), (o0, n0) = self._net.grad_buckets()
-      self._graphs[0].replay()
-      self._dp.global_max_(self._wmax)
-      self._graphs[1].replay()                    # loss, head and fc1 backward: the tail of the gradient buffer is final
-      work = dist.all_reduce(g[o1:o1 + n1], op=dist.ReduceOp.SUM, group=self._dp.group, async_op=True)
-      self._graphs[2].replay()                    # convolution backward runs while NCCL moves fc1's 31.7 MB
-      self._dp.sum_(g[o0:o0 + n0])                # the convolutions' 0.3 MB
-      work.wait()
+      self._dp.sum_(g)                            # 32 MB of gradients over NVLink; Adam applies the 1/R
       self._graphs[3].replay()
+      return
+    (o1, n1), (o0, n0) = self._net.grad_buckets()
+    self._graphs[2].replay()                      # loss, head and fc1 backward: the tail of the gradient buffer is final
+    work = dist.all_reduce(g[o1:o1 + n1], op=dist.ReduceOp.SUM, group=grp, async_op=True)
+    self._graphs[3].replay()                      # convolution backward runs while NCCL moves fc1's 31.7 MB ...
+    self._adam_tail_async(after=work)             # ... and then Adam streams that bucket on side stream 1
+    self._dp.sum_(g[o0:o0 + n0])                  # the convolutions' 0.3 MB
+    torch.cuda.current_stream().wait_event(self._tail_done)
+    self._graphs[4].replay()                      # Adam on the conv bucket, priorities, target copy, step counter
 
   # ------------------------------------------------------------------ acme.core.Learner
   def step(self, uniforms=None, fetch_loss=True):

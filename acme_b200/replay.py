@@ -396,15 +396,22 @@ class ReplayDataset:
 
   def sample_raw(self, uniforms=None):
     """Runs K1 + K3 into the dataset's static buffers (no host sync, graph-capturable)."""
+    self.sample_only(uniforms)
+    self.gather_only()
+
+  def sample_only(self, uniforms=None):
+    """K1: uniforms -> item indices, keys and probabilities (static buffers)."""
     stream = _capi.current_stream()
     if uniforms is None:
       _capi.call('b200rl_uniform', _capi.ptr(self.u), self.B, self.seed, _capi.ptr(self.counter), 0, stream)
       _capi.call('b200rl_step_increment', _capi.ptr(self.counter), stream)
     else:
       self.u.copy_(uniforms)
-    t = self.table
-    t.sample_into(self.u, self.idx, self.keys, self.prob, self.stratified)
-    t.gather_into(self.idx, self.o_tm1, self.a_tm1, self.R, self.D, self.o_t)
+    self.table.sample_into(self.u, self.idx, self.keys, self.prob, self.stratified)
+
+  def gather_only(self):
+    """K3: the sampled items' transitions (n-step return and discount built on the fly)."""
+    self.table.gather_into(self.idx, self.o_tm1, self.a_tm1, self.R, self.D, self.o_t)
 
   def as_sample(self, table_size: Optional[int] = None) -> ReplaySample:
     import torch
