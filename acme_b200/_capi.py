@@ -23,6 +23,10 @@ class ReplayCfg(C.Structure):
               ('reserved', c_i32), ('gamma', c_f32), ('reserved_f', c_f32), ('alpha', c_f64)]
 
 
+class DpCfg(C.Structure):
+  _fields_ = [('world', c_i32), ('rank', c_i32), ('device', c_i32), ('reserved', c_i32), ('n_params', c_i64)]
+
+
 class ConvGeom(C.Structure):
   _fields_ = [(n, c_i32) for n in ('B', 'H', 'W', 'C', 'kh', 'kw', 'stride', 'pad_top',
                                    'pad_left', 'OH', 'OW', 'Cout')]
@@ -94,6 +98,15 @@ PROTOTYPES = {
     'b200rl_concat2': (c_int, [c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     'b200rl_split_second': (c_int, [c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     'b200rl_workspace_bytes': (c_i64, [c_i64]),
+    'b200rl_dp_create': (c_int, [C.POINTER(c_vp), C.POINTER(DpCfg)]),
+    'b200rl_dp_destroy': (c_int, [c_vp]),
+    'b200rl_dp_buffers': (c_int, [c_vp, C.POINTER(c_vp), C.POINTER(c_vp)]),
+    'b200rl_dp_export': (c_int, [c_vp, c_vp]),
+    'b200rl_dp_import': (c_int, [c_vp, c_i32, c_vp]),
+    'b200rl_dp_max_f64': (c_int, [c_vp, c_vp, c_vp, c_vp]),
+    'b200rl_dp_adam': (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, C.c_float, C.c_double, C.c_double, C.c_float, c_int,
+                               c_i32, c_vp]),
+    'b200rl_dp_status': (c_int, [c_vp]),
 }
 
 ACT_NONE, ACT_RELU, ACT_ELU, ACT_TANH = 0, 1, 2, 3

@@ -1,0 +1,292 @@
+// Data-parallel learner exchange over NVLink / NVSwitch peer memory (include/b200rl.h "data parallel").
+//
+// The reference's multi-replica learner does all_reduce('mean', grads) -> optimizer.apply on every replica
+// (`acme/agents/tf/crr/recurrent_learning.py:346-359`).  Here the collective and the optimizer are ONE kernel per
+// gradient bucket:
+//
+//   barrier      every rank tells every peer (a flag in the peer's memory) that its gradients of this step are final
+//   reduce       rank r owns shard r of the bucket: it reads that shard of ALL ranks' gradient buffers straight
+//                through NVLink (peer loads), adds them in rank order and scales by 1/R            [reduce-scatter]
+//   Adam         ... updates its shard of the parameters and moments (only the owner keeps moments for a shard)
+//   broadcast    ... and stores the new parameters into EVERY rank's parameter buffer (peer stores)   [all-gather]
+//   barrier      the kernel ends when every rank has finished its stores, so the next forward sees them
+//
+// so a step moves 2 x (R-1)/R x bytes per rank like a ring all-reduce, the optimizer work drops to 1/R per rank,
+// no rank ever waits for a host, and the replicas are bit-identical by construction (one writer per parameter).
+// The scalar all-reduce(MAX) of the importance-weight normaliser uses the same flag mechanism.
+//
+// Memory: one cudaMalloc region per rank [params | grads | mailbox], exported with cudaIpcGetMemHandle and opened by
+// the peers (one process per GPU).  All cross-GPU traffic uses volatile (system-coherent, L1-bypassing) accesses and
+// __threadfence_system(); flags carry the learner's step number, so the kernels are CUDA-graph capturable.
+// Spin loops give up after a few seconds and raise the region's error word instead of hanging the GPU.
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace b200rl {
+
+constexpr int kMaxRanks = 8;    // one NVSwitch box
+constexpr int kBuckets = 4;
+
+struct Mailbox {   // lives at the end of every rank's region; written by peers
+  volatile long long grads_ready[kBuckets][kMaxRanks];   // [bucket][src rank] = epoch
+  volatile long long params_done[kBuckets][kMaxRanks];
+  volatile long long max_epoch[2][kMaxRanks];            // parity double-buffered scalar exchange
+  volatile double max_value[2][kMaxRanks];
+  unsigned int cta_done[kBuckets];                       // local: CTAs that finished their shard part
+  volatile int error;                                    // 1 = a spin loop timed out
+};
+
+struct DpPeers {
+  float* params[kMaxRanks];
+  float* grads[kMaxRanks];
+  Mailbox* mail[kMaxRanks];
+};
+
+struct DpState {
+  int world, rank, device;
+  int64_t n;
+  void* region;              // local allocation
+  size_t region_bytes;
+  void* opened[kMaxRanks];   // peer regions from cudaIpcOpenMemHandle
+  DpPeers peers;
+};
+
+static size_t params_bytes(int64_t n) { return ((size_t)n * 4 + 255) & ~(size_t)255; }
+
+__device__ __forceinline__ float4 ld_sys4(const float* p) {
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_sys4(float* p, float4 v) {
+  asm volatile("st.volatile.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// waits until flag[j] >= epoch for every rank j; false on timeout
+__device__ __forceinline__ bool wait_all(const volatile long long* flag, int world, long long epoch, volatile int* error) {
+  for (int j = 0; j < world; ++j) {
+    long long spins = 0;
+    while (flag[j] < epoch) {
+      __nanosleep(64);
+      if (++spins > (1ll << 26)) { *error = 1; return false; }   // >= 4 s
+    }
+  }
+  return true;
+}
+
+struct AdamC { float bc1, bc2, b1, b2, omb1, omb2, k1, lr, eps, gs; int eps_mode; };
+__device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, const AdamC& c) {
+  const float gj = __fmul_rn(g, c.gs);
+  m = __fadd_rn(__fmul_rn(c.b1, m), __fmul_rn(c.omb1, gj));
+  v = __fadd_rn(__fmul_rn(c.b2, v), __fmul_rn(c.omb2, __fmul_rn(gj, gj)));
+  float upd;
+  if (c.eps_mode == 0) upd = __fdiv_rn(__fdiv_rn(m, c.bc1), __fadd_rn(__fsqrt_rn(__fdiv_rn(v, c.bc2)), c.eps));
+  else upd = __fdiv_rn(__fmul_rn(c.k1, m), __fadd_rn(__fsqrt_rn(v), c.eps));
+  p = __fsub_rn(p, __fmul_rn(c.lr, upd));
+}
+
+// One launch per gradient bucket [off, off + n).  The shard of rank r is [off + r * chunk, off + (r + 1) * chunk)
+// with chunk a multiple of 4 floats.  (Same arithmetic as adam_kernel in learner_math.cu with gscale = 1/R.)
+__global__ void __launch_bounds__(256)
+dp_adam_kernel(DpPeers peers, int world, int rank, long long off, long long n, long long chunk, float* __restrict__ m,
+               float* __restrict__ v, const long long* __restrict__ step_dev, float lr, double b1, double b2, float eps,
+               int eps_mode, int bucket) {
+  Mailbox* mine = peers.mail[rank];
+  const long long epoch = *step_dev + 1;
+  __shared__ AdamC c;
+  __shared__ bool ok;
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0) {
+      // this rank's gradients are final (previous kernels of the stream): tell every rank, including ourselves
+      __threadfence_system();
+      for (int j = 0; j < world; ++j) peers.mail[j]->grads_ready[bucket][rank] = epoch;
+    }
+    const double t = (double)epoch;
+    c.bc1 = (float)(1.0 - pow(b1, t)); c.bc2 = (float)(1.0 - pow(b2, t));
+    c.b1 = (float)b1; c.b2 = (float)b2; c.omb1 = (float)(1.0 - b1); c.omb2 = (float)(1.0 - b2);
+    c.k1 = sqrtf(c.bc2) / c.bc1; c.lr = lr; c.eps = eps; c.gs = 1.f / (float)world; c.eps_mode = eps_mode;
+    ok = wait_all(mine->grads_ready[bucket], world, epoch, &mine->error);
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (ok) {
+    const long long s0 = off + (long long)rank * chunk;
+    const long long s1 = min(off + n, s0 + chunk);
+    const long long stride = (long long)gridDim.x * blockDim.x * 4;
+    for (long long i = s0 + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < s1; i += stride) {
+      if (i + 4 <= s1) {
+        float4 t[kMaxRanks];   // all peer loads are issued before the first is consumed (NVLink latency ~2 us)
+#pragma unroll
+        for (int j = 0; j < kMaxRanks; ++j)
+          if (j < world) t[j] = ld_sys4(peers.grads[j] + i);
+        float4 g = t[0];
+#pragma unroll
+        for (int j = 1; j < kMaxRanks; ++j)   // fixed rank order: deterministic
+          if (j < world) {
+            g.x = __fadd_rn(g.x, t[j].x); g.y = __fadd_rn(g.y, t[j].y); g.z = __fadd_rn(g.z, t[j].z); g.w = __fadd_rn(g.w, t[j].w);
+          }
+        float4 p = *reinterpret_cast<const float4*>(peers.params[rank] + i);
+        float4 mm = *reinterpret_cast<const float4*>(m + i), vv = *reinterpret_cast<const float4*>(v + i);
+        adam1(p.x, g.x, mm.x, vv.x, c); adam1(p.y, g.y, mm.y, vv.y, c);
+        adam1(p.z, g.z, mm.z, vv.z, c); adam1(p.w, g.w, mm.w, vv.w, c);
+        *reinterpret_cast<float4*>(m + i) = mm;
+        *reinterpret_cast<float4*>(v + i) = vv;
+        for (int j = 0; j < world; ++j) st_sys4(peers.params[j] + i, p);
+      } else {
+        for (long long k = i; k < s1; ++k) {   // ragged end of the bucket
+          float g = *(volatile float*)(peers.grads[0] + k);
+          for (int j = 1; j < world; ++j) g = __fadd_rn(g, *(volatile float*)(peers.grads[j] + k));
+          float p = peers.params[rank][k], mm = m[k], vv = v[k];
+          adam1(p, g, mm, vv, c);
+          m[k] = mm; v[k] = vv;
+          for (int j = 0; j < world; ++j) *(volatile float*)(peers.params[j] + k) = p;
+        }
+      }
+    }
+  }
+  // the last CTA of this rank to finish announces it to every rank, then waits for everybody's announcement
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(&mine->cta_done[bucket], 1u);
+    if (done == gridDim.x - 1) {
+      mine->cta_done[bucket] = 0;
+      __threadfence_system();
+      for (int j = 0; j < world; ++j) peers.mail[j]->params_done[bucket][rank] = epoch;
+      wait_all(mine->params_done[bucket], world, epoch, &mine->error);
+      __threadfence_system();
+    }
+  }
+}
+
+// all-reduce(MAX) of one double per rank: each rank drops (value, epoch) into every peer's mailbox
+__global__ void dp_max_kernel(DpPeers peers, int world, int rank, double* __restrict__ value, const long long* __restrict__ step_dev) {
+  if (threadIdx.x != 0) return;
+  Mailbox* mine = peers.mail[rank];
+  const long long epoch = *step_dev + 1;
+  const int par = (int)(epoch & 1);
+  const double x = *value;
+  for (int j = 0; j < world; ++j) peers.mail[j]->max_value[par][rank] = x;
+  __threadfence_system();
+  for (int j = 0; j < world; ++j) peers.mail[j]->max_epoch[par][rank] = epoch;
+  if (!wait_all(mine->max_epoch[par], world, epoch, &mine->error)) return;
+  __threadfence_system();
+  double best = mine->max_value[par][0];
+  for (int j = 1; j < world; ++j) best = fmax(best, mine->max_value[par][j]);
+  *value = best;
+}
+
+}  // namespace b200rl
+
+using namespace b200rl;
+
+extern "C" int b200rl_dp_create(b200rl_dp_t* out, const b200rl_dp_cfg* cfg) {
+  B200RL_REQUIRE(out && cfg, "null argument");
+  B200RL_REQUIRE(cfg->world >= 1 && cfg->world <= kMaxRanks && cfg->rank >= 0 && cfg->rank < cfg->world, "bad world/rank");
+  B200RL_REQUIRE(cfg->n_params >= 1, "bad parameter count");
+  B200RL_CUDA_OK(cudaSetDevice(cfg->device));
+  DpState* s = new DpState();
+  memset(s, 0, sizeof(*s));
+  s->world = cfg->world; s->rank = cfg->rank; s->device = cfg->device; s->n = cfg->n_params;
+  const size_t pb = params_bytes(s->n);
+  s->region_bytes = 2 * pb + ((sizeof(Mailbox) + 255) & ~(size_t)255);
+  cudaError_t e = cudaMalloc(&s->region, s->region_bytes);
+  if (e != cudaSuccess) { delete s; set_error("cudaMalloc(%zu): %s", s->region_bytes, cudaGetErrorString(e)); return B200RL_ECUDA; }
+  B200RL_CUDA_OK(cudaMemset(s->region, 0, s->region_bytes));
+  B200RL_CUDA_OK(cudaDeviceSynchronize());
+  s->peers.params[s->rank] = (float*)s->region;
+  s->peers.grads[s->rank] = (float*)((char*)s->region + pb);
+  s->peers.mail[s->rank] = (Mailbox*)((char*)s->region + 2 * pb);
+  *out = (b200rl_dp_t)s;
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_dp_destroy(b200rl_dp_t h) {
+  DpState* s = (DpState*)h;
+  if (!s) return B200RL_OK;
+  cudaDeviceSynchronize();
+  for (int j = 0; j < s->world; ++j)
+    if (s->opened[j]) cudaIpcCloseMemHandle(s->opened[j]);
+  if (s->region) cudaFree(s->region);
+  delete s;
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_dp_buffers(b200rl_dp_t h, float** params, float** grads) {
+  DpState* s = (DpState*)h;
+  B200RL_REQUIRE(s && params && grads, "null argument");
+  *params = s->peers.params[s->rank];
+  *grads = s->peers.grads[s->rank];
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_dp_export(b200rl_dp_t h, void* handle64) {
+  DpState* s = (DpState*)h;
+  B200RL_REQUIRE(s && handle64, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  cudaIpcMemHandle_t hd;
+  B200RL_CUDA_OK(cudaIpcGetMemHandle(&hd, s->region));
+  memcpy(handle64, &hd, 64);
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_dp_import(b200rl_dp_t h, int32_t peer_rank, const void* handle64) {
+  DpState* s = (DpState*)h;
+  B200RL_REQUIRE(s && handle64, "null argument");
+  B200RL_REQUIRE(peer_rank >= 0 && peer_rank < s->world && peer_rank != s->rank, "bad peer rank");
+  B200RL_REQUIRE(!s->opened[peer_rank], "peer already imported");
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, handle64, 64);
+  void* base = nullptr;
+  B200RL_CUDA_OK(cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess));
+  const size_t pb = params_bytes(s->n);
+  s->opened[peer_rank] = base;
+  s->peers.params[peer_rank] = (float*)base;
+  s->peers.grads[peer_rank] = (float*)((char*)base + pb);
+  s->peers.mail[peer_rank] = (Mailbox*)((char*)base + 2 * pb);
+  return B200RL_OK;
+}
+
+static int dp_ready(DpState* s) {
+  for (int j = 0; j < s->world; ++j)
+    if (!s->peers.mail[j]) { set_error("data-parallel region of rank %d has not been imported", j); return B200RL_EINVAL; }
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_dp_max_f64(b200rl_dp_t h, double* value_dev, const int64_t* step_dev, void* stream) {
+  DpState* s = (DpState*)h;
+  B200RL_REQUIRE(s && value_dev && step_dev, "null argument");
+  if (int rc = dp_ready(s)) return rc;
+  dp_max_kernel<<<1, 32, 0, as_stream(stream)>>>(s->peers, s->world, s->rank, value_dev, (const long long*)step_dev);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_dp_adam(b200rl_dp_t h, int64_t off, int64_t n, float* m, float* v, const int64_t* step_dev, float lr,
+                              double b1, double b2, float eps, int eps_mode, int32_t bucket, void* stream) {
+  DpState* s = (DpState*)h;
+  B200RL_REQUIRE(s && m && v && step_dev, "null argument");
+  B200RL_REQUIRE(off >= 0 && n >= 1 && off + n <= s->n && off % 4 == 0, "bad bucket range");
+  B200RL_REQUIRE(bucket >= 0 && bucket < kBuckets && (eps_mode == 0 || eps_mode == 1), "bad argument");
+  B200RL_REQUIRE((((uintptr_t)m | (uintptr_t)v) & 15) == 0, "moment buffers must be 16-byte aligned");
+  if (int rc = dp_ready(s)) return rc;
+  long long chunk = (n + s->world - 1) / s->world;
+  chunk = (chunk + 3) & ~3ll;
+  const long long vec = (chunk + 3) / 4;
+  int blocks = (int)std::max<long long>(1, std::min<long long>((vec + 255) / 256, 2 * kNumSMs));
+  dp_adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(s->peers, s->world, s->rank, off, n, chunk, m, v,
+                                                       (const long long*)step_dev, lr, b1, b2, eps, eps_mode, bucket);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_dp_status(b200rl_dp_t h) {
+  DpState* s = (DpState*)h;
+  B200RL_REQUIRE(s, "null argument");
+  int err = 0;
+  const Mailbox* mb = s->peers.mail[s->rank];
+  B200RL_CUDA_OK(cudaMemcpy(&err, (const void*)&mb->error, sizeof(int), cudaMemcpyDeviceToHost));
+  if (err) { set_error("data-parallel exchange timed out waiting for a peer"); return B200RL_ECUDA; }
+  return B200RL_OK;
+}

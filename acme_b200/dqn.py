@@ -28,7 +28,8 @@ class DQNLearner(core.Learner, core.Saveable):
                huber_loss_parameter: float = 1., replay_client: Optional[replay.Client] = None,
                counter: counting.Counter = None, logger: loggers.Logger = None, checkpoint: bool = True,
                max_abs_reward: float = 1., eps_mode: int = 0, use_cuda_graph: bool = True,
-               process_group=None, adam_eps: float = 1e-8, concurrent_streams: bool = True):
+               process_group=None, adam_eps: float = 1e-8, concurrent_streams: bool = True,
+               peer_exchange: Optional[bool] = None):
     import torch
     if huber_loss_parameter < 0:
       raise ValueError('quadratic_linear_boundary must be >= 0.')   # huber.py:45-46
@@ -79,6 +80,16 @@ class DQNLearner(core.Learner, core.Saveable):
     self._split_adam = self._concurrent and hasattr(network, 'grad_buckets')
     self._tail_done = None
     self._side = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)] if self._concurrent else None
+    # data parallel: gradients and parameters live in a peer-mapped region and the exchange is fused with Adam
+    # (parallel.PeerExchange); peer_exchange=False keeps the NCCL all-reduce + replicated Adam path
+    if peer_exchange is None:
+      peer_exchange = self._world > 1 and self._split_adam and os.environ.get('B200RL_PEER_EXCHANGE', '1') != '0'
+    self._px = None
+    if peer_exchange and self._world > 1:
+      if not self._split_adam:
+        raise ValueError('peer_exchange needs a network with grad_buckets() and concurrent_streams=True')
+      self._px = parallel.PeerExchange(self._dp, network.params.size, network.device)
+      network.params.rebind(self._px.params, self._px.grads)
     self._steps_done = 0
     self.kernel_launches_per_step = None
 
@@ -143,6 +154,8 @@ class DQNLearner(core.Learner, core.Saveable):
     ds.sample_only(uniforms)
     if self._world > 1:
       _capi.call('b200rl_is_weight_max', self.B, _capi.ptr(ds.prob), self._beta, _capi.ptr(self._wmax), _capi.current_stream())
+      if self._px is not None:      # all-reduce(MAX) through the peers' mailboxes, inside the captured step
+        self._px.max_f64_(self._wmax, self._num_steps)
 
   def _loss_backward(self, part: str = 'all'):
     """K4 (learning.py:127-154) and the backward pass through net(o_tm1).  `part` lets the data-parallel
@@ -163,7 +176,7 @@ class DQNLearner(core.Learner, core.Saveable):
     self._stamp(3)
     if part == 'dense':
       net.backward_dense_part(self._bufs_train, self._gbufs, self.dq, self._side[0])
-    elif self._concurrent and self._split_adam and self._world == 1:
+    elif self._concurrent and self._split_adam and (self._world == 1 or self._px is not None):
       # fc1 + heads (99% of the parameters) are final after the dense part: their Adam update streams 200 MB and
       # runs on a third stream underneath the latency-bound convolution backward
       net.backward_dense_part(self._bufs_train, self._gbufs, self.dq, self._side[0])
@@ -176,13 +189,17 @@ class DQNLearner(core.Learner, core.Saveable):
 
   def _forward_loss(self):
     self._forwards()
-    if self._world > 1:
+    if self._world > 1 and self._px is None:
       self._dp.global_max_(self._wmax)
     self._loss_backward()
     self._stamp(4)
 
-  def _adam(self, off: int, n: int):
-    """K7 over params[off : off + n] (snt.optimizers.Adam.apply, dqn/learning.py:147-149)."""
+  def _adam(self, off: int, n: int, bucket: int = 0):
+    """K7 over params[off : off + n] (snt.optimizers.Adam.apply, dqn/learning.py:147-149); with a peer exchange the
+    gradient mean over the ranks, Adam on the owned shard and the parameter broadcast are one kernel."""
+    if self._px is not None:
+      self._px.adam(off, n, self._m, self._v, self._num_steps, self._lr, 0.9, 0.999, self._adam_eps, self._eps_mode, bucket)
+      return
     P, b = self._net.params, 4 * off
     _capi.call('b200rl_adam', n, _capi.ptr(P.flat) + b, _capi.ptr(P.grad) + b, _capi.ptr(self._m) + b, _capi.ptr(self._v) + b,
                _capi.ptr(self._num_steps), self._lr, 0.9, 0.999, self._adam_eps, self._eps_mode,
@@ -199,7 +216,7 @@ class DQNLearner(core.Learner, core.Saveable):
     with torch.cuda.stream(side):
       if after is not None:
         after.wait()
-      self._adam(o1, n1)
+      self._adam(o1, n1, bucket=0)
       self._tail_done = torch.cuda.Event()
       self._tail_done.record(side)
 
@@ -209,14 +226,15 @@ class DQNLearner(core.Learner, core.Saveable):
     net, tgt, st = self._net, self._tgt, _capi.current_stream()
     P = net.params
     if adam == 'auto':
-      adam = 'conv+join' if (self._concurrent and self._split_adam and self._world == 1) else 'all'
+      split = self._concurrent and self._split_adam and (self._world == 1 or self._px is not None)
+      adam = 'conv+join' if split else 'all'
     if adam == 'all':
       self._adam(0, P.size)
     else:
       if adam == 'conv+join':
         self._torch.cuda.current_stream().wait_event(self._tail_done)
       _, (o0, n0) = net.grad_buckets()
-      self._adam(o0, n0)
+      self._adam(o0, n0, bucket=1)
     self._stamp(5)
     if self._replay_client is not None:                         # learning.py:151-154
       self._dataset.table.update_priorities_device(self._dataset.keys, self.priority)
@@ -232,7 +250,8 @@ class DQNLearner(core.Learner, core.Saveable):
     self._sample(uniforms)
     self._dataset.gather_only()
     self._forward_loss()
-    self._dp.sum_(self._net.params.grad)   # all-reduce(SUM); Adam multiplies by 1/R (mean), then applies
+    if self._px is None:
+      self._dp.sum_(self._net.params.grad)   # all-reduce(SUM); Adam multiplies by 1/R (mean), then applies
     self._apply()
     self.kernel_launches_per_step = int(lib.b200rl_launch_count() - n0)
 
@@ -252,7 +271,7 @@ class DQNLearner(core.Learner, core.Saveable):
       self._eager_step(uniforms)      # also the un-captured warm-up (one-time attribute setup inside the library)
       return
     if self._graphs is None:
-      if self._world == 1:
+      if self._world == 1 or self._px is not None:
         def whole():
           self._stamp(0)
           self._sample()
@@ -260,6 +279,9 @@ class DQNLearner(core.Learner, core.Saveable):
           self._forward_loss()
           self._apply()
         self._graphs = [self._capture(whole)]
+        if self._px is not None:
+          import torch.distributed as dist
+          dist.barrier(group=self._dp.group)    # every rank has its graph before anyone spins on a peer
       else:
         def second():
           self._dataset.gather_only()
@@ -271,7 +293,7 @@ class DQNLearner(core.Learner, core.Saveable):
         else:
           self._graphs = [self._capture(self._sample), self._capture(second), self._capture(self._loss_backward),
                           self._capture(lambda: self._apply('all'))]
-    if self._world == 1:
+    if self._world == 1 or self._px is not None:
       self._graphs[0].replay()
       return
     import torch.distributed as dist

@@ -61,6 +61,14 @@ class ParamStore:
     self.flat = torch.zeros(self.size, dtype=torch.float32, device=dev)
     self.grad = torch.zeros(self.size, dtype=torch.float32, device=dev)
 
+  def rebind(self, flat, grad):
+    """Moves the parameters / gradients into caller-provided storage (the peer-mapped region of
+    `parallel.PeerExchange`); call before any CUDA graph that uses them is captured."""
+    assert flat.numel() == self.size and grad.numel() == self.size
+    flat.copy_(self.flat)
+    grad.copy_(self.grad)
+    self.flat, self.grad = flat, grad
+
   def view(self, name: str, grad: bool = False):
     off, shape = self.entries[name]
     n = int(np.prod(shape))

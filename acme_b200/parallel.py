@@ -68,3 +68,67 @@ class DataParallel:
     dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=self.group)
     if not torch.equal(hi, lo):
       raise RuntimeError(f'{what} differ across data-parallel ranks: checksum range [{lo.item()}, {hi.item()}]')
+
+
+class _RawDeviceArray:
+  """A device pointer dressed up for torch.as_tensor (zero copy)."""
+
+  def __init__(self, ptr: int, n: int):
+    self.__cuda_array_interface__ = {'shape': (n,), 'typestr': '<f4', 'data': (ptr, False), 'version': 2}
+
+
+class PeerExchange:
+  """The learner's exchange over NVLink peer memory (`include/b200rl.h` "data-parallel learner"): one fused
+  reduce-scatter + Adam + all-gather kernel per gradient bucket, and the scalar all-reduce(MAX).
+
+  The flat parameter and gradient buffers live in a region that every peer maps through CUDA IPC; `torch.distributed`
+  is used once, to exchange the 64-byte handles.  Requires one process per GPU on one node with P2P access.
+  """
+
+  def __init__(self, dp: DataParallel, n_params: int, device: int):
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    from acme_b200 import _capi
+    assert dp.enabled
+    self.dp, self.n = dp, int(n_params)
+    self._h = ctypes.c_void_p()
+    _capi.call('b200rl_dp_create', ctypes.byref(self._h),
+               ctypes.byref(_capi.DpCfg(world=dp.world, rank=dp.rank, device=device, reserved=0, n_params=self.n)))
+    p, g = ctypes.c_void_p(), ctypes.c_void_p()
+    _capi.call('b200rl_dp_buffers', self._h, ctypes.byref(p), ctypes.byref(g))
+    dev = torch.device('cuda', device)
+    self.params = torch.as_tensor(_RawDeviceArray(p.value, self.n), device=dev)
+    self.grads = torch.as_tensor(_RawDeviceArray(g.value, self.n), device=dev)
+    mine = ctypes.create_string_buffer(64)
+    _capi.call('b200rl_dp_export', self._h, mine)
+    handles = [None] * dp.world
+    dist.all_gather_object(handles, bytes(mine.raw), group=dp.group)
+    for r, hb in enumerate(handles):
+      if r != dp.rank:
+        _capi.call('b200rl_dp_import', self._h, r, ctypes.create_string_buffer(hb, 64))
+    dist.barrier(group=dp.group)
+
+  def max_f64_(self, value, step):
+    from acme_b200 import _capi
+    _capi.call('b200rl_dp_max_f64', self._h, _capi.ptr(value), _capi.ptr(step), _capi.current_stream())
+
+  def adam(self, off: int, n: int, m, v, step, lr: float, b1: float, b2: float, eps: float, eps_mode: int, bucket: int):
+    from acme_b200 import _capi
+    _capi.call('b200rl_dp_adam', self._h, off, n, _capi.ptr(m), _capi.ptr(v), _capi.ptr(step), lr, b1, b2, eps, eps_mode,
+               bucket, _capi.current_stream())
+
+  def check(self):
+    from acme_b200 import _capi
+    _capi.call('b200rl_dp_status', self._h)
+
+  def close(self):
+    import torch
+    import torch.distributed as dist
+    from acme_b200 import _capi
+    if self._h:
+      torch.cuda.synchronize()
+      dist.barrier(group=self.dp.group)     # nobody unmaps while a peer may still touch the region
+      self.params = self.grads = None
+      _capi.call('b200rl_dp_destroy', self._h)
+      self._h = None

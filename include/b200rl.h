@@ -247,6 +247,36 @@ int b200rl_tanh_to_spec_bwd(int32_t B, int32_t A, const float* da, const float* 
 /* batch_concat([obs, act]) (tf/utils.py:39-54) and its split for the backward */
 int b200rl_concat2(int32_t B, int32_t n0, int32_t n1, const float* x0, const float* x1, float* y, void* stream);
 int b200rl_split_second(int32_t B, int32_t n0, int32_t n1, const float* dy, float* dx1, void* stream);
+/* ------------------------------------------------------------------ data-parallel learner
+ * Replaces all_reduce('mean', grads) followed by optimizer.apply on every replica
+ * (acme/agents/tf/crr/recurrent_learning.py:346-359, the reference's only multi-replica learner) by ONE kernel
+ * per gradient bucket over NVLink peer memory: reduce-scatter by peer loads, Adam on the owned 1/R shard,
+ * all-gather of the new parameters by peer stores (see acme_b200/csrc/dp_p2p.cu).  One process per GPU.
+ *   create   allocates this rank's region [params | grads | mailbox]; the learner keeps its flat parameter and
+ *            gradient buffers THERE (b200rl_dp_buffers)
+ *   export / import   64-byte IPC handle of the region; every rank imports every peer's (exchange them with any
+ *            host-side all-gather) before the first exchange call
+ *   max_f64  in-place all-reduce(MAX) of one device double (the importance-weight normaliser, dqn/learning.py:140)
+ *   adam     parameters[off, off+n) of all ranks <- Adam(mean over ranks of grads[off, off+n)); m, v: this rank's
+ *            full-size moment buffers (only the owned shard is touched); `bucket` (0..3) names the mailbox slot, two
+ *            buckets may be in flight at once; step_dev as in b200rl_adam.  All ranks must issue the same calls in
+ *            the same order each step; both calls are CUDA-graph capturable.
+ *   status   < 0 if an exchange gave up waiting for a peer (~2 s) */
+typedef struct b200rl_dp* b200rl_dp_t;
+typedef struct b200rl_dp_cfg {
+  int32_t world, rank, device, reserved;
+  int64_t n_params;
+} b200rl_dp_cfg;
+int b200rl_dp_create(b200rl_dp_t* out, const b200rl_dp_cfg* cfg);
+int b200rl_dp_destroy(b200rl_dp_t h);
+int b200rl_dp_buffers(b200rl_dp_t h, float** params, float** grads);
+int b200rl_dp_export(b200rl_dp_t h, void* handle64);
+int b200rl_dp_import(b200rl_dp_t h, int32_t peer_rank, const void* handle64);
+int b200rl_dp_max_f64(b200rl_dp_t h, double* value_dev, const int64_t* step_dev, void* stream);
+int b200rl_dp_adam(b200rl_dp_t h, int64_t off, int64_t n, float* m, float* v, const int64_t* step_dev, float lr,
+                   double b1, double b2, float eps, int eps_mode, int32_t bucket, void* stream);
+int b200rl_dp_status(b200rl_dp_t h);
+
 /* bytes of split-K workspace that lets every layer call on outputs of up to max_out_elems
  * elements use its preferred split count (smaller workspaces only reduce the split count) */
 int64_t b200rl_workspace_bytes(int64_t max_out_elems);

@@ -73,3 +73,25 @@ def sync_oracle_leaves_loose(table, oracle, rtol=5e-3):
   np.testing.assert_allclose(got, oracle.tree.levels[L], rtol=rtol, atol=1e-4)
   oracle.tree.levels[L][:] = got
   oracle.tree.rebuild()
+
+
+def make_dqn_dp_learner(rank, world, group, peer_exchange, items=4096, precision=0):
+  """Atari-shaped DQN learner on replay shard `rank` of a data-parallel job (same parameters on every rank)."""
+  import sys, os
+  sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+  import bench
+  from acme_b200 import adders, dqn, loggers, networks, replay, specs
+  spec = specs.EnvironmentSpec(specs.Array(bench.OBS_SHAPE, np.uint8), specs.DiscreteArray(bench.NUM_ACTIONS),
+                               specs.Array((), np.float32), specs.BoundedArray((), np.float32, 0., 1.))
+  table = replay.Table(replay.DEFAULT_PRIORITY_TABLE, replay.selectors.Prioritized(0.6), replay.selectors.Fifo(),
+                       max_size=items, rate_limiter=replay.rate_limiters.MinSize(1),
+                       signature=adders.NStepTransitionAdder.signature(spec), max_window=3, discount=0.99, device=rank,
+                       slot_capacity=items + 4096, shard_count=world, shard_rank=rank, stage_slots=4096)
+  server = replay.Server([table])
+  bench.fill_replay(table, items, 3, seed=77 + rank)
+  net = networks.DQNAtariNetwork(bench.NUM_ACTIONS, device=rank, precision=precision, seed=5)
+  ds = replay.ReplayDataset(table, 64, seed=11 + rank)
+  learner = dqn.DQNLearner(net, net.clone(), 0.99, 0.2, 1e-3, 100, ds, replay_client=replay.Client(server),
+                           logger=loggers.NoOpLogger(), process_group=group, peer_exchange=peer_exchange)
+  learner._keepalive = (server, table)
+  return learner

@@ -1,0 +1,106 @@
+"""Data-parallel learner over NVLink peer memory (`acme_b200/csrc/dp_p2p.cu`): two ranks, two GPUs.
+
+Skipped on boxes with fewer than two GPUs (run with `gpurun --gpus 2`).  Checks the fused reduce-scatter + Adam +
+all-gather against NCCL all-reduce + the replicated Adam kernel on identical gradients, the scalar all-reduce(MAX),
+and a few whole learner steps (replicas must stay bit-identical; losses must match the NCCL path).
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+  os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+  sys.path.insert(0, ROOT)
+  sys.path.insert(0, os.path.join(ROOT, 'tests'))
+  import torch
+  import torch.distributed as dist
+  torch.cuda.set_device(rank)
+  dist.init_process_group('nccl', device_id=torch.device('cuda', rank))
+  try:
+    from acme_b200 import _capi, parallel
+    dp = parallel.DataParallel(dist.group.WORLD)
+    n = 100_003 * 4
+    px = parallel.PeerExchange(dp, n, rank)
+    gen = torch.Generator(device='cuda').manual_seed(7)            # same parameters everywhere
+    p0 = torch.randn(n, device='cuda', generator=gen)
+    gen_r = torch.Generator(device='cuda').manual_seed(100 + rank)  # rank-specific gradients
+    step = torch.zeros(1, dtype=torch.int64, device='cuda')
+    px.params.copy_(p0)
+    m, v = torch.zeros(n, device='cuda'), torch.zeros(n, device='cuda')
+    p_ref, m_ref, v_ref = p0.clone(), torch.zeros(n, device='cuda'), torch.zeros(n, device='cuda')
+    gscale = torch.full((1,), 1.0 / world, device='cuda')
+    for it in range(3):
+      g = torch.randn(n, device='cuda', generator=gen_r)
+      px.grads.copy_(g)
+      # reference: NCCL all-reduce(SUM) then the replicated Adam kernel with 1/R
+      g_sum = g.clone()
+      dist.all_reduce(g_sum)
+      _capi.call('b200rl_adam', n, _capi.ptr(p_ref), _capi.ptr(g_sum), _capi.ptr(m_ref), _capi.ptr(v_ref), _capi.ptr(step),
+                 1e-3, 0.9, 0.999, 1e-8, 0, _capi.ptr(gscale), None, _capi.current_stream())
+      # two buckets, odd split, like the learner
+      cut = 40_000
+      px.adam(cut, n - cut, m, v, step, 1e-3, 0.9, 0.999, 1e-8, 0, 0)
+      px.adam(0, cut, m, v, step, 1e-3, 0.9, 0.999, 1e-8, 0, 1)
+      w = torch.tensor([float(rank * 10 + it)], dtype=torch.float64, device='cuda')
+      px.max_f64_(w, step)
+      torch.cuda.synchronize()
+      px.check()
+      assert float(w) == (world - 1) * 10 + it
+      # NCCL's summation order may differ from rank order by an ulp of the gradient sum
+      err = (px.params - p_ref).abs().max().item()
+      assert err <= 2e-6, (it, err)
+      dp.assert_replicated(px.params)
+      chunk = -(-((n - cut + world - 1) // world) // 4) * 4
+      lo = cut + rank * chunk
+      hi = min(n, lo + chunk)
+      assert torch.allclose(m[lo:hi], m_ref[lo:hi], rtol=1e-5, atol=1e-7)   # owner keeps the moments of its shard
+      step += 1
+    px.close()
+
+    # ---- whole learner: peer exchange vs NCCL path, same seeds
+    import helpers
+    losses = {}
+    for mode in (True, False):
+      pair = helpers.make_dqn_dp_learner(rank, world, dist.group.WORLD, peer_exchange=mode)
+      ls = []
+      for _ in range(6):
+        pair.step(fetch_loss=False)
+        ls.append(float(pair.loss))
+      dp.assert_replicated(pair._net.params.flat)
+      if pair._px is not None:
+        pair._px.check()
+      losses[mode] = ls
+      if pair._px is not None:
+        pair._px.close()
+    np.testing.assert_allclose(losses[True], losses[False], rtol=2e-3)
+    q.put((rank, 'ok'))
+  except Exception as e:   # pragma: no cover
+    import traceback
+    q.put((rank, traceback.format_exc()))
+  finally:
+    dist.destroy_process_group()
+
+
+def test_peer_exchange_two_gpus():
+  import torch
+  if torch.cuda.device_count() < 2:
+    pytest.skip('needs two GPUs')
+  import torch.multiprocessing as mp
+  ctx = mp.get_context('spawn')
+  q = ctx.Queue()
+  port = 29600 + os.getpid() % 200
+  procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+  for p in procs:
+    p.start()
+  results = [q.get(timeout=300) for _ in procs]
+  for p in procs:
+    p.join(timeout=60)
+  for rank, msg in results:
+    assert msg == 'ok', f'rank {rank}: {msg}'
