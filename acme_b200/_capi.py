@@ -105,7 +105,7 @@ PROTOTYPES = {
     'b200rl_dp_import': (c_int, [c_vp, c_i32, c_vp]),
     'b200rl_dp_max_f64': (c_int, [c_vp, c_vp, c_vp, c_vp]),
     'b200rl_dp_adam': (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, C.c_float, C.c_double, C.c_double, C.c_float, c_int,
-                               c_i32, c_vp]),
+                               c_i32, c_i32, c_vp]),
     'b200rl_dp_status': (c_int, [c_vp]),
 }
 

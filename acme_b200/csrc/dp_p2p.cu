@@ -16,9 +16,10 @@
 // The scalar all-reduce(MAX) of the importance-weight normaliser uses the same flag mechanism.
 //
 // Memory: one cudaMalloc region per rank [params | grads | mailbox], exported with cudaIpcGetMemHandle and opened by
-// the peers (one process per GPU).  All cross-GPU traffic uses volatile (system-coherent, L1-bypassing) accesses and
-// __threadfence_system(); flags carry the learner's step number, so the kernels are CUDA-graph capturable.
+// the peers (one process per GPU).  Flags are volatile (system-coherent) words, bulk data uses L1-bypassing accesses
+// ordered by __threadfence_system(); flags carry the learner's step number, so the kernels are CUDA-graph capturable.
 // Spin loops give up after a few seconds and raise the region's error word instead of hanging the GPU.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -36,6 +37,7 @@ struct Mailbox {   // lives at the end of every rank's region; written by peers
   volatile double max_value[2][kMaxRanks];
   unsigned int cta_done[kBuckets];                       // local: CTAs that finished their shard part
   volatile int error;                                    // 1 = a spin loop timed out
+  long long dbg[8];                                      // tools/dp_bench.py: global-timer stamps of the last exchange
 };
 
 struct DpPeers {
@@ -55,13 +57,21 @@ struct DpState {
 
 static size_t params_bytes(int64_t n) { return ((size_t)n * 4 + 255) & ~(size_t)255; }
 
+// Bulk data moves with L1-bypassing (.cg) accesses: peer memory is only ever cached at its owner's L2, so these are
+// coherent once the flag protocol (volatile flags + __threadfence_system on both sides) has ordered them, and -- unlike
+// volatile accesses, which a thread issues one at a time -- they pipeline.
+__device__ __forceinline__ long long gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ float4 ld_sys4(const float* p) {
   float4 v;
-  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_sys4(float* p, float4 v) {
-  asm volatile("st.volatile.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  asm volatile("st.global.cg.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 // waits until flag[j] >= epoch for every rank j; false on timeout
 __device__ __forceinline__ bool wait_all(const volatile long long* flag, int world, long long epoch, volatile int* error) {
@@ -88,16 +98,21 @@ __device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, con
 
 // One launch per gradient bucket [off, off + n).  The shard of rank r is [off + r * chunk, off + (r + 1) * chunk)
 // with chunk a multiple of 4 floats.  (Same arithmetic as adam_kernel in learner_math.cu with gscale = 1/R.)
+// W = compile-time bound on the world size, U = float4 groups per thread per iteration: all W * U peer loads of an
+// iteration are issued before the first is consumed (NVLink round trips are microseconds; bytes in flight are
+// what buys bandwidth).
+template <int W, int U>
 __global__ void __launch_bounds__(256)
 dp_adam_kernel(DpPeers peers, int world, int rank, long long off, long long n, long long chunk, float* __restrict__ m,
                float* __restrict__ v, const long long* __restrict__ step_dev, float lr, double b1, double b2, float eps,
-               int eps_mode, int bucket) {
+               int eps_mode, int bucket, int final_barrier) {
   Mailbox* mine = peers.mail[rank];
   const long long epoch = *step_dev + 1;
   __shared__ AdamC c;
   __shared__ bool ok;
   if (threadIdx.x == 0) {
     if (blockIdx.x == 0) {
+      mine->dbg[0] = gtime();
       // this rank's gradients are final (previous kernels of the stream): tell every rank, including ourselves
       __threadfence_system();
       for (int j = 0; j < world; ++j) peers.mail[j]->grads_ready[bucket][rank] = epoch;
@@ -108,54 +123,83 @@ dp_adam_kernel(DpPeers peers, int world, int rank, long long off, long long n, l
     c.k1 = sqrtf(c.bc2) / c.bc1; c.lr = lr; c.eps = eps; c.gs = 1.f / (float)world; c.eps_mode = eps_mode;
     ok = wait_all(mine->grads_ready[bucket], world, epoch, &mine->error);
     __threadfence_system();
+    if (blockIdx.x == 0) mine->dbg[1] = gtime();
   }
   __syncthreads();
   if (ok) {
     const long long s0 = off + (long long)rank * chunk;
     const long long s1 = min(off + n, s0 + chunk);
-    const long long stride = (long long)gridDim.x * blockDim.x * 4;
-    for (long long i = s0 + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < s1; i += stride) {
-      if (i + 4 <= s1) {
-        float4 t[kMaxRanks];   // all peer loads are issued before the first is consumed (NVLink latency ~2 us)
+    const long long s1v = s0 + ((s1 - s0) & ~3ll);                     // whole float4 groups
+    const long long tile = (long long)blockDim.x * 4 * U;              // floats per CTA per iteration
+    const long long step_f = (long long)gridDim.x * tile;
+    // software pipeline: the peer loads of iteration k+1 are in flight while iteration k does its Adam update and its
+    // peer stores, so NVLink carries reads and writes at the same time
+    float4 raw[W][U];
+    auto issue = [&](long long base) {
 #pragma unroll
-        for (int j = 0; j < kMaxRanks; ++j)
-          if (j < world) t[j] = ld_sys4(peers.grads[j] + i);
-        float4 g = t[0];
+      for (int j = 0; j < W; ++j)
+        if (j < world) {
 #pragma unroll
-        for (int j = 1; j < kMaxRanks; ++j)   // fixed rank order: deterministic
-          if (j < world) {
-            g.x = __fadd_rn(g.x, t[j].x); g.y = __fadd_rn(g.y, t[j].y); g.z = __fadd_rn(g.z, t[j].z); g.w = __fadd_rn(g.w, t[j].w);
+          for (int u = 0; u < U; ++u) {
+            const long long i = base + ((long long)u * blockDim.x + threadIdx.x) * 4;
+            if (i < s1v) raw[j][u] = ld_sys4(peers.grads[j] + i);
           }
+        }
+    };
+    long long base = s0 + (long long)blockIdx.x * tile;
+    if (base < s1v) issue(base);
+    for (; base < s1v; base += step_f) {
+      float4 g[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        g[u] = raw[0][u];
+#pragma unroll
+        for (int j = 1; j < W; ++j)            // fixed rank order: deterministic
+          if (j < world) {
+            g[u].x = __fadd_rn(g[u].x, raw[j][u].x); g[u].y = __fadd_rn(g[u].y, raw[j][u].y);
+            g[u].z = __fadd_rn(g[u].z, raw[j][u].z); g[u].w = __fadd_rn(g[u].w, raw[j][u].w);
+          }
+      }
+      if (base + step_f < s1v) issue(base + step_f);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long i = base + ((long long)u * blockDim.x + threadIdx.x) * 4;
+        if (i >= s1v) continue;
         float4 p = *reinterpret_cast<const float4*>(peers.params[rank] + i);
         float4 mm = *reinterpret_cast<const float4*>(m + i), vv = *reinterpret_cast<const float4*>(v + i);
-        adam1(p.x, g.x, mm.x, vv.x, c); adam1(p.y, g.y, mm.y, vv.y, c);
-        adam1(p.z, g.z, mm.z, vv.z, c); adam1(p.w, g.w, mm.w, vv.w, c);
+        adam1(p.x, g[u].x, mm.x, vv.x, c); adam1(p.y, g[u].y, mm.y, vv.y, c);
+        adam1(p.z, g[u].z, mm.z, vv.z, c); adam1(p.w, g[u].w, mm.w, vv.w, c);
         *reinterpret_cast<float4*>(m + i) = mm;
         *reinterpret_cast<float4*>(v + i) = vv;
-        for (int j = 0; j < world; ++j) st_sys4(peers.params[j] + i, p);
-      } else {
-        for (long long k = i; k < s1; ++k) {   // ragged end of the bucket
-          float g = *(volatile float*)(peers.grads[0] + k);
-          for (int j = 1; j < world; ++j) g = __fadd_rn(g, *(volatile float*)(peers.grads[j] + k));
-          float p = peers.params[rank][k], mm = m[k], vv = v[k];
-          adam1(p, g, mm, vv, c);
-          m[k] = mm; v[k] = vv;
-          for (int j = 0; j < world; ++j) *(volatile float*)(peers.params[j] + k) = p;
-        }
+#pragma unroll
+        for (int j = 0; j < W; ++j)
+          if (j < world) st_sys4(peers.params[j] + i, p);
       }
     }
+    if (blockIdx.x == 0 && threadIdx.x < (int)(s1 - s1v)) {   // ragged end of the bucket (< 4 floats)
+      const long long k = s1v + threadIdx.x;
+      float g = *(volatile float*)(peers.grads[0] + k);
+      for (int j = 1; j < world; ++j) g = __fadd_rn(g, *(volatile float*)(peers.grads[j] + k));
+      float p = peers.params[rank][k], mm = m[k], vv = v[k];
+      adam1(p, g, mm, vv, c);
+      m[k] = mm; v[k] = vv;
+      for (int j = 0; j < world; ++j) *(volatile float*)(peers.params[j] + k) = p;
+    }
   }
-  // the last CTA of this rank to finish announces it to every rank, then waits for everybody's announcement
+  // the last CTA of this rank to finish announces it to every rank, then (unless a later exchange of the same step
+  // does it) waits for everybody's announcement: when the kernel ends, all parameters are in place everywhere
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned int done = atomicAdd(&mine->cta_done[bucket], 1u);
     if (done == gridDim.x - 1) {
       mine->cta_done[bucket] = 0;
+      mine->dbg[2] = gtime();
       __threadfence_system();
       for (int j = 0; j < world; ++j) peers.mail[j]->params_done[bucket][rank] = epoch;
-      wait_all(mine->params_done[bucket], world, epoch, &mine->error);
+      if (final_barrier) wait_all(mine->params_done[bucket], world, epoch, &mine->error);
       __threadfence_system();
+      mine->dbg[3] = gtime();
     }
   }
 }
@@ -264,7 +308,8 @@ extern "C" int b200rl_dp_max_f64(b200rl_dp_t h, double* value_dev, const int64_t
 }
 
 extern "C" int b200rl_dp_adam(b200rl_dp_t h, int64_t off, int64_t n, float* m, float* v, const int64_t* step_dev, float lr,
-                              double b1, double b2, float eps, int eps_mode, int32_t bucket, void* stream) {
+                              double b1, double b2, float eps, int eps_mode, int32_t bucket, int32_t final_barrier,
+                              void* stream) {
   DpState* s = (DpState*)h;
   B200RL_REQUIRE(s && m && v && step_dev, "null argument");
   B200RL_REQUIRE(off >= 0 && n >= 1 && off + n <= s->n && off % 4 == 0, "bad bucket range");
@@ -274,11 +319,56 @@ extern "C" int b200rl_dp_adam(b200rl_dp_t h, int64_t off, int64_t n, float* m, f
   long long chunk = (n + s->world - 1) / s->world;
   chunk = (chunk + 3) & ~3ll;
   const long long vec = (chunk + 3) / 4;
-  int blocks = (int)std::max<long long>(1, std::min<long long>((vec + 255) / 256, 2 * kNumSMs));
-  dp_adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(s->peers, s->world, s->rank, off, n, chunk, m, v,
-                                                       (const long long*)step_dev, lr, b1, b2, eps, eps_mode, bucket);
+  cudaStream_t st = as_stream(stream);
+  // NVLink saturates with one CTA per SM; more only helps the local (HBM) part of the update, which dominates at R = 2
+  static const int per_sm_env = getenv("B200RL_DP_CTAS_PER_SM") ? atoi(getenv("B200RL_DP_CTAS_PER_SM")) : 0;
+  const int per_sm = per_sm_env > 0 ? per_sm_env : (s->world <= 2 ? 3 : 1);
+#define DP_LAUNCH(W_, U_)                                                                                              \
+  {                                                                                                                    \
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((vec + 256 * U_ - 1) / (256 * U_), per_sm * kNumSMs)); \
+    dp_adam_kernel<W_, U_><<<blocks, 256, 0, st>>>(s->peers, s->world, s->rank, off, n, chunk, m, v,                   \
+                                                  (const long long*)step_dev, lr, b1, b2, eps, eps_mode, bucket,        \
+                                                  final_barrier);                                                      \
+  }
+  if (s->world <= 2) DP_LAUNCH(2, 2) else if (s->world <= 4) DP_LAUNCH(4, 2) else DP_LAUNCH(8, 2)
+#undef DP_LAUNCH
   B200RL_LAUNCH_OK();
   return B200RL_OK;
+}
+
+// tools/dp_bench.py: raw peer-memory bandwidth as seen by SM loads / stores (mode 0 = read the peer's gradient
+// region, 1 = write the peer's gradient region, 2 = read the local one)
+__global__ void __launch_bounds__(256) dp_probe_kernel(b200rl::DpPeers peers, int peer, int rank, long long n4, int mode, float* sink) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  float* base = mode == 2 ? peers.grads[rank] : peers.grads[peer];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += 4 * stride) {
+    if (mode == 1) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i + u * stride < n4) b200rl::st_sys4(base + 4 * (i + u * stride), make_float4(1.f, 2.f, 3.f, 4.f));
+    } else {
+      float4 t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i + u * stride < n4) t[u] = b200rl::ld_sys4(base + 4 * (i + u * stride));
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i + u * stride < n4) { acc.x += t[u].x; acc.y += t[u].y; acc.z += t[u].z; acc.w += t[u].w; }
+    }
+  }
+  if (mode != 1 && acc.x + acc.y + acc.z + acc.w == 123.456f) sink[0] = acc.x;
+}
+extern "C" int b200rl_debug_dp_probe(b200rl_dp_t h, int peer, long long n_floats, int mode, int blocks, float* sink, void* stream) {
+  DpState* s = (DpState*)h;
+  dp_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(s->peers, peer, s->rank, n_floats / 4, mode, sink);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+extern "C" int b200rl_debug_dp_stamps(b200rl_dp_t h, long long* out8) {
+  DpState* s = (DpState*)h;
+  const Mailbox* mb = s->peers.mail[s->rank];
+  return cudaMemcpy(out8, (const void*)mb->dbg, 64, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
 }
 
 extern "C" int b200rl_dp_status(b200rl_dp_t h) {

@@ -77,17 +77,21 @@ class DQNLearner(core.Learner, core.Saveable):
     # the three forward passes are independent, and so are a layer's weight- and data-gradient: run them on
     # parallel streams (fork/join with events, also inside the captured graph)
     self._concurrent = bool(concurrent_streams) and hasattr(network, '_backward_two_streams')
-    self._split_adam = self._concurrent and hasattr(network, 'grad_buckets')
+    # Adam on the fc1 + head bucket underneath the convolution backward: measured zero-sum on B200 (the update streams
+    # 200 MB and takes the SM slots the latency-bound conv kernels need), so it is off unless asked for
+    # With a peer exchange on >= 4 ranks the bucket's kernel is NVLink-bound (1/R of the Adam work) and does hide
+    # behind the convolution backward.
+    split_default = '1' if self._world >= 4 else '0'
+    self._split_adam = (self._concurrent and hasattr(network, 'grad_buckets') and
+                        os.environ.get('B200RL_SPLIT_ADAM', split_default) == '1')
     self._tail_done = None
     self._side = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)] if self._concurrent else None
     # data parallel: gradients and parameters live in a peer-mapped region and the exchange is fused with Adam
     # (parallel.PeerExchange); peer_exchange=False keeps the NCCL all-reduce + replicated Adam path
     if peer_exchange is None:
-      peer_exchange = self._world > 1 and self._split_adam and os.environ.get('B200RL_PEER_EXCHANGE', '1') != '0'
+      peer_exchange = self._world > 1 and os.environ.get('B200RL_PEER_EXCHANGE', '1') != '0'
     self._px = None
     if peer_exchange and self._world > 1:
-      if not self._split_adam:
-        raise ValueError('peer_exchange needs a network with grad_buckets() and concurrent_streams=True')
       self._px = parallel.PeerExchange(self._dp, network.params.size, network.device)
       network.params.rebind(self._px.params, self._px.grads)
     self._steps_done = 0
@@ -198,15 +202,18 @@ class DQNLearner(core.Learner, core.Saveable):
     """K7 over params[off : off + n] (snt.optimizers.Adam.apply, dqn/learning.py:147-149); with a peer exchange the
     gradient mean over the ranks, Adam on the owned shard and the parameter broadcast are one kernel."""
     if self._px is not None:
-      self._px.adam(off, n, self._m, self._v, self._num_steps, self._lr, 0.9, 0.999, self._adam_eps, self._eps_mode, bucket)
+      # the fc1 + head bucket (0) of a split update is followed by the conv bucket (1), whose barrier covers both
+      final = not (self._split_adam and bucket == 0)
+      self._px.adam(off, n, self._m, self._v, self._num_steps, self._lr, 0.9, 0.999, self._adam_eps, self._eps_mode, bucket,
+                    final_barrier=final)
       return
     P, b = self._net.params, 4 * off
     _capi.call('b200rl_adam', n, _capi.ptr(P.flat) + b, _capi.ptr(P.grad) + b, _capi.ptr(self._m) + b, _capi.ptr(self._v) + b,
                _capi.ptr(self._num_steps), self._lr, 0.9, 0.999, self._adam_eps, self._eps_mode,
                _capi.ptr(self._gscale) if self._world > 1 else None, None, _capi.current_stream())
 
-  def _adam_tail_async(self, after=None):
-    """Adam on the fc1 + head bucket on side stream 1; `after` = the bucket's pending all-reduce (data parallel)."""
+  def _adam_tail_async(self):
+    """Adam on the fc1 + head bucket on side stream 1 (B200RL_SPLIT_ADAM=1)."""
     torch = self._torch
     (o1, n1), _ = self._net.grad_buckets()
     main, side = torch.cuda.current_stream(), self._side[1]
@@ -214,8 +221,6 @@ class DQNLearner(core.Learner, core.Saveable):
     ev.record(main)
     side.wait_event(ev)
     with torch.cuda.stream(side):
-      if after is not None:
-        after.wait()
       self._adam(o1, n1, bucket=0)
       self._tail_done = torch.cuda.Event()
       self._tail_done.record(side)
@@ -286,10 +291,10 @@ class DQNLearner(core.Learner, core.Saveable):
         def second():
           self._dataset.gather_only()
           self._forwards()
-        if self._concurrent and self._split_adam:
+        if self._concurrent and hasattr(self._net, 'grad_buckets'):
           self._graphs = [self._capture(self._sample), self._capture(second),
                           self._capture(lambda: self._loss_backward('dense')),
-                          self._capture(lambda: self._loss_backward('conv')), self._capture(lambda: self._apply('conv'))]
+                          self._capture(lambda: self._loss_backward('conv')), self._capture(lambda: self._apply('all'))]
         else:
           self._graphs = [self._capture(self._sample), self._capture(second), self._capture(self._loss_backward),
                           self._capture(lambda: self._apply('all'))]
@@ -311,11 +316,10 @@ class DQNLearner(core.Learner, core.Saveable):
     (o1, n1), (o0, n0) = self._net.grad_buckets()
     self._graphs[2].replay()                      # loss, head and fc1 backward: the tail of the gradient buffer is final
     work = dist.all_reduce(g[o1:o1 + n1], op=dist.ReduceOp.SUM, group=grp, async_op=True)
-    self._graphs[3].replay()                      # convolution backward runs while NCCL moves fc1's 31.7 MB ...
-    self._adam_tail_async(after=work)             # ... and then Adam streams that bucket on side stream 1
+    self._graphs[3].replay()                      # convolution backward runs while NCCL moves fc1's 31.7 MB
     self._dp.sum_(g[o0:o0 + n0])                  # the convolutions' 0.3 MB
-    torch.cuda.current_stream().wait_event(self._tail_done)
-    self._graphs[4].replay()                      # Adam on the conv bucket, priorities, target copy, step counter
+    work.wait()
+    self._graphs[4].replay()                      # Adam (x 1/R), priorities, target copy, step counter
 
   # ------------------------------------------------------------------ acme.core.Learner
   def step(self, uniforms=None, fetch_loss=True):

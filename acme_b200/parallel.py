@@ -113,10 +113,11 @@ class PeerExchange:
     from acme_b200 import _capi
     _capi.call('b200rl_dp_max_f64', self._h, _capi.ptr(value), _capi.ptr(step), _capi.current_stream())
 
-  def adam(self, off: int, n: int, m, v, step, lr: float, b1: float, b2: float, eps: float, eps_mode: int, bucket: int):
+  def adam(self, off: int, n: int, m, v, step, lr: float, b1: float, b2: float, eps: float, eps_mode: int, bucket: int,
+           final_barrier: bool = True):
     from acme_b200 import _capi
     _capi.call('b200rl_dp_adam', self._h, off, n, _capi.ptr(m), _capi.ptr(v), _capi.ptr(step), lr, b1, b2, eps, eps_mode,
-               bucket, _capi.current_stream())
+               bucket, int(final_barrier), _capi.current_stream())
 
   def check(self):
     from acme_b200 import _capi

@@ -259,8 +259,10 @@ int b200rl_split_second(int32_t B, int32_t n0, int32_t n1, const float* dy, floa
  *   max_f64  in-place all-reduce(MAX) of one device double (the importance-weight normaliser, dqn/learning.py:140)
  *   adam     parameters[off, off+n) of all ranks <- Adam(mean over ranks of grads[off, off+n)); m, v: this rank's
  *            full-size moment buffers (only the owned shard is touched); `bucket` (0..3) names the mailbox slot, two
- *            buckets may be in flight at once; step_dev as in b200rl_adam.  All ranks must issue the same calls in
- *            the same order each step; both calls are CUDA-graph capturable.
+ *            buckets may be in flight at once; step_dev as in b200rl_adam.  final_barrier = 0 lets the kernel end
+ *            without waiting for the peers' stores: only allowed when a later exchange of the same step (issued
+ *            after this one on every rank) has final_barrier = 1.  All ranks must issue the same calls in the same
+ *            order each step; both calls are CUDA-graph capturable.
  *   status   < 0 if an exchange gave up waiting for a peer (~2 s) */
 typedef struct b200rl_dp* b200rl_dp_t;
 typedef struct b200rl_dp_cfg {
@@ -274,7 +276,7 @@ int b200rl_dp_export(b200rl_dp_t h, void* handle64);
 int b200rl_dp_import(b200rl_dp_t h, int32_t peer_rank, const void* handle64);
 int b200rl_dp_max_f64(b200rl_dp_t h, double* value_dev, const int64_t* step_dev, void* stream);
 int b200rl_dp_adam(b200rl_dp_t h, int64_t off, int64_t n, float* m, float* v, const int64_t* step_dev, float lr,
-                   double b1, double b2, float eps, int eps_mode, int32_t bucket, void* stream);
+                   double b1, double b2, float eps, int eps_mode, int32_t bucket, int32_t final_barrier, void* stream);
 int b200rl_dp_status(b200rl_dp_t h);
 
 /* bytes of split-K workspace that lets every layer call on outputs of up to max_out_elems

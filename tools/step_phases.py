@@ -6,18 +6,25 @@ import numpy as np, torch
 import bench
 from acme_b200 import _capi, adders, dqn, loggers, networks, replay, specs
 
+world, rank = int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('RANK', '0'))
+pg = None
+if world > 1:
+  import torch.distributed as dist
+  torch.cuda.set_device(rank)
+  dist.init_process_group('nccl', device_id=torch.device('cuda', rank))
+  pg = dist.group.WORLD
 spec = specs.EnvironmentSpec(specs.Array(bench.OBS_SHAPE, np.uint8), specs.DiscreteArray(18), specs.Array((), np.float32), specs.BoundedArray((), np.float32, 0., 1.))
 items = 131072
 table = replay.Table(replay.DEFAULT_PRIORITY_TABLE, replay.selectors.Prioritized(0.6), replay.selectors.Fifo(), max_size=items,
                      rate_limiter=replay.rate_limiters.MinSize(1), signature=adders.NStepTransitionAdder.signature(spec), max_window=3,
-                     discount=0.99, slot_capacity=items + 4096, stage_slots=4096)
+                     discount=0.99, slot_capacity=items + 4096, stage_slots=4096, device=rank, shard_count=world, shard_rank=rank)
 server = replay.Server([table])
-bench.fill_replay(table, items, 3, seed=1)
+bench.fill_replay(table, items, 3, seed=1 + rank)
 prec = 1 if (len(sys.argv) < 2 or sys.argv[1] != 'fp32') else 0
-net = networks.DQNAtariNetwork(18, precision=prec, seed=1)
+net = networks.DQNAtariNetwork(18, precision=prec, seed=1, device=rank)
 tgt = net.clone()
-ds = replay.ReplayDataset(table, 256, seed=1)
-L = dqn.DQNLearner(net, tgt, 0.99, 0.2, 1e-3, 100, ds, replay_client=replay.Client(server), logger=loggers.NoOpLogger())
+ds = replay.ReplayDataset(table, 256, seed=1 + rank)
+L = dqn.DQNLearner(net, tgt, 0.99, 0.2, 1e-3, 100, ds, replay_client=replay.Client(server), logger=loggers.NoOpLogger(), process_group=pg)
 names = ['k1 sample + k3 gather', 'forwards x3 (3 streams)', 'k4 td/loss', 'backward (2 streams)', 'k7 adam', 'k2 priorities + copy + inc']
 for _ in range(10): L.step(fetch_loss=False)
 tot = np.zeros(6); n = 50
@@ -25,6 +32,9 @@ for _ in range(n):
   L.step(fetch_loss=False); torch.cuda.synchronize()
   t = L._stamps.cpu().numpy()
   tot += np.diff(t[:7]) / 1e3
-for nm, v in zip(names, tot / n): print(f'{nm:28s} {v:8.1f} us')
-print('sum', round(float((tot / n).sum()), 1), '(each stamp kernel adds ~2 us)')
+if rank == 0:
+  for nm, v in zip(names, tot / n): print(f'{nm:28s} {v:8.1f} us')
+if rank == 0: print('sum', round(float((tot / n).sum()), 1), '(each stamp kernel adds ~2 us)')
+if L._px is not None: L._px.close()
 server.stop()
+if world > 1: dist.destroy_process_group()
