@@ -11,6 +11,7 @@ dataset, actor and learner like `acme/agents/tf/dqn/agent.py:45-162`.
 
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import os
 import time
@@ -81,11 +82,12 @@ class DQNLearner(core.Learner, core.Saveable):
     # 200 MB and takes the SM slots the latency-bound conv kernels need), so it is off unless asked for
     # With a peer exchange on >= 4 ranks the bucket's kernel is NVLink-bound (1/R of the Adam work) and does hide
     # behind the convolution backward.
-    split_default = '1' if self._world >= 4 else '0'
+    split_default = '0'   # measured on 8 GPUs: 0.540 ms split vs 0.522 ms unsplit (more barriers, contention)
     self._split_adam = (self._concurrent and hasattr(network, 'grad_buckets') and
                         os.environ.get('B200RL_SPLIT_ADAM', split_default) == '1')
     self._tail_done = None
-    self._side = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)] if self._concurrent else None
+    self._side = [torch.cuda.Stream(device=dev) for _ in range(3)] if self._concurrent else None
+    self._wmax_done = None
     # data parallel: gradients and parameters live in a peer-mapped region and the exchange is fused with Adam
     # (parallel.PeerExchange); peer_exchange=False keeps the NCCL all-reduce + replicated Adam path
     if peer_exchange is None:
@@ -133,7 +135,7 @@ class DQNLearner(core.Learner, core.Saveable):
       main = torch.cuda.current_stream()
       start = torch.cuda.Event()
       start.record(main)
-      for s in self._side:
+      for s in self._side[:2]:
         s.wait_event(start)
       with torch.cuda.stream(self._side[0]):
         tgt.lane(1).forward(o_t, self._bufs_tgt)                 # learning.py:124
@@ -141,7 +143,7 @@ class DQNLearner(core.Learner, core.Saveable):
       with torch.cuda.stream(self._side[1]):
         net.lane(2).forward(o_t, self._bufs_sel)                 # learning.py:125
       net.lane(0).forward(o_tm1, self._bufs_train)               # learning.py:123
-      for s in self._side:
+      for s in self._side[:2]:
         done = torch.cuda.Event()
         done.record(s)
         main.wait_event(done)
@@ -157,9 +159,19 @@ class DQNLearner(core.Learner, core.Saveable):
     ds = self._dataset
     ds.sample_only(uniforms)
     if self._world > 1:
-      _capi.call('b200rl_is_weight_max', self.B, _capi.ptr(ds.prob), self._beta, _capi.ptr(self._wmax), _capi.current_stream())
-      if self._px is not None:      # all-reduce(MAX) through the peers' mailboxes, inside the captured step
-        self._px.max_f64_(self._wmax, self._num_steps)
+      torch = self._torch
+      aux = self._side[2] if (self._concurrent and self._px is not None) else None
+      if aux is not None:           # the exchange waits for the slowest rank: keep it off the gather / forward path
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        aux.wait_event(ev)
+      with torch.cuda.stream(aux) if aux is not None else contextlib.nullcontext():
+        _capi.call('b200rl_is_weight_max', self.B, _capi.ptr(ds.prob), self._beta, _capi.ptr(self._wmax), _capi.current_stream())
+        if self._px is not None:    # all-reduce(MAX) through the peers' mailboxes, inside the captured step
+          self._px.max_f64_(self._wmax, self._num_steps)
+        if aux is not None:
+          self._wmax_done = torch.cuda.Event()
+          self._wmax_done.record(aux)
 
   def _loss_backward(self, part: str = 'all'):
     """K4 (learning.py:127-154) and the backward pass through net(o_tm1).  `part` lets the data-parallel
@@ -171,6 +183,9 @@ class DQNLearner(core.Learner, core.Saveable):
       return
     st = _capi.current_stream()
     o_tm1 = self._obs_view(ds.o_tm1)
+    if self._wmax_done is not None:
+      self._torch.cuda.current_stream().wait_event(self._wmax_done)
+      self._wmax_done = None
     wmax = _capi.ptr(self._wmax) if self._world > 1 else None
     _capi.call('b200rl_dqn_td', self.B, net.A, _capi.ptr(self._bufs_train['q']), _capi.ptr(self._bufs_tgt['q']),
                _capi.ptr(self._bufs_sel['q']), _capi.ptr(self._actions_i32()), _capi.ptr(ds.R), _capi.ptr(ds.D),
@@ -233,6 +248,17 @@ class DQNLearner(core.Learner, core.Saveable):
     if adam == 'auto':
       split = self._concurrent and self._split_adam and (self._world == 1 or self._px is not None)
       adam = 'conv+join' if split else 'all'
+    prio_done = None
+    if self._replay_client is not None and self._concurrent:
+      # K2 only needs the priorities K4 produced: it runs beside the optimizer / exchange
+      torch = self._torch
+      ev = torch.cuda.Event()
+      ev.record(torch.cuda.current_stream())
+      self._side[2].wait_event(ev)
+      with torch.cuda.stream(self._side[2]):
+        self._dataset.table.update_priorities_device(self._dataset.keys, self.priority)   # learning.py:151-154
+        prio_done = torch.cuda.Event()
+        prio_done.record(self._side[2])
     if adam == 'all':
       self._adam(0, P.size)
     else:
@@ -241,7 +267,9 @@ class DQNLearner(core.Learner, core.Saveable):
       _, (o0, n0) = net.grad_buckets()
       self._adam(o0, n0, bucket=1)
     self._stamp(5)
-    if self._replay_client is not None:                         # learning.py:151-154
+    if prio_done is not None:
+      self._torch.cuda.current_stream().wait_event(prio_done)
+    elif self._replay_client is not None:                       # learning.py:151-154
       self._dataset.table.update_priorities_device(self._dataset.keys, self.priority)
     # learning.py:157-161: copy when num_steps % period == 0, evaluated before the increment
     _capi.call('b200rl_copy_if_period', P.size * 4, _capi.ptr(tgt.params.flat), _capi.ptr(P.flat),
