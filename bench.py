@@ -292,11 +292,15 @@ def run_ours(args):
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   barrier()
   clocks.mark()
+  if args.profile:
+    torch.cuda.profiler.start()     # ncu --profile-from-start off: only the timed learner steps are captured
   e0.record()
   for _ in range(args.steps):
     learner.step(fetch_loss=False)
   e1.record()
   barrier()
+  if args.profile:
+    torch.cuda.profiler.stop()
   clocks.mark()
   dev_s = e0.elapsed_time(e1) * 1e-3
   clk = clocks.stop()
@@ -410,6 +414,10 @@ def run_ours(args):
     kname = 'k6_network_gemm_conv (3 forwards + 1 backward, fp32 SIMT FFMA)' if precision == 0 else \
             'k6_network_gemm_conv (3 forwards + 1 backward; tcgen05: TMA-fed kind::tf32 for conv2/conv3/fc1, kind::f16 bf16 for conv1)'
     achieved = STEP_FLOPS / net_s / 1e12 if net_s > 0 else None
+    traffic = None    # dram bytes of the same kernel group from the committed `ncu --set full` capture (tensor-core mode)
+    prof = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'ncu_full_r01_tc_layers_summary.json')
+    if precision != 0 and os.path.exists(prof):
+      traffic = json.load(open(prof)).get('step_group_dram_bytes')
     out = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -428,7 +436,7 @@ def run_ours(args):
                         'inside the timed region), per update (the reference loop cadence)', 'steps': e2e_steps},
         'gpu_launches': gpu_launches,
         'roofline': {'kernel': kname, 'bound': 'tensor', 'achieved': achieved, 'peak': P['tf_sustained'], 'unit': 'TFLOP/s',
-                     'frac': (achieved / P['tf_sustained']) if achieved else None, 'traffic': None,
+                     'frac': (achieved / P['tf_sustained']) if achieved else None, 'traffic': traffic,
                      'peak_source': f"{P['src']} (sustained bf16: kernel timed inside a long step)",
                      'alg_flops_per_launch_group': STEP_FLOPS, 'group_seconds': net_s},
         'cpu_baseline': cpu_baseline,
