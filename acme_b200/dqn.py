@@ -86,8 +86,9 @@ class DQNLearner(core.Learner, core.Saveable):
     self._split_adam = (self._concurrent and hasattr(network, 'grad_buckets') and
                         os.environ.get('B200RL_SPLIT_ADAM', split_default) == '1')
     self._tail_done = None
-    self._side = [torch.cuda.Stream(device=dev) for _ in range(3)] if self._concurrent else None
+    self._side = [torch.cuda.Stream(device=dev) for _ in range(4)] if self._concurrent else None
     self._wmax_done = None
+    self._params_ready = None      # pipelined exchange: event the online forwards wait for
     # data parallel: gradients and parameters live in a peer-mapped region and the exchange is fused with Adam
     # (parallel.PeerExchange); peer_exchange=False keeps the NCCL all-reduce + replicated Adam path
     if peer_exchange is None:
@@ -96,6 +97,15 @@ class DQNLearner(core.Learner, core.Saveable):
     if peer_exchange and self._world > 1:
       self._px = parallel.PeerExchange(self._dp, network.params.size, network.device)
       network.params.rebind(self._px.params, self._px.grads)
+    # Pipelined exchange (data parallel with a peer exchange): the optimizer update of step t is issued at the START of
+    # step t+1's graph, beside K1 / K3 / the target-network forward, none of which read the online parameters; only the
+    # two online forwards wait for it.  Same values as the serial order, the NVLink-bound exchange just leaves the
+    # critical path.  `flush()` applies the update still in flight (collective: every rank must call it).
+    self._pipeline = (self._px is not None and self._concurrent and bool(use_cuda_graph) and
+                      os.environ.get('B200RL_DP_PIPELINE', '1') != '0')
+    self._pending = False            # gradients computed, update not applied yet
+    self._applied_host = 0           # host mirror of the device step counter (number of applied updates)
+    self._pgraphs = {}
     self._steps_done = 0
     self.kernel_launches_per_step = None
 
@@ -140,6 +150,10 @@ class DQNLearner(core.Learner, core.Saveable):
       with torch.cuda.stream(self._side[0]):
         tgt.lane(1).forward(o_t, self._bufs_tgt)                 # learning.py:124
       tgt.lane(0)
+      if self._params_ready is not None:   # pipelined exchange: the new online parameters must have landed
+        self._side[1].wait_event(self._params_ready)
+        main.wait_event(self._params_ready)
+        self._params_ready = None
       with torch.cuda.stream(self._side[1]):
         net.lane(2).forward(o_t, self._bufs_sel)                 # learning.py:125
       net.lane(0).forward(o_tm1, self._bufs_train)               # learning.py:123
@@ -168,7 +182,8 @@ class DQNLearner(core.Learner, core.Saveable):
       with torch.cuda.stream(aux) if aux is not None else contextlib.nullcontext():
         _capi.call('b200rl_is_weight_max', self.B, _capi.ptr(ds.prob), self._beta, _capi.ptr(self._wmax), _capi.current_stream())
         if self._px is not None:    # all-reduce(MAX) through the peers' mailboxes, inside the captured step
-          self._px.max_f64_(self._wmax, self._num_steps)
+          # epoch = the dataset's draw counter: unlike the step counter it is not touched by a pipelined update
+          self._px.max_f64_(self._wmax, self._dataset.counter)
         if aux is not None:
           self._wmax_done = torch.cuda.Event()
           self._wmax_done.record(aux)
@@ -277,6 +292,77 @@ class DQNLearner(core.Learner, core.Saveable):
     _capi.call('b200rl_step_increment', _capi.ptr(self._num_steps), st)
     self._stamp(6)
 
+  # ---- pipelined exchange (see __init__)
+  def _apply_update(self, copy: bool = True):
+    """The optimizer half of a step: exchange + Adam, periodic target copy, step counter."""
+    P, st = self._net.params, _capi.current_stream()
+    self._adam(0, P.size)
+    if copy:
+      _capi.call('b200rl_copy_if_period', P.size * 4, _capi.ptr(self._tgt.params.flat), _capi.ptr(P.flat),
+                 _capi.ptr(self._num_steps), self._period, 0, st)
+    _capi.call('b200rl_step_increment', _capi.ptr(self._num_steps), st)
+
+  def _compute(self, uniforms=None):
+    """The gradient half of a step: K1, K3, forwards, K4, backward, K2."""
+    self._sample(uniforms)
+    self._dataset.gather_only()
+    self._forwards()
+    self._loss_backward()
+    if self._replay_client is not None:
+      self._dataset.table.update_priorities_device(self._dataset.keys, self.priority)
+
+  def _pipelined_graph(self, variant: str):
+    torch = self._torch
+
+    def body():
+      if variant == 'copy':          # the target network changes in this update: strict order
+        self._apply_update(copy=True)
+      elif variant == 'norm':        # update on a side stream; only the online forwards wait for it
+        main, side = torch.cuda.current_stream(), self._side[3]
+        ev = torch.cuda.Event()
+        ev.record(main)
+        side.wait_event(ev)
+        with torch.cuda.stream(side):
+          self._apply_update(copy=False)
+          self._params_ready = torch.cuda.Event()
+          self._params_ready.record(side)
+      self._compute()
+    g = self._capture(body)
+    import torch.distributed as dist
+    dist.barrier(group=self._dp.group)      # every rank has the graph before anyone spins on a peer
+    return g
+
+  def _pipelined_step(self, uniforms):
+    if not self._use_graph or uniforms is not None or self._steps_done < 2:
+      lib = _capi.load()
+      n0 = lib.b200rl_launch_count()
+      had_update = self._pending
+      self.flush()
+      self._compute(uniforms)
+      self._pending = True
+      if had_update:
+        self.kernel_launches_per_step = int(lib.b200rl_launch_count() - n0)
+      return
+    if not self._pending:
+      variant = 'first'
+    else:
+      variant = 'copy' if self._applied_host % self._period == 0 else 'norm'
+    if not self._pgraphs:              # all three at once: no capture (and no host barrier) later inside a run
+      for v in ('first', 'norm', 'copy'):
+        self._pgraphs[v] = self._pipelined_graph(v)
+    self._pgraphs[variant].replay()
+    if self._pending:
+      self._applied_host += 1
+    self._pending = True
+
+  def flush(self):
+    """Applies the optimizer update still in flight (pipelined exchange only; COLLECTIVE: all ranks call it together).
+    Called by save() / state / num_steps; get_variables() does not (actors lag by that one update)."""
+    if self._pending:
+      self._apply_update(copy=True)
+      self._applied_host += 1
+      self._pending = False
+
   def _eager_step(self, uniforms):
     lib = _capi.load()
     n0 = lib.b200rl_launch_count()
@@ -300,6 +386,9 @@ class DQNLearner(core.Learner, core.Saveable):
     """One update on the device.  Single GPU: the whole step is one CUDA graph.  Data parallel: three graphs
     (forwards | loss + backward | apply) with the two NCCL all-reduces issued between them, so the host
     does 5 launches per step instead of ~50."""
+    if self._pipeline:
+      self._pipelined_step(uniforms)
+      return
     if not self._use_graph or uniforms is not None or self._steps_done < 2:
       self._eager_step(uniforms)      # also the un-captured warm-up (one-time attribute setup inside the library)
       return
@@ -396,19 +485,24 @@ class DQNLearner(core.Learner, core.Saveable):
 
   @property
   def num_steps(self) -> int:
+    self.flush()
     return int(self._num_steps.item())
 
   @property
   def state(self):
+    self.flush()
     return {'network': self._net, 'target_network': self._tgt, 'optimizer': (self._m, self._v),
             'num_steps': self._num_steps}
 
   def save(self):
+    self.flush()
     return {'network': self._net.params.flat.cpu().numpy(), 'target_network': self._tgt.params.flat.cpu().numpy(),
             'adam_m': self._m.cpu().numpy(), 'adam_v': self._v.cpu().numpy(), 'num_steps': self.num_steps}
 
   def restore(self, state):
     torch = self._torch
+    self._pending = False
+    self._applied_host = int(state['num_steps'])
     self._net.params.flat.copy_(torch.as_tensor(state['network']))
     self._tgt.params.flat.copy_(torch.as_tensor(state['target_network']))
     self._m.copy_(torch.as_tensor(state['adam_m']))

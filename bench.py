@@ -297,6 +297,7 @@ def run_ours(args):
   e0.record()
   for _ in range(args.steps):
     learner.step(fetch_loss=False)
+  learner.flush()                   # pipelined data-parallel exchange: the last update is applied inside the timed region
   e1.record()
   barrier()
   if args.profile:
@@ -341,6 +342,7 @@ def run_ours(args):
   e2e_steps = max(args.steps // 2, 10)
   for i in range(e2e_steps):
     e2e_step(i + 3)
+  learner.flush()
   last_loss = learner.drain()            # the final update's loss, read inside the timed region
   assert last_loss is not None and np.isfinite(last_loss)
   barrier()
