@@ -150,13 +150,19 @@ class DQNLearner(core.Learner, core.Saveable):
       with torch.cuda.stream(self._side[0]):
         tgt.lane(1).forward(o_t, self._bufs_tgt)                 # learning.py:124
       tgt.lane(0)
-      if self._params_ready is not None:   # pipelined exchange: the new online parameters must have landed
-        self._side[1].wait_event(self._params_ready)
-        main.wait_event(self._params_ready)
+      hook = None
+      if self._params_ready is not None:
+        # pipelined exchange: the torso's parameters (a 0.3 MB bucket, exchanged first) must have landed before the
+        # online forwards start; the fc1 + head bucket (31.7 MB) only before their first dense layer
+        ev_conv, ev_tail = self._params_ready
         self._params_ready = None
+        self._side[1].wait_event(ev_conv)
+        main.wait_event(ev_conv)
+        hook = lambda: torch.cuda.current_stream().wait_event(ev_tail)
+      kw = dict(before_fc1=hook) if hook is not None else {}
       with torch.cuda.stream(self._side[1]):
-        net.lane(2).forward(o_t, self._bufs_sel)                 # learning.py:125
-      net.lane(0).forward(o_tm1, self._bufs_train)               # learning.py:123
+        net.lane(2).forward(o_t, self._bufs_sel, **kw)           # learning.py:125
+      net.lane(0).forward(o_tm1, self._bufs_train, **kw)         # learning.py:123
       for s in self._side[:2]:
         done = torch.cuda.Event()
         done.record(s)
@@ -294,13 +300,30 @@ class DQNLearner(core.Learner, core.Saveable):
 
   # ---- pipelined exchange (see __init__)
   def _apply_update(self, copy: bool = True):
-    """The optimizer half of a step: exchange + Adam, periodic target copy, step counter."""
+    """The optimizer half of a step: exchange + Adam, periodic target copy, step counter.  With a peer exchange: two
+    exchanges, torso bucket first, each followed by an event (returned) that the forwards can wait for."""
     P, st = self._net.params, _capi.current_stream()
-    self._adam(0, P.size)
+    events = None
+    # NOTE: the owner of a parameter's moments is fixed by the bucket partition, so every update of a run must use
+    # the same one: with a peer exchange and a bucketed network it is always the two-bucket form
+    if self._px is not None and hasattr(self._net, 'grad_buckets'):
+      torch = self._torch
+      (o1, n1), (o0, n0) = self._net.grad_buckets()
+      px, args = self._px, (self._m, self._v, self._num_steps, self._lr, 0.9, 0.999, self._adam_eps, self._eps_mode)
+      px.adam(o0, n0, *args, 1, final_barrier=True)
+      ev_conv = torch.cuda.Event()
+      ev_conv.record(torch.cuda.current_stream())
+      px.adam(o1, n1, *args, 0, final_barrier=True)
+      ev_tail = torch.cuda.Event()
+      ev_tail.record(torch.cuda.current_stream())
+      events = (ev_conv, ev_tail)
+    else:
+      self._adam(0, P.size)
     if copy:
       _capi.call('b200rl_copy_if_period', P.size * 4, _capi.ptr(self._tgt.params.flat), _capi.ptr(P.flat),
                  _capi.ptr(self._num_steps), self._period, 0, st)
     _capi.call('b200rl_step_increment', _capi.ptr(self._num_steps), st)
+    return events
 
   def _compute(self, uniforms=None):
     """The gradient half of a step: K1, K3, forwards, K4, backward, K2."""
@@ -323,10 +346,16 @@ class DQNLearner(core.Learner, core.Saveable):
         ev.record(main)
         side.wait_event(ev)
         with torch.cuda.stream(side):
-          self._apply_update(copy=False)
-          self._params_ready = torch.cuda.Event()
-          self._params_ready.record(side)
+          self._params_ready = self._apply_update(copy=False)
+          if self._params_ready is None:
+            ev = torch.cuda.Event()
+            ev.record(side)
+            self._params_ready = (ev, ev)
+          self._update_done = torch.cuda.Event()     # the side stream must rejoin the capture's origin stream
+          self._update_done.record(side)
       self._compute()
+      if variant == 'norm':
+        torch.cuda.current_stream().wait_event(self._update_done)
     g = self._capture(body)
     import torch.distributed as dist
     dist.barrier(group=self._dp.group)      # every rank has the graph before anyone spins on a peer

@@ -253,8 +253,10 @@ class DQNAtariNetwork(Network):
       g[f'dy{i}'] = f(B, oh, oh, co)
     return g
 
-  def forward(self, obs, bufs) -> 'torch.Tensor':
-    """obs: uint8 or float32 [B, H, W, C] (NHWC).  uint8 is read as float32(x)/255."""
+  def forward(self, obs, bufs, before_fc1=None) -> 'torch.Tensor':
+    """obs: uint8 or float32 [B, H, W, C] (NHWC).  uint8 is read as float32(x)/255.  `before_fc1` (optional callable)
+    runs after the torso has been issued and before the first dense layer: the pipelined data-parallel learner makes
+    the stream wait there for the fc1 + head parameters, which arrive while the convolutions run."""
     import torch
     B, P, st = bufs['B'], self.params, _capi.current_stream()
     ws, wsb = self.ws
@@ -265,6 +267,8 @@ class DQNAtariNetwork(Network):
       _capi.call('b200rl_conv2d_fwd', x, x_u8, P.p(f'conv{i + 1}.w'), P.p(f'conv{i + 1}.b'), y.data_ptr(),
                  g, ACT_RELU, self.precision, ws, wsb, st)
       x, x_u8 = y.data_ptr(), 0
+    if before_fc1 is not None:
+      before_fc1()
     h = bufs['h']
     _linear(B, 1024, self.flat_dim, x, self.flat_dim, P.p('fc1.w'), P.p('fc1.b'), h.data_ptr(), 1024, ACT_RELU, self)
     _capi.call('b200rl_duelling_head_fwd', B, self.A, 512, h.data_ptr(), 1024, P.p('v2.w'), P.p('v2.b'), P.p('a2.w'),
