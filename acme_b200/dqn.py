@@ -86,7 +86,7 @@ class DQNLearner(core.Learner, core.Saveable):
     self._split_adam = (self._concurrent and hasattr(network, 'grad_buckets') and
                         os.environ.get('B200RL_SPLIT_ADAM', split_default) == '1')
     self._tail_done = None
-    self._side = [torch.cuda.Stream(device=dev) for _ in range(4)] if self._concurrent else None
+    self._side = [torch.cuda.Stream(device=dev) for _ in range(5)] if self._concurrent else None
     self._wmax_done = None
     self._params_ready = None      # pipelined exchange: event the online forwards wait for
     # data parallel: gradients and parameters live in a peer-mapped region and the exchange is fused with Adam
@@ -310,6 +310,8 @@ class DQNLearner(core.Learner, core.Saveable):
       torch = self._torch
       (o1, n1), (o0, n0) = self._net.grad_buckets()
       px, args = self._px, (self._m, self._v, self._num_steps, self._lr, 0.9, 0.999, self._adam_eps, self._eps_mode)
+      # torso bucket first (0.3 MB: one barrier round trip), then fc1 + heads (NVLink-bound).  Running the two
+      # concurrently was measured slower on 2 GPUs (0.463 vs 0.436 ms): the big kernel delays the small one
       px.adam(o0, n0, *args, 1, final_barrier=True)
       ev_conv = torch.cuda.Event()
       ev_conv.record(torch.cuda.current_stream())
@@ -327,12 +329,16 @@ class DQNLearner(core.Learner, core.Saveable):
 
   def _compute(self, uniforms=None):
     """The gradient half of a step: K1, K3, forwards, K4, backward, K2."""
+    self._stamp(0)
     self._sample(uniforms)
     self._dataset.gather_only()
     self._forwards()
     self._loss_backward()
+    self._stamp(4)
     if self._replay_client is not None:
       self._dataset.table.update_priorities_device(self._dataset.keys, self.priority)
+    self._stamp(5)
+    self._stamp(6)
 
   def _pipelined_graph(self, variant: str):
     torch = self._torch

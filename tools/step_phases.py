@@ -35,6 +35,12 @@ for _ in range(n):
 if rank == 0:
   for nm, v in zip(names, tot / n): print(f'{nm:28s} {v:8.1f} us')
 if rank == 0: print('sum', round(float((tot / n).sum()), 1), '(each stamp kernel adds ~2 us)')
-if L._px is not None: L._px.close()
+if L._px is not None:
+  import ctypes
+  st = np.zeros(8, np.int64)
+  _capi.load().b200rl_debug_dp_stamps(L._px._h, ctypes.c_void_p(st.ctypes.data))
+  print(f'rank {rank}: last exchange kernel: wait-for-grads {(st[1]-st[0])/1e3:.1f} us, reduce+adam+broadcast {(st[2]-st[1])/1e3:.1f} us, final barrier {(st[3]-st[2])/1e3:.1f} us', flush=True)
+  L.flush(); torch.cuda.synchronize()
+  L._px.close()
 server.stop()
 if world > 1: dist.destroy_process_group()
