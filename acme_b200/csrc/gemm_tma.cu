@@ -432,23 +432,24 @@ int tma_conv_wgrad(const float* x, const float* dy, float* dw, float* db, const 
 // float offset ox * stride * C, i.e. neighbouring wide pixels OVERLAP in memory (TMA strides need not be >= the
 // extent of the inner dimension).  If the driver refuses the overlapping view the rows are materialised without
 // overlap instead ([.., OW, 32], twice the bytes).
+constexpr int kRowsPerCta = 8;   // one CTA per padded row made the CTA launch rate (152 tiny CTAs per SM) the bottleneck
 __global__ void __launch_bounds__(256)
 u8_rows_to_f32_kernel(const uint8_t* __restrict__ x, float* __restrict__ out, int H, int W, int Hp, int per_row /* float4s */,
                       int wq /* float4s per wide pixel */, int src_step /* source pixels between wide pixels */, int pad_left,
-                      int pad_top) {
-  // blockIdx.x = padded row (b, hp); threads = the row's float4s (one float4 = the 4 channels of one pixel)
-  const int row = blockIdx.x, b = row / Hp, hp = row - b * Hp, ys = hp - pad_top;
-  float4* dst = reinterpret_cast<float4*>(out) + (size_t)row * per_row;
-  const bool live = ys >= 0 && ys < H;
-  const uchar4* src = reinterpret_cast<const uchar4*>(x) + ((size_t)b * H + (live ? ys : 0)) * W;
-  for (int q = blockIdx.y * blockDim.x + threadIdx.x; q < per_row; q += gridDim.y * blockDim.x) {
+                      int pad_top, int total_rows) {
+  // a CTA converts kRowsPerCta consecutive padded rows (b, hp); one float4 = the 4 channels of one pixel
+  const int row0 = blockIdx.x * kRowsPerCta;
+  const int nrows = min(kRowsPerCta, total_rows - row0);
+  for (int e = threadIdx.x; e < nrows * per_row; e += blockDim.x) {
+    const int r = e / per_row, q = e - r * per_row;
+    const int row = row0 + r, b = row / Hp, hp = row - b * Hp, ys = hp - pad_top;
     const int xs = wq == 1 ? q - pad_left : (q / wq) * src_step + (q % wq) - pad_left;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (live && xs >= 0 && xs < W) {
-      const uchar4 p = __ldg(src + xs);
+    if (ys >= 0 && ys < H && xs >= 0 && xs < W) {
+      const uchar4 p = __ldg(reinterpret_cast<const uchar4*>(x) + ((size_t)b * H + ys) * W + xs);
       v = make_float4(__fdiv_rn((float)p.x, 255.f), __fdiv_rn((float)p.y, 255.f), __fdiv_rn((float)p.z, 255.f), __fdiv_rn((float)p.w, 255.f));
     }
-    dst[q] = v;
+    reinterpret_cast<float4*>(out)[(size_t)row * per_row + q] = v;
   }
 }
 
@@ -473,9 +474,9 @@ static WideView wide_view(const b200rl_conv_geom& g, bool overlap) {
 static int wide_convert(const uint8_t* x, float* out, const b200rl_conv_geom& g, const WideView& v, bool overlap, cudaStream_t s) {
   // overlapping view: the row is the padded image itself, "wide pixel" granularity = one source pixel
   const int per_row = v.row_floats / 4, wq = overlap ? 1 : v.wide_stride / 4, step = overlap ? 1 : g.stride;
-  const int threads = per_row <= 96 ? 96 : 256;
-  u8_rows_to_f32_kernel<<<dim3(g.B * v.Hp, ceil_div(per_row, threads)), threads, 0, s>>>(x, out, g.H, g.W, v.Hp, per_row, wq, step,
-                                                                                        g.pad_left, g.pad_top);
+  const int rows = g.B * v.Hp;
+  u8_rows_to_f32_kernel<<<ceil_div(rows, kRowsPerCta), 256, 0, s>>>(x, out, g.H, g.W, v.Hp, per_row, wq, step, g.pad_left,
+                                                                    g.pad_top, rows);
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }

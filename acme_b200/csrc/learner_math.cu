@@ -712,8 +712,8 @@ extern "C" int b200rl_adam(int64_t n, float* param, const float* grad, float* m,
   B200RL_REQUIRE(n >= 0 && (eps_mode == 0 || eps_mode == 1), "bad argument");
   B200RL_REQUIRE((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "buffers must be 16-byte aligned");
   if (n == 0) return B200RL_OK;
-  static const int per_sm = getenv("B200RL_ADAM_CTAS_PER_SM") ? atoi(getenv("B200RL_ADAM_CTAS_PER_SM")) : 8;
-  int blocks = grid1d((n + 7) / 8, 256, kNumSMs * per_sm);
+  static const int per_sm = getenv("B200RL_ADAM_CTAS_PER_SM") ? atoi(getenv("B200RL_ADAM_CTAS_PER_SM")) : 8;   // 0 = one pass, no loop
+  int blocks = grid1d((n + 7) / 8, 256, per_sm > 0 ? kNumSMs * per_sm : (1 << 30));
   adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(n, param, grad, m, v, (const long long*)step_dev, lr, b1, b2, eps,
                                                     eps_mode, grad_scale_dev, (__nv_bfloat16*)bf16_shadow);
   B200RL_LAUNCH_OK();
