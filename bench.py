@@ -463,8 +463,8 @@ def run_ours(args):
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
-  ap.add_argument('--steps', type=int, default=500)
-  ap.add_argument('--warmup', type=int, default=20)
+  ap.add_argument('--steps', type=int, default=2000)
+  ap.add_argument('--warmup', type=int, default=50)
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   ap.add_argument('--precision', default=os.environ.get('B200RL_PRECISION', 'tc'), choices=['fp32', 'tc', 'bf16'],
                   help="'tc' (default; 'bf16' is an alias): tcgen05 tensor cores with tf32/bf16 operands, stated tolerance in "
