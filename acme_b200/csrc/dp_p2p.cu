@@ -90,6 +90,8 @@ __device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, con
   const float gj = __fmul_rn(g, c.gs);
   m = __fadd_rn(__fmul_rn(c.b1, m), __fmul_rn(c.omb1, gj));
   v = __fadd_rn(__fmul_rn(c.b2, v), __fmul_rn(c.omb2, __fmul_rn(gj, gj)));
+  m = fabsf(m) < 1.17549435e-38f ? 0.f : m;   // subnormal moments: see adam_one in learner_math.cu
+  v = v < 1.17549435e-38f ? 0.f : v;
   float upd;
   if (c.eps_mode == 0) upd = __fdiv_rn(__fdiv_rn(m, c.bc1), __fadd_rn(__fsqrt_rn(__fdiv_rn(v, c.bc2)), c.eps));
   else upd = __fdiv_rn(__fmul_rn(c.k1, m), __fadd_rn(__fsqrt_rn(v), c.eps));

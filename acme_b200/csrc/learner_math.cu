@@ -245,6 +245,11 @@ __device__ __forceinline__ float adam_one(float& p, float g, float& m, float& v,
   const float gj = c.gs == 1.f ? g : __fmul_rn(g, c.gs);
   m = __fadd_rn(__fmul_rn(c.b1f, m), __fmul_rn(c.omb1, gj));
   v = __fadd_rn(__fmul_rn(c.b2f, v), __fmul_rn(c.omb2, __fmul_rn(gj, gj)));
+  // Moments of (nearly) dead units decay through the subnormal range and stay there for hundreds of steps; the IEEE
+  // division / square-root sequences below take a slow path on subnormal operands (measured: the kernel went from
+  // 55 to 88 us after 3000 updates).  Flushing |m|, v < FLT_MIN to zero changes the update by < 1e-30.
+  m = fabsf(m) < 1.17549435e-38f ? 0.f : m;
+  v = v < 1.17549435e-38f ? 0.f : v;
   float upd;
   if (c.eps_mode == 0) upd = __fdiv_rn(__fdiv_rn(m, c.bc1), __fadd_rn(__fsqrt_rn(__fdiv_rn(v, c.bc2)), c.eps));
   else upd = __fdiv_rn(__fmul_rn(c.k1, m), __fadd_rn(__fsqrt_rn(v), c.eps));

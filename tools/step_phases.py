@@ -27,6 +27,8 @@ ds = replay.ReplayDataset(table, 256, seed=1 + rank)
 L = dqn.DQNLearner(net, tgt, 0.99, 0.2, 1e-3, 100, ds, replay_client=replay.Client(server), logger=loggers.NoOpLogger(), process_group=pg)
 names = ['k1 sample + k3 gather', 'forwards x3 (3 streams)', 'k4 td/loss', 'backward (2 streams)', 'k7 adam', 'k2 priorities + copy + inc']
 for _ in range(10): L.step(fetch_loss=False)
+late = int(os.environ.get('B200RL_PHASES_AFTER', '0'))   # measure after this many extra steps (drift over long runs)
+for _ in range(late): L.step(fetch_loss=False)
 tot = np.zeros(6); n = 50
 for _ in range(n):
   L.step(fetch_loss=False); torch.cuda.synchronize()
