@@ -414,7 +414,7 @@ def run_ours(args):
     if not gpu_launches:
       gpu_launches = int(lib.b200rl_launch_count() - launches0)
     kname = 'k6_network_gemm_conv (3 forwards + 1 backward, fp32 SIMT FFMA)' if precision == 0 else \
-            'k6_network_gemm_conv (3 forwards + 1 backward; tcgen05: TMA-fed kind::tf32 for conv2/conv3/fc1, kind::f16 bf16 for conv1)'
+            'k6_network_gemm_conv (3 forwards + 1 backward; tcgen05 kind::tf32, TMA-fed: im2col for the convolutions incl. conv1 on uint8 frames via fp32 row images)'
     achieved = STEP_FLOPS / net_s / 1e12 if net_s > 0 else None
     traffic = None    # dram bytes of the same kernel group from the committed `ncu --set full` capture (tensor-core mode)
     prof = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'ncu_full_r01_tc_layers_summary.json')
