@@ -1,18 +1,20 @@
-// K6, speed mode, dense layers: TMA-fed tf32 GEMM on tcgen05 (fp32 operands straight from HBM, no
-// register staging, no conversion pass, no bf16 copies).
+// K6, tensor-core mode: TMA-fed tf32 GEMM / implicit-GEMM convolution on tcgen05 (fp32 operands straight from HBM,
+// no register staging, no conversion pass, no transposed copies).
 //
-//   producer (1 thread)  cp.async.bulk.tensor.2d (TMA, 128-byte swizzle) -> 4-stage shared-memory ring,
-//                        completion by mbarrier transaction bytes
+//   producer (1 thread)  cp.async.bulk.tensor (tiled 2-D, or 4-D im2col for convolutions), 128-byte swizzle
+//                        -> 3-stage shared-memory ring, completion by mbarrier transaction bytes
 //   MMA      (1 thread)  tcgen05.mma.cta_group::1.kind::tf32  (M = 128, N = BN, K = 8 per instruction),
 //                        accumulator in TMEM; tcgen05.commit frees the stage / signals the epilogue
-//   epilogue (4 warps)   tcgen05.ld -> bias / activation / activation-derivative mask -> float4 stores
-//                        (or split-K partials)
-// An operand whose memory-contiguous direction is the reduction index is loaded K-major (box = 32 k x
-// rows); otherwise MN-major (boxes of 32 rows/columns x 32 k, the smem image is the same 128-byte
-// swizzled rows, only the instruction descriptor's major bit and the LBO/SBO strides differ), so the
+//   epilogue (4 warps)   tcgen05.ld -> per-warp slab in the drained stages -> row-wise coalesced stores with bias /
+//                        activation / activation-derivative mask (or split-K partials, or a transposed store)
+// An operand whose memory-contiguous direction is the reduction index is loaded K-major (box = 32 k x rows);
+// otherwise MN-major (boxes of 32 rows/columns x 32 k; same 128-byte swizzled rows in shared memory, but the 32-byte
+// atom flavour of the swizzle, the instruction descriptor's major bit and the LBO/SBO strides differ), so the
 // data-gradient and weight-gradient products need no transposed copies.
-// Used for linear fwd / dgrad / wgrad whenever the matrices satisfy TMA's 16-byte stride rule; the
-// accessor-fed kernel in gemm_tc.cu covers the convolutions and everything else.
+// Entry points (each returns 1 when the shapes break TMA's rules; layers_api.cu then falls back to gemm_tc.cu):
+//   tma_linear_fwd / dgrad / wgrad          dense layers
+//   tma_conv_fwd / wgrad / dgrad            NHWC fp32 activations with C % 32 == 0 (dgrad: one sub-problem per stride phase)
+//   tma_conv_fwd_u8 / wgrad_u8              first layer on uint8 frames (padded fp32 row image + overlapping wide pixels)
 #include <algorithm>
 
 #include <cuda.h>

@@ -459,9 +459,13 @@ class DQNLearner(core.Learner, core.Saveable):
     return g
 
   def _device_step(self, uniforms=None):
-    """One update on the device.  Single GPU: the whole step is one CUDA graph.  Data parallel: three graphs
-    (forwards | loss + backward | apply) with the two NCCL all-reduces issued between them, so the host
-    does 5 launches per step instead of ~50."""
+    """One update on the device.
+    * single GPU: the whole step is ONE CUDA graph (forks onto side streams inside it);
+    * data parallel with a peer exchange (default): `_pipelined_step` -- one graph per step, the optimizer half of step
+      t at the start of step t+1's graph; B200RL_DP_PIPELINE=0 keeps the exchange at the end of the same graph;
+    * data parallel over NCCL (`peer_exchange=False`): 4-5 graphs with the all-reduces issued between them (the fc1 +
+      head bucket asynchronously, overlapped with the convolution backward).
+    The first two steps of a run are eager (one-time attribute set-up inside the library, launch counting)."""
     if self._pipeline:
       self._pipelined_step(uniforms)
       return
