@@ -110,7 +110,8 @@ PROTOTYPES = {
 }
 
 ACT_NONE, ACT_RELU, ACT_ELU, ACT_TANH = 0, 1, 2, 3
-PRECISION_FP32, PRECISION_BF16 = 0, 1
+PRECISION_FP32, PRECISION_BF16 = 0, 1      # 1 = tensor-core mode (tf32 via TMA where eligible, else bf16 operands)
+PRECISION_TC = PRECISION_BF16
 
 _lib = None
 

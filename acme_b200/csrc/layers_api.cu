@@ -1,6 +1,9 @@
-// C-ABI entry points of K6: dispatch on `precision` between the fp32 SIMT path (gemm_simt.cu)
-// and the bf16 tcgen05 path (gemm_tc.cu).  There is no silent downgrade: asking for a precision
-// or shape a path does not implement is an error.
+// C-ABI entry points of K6: dispatch on `precision`.
+//   0  fp32 FFMA path (gemm_simt.cu): the 1e-5 parity mode
+//   1  tensor cores: the TMA-fed tf32 tcgen05 kernels (gemm_tma.cu) when the operands satisfy TMA's rules, else the
+//      loader-fed bf16 tcgen05 kernel (gemm_tc.cu); dense layers too small to amortise a tensor-core pipeline take
+//      the (exact) fp32 path.  Results never come from a less precise path than the one asked for, and a
+//      precision / shape no path implements is an error.
 #include "common.cuh"
 
 namespace b200rl {

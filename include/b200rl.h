@@ -177,8 +177,12 @@ int b200rl_step_increment(int64_t* step_dev, void* stream);
 /* ------------------------------------------------------------------------------------------
  * K6.  Network layers (acme/tf/networks/atari.py:36-69, duelling.py:37-59, continuous.py:37-68).
  * Activations NHWC / row-major fp32; weights [out][in] (conv: [Cout][kh][kw][Cin]) fp32.
- * precision: 0 = fp32 SIMT (parity mode, 1e-5), 1 = bf16 operands on tcgen05 tensor cores with
- * fp32 accumulation (speed mode; stated tolerance in DESIGN.md).
+ * precision: 0 = fp32 SIMT (parity mode, 1e-5); 1 = tcgen05 tensor cores with fp32 accumulation: tf32 operands
+ * fetched by TMA where the tensors satisfy its alignment rules, bf16 operands otherwise, and the exact fp32 path for
+ * dense layers too small to amortise a tensor-core pipeline (speed mode; stated tolerance in DESIGN.md).
+ * ws / ws_bytes: caller-owned scratch (split-K partial sums, column-sum partials, and for a first-layer convolution
+ * on uint8 frames in precision 1 the zero-padded fp32 row image, B * (H + pad) * (W + pad) * C * 4 bytes); one workspace
+ * per stream -- calls on different streams must not share it.
  * ------------------------------------------------------------------------------------------ */
 typedef struct b200rl_conv_geom {
   int32_t B, H, W, C;       /* input NHWC                         */
