@@ -35,6 +35,7 @@ __device__ __forceinline__ void tm_mark(int slot) {
 }
 
 constexpr int GBM = 128, GBK = 32 /* fp32 elements = 128 bytes */, G_STAGES = 3, G_THREADS = 192;
+int g_tma_dgrad_bn64 = 1;   // tools/layer_bench.py toggles it (B200RL_DGRAD_BN64)
 int g_tma_stage_mode = 0;   // 0 = heuristic, 1 = always shallow, 2 = always deep (tools/layer_bench.py)
 
 // ---- tensor maps (driver entry point fetched at run time: no link-time dependency on libcuda)
@@ -378,7 +379,10 @@ int tma_linear_dgrad(int M, int N, int K, const float* dy, int lddy, const float
                      const float* mask, int ldmask, int mask_act, void* ws, int64_t wsb, cudaStream_t s) {
   // dx[m, k] = sum_n dy[m, n] w[n, k]: A = dy K-major (reduction n contiguous), B = w MN-major (line = n, pos = k)
   if (!tma_ok(dy, lddy) || !tma_ok(w, K) || N < GBK) return 1;
-  const int BN = pick_bn(K);
+  int BN = pick_bn(K);
+  // no split-K here (its finish pass would re-read the whole output): when 128-wide tiles leave SMs idle, halve them
+  // so that two CTAs per SM overlap each other's load latency and epilogue
+  if (BN == 128 && ceil_div(M, GBM) * ceil_div(K, 128) < kNumSMs && g_tma_dgrad_bn64) BN = 64;
   CUtensorMap ma, mb;
   if (!make_map(&ma, dy, M, N, lddy, GBK, GBM, false) || !make_map(&mb, w, N, K, K, 32, GBK, true)) return 1;
   Epilogue e{dx, lddx, nullptr, 0, mask, ldmask, mask_act, nullptr, 0};
@@ -713,6 +717,7 @@ int tma_conv_dgrad(const float* dy, const float* w, float* dx, const b200rl_conv
 }  // namespace b200rl
 
 extern "C" int b200rl_debug_tma_stage_mode(int mode) { b200rl::g_tma_stage_mode = mode; return 0; }
+extern "C" int b200rl_debug_tma_dgrad_bn64(int on) { b200rl::g_tma_dgrad_bn64 = on; return 0; }
 extern "C" int b200rl_debug_tma_timeline(unsigned long long* buf_dev) {
   cudaError_t e = cudaMemcpyToSymbol(b200rl::g_tma_timeline, &buf_dev, sizeof(buf_dev));
   return e == cudaSuccess ? 0 : -2;

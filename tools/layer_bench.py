@@ -21,6 +21,7 @@ def main():
   out = {}
   mode = int(os.environ.get('B200RL_STAGE_MODE', '0'))
   _capi.load().b200rl_debug_tma_stage_mode(mode)
+  _capi.load().b200rl_debug_tma_dgrad_bn64(int(os.environ.get('B200RL_DGRAD_BN64', '1')))
   for prec in ((1,) if mode else (0, 1)):
     net = networks.DQNAtariNetwork(18, precision=prec)
     P = net.params
