@@ -440,57 +440,6 @@ duelling_head_fwd_kernel(int B, int A, const float* __restrict__ h, int ldh, con
   }
 }
 
-// Forward for H % 128 == 0 without the shared-memory staging: a warp per sample, float4 loads, the 40 KB of weights are
-// read through L1 (resident after the first warp of an SM), twice as many CTAs -- 4 samples per 128-thread CTA.
-// The staged kernel above spent most of its 11 us copying the weights into each of its 32 CTAs.
-template <int NV>
-__global__ void __launch_bounds__(128)
-duelling_head_fwd_vec_kernel(int B, int A, const float* __restrict__ h, int ldh, const float* __restrict__ wv,
-                             const float* __restrict__ bv, const float* __restrict__ wa, const float* __restrict__ ba,
-                             float* __restrict__ val, float* __restrict__ adv, float* __restrict__ q) {
-  constexpr int H = 128 * NV;
-  const int lane = threadIdx.x & 31;
-  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (b >= B) return;
-  float4 hv[NV], ha[NV];
-#pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    hv[j] = __ldg(reinterpret_cast<const float4*>(h + (size_t)b * ldh) + lane + 32 * j);
-    ha[j] = __ldg(reinterpret_cast<const float4*>(h + (size_t)b * ldh + H) + lane + 32 * j);
-  }
-  float sv = 0.f;
-#pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    const float4 w = __ldg(reinterpret_cast<const float4*>(wv) + lane + 32 * j);
-    sv = fmaf(hv[j].x, w.x, sv); sv = fmaf(hv[j].y, w.y, sv); sv = fmaf(hv[j].z, w.z, sv); sv = fmaf(hv[j].w, w.w, sv);
-  }
-  for (int d = 16; d > 0; d >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, d);
-  sv += bv[0];
-  float total = 0.f, mine = 0.f;
-  for (int a = 0; a < A; ++a) {
-    const float4* w4 = reinterpret_cast<const float4*>(wa + (size_t)a * H);
-    float s = 0.f;
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const float4 w = __ldg(w4 + lane + 32 * j);
-      s = fmaf(ha[j].x, w.x, s); s = fmaf(ha[j].y, w.y, s); s = fmaf(ha[j].z, w.z, s); s = fmaf(ha[j].w, w.w, s);
-    }
-    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-    s += ba[a];
-    total += s;
-    if (lane == (a & 31)) mine = s;
-    if (A > 32 && lane == 0) adv[(size_t)b * A + a] = s;
-  }
-  const float mean = total / (float)A;
-  if (lane == 0) val[b] = sv;
-  if (A <= 32) {
-    if (lane < A) { adv[(size_t)b * A + lane] = mine; q[(size_t)b * A + lane] = sv + (mine - mean); }
-  } else {
-    __syncwarp();
-    for (int a = lane; a < A; a += 32) q[(size_t)b * A + a] = sv + (adv[(size_t)b * A + a] - mean);
-  }
-}
-
 // backward, part 1 (thread per sample x 4 hidden units): dval = sum_a dq, dadv = dq - mean(dq), and
 // dh = [dval * wv, dadv @ wa] * relu'(h).  The (A+1) x H weights are 40 KB: they stay in L1/L2, the dq row is a
 // warp-wide broadcast load.
@@ -847,18 +796,6 @@ extern "C" int b200rl_duelling_head_fwd(int32_t B, int32_t A, int32_t H, const f
   const size_t smem = (size_t)(A + 1) * H * 4;
   B200RL_REQUIRE(smem <= 200 * 1024 && H % 4 == 0, "duelling head weights do not fit in shared memory");
   if (int rc = ensure_head_attrs()) return rc;
-  const bool vec = H % 128 == 0 && H <= 512 && ldh % 4 == 0 && (((uintptr_t)h | (uintptr_t)wv | (uintptr_t)wa) & 15) == 0;
-  if (vec) {
-    const int vb = ceil_div(B * 32, 128);
-    switch (H / 128) {
-      case 4: duelling_head_fwd_vec_kernel<4><<<vb, 128, 0, st>>>(B, A, h, ldh, wv, bv, wa, ba, value, adv, q); break;
-      case 3: duelling_head_fwd_vec_kernel<3><<<vb, 128, 0, st>>>(B, A, h, ldh, wv, bv, wa, ba, value, adv, q); break;
-      case 2: duelling_head_fwd_vec_kernel<2><<<vb, 128, 0, st>>>(B, A, h, ldh, wv, bv, wa, ba, value, adv, q); break;
-      default: duelling_head_fwd_vec_kernel<1><<<vb, 128, 0, st>>>(B, A, h, ldh, wv, bv, wa, ba, value, adv, q); break;
-    }
-    B200RL_LAUNCH_OK();
-    return B200RL_OK;
-  }
   switch (H) {
     case 512: duelling_head_fwd_kernel<16><<<blocks, 256, smem, st>>>(B, A, h, ldh, wv, bv, wa, ba, value, adv, q); break;
     case 256: duelling_head_fwd_kernel<8><<<blocks, 256, smem, st>>>(B, A, h, ldh, wv, bv, wa, ba, value, adv, q); break;
