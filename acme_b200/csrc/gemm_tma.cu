@@ -127,6 +127,9 @@ struct ConvA {
   int enabled;
   int C, kw, OW, OH, stride_w, stride_h, pad_left, pad_top, taps;
 };
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -172,6 +175,8 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const int nkb = min(total_kblocks, kb_begin + kblocks_per_split) - kb_begin;
 
   if (tid == 0) {
+    prefetch_tensormap(&map_a);   // the descriptor fetch otherwise sits in front of the first load
+    prefetch_tensormap(&map_b);
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
     mbar_init(&bar_done, 1);
@@ -588,6 +593,8 @@ tma_conv_dgrad_kernel(const __grid_constant__ DgradMaps maps, const __grid_const
   const int nkb = ph.Ty * ph.Tx * cb;
 
   if (tid == 0) {
+    prefetch_tensormap(&maps.m[phase]);
+    prefetch_tensormap(&map_w);
 #pragma unroll
     for (int s = 0; s < G_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
     mbar_init(&bar_done, 1);
