@@ -74,3 +74,39 @@ def test_counter_hierarchy():
   fresh = counting.Counter()
   fresh.restore(state)
   assert fresh.get_counts() == parent.get_counts()
+
+
+# ---- acme/utils/counting_test.py:46-86 restated against acme_b200.counting
+def test_counter_threading():
+  import threading
+  from acme_b200 import counting
+  counter = counting.Counter()
+  n = 10
+  gate = threading.Barrier(n)
+
+  def add():
+    gate.wait()
+    counter.increment(foo=1)
+  threads = [threading.Thread(target=add) for _ in range(n)]
+  for t in threads:
+    t.start()
+  for t in threads:
+    t.join()
+  assert counter.get_counts()['foo'] == n
+
+
+def test_counter_caching():
+  from acme_b200 import counting
+  parent = counting.Counter()
+  counter = counting.Counter(parent, time_delta=0.)
+  counter.increment(foo=12)
+  assert parent.get_counts() == counter.get_counts()
+
+
+def test_counter_shared_counts():
+  from acme_b200 import counting
+  parent = counting.Counter()
+  child1 = counting.Counter(parent, 'child1')
+  child2 = counting.Counter(parent, 'child2')
+  child1.increment(foo=1)
+  assert child2.increment(foo=2) == {'child1_foo': 1, 'child2_foo': 2}
