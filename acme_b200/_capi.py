@@ -98,6 +98,8 @@ PROTOTYPES = {
     'b200rl_concat2': (c_int, [c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     'b200rl_split_second': (c_int, [c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     'b200rl_workspace_bytes': (c_i64, [c_i64]),
+    'b200rl_conv2d_rows_bytes': (c_i64, [C.POINTER(ConvGeom)]),
+    'b200rl_conv2d_rows_from_u8': (c_int, [c_vp, C.POINTER(ConvGeom), c_vp, c_i64, c_vp]),
     'b200rl_dp_create': (c_int, [C.POINTER(c_vp), C.POINTER(DpCfg)]),
     'b200rl_dp_destroy': (c_int, [c_vp]),
     'b200rl_dp_buffers': (c_int, [c_vp, C.POINTER(c_vp), C.POINTER(c_vp)]),

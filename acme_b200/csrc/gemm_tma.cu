@@ -503,52 +503,75 @@ static bool make_wide_map(CUtensorMap* m, const float* xw, const b200rl_conv_geo
              CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
-// picks the view (overlapping first), converts the frames into ws and builds the A map; *used = bytes of ws taken
-static int wide_prepare(const uint8_t* x, const b200rl_conv_geom& g, void* ws, int64_t wsb, int pixels, bool mn_major,
-                        CUtensorMap* ma, int64_t* used, cudaStream_t s) {
-  if (!wide_eligible(g) || !ws || (((uintptr_t)ws) & 127) != 0) return 1;
+// Size of the row image of `g` (0: geometry not eligible).  The larger (non-overlapping) layout is reported so that a
+// buffer of this size works whichever view the driver accepts.
+int64_t tma_rows_bytes(const b200rl_conv_geom& g) {
+  if (!wide_eligible(g)) return 0;
+  return std::max(wide_view(g, true).bytes, wide_view(g, false).bytes);
+}
+// Picks the view (overlapping first; remembered process-wide) and converts the frames into `rows`.
+int tma_rows_from_u8(const uint8_t* x, const b200rl_conv_geom& g, float* rows, int64_t bytes, cudaStream_t s) {
+  if (!wide_eligible(g) || !rows || (((uintptr_t)rows) & 127) != 0) return 1;
   for (int attempt = 0; attempt < 2; ++attempt) {
     const bool overlap = g_wide_overlap != 0;
     const WideView v = wide_view(g, overlap);
-    if (v.bytes > wsb) return 1;
-    if (make_wide_map(ma, (const float*)ws, g, v, pixels, mn_major)) {
-      *used = (v.bytes + 1023) & ~(int64_t)1023;
-      return wide_convert(x, (float*)ws, g, v, overlap, s);
-    }
+    if (v.bytes > bytes) return 1;
+    CUtensorMap probe;
+    if (make_wide_map(&probe, rows, g, v, GBM, false)) return wide_convert(x, rows, g, v, overlap, s);
     if (!overlap) return 1;
     g_wide_overlap = 0;
   }
   return 1;
 }
+static int64_t rows_used(const b200rl_conv_geom& g) {
+  return (wide_view(g, g_wide_overlap != 0).bytes + 1023) & ~(int64_t)1023;
+}
 
+// first-layer convolution / weight gradient on a row image built by tma_rows_from_u8 (same geometry)
+int tma_conv_fwd_rows(const float* rows, const float* w, const float* bias, float* y, const b200rl_conv_geom& g, int act,
+                      void* ws, int64_t wsb, cudaStream_t s) {
+  const int M = g.B * g.OH * g.OW, K = g.kh * g.kw * g.C;
+  if (!wide_eligible(g) || !tma_ok(w, K)) return 1;
+  CUtensorMap ma, mb;
+  const int BN = pick_bn(g.Cout);
+  if (!make_map(&mb, w, g.Cout, K, K, GBK, BN, false)) return 1;
+  if (!make_wide_map(&ma, rows, g, wide_view(g, g_wide_overlap != 0), GBM, false)) return 1;
+  Epilogue e{y, g.Cout, bias, act, nullptr, 0, 0, nullptr, 0};
+  ConvA conv{1, GBK, 1, g.OW, g.OH, 1, g.stride, 0, 0, g.kh};
+  return launch_tma<false, false>(ma, mb, e, M, g.Cout, K, BN, ws, wsb, s, conv);
+}
+int tma_conv_wgrad_rows(const float* rows, const float* dy, float* dw, float* db, const b200rl_conv_geom& g, void* ws,
+                        int64_t wsb, cudaStream_t s) {
+  const int M = g.B * g.OH * g.OW, K = g.kh * g.kw * g.C;
+  if (!wide_eligible(g) || !tma_ok(dy, g.Cout) || g.Cout % 32 != 0 || M < GBK) return 1;
+  CUtensorMap ma, mb;
+  const int BN = pick_bn(g.Cout);
+  if (!make_map(&mb, dy, M, g.Cout, g.Cout, 32, GBK, true)) return 1;
+  if (!make_wide_map(&ma, rows, g, wide_view(g, g_wide_overlap != 0), GBK, true)) return 1;
+  Epilogue e{dw, K, nullptr, 0, nullptr, 0, 0, nullptr, 1};
+  ConvA conv{1, GBK, 1, g.OW, g.OH, 1, g.stride, 0, 0, g.kh};
+  int rc = launch_tma<true, true>(ma, mb, e, K, g.Cout, M, BN, ws, wsb, s, conv);
+  if (rc) return rc;
+  if (db) return launch_colsum(M, g.Cout, dy, g.Cout, db, ws, wsb, s);
+  return B200RL_OK;
+}
+
+// uint8 frames: the row image goes to the head of the workspace, then as above
 int tma_conv_fwd_u8(const uint8_t* x, const float* w, const float* bias, float* y, const b200rl_conv_geom& g, int act,
                     void* ws, int64_t wsb, cudaStream_t s) {
   const int M = g.B * g.OH * g.OW, K = g.kh * g.kw * g.C;
-  if (!tma_ok(w, K) || (int64_t)M * g.Cout * 4 < 131072) return 1;
-  CUtensorMap ma, mb;
-  int64_t used = 0;
-  const int BN = pick_bn(g.Cout);
-  if (!make_map(&mb, w, g.Cout, K, K, GBK, BN, false)) return 1;
-  if (int rc = wide_prepare(x, g, ws, wsb, GBM, false, &ma, &used, s)) return rc;
-  Epilogue e{y, g.Cout, bias, act, nullptr, 0, 0, nullptr, 0};
-  ConvA conv{1, GBK, 1, g.OW, g.OH, 1, g.stride, 0, 0, g.kh};
-  return launch_tma<false, false>(ma, mb, e, M, g.Cout, K, BN, (char*)ws + used, wsb - used, s, conv);
+  if (!tma_ok(w, K) || (int64_t)M * g.Cout * 4 < 131072 || !ws) return 1;
+  if (int rc = tma_rows_from_u8(x, g, (float*)ws, wsb, s)) return rc;
+  const int64_t used = rows_used(g);
+  return tma_conv_fwd_rows((const float*)ws, w, bias, y, g, act, (char*)ws + used, wsb - used, s);
 }
 int tma_conv_wgrad_u8(const uint8_t* x, const float* dy, float* dw, float* db, const b200rl_conv_geom& g, void* ws, int64_t wsb,
                       cudaStream_t s) {
-  const int M = g.B * g.OH * g.OW, K = g.kh * g.kw * g.C;
-  if (!tma_ok(dy, g.Cout) || g.Cout % 32 != 0 || (int64_t)M * g.Cout * 4 < 131072 || M < GBK) return 1;
-  CUtensorMap ma, mb;
-  int64_t used = 0;
-  const int BN = pick_bn(g.Cout);
-  if (!make_map(&mb, dy, M, g.Cout, g.Cout, 32, GBK, true)) return 1;
-  if (int rc = wide_prepare(x, g, ws, wsb, GBK, true, &ma, &used, s)) return rc;
-  Epilogue e{dw, K, nullptr, 0, nullptr, 0, 0, nullptr, 1};
-  ConvA conv{1, GBK, 1, g.OW, g.OH, 1, g.stride, 0, 0, g.kh};
-  int rc = launch_tma<true, true>(ma, mb, e, K, g.Cout, M, BN, (char*)ws + used, wsb - used, s, conv);
-  if (rc) return rc;
-  if (db) return launch_colsum(M, g.Cout, dy, g.Cout, db, (char*)ws + used, wsb - used, s);
-  return B200RL_OK;
+  const int M = g.B * g.OH * g.OW;
+  if (!tma_ok(dy, g.Cout) || g.Cout % 32 != 0 || (int64_t)M * g.Cout * 4 < 131072 || M < GBK || !ws) return 1;
+  if (int rc = tma_rows_from_u8(x, g, (float*)ws, wsb, s)) return rc;
+  const int64_t used = rows_used(g);
+  return tma_conv_wgrad_rows((const float*)ws, dy, dw, db, g, (char*)ws + used, wsb - used, s);
 }
 
 // ---- conv data gradient as an implicit GEMM over dy, one sub-problem per stride phase.

@@ -48,6 +48,12 @@ int tma_conv_fwd_u8(const uint8_t* x, const float* w, const float* bias, float* 
                     void* ws, int64_t wsb, cudaStream_t s);
 int tma_conv_wgrad_u8(const uint8_t* x, const float* dy, float* dw, float* db, const b200rl_conv_geom& g, void* ws, int64_t wsb,
                       cudaStream_t s);
+int64_t tma_rows_bytes(const b200rl_conv_geom& g);
+int tma_rows_from_u8(const uint8_t* x, const b200rl_conv_geom& g, float* rows, int64_t bytes, cudaStream_t s);
+int tma_conv_fwd_rows(const float* rows, const float* w, const float* bias, float* y, const b200rl_conv_geom& g, int act,
+                      void* ws, int64_t wsb, cudaStream_t s);
+int tma_conv_wgrad_rows(const float* rows, const float* dy, float* dw, float* db, const b200rl_conv_geom& g, void* ws,
+                        int64_t wsb, cudaStream_t s);
 }  // namespace b200rl
 
 using namespace b200rl;
@@ -79,6 +85,12 @@ extern "C" int b200rl_conv2d_fwd(const void* x, int x_u8, const float* w, const 
                                  const b200rl_conv_geom* g, int act, int precision, void* ws, int64_t wsb, void* stream) {
   B200RL_REQUIRE(x && w && y, "null argument");
   if (int rc = check_geom(g)) return rc;
+  if (x_u8 == 2) {   // a row image from b200rl_conv2d_rows_from_u8
+    B200RL_REQUIRE(precision == 1, "row images are a tensor-core-mode input");
+    int rc = tma_conv_fwd_rows((const float*)x, w, bias, y, *g, act, ws, wsb, as_stream(stream));
+    B200RL_REQUIRE(rc != 1, "geometry / alignment not supported for a row-image convolution");
+    return rc;
+  }
   if (precision == 1 && g_use_tma) {
     int rc = x_u8 ? tma_conv_fwd_u8((const uint8_t*)x, w, bias, y, *g, act, ws, wsb, as_stream(stream))
                   : tma_conv_fwd((const float*)x, w, bias, y, *g, act, ws, wsb, as_stream(stream));
@@ -91,6 +103,12 @@ extern "C" int b200rl_conv2d_wgrad(const void* x, int x_u8, const float* dy, flo
                                    const b200rl_conv_geom* g, int precision, void* ws, int64_t wsb, void* stream) {
   B200RL_REQUIRE(x && dy && dw, "null argument");
   if (int rc = check_geom(g)) return rc;
+  if (x_u8 == 2) {
+    B200RL_REQUIRE(precision == 1, "row images are a tensor-core-mode input");
+    int rc = tma_conv_wgrad_rows((const float*)x, dy, dw, db, *g, ws, wsb, as_stream(stream));
+    B200RL_REQUIRE(rc != 1, "geometry / alignment not supported for a row-image weight gradient");
+    return rc;
+  }
   if (precision == 1 && g_use_tma) {
     int rc = x_u8 ? tma_conv_wgrad_u8((const uint8_t*)x, dy, dw, db, *g, ws, wsb, as_stream(stream))
                   : tma_conv_wgrad((const float*)x, dy, dw, db, *g, ws, wsb, as_stream(stream));
@@ -99,6 +117,19 @@ extern "C" int b200rl_conv2d_wgrad(const void* x, int x_u8, const float* dy, flo
   PRECISION_SWITCH(simt_conv_wgrad(x, x_u8, dy, dw, db, *g, ws, wsb, as_stream(stream)),
                    tc_conv_wgrad(x, x_u8, dy, dw, db, *g, ws, wsb, as_stream(stream)));
 }
+extern "C" int64_t b200rl_conv2d_rows_bytes(const b200rl_conv_geom* g) {
+  if (!g || check_geom(g)) return 0;
+  return tma_rows_bytes(*g);
+}
+extern "C" int b200rl_conv2d_rows_from_u8(const void* x_u8, const b200rl_conv_geom* g, float* rows, int64_t rows_bytes,
+                                          void* stream) {
+  B200RL_REQUIRE(x_u8 && rows, "null argument");
+  if (int rc = check_geom(g)) return rc;
+  int rc = tma_rows_from_u8((const uint8_t*)x_u8, *g, rows, rows_bytes, as_stream(stream));
+  B200RL_REQUIRE(rc != 1, "geometry not eligible for a row image, buffer too small or not 128-byte aligned");
+  return rc;
+}
+
 extern "C" int b200rl_conv2d_dgrad(const float* dy, const float* w, float* dx, const b200rl_conv_geom* g,
                                    const float* mask_y, int mask_act, int precision, void* ws, int64_t wsb, void* stream) {
   B200RL_REQUIRE(dy && w && dx, "null argument");

@@ -157,9 +157,23 @@ class DQNLearner(core.Learner, core.Saveable):
       start.record(main)
       for s in self._side[:2]:
         s.wait_event(start)
+      # uint8 frames in tensor-core mode: one fp32 row image per observation batch serves every pass over it
+      # (o_t: target + online forward; o_tm1: online forward + conv1's weight gradient)
+      shared = hasattr(net, 'prepare_frames') and os.environ.get('B200RL_SHARED_ROWS', '1') == '1'
+      rows_t = None
+      self._rows_tm1 = None
       with torch.cuda.stream(self._side[0]):
-        tgt.lane(1).forward(o_t, self._bufs_tgt)                 # learning.py:124
+        if shared:
+          rows_t = net.prepare_frames(o_t, 't')
+          if rows_t is not None:
+            rows_ready = torch.cuda.Event()
+            rows_ready.record(self._side[0])
+            self._side[1].wait_event(rows_ready)
+        tkw = dict(rows=rows_t) if rows_t is not None else {}
+        tgt.lane(1).forward(o_t, self._bufs_tgt, **tkw)          # learning.py:124
       tgt.lane(0)
+      if shared:
+        self._rows_tm1 = net.prepare_frames(o_tm1, 'tm1')
       hook = None
       if self._params_ready is not None:
         # pipelined exchange: the torso's parameters (a 0.3 MB bucket, exchanged first) must have landed before the
@@ -171,13 +185,16 @@ class DQNLearner(core.Learner, core.Saveable):
         hook = lambda: torch.cuda.current_stream().wait_event(ev_tail)
       kw = dict(before_fc1=hook) if hook is not None else {}
       with torch.cuda.stream(self._side[1]):
-        net.lane(2).forward(o_t, self._bufs_sel, **kw)           # learning.py:125
+        net.lane(2).forward(o_t, self._bufs_sel, **kw, **tkw)    # learning.py:125
+      if self._rows_tm1 is not None:
+        kw = dict(kw, rows=self._rows_tm1)
       net.lane(0).forward(o_tm1, self._bufs_train, **kw)         # learning.py:123
       for s in self._side[:2]:
         done = torch.cuda.Event()
         done.record(s)
         main.wait_event(done)
     else:
+      self._rows_tm1 = None
       net.forward(o_tm1, self._bufs_train)                       # learning.py:123
       tgt.forward(o_t, self._bufs_tgt)                           # learning.py:124
       net.forward(o_t, self._bufs_sel)                           # learning.py:125
@@ -204,13 +221,18 @@ class DQNLearner(core.Learner, core.Saveable):
           self._wmax_done = torch.cuda.Event()
           self._wmax_done.record(aux)
 
+  def _rows_kw(self):
+    rows = getattr(self, '_rows_tm1', None)
+    return dict(rows=rows) if rows is not None else {}
+
   def _loss_backward(self, part: str = 'all'):
     """K4 (learning.py:127-154) and the backward pass through net(o_tm1).  `part` lets the data-parallel
     step cut the backward in two ('dense' = loss + head + fc1, 'conv' = the torso) so that the all-reduce
     of the fc1/head gradients (99% of the bytes) overlaps the convolution backward."""
     ds, net = self._dataset, self._net
     if part == 'conv':
-      net.backward_conv_part(self._obs_view(ds.o_tm1), self._bufs_train, self._gbufs, self._side[0])
+      net.backward_conv_part(self._obs_view(ds.o_tm1), self._bufs_train, self._gbufs, self._side[0],
+                             **self._rows_kw())
       return
     st = _capi.current_stream()
     o_tm1 = self._obs_view(ds.o_tm1)
@@ -231,7 +253,7 @@ class DQNLearner(core.Learner, core.Saveable):
       # runs on a third stream underneath the latency-bound convolution backward
       net.backward_dense_part(self._bufs_train, self._gbufs, self.dq, self._side[0])
       self._adam_tail_async()
-      net.backward_conv_part(o_tm1, self._bufs_train, self._gbufs, self._side[0])
+      net.backward_conv_part(o_tm1, self._bufs_train, self._gbufs, self._side[0], **self._rows_kw())
     elif self._concurrent and self._early_tail_now:
       torch = self._torch
       net.backward_dense_part(self._bufs_train, self._gbufs, self.dq, self._side[0])
@@ -245,9 +267,9 @@ class DQNLearner(core.Learner, core.Saveable):
                       final_barrier=False)
         self._early_done = torch.cuda.Event()
         self._early_done.record(side)
-      net.backward_conv_part(o_tm1, self._bufs_train, self._gbufs, self._side[0])
+      net.backward_conv_part(o_tm1, self._bufs_train, self._gbufs, self._side[0], **self._rows_kw())
     elif self._concurrent:
-      net.backward(o_tm1, self._bufs_train, self._gbufs, self.dq, side_stream=self._side[0])
+      net.backward(o_tm1, self._bufs_train, self._gbufs, self.dq, side_stream=self._side[0], **self._rows_kw())
     else:
       net.backward(o_tm1, self._bufs_train, self._gbufs, self.dq)
 

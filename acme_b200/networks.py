@@ -253,7 +253,26 @@ class DQNAtariNetwork(Network):
       g[f'dy{i}'] = f(B, oh, oh, co)
     return g
 
-  def forward(self, obs, bufs, before_fc1=None) -> 'torch.Tensor':
+  def prepare_frames(self, obs, slot: str = 'x'):
+    """uint8 frames -> the fp32 row image that first-layer calls accept (`b200rl_conv2d_rows_from_u8`), built ONCE for all
+    the passes over the same frames (two networks on o_t; forward + weight gradient on o_tm1).  None when not applicable
+    (fp32 mode, float frames, geometry not eligible): callers then pass the frames themselves."""
+    import ctypes
+    import torch
+    if self.precision != _capi.PRECISION_BF16 or obs.dtype != torch.uint8:
+      return None
+    B = obs.shape[0]
+    cache = self.__dict__.setdefault('_rows', {})
+    if (slot, B) not in cache:
+      nbytes = int(_capi.load().b200rl_conv2d_rows_bytes(ctypes.byref(self.geom(0, B))))
+      cache[(slot, B)] = (torch.empty(nbytes, dtype=torch.uint8, device=obs.device) if nbytes > 0 else None)
+    buf = cache[(slot, B)]
+    if buf is None:
+      return None
+    _capi.call('b200rl_conv2d_rows_from_u8', obs.data_ptr(), self.geom(0, B), buf.data_ptr(), buf.numel(), _capi.current_stream())
+    return buf
+
+  def forward(self, obs, bufs, before_fc1=None, rows=None) -> 'torch.Tensor':
     """obs: uint8 or float32 [B, H, W, C] (NHWC).  uint8 is read as float32(x)/255.  `before_fc1` (optional callable)
     runs after the torso has been issued and before the first dense layer: the pipelined data-parallel learner makes
     the stream wait there for the fc1 + head parameters, which arrive while the convolutions run."""
@@ -261,6 +280,8 @@ class DQNAtariNetwork(Network):
     B, P, st = bufs['B'], self.params, _capi.current_stream()
     ws, wsb = self.ws
     x, x_u8 = obs.data_ptr(), int(obs.dtype == torch.uint8)
+    if rows is not None:              # the frames' row image from prepare_frames()
+      x, x_u8 = rows.data_ptr(), 2
     for i in range(3):
       y = bufs[f'y{i + 1}']
       g = self.geom(i, B)
@@ -275,15 +296,16 @@ class DQNAtariNetwork(Network):
                P.p('a2.b'), bufs['val'].data_ptr(), bufs['adv'].data_ptr(), bufs['q'].data_ptr(), st)
     return bufs['q']
 
-  def backward(self, obs, bufs, gbufs, dq, side_stream=None):
-    """Accumulates nothing: overwrites params.grad with d(loss)/d(params) given dq [B, A].
+  def backward(self, obs, bufs, gbufs, dq, side_stream=None, rows=None):
+    """Accumulates nothing: overwrites params.grad with d(loss)/d(params) given dq [B, A].  `rows`: the row image of
+    `obs` from prepare_frames(), if the caller has one.
 
     With `side_stream`, the weight-gradient GEMMs of fc1 / conv3 / conv2 run on it (workspace lane 1)
     concurrently with the data-gradient chain on the current stream: the two are independent once a
     layer's dy exists, and each kernel alone is too latency-bound to fill the machine."""
     import torch
     if side_stream is not None:
-      return self._backward_two_streams(obs, bufs, gbufs, dq, side_stream)
+      return self._backward_two_streams(obs, bufs, gbufs, dq, side_stream, rows)
     B, P, st = bufs['B'], self.params, _capi.current_stream()
     ws, wsb = self.ws
     h = bufs['h']
@@ -300,6 +322,8 @@ class DQNAtariNetwork(Network):
       dy = gbufs[f'dy{i + 1}'].data_ptr()
       if i > 0:
         x, x_u8 = bufs[f'y{i}'].data_ptr(), 0
+      elif rows is not None:
+        x, x_u8 = rows.data_ptr(), 2
       else:
         x, x_u8 = obs.data_ptr(), int(obs.dtype == torch.uint8)
       _capi.call('b200rl_conv2d_wgrad', x, x_u8, dy, P.g(f'conv{i + 1}.w'), P.g(f'conv{i + 1}.b'), g,
@@ -309,9 +333,9 @@ class DQNAtariNetwork(Network):
                    bufs[f'y{i}'].data_ptr(), ACT_RELU, self.precision, ws, wsb, st)
 
 
-  def _backward_two_streams(self, obs, bufs, gbufs, dq, side):
+  def _backward_two_streams(self, obs, bufs, gbufs, dq, side, rows=None):
     self.backward_dense_part(bufs, gbufs, dq, side)
-    self.backward_conv_part(obs, bufs, gbufs, side)
+    self.backward_conv_part(obs, bufs, gbufs, side, rows)
 
   def grad_buckets(self):
     """(offset, count) in floats of the gradient regions that become final after backward_dense_part
@@ -344,7 +368,7 @@ class DQNAtariNetwork(Network):
     ev.record(side)
     main.wait_event(ev)
 
-  def backward_conv_part(self, obs, bufs, gbufs, side):
+  def backward_conv_part(self, obs, bufs, gbufs, side, rows=None):
     """The three convolutions: weight gradients on `side`, data gradients on the current stream."""
     import torch
     B, P = bufs['B'], self.params
@@ -368,6 +392,8 @@ class DQNAtariNetwork(Network):
                    bufs[f'y{i}'].data_ptr(), ACT_RELU, self.precision, ws, wsb, _capi.current_stream())
       else:   # conv1 has no data gradient: its weight gradient finishes the main chain
         x, x_u8 = obs.data_ptr(), int(obs.dtype == torch.uint8)
+        if rows is not None:
+          x, x_u8 = rows.data_ptr(), 2
         ws, wsb = self.ws
         _capi.call('b200rl_conv2d_wgrad', x, x_u8, dy, P.g('conv1.w'), P.g('conv1.b'), g, self.precision, ws, wsb,
                    _capi.current_stream())

@@ -196,7 +196,16 @@ typedef struct b200rl_conv_geom {
 #define B200RL_ACT_ELU 2
 #define B200RL_ACT_TANH 3
 
-/* y = act(conv(x, w) + b).  x_u8 != 0: x is uint8 and is read as float(x)/255 (atari_wrapper.py:303). */
+/* Row images.  In precision 1 a first-layer convolution on uint8 frames (C = 4, kw * C = 32: the Atari torso,
+ * networks/atari.py:44) first rewrites the frames as zero-padded fp32 rows float(x)/255 (atari_wrapper.py:303-304).
+ * A caller that convolves the same frames several times (two networks on o_t; forward and weight gradient on o_tm1:
+ * dqn/learning.py:123-125,147) builds that image once and passes it as x with x_u8 = 2.
+ * rows_bytes: size of the image for geometry g, 0 if g is not eligible (then pass the uint8 frames). */
+int64_t b200rl_conv2d_rows_bytes(const b200rl_conv_geom* g);
+int b200rl_conv2d_rows_from_u8(const void* x_u8, const b200rl_conv_geom* g, float* rows, int64_t rows_bytes,
+                               void* stream);
+/* y = act(conv(x, w) + b).  x_u8 = 1: x is uint8 and is read as float(x)/255 (atari_wrapper.py:303); x_u8 = 2: x is
+ * the row image of the frames (precision 1 only). */
 int b200rl_conv2d_fwd(const void* x, int x_u8, const float* w, const float* bias, float* y,
                       const b200rl_conv_geom* g, int act, int precision, void* ws, int64_t ws_bytes,
                       void* stream);

@@ -233,6 +233,19 @@ def test_conv_fwd_wgrad_dgrad_vs_torch_cpu(H, C, k, s, Cout, u8, B, precision):
              ws.data_ptr(), ws.numel(), _capi.current_stream())
   close(dw.cpu().numpy().transpose(1, 2, 3, 0), wt.grad.numpy(), name='conv wgrad', **tol(precision, atol_scale=2e-6))
   close(db.cpu().numpy(), bt.grad.numpy(), atol_scale=2e-6, name='conv bias grad')
+  if u8 and precision == 1:
+    # the same frames through a shared row image (x_u8 = 2): identical kernels, identical bits
+    import ctypes
+    nbytes = int(_capi.load().b200rl_conv2d_rows_bytes(ctypes.byref(g)))
+    assert nbytes > 0
+    rows = empty(nbytes, dtype=torch.uint8)
+    _capi.call('b200rl_conv2d_rows_from_u8', xd.data_ptr(), g, rows.data_ptr(), nbytes, _capi.current_stream())
+    y2, dw2, db2 = empty(B, OH, OH, Cout), empty(Cout, k, k, C), empty(Cout)
+    _capi.call('b200rl_conv2d_fwd', rows.data_ptr(), 2, w_ohwi.data_ptr(), dev(bias).data_ptr(), y2.data_ptr(), g,
+               _capi.ACT_RELU, precision, ws.data_ptr(), ws.numel(), _capi.current_stream())
+    _capi.call('b200rl_conv2d_wgrad', rows.data_ptr(), 2, dy_pre.data_ptr(), dw2.data_ptr(), db2.data_ptr(), g, precision,
+               ws.data_ptr(), ws.numel(), _capi.current_stream())
+    assert torch.equal(y2, y) and torch.equal(dw2, dw) and torch.equal(db2, db)
   if C % 4 == 0 and not u8:
     dx = empty(B, H, H, C)
     _capi.call('b200rl_conv2d_dgrad', dy_pre.data_ptr(), w_ohwi.data_ptr(), dx.data_ptr(), g, None, 0, precision,
