@@ -81,6 +81,15 @@ class _Packer:
     self.single = len(self.leaves) == 1 and not tree.is_nest(spec_nest)
 
   def pack(self, value_nest) -> np.ndarray:
+    if self.single:
+      # one leaf (the usual observation / action): hand the array's own bytes to the C layer, which copies them into
+      # pinned staging during the call -- no intermediate row
+      shape, dt, _, n = self.leaves[0]
+      a = np.asarray(value_nest, dtype=dt)
+      if a.shape != shape:
+        raise ValueError(f'expected shape {shape}, got {a.shape}')
+      if n and a.flags.c_contiguous:
+        return a.reshape(-1).view(np.uint8)
     row = np.zeros(max(self.nbytes, 1), np.uint8)
     vals = tree.flatten(value_nest)
     if len(vals) != len(self.leaves):
@@ -289,6 +298,7 @@ class Writer:
     self._client = client
     self.max_sequence_length = max_sequence_length
     self._ids: Dict[str, int] = {}
+    self._started = set()      # tables that already hold this episode's first observation
     self.closed = False
 
   def _wid(self, table: Table) -> int:
@@ -304,11 +314,14 @@ class Writer:
       raise RuntimeError('writer is closed')
     for name in (tables or self._client.server.tables):
       t = self._client.server.tables[name]
-      obs = t.obs_packer.pack(observation)
+      # the ring stores every observation once: `observation` is only needed for the first step of an episode
+      # (later it is the previous call's next_observation, already in the ring; the C layer ignores the pointer)
+      obs = None if name in self._started else t.obs_packer.pack(observation)
       nxt = t.obs_packer.pack(next_observation)
       act = t.act_packer.pack((action, extras) if t.has_extras else action)
-      _capi.call('b200rl_writer_append', t.handle, self._wid(t), obs.ctypes.data, act.ctypes.data,
-                 float(np.float32(reward)), float(np.float32(discount)), nxt.ctypes.data)
+      _capi.call('b200rl_writer_append', t.handle, self._wid(t), None if obs is None else obs.ctypes.data,
+                 act.ctypes.data, float(np.float32(reward)), float(np.float32(discount)), nxt.ctypes.data)
+      self._started.add(name)
 
   def create_item(self, table: str, num_timesteps: int, priority: float) -> int:
     if self.closed:
