@@ -85,6 +85,8 @@ class SumTree:
     """Sequential 'last wins' scatter + recompute of the touched ancestors."""
     positions = np.asarray(positions, dtype=np.int64)
     weights = np.asarray(weights, dtype=_f32)
+    if positions.size == 0:
+      return
     for p, w in zip(positions, weights):
       self.levels[self.L][p] = w
     touched = np.unique(positions)

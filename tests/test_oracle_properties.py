@@ -222,3 +222,68 @@ def test_oracle_conv_is_torch_conv_with_explicit_asymmetric_padding():
   ref = F.conv2d(xp, w.permute(3, 2, 0, 1), b, stride=2).permute(0, 2, 3, 1)
   assert tuple(y.shape) == (2, 11, 11, 16)
   torch.testing.assert_close(y, ref, rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------ the ring-of-steps table against materialised transitions
+def _episodes(rng, n_eps, obs_dim=3):
+  eps = []
+  for _ in range(n_eps):
+    T = int(rng.integers(2, 12))
+    eps.append(dict(obs=rng.standard_normal((T + 1, obs_dim)).astype(f32), act=rng.integers(0, 4, T).astype(np.int32),
+                    rew=rng.standard_normal(T).astype(f32), disc=np.concatenate([np.ones(T - 1, f32), np.zeros(1, f32)])))
+  return eps
+
+
+def test_ring_table_yields_the_reference_adders_transitions():
+  """Feeding steps to the ring table and gathering every item gives exactly the (o, a, R, D, o') tuples that the reference
+  adder's arithmetic (oracle.nstep, pinned to the reference's golden cases) materialises for the same episodes."""
+  from oracle import nstep as onstep
+  from oracle import replay as oreplay
+  rng = np.random.default_rng(12)
+  n, gamma = 3, 0.95
+  table = oreplay.Table(4096, 8192, (3,), f32, (), np.int32, gamma, 0.6, max_window=n)
+  expect = []
+  for ep in _episodes(rng, 12):
+    w = table.writer()
+    T = len(ep['act'])
+    window = []
+    for t in range(T):
+      table.append(w, ep['obs'][t], ep['act'][t], ep['rew'][t], ep['disc'][t], ep['obs'][t + 1])
+      window.append(t)
+      window = window[-n:]
+      table.create_item(w, len(window), 1.0)
+      expect.append((window[0], t + 1, list(window), ep))
+    window = window[1:]
+    while window:                                  # episode end: the shrinking tails (transition.py:147-172)
+      table.create_item(w, len(window), 1.0)
+      expect.append((window[0], T, list(window), ep))
+      window = window[1:]
+    table.close(w)
+  assert table.size == len(expect)
+  o, a, R, D, o2 = table.gather(np.arange(len(expect)))
+  for i, (s, e, win, ep) in enumerate(expect):
+    r, d = onstep.nstep_return([ep['rew'][t] for t in win], [ep['disc'][t] for t in win], f32(gamma))
+    np.testing.assert_array_equal(o[i], ep['obs'][s])
+    np.testing.assert_array_equal(o2[i], ep['obs'][e])
+    assert a[i] == ep['act'][s] and R[i] == r and D[i] == d
+
+
+def test_ring_table_fifo_and_stale_keys():
+  from oracle import replay as oreplay
+  table = oreplay.Table(8, 64, (1,), f32, (), np.int32, 0.99, 1.0, max_window=1)
+  w = table.writer()
+  keys = []
+  for t in range(20):
+    table.append(w, [t], 0, 1.0, 1.0, [t + 1])
+    keys.append(table.create_item(w, 1, float(t + 1)))
+  assert table.size == 8 and keys == list(range(20))                      # Fifo remover, max_size 8
+  live = table.tree.leaves[:8]
+  np.testing.assert_array_equal(np.sort(live), np.arange(13, 21, dtype=f32))   # priorities of items 12..19 (alpha = 1)
+  before = table.tree.leaves.copy()
+  table.update_priorities([3, 11], [100.0, 100.0])                        # evicted keys: ignored, like Reverb
+  np.testing.assert_array_equal(table.tree.leaves, before)
+  table.update_priorities([19, 19], [5.0, 7.0])                           # duplicates: the last one wins
+  assert table.tree.leaves[19 % 8] == f32(7.0)
+  k, pos, prob = table.sample(np.linspace(0.01, 0.99, 50).astype(f32), stratified=False)
+  assert set(k.tolist()) <= set(range(12, 20))
+  np.testing.assert_allclose(prob, table.tree.leaves[pos] / table.tree.total, rtol=1e-6)
