@@ -117,3 +117,44 @@ def test_signature_order():
   assert sig == (spec.observations, spec.actions, spec.rewards, spec.discounts, spec.observations)
   sig = adders.NStepTransitionAdder.signature(spec, extras_spec={'s': specs.Array((), np.int32)})
   assert len(sig) == 6
+
+
+# ---- randomised: product adder (windows over appended steps) == the reference adder restatement (materialised items)
+def _fuzz_once(rng):
+  n_step = int(rng.integers(1, 7))
+  gamma = float(rng.choice([1.0, 0.99, 0.5]))
+  product_client, reference_client = FakeClient(), onstep.RecordingClient()
+  product = adders.NStepTransitionAdder(product_client, n_step, gamma)
+  reference = onstep.ReferenceAdder(reference_client, n_step, gamma)
+  for _ in range(int(rng.integers(1, 4))):                       # a few episodes through the same adders
+    T = int(rng.integers(1, 15))
+    first = dm_env.restart(float(rng.standard_normal()))
+    product.add_first(first)
+    reference.add_first(first)
+    for t in range(T):
+      obs, rew = float(rng.standard_normal()), np.float32(rng.standard_normal())
+      if t < T - 1:
+        step = dm_env.transition(reward=rew, observation=obs, discount=np.float32(rng.choice([1.0, 0.9, 0.0])))
+      elif rng.random() < 0.5:
+        step = dm_env.termination(reward=rew, observation=obs)
+      else:
+        step = dm_env.truncation(reward=rew, observation=obs, discount=np.float32(1.0))
+      a = int(rng.integers(0, 5))
+      product.add(a, step)
+      reference.add(a, step)
+  assert len(product_client.writers) == len(reference_client.writers)
+  for pw, rw in zip(product_client.writers, reference_client.writers):
+    assert pw.closed and rw.closed
+    assert len(pw.items) == len(rw.priorities)
+    for (table, start, length, prio), (rtable, item, rprio) in zip(pw.items, rw.priorities):
+      window = pw.steps[start:start + length]
+      R, D = onstep.nstep_return([np.float32(s[2]) for s in window], [np.float32(s[3]) for s in window], np.float32(gamma))
+      assert (table, prio) == (rtable, rprio)
+      assert window[0][0] == item[0] and window[0][1] == item[1] and window[-1][4] == item[4]
+      assert np.float32(R) == np.float32(item[2]) and np.float32(D) == np.float32(item[3])   # bit-exact bookkeeping
+
+
+def test_random_episodes_match_the_reference_adder():
+  rng = np.random.default_rng(2024)
+  for _ in range(300):
+    _fuzz_once(rng)
