@@ -61,8 +61,8 @@ PROTOTYPES = {
     'b200rl_replay_set_weights': (c_int, [c_vp, c_i64, c_vp, c_vp]),
     'b200rl_uniform': (c_int, [c_vp, c_i32, c_u64, c_vp, c_i64, c_vp]),
     'b200rl_dqn_td': (c_int, [c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_f32,
-                              c_f64, c_f32, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    'b200rl_is_weight_max': (c_int, [c_i32, c_vp, c_f64, c_vp, c_vp]),
+                              c_f64, c_f32, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp]),
+    'b200rl_is_weight_max': (c_int, [c_i32, c_vp, c_f64, c_vp, c_i32, c_vp]),
     'b200rl_c51_loss': (c_int, [c_i32, c_i32, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_f32, c_f32,
                                 c_vp, c_vp, c_vp, c_vp, c_vp]),
     'b200rl_c51_mean_fwd': (c_int, [c_i32, c_i32, c_f32, c_f32, c_vp, c_vp, c_vp]),
@@ -112,6 +112,7 @@ PROTOTYPES = {
 }
 
 ACT_NONE, ACT_RELU, ACT_ELU, ACT_TANH = 0, 1, 2, 3
+TD_IS_WEIGHTS_F32 = 1
 PRECISION_FP32, PRECISION_BF16 = 0, 1      # 1 = tensor-core mode (tf32 via TMA where eligible, else bf16 operands)
 PRECISION_TC = PRECISION_BF16
 

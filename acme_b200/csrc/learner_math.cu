@@ -63,11 +63,21 @@ struct SumD { __device__ double operator()(double a, double b) const { return a 
 
 // ------------------------------------------------------------------------------------------ K4
 // acme/agents/tf/dqn/learning.py:127-154; trfl.double_qlearning; acme/tf/losses/huber.py:48-57.
+// importance weight before normalisation: TF learner (f64, learning.py:138-139) or JAX learner (f32, jax learning.py:94-95)
+__device__ __forceinline__ double is_weight_raw(float prob, double beta, int flags) {
+  if (flags & B200RL_TD_IS_WEIGHTS_F32) return (double)powf((float)(1.0 / (double)prob), (float)beta);
+  return pow(1.0 / (double)prob, beta);
+}
+__device__ __forceinline__ float is_weight_norm(double raw, double wmax, int flags) {
+  if (flags & B200RL_TD_IS_WEIGHTS_F32) return __fdiv_rn((float)raw, (float)wmax);
+  return (float)(raw / wmax);
+}
+
 __global__ void __launch_bounds__(1024)
-is_weight_max_kernel(int B, const float* __restrict__ prob, double beta, double* __restrict__ out) {
+is_weight_max_kernel(int B, const float* __restrict__ prob, double beta, double* __restrict__ out, int flags) {
   __shared__ double scratch[32];
   double m = 0.0;
-  for (int b = threadIdx.x; b < B; b += blockDim.x) m = fmax(m, pow(1.0 / (double)prob[b], beta));
+  for (int b = threadIdx.x; b < B; b += blockDim.x) m = fmax(m, is_weight_raw(prob[b], beta, flags));
   m = block_reduce(m, MaxD(), 0.0, scratch);
   if (threadIdx.x == 0) *out = m;
 }
@@ -79,11 +89,11 @@ dqn_td_kernel(int B, int A, const float* __restrict__ q_tm1, const float* __rest
               float gamma, float delta, double beta, float max_abs_r, const double* __restrict__ wmax_dev,
               float grad_scale, float* __restrict__ td_out, float* __restrict__ loss_ps,
               float* __restrict__ weight, float* __restrict__ priority, float* __restrict__ dq,
-              float* __restrict__ loss_mean) {
+              float* __restrict__ loss_mean, int flags) {
   __shared__ double scratch_d[32];
   __shared__ float scratch_f[32];
   double wmax = 0.0;
-  for (int b = threadIdx.x; b < B; b += blockDim.x) wmax = fmax(wmax, pow(1.0 / (double)prob[b], beta));
+  for (int b = threadIdx.x; b < B; b += blockDim.x) wmax = fmax(wmax, is_weight_raw(prob[b], beta, flags));
   if (wmax_dev) wmax = *wmax_dev;                          // global max (data-parallel learners)
   else wmax = block_reduce(wmax, MaxD(), 0.0, scratch_d);  // tf.reduce_max, learning.py:140
   float lsum = 0.f;
@@ -104,7 +114,7 @@ dqn_td_kernel(int B, int A, const float* __restrict__ q_tm1, const float* __rest
     float quad = fminf(absx, delta);
     float lin = __fsub_rn(absx, quad);
     float hub = __fadd_rn(__fmul_rn(__fmul_rn(0.5f, quad), quad), __fmul_rn(delta, lin));
-    float w = (float)(pow(1.0 / (double)prob[b], beta) / wmax);   // f64 then cast, learning.py:138-143
+    float w = is_weight_norm(is_weight_raw(prob[b], beta, flags), wmax, flags);   // f64 then cast, learning.py:138-143
     float l = __fmul_rn(hub, w);
     td_out[b] = td;
     loss_ps[b] = l;
@@ -631,9 +641,9 @@ extern "C" int b200rl_uniform(float* out, int32_t n, uint64_t seed, const int64_
   return B200RL_OK;
 }
 
-extern "C" int b200rl_is_weight_max(int32_t B, const float* prob, double beta, double* out, void* stream) {
+extern "C" int b200rl_is_weight_max(int32_t B, const float* prob, double beta, double* out, int32_t flags, void* stream) {
   B200RL_REQUIRE(prob && out && B >= 1, "bad argument");
-  is_weight_max_kernel<<<1, B >= 1024 ? 1024 : ((B + 31) / 32) * 32, 0, as_stream(stream)>>>(B, prob, beta, out);
+  is_weight_max_kernel<<<1, B >= 1024 ? 1024 : ((B + 31) / 32) * 32, 0, as_stream(stream)>>>(B, prob, beta, out, flags);
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }
@@ -642,7 +652,7 @@ extern "C" int b200rl_dqn_td(int32_t B, int32_t A, const float* q_tm1, const flo
                              const int32_t* a_tm1, const float* R, const float* D, const float* prob,
                              float gamma, float delta, double beta, float max_abs_reward,
                              const double* wmax_dev, float grad_scale, float* td, float* loss_ps,
-                             float* weight, float* priority, float* dq, float* loss_mean, void* stream) {
+                             float* weight, float* priority, float* dq, float* loss_mean, int32_t flags, void* stream) {
   B200RL_REQUIRE(q_tm1 && q_tv && q_ts && a_tm1 && R && D && prob && td && loss_ps && weight && priority && dq,
                  "null argument");
   B200RL_REQUIRE(B >= 1 && A >= 1, "bad shape");
@@ -650,7 +660,7 @@ extern "C" int b200rl_dqn_td(int32_t B, int32_t A, const float* q_tm1, const flo
   int threads = B >= 1024 ? 1024 : ((B + 31) / 32) * 32;
   dqn_td_kernel<<<1, threads, 0, as_stream(stream)>>>(B, A, q_tm1, q_tv, q_ts, a_tm1, R, D, prob, gamma, delta, beta,
                                                      max_abs_reward, wmax_dev, grad_scale, td, loss_ps, weight,
-                                                     priority, dq, loss_mean);
+                                                     priority, dq, loss_mean, flags);
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }

@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstring>
 #include <deque>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -205,6 +206,10 @@ struct b200rl_replay {
 
   uint64_t slot_head = 0, item_head = 0, item_tail = 0;
   std::vector<uint64_t> item_start_seq;
+  // Sliding-window minimum of the live items' first-slot sequence numbers, as (key, start) with increasing start.
+  // With one writer the starts are monotone in key order and this holds one entry; with interleaved writers a slow
+  // writer can create an item whose window begins long before the tail item's, and the slot ring must not overwrite it.
+  std::deque<std::pair<uint64_t, uint64_t>> start_min;
   std::vector<Writer> writers;
 
   Stage stage[2];
@@ -215,7 +220,12 @@ struct b200rl_replay {
   bool state_dirty = false;
   cudaStream_t last_flush_stream = nullptr;  // flushes on different streams are chained by event
   cudaEvent_t last_flush_event = nullptr;
+  // Host bookkeeping (staging sets, writer histories, key counters) is shared by actor threads that append and the
+  // learner thread that flushes / samples; ctypes drops the GIL during calls, so every entry point takes this lock
+  // (Reverb's table is thread-safe too: acme runs actors and learner against one server).
+  std::recursive_mutex mu;
 };
+#define B200RL_LOCK(h) std::lock_guard<std::recursive_mutex> _guard((h)->mu)
 
 static int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
@@ -382,11 +392,15 @@ extern "C" int b200rl_replay_create(b200rl_replay** out, const b200rl_replay_cfg
 
 // ----------------------------------------------------------------------------------- flush
 static int flush_impl(b200rl_replay* h, cudaStream_t stream) {
+  // Order `stream` after the previous flush even when nothing is staged now: an implicit flush (staging full) runs on
+  // g_implicit_stream, and the sample / gather kernels the caller is about to issue on `stream` must see its copies.
+  if (h->last_flush_event && h->last_flush_stream != stream) {
+    B200RL_CUDA_OK(cudaStreamWaitEvent(stream, h->last_flush_event, 0));
+    h->last_flush_stream = stream;   // `stream` is now ordered after that flush: later calls on it need no second wait
+  }
   if (h->n_obs == 0 && h->n_fill == 0 && h->n_item == 0 && !h->state_dirty) return B200RL_OK;
   Stage& s = h->stage[h->cur];
   RingView& r = h->ring;
-  if (h->last_flush_event && h->last_flush_stream != stream)
-    B200RL_CUDA_OK(cudaStreamWaitEvent(stream, h->last_flush_event, 0));
   if (h->n_obs > 0) {
     // staged observations occupy consecutive slot sequence numbers -> at most two runs in the ring
     int64_t first = (int64_t)(h->obs_first_seq % (uint64_t)h->S);
@@ -434,6 +448,7 @@ static int flush_impl(b200rl_replay* h, cudaStream_t stream) {
 
 extern "C" int b200rl_replay_flush(b200rl_replay* h, void* stream) {
   B200RL_REQUIRE(h, "null handle");
+  B200RL_LOCK(h);
   int rc = ensure_device(h);
   if (rc) return rc;
   return flush_impl(h, as_stream(stream));
@@ -471,7 +486,11 @@ static int alloc_slot(b200rl_replay* h, const void* obs_host, uint64_t* seq_out)
   }
   if (h->slot_head > (uint64_t)h->S) {
     uint64_t floor_seq = h->slot_head - (uint64_t)h->S;
-    while (h->item_tail < h->item_head && h->item_start_seq[h->item_tail % h->M] < floor_seq) {
+    // FIFO eviction until NO live item starts in a slot that is about to be overwritten (oldest keys go first,
+    // like Reverb's Fifo remover, even when the offending item is not the tail)
+    while (h->item_tail < h->item_head) {
+      while (!h->start_min.empty() && h->start_min.front().first < h->item_tail) h->start_min.pop_front();
+      if (h->start_min.empty() || h->start_min.front().second >= floor_seq) break;
       int rc = stage_tree_only(h, (int64_t)(h->item_tail % h->M), 0.f);
       if (rc) return rc;
       h->item_tail++;
@@ -517,8 +536,11 @@ static int make_item(b200rl_replay* h, Writer& w, int32_t num_timesteps, double 
   }
   uint64_t key = h->item_head++;
   if (h->item_head - h->item_tail > (uint64_t)h->M) h->item_tail++;  // Fifo remover: same tree position
+  while (!h->start_min.empty() && h->start_min.front().first < h->item_tail) h->start_min.pop_front();
   int64_t pos = (int64_t)(key % (uint64_t)h->M);
   h->item_start_seq[pos] = start_seq;
+  while (!h->start_min.empty() && h->start_min.back().second >= start_seq) h->start_min.pop_back();
+  h->start_min.emplace_back(key, start_seq);
   ItemRec& it = h->stage[h->cur].h_item[h->n_item++];
   it.pos = pos;
   it.start = (int32_t)(start_seq % (uint64_t)h->S);
@@ -541,6 +563,7 @@ static Writer* get_writer(b200rl_replay* h, int32_t id) {
 
 extern "C" int b200rl_writer_open(b200rl_replay* h, int32_t* writer_id) {
   B200RL_REQUIRE(h && writer_id, "null argument");
+  B200RL_LOCK(h);
   B200RL_REQUIRE(h->cfg.obs_bytes > 0, "this replay was created without payload storage");
   for (size_t i = 0; i < h->writers.size(); ++i)
     if (!h->writers[i].in_use) {
@@ -563,6 +586,7 @@ static void push_hist(b200rl_replay* h, Writer& w, uint64_t seq) {
 extern "C" int b200rl_writer_append(b200rl_replay* h, int32_t writer, const void* obs, const void* act,
                                     float rew, float disc, const void* next_obs) {
   B200RL_REQUIRE(h && next_obs, "null argument");
+  B200RL_LOCK(h);
   Writer* w = get_writer(h, writer);
   if (!w) return B200RL_EINVAL;
   int rc = ensure_device(h);
@@ -588,6 +612,7 @@ extern "C" int b200rl_writer_append(b200rl_replay* h, int32_t writer, const void
 extern "C" int b200rl_writer_create_item(b200rl_replay* h, int32_t writer, int32_t num_timesteps,
                                          double priority, uint64_t* key_out) {
   B200RL_REQUIRE(h, "null handle");
+  B200RL_LOCK(h);
   Writer* w = get_writer(h, writer);
   if (!w) return B200RL_EINVAL;
   int rc = ensure_device(h);
@@ -597,6 +622,7 @@ extern "C" int b200rl_writer_create_item(b200rl_replay* h, int32_t writer, int32
 
 extern "C" int b200rl_writer_close(b200rl_replay* h, int32_t writer) {
   B200RL_REQUIRE(h, "null handle");
+  B200RL_LOCK(h);
   Writer* w = get_writer(h, writer);
   if (!w) return B200RL_EINVAL;
   w->in_use = false;
@@ -610,6 +636,7 @@ extern "C" int b200rl_writer_append_stream(b200rl_replay* h, int32_t writer, int
                                            const uint8_t* last, int32_t n_step, double priority,
                                            void* stream_) {
   B200RL_REQUIRE(h && obs && rew && disc && first && last, "null argument");
+  B200RL_LOCK(h);
   B200RL_REQUIRE(n_step >= 1 && n_step <= h->cfg.max_window, "n_step must be in [1, max_window]");
   B200RL_REQUIRE(n >= 0 && n <= h->S, "a stream chunk cannot exceed slot_capacity");
   Writer* w = get_writer(h, writer);
@@ -687,11 +714,13 @@ extern "C" int b200rl_writer_append_stream(b200rl_replay* h, int32_t writer, int
 
 extern "C" int b200rl_replay_reset(b200rl_replay* h, void* stream_) {
   B200RL_REQUIRE(h, "null handle");
+  B200RL_LOCK(h);
   int rc = ensure_device(h);
   if (rc) return rc;
   cudaStream_t stream = as_stream(stream_);
   h->n_obs = h->n_fill = h->n_item = 0;
   h->item_tail = h->item_head;  // every key issued so far is dead
+  h->start_min.clear();
   for (auto& w : h->writers) { w.hist.clear(); w.k = 0; w.has_pending = false; }
   B200RL_CUDA_OK(cudaMemsetAsync(h->d_tree, 0, h->tree_floats * 4, stream));
   h->state_dirty = true;
@@ -702,6 +731,7 @@ extern "C" int b200rl_replay_reset(b200rl_replay* h, void* stream_) {
 extern "C" int b200rl_replay_sample(b200rl_replay* h, int32_t B, const float* u_dev, int stratified,
                                     int64_t* idx_dev, uint64_t* keys_dev, float* prob_dev, void* stream) {
   B200RL_REQUIRE(h && u_dev && idx_dev && prob_dev, "null argument");
+  B200RL_LOCK(h);
   B200RL_REQUIRE(B >= 1, "batch must be >= 1");
   if (h->item_head == h->item_tail) {
     set_error("replay is empty (MinSize(1) not met)");
@@ -716,6 +746,7 @@ extern "C" int b200rl_replay_sample(b200rl_replay* h, int32_t B, const float* u_
 extern "C" int b200rl_replay_gather(b200rl_replay* h, int32_t B, const int64_t* idx_dev, void* o_tm1,
                                     void* a_tm1, float* R, float* D, void* o_t, void* stream) {
   B200RL_REQUIRE(h && idx_dev && o_tm1 && a_tm1 && R && D && o_t, "null argument");
+  B200RL_LOCK(h);
   B200RL_REQUIRE(h->cfg.obs_bytes > 0, "this replay was created without payload storage");
   B200RL_REQUIRE(B >= 1, "batch must be >= 1");
   int rc = ensure_device(h);
@@ -736,6 +767,7 @@ extern "C" int b200rl_replay_gather(b200rl_replay* h, int32_t B, const int64_t* 
 extern "C" int b200rl_replay_update_priorities(b200rl_replay* h, int32_t B, const uint64_t* keys_dev,
                                                const float* priority_dev, void* stream) {
   B200RL_REQUIRE(h && keys_dev && priority_dev, "null argument");
+  B200RL_LOCK(h);
   B200RL_REQUIRE(B >= 0, "negative batch");
   int rc = ensure_device(h);
   if (rc) return rc;
@@ -746,6 +778,7 @@ extern "C" int b200rl_replay_update_priorities(b200rl_replay* h, int32_t B, cons
 extern "C" int b200rl_replay_info(b200rl_replay* h, int64_t* size, uint64_t* head_key, uint64_t* tail_key,
                                   float* total_mass, void* stream) {
   B200RL_REQUIRE(h, "null handle");
+  B200RL_LOCK(h);
   if (size) *size = (int64_t)(h->item_head - h->item_tail);
   if (head_key) *head_key = h->item_head;
   if (tail_key) *tail_key = h->item_tail;
@@ -800,6 +833,7 @@ extern "C" int b200rl_replay_mass_ptr(b200rl_replay* h, float** mass_dev) {
 
 extern "C" int b200rl_replay_set_weights(b200rl_replay* h, int64_t n, const float* weights_dev, void* stream_) {
   B200RL_REQUIRE(h && weights_dev, "null argument");
+  B200RL_LOCK(h);
   B200RL_REQUIRE(n >= 1 && n <= h->M, "n must be in [1, max_items]");
   int rc = ensure_device(h);
   if (rc) return rc;

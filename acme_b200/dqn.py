@@ -30,10 +30,22 @@ class DQNLearner(core.Learner, core.Saveable):
                counter: counting.Counter = None, logger: loggers.Logger = None, checkpoint: bool = True,
                max_abs_reward: float = 1., eps_mode: int = 0, use_cuda_graph: bool = True,
                process_group=None, adam_eps: float = 1e-8, concurrent_streams: bool = True,
-               peer_exchange: Optional[bool] = None):
+               peer_exchange: Optional[bool] = None, target_update_mode: str = 'pre_increment',
+               is_weights_dtype: str = 'f64'):
+    """Arguments up to `checkpoint` are the reference's (`dqn/learning.py:43-58`).  The two JAX-learner variants of
+    SURVEY App. A.6 are switches: `target_update_mode='post_increment'` copies the target when (steps + 1) % period == 0
+    (`jax/dqn/learning.py:114-119`, `jax/utils.py:148-154`) instead of the TF learner's test before the increment
+    (`dqn/learning.py:157-161`); `is_weights_dtype='f32'` computes the importance weights in f32
+    (`jax/dqn/learning.py:94-96`) instead of f64-then-cast (`dqn/learning.py:138-143`)."""
     import torch
     if huber_loss_parameter < 0:
       raise ValueError('quadratic_linear_boundary must be >= 0.')   # huber.py:45-46
+    if target_update_mode not in ('pre_increment', 'post_increment'):
+      raise ValueError(f'unknown target_update_mode {target_update_mode!r}')
+    if is_weights_dtype not in ('f64', 'f32'):
+      raise ValueError(f'unknown is_weights_dtype {is_weights_dtype!r}')
+    self._copy_phase = 1 if target_update_mode == 'post_increment' else 0
+    self._td_flags = _capi.TD_IS_WEIGHTS_F32 if is_weights_dtype == 'f32' else 0
     self._torch = torch
     self._net, self._tgt = network, target_network
     self._dataset = dataset
@@ -213,7 +225,8 @@ class DQNLearner(core.Learner, core.Saveable):
         ev.record(torch.cuda.current_stream())
         aux.wait_event(ev)
       with torch.cuda.stream(aux) if aux is not None else contextlib.nullcontext():
-        _capi.call('b200rl_is_weight_max', self.B, _capi.ptr(ds.prob), self._beta, _capi.ptr(self._wmax), _capi.current_stream())
+        _capi.call('b200rl_is_weight_max', self.B, _capi.ptr(ds.prob), self._beta, _capi.ptr(self._wmax), self._td_flags,
+                   _capi.current_stream())
         if self._px is not None:    # all-reduce(MAX) through the peers' mailboxes, inside the captured step
           # epoch = the dataset's draw counter: unlike the step counter it is not touched by a pipelined update
           self._px.max_f64_(self._wmax, self._dataset.counter)
@@ -244,7 +257,7 @@ class DQNLearner(core.Learner, core.Saveable):
                _capi.ptr(self._bufs_sel['q']), _capi.ptr(self._actions_i32()), _capi.ptr(ds.R), _capi.ptr(ds.D),
                _capi.ptr(ds.prob), self._discount, self._delta, self._beta, self._max_abs_reward, wmax, 1.0 / self.B,
                _capi.ptr(self.td), _capi.ptr(self.loss_ps), _capi.ptr(self.weight), _capi.ptr(self.priority),
-               _capi.ptr(self.dq), _capi.ptr(self.loss), st)
+               _capi.ptr(self.dq), _capi.ptr(self.loss), self._td_flags, st)
     self._stamp(3)
     if part == 'dense':
       net.backward_dense_part(self._bufs_train, self._gbufs, self.dq, self._side[0])
@@ -340,7 +353,7 @@ class DQNLearner(core.Learner, core.Saveable):
       self._dataset.table.update_priorities_device(self._dataset.keys, self.priority)
     # learning.py:157-161: copy when num_steps % period == 0, evaluated before the increment
     _capi.call('b200rl_copy_if_period', P.size * 4, _capi.ptr(tgt.params.flat), _capi.ptr(P.flat),
-               _capi.ptr(self._num_steps), self._period, 0, st)
+               _capi.ptr(self._num_steps), self._period, self._copy_phase, st)
     _capi.call('b200rl_step_increment', _capi.ptr(self._num_steps), st)
     self._stamp(6)
 
@@ -372,7 +385,7 @@ class DQNLearner(core.Learner, core.Saveable):
       self._adam(0, P.size)
     if copy:
       _capi.call('b200rl_copy_if_period', P.size * 4, _capi.ptr(self._tgt.params.flat), _capi.ptr(P.flat),
-                 _capi.ptr(self._num_steps), self._period, 0, st)
+                 _capi.ptr(self._num_steps), self._period, self._copy_phase, st)
     _capi.call('b200rl_step_increment', _capi.ptr(self._num_steps), st)
     if tail_done and events is not None:
       # the early tail exchange of THIS graph reads the step counter: everything downstream must see the increment
@@ -442,7 +455,7 @@ class DQNLearner(core.Learner, core.Saveable):
     if not self._pending:
       variant = 'first'
     else:
-      variant = 'copy' if self._applied_host % self._period == 0 else 'norm'
+      variant = 'copy' if (self._applied_host + self._copy_phase) % self._period == 0 else 'norm'
     if not self._pgraphs:              # all three at once: no capture (and no host barrier) later inside a run
       for v in ('first', 'norm', 'copy'):
         self._pgraphs[v] = self._pipelined_graph(v)
@@ -582,6 +595,10 @@ class DQNLearner(core.Learner, core.Saveable):
     self._logger.write({'loss': loss})
     return loss
 
+  def q_values(self):
+    """(q_tm1, q_t_value, q_t_selector) of the last update, device tensors [B, A] (`dqn/learning.py:123-125`)."""
+    return self._bufs_train['q'], self._bufs_tgt['q'], self._bufs_sel['q']
+
   def get_variables(self, names: List[str]) -> List[List[np.ndarray]]:
     return [list(self._net.variables().values())]
 
@@ -603,6 +620,10 @@ class DQNLearner(core.Learner, core.Saveable):
 
   def restore(self, state):
     torch = self._torch
+    if self._px is not None and int(state['num_steps']) < self._applied_host:
+      # the exchange's mailbox flags carry step numbers: going backwards would let barriers pass on stale flags
+      raise RuntimeError('restore() to an earlier step is not supported while a peer exchange is live; '
+                         'build a new learner and restore into it')
     self._pending = False
     self._applied_host = int(state['num_steps'])
     self._net.params.flat.copy_(torch.as_tensor(state['network']))

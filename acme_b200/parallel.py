@@ -100,6 +100,7 @@ class PeerExchange:
     dev = torch.device('cuda', device)
     self.params = torch.as_tensor(_RawDeviceArray(p.value, self.n), device=dev)
     self.grads = torch.as_tensor(_RawDeviceArray(g.value, self.n), device=dev)
+    self._max_epoch = torch.zeros(1, dtype=torch.int64, device=dev)
     mine = ctypes.create_string_buffer(64)
     _capi.call('b200rl_dp_export', self._h, mine)
     handles = [None] * dp.world
@@ -109,9 +110,15 @@ class PeerExchange:
         _capi.call('b200rl_dp_import', self._h, r, ctypes.create_string_buffer(hb, 64))
     dist.barrier(group=dp.group)
 
-  def max_f64_(self, value, step):
+  def max_f64_(self, value, step=None):
+    """all-reduce(MAX) of one f64 through the peers' mailboxes.  The barrier epoch is a device counter owned by this
+    object and advanced by every call (graph-capturable), so consecutive exchanges never share an epoch whatever the
+    caller's own counters do (injected uniforms do not advance the dataset's draw counter; restore() can rewind the
+    step counter).  `step` is accepted for backward compatibility and ignored."""
     from acme_b200 import _capi
-    _capi.call('b200rl_dp_max_f64', self._h, _capi.ptr(value), _capi.ptr(step), _capi.current_stream())
+    st = _capi.current_stream()
+    _capi.call('b200rl_dp_max_f64', self._h, _capi.ptr(value), _capi.ptr(self._max_epoch), st)
+    _capi.call('b200rl_step_increment', _capi.ptr(self._max_epoch), st)
 
   def adam(self, off: int, n: int, m, v, step, lr: float, b1: float, b2: float, eps: float, eps_mode: int, bucket: int,
            final_barrier: bool = True):

@@ -68,16 +68,19 @@ class _Packer:
   def __init__(self, spec_nest):
     self.structure = spec_nest
     self.leaves = []
-    off = 0
+    off, row_align = 0, 1
     for s in tree.flatten(spec_nest):
       dt = np.dtype(s.dtype)
       shape = tuple(int(d) for d in s.shape)
       n = int(np.prod(shape, dtype=np.int64)) * dt.itemsize
       align = min(dt.itemsize, 16)
+      row_align = max(row_align, align)
       off = -(-off // align) * align
       self.leaves.append((shape, dt, off, n))
       off += n
-    self.nbytes = off
+    # rows of a batch are `nbytes` apart: the row size must keep EVERY leaf aligned in rows b > 0 too
+    # (a {float32[3], uint8[1]} nest is 13 bytes of payload in a 16-byte row)
+    self.nbytes = -(-off // row_align) * row_align
     self.single = len(self.leaves) == 1 and not tree.is_nest(spec_nest)
 
   def pack(self, value_nest) -> np.ndarray:
@@ -381,6 +384,13 @@ TFClient = Client
 
 
 # ----------------------------------------------------------------------------- dataset
+class _MassView:
+  """The tree's root mass (one device float) as a zero-copy array for torch.as_tensor."""
+
+  def __init__(self, ptr: int):
+    self.__cuda_array_interface__ = {'shape': (1,), 'typestr': '<f4', 'data': (ptr, False), 'version': 2}
+
+
 class ReplayDataset:
   """What `make_reverb_dataset(...)` returns: an iterable of batched ReplaySamples living in HBM.
 
@@ -437,9 +447,19 @@ class ReplayDataset:
     if extras is not None:
       data = data + (extras,)
     size = t.size if table_size is None else table_size
-    info = SampleInfo(key=self.keys, probability=self.prob.to(torch.float64),
+    # SampleInfo dtypes as in `acme/testing/fakes.py:251-259` (u64 key, f64 probability, i64 table_size, f64 priority).
+    # The tree stores priority^alpha in fp32 (that is what K1 reads): the reported probability is that fp32 quotient
+    # widened, and the priority is recovered from it (leaf = probability * shards * shard mass; priority =
+    # leaf^(1/alpha)).  With alpha = 0 (Uniform) every stored weight is 1 and the raw priority is not retained: 1.0.
+    prob64 = self.prob.to(torch.float64)
+    if t.alpha > 0:
+      mass = torch.as_tensor(_MassView(t.mass_ptr()), device=self.prob.device).to(torch.float64)
+      priority = (prob64 * (t.shard_count * mass)).pow(1.0 / t.alpha)
+    else:
+      priority = torch.ones_like(prob64)
+    info = SampleInfo(key=self.keys, probability=prob64,
                       table_size=torch.full((self.B,), size, dtype=torch.int64, device=self.prob.device),
-                      priority=None)
+                      priority=priority)
     return ReplaySample(info=info, data=data)
 
   def __iter__(self):

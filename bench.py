@@ -369,7 +369,7 @@ def run_ours(args):
         'b200rl_dqn_td', B, NUM_ACTIONS, learner._bufs_train['q'].data_ptr(), learner._bufs_tgt['q'].data_ptr(),
         learner._bufs_sel['q'].data_ptr(), learner._actions_i32().data_ptr(), ds.R.data_ptr(), ds.D.data_ptr(),
         ds.prob.data_ptr(), 0.99, 1.0, 0.2, 1.0, None, 1.0 / B, learner.td.data_ptr(), learner.loss_ps.data_ptr(),
-        learner.weight.data_ptr(), learner.priority.data_ptr(), learner.dq.data_ptr(), learner.loss.data_ptr(),
+        learner.weight.data_ptr(), learner.priority.data_ptr(), learner.dq.data_ptr(), learner.loss.data_ptr(), 0,
         _capi.current_stream()), it, torch)
     Pn = net.params
     scratch_p, scratch_m, scratch_v = torch.zeros_like(Pn.flat), torch.zeros_like(Pn.flat), torch.zeros_like(Pn.flat)

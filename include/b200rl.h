@@ -138,9 +138,13 @@ int b200rl_dqn_td(int32_t B, int32_t A, const float* q_tm1, const float* q_t_val
                   const float* prob, float gamma, float huber_delta, double is_exponent,
                   float max_abs_reward, const double* wmax_dev, float grad_scale, float* td,
                   float* loss_per_sample, float* weight, float* priority, float* dq_tm1,
-                  float* loss_mean, void* stream);
+                  float* loss_mean, int32_t flags, void* stream);
+/* flags for b200rl_dqn_td / b200rl_dqn_head_td.  IS_WEIGHTS_F32: the JAX learner's importance weights
+ * (acme/agents/jax/dqn/learning.py:94-96: 1/probs cast to f32, power and max in f32) instead of the TF learner's
+ * f64 power / max / divide followed by a cast (acme/agents/tf/dqn/learning.py:138-143). */
+#define B200RL_TD_IS_WEIGHTS_F32 1
 int b200rl_is_weight_max(int32_t B, const float* prob, double is_exponent, double* wmax_out_dev,
-                         void* stream);
+                         int32_t flags, void* stream);
 
 /* K5.  losses/distributional.py:22-83: target = l2_project(R + Dg*z, softmax(logits_t), z); loss =
  * CE(logits_tm1, target); dlogits = (softmax(logits_tm1)*sum(target) - target) * grad_scale. */

@@ -41,6 +41,12 @@ class Adam:
       v = self.v.get(k, np.zeros_like(p))
       m = f(self.b1) * m + f(1 - self.b1) * g
       v = f(self.b2) * v + f(1 - self.b2) * (g * g)
+      # K7 flushes moments below FLT_MIN to zero (they would otherwise sit in the subnormal range for hundreds of
+      # updates, where IEEE div/sqrt take a slow path on the GPU); restated here so both sides state one arithmetic.
+      # Effect on the update: < 1e-30 absolute.
+      tiny = f(np.finfo(np.float32).tiny)
+      m = np.where(np.abs(m) < tiny, f(0), m)
+      v = np.where(v < tiny, f(0), v)
       if self.eps_mode == 0:
         upd = (m / bc1) / (np.sqrt(v / bc2) + f(self.eps))
       else:
@@ -62,7 +68,12 @@ class DQNOracleLearner:
 
   def __init__(self, network, target_network, discount, importance_sampling_exponent,
                learning_rate, target_update_period, huber_loss_parameter=1.0,
-               max_abs_reward=1.0, eps_mode=0):
+               max_abs_reward=1.0, eps_mode=0, target_update_mode='pre_increment', is_weights_dtype='f64'):
+    # target_update_mode: 'pre_increment' = TF learner (copy when num_steps % period == 0, tested BEFORE the
+    # increment: dqn/learning.py:157-161); 'post_increment' = JAX learner (copy when (steps + 1) % period == 0,
+    # jax/dqn/learning.py:114-119 + jax/utils.py:148-154).  is_weights_dtype: see losses.dqn_loss.
+    assert target_update_mode in ('pre_increment', 'post_increment') and is_weights_dtype in ('f64', 'f32')
+    self.target_update_mode, self.is_weights_dtype = target_update_mode, is_weights_dtype
     self.net, self.tgt = network, target_network
     self.discount = discount
     self.beta = importance_sampling_exponent
@@ -81,7 +92,7 @@ class DQNOracleLearner:
       q_ts = self.net(x1)
     ref = L.dqn_loss(q_tm1.detach().numpy(), q_tv.numpy(), q_ts.numpy(), np.asarray(a_tm1, np.int64),
                      R, D, prob, self.discount, self.delta, self.beta, self.max_abs_reward,
-                     global_wmax=global_wmax)
+                     global_wmax=global_wmax, weights_dtype=self.is_weights_dtype)
     # autograd through the same expression (independent check of dq_tm1)
     rows = torch.arange(q_tm1.shape[0])
     a = torch.tensor(np.asarray(a_tm1, np.int64))
@@ -100,7 +111,8 @@ class DQNOracleLearner:
       gdict = grad_hook(gdict)
     new = self.opt.apply(gdict, self.net.numpy())
     self.net.load(new)
-    if self.num_steps % self.period == 0:
+    phase = 1 if self.target_update_mode == 'post_increment' else 0
+    if (self.num_steps + phase) % self.period == 0:
       self.tgt.copy_from(self.net)
     self.num_steps += 1
     out = dict(ref)

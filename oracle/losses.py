@@ -25,8 +25,11 @@ def huber(x, delta):
 
 
 def dqn_loss(q_tm1, q_t_value, q_t_selector, a_tm1, R, D, prob, gamma, huber_delta=1.0,
-             is_exponent=0.2, max_abs_reward=1.0, global_wmax=None):
-  """Returns dict(td, huber, weight, loss, priority, dq_tm1)."""
+             is_exponent=0.2, max_abs_reward=1.0, global_wmax=None, weights_dtype='f64'):
+  """Returns dict(td, huber, weight, loss, priority, dq_tm1).
+
+  weights_dtype: 'f64' = the TF learner (power and max in f64, then cast; dqn/learning.py:138-143);
+  'f32' = the JAX learner (1/probs cast to f32 first, power and max in f32; jax/dqn/learning.py:94-96)."""
   q_tm1 = np.asarray(q_tm1, f32)
   q_t_value = np.asarray(q_t_value, f32)
   q_t_selector = np.asarray(q_t_selector, f32)
@@ -38,9 +41,15 @@ def dqn_loss(q_tm1, q_t_value, q_t_selector, a_tm1, R, D, prob, gamma, huber_del
   target = (r + d * q_t_value[rows, best]).astype(f32)
   td = (target - q_tm1[rows, a_tm1]).astype(f32)
   h = huber(td, huber_delta)
-  w64 = (1.0 / np.asarray(prob, np.float64))**np.float64(is_exponent)
-  wmax = np.max(w64) if global_wmax is None else np.float64(global_wmax)
-  w = (w64 / wmax).astype(f32)
+  if weights_dtype == 'f32':
+    w32 = (1.0 / np.asarray(prob, np.float64)).astype(f32)**f32(is_exponent)
+    w64 = w32.astype(np.float64)      # reported maximum only
+    wmax32 = np.max(w32) if global_wmax is None else f32(global_wmax)
+    w = (w32 / wmax32).astype(f32)
+  else:
+    w64 = (1.0 / np.asarray(prob, np.float64))**np.float64(is_exponent)
+    wmax = np.max(w64) if global_wmax is None else np.float64(global_wmax)
+    w = (w64 / wmax).astype(f32)
   per_sample = (h * w).astype(f32)
   loss = per_sample.astype(np.float64).sum() / B      # reporting only; kernel sums fp32 in fixed order
   dq = np.zeros((B, A), f32)

@@ -94,7 +94,16 @@ def test_lockstep_with_oracle(n_step, alpha, max_size):
     np.testing.assert_array_equal(ds.keys.cpu().numpy().view(np.uint64), keys)
     np.testing.assert_array_equal(ds.prob.cpu().numpy(), prob)
     o0, a, R, D, o1 = oracle.gather(pos)
-    s = ds.as_sample().data
+    sample = ds.as_sample()
+    # SampleInfo as the reference's fake dataset pins it (acme/testing/fakes.py:251-259): u64 / f64 / i64 / f64
+    assert (sample.info.key.dtype, sample.info.probability.dtype, sample.info.table_size.dtype,
+            sample.info.priority.dtype) == (torch.uint64, torch.float64, torch.int64, torch.float64)
+    leaves = oracle.tree.levels[oracle.tree.L][pos].astype(np.float64)
+    if alpha > 0:   # priority = stored weight ^ (1/alpha); new items enter with priority 1
+      np.testing.assert_allclose(sample.info.priority.cpu().numpy(), leaves**(1.0 / alpha), rtol=1e-5)
+    else:
+      np.testing.assert_array_equal(sample.info.priority.cpu().numpy(), np.ones(B))
+    s = sample.data
     np.testing.assert_array_equal(s[0].cpu().numpy(), o0)
     np.testing.assert_array_equal(s[1].cpu().numpy(), a)
     np.testing.assert_array_equal(s[2].cpu().numpy().view(np.uint32), R.view(np.uint32))   # bit-exact fp32

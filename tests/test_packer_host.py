@@ -67,3 +67,29 @@ def test_writer_sends_the_first_observation_once(monkeypatch):
   assert len(appends) == 3
   assert appends[0][2] is not None and appends[1][2] is None and appends[2][2] is None   # obs pointer
   assert all(a[6] is not None for a in appends)                                          # next_obs pointer
+
+
+@pytest.mark.parametrize('nest', [
+    {'a': specs.Array((3,), np.float32), 'b': specs.Array((1,), np.uint8)},          # 13 payload bytes
+    (specs.Array((), np.float64), specs.Array((), np.int32)),                        # 12 payload bytes
+    (specs.Array((5,), np.uint8), specs.Array((2,), np.float64), specs.Array((3,), np.int16)),
+])
+def test_mixed_dtype_rows_stay_aligned_in_a_batch(nest):
+  """the ROW size must be a multiple of the largest leaf alignment, or `rows[:, off:off+n].view(dtype)`
+  fails (and rows b > 0 are misaligned on the device too).  Pack B rows, unpack them as a batch."""
+  import torch
+  from acme_b200 import tree
+  p = replay._Packer(nest)
+  assert p.nbytes % max(min(dt.itemsize, 16) for _, dt, _, _ in p.leaves) == 0
+  rng = np.random.default_rng(5)
+  B = 4
+  values = []
+  for _ in range(B):
+    leaves = [(rng.standard_normal(shape) * 50).astype(dt) for shape, dt, _, _ in p.leaves]
+    values.append(tree.unflatten_as(nest, leaves))
+  rows = torch.as_tensor(np.stack([p.pack(v) for v in values]))
+  assert rows.shape == (B, p.nbytes)
+  out = tree.flatten(p.unpack_batch(rows))
+  for j, (shape, dt, _, _) in enumerate(p.leaves):
+    want = np.stack([np.asarray(tree.flatten(v)[j], dt) for v in values])
+    np.testing.assert_array_equal(out[j].numpy(), want)
