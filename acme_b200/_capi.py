@@ -91,6 +91,21 @@ PROTOTYPES = {
     'b200rl_duelling_head_fwd': (c_int, [c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'b200rl_duelling_head_bwd': (c_int, [c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp,
                                           c_vp, c_vp, c_vp, c_i64, c_vp]),
+    'b200rl_dqn_head_td': (c_int, [c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                   c_vp, c_vp, c_vp, c_vp, c_f32, c_f32, c_f64, c_f32, c_vp, c_f32, c_i32, c_vp, c_vp, c_vp, c_vp,
+                                   c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp]),
+    'b200rl_mean': (c_int, [c_i32, c_vp, c_vp, c_vp]),
+    'b200rl_duelling_head_wgrad': (c_int, [c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    'b200rl_bf16_from_f32': (c_int, [c_i64, c_vp, c_vp, c_vp]),
+    'b200rl_conv2d_rows_bf16_bytes': (c_i64, [C.POINTER(ConvGeom)]),
+    'b200rl_conv2d_rows_bf16_from_u8': (c_int, [c_vp, C.POINTER(ConvGeom), c_vp, c_i64, c_vp]),
+    'b200rl_conv2d_fwd_bf16': (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_int, C.POINTER(ConvGeom), c_int, c_vp, c_i64, c_vp]),
+    'b200rl_conv2d_wgrad_bf16': (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, C.POINTER(ConvGeom), c_vp, c_i64, c_vp]),
+    'b200rl_conv2d_dgrad_bf16': (c_int, [c_vp, c_vp, c_vp, c_int, C.POINTER(ConvGeom), c_vp, c_int, c_int, c_vp]),
+    'b200rl_linear_fwd_bf16': (c_int, [c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_i32, c_int, c_int, c_vp, c_i64, c_vp]),
+    'b200rl_linear_dgrad_bf16': (c_int, [c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp, c_i32, c_int, c_vp, c_int, c_int, c_vp,
+                                         c_i64, c_vp]),
+    'b200rl_linear_wgrad_bf16': (c_int, [c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_i64, c_vp]),
     'b200rl_layernorm_tanh_fwd': (c_int, [c_i32, c_i32, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp]),
     'b200rl_layernorm_tanh_bwd': (c_int, [c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'b200rl_tanh_to_spec_fwd': (c_int, [c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -113,8 +128,13 @@ PROTOTYPES = {
 
 ACT_NONE, ACT_RELU, ACT_ELU, ACT_TANH = 0, 1, 2, 3
 TD_IS_WEIGHTS_F32 = 1
-PRECISION_FP32, PRECISION_BF16 = 0, 1      # 1 = tensor-core mode (tf32 via TMA where eligible, else bf16 operands)
-PRECISION_TC = PRECISION_BF16
+# precision of the network layers (K6):
+#   0  fp32 FFMA: the 1e-5 parity mode
+#   1  tcgen05 with fp32 tensors: tf32 operands fetched by TMA where eligible, bf16 operands converted on the fly otherwise
+#   2  bf16 dataflow: activations, weight shadows and back-propagated gradients in bf16 (kind::f16), fp32 master weights /
+#      accumulation / optimizer; networks that do not implement it treat 2 as 1
+PRECISION_FP32, PRECISION_TC, PRECISION_BF16FLOW = 0, 1, 2
+PRECISION_BF16 = PRECISION_TC      # historical name of mode 1
 
 _lib = None
 

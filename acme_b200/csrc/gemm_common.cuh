@@ -1,5 +1,7 @@
 // Pieces shared by the fp32 SIMT GEMM (gemm_simt.cu) and the bf16 tcgen05 GEMM (gemm_tc.cu).
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace b200rl {
@@ -13,7 +15,11 @@ struct Epilogue {
   int ldmask; int mask_act;
   float* partial;      // non-null: split-K partial sums [split][M][N], epilogue deferred
   int transpose_out;   // store C^T: out[col * ldo + row] (conv wgrad computes dW^T)
+  int out_bf16;        // `out` holds __nv_bfloat16 (bf16 activation / gradient dataflow), else fp32
+  int mask_bf16;       // `mask` holds __nv_bfloat16
+  float scale;         // accumulator multiplier applied before the bias; 0 means 1 (conv1 on integer-valued frames: 1/255)
 };
+__device__ __forceinline__ float epi_scale(const Epilogue& e) { return e.scale == 0.f ? 1.f : e.scale; }
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
@@ -32,11 +38,17 @@ __device__ __forceinline__ float act_grad_out(float y, int act) {
   }
 }
 __device__ __forceinline__ void finish(const Epilogue& e, int row, int col, float acc) {
+  acc *= epi_scale(e);
   if (e.bias) acc += e.bias[col];
   acc = apply_act(acc, e.act);
-  if (e.mask) acc *= act_grad_out(e.mask[(size_t)row * e.ldmask + col], e.mask_act);
-  if (e.transpose_out) e.out[(size_t)col * e.ldo + row] = acc;
-  else e.out[(size_t)row * e.ldo + col] = acc;
+  if (e.mask) {
+    const size_t mi = (size_t)row * e.ldmask + col;
+    const float y = e.mask_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(e.mask)[mi]) : e.mask[mi];
+    acc *= act_grad_out(y, e.mask_act);
+  }
+  const size_t oi = e.transpose_out ? (size_t)col * e.ldo + row : (size_t)row * e.ldo + col;
+  if (e.out_bf16) reinterpret_cast<__nv_bfloat16*>(e.out)[oi] = __float2bfloat16_rn(acc);
+  else e.out[oi] = acc;
 }
 
 

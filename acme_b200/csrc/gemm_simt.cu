@@ -291,7 +291,21 @@ static int launch_gemm(const AL& a, const BL& b, Epilogue epi, int M, int N, int
 // every addition is fixed by indices, never by arrival, so the result is deterministic.
 __device__ unsigned int g_tail_tickets[64];
 
-__device__ __forceinline__ float4 block_colsum(const float* __restrict__ x, int ld, int m0, int m1, int cpr, float4* red,
+// one 4-column chunk of row m: fp32 (16 bytes) or bf16 (8 bytes, widened)
+template <bool BF>
+__device__ __forceinline__ float4 load_chunk4(const void* __restrict__ x, size_t m, int ld, int c, bool through_l2) {
+  if (BF) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(x) + m * ld) + c);
+    const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+    const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+  }
+  const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + m * ld) + c;
+  return through_l2 ? __ldcg(p) : __ldg(p);
+}
+
+template <bool BF>
+__device__ __forceinline__ float4 block_colsum(const void* __restrict__ x, int ld, int m0, int m1, int cpr, float4* red,
                                                bool through_l2) {
   const int rl = threadIdx.x / cpr, c = threadIdx.x % cpr, rpi = 256 / cpr;
   float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
@@ -299,10 +313,7 @@ __device__ __forceinline__ float4 block_colsum(const float* __restrict__ x, int 
   for (; m + 7 * rpi < m1; m += 8 * rpi) {   // 8 independent 16-byte loads in flight per thread
     float4 v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4* p = reinterpret_cast<const float4*>(x + (size_t)(m + j * rpi) * ld) + c;
-      v[j] = through_l2 ? __ldcg(p) : __ldg(p);
-    }
+    for (int j = 0; j < 8; ++j) v[j] = load_chunk4<BF>(x, (size_t)(m + j * rpi), ld, c, through_l2);
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
       a0.x += v[j].x; a0.y += v[j].y; a0.z += v[j].z; a0.w += v[j].w;
@@ -310,8 +321,7 @@ __device__ __forceinline__ float4 block_colsum(const float* __restrict__ x, int 
     }
   }
   for (; m < m1; m += rpi) {
-    const float4* p0 = reinterpret_cast<const float4*>(x + (size_t)m * ld) + c;
-    const float4 v0 = through_l2 ? __ldcg(p0) : __ldg(p0);
+    const float4 v0 = load_chunk4<BF>(x, (size_t)m, ld, c, through_l2);
     a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
   }
   red[threadIdx.x] = make_float4(a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w);
@@ -326,14 +336,15 @@ __device__ __forceinline__ float4 block_colsum(const float* __restrict__ x, int 
   return t;   // valid in threads < cpr
 }
 
+template <bool BF>
 __global__ void __launch_bounds__(256)
-colsum_vec_kernel(int M, int N, const float* __restrict__ x, int ld, int rows_per_block, float* __restrict__ partial,
+colsum_vec_kernel(int M, int N, const void* __restrict__ x, int ld, int rows_per_block, float* __restrict__ partial,
                   float* __restrict__ out, int ticket) {
   __shared__ float4 red[256];
   __shared__ bool last;
   const int cpr = N >> 2;
   const int m0 = blockIdx.x * rows_per_block, m1 = min(M, m0 + rows_per_block);
-  float4 t = block_colsum(x, ld, m0, m1, cpr, red, false);
+  float4 t = block_colsum<BF>(x, ld, m0, m1, cpr, red, false);
   if (gridDim.x == 1) {
     if (threadIdx.x < cpr) reinterpret_cast<float4*>(out)[threadIdx.x] = t;
     return;
@@ -345,7 +356,7 @@ colsum_vec_kernel(int M, int N, const float* __restrict__ x, int ld, int rows_pe
   __syncthreads();
   if (!last) return;
   __threadfence();
-  t = block_colsum(partial, N, 0, (int)gridDim.x, cpr, red, true);
+  t = block_colsum<false>(partial, N, 0, (int)gridDim.x, cpr, red, true);
   if (threadIdx.x < cpr) reinterpret_cast<float4*>(out)[threadIdx.x] = t;
   if (threadIdx.x == 0) g_tail_tickets[ticket] = 0;
 }
@@ -372,7 +383,7 @@ int launch_colsum(int M, int N, const float* x, int ld, float* out, void* ws, in
     blocks = (int)std::max<int64_t>(1, std::min<int64_t>(blocks, ws ? ws_bytes / ((int64_t)N * 4) : 1));
     const int rpb = ceil_div(M, blocks);
     blocks = ceil_div(M, rpb);
-    colsum_vec_kernel<<<blocks, 256, 0, stream>>>(M, N, x, ld, rpb, (float*)ws, out, ticket);
+    colsum_vec_kernel<false><<<blocks, 256, 0, stream>>>(M, N, x, ld, rpb, (float*)ws, out, ticket);
     B200RL_LAUNCH_OK();
     return B200RL_OK;
   }
@@ -389,6 +400,25 @@ int launch_colsum(int M, int N, const float* x, int ld, float* out, void* ws, in
   colsum_partial_kernel<<<dim3(col_blocks, splits), dim3(32, 8), 0, stream>>>(M, N, x, ld, rpb, (float*)ws);
   B200RL_LAUNCH_OK();
   colsum_finish_kernel<<<ceil_div(N, 128), 128, 0, stream>>>(N, splits, (const float*)ws, out);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+
+// bias gradients of the bf16 dataflow: out[n] = sum_m x[m, n] over bf16 rows, fp32 sums in the fixed order of
+// colsum_vec_kernel (one launch; N a power of two in [4, 1024], 8-byte aligned rows)
+int launch_colsum_bf16(int M, int N, const __nv_bfloat16* x, int ld, float* out, void* ws, int64_t ws_bytes, cudaStream_t stream) {
+  const bool vec = N >= 4 && N <= 1024 && (N & (N - 1)) == 0 && ld % 4 == 0 && (((uintptr_t)x) & 7) == 0 &&
+                   ((((uintptr_t)out) | ((uintptr_t)ws)) & 15) == 0;
+  const int ticket = vec ? ticket_for(stream) : -1;
+  if (!vec || ticket < 0) {
+    set_error("bf16 column sum: N = %d must be a power of two in [4, 1024] with aligned rows", N);
+    return B200RL_EINVAL;
+  }
+  int blocks = std::max(1, std::min((int)std::lround(std::sqrt((double)M)), 2 * kNumSMs));
+  blocks = (int)std::max<int64_t>(1, std::min<int64_t>(blocks, ws ? ws_bytes / ((int64_t)N * 4) : 1));
+  const int rpb = ceil_div(M, blocks);
+  blocks = ceil_div(M, rpb);
+  colsum_vec_kernel<true><<<blocks, 256, 0, stream>>>(M, N, x, ld, rpb, (float*)ws, out, ticket);
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }

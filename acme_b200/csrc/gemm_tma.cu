@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "gemm_common.cuh"
 #include "tc_common.cuh"
+#include "tma_common.cuh"
 
 namespace b200rl {
 
@@ -38,40 +39,6 @@ constexpr int GBM = 128, GBK = 32 /* fp32 elements = 128 bytes */, G_STAGES = 3,
 int g_tma_dgrad_bn64 = 1;   // tools/layer_bench.py toggles it (B200RL_DGRAD_BN64)
 int g_tma_stage_mode = 0;   // 0 = heuristic, 1 = always shallow, 2 = always deep (tools/layer_bench.py)
 
-// ---- tensor maps (driver entry point fetched at run time: no link-time dependency on libcuda)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
-  return fn;
-}
-
-typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
-                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeIm2colFn get_encode_im2col() {
-  static EncodeIm2colFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (EncodeIm2colFn)p;
-  }
-  return fn;
-}
 // NHWC fp32 activation tensor viewed through TMA's im2col mode: one instruction loads `pixels` consecutive
 // output pixels (b, oy, ox order) x `channels` input channels of ONE filter tap; padding reads as zero.
 // Corners as in CUTLASS (conv/collective/detail.hpp): lower = -pad_before, upper = pad_after - (k - 1).
@@ -107,32 +74,6 @@ static bool make_map(CUtensorMap* m, const float* p, int64_t lines, int64_t pos,
 }
 static bool tma_ok(const float* p, int64_t ld) { return (((uintptr_t)p) & 15) == 0 && (ld * 4) % 16 == 0; }
 
-// ---- device helpers
-__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_im2col(uint32_t smem_dst, const CUtensorMap* map, int c, int w, int h, int n,
-                                                uint16_t off_w, uint16_t off_h, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
-      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w),
-      "h"(off_h)
-      : "memory");
-}
-// When A is the implicit im2col of a convolution input: k-block i = (filter tap, block of 32 channels)
-struct ConvA {
-  int enabled;
-  int C, kw, OW, OH, stride_w, stride_h, pad_left, pad_top, taps;
-};
-__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"

@@ -4,6 +4,8 @@
 //      loader-fed bf16 tcgen05 kernel (gemm_tc.cu); dense layers too small to amortise a tensor-core pipeline take
 //      the (exact) fp32 path.  Results never come from a less precise path than the one asked for, and a
 //      precision / shape no path implements is an error.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace b200rl {
@@ -54,6 +56,26 @@ int tma_conv_fwd_rows(const float* rows, const float* w, const float* bias, floa
                       void* ws, int64_t wsb, cudaStream_t s);
 int tma_conv_wgrad_rows(const float* rows, const float* dy, float* dw, float* db, const b200rl_conv_geom& g, void* ws,
                         int64_t wsb, cudaStream_t s);
+// gemm_bf16.cu (bf16 dataflow): return 1 = shapes outside what the kernels cover (reported as an error: no fallback)
+int h_linear_fwd(int M, int N, int K, const __nv_bfloat16* x, int ldx, const __nv_bfloat16* w, const float* bias, void* y, int ldy,
+                 int act, int out_bf16, void* ws, int64_t wsb, cudaStream_t s);
+int h_linear_dgrad(int M, int N, int K, const __nv_bfloat16* dy, int lddy, const __nv_bfloat16* w, void* dx, int lddx,
+                   const void* mask, int ldmask, int mask_act, int out_bf16, int mask_bf16, void* ws, int64_t wsb, cudaStream_t s);
+int h_linear_wgrad(int M, int N, int K, const __nv_bfloat16* dy, int lddy, const __nv_bfloat16* x, int ldx, float* dw, float* db,
+                   void* ws, int64_t wsb, cudaStream_t s);
+int h_conv_fwd(const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, void* y, const b200rl_conv_geom& g, int act,
+               int out_bf16, void* ws, int64_t wsb, cudaStream_t s);
+int h_conv_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* db, const b200rl_conv_geom& g, void* ws,
+                 int64_t wsb, cudaStream_t s);
+int h_conv_dgrad(const __nv_bfloat16* dy, const __nv_bfloat16* w, void* dx, const b200rl_conv_geom& g, const void* mask,
+                 int mask_act, int out_bf16, int mask_bf16, cudaStream_t s);
+int64_t h_rows_bytes(const b200rl_conv_geom& g);
+int h_rows_from_u8(const uint8_t* x, const b200rl_conv_geom& g, __nv_bfloat16* rows, int64_t bytes, cudaStream_t s);
+int h_conv_fwd_rows(const __nv_bfloat16* rows, const __nv_bfloat16* w, const float* bias, void* y, const b200rl_conv_geom& g,
+                    int act, int out_bf16, void* ws, int64_t wsb, cudaStream_t s);
+int h_conv_wgrad_rows(const __nv_bfloat16* rows, const __nv_bfloat16* dy, float* dw, float* db, const b200rl_conv_geom& g,
+                      void* ws, int64_t wsb, cudaStream_t s);
+int h_f32_to_bf16(int64_t n, const float* src, __nv_bfloat16* dst, cudaStream_t s);
 }  // namespace b200rl
 
 using namespace b200rl;
@@ -178,3 +200,75 @@ extern "C" int b200rl_linear_wgrad(int32_t M, int32_t N, int32_t K, const float*
                    tc_linear_wgrad(M, N, K, dy, lddy, x, ldx, dw, db, ws, wsb, as_stream(stream)));
 }
 extern "C" int64_t b200rl_workspace_bytes(int64_t max_out_elems) { return 64 * max_out_elems * 4; }
+
+
+// ------------------------------------------------------------------------------ bf16 dataflow (precision 2)
+#define H_CALL(expr, what)                                                                                  \
+  do {                                                                                                      \
+    int _rc = (expr);                                                                                       \
+    if (_rc == 1) {                                                                                         \
+      set_error("%s: shape / alignment outside the bf16 tensor-core kernels (there is no fallback)", what); \
+      return B200RL_EINVAL;                                                                                 \
+    }                                                                                                       \
+    return _rc;                                                                                             \
+  } while (0)
+typedef __nv_bfloat16 bf16_t;
+
+extern "C" int b200rl_bf16_from_f32(int64_t n, const float* src, void* dst_bf16, void* stream) {
+  B200RL_REQUIRE(src && dst_bf16 && n >= 0, "bad argument");
+  if (n == 0) return B200RL_OK;
+  H_CALL(h_f32_to_bf16(n, src, (bf16_t*)dst_bf16, as_stream(stream)), "bf16_from_f32 (n % 8 == 0, 16-byte aligned)");
+}
+extern "C" int64_t b200rl_conv2d_rows_bf16_bytes(const b200rl_conv_geom* g) {
+  if (!g || check_geom(g)) return 0;
+  return h_rows_bytes(*g);
+}
+extern "C" int b200rl_conv2d_rows_bf16_from_u8(const void* x_u8, const b200rl_conv_geom* g, void* rows, int64_t rows_bytes,
+                                               void* stream) {
+  B200RL_REQUIRE(x_u8 && rows, "null argument");
+  if (int rc = check_geom(g)) return rc;
+  H_CALL(h_rows_from_u8((const uint8_t*)x_u8, *g, (bf16_t*)rows, rows_bytes, as_stream(stream)), "bf16 row image");
+}
+extern "C" int b200rl_conv2d_fwd_bf16(const void* x, int x_rows, const void* w, const float* bias, void* y, int y_bf16,
+                                      const b200rl_conv_geom* g, int act, void* ws, int64_t wsb, void* stream) {
+  B200RL_REQUIRE(x && w && y, "null argument");
+  if (int rc = check_geom(g)) return rc;
+  if (x_rows)
+    H_CALL(h_conv_fwd_rows((const bf16_t*)x, (const bf16_t*)w, bias, y, *g, act, y_bf16, ws, wsb, as_stream(stream)), "conv2d_fwd_bf16(rows)");
+  H_CALL(h_conv_fwd((const bf16_t*)x, (const bf16_t*)w, bias, y, *g, act, y_bf16, ws, wsb, as_stream(stream)), "conv2d_fwd_bf16");
+}
+extern "C" int b200rl_conv2d_wgrad_bf16(const void* x, int x_rows, const void* dy, float* dw, float* db, const b200rl_conv_geom* g,
+                                        void* ws, int64_t wsb, void* stream) {
+  B200RL_REQUIRE(x && dy && dw && ws, "null argument");
+  if (int rc = check_geom(g)) return rc;
+  if (x_rows)
+    H_CALL(h_conv_wgrad_rows((const bf16_t*)x, (const bf16_t*)dy, dw, db, *g, ws, wsb, as_stream(stream)), "conv2d_wgrad_bf16(rows)");
+  H_CALL(h_conv_wgrad((const bf16_t*)x, (const bf16_t*)dy, dw, db, *g, ws, wsb, as_stream(stream)), "conv2d_wgrad_bf16");
+}
+extern "C" int b200rl_conv2d_dgrad_bf16(const void* dy, const void* w, void* dx, int dx_bf16, const b200rl_conv_geom* g,
+                                        const void* mask_y, int mask_bf16, int mask_act, void* stream) {
+  B200RL_REQUIRE(dy && w && dx, "null argument");
+  if (int rc = check_geom(g)) return rc;
+  H_CALL(h_conv_dgrad((const bf16_t*)dy, (const bf16_t*)w, dx, *g, mask_y, mask_act, dx_bf16, mask_bf16, as_stream(stream)),
+         "conv2d_dgrad_bf16");
+}
+extern "C" int b200rl_linear_fwd_bf16(int32_t M, int32_t N, int32_t K, const void* x, int32_t ldx, const void* w, const float* bias,
+                                      void* y, int32_t ldy, int y_bf16, int act, void* ws, int64_t wsb, void* stream) {
+  B200RL_REQUIRE(x && w && y && M >= 1 && N >= 1 && K >= 1 && ldx >= K && ldy >= N, "bad argument");
+  H_CALL(h_linear_fwd(M, N, K, (const bf16_t*)x, ldx, (const bf16_t*)w, bias, y, ldy, act, y_bf16, ws, wsb, as_stream(stream)),
+         "linear_fwd_bf16");
+}
+extern "C" int b200rl_linear_dgrad_bf16(int32_t M, int32_t N, int32_t K, const void* dy, int32_t lddy, const void* w, void* dx,
+                                        int32_t lddx, int dx_bf16, const void* mask_y, int mask_bf16, int mask_act, void* ws,
+                                        int64_t wsb, void* stream) {
+  B200RL_REQUIRE(dy && w && dx && M >= 1 && N >= 1 && K >= 1 && lddy >= N && lddx >= K, "bad argument");
+  H_CALL(h_linear_dgrad(M, N, K, (const bf16_t*)dy, lddy, (const bf16_t*)w, dx, lddx, mask_y, lddx, mask_act, dx_bf16, mask_bf16, ws,
+                        wsb, as_stream(stream)),
+         "linear_dgrad_bf16");
+}
+extern "C" int b200rl_linear_wgrad_bf16(int32_t M, int32_t N, int32_t K, const void* dy, int32_t lddy, const void* x, int32_t ldx,
+                                        float* dw, float* db, void* ws, int64_t wsb, void* stream) {
+  B200RL_REQUIRE(dy && x && dw && ws && M >= 1 && N >= 1 && K >= 1 && lddy >= N && ldx >= K, "bad argument");
+  H_CALL(h_linear_wgrad(M, N, K, (const bf16_t*)dy, lddy, (const bf16_t*)x, ldx, dw, db, ws, wsb, as_stream(stream)),
+         "linear_wgrad_bf16");
+}

@@ -450,6 +450,155 @@ duelling_head_fwd_kernel(int B, int A, const float* __restrict__ h, int ldh, con
   }
 }
 
+// ------------------------------------------------------------------------------ K4 fused into the duelling head
+// One warp per sample: the three duelling heads (online(o_tm1), target(o_t), online(o_t); duelling.py:37-59), the
+// double-Q TD error / Huber / importance weight / priority (learning.py:127-154) and the head's data gradient
+// dh = [dval * wv, dadv @ wa] * relu'(h) in ONE launch -- three head kernels, the single-CTA TD kernel and the
+// head-backward kernel of the unfused path sat back to back on the step's critical path.  The arithmetic of every
+// piece is the unfused kernels', operation for operation (same dot-product order, same __f*_rn sequence), so the two
+// paths agree bit for bit.  Needs A <= 32 and the batch-max importance weight precomputed (b200rl_is_weight_max).
+template <int HPL>
+__device__ __forceinline__ float head_q(const float* __restrict__ hrow, const float* __restrict__ sw, const float* __restrict__ bv,
+                                        const float* __restrict__ ba, int A, int lane, float (&hv)[HPL], float (&ha)[HPL],
+                                        float& val_out, float& adv_out) {
+  constexpr int H = 32 * HPL;
+#pragma unroll
+  for (int j = 0; j < HPL; ++j) {
+    hv[j] = hrow[lane + 32 * j];
+    ha[j] = hrow[H + lane + 32 * j];
+  }
+  float sv = 0.f;
+#pragma unroll
+  for (int j = 0; j < HPL; ++j) sv = fmaf(hv[j], sw[lane + 32 * j], sv);
+  for (int d = 16; d > 0; d >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, d);
+  sv += bv[0];
+  float total = 0.f, mine = 0.f;
+  for (int a = 0; a < A; ++a) {
+    const float* w = sw + (size_t)(a + 1) * H;
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < HPL; ++j) s = fmaf(ha[j], w[lane + 32 * j], s);
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    s += ba[a];
+    total += s;
+    if (lane == a) mine = s;
+  }
+  const float mean = total / (float)A;
+  val_out = sv;
+  adv_out = mine;
+  return sv + (mine - mean);   // lane a < A holds q[a]
+}
+
+struct HeadTdArgs {
+  int B, A, ldh, lddh, flags, dh_bf16;
+  const float *h_tm1, *h_sel, *h_tgt;
+  const float *wv, *bv, *wa, *ba, *twv, *tbv, *twa, *tba;
+  const int* a_tm1;
+  const float *R, *D, *prob;
+  float gamma, delta, max_abs_r, grad_scale;
+  double beta;
+  const double* wmax_dev;
+  float *q_tm1, *q_tv, *q_ts, *td, *loss_ps, *weight, *priority, *dq, *dval, *dadv;
+  void* dh;
+};
+
+template <int HPL>
+__global__ void __launch_bounds__(128)
+dqn_head_td_kernel(HeadTdArgs p) {
+  constexpr int H = 32 * HPL;
+  extern __shared__ __align__(16) float sw[];   // online [A + 1][H], then target [A + 1][H]
+  float* swt = sw + (size_t)(p.A + 1) * H;
+  {
+    const int nv = H / 4, na = p.A * H / 4;
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+      reinterpret_cast<float4*>(sw)[i] = __ldg(reinterpret_cast<const float4*>(p.wv) + i);
+      reinterpret_cast<float4*>(swt)[i] = __ldg(reinterpret_cast<const float4*>(p.twv) + i);
+    }
+    for (int i = threadIdx.x; i < na; i += blockDim.x) {
+      reinterpret_cast<float4*>(sw + H)[i] = __ldg(reinterpret_cast<const float4*>(p.wa) + i);
+      reinterpret_cast<float4*>(swt + H)[i] = __ldg(reinterpret_cast<const float4*>(p.twa) + i);
+    }
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= p.B) return;
+  const int A = p.A;
+  float hv[HPL], ha[HPL], tv[HPL], ta[HPL], val, adv;
+  // learning.py:124-125: the target network and the online network on o_t
+  const float q_tv = head_q<HPL>(p.h_tgt + (size_t)b * p.ldh, swt, p.tbv, p.tba, A, lane, tv, ta, val, adv);
+  const float q_ts = head_q<HPL>(p.h_sel + (size_t)b * p.ldh, sw, p.bv, p.ba, A, lane, tv, ta, val, adv);
+  // learning.py:123: the online network on o_tm1 (its hidden row stays in registers for the backward)
+  const float q_tm1 = head_q<HPL>(p.h_tm1 + (size_t)b * p.ldh, sw, p.bv, p.ba, A, lane, hv, ha, val, adv);
+  if (lane < A) {
+    if (p.q_tm1) p.q_tm1[(size_t)b * A + lane] = q_tm1;
+    if (p.q_tv) p.q_tv[(size_t)b * A + lane] = q_tv;
+    if (p.q_ts) p.q_ts[(size_t)b * A + lane] = q_ts;
+  }
+  // trfl.double_qlearning: first maximum of the selector wins
+  int best = 0;
+  float bvv = __shfl_sync(0xffffffffu, q_ts, 0);
+  for (int a = 1; a < A; ++a) {
+    const float v = __shfl_sync(0xffffffffu, q_ts, a);
+    if (v > bvv) { bvv = v; best = a; }
+  }
+  const int act = p.a_tm1[b];
+  const float q_next = __shfl_sync(0xffffffffu, q_tv, best);
+  const float q_act = __shfl_sync(0xffffffffu, q_tm1, act);
+  const float r = fminf(fmaxf(p.R[b], -p.max_abs_r), p.max_abs_r);          // learning.py:129
+  const float d = __fmul_rn(p.D[b], p.gamma);                               // learning.py:130
+  const float target = __fadd_rn(r, __fmul_rn(d, q_next));
+  const float td = __fsub_rn(target, q_act);
+  const float absx = fabsf(td);
+  const float quad = fminf(absx, p.delta);
+  const float lin = __fsub_rn(absx, quad);
+  const float hub = __fadd_rn(__fmul_rn(__fmul_rn(0.5f, quad), quad), __fmul_rn(p.delta, lin));   // huber.py:48-57
+  float w = 0.f;
+  if (lane == 0) w = is_weight_norm(is_weight_raw(p.prob[b], p.beta, p.flags), *p.wmax_dev, p.flags);   // learning.py:138-143
+  w = __shfl_sync(0xffffffffu, w, 0);
+  const float g = -(w * p.grad_scale) * fminf(fmaxf(td, -p.delta), p.delta);
+  if (lane == 0) {
+    p.td[b] = td;
+    p.loss_ps[b] = __fmul_rn(hub, w);
+    p.weight[b] = w;
+    p.priority[b] = absx;                                                    // learning.py:152 (no epsilon)
+  }
+  // duelling backward: dval = sum_a dq, dadv = dq - mean(dq) (dq has one non-zero, g at the action taken)
+  float s = 0.f;
+  for (int a = 0; a < A; ++a) s += (a == act) ? g : 0.f;
+  const float mean = s / (float)A;
+  const float my_dq = (lane == act) ? g : 0.f;
+  if (lane < A) {
+    if (p.dq) p.dq[(size_t)b * A + lane] = my_dq;
+    p.dadv[(size_t)b * A + lane] = my_dq - mean;
+  }
+  if (lane == 0) p.dval[b] = s;
+  float acc[HPL];
+#pragma unroll
+  for (int j = 0; j < HPL; ++j) acc[j] = 0.f;
+  for (int a = 0; a < A; ++a) {
+    const float ga = ((a == act) ? g : 0.f) - mean;
+    const float* wr = sw + (size_t)(a + 1) * H;
+#pragma unroll
+    for (int j = 0; j < HPL; ++j) acc[j] = fmaf(ga, wr[lane + 32 * j], acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < HPL; ++j) {
+    const int k = lane + 32 * j;
+    const float dv = hv[j] > 0.f ? s * sw[k] : 0.f;
+    const float da = ha[j] > 0.f ? acc[j] : 0.f;
+    if (p.dh_bf16) {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.dh) + (size_t)b * p.lddh;
+      o[k] = __float2bfloat16_rn(dv);
+      o[H + k] = __float2bfloat16_rn(da);
+    } else {
+      float* o = reinterpret_cast<float*>(p.dh) + (size_t)b * p.lddh;
+      o[k] = dv;
+      o[H + k] = da;
+    }
+  }
+}
+
 // backward, part 1 (thread per sample x 4 hidden units): dval = sum_a dq, dadv = dq - mean(dq), and
 // dh = [dval * wv, dadv @ wa] * relu'(h).  The (A+1) x H weights are 40 KB: they stay in L1/L2, the dq row is a
 // warp-wide broadcast load.
@@ -832,6 +981,78 @@ extern "C" int b200rl_duelling_head_bwd(int32_t B, int32_t A, int32_t H, const f
   duelling_head_bwd_dh_kernel<<<(int)ceil_div<long long>((long long)B * (H / 4), 256), 256, 0, st>>>(B, A, H, dq, h, ldh, wv, wa,
                                                                                                      dvalue, dadv, dh, lddh);
   B200RL_LAUNCH_OK();
+  int segs = std::max(1, std::min(B / 32, 8));
+  const int64_t per = (int64_t)(A + 1) * (H + 1) * 4;
+  segs = (int)std::max<int64_t>(1, std::min<int64_t>(segs, ws_bytes / per));
+  duelling_head_bwd_dw_kernel<<<dim3(ceil_div(H, 128), A + 1, segs), 128, 0, st>>>(B, A, H, dvalue, dadv, h, ldh, (float*)ws);
+  B200RL_LAUNCH_OK();
+  duelling_head_bwd_finish_kernel<<<ceil_div((A + 1) * (H + 1), 256), 256, 0, st>>>(A, H, segs, (const float*)ws, dwv, dbv, dwa, dba);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_dqn_head_td(int32_t B, int32_t A, int32_t H, const float* h_tm1, const float* h_sel, const float* h_tgt,
+                                  int32_t ldh, const float* wv, const float* bv, const float* wa, const float* ba,
+                                  const float* twv, const float* tbv, const float* twa, const float* tba,
+                                  const int32_t* a_tm1, const float* R, const float* D, const float* prob, float gamma,
+                                  float huber_delta, double is_exponent, float max_abs_reward, const double* wmax_dev,
+                                  float grad_scale, int32_t flags, float* q_tm1, float* q_tv, float* q_ts, float* td,
+                                  float* loss_ps, float* weight, float* priority, float* dq, float* dval, float* dadv,
+                                  void* dh, int32_t lddh, int32_t dh_bf16, void* stream) {
+  B200RL_REQUIRE(h_tm1 && h_sel && h_tgt && wv && bv && wa && ba && twv && tbv && twa && tba && a_tm1 && R && D && prob &&
+                     wmax_dev && td && loss_ps && weight && priority && dval && dadv && dh,
+                 "null argument");
+  B200RL_REQUIRE(B >= 1 && A >= 1 && A <= 32 && ldh >= 2 * H && lddh >= 2 * H, "bad shape (the fused head needs A <= 32)");
+  B200RL_REQUIRE(huber_delta >= 0.f, "quadratic_linear_boundary must be >= 0");
+  B200RL_REQUIRE((((uintptr_t)wv | (uintptr_t)wa | (uintptr_t)twv | (uintptr_t)twa) & 15) == 0 && H % 4 == 0,
+                 "head weights must be 16-byte aligned");
+  const size_t smem = 2 * (size_t)(A + 1) * H * 4;
+  B200RL_REQUIRE(smem <= 200 * 1024, "duelling head weights do not fit in shared memory");
+  HeadTdArgs p;
+  p.B = B; p.A = A; p.ldh = ldh; p.lddh = lddh; p.flags = flags; p.dh_bf16 = dh_bf16;
+  p.h_tm1 = h_tm1; p.h_sel = h_sel; p.h_tgt = h_tgt;
+  p.wv = wv; p.bv = bv; p.wa = wa; p.ba = ba; p.twv = twv; p.tbv = tbv; p.twa = twa; p.tba = tba;
+  p.a_tm1 = a_tm1; p.R = R; p.D = D; p.prob = prob;
+  p.gamma = gamma; p.delta = huber_delta; p.max_abs_r = max_abs_reward; p.grad_scale = grad_scale; p.beta = is_exponent;
+  p.wmax_dev = wmax_dev;
+  p.q_tm1 = q_tm1; p.q_tv = q_tv; p.q_ts = q_ts; p.td = td; p.loss_ps = loss_ps; p.weight = weight; p.priority = priority;
+  p.dq = dq; p.dval = dval; p.dadv = dadv; p.dh = dh;
+  static bool attr = false;
+  if (!attr) {
+    B200RL_CUDA_OK(cudaFuncSetAttribute(dqn_head_td_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    B200RL_CUDA_OK(cudaFuncSetAttribute(dqn_head_td_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    B200RL_CUDA_OK(cudaFuncSetAttribute(dqn_head_td_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    B200RL_CUDA_OK(cudaFuncSetAttribute(dqn_head_td_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  const int blocks = ceil_div(B * 32, 128);
+  cudaStream_t st = as_stream(stream);
+  switch (H) {
+    case 512: dqn_head_td_kernel<16><<<blocks, 128, smem, st>>>(p); break;
+    case 256: dqn_head_td_kernel<8><<<blocks, 128, smem, st>>>(p); break;
+    case 128: dqn_head_td_kernel<4><<<blocks, 128, smem, st>>>(p); break;
+    case 64: dqn_head_td_kernel<2><<<blocks, 128, smem, st>>>(p); break;
+    default: set_error("fused duelling head: hidden size %d not in {64,128,256,512}", H); return B200RL_EINVAL;
+  }
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_mean(int32_t n, const float* x, float* out, void* stream) {
+  B200RL_REQUIRE(x && out && n >= 1, "bad argument");
+  mean_kernel<<<1, 256, 0, as_stream(stream)>>>(x, n, out);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+
+// parameter gradients of the duelling head alone (dwv, dbv, dwa, dba) from dval / dadv and the hidden rows: the part of
+// b200rl_duelling_head_bwd that is NOT on the critical path once the fused kernel above has produced dh
+extern "C" int b200rl_duelling_head_wgrad(int32_t B, int32_t A, int32_t H, const float* dvalue, const float* dadv, const float* h,
+                                          int32_t ldh, float* dwv, float* dbv, float* dwa, float* dba, void* ws, int64_t ws_bytes,
+                                          void* stream) {
+  B200RL_REQUIRE(dvalue && dadv && h && dwv && dbv && dwa && dba && ws, "null argument");
+  B200RL_REQUIRE(B >= 1 && A >= 1 && H >= 1 && ldh >= 2 * H, "bad shape");
+  cudaStream_t st = as_stream(stream);
   int segs = std::max(1, std::min(B / 32, 8));
   const int64_t per = (int64_t)(A + 1) * (H + 1) * 4;
   segs = (int)std::max<int64_t>(1, std::min<int64_t>(segs, ws_bytes / per));

@@ -84,6 +84,15 @@ __device__ __forceinline__ void finish16(const Epilogue& e, int row, int c0, int
     return;
   }
   // bias, activation, activation-derivative mask -- each decided once per 16 columns
+  if (e.out_bf16 || e.mask_bf16) {   // the bf16 dataflow reaches this (unaligned / transposed) path rarely: scalar form
+#pragma unroll
+    for (int j = 0; j < 16; ++j) if (c0 + j < N) finish(e, row, c0 + j, v[j]);
+    return;
+  }
+  if (e.scale != 0.f) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] *= e.scale;
+  }
   if (e.bias) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) if (c0 + j < N) v[j] += __ldg(e.bias + c0 + j);
@@ -221,17 +230,27 @@ __device__ __forceinline__ void store_staged_rows(const Epilogue& e, const float
   float* const base = e.partial ? e.partial + (size_t)blockIdx.z * M * N : e.out;
   const int ldo = e.partial ? N : e.ldo;
   const bool use_mask = e.mask && !e.partial;
-  const bool fast = col + 3 < N && (ldo & 3) == 0 && ((uintptr_t)base & 15) == 0 &&
-                    (!use_mask || ((e.ldmask & 3) == 0 && ((uintptr_t)e.mask & 15) == 0));
+  const bool obf = e.out_bf16 && !e.partial, mbf = e.mask_bf16 != 0;
+  const bool fast = col + 3 < N && (ldo & 3) == 0 && ((uintptr_t)base & (obf ? 7 : 15)) == 0 &&
+                    (!use_mask || ((e.ldmask & 3) == 0 && ((uintptr_t)e.mask & (mbf ? 7 : 15)) == 0));
   if (!__all_sync(0xffffffffu, fast)) {
 #pragma unroll 1
     for (int it = 0; it < ITERS; ++it) {
       const int r = it * RPI + rl;
       const long long row = dst_row(r);
-      if (row >= 0 && col < N) finish4(e, (size_t)row, col, N, M, staged_chunk<BN>(slab, r, c));
+      if (row < 0 || col >= N) continue;
+      const float4 a = staged_chunk<BN>(slab, r, c);
+      if (obf || mbf || e.scale != 0.f) {
+        const float v[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (col + j < N) finish(e, (int)row, col + j, v[j]);
+      } else {
+        finish4(e, (size_t)row, col, N, M, a);
+      }
     }
     return;
   }
+  const float sc = e.partial ? 1.f : epi_scale(e);
   float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (e.bias && !e.partial) b4 = make_float4(__ldg(e.bias + col), __ldg(e.bias + col + 1), __ldg(e.bias + col + 2), __ldg(e.bias + col + 3));
   const int act = e.partial ? B200RL_ACT_NONE : e.act;
@@ -247,13 +266,22 @@ __device__ __forceinline__ void store_staged_rows(const Epilogue& e, const float
     }
     if (use_mask) {
 #pragma unroll
-      for (int g = 0; g < G; ++g)
-        if (rows[g] >= 0) m[g] = __ldg(reinterpret_cast<const float4*>(e.mask + (size_t)rows[g] * e.ldmask + col));
+      for (int g = 0; g < G; ++g) {
+        if (rows[g] < 0) continue;
+        if (mbf) {
+          const uint2 t = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(e.mask) + (size_t)rows[g] * e.ldmask + col));
+          const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+          const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+          m[g] = make_float4(lo.x, lo.y, hi.x, hi.y);
+        } else {
+          m[g] = __ldg(reinterpret_cast<const float4*>(e.mask + (size_t)rows[g] * e.ldmask + col));
+        }
+      }
     }
 #pragma unroll
     for (int g = 0; g < G; ++g) {
       if (rows[g] < 0) continue;
-      float4 v = make_float4(a[g].x + b4.x, a[g].y + b4.y, a[g].z + b4.z, a[g].w + b4.w);
+      float4 v = make_float4(fmaf(a[g].x, sc, b4.x), fmaf(a[g].y, sc, b4.y), fmaf(a[g].z, sc, b4.z), fmaf(a[g].w, sc, b4.w));
       if (act == B200RL_ACT_RELU) {
         v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
       } else if (act != B200RL_ACT_NONE) {
@@ -267,7 +295,15 @@ __device__ __forceinline__ void store_staged_rows(const Epilogue& e, const float
           v.z *= act_grad_slow(m[g].z, e.mask_act); v.w *= act_grad_slow(m[g].w, e.mask_act);
         }
       }
-      *reinterpret_cast<float4*>(base + (size_t)rows[g] * ldo + col) = v;
+      if (obf) {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + (size_t)rows[g] * ldo + col) = pk;
+      } else {
+        *reinterpret_cast<float4*>(base + (size_t)rows[g] * ldo + col) = v;
+      }
     }
   }
 }

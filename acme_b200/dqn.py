@@ -67,8 +67,18 @@ class DQNLearner(core.Learner, core.Saveable):
     B, A = dataset.B, network.A
     self.B = B
     f32 = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
-    self._bufs_train = network.make_buffers(B)
-    self._bufs_sel = network.make_buffers(B)
+    # Fused path (networks with a duelling head and features(): DQNAtariNetwork): the two online forwards
+    # (learning.py:123,125) run as ONE pass over the 2B frames [o_tm1; o_t] (fc1's weights are read once, half the
+    # launches), and the three heads + K4 + the head's data gradient are one kernel (b200rl_dqn_head_td).
+    self._fused = (hasattr(network, 'features') and A <= 32 and os.environ.get('B200RL_FUSED_HEAD', '1') != '0')
+    if self._fused:
+      self._bufs_on = network.make_buffers(2 * B)                 # rows [0, B) = o_tm1, rows [B, 2B) = o_t
+      self._bufs_train = dict(self._bufs_on, B=B)                 # the same storage seen as the o_tm1 batch (backward)
+      self._bufs_sel = None
+      self._q3 = f32(3, B, A)                                     # q_tm1, q_t_value, q_t_selector
+    else:
+      self._bufs_train = network.make_buffers(B)
+      self._bufs_sel = network.make_buffers(B)
     self._bufs_tgt = target_network.make_buffers(B)
     self._gbufs = network.make_grad_buffers(B)
     self.td, self.loss_ps, self.weight, self.priority = f32(B), f32(B), f32(B), f32(B)
@@ -95,7 +105,7 @@ class DQNLearner(core.Learner, core.Saveable):
     # With a peer exchange on >= 4 ranks the bucket's kernel is NVLink-bound (1/R of the Adam work) and does hide
     # behind the convolution backward.
     split_default = '0'   # measured on 8 GPUs: 0.540 ms split vs 0.522 ms unsplit (more barriers, contention)
-    self._split_adam = (self._concurrent and hasattr(network, 'grad_buckets') and
+    self._split_adam = (self._concurrent and hasattr(network, 'grad_buckets') and not self._fused and
                         os.environ.get('B200RL_SPLIT_ADAM', split_default) == '1')
     self._tail_done = None
     self._side = [torch.cuda.Stream(device=dev) for _ in range(5)] if self._concurrent else None
@@ -161,6 +171,10 @@ class DQNLearner(core.Learner, core.Saveable):
     ds, net, tgt = self._dataset, self._net, self._tgt
     st = _capi.current_stream()
     self._stamp(1)
+    if self._fused:
+      self._forwards_fused()
+      self._stamp(2)
+      return
     o_tm1, o_t = self._obs_view(ds.o_tm1), self._obs_view(ds.o_t)
     if self._concurrent:
       torch = self._torch
@@ -212,14 +226,73 @@ class DQNLearner(core.Learner, core.Saveable):
       net.forward(o_t, self._bufs_sel)                           # learning.py:125
     self._stamp(2)
 
+  def _obs_view_n(self, rows, n):
+    torch = self._torch
+    if self._obs_dtype == np.uint8:
+      return rows.view((n,) + self._obs_shape)
+    return rows.view(getattr(torch, self._obs_dtype.name)).view((n,) + self._obs_shape)
+
+  def _forwards_fused(self):
+    """Target features on o_t (side stream) beside ONE online pass over the 2B frames [o_tm1; o_t]."""
+    torch = self._torch
+    ds, net, tgt, B = self._dataset, self._net, self._tgt, self.B
+    o_all = self._obs_view_n(ds.o_both, 2 * B)
+    o_t = self._obs_view(ds.o_t)
+    main = torch.cuda.current_stream()
+    rows_all = rows_t = None
+    self._rows_tm1 = None
+    if hasattr(net, 'prepare_frames'):
+      rows_all = net.prepare_frames(o_all, 'all')            # one row image of the 2B frames
+      if rows_all is not None:
+        self._rows_tm1 = rows_all                            # its first B frames: conv1's weight gradient
+        fb = net.rows_frame_bytes()
+        if fb:                                               # bf16 dataflow: the target pass reads the image's second half
+          rows_t = rows_all[B * fb:]
+    hook = None
+    if self._params_ready is not None:
+      ev_conv, ev_tail = self._params_ready
+      self._params_ready = None
+    else:
+      ev_conv = ev_tail = None
+    if self._concurrent:
+      side = self._side[0]
+      start = torch.cuda.Event()
+      start.record(main)
+      side.wait_event(start)
+      with torch.cuda.stream(side):
+        if rows_all is not None and rows_t is None:
+          rows_t = tgt.prepare_frames(o_t, 't')              # precision 1: the row image cannot be sliced
+        tgt.lane(1).features(o_t, self._bufs_tgt, **(dict(rows=rows_t) if rows_t is not None else {}))   # learning.py:124
+        done = torch.cuda.Event()
+        done.record(side)
+      tgt.lane(0)
+      if ev_conv is not None:
+        # pipelined exchange: the torso's parameters (a 0.3 MB bucket, exchanged first) must have landed before the
+        # online pass starts; the fc1 + head bucket (31.7 MB) only before its dense layer
+        main.wait_event(ev_conv)
+        hook = lambda: torch.cuda.current_stream().wait_event(ev_tail)
+      kw = dict(before_fc1=hook) if hook is not None else {}
+      if rows_all is not None:
+        kw['rows'] = rows_all
+      net.lane(0).features(o_all, self._bufs_on, **kw)       # learning.py:123 and :125 in one pass
+      main.wait_event(done)
+    else:
+      if rows_all is not None and rows_t is None:
+        rows_t = tgt.prepare_frames(o_t, 't')
+      tgt.features(o_t, self._bufs_tgt, **(dict(rows=rows_t) if rows_t is not None else {}))
+      if ev_conv is not None:
+        main.wait_event(ev_conv)
+        main.wait_event(ev_tail)
+      net.features(o_all, self._bufs_on, **(dict(rows=rows_all) if rows_all is not None else {}))
+
   def _sample(self, uniforms=None):
     """K1, and in data-parallel mode the local max importance weight: its all-reduce(MAX) (one f64) is issued right
     after this and hides behind the gather and the forward passes."""
     ds = self._dataset
     ds.sample_only(uniforms)
-    if self._world > 1:
+    if self._world > 1 or self._fused:
       torch = self._torch
-      aux = self._side[2] if (self._concurrent and self._px is not None) else None
+      aux = self._side[2] if (self._concurrent and (self._px is not None or self._world == 1)) else None
       if aux is not None:           # the exchange waits for the slowest rank: keep it off the gather / forward path
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
@@ -252,6 +325,9 @@ class DQNLearner(core.Learner, core.Saveable):
     if self._wmax_done is not None:
       self._torch.cuda.current_stream().wait_event(self._wmax_done)
       self._wmax_done = None
+    if self._fused:
+      self._head_td_fused(part)
+      return
     wmax = _capi.ptr(self._wmax) if self._world > 1 else None
     _capi.call('b200rl_dqn_td', self.B, net.A, _capi.ptr(self._bufs_train['q']), _capi.ptr(self._bufs_tgt['q']),
                _capi.ptr(self._bufs_sel['q']), _capi.ptr(self._actions_i32()), _capi.ptr(ds.R), _capi.ptr(ds.D),
@@ -286,6 +362,67 @@ class DQNLearner(core.Learner, core.Saveable):
     else:
       net.backward(o_tm1, self._bufs_train, self._gbufs, self.dq)
 
+  def _head_td_fused(self, part: str):
+    """The three duelling heads + K4 + dh in one launch, then the backward through fc1 and the torso."""
+    torch = self._torch
+    ds, net, tgt, B = self._dataset, self._net, self._tgt, self.B
+    on, tg, gb = self._bufs_on, self._bufs_tgt, self._gbufs
+    h_on = on['h']
+    wv, bv, wa, ba = net.head_params()
+    twv, tbv, twa, tba = tgt.head_params()
+    q = self._q3
+    flow = bool(getattr(net, 'flow', False))
+    _capi.call('b200rl_dqn_head_td', B, net.A, 512, h_on.data_ptr(), h_on.data_ptr() + 4 * B * 1024, tg['h'].data_ptr(), 1024,
+               wv, bv, wa, ba, twv, tbv, twa, tba, _capi.ptr(self._actions_i32()), _capi.ptr(ds.R), _capi.ptr(ds.D),
+               _capi.ptr(ds.prob), self._discount, self._delta, self._beta, self._max_abs_reward, _capi.ptr(self._wmax),
+               1.0 / B, self._td_flags, q[0].data_ptr(), q[1].data_ptr(), q[2].data_ptr(), _capi.ptr(self.td),
+               _capi.ptr(self.loss_ps), _capi.ptr(self.weight), _capi.ptr(self.priority), _capi.ptr(self.dq),
+               gb['dval'].data_ptr(), gb['dadv'].data_ptr(), gb['dh'].data_ptr(), 1024, int(flow), _capi.current_stream())
+    self._stamp(3)
+    # the scalar loss (learning.py:143-144) is only logged: off the critical path
+    if self._concurrent:
+      main, aux = torch.cuda.current_stream(), self._side[2]
+      ev = torch.cuda.Event()
+      ev.record(main)
+      aux.wait_event(ev)
+      with torch.cuda.stream(aux):
+        _capi.call('b200rl_mean', B, _capi.ptr(self.loss_ps), _capi.ptr(self.loss), _capi.current_stream())
+        self._loss_done = torch.cuda.Event()
+        self._loss_done.record(aux)
+    else:
+      _capi.call('b200rl_mean', B, _capi.ptr(self.loss_ps), _capi.ptr(self.loss), _capi.current_stream())
+    o_tm1 = self._obs_view(ds.o_tm1)
+    bt = self._bufs_train
+    if part == 'dense':
+      net.backward_dense_part(bt, gb, None, self._side[0])
+    elif self._concurrent and self._early_tail_now:
+      net.backward_dense_part(bt, gb, None, self._side[0])
+      main, side = torch.cuda.current_stream(), self._side[4]
+      ev = torch.cuda.Event()
+      ev.record(main)
+      side.wait_event(ev)
+      with torch.cuda.stream(side):
+        (o1, n1), _ = net.grad_buckets()
+        self._px.adam(o1, n1, self._m, self._v, self._num_steps, self._lr, 0.9, 0.999, self._adam_eps, self._eps_mode, 0,
+                      final_barrier=False)
+        self._early_done = torch.cuda.Event()
+        self._early_done.record(side)
+      net.backward_conv_part(o_tm1, bt, gb, self._side[0], **self._rows_kw())
+    elif self._concurrent:
+      net.backward_dense_part(bt, gb, None, self._side[0])
+      net.backward_conv_part(o_tm1, bt, gb, self._side[0], **self._rows_kw())
+    else:
+      net.head_wgrad(bt, gb)
+      net._fc1_wgrad(bt, gb)
+      net._fc1_dgrad(bt, gb)
+      for i in (2, 1, 0):
+        net._conv_wgrad(i, o_tm1, bt, gb, self._rows_kw().get('rows'))
+        if i > 0:
+          net._conv_dgrad(i, bt, gb)
+    if getattr(self, '_loss_done', None) is not None:
+      torch.cuda.current_stream().wait_event(self._loss_done)
+      self._loss_done = None
+
   def _forward_loss(self):
     self._forwards()
     if self._world > 1 and self._px is None:
@@ -301,11 +438,13 @@ class DQNLearner(core.Learner, core.Saveable):
       final = not (self._split_adam and bucket == 0)
       self._px.adam(off, n, self._m, self._v, self._num_steps, self._lr, 0.9, 0.999, self._adam_eps, self._eps_mode, bucket,
                     final_barrier=final)
+      self._net.params.refresh_shadow(off, n)
       return
     P, b = self._net.params, 4 * off
+    shadow = (P.shadow.data_ptr() + 2 * off) if P.shadow is not None else None      # bf16 dataflow: weights' bf16 copy
     _capi.call('b200rl_adam', n, _capi.ptr(P.flat) + b, _capi.ptr(P.grad) + b, _capi.ptr(self._m) + b, _capi.ptr(self._v) + b,
                _capi.ptr(self._num_steps), self._lr, 0.9, 0.999, self._adam_eps, self._eps_mode,
-               _capi.ptr(self._gscale) if self._world > 1 else None, None, _capi.current_stream())
+               _capi.ptr(self._gscale) if self._world > 1 else None, shadow, _capi.current_stream())
 
   def _adam_tail_async(self):
     """Adam on the fc1 + head bucket on side stream 1 (B200RL_SPLIT_ADAM=1)."""
@@ -352,10 +491,19 @@ class DQNLearner(core.Learner, core.Saveable):
     elif self._replay_client is not None:                       # learning.py:151-154
       self._dataset.table.update_priorities_device(self._dataset.keys, self.priority)
     # learning.py:157-161: copy when num_steps % period == 0, evaluated before the increment
-    _capi.call('b200rl_copy_if_period', P.size * 4, _capi.ptr(tgt.params.flat), _capi.ptr(P.flat),
-               _capi.ptr(self._num_steps), self._period, self._copy_phase, st)
+    self._target_copy()
     _capi.call('b200rl_step_increment', _capi.ptr(self._num_steps), st)
     self._stamp(6)
+
+  def _target_copy(self):
+    """learning.py:157-161: target <- online when (num_steps + phase) % period == 0, tested before the increment
+    (phase 1 = the JAX learner's post-increment test).  The bf16 weight shadow follows its parameters."""
+    P, T, st = self._net.params, self._tgt.params, _capi.current_stream()
+    _capi.call('b200rl_copy_if_period', P.size * 4, _capi.ptr(T.flat), _capi.ptr(P.flat), _capi.ptr(self._num_steps),
+               self._period, self._copy_phase, st)
+    if P.shadow is not None and T.shadow is not None:
+      _capi.call('b200rl_copy_if_period', P.size * 2, _capi.ptr(T.shadow), _capi.ptr(P.shadow), _capi.ptr(self._num_steps),
+                 self._period, self._copy_phase, st)
 
   # ---- pipelined exchange (see __init__)
   def _apply_update(self, copy: bool = True, tail_done: bool = False):
@@ -373,19 +521,20 @@ class DQNLearner(core.Learner, core.Saveable):
       # torso bucket first (0.3 MB: one barrier round trip), then fc1 + heads (NVLink-bound).  Running the two
       # concurrently was measured slower on 2 GPUs (0.463 vs 0.436 ms): the big kernel delays the small one
       px.adam(o0, n0, *args, 1, final_barrier=True)
+      self._net.params.refresh_shadow(o0, n0)
       ev_conv = torch.cuda.Event()
       ev_conv.record(torch.cuda.current_stream())
       ev_tail = ev_conv
       if not tail_done:
         px.adam(o1, n1, *args, 0, final_barrier=True)
+        self._net.params.refresh_shadow(o1, n1)
         ev_tail = torch.cuda.Event()
         ev_tail.record(torch.cuda.current_stream())
       events = (ev_conv, ev_tail)
     else:
       self._adam(0, P.size)
     if copy:
-      _capi.call('b200rl_copy_if_period', P.size * 4, _capi.ptr(self._tgt.params.flat), _capi.ptr(P.flat),
-                 _capi.ptr(self._num_steps), self._period, self._copy_phase, st)
+      self._target_copy()
     _capi.call('b200rl_step_increment', _capi.ptr(self._num_steps), st)
     if tail_done and events is not None:
       # the early tail exchange of THIS graph reads the step counter: everything downstream must see the increment
@@ -597,6 +746,8 @@ class DQNLearner(core.Learner, core.Saveable):
 
   def q_values(self):
     """(q_tm1, q_t_value, q_t_selector) of the last update, device tensors [B, A] (`dqn/learning.py:123-125`)."""
+    if self._fused:
+      return self._q3[0], self._q3[1], self._q3[2]
     return self._bufs_train['q'], self._bufs_tgt['q'], self._bufs_sel['q']
 
   def get_variables(self, names: List[str]) -> List[List[np.ndarray]]:
@@ -631,6 +782,8 @@ class DQNLearner(core.Learner, core.Saveable):
     self._m.copy_(torch.as_tensor(state['adam_m']))
     self._v.copy_(torch.as_tensor(state['adam_v']))
     self._num_steps.fill_(int(state['num_steps']))
+    self._net.params.refresh_shadow()
+    self._tgt.params.refresh_shadow()
 
 
 class DQN(agent.Agent):

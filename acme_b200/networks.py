@@ -48,18 +48,40 @@ class ParamStore:
     self.size = 0
     self.flat = None
     self.grad = None
+    self.shadow = None
 
   def declare(self, name: str, shape):
     shape = tuple(int(s) for s in shape)
     self.entries[name] = (self.size, shape)
     n = int(np.prod(shape))
-    self.size += -(-n // 4) * 4          # keep every tensor 16-byte aligned
+    self.size += -(-n // 8) * 8          # every tensor 32-byte aligned in fp32 and 16-byte aligned in the bf16 shadow
 
   def allocate(self):
     import torch
     dev = torch.device('cuda', self.device)
     self.flat = torch.zeros(self.size, dtype=torch.float32, device=dev)
     self.grad = torch.zeros(self.size, dtype=torch.float32, device=dev)
+
+  def ensure_shadow(self):
+    """bf16 copy of the parameters at the same element offsets (the weight operands of the bf16 dataflow).  Kept in
+    step by the optimizer (`b200rl_adam(..., bf16_shadow)`) or `refresh_shadow()` after any other parameter write."""
+    import torch
+    if self.shadow is None:
+      self.shadow = torch.zeros(self.size, dtype=torch.bfloat16, device=self.flat.device)
+      self.refresh_shadow()
+    return self.shadow
+
+  def refresh_shadow(self, off: int = 0, n: Optional[int] = None):
+    if self.shadow is None:
+      return
+    n = self.size - off if n is None else n
+    assert off % 8 == 0 and n % 8 == 0
+    _capi.call('b200rl_bf16_from_f32', n, self.flat.data_ptr() + 4 * off, self.shadow.data_ptr() + 2 * off,
+               _capi.current_stream())
+
+  def sp(self, name: str) -> int:
+    """Device address of `name` in the bf16 shadow."""
+    return self.shadow.data_ptr() + 2 * self.entries[name][0]
 
   def rebind(self, flat, grad):
     """Moves the parameters / gradients into caller-provided storage (the peer-mapped region of
@@ -83,6 +105,8 @@ class ParamStore:
   def set(self, name: str, value: np.ndarray):
     import torch
     self.view(name).copy_(torch.as_tensor(np.ascontiguousarray(value, dtype=np.float32)))
+    if self.shadow is not None:
+      self.refresh_shadow()
 
   def get(self, name: str, grad: bool = False) -> np.ndarray:
     return self.view(name, grad).detach().cpu().numpy().copy()
@@ -118,6 +142,7 @@ class Network:
 
   def copy_params_from(self, other: 'Network'):
     self.params.flat.copy_(other.params.flat)
+    self.params.refresh_shadow()
 
   def clone(self) -> 'Network':
     """Same architecture, separately stored copy of the parameters (copy.deepcopy(network),
@@ -129,6 +154,10 @@ class Network:
     other.params.size = self.params.size
     other.params.allocate()
     other.params.flat.copy_(self.params.flat)
+    if self.params.shadow is not None:
+      other.params.ensure_shadow()
+    if hasattr(self, '_rows'):
+      other._rows = {}                  # row images are per network (their forwards may run concurrently)
     return other
 
   # --- Sonnet-shaped export / import (get_variables, checkpoints, parity tests)
@@ -235,50 +264,92 @@ class DQNAtariNetwork(Network):
     k, s, ci, co, h, oh, pad = self.convs[i]
     return ConvGeom(B=B, H=h, W=h, C=ci, kh=k, kw=k, stride=s, pad_top=pad, pad_left=pad, OH=oh, OW=oh, Cout=co)
 
+  # ---- buffers.  In the bf16 dataflow (precision 2) activations y1..y3 and the back-propagated gradients dh, dy1..dy3
+  # are bf16; the hidden row h (consumed by the duelling head in fp32), q, value / advantage and everything the loss
+  # touches stay fp32.
+  @property
+  def flow(self) -> bool:
+    return self.precision == _capi.PRECISION_BF16FLOW
+
   def make_buffers(self, B: int):
     import torch
     dev = torch.device('cuda', self.device)
     f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+    a = (lambda *shape: torch.empty(shape, dtype=torch.bfloat16, device=dev)) if self.flow else f
     bufs = dict(B=B, q=f(B, self.A), h=f(B, 1024), val=f(B, 1), adv=f(B, self.A))
     for i, (k, s, ci, co, h, oh, pad) in enumerate(self.convs, 1):
-      bufs[f'y{i}'] = f(B, oh, oh, co)
+      bufs[f'y{i}'] = a(B, oh, oh, co)
     return bufs
 
   def make_grad_buffers(self, B: int):
     import torch
     dev = torch.device('cuda', self.device)
     f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
-    g = dict(dh=f(B, 1024), dval=f(B, 1), dadv=f(B, self.A))
+    a = (lambda *shape: torch.empty(shape, dtype=torch.bfloat16, device=dev)) if self.flow else f
+    g = dict(dh=a(B, 1024), dval=f(B, 1), dadv=f(B, self.A))
+    if self.flow:
+      g['dh32'] = f(B, 1024)           # the unfused head backward writes fp32; converted for the bf16 GEMMs
     for i, (k, s, ci, co, h, oh, pad) in enumerate(self.convs, 1):
-      g[f'dy{i}'] = f(B, oh, oh, co)
+      g[f'dy{i}'] = a(B, oh, oh, co)
     return g
 
+  def rows_frame_bytes(self) -> int:
+    """Bytes of ONE frame in the bf16 row image (bf16 dataflow): a batched image can be sliced per sample range."""
+    import ctypes
+    return int(_capi.load().b200rl_conv2d_rows_bf16_bytes(ctypes.byref(self.geom(0, 1)))) if self.flow else 0
+
   def prepare_frames(self, obs, slot: str = 'x'):
-    """uint8 frames -> the fp32 row image that first-layer calls accept (`b200rl_conv2d_rows_from_u8`), built ONCE for all
-    the passes over the same frames (two networks on o_t; forward + weight gradient on o_tm1).  None when not applicable
-    (fp32 mode, float frames, geometry not eligible): callers then pass the frames themselves."""
+    """uint8 frames -> the row image that first-layer calls accept, built ONCE for all the passes over the same frames
+    (two networks on o_t; forward + weight gradient on o_tm1).  Precision 1: zero-padded fp32 rows x/255
+    (`b200rl_conv2d_rows_from_u8`); precision 2: zero-padded bf16 rows of the integer pixel values
+    (`b200rl_conv2d_rows_bf16_from_u8`).  None when not applicable (fp32 mode, float frames, geometry not eligible):
+    callers then pass the frames themselves."""
     import ctypes
     import torch
-    if self.precision != _capi.PRECISION_BF16 or obs.dtype != torch.uint8:
+    if self.precision == _capi.PRECISION_FP32 or obs.dtype != torch.uint8:
       return None
     B = obs.shape[0]
     cache = self.__dict__.setdefault('_rows', {})
+    lib = _capi.load()
     if (slot, B) not in cache:
-      nbytes = int(_capi.load().b200rl_conv2d_rows_bytes(ctypes.byref(self.geom(0, B))))
+      fn = lib.b200rl_conv2d_rows_bf16_bytes if self.flow else lib.b200rl_conv2d_rows_bytes
+      nbytes = int(fn(ctypes.byref(self.geom(0, B))))
       cache[(slot, B)] = (torch.empty(nbytes, dtype=torch.uint8, device=obs.device) if nbytes > 0 else None)
     buf = cache[(slot, B)]
     if buf is None:
+      if self.flow:
+        raise ValueError('the bf16 dataflow needs the Atari first-layer geometry (C = 4, kw * C = 32)')
       return None
-    _capi.call('b200rl_conv2d_rows_from_u8', obs.data_ptr(), self.geom(0, B), buf.data_ptr(), buf.numel(), _capi.current_stream())
+    name = 'b200rl_conv2d_rows_bf16_from_u8' if self.flow else 'b200rl_conv2d_rows_from_u8'
+    _capi.call(name, obs.data_ptr(), self.geom(0, B), buf.data_ptr(), buf.numel(), _capi.current_stream())
     return buf
 
-  def forward(self, obs, bufs, before_fc1=None, rows=None) -> 'torch.Tensor':
-    """obs: uint8 or float32 [B, H, W, C] (NHWC).  uint8 is read as float32(x)/255.  `before_fc1` (optional callable)
-    runs after the torso has been issued and before the first dense layer: the pipelined data-parallel learner makes
-    the stream wait there for the fc1 + head parameters, which arrive while the convolutions run."""
+  def features(self, obs, bufs, before_fc1=None, rows=None):
+    """The torso and the first dense layer of both streams: obs -> bufs['h'] (post-ReLU, fp32 [B, 1024]).
+    obs: uint8 or float32 [B, H, W, C] (NHWC); uint8 is read as float32(x)/255.  `rows`: the frames' row image from
+    prepare_frames() (required in the bf16 dataflow; built here if absent).  `before_fc1` (optional callable) runs after
+    the torso has been issued and before the dense layer: the pipelined data-parallel learner makes the stream wait there
+    for the fc1 + head parameters, which arrive while the convolutions run."""
     import torch
     B, P, st = bufs['B'], self.params, _capi.current_stream()
     ws, wsb = self.ws
+    if self.flow:
+      P.ensure_shadow()
+      if rows is None:
+        if obs.dtype != torch.uint8:
+          raise ValueError('the bf16 dataflow reads uint8 frames')
+        rows = self.prepare_frames(obs, 'fwd')
+      x, x_rows = rows.data_ptr(), 1
+      for i in range(3):
+        y = bufs[f'y{i + 1}']
+        _capi.call('b200rl_conv2d_fwd_bf16', x, x_rows, P.sp(f'conv{i + 1}.w'), P.p(f'conv{i + 1}.b'), y.data_ptr(), 1,
+                   self.geom(i, B), ACT_RELU, ws, wsb, st)
+        x, x_rows = y.data_ptr(), 0
+      if before_fc1 is not None:
+        before_fc1()
+      _capi.call('b200rl_linear_fwd_bf16', B, 1024, self.flat_dim, x, self.flat_dim, P.sp('fc1.w'), P.p('fc1.b'),
+                 bufs['h'].data_ptr(), 1024, 0, ACT_RELU, ws, wsb, st)
+      return bufs['h']
     x, x_u8 = obs.data_ptr(), int(obs.dtype == torch.uint8)
     if rows is not None:              # the frames' row image from prepare_frames()
       x, x_u8 = rows.data_ptr(), 2
@@ -292,9 +363,96 @@ class DQNAtariNetwork(Network):
       before_fc1()
     h = bufs['h']
     _linear(B, 1024, self.flat_dim, x, self.flat_dim, P.p('fc1.w'), P.p('fc1.b'), h.data_ptr(), 1024, ACT_RELU, self)
+    return h
+
+  def head_params(self):
+    """(wv, bv, wa, ba) device addresses of the duelling head (fp32 master weights)."""
+    P = self.params
+    return P.p('v2.w'), P.p('v2.b'), P.p('a2.w'), P.p('a2.b')
+
+  def forward(self, obs, bufs, before_fc1=None, rows=None) -> 'torch.Tensor':
+    """features() followed by the duelling head (`duelling.py:37-59`): q [B, A]."""
+    P, B = self.params, bufs['B']
+    h = self.features(obs, bufs, before_fc1=before_fc1, rows=rows)
     _capi.call('b200rl_duelling_head_fwd', B, self.A, 512, h.data_ptr(), 1024, P.p('v2.w'), P.p('v2.b'), P.p('a2.w'),
-               P.p('a2.b'), bufs['val'].data_ptr(), bufs['adv'].data_ptr(), bufs['q'].data_ptr(), st)
+               P.p('a2.b'), bufs['val'].data_ptr(), bufs['adv'].data_ptr(), bufs['q'].data_ptr(), _capi.current_stream())
     return bufs['q']
+
+  def _head_backward(self, bufs, gbufs, dq):
+    """Unfused duelling-head backward: dval, dadv, dh (masked by relu'(h)) and the head's four parameter gradients."""
+    B, P = bufs['B'], self.params
+    ws, wsb = self.ws
+    dh = gbufs['dh32'] if self.flow else gbufs['dh']
+    _capi.call('b200rl_duelling_head_bwd', B, self.A, 512, dq.data_ptr(), bufs['h'].data_ptr(), 1024, P.p('v2.w'), P.p('a2.w'),
+               gbufs['dval'].data_ptr(), gbufs['dadv'].data_ptr(), dh.data_ptr(), 1024, P.g('v2.w'), P.g('v2.b'), P.g('a2.w'),
+               P.g('a2.b'), ws, wsb, _capi.current_stream())
+    if self.flow:
+      _capi.call('b200rl_bf16_from_f32', B * 1024, dh.data_ptr(), gbufs['dh'].data_ptr(), _capi.current_stream())
+
+  def head_wgrad(self, bufs, gbufs):
+    """The head's parameter gradients from gbufs['dval'] / ['dadv'] (after the fused head + TD kernel)."""
+    B, P = bufs['B'], self.params
+    ws, wsb = self.ws
+    _capi.call('b200rl_duelling_head_wgrad', B, self.A, 512, gbufs['dval'].data_ptr(), gbufs['dadv'].data_ptr(),
+               bufs['h'].data_ptr(), 1024, P.g('v2.w'), P.g('v2.b'), P.g('a2.w'), P.g('a2.b'), ws, wsb, _capi.current_stream())
+
+  # layer calls of the backward pass in either dataflow
+  def _fc1_wgrad(self, bufs, gbufs):
+    B, P = bufs['B'], self.params
+    ws, wsb = self.ws
+    if self.flow:
+      _capi.call('b200rl_linear_wgrad_bf16', B, 1024, self.flat_dim, gbufs['dh'].data_ptr(), 1024, bufs['y3'].data_ptr(),
+                 self.flat_dim, P.g('fc1.w'), P.g('fc1.b'), ws, wsb, _capi.current_stream())
+    else:
+      _linear_wgrad(B, 1024, self.flat_dim, gbufs['dh'].data_ptr(), 1024, bufs['y3'].data_ptr(), self.flat_dim, P.g('fc1.w'),
+                    P.g('fc1.b'), self)
+
+  def _fc1_dgrad(self, bufs, gbufs):
+    B, P = bufs['B'], self.params
+    ws, wsb = self.ws
+    if self.flow:
+      _capi.call('b200rl_linear_dgrad_bf16', B, 1024, self.flat_dim, gbufs['dh'].data_ptr(), 1024, P.sp('fc1.w'),
+                 gbufs['dy3'].data_ptr(), self.flat_dim, 1, bufs['y3'].data_ptr(), 1, ACT_RELU, ws, wsb, _capi.current_stream())
+    else:
+      _linear_dgrad(B, 1024, self.flat_dim, gbufs['dh'].data_ptr(), 1024, P.p('fc1.w'), gbufs['dy3'].data_ptr(), self.flat_dim,
+                    bufs['y3'].data_ptr(), ACT_RELU, self)
+
+  def _conv_wgrad(self, i, obs, bufs, gbufs, rows):
+    import torch
+    B, P = bufs['B'], self.params
+    ws, wsb = self.ws
+    g = self.geom(i, B)
+    dy = gbufs[f'dy{i + 1}'].data_ptr()
+    if self.flow:
+      if i > 0:
+        x, x_rows = bufs[f'y{i}'].data_ptr(), 0
+      else:
+        if rows is None:
+          rows = self.prepare_frames(obs, 'bwd')
+        x, x_rows = rows.data_ptr(), 1
+      _capi.call('b200rl_conv2d_wgrad_bf16', x, x_rows, dy, P.g(f'conv{i + 1}.w'), P.g(f'conv{i + 1}.b'), g, ws, wsb,
+                 _capi.current_stream())
+      return
+    if i > 0:
+      x, x_u8 = bufs[f'y{i}'].data_ptr(), 0
+    elif rows is not None:
+      x, x_u8 = rows.data_ptr(), 2
+    else:
+      x, x_u8 = obs.data_ptr(), int(obs.dtype == torch.uint8)
+    _capi.call('b200rl_conv2d_wgrad', x, x_u8, dy, P.g(f'conv{i + 1}.w'), P.g(f'conv{i + 1}.b'), g, self.precision, ws, wsb,
+               _capi.current_stream())
+
+  def _conv_dgrad(self, i, bufs, gbufs):
+    B, P = bufs['B'], self.params
+    ws, wsb = self.ws
+    g = self.geom(i, B)
+    dy = gbufs[f'dy{i + 1}'].data_ptr()
+    if self.flow:
+      _capi.call('b200rl_conv2d_dgrad_bf16', dy, P.sp(f'conv{i + 1}.w'), gbufs[f'dy{i}'].data_ptr(), 1, g,
+                 bufs[f'y{i}'].data_ptr(), 1, ACT_RELU, _capi.current_stream())
+    else:
+      _capi.call('b200rl_conv2d_dgrad', dy, P.p(f'conv{i + 1}.w'), gbufs[f'dy{i}'].data_ptr(), g, bufs[f'y{i}'].data_ptr(),
+                 ACT_RELU, self.precision, ws, wsb, _capi.current_stream())
 
   def backward(self, obs, bufs, gbufs, dq, side_stream=None, rows=None):
     """Accumulates nothing: overwrites params.grad with d(loss)/d(params) given dq [B, A].  `rows`: the row image of
@@ -303,35 +461,15 @@ class DQNAtariNetwork(Network):
     With `side_stream`, the weight-gradient GEMMs of fc1 / conv3 / conv2 run on it (workspace lane 1)
     concurrently with the data-gradient chain on the current stream: the two are independent once a
     layer's dy exists, and each kernel alone is too latency-bound to fill the machine."""
-    import torch
     if side_stream is not None:
       return self._backward_two_streams(obs, bufs, gbufs, dq, side_stream, rows)
-    B, P, st = bufs['B'], self.params, _capi.current_stream()
-    ws, wsb = self.ws
-    h = bufs['h']
-    dh = gbufs['dh'].data_ptr()
-    _capi.call('b200rl_duelling_head_bwd', B, self.A, 512, dq.data_ptr(), h.data_ptr(), 1024, P.p('v2.w'), P.p('a2.w'),
-               gbufs['dval'].data_ptr(), gbufs['dadv'].data_ptr(), dh, 1024, P.g('v2.w'), P.g('v2.b'), P.g('a2.w'),
-               P.g('a2.b'), ws, wsb, st)
-    y3 = bufs['y3']
-    _linear_wgrad(B, 1024, self.flat_dim, dh, 1024, y3.data_ptr(), self.flat_dim, P.g('fc1.w'), P.g('fc1.b'), self)
-    _linear_dgrad(B, 1024, self.flat_dim, dh, 1024, P.p('fc1.w'), gbufs['dy3'].data_ptr(), self.flat_dim,
-                  y3.data_ptr(), ACT_RELU, self)
+    self._head_backward(bufs, gbufs, dq)
+    self._fc1_wgrad(bufs, gbufs)
+    self._fc1_dgrad(bufs, gbufs)
     for i in (2, 1, 0):
-      g = self.geom(i, B)
-      dy = gbufs[f'dy{i + 1}'].data_ptr()
+      self._conv_wgrad(i, obs, bufs, gbufs, rows)
       if i > 0:
-        x, x_u8 = bufs[f'y{i}'].data_ptr(), 0
-      elif rows is not None:
-        x, x_u8 = rows.data_ptr(), 2
-      else:
-        x, x_u8 = obs.data_ptr(), int(obs.dtype == torch.uint8)
-      _capi.call('b200rl_conv2d_wgrad', x, x_u8, dy, P.g(f'conv{i + 1}.w'), P.g(f'conv{i + 1}.b'), g,
-                 self.precision, ws, wsb, st)
-      if i > 0:
-        _capi.call('b200rl_conv2d_dgrad', dy, P.p(f'conv{i + 1}.w'), gbufs[f'dy{i}'].data_ptr(), g,
-                   bufs[f'y{i}'].data_ptr(), ACT_RELU, self.precision, ws, wsb, st)
-
+        self._conv_dgrad(i, bufs, gbufs)
 
   def _backward_two_streams(self, obs, bufs, gbufs, dq, side, rows=None):
     self.backward_dense_part(bufs, gbufs, dq, side)
@@ -344,26 +482,23 @@ class DQNAtariNetwork(Network):
     return (split, self.params.size - split), (0, split)
 
   def backward_dense_part(self, bufs, gbufs, dq, side):
-    """Duelling head + fc1: parameter gradients of everything after the torso, and dy3."""
+    """Duelling head + fc1: parameter gradients of everything after the torso, and dy3.  dq = None: the fused head + TD
+    kernel has already produced gbufs['dh'] / ['dval'] / ['dadv']; only the head's parameter gradients remain (side)."""
     import torch
-    B, P = bufs['B'], self.params
     main = torch.cuda.current_stream()
-    h, y3 = bufs['h'], bufs['y3']
-    dh = gbufs['dh'].data_ptr()
     self.lane(0)
-    ws, wsb = self.ws
-    _capi.call('b200rl_duelling_head_bwd', B, self.A, 512, dq.data_ptr(), h.data_ptr(), 1024, P.p('v2.w'), P.p('a2.w'),
-               gbufs['dval'].data_ptr(), gbufs['dadv'].data_ptr(), dh, 1024, P.g('v2.w'), P.g('v2.b'), P.g('a2.w'),
-               P.g('a2.b'), ws, wsb, _capi.current_stream())
+    if dq is not None:
+      self._head_backward(bufs, gbufs, dq)
     ev = torch.cuda.Event()
     ev.record(main)
     side.wait_event(ev)
     with torch.cuda.stream(side):
       self.lane(1)
-      _linear_wgrad(B, 1024, self.flat_dim, dh, 1024, y3.data_ptr(), self.flat_dim, P.g('fc1.w'), P.g('fc1.b'), self)
+      if dq is None:
+        self.head_wgrad(bufs, gbufs)
+      self._fc1_wgrad(bufs, gbufs)
     self.lane(0)
-    _linear_dgrad(B, 1024, self.flat_dim, dh, 1024, P.p('fc1.w'), gbufs['dy3'].data_ptr(), self.flat_dim,
-                  y3.data_ptr(), ACT_RELU, self)
+    self._fc1_dgrad(bufs, gbufs)
     ev = torch.cuda.Event()
     ev.record(side)
     main.wait_event(ev)
@@ -371,32 +506,19 @@ class DQNAtariNetwork(Network):
   def backward_conv_part(self, obs, bufs, gbufs, side, rows=None):
     """The three convolutions: weight gradients on `side`, data gradients on the current stream."""
     import torch
-    B, P = bufs['B'], self.params
     main = torch.cuda.current_stream()
     for i in (2, 1, 0):
-      g = self.geom(i, B)
-      dy = gbufs[f'dy{i + 1}'].data_ptr()
       if i > 0:
-        x, x_u8 = bufs[f'y{i}'].data_ptr(), 0
         ev = torch.cuda.Event()
         ev.record(main)
         side.wait_event(ev)
         with torch.cuda.stream(side):
           self.lane(1)
-          ws1, wsb1 = self.ws
-          _capi.call('b200rl_conv2d_wgrad', x, x_u8, dy, P.g(f'conv{i + 1}.w'), P.g(f'conv{i + 1}.b'), g,
-                     self.precision, ws1, wsb1, _capi.current_stream())
+          self._conv_wgrad(i, obs, bufs, gbufs, rows)
         self.lane(0)
-        ws, wsb = self.ws
-        _capi.call('b200rl_conv2d_dgrad', dy, P.p(f'conv{i + 1}.w'), gbufs[f'dy{i}'].data_ptr(), g,
-                   bufs[f'y{i}'].data_ptr(), ACT_RELU, self.precision, ws, wsb, _capi.current_stream())
+        self._conv_dgrad(i, bufs, gbufs)
       else:   # conv1 has no data gradient: its weight gradient finishes the main chain
-        x, x_u8 = obs.data_ptr(), int(obs.dtype == torch.uint8)
-        if rows is not None:
-          x, x_u8 = rows.data_ptr(), 2
-        ws, wsb = self.ws
-        _capi.call('b200rl_conv2d_wgrad', x, x_u8, dy, P.g('conv1.w'), P.g('conv1.b'), g, self.precision, ws, wsb,
-                   _capi.current_stream())
+        self._conv_wgrad(0, obs, bufs, gbufs, rows)
     ev = torch.cuda.Event()
     ev.record(side)
     main.wait_event(ev)

@@ -411,8 +411,10 @@ class ReplayDataset:
     self.idx = torch.empty(B, dtype=torch.int64, device=dev)
     self.keys = torch.empty(B, dtype=torch.uint64, device=dev)
     self.prob = torch.empty(B, dtype=torch.float32, device=dev)
-    self.o_tm1 = torch.empty((B, max(table.obs_packer.nbytes, 1)), dtype=torch.uint8, device=dev)
-    self.o_t = torch.empty_like(self.o_tm1)
+    # o_tm1 and o_t are the two halves of ONE [2B, obs_bytes] buffer: a learner can run its network over both batches
+    # in a single pass (the online network sees o_tm1 and o_t, dqn/learning.py:123,125)
+    self.o_both = torch.empty((2 * B, max(table.obs_packer.nbytes, 1)), dtype=torch.uint8, device=dev)
+    self.o_tm1, self.o_t = self.o_both[:B], self.o_both[B:]
     self.a_tm1 = torch.empty((B, max(table.act_packer.nbytes, 1)), dtype=torch.uint8, device=dev)
     self.R = torch.empty(B, dtype=torch.float32, device=dev)
     self.D = torch.empty(B, dtype=torch.float32, device=dev)

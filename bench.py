@@ -257,7 +257,8 @@ def run_ours(args):
     pg = dist.group.WORLD
   P = peaks()
   B, n_step, items = 256, 3, args.items
-  precision = {'fp32': _capi.PRECISION_FP32, 'tc': _capi.PRECISION_BF16, 'bf16': _capi.PRECISION_BF16}[args.precision]
+  precision = {'fp32': _capi.PRECISION_FP32, 'tf32': _capi.PRECISION_TC, 'tc': _capi.PRECISION_TC,
+               'bf16': _capi.PRECISION_BF16FLOW}[args.precision]
 
   spec = specs.EnvironmentSpec(specs.Array(OBS_SHAPE, np.uint8), specs.DiscreteArray(NUM_ACTIONS),
                                specs.Array((), np.float32), specs.BoundedArray((), np.float32, 0., 1.))
@@ -362,15 +363,15 @@ def run_ours(args):
     u = torch.rand(B, device='cuda')
     stages['k1_sample'] = time_stage(lambda: table.sample_into(u, ds.idx, ds.keys, ds.prob, True), it, torch)
     stages['k3_gather_nstep'] = time_stage(lambda: table.gather_into(ds.idx, ds.o_tm1, ds.a_tm1, ds.R, ds.D, ds.o_t), it, torch)
-    o0 = learner._obs_view(ds.o_tm1)
-    stages['k6_forward_x1'] = time_stage(lambda: net.forward(o0, learner._bufs_train), it, torch)
-    stages['k6_backward'] = time_stage(lambda: net.backward(o0, learner._bufs_train, learner._gbufs, learner.dq), it, torch)
-    stages['k4_td'] = time_stage(lambda: _capi.call(
-        'b200rl_dqn_td', B, NUM_ACTIONS, learner._bufs_train['q'].data_ptr(), learner._bufs_tgt['q'].data_ptr(),
-        learner._bufs_sel['q'].data_ptr(), learner._actions_i32().data_ptr(), ds.R.data_ptr(), ds.D.data_ptr(),
-        ds.prob.data_ptr(), 0.99, 1.0, 0.2, 1.0, None, 1.0 / B, learner.td.data_ptr(), learner.loss_ps.data_ptr(),
-        learner.weight.data_ptr(), learner.priority.data_ptr(), learner.dq.data_ptr(), learner.loss.data_ptr(), 0,
-        _capi.current_stream()), it, torch)
+    # the network group exactly as the step runs it: target pass beside the batched online pass, then the fused
+    # head + K4 kernel and the backward (weight gradients beside data gradients), recorded into ONE graph and replayed,
+    # so the figure is the in-step time of the group, not a sum of serialised eager launches
+    g_fwd = learner._capture(learner._forwards)
+    g_bwd = learner._capture(learner._loss_backward)
+    g_net = learner._capture(lambda: (learner._forwards(), learner._loss_backward()))
+    stages['k6_forwards_in_graph'] = time_stage(g_fwd.replay, it, torch)
+    stages['k4_k6_loss_backward_in_graph'] = time_stage(g_bwd.replay, it, torch)
+    stages['k6_network_group_in_graph'] = time_stage(g_net.replay, it, torch)
     Pn = net.params
     scratch_p, scratch_m, scratch_v = torch.zeros_like(Pn.flat), torch.zeros_like(Pn.flat), torch.zeros_like(Pn.flat)
     stages['k7_adam'] = time_stage(lambda: _capi.call(
@@ -378,7 +379,7 @@ def run_ours(args):
         learner._num_steps.data_ptr(), 1e-3, 0.9, 0.999, 1e-8, 0, None, None, _capi.current_stream()), it, torch)
     stages['k2_update_priorities'] = time_stage(lambda: table.update_priorities_device(ds.keys, learner.priority), it, torch)
     del scratch_p, scratch_m, scratch_v
-  net_s = (3 * stages.get('k6_forward_x1', 0) + stages.get('k6_backward', 0))
+  net_s = stages.get('k6_network_group_in_graph', 0)
 
   # ---- PER sampling throughput (sample + gather), batch 256 and a large-batch sweep point
   per = {}
@@ -413,23 +414,31 @@ def run_ours(args):
     gpu_launches = int(learner.kernel_launches_per_step or 0) * args.steps
     if not gpu_launches:
       gpu_launches = int(lib.b200rl_launch_count() - launches0)
-    kname = 'k6_network_gemm_conv (3 forwards + 1 backward, fp32 SIMT FFMA)' if precision == 0 else \
-            'k6_network_gemm_conv (3 forwards + 1 backward; tcgen05 kind::tf32, TMA-fed: im2col for the convolutions incl. conv1 on uint8 frames via fp32 row images)'
+    kname = {0: 'k6_network_gemm_conv (3 forwards + 1 backward, fp32 SIMT FFMA)',
+             1: 'k6_network_gemm_conv (3 forwards + 1 backward; tcgen05 kind::tf32, TMA-fed, fp32 tensors)',
+             2: 'k6_network_gemm_conv (3 forwards + 1 backward; tcgen05 kind::f16 on bf16 activations / weight shadows / '
+                'gradients, TMA-fed: im2col for the convolutions incl. conv1 on uint8 frames via an integer-valued bf16 row image)'}[precision]
     achieved = STEP_FLOPS / net_s / 1e12 if net_s > 0 else None
     traffic = None    # dram bytes of the same kernel group from the committed `ncu --set full` capture (tensor-core mode)
-    prof = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'ncu_full_r01_tc_layers_summary.json')
-    if precision != 0 and os.path.exists(prof):
+    prof_name = {1: 'ncu_full_r01_tc_layers_summary.json', 2: 'ncu_full_r02_bf16_step_summary.json'}.get(precision)
+    prof = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', prof_name or 'none')
+    traffic_source = None
+    if os.path.exists(prof):
       traffic = json.load(open(prof)).get('step_group_dram_bytes')
+      traffic_source = f'profiles/{prof_name} (committed ncu --set full capture of the same kernels; not measured in this run)'
     out = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f32' if precision == 0 else 'tf32/bf16 tensor-core operands, f32 accumulate, f32 master weights and optimizer',
+        'dtype': {0: 'f32', 1: 'tf32 tensor-core operands, f32 accumulate, f32 master weights and optimizer',
+                  2: 'bf16 tensor-core operands (activations, weight shadows, back-propagated gradients), f32 accumulate, '
+                     'f32 master weights, weight gradients and optimizer'}[precision],
         'data': 'synthetic',
         'config': {'workload': 'DQN Atari-shaped 84x84x4 uint8, PER 1M items, batch 256, n=3 (BASELINE configs[1])',
                    'items_per_rank': info['size'], 'batch_per_rank': B, 'n_step': n_step, 'alpha': 0.6, 'beta': 0.2,
                    'network': 'DQNAtariNetwork(18), 8,018,611 params', 'optimizer': 'Adam 1e-3',
-                   'parallelism': f'dp{world}: per-rank replay shard, NCCL grad all-reduce' if world > 1 else 'single GPU',
-                   'cuda_graph': not args.no_graph and world == 1,
+                   'parallelism': (f'dp{world}: per-rank replay shard; gradient mean + Adam + parameter broadcast fused over '
+                                   'NVLink peer memory (NCCL for set-up only)') if world > 1 else 'single GPU',
+                   'cuda_graph': not args.no_graph,
                    'l2_policy': 'inputs larger than L2: 28 GB ring sampled at random + 160 MB of params/moments/grads per step'},
         'clocks': clk,
         'e2e': {'value': e2e_value, 'unit': 'updates/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
@@ -439,8 +448,10 @@ def run_ours(args):
         'gpu_launches': gpu_launches,
         'roofline': {'kernel': kname, 'bound': 'tensor', 'achieved': achieved, 'peak': P['tf_sustained'], 'unit': 'TFLOP/s',
                      'frac': (achieved / P['tf_sustained']) if achieved else None, 'traffic': traffic,
-                     'peak_source': f"{P['src']} (sustained bf16: kernel timed inside a long step)",
-                     'alg_flops_per_launch_group': STEP_FLOPS, 'group_seconds': net_s},
+                     'peak_source': f"{P['src']} (sustained bf16 dense peak: the group is timed inside a long run; "
+                                    'tf32 runs at half that rate)',
+                     'traffic_source': traffic_source, 'alg_flops_per_launch_group': STEP_FLOPS, 'group_seconds': net_s,
+                     'group_timing': 'CUDA events around replays of the captured network group (forwards + head/K4 + backward)'},
         'cpu_baseline': cpu_baseline,
         'stages_us': {k: v * 1e6 for k, v in stages.items()},
         'hbm_kernels': {
@@ -466,9 +477,9 @@ def main():
   ap.add_argument('--steps', type=int, default=2000)
   ap.add_argument('--warmup', type=int, default=50)
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-  ap.add_argument('--precision', default=os.environ.get('B200RL_PRECISION', 'tc'), choices=['fp32', 'tc', 'bf16'],
-                  help="'tc' (default; 'bf16' is an alias): tcgen05 tensor cores with tf32/bf16 operands, stated tolerance in "
-                       "tests/test_gpu_learner.py; 'fp32': SIMT FFMA, 1e-5 parity with the oracle")
+  ap.add_argument('--precision', default=os.environ.get('B200RL_PRECISION', 'bf16'), choices=['fp32', 'tf32', 'tc', 'bf16'],
+                  help="'bf16' (default): bf16 dataflow on tcgen05 (kind::f16); 'tf32' ('tc'): fp32 tensors with tf32 operands; "
+                       "both with the stated tolerances of tests/test_gpu_learner.py; 'fp32': SIMT FFMA, 1e-5 parity with the oracle")
   ap.add_argument('--items', type=int, default=1_000_000)
   ap.add_argument('--no-graph', action='store_true')
   ap.add_argument('--no-cpu-baseline', action='store_true')

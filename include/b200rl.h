@@ -264,6 +264,56 @@ int b200rl_tanh_to_spec_bwd(int32_t B, int32_t A, const float* da, const float* 
 /* batch_concat([obs, act]) (tf/utils.py:39-54) and its split for the backward */
 int b200rl_concat2(int32_t B, int32_t n0, int32_t n1, const float* x0, const float* x1, float* y, void* stream);
 int b200rl_split_second(int32_t B, int32_t n0, int32_t n1, const float* dy, float* dx1, void* stream);
+/* K4 fused into the duelling head (dqn/learning.py:123-154 after the three fc1 layers): for every sample the three
+ * heads q_tm1 = head(h_tm1), q_t_value = target_head(h_tgt), q_t_selector = head(h_sel), the double-Q TD error, Huber
+ * loss, importance weight and new priority of b200rl_dqn_td, and the head's data gradient
+ * dh = [dval * wv, dadv @ wa] * relu'(h_tm1) -- one launch instead of five on the step's critical path; arithmetic
+ * identical to the separate kernels.  wmax_dev is REQUIRED (b200rl_is_weight_max right after sampling; the global max
+ * for data-parallel learners); A <= 32.  q_*, dq nullable.  dh_bf16 = 1 writes dh as bf16 (bf16 dataflow). */
+int b200rl_dqn_head_td(int32_t B, int32_t A, int32_t H, const float* h_tm1, const float* h_sel, const float* h_tgt,
+                       int32_t ldh, const float* wv, const float* bv, const float* wa, const float* ba,
+                       const float* target_wv, const float* target_bv, const float* target_wa, const float* target_ba,
+                       const int32_t* a_tm1, const float* R, const float* D, const float* prob, float gamma,
+                       float huber_delta, double is_exponent, float max_abs_reward, const double* wmax_dev,
+                       float grad_scale, int32_t flags, float* q_tm1, float* q_t_value, float* q_t_selector, float* td,
+                       float* loss_per_sample, float* weight, float* priority, float* dq_tm1, float* dvalue, float* dadv,
+                       void* dh, int32_t lddh, int32_t dh_bf16, void* stream);
+/* out[0] = mean(x[0..n)) in a fixed order (the learner's scalar loss, dqn/learning.py:143-144) */
+int b200rl_mean(int32_t n, const float* x, float* out, void* stream);
+/* the four parameter gradients of the duelling head from dvalue / dadv (the part of b200rl_duelling_head_bwd that is
+ * off the critical path once b200rl_dqn_head_td has produced dh) */
+int b200rl_duelling_head_wgrad(int32_t B, int32_t A, int32_t H, const float* dvalue, const float* dadv, const float* h,
+                               int32_t ldh, float* dwv, float* dbv, float* dwa, float* dba, void* ws, int64_t ws_bytes,
+                               void* stream);
+
+/* ------------------------------------------------------------------ K6, bf16 dataflow (speed mode of the networks)
+ * Same layers as above with activations, weight SHADOWS and back-propagated gradients in bf16 (tcgen05 kind::f16, fp32
+ * accumulation; TMA-fed, im2col mode for the convolutions); master weights, weight gradients, biases and the optimizer
+ * stay fp32.  `*_bf16` flags name the element type of an OUTPUT or mask buffer (1 = bf16, 0 = fp32); x, w, dy are
+ * always bf16 here.  Shapes outside the kernels' coverage are an error (no fallback): channel counts 32 or multiples
+ * of 64, Cout in {32, 64, 128}, dense K and N multiples of 64, 16-byte aligned rows.  Stated tolerance: DESIGN.md. */
+int b200rl_bf16_from_f32(int64_t n, const float* src, void* dst_bf16, void* stream);   /* n % 8 == 0: weight shadows */
+/* First layer on uint8 frames (C = 4, kw * C = 32, networks/atari.py:44): zero-padded bf16 row image holding the
+ * INTEGER pixel values (exact in bf16); the 1/255 of atari_wrapper.py:303-304 is applied to the fp32 accumulator. */
+int64_t b200rl_conv2d_rows_bf16_bytes(const b200rl_conv_geom* g);
+int b200rl_conv2d_rows_bf16_from_u8(const void* x_u8, const b200rl_conv_geom* g, void* rows_bf16, int64_t rows_bytes,
+                                    void* stream);
+/* x_rows = 1: x is the row image above (first layer); 0: x is an NHWC bf16 activation */
+int b200rl_conv2d_fwd_bf16(const void* x, int x_rows, const void* w_bf16, const float* bias, void* y, int y_bf16,
+                           const b200rl_conv_geom* g, int act, void* ws, int64_t ws_bytes, void* stream);
+int b200rl_conv2d_wgrad_bf16(const void* x, int x_rows, const void* dy_bf16, float* dw, float* db,
+                             const b200rl_conv_geom* g, void* ws, int64_t ws_bytes, void* stream);
+int b200rl_conv2d_dgrad_bf16(const void* dy_bf16, const void* w_bf16, void* dx, int dx_bf16, const b200rl_conv_geom* g,
+                             const void* mask_y, int mask_bf16, int mask_act, void* stream);
+int b200rl_linear_fwd_bf16(int32_t M, int32_t N, int32_t K, const void* x_bf16, int32_t ldx, const void* w_bf16,
+                           const float* bias, void* y, int32_t ldy, int y_bf16, int act, void* ws, int64_t ws_bytes,
+                           void* stream);
+int b200rl_linear_dgrad_bf16(int32_t M, int32_t N, int32_t K, const void* dy_bf16, int32_t lddy, const void* w_bf16,
+                             void* dx, int32_t lddx, int dx_bf16, const void* mask_y, int mask_bf16, int mask_act,
+                             void* ws, int64_t ws_bytes, void* stream);
+int b200rl_linear_wgrad_bf16(int32_t M, int32_t N, int32_t K, const void* dy_bf16, int32_t lddy, const void* x_bf16,
+                             int32_t ldx, float* dw, float* db, void* ws, int64_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------ data-parallel learner
  * Replaces all_reduce('mean', grads) followed by optimizer.apply on every replica
  * (acme/agents/tf/crr/recurrent_learning.py:346-359, the reference's only multi-replica learner) by ONE kernel

