@@ -50,6 +50,7 @@ PROTOTYPES = {
     'b200rl_replay_flush': (c_int, [c_vp, c_vp]),
     'b200rl_replay_sample': (c_int, [c_vp, c_i32, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
     'b200rl_replay_gather': (c_int, [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'b200rl_replay_gather_rows': (c_int, [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.POINTER(ConvGeom), c_vp]),
     'b200rl_replay_update_priorities': (c_int, [c_vp, c_i32, c_vp, c_vp, c_vp]),
     'b200rl_replay_info': (c_int, [c_vp, C.POINTER(c_i64), C.POINTER(c_u64), C.POINTER(c_u64),
                                    C.POINTER(c_f32), c_vp]),
@@ -58,6 +59,9 @@ PROTOTYPES = {
     'b200rl_replay_tree_read': (c_int, [c_vp, c_i32, c_vp, c_i64, c_vp]),
     'b200rl_replay_tree_read_prefix': (c_int, [c_vp, c_i32, c_vp, c_i64, c_vp]),
     'b200rl_replay_mass_ptr': (c_int, [c_vp, C.POINTER(c_vp)]),
+    'b200rl_replay_host_state': (c_int, [c_vp, c_vp, c_i64, C.POINTER(c_i64), c_vp]),
+    'b200rl_replay_set_host_state': (c_int, [c_vp, c_vp, c_i64]),
+    'b200rl_replay_segment': (c_int, [c_vp, c_i32, C.POINTER(c_vp), C.POINTER(c_i64)]),
     'b200rl_replay_set_weights': (c_int, [c_vp, c_i64, c_vp, c_vp]),
     'b200rl_uniform': (c_int, [c_vp, c_i32, c_u64, c_vp, c_i64, c_vp]),
     'b200rl_dqn_td': (c_int, [c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_f32,
@@ -105,6 +109,7 @@ PROTOTYPES = {
     'b200rl_linear_fwd_bf16': (c_int, [c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_i32, c_int, c_int, c_vp, c_i64, c_vp]),
     'b200rl_linear_dgrad_bf16': (c_int, [c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp, c_i32, c_int, c_vp, c_int, c_int, c_vp,
                                          c_i64, c_vp]),
+    'b200rl_colsum_bf16': (c_int, [c_i32, c_i32, c_vp, c_i32, c_vp, c_vp, c_i64, c_vp]),
     'b200rl_linear_wgrad_bf16': (c_int, [c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_i64, c_vp]),
     'b200rl_layernorm_tanh_fwd': (c_int, [c_i32, c_i32, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp]),
     'b200rl_layernorm_tanh_bwd': (c_int, [c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),

@@ -373,6 +373,14 @@ static RowsView rows_view(const b200rl_conv_geom& g) {
   return v;
 }
 int64_t h_rows_bytes(const b200rl_conv_geom& g) { return rows_eligible(g) ? rows_view(g).bytes : 0; }
+// layout of the row image for replay.cu's gather (which writes it directly): padded rows per frame, bf16 elements per row
+int h_rows_layout(const b200rl_conv_geom& g, int* Hp, int* row_elems) {
+  if (!rows_eligible(g)) return 1;
+  const RowsView v = rows_view(g);
+  *Hp = v.Hp;
+  *row_elems = v.row_elems;
+  return 0;
+}
 
 __global__ void __launch_bounds__(256)
 u8_rows_to_bf16_kernel(const uint8_t* __restrict__ x, bf16* __restrict__ out, int H, int W, int Hp, int per_row /* pixels */,

@@ -76,6 +76,7 @@ int h_conv_fwd_rows(const __nv_bfloat16* rows, const __nv_bfloat16* w, const flo
 int h_conv_wgrad_rows(const __nv_bfloat16* rows, const __nv_bfloat16* dy, float* dw, float* db, const b200rl_conv_geom& g,
                       void* ws, int64_t wsb, cudaStream_t s);
 int h_f32_to_bf16(int64_t n, const float* src, __nv_bfloat16* dst, cudaStream_t s);
+int launch_colsum_bf16(int M, int N, const __nv_bfloat16* x, int ld, float* out, void* ws, int64_t ws_bytes, cudaStream_t stream);
 }  // namespace b200rl
 
 using namespace b200rl;
@@ -271,4 +272,12 @@ extern "C" int b200rl_linear_wgrad_bf16(int32_t M, int32_t N, int32_t K, const v
   B200RL_REQUIRE(dy && x && dw && ws && M >= 1 && N >= 1 && K >= 1 && lddy >= N && ldx >= K, "bad argument");
   H_CALL(h_linear_wgrad(M, N, K, (const bf16_t*)dy, lddy, (const bf16_t*)x, ldx, dw, db, ws, wsb, as_stream(stream)),
          "linear_wgrad_bf16");
+}
+
+/* out[n] = sum_m x[m, n] over bf16 rows: a layer's bias gradient on its own stream (the wgrad calls above do it in-line
+ * when db != NULL) */
+extern "C" int b200rl_colsum_bf16(int32_t M, int32_t N, const void* x_bf16, int32_t ld, float* out, void* ws, int64_t wsb,
+                                  void* stream) {
+  B200RL_REQUIRE(x_bf16 && out && ws && M >= 1 && N >= 1 && ld >= N, "bad argument");
+  return launch_colsum_bf16(M, N, (const bf16_t*)x_bf16, ld, out, ws, wsb, as_stream(stream));
 }

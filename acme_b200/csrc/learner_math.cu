@@ -462,10 +462,12 @@ __device__ __forceinline__ float head_q(const float* __restrict__ hrow, const fl
                                         const float* __restrict__ ba, int A, int lane, float (&hv)[HPL], float (&ha)[HPL],
                                         float& val_out, float& adv_out) {
   constexpr int H = 32 * HPL;
+  if (hrow) {
 #pragma unroll
-  for (int j = 0; j < HPL; ++j) {
-    hv[j] = hrow[lane + 32 * j];
-    ha[j] = hrow[H + lane + 32 * j];
+    for (int j = 0; j < HPL; ++j) {
+      hv[j] = hrow[lane + 32 * j];
+      ha[j] = hrow[H + lane + 32 * j];
+    }
   }
   float sv = 0.f;
 #pragma unroll
@@ -502,34 +504,63 @@ struct HeadTdArgs {
   void* dh;
 };
 
+constexpr int kHeadThreads = 256;
 template <int HPL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kHeadThreads)
 dqn_head_td_kernel(HeadTdArgs p) {
   constexpr int H = 32 * HPL;
-  extern __shared__ __align__(16) float sw[];   // online [A + 1][H], then target [A + 1][H]
+  extern __shared__ __align__(128) float sw[];   // online [A + 1][H], then target [A + 1][H]
+  __shared__ __align__(8) unsigned long long bar;
   float* swt = sw + (size_t)(p.A + 1) * H;
-  {
-    const int nv = H / 4, na = p.A * H / 4;
-    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
-      reinterpret_cast<float4*>(sw)[i] = __ldg(reinterpret_cast<const float4*>(p.wv) + i);
-      reinterpret_cast<float4*>(swt)[i] = __ldg(reinterpret_cast<const float4*>(p.twv) + i);
-    }
-    for (int i = threadIdx.x; i < na; i += blockDim.x) {
-      reinterpret_cast<float4*>(sw + H)[i] = __ldg(reinterpret_cast<const float4*>(p.wa) + i);
-      reinterpret_cast<float4*>(swt + H)[i] = __ldg(reinterpret_cast<const float4*>(p.twa) + i);
-    }
-    __syncthreads();
+  // the four weight blocks arrive by bulk async copies (one instruction each, completion on an mbarrier) while the
+  // warps below already fetch their hidden rows
+  if (threadIdx.x == 0) {
+    const uint32_t b32 = (uint32_t)__cvta_generic_to_shared(&bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b32) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t nv = H * 4, na = p.A * H * 4;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b32), "r"(2 * (nv + na)) : "memory");
+    const float* src[4] = {p.wv, p.wa, p.twv, p.twa};
+    float* dst[4] = {sw, sw + H, swt, swt + H};
+    const uint32_t nb[4] = {nv, na, nv, na};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       (uint32_t)__cvta_generic_to_shared(dst[i])),
+                   "l"(src[i]), "r"(nb[i]), "r"(b32)
+                   : "memory");
   }
+  __syncthreads();   // the barrier is initialised before anyone waits on it
   const int lane = threadIdx.x & 31;
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (b >= p.B) return;
   const int A = p.A;
-  float hv[HPL], ha[HPL], tv[HPL], ta[HPL], val, adv;
+  float hv[HPL], ha[HPL], tv[HPL], ta[HPL], sv_[HPL], sa_[HPL], val, adv;
+  {   // the three hidden rows of this sample: in flight while the weights land
+    const float *r0 = p.h_tm1 + (size_t)b * p.ldh, *r1 = p.h_tgt + (size_t)b * p.ldh, *r2 = p.h_sel + (size_t)b * p.ldh;
+#pragma unroll
+    for (int j = 0; j < HPL; ++j) {
+      hv[j] = r0[lane + 32 * j]; ha[j] = r0[H + lane + 32 * j];
+      tv[j] = r1[lane + 32 * j]; ta[j] = r1[H + lane + 32 * j];
+      sv_[j] = r2[lane + 32 * j]; sa_[j] = r2[H + lane + 32 * j];
+    }
+  }
+  {
+    const uint32_t b32 = (uint32_t)__cvta_generic_to_shared(&bar);
+    uint32_t ok;
+    do {
+      asm volatile(
+          "{\n.reg .pred q;\nmbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0;\nselp.u32 %0, 1, 0, q;\n}\n"
+          : "=r"(ok)
+          : "r"(b32)
+          : "memory");
+    } while (!ok);
+  }
   // learning.py:124-125: the target network and the online network on o_t
-  const float q_tv = head_q<HPL>(p.h_tgt + (size_t)b * p.ldh, swt, p.tbv, p.tba, A, lane, tv, ta, val, adv);
-  const float q_ts = head_q<HPL>(p.h_sel + (size_t)b * p.ldh, sw, p.bv, p.ba, A, lane, tv, ta, val, adv);
+  const float q_tv = head_q<HPL>(nullptr, swt, p.tbv, p.tba, A, lane, tv, ta, val, adv);
+  const float q_ts = head_q<HPL>(nullptr, sw, p.bv, p.ba, A, lane, sv_, sa_, val, adv);
   // learning.py:123: the online network on o_tm1 (its hidden row stays in registers for the backward)
-  const float q_tm1 = head_q<HPL>(p.h_tm1 + (size_t)b * p.ldh, sw, p.bv, p.ba, A, lane, hv, ha, val, adv);
+  const float q_tm1 = head_q<HPL>(nullptr, sw, p.bv, p.ba, A, lane, hv, ha, val, adv);
   if (lane < A) {
     if (p.q_tm1) p.q_tm1[(size_t)b * A + lane] = q_tm1;
     if (p.q_tv) p.q_tv[(size_t)b * A + lane] = q_tv;
@@ -1025,13 +1056,13 @@ extern "C" int b200rl_dqn_head_td(int32_t B, int32_t A, int32_t H, const float* 
     B200RL_CUDA_OK(cudaFuncSetAttribute(dqn_head_td_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
-  const int blocks = ceil_div(B * 32, 128);
+  const int blocks = ceil_div(B * 32, kHeadThreads);
   cudaStream_t st = as_stream(stream);
   switch (H) {
-    case 512: dqn_head_td_kernel<16><<<blocks, 128, smem, st>>>(p); break;
-    case 256: dqn_head_td_kernel<8><<<blocks, 128, smem, st>>>(p); break;
-    case 128: dqn_head_td_kernel<4><<<blocks, 128, smem, st>>>(p); break;
-    case 64: dqn_head_td_kernel<2><<<blocks, 128, smem, st>>>(p); break;
+    case 512: dqn_head_td_kernel<16><<<blocks, kHeadThreads, smem, st>>>(p); break;
+    case 256: dqn_head_td_kernel<8><<<blocks, kHeadThreads, smem, st>>>(p); break;
+    case 128: dqn_head_td_kernel<4><<<blocks, kHeadThreads, smem, st>>>(p); break;
+    case 64: dqn_head_td_kernel<2><<<blocks, kHeadThreads, smem, st>>>(p); break;
     default: set_error("fused duelling head: hidden size %d not in {64,128,256,512}", H); return B200RL_EINVAL;
   }
   B200RL_LAUNCH_OK();

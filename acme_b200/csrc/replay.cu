@@ -13,9 +13,12 @@
 #include <mutex>
 #include <vector>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace b200rl {
+int h_rows_layout(const b200rl_conv_geom& g, int* Hp, int* row_elems);   // gemm_bf16.cu
 
 static thread_local std::string g_last_error;
 static unsigned long long g_launches = 0;
@@ -132,6 +135,63 @@ gather_kernel(RingView r, const long long* __restrict__ idx, uint8_t* __restrict
     for (int i = threadIdx.x; i < (r.obs_bytes >> 2); i += 256) d1[i] = __ldg(s1 + i);
   } else {
     for (int i = threadIdx.x; i < r.obs_bytes; i += 256) dst[i] = src[i];
+  }
+  if (which == 0) {
+    const uint8_t* as = r.act + (size_t)slot * r.act_stride;
+    uint8_t* ad = a_tm1 + (size_t)b * r.act_bytes;
+    for (int i = threadIdx.x; i < r.act_bytes; i += 256) ad[i] = as[i];
+    if (threadIdx.x == 0) {
+      // acme/adders/reverb/transition.py:135-145, fp32, every op rounded separately (no FMA)
+      int cur = slot;
+      const int len = r.item_len[pos];
+      float Rv = r.rew[cur], Dv = r.disc[cur];
+      cur = r.next[cur];
+      for (int j = 1; j < len; ++j) {
+        Dv = __fmul_rn(Dv, r.gamma);
+        Rv = __fadd_rn(Rv, __fmul_rn(r.rew[cur], Dv));
+        Dv = __fmul_rn(Dv, r.disc[cur]);
+        cur = r.next[cur];
+      }
+      R[b] = Rv;
+      D[b] = Dv;
+    }
+  }
+}
+
+// K3 with the first layer's input fused in: besides the uint8 batch rows the kernel writes the frames straight into the
+// zero-padded bf16 ROW IMAGE that conv1 reads through TMA (gemm_bf16.cu: integer pixel values, exact in bf16; padding
+// stays zero from allocation), so no separate conversion pass runs between replay and the network.
+// Frames are [H][W][4] uint8; one 16-byte vector = 4 pixels x 4 channels -> 16 bf16 = two 16-byte stores.
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(RingView r, const long long* __restrict__ idx, uint8_t* __restrict__ o_tm1, uint8_t* __restrict__ a_tm1,
+                   float* __restrict__ R, float* __restrict__ D, uint8_t* __restrict__ o_t, uint4* __restrict__ rows_tm1,
+                   uint4* __restrict__ rows_t, int W4 /* 16-byte vectors per image row */, int pad_left, int pad_top, int Hp,
+                   int row_v16 /* 16-byte units per padded row */) {
+  const int b = blockIdx.x;
+  const long long pos = idx[b];
+  const int which = blockIdx.y;
+  const int slot = which == 0 ? r.item_start[pos] : r.item_end[pos];
+  const int4* s4 = reinterpret_cast<const int4*>(r.obs + (size_t)slot * r.obs_stride);
+  int4* d4 = reinterpret_cast<int4*>((which == 0 ? o_tm1 : o_t) + (size_t)b * r.obs_bytes);
+  uint4* rows = (which == 0 ? rows_tm1 : rows_t) + (size_t)b * Hp * row_v16;
+  const int nv = r.obs_bytes >> 4;
+  for (int i = threadIdx.x; i < nv; i += 256) {
+    const int4 v = __ldg(s4 + i);
+    d4[i] = v;
+    const int y = i / W4, xv = i - y * W4;
+    const uint32_t px[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
+    uint32_t o[8];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const __nv_bfloat162 lo = __floats2bfloat162_rn((float)(px[p] & 0xffu), (float)((px[p] >> 8) & 0xffu));
+      const __nv_bfloat162 hi = __floats2bfloat162_rn((float)((px[p] >> 16) & 0xffu), (float)(px[p] >> 24));
+      o[2 * p] = *reinterpret_cast<const uint32_t*>(&lo);
+      o[2 * p + 1] = *reinterpret_cast<const uint32_t*>(&hi);
+    }
+    // pixel x = 4 xv sits at bf16 element (x + pad_left) * 4 of the padded row = 16-byte unit (x + pad_left) / 2
+    uint4* dst = rows + (size_t)(y + pad_top) * row_v16 + ((4 * xv + pad_left) >> 1);
+    dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
   }
   if (which == 0) {
     const uint8_t* as = r.act + (size_t)slot * r.act_stride;
@@ -727,6 +787,133 @@ extern "C" int b200rl_replay_reset(b200rl_replay* h, void* stream_) {
   return flush_impl(h, stream);
 }
 
+
+// ------------------------------------------------------------------------------ checkpoint / resume
+// The reference never checkpoints replay contents (acme/tf/savers.py:76-167 saves learner state only); a resumed
+// run there starts from an empty table.  Here the whole shard can be saved: its device arrays are exposed one by one
+// (the host side copies them with any D2H mechanism) and the host bookkeeping is serialised into one blob.
+enum { SEG_OBS = 0, SEG_ACT, SEG_REW, SEG_DISC, SEG_NEXT, SEG_ITEM_START, SEG_ITEM_END, SEG_ITEM_LEN, SEG_TREE, SEG_STATE, SEG_COUNT };
+
+extern "C" int b200rl_replay_segment(b200rl_replay* h, int32_t which, void** dev_ptr, int64_t* bytes) {
+  B200RL_REQUIRE(h && dev_ptr && bytes, "null argument");
+  B200RL_LOCK(h);
+  const RingView& r = h->ring;
+  const bool payload = h->cfg.obs_bytes > 0;
+  void* p = nullptr;
+  int64_t n = 0;
+  switch (which) {
+    case SEG_OBS: p = r.obs; n = payload ? h->S * h->obs_stride : 0; break;
+    case SEG_ACT: p = r.act; n = payload ? h->S * (int64_t)h->act_stride : 0; break;
+    case SEG_REW: p = r.rew; n = payload ? h->S * 4 : 0; break;
+    case SEG_DISC: p = r.disc; n = payload ? h->S * 4 : 0; break;
+    case SEG_NEXT: p = r.next; n = payload ? h->S * 4 : 0; break;
+    case SEG_ITEM_START: p = r.item_start; n = payload ? h->M * 4 : 0; break;
+    case SEG_ITEM_END: p = r.item_end; n = payload ? h->M * 4 : 0; break;
+    case SEG_ITEM_LEN: p = r.item_len; n = payload ? h->M * 4 : 0; break;
+    case SEG_TREE: p = h->d_tree; n = h->tree_floats * 4; break;
+    case SEG_STATE: p = h->d_state; n = sizeof(ReplayState); break;
+    default: set_error("unknown replay segment %d (0..%d)", which, SEG_COUNT - 1); return B200RL_EINVAL;
+  }
+  *dev_ptr = p;
+  *bytes = n;
+  return B200RL_OK;
+}
+
+namespace {
+struct BlobWriter {
+  std::vector<uint8_t> b;
+  void u64(uint64_t v) { const uint8_t* p = (const uint8_t*)&v; b.insert(b.end(), p, p + 8); }
+  void bytes(const void* p, size_t n) { const uint8_t* q = (const uint8_t*)p; b.insert(b.end(), q, q + n); }
+};
+struct BlobReader {
+  const uint8_t* p; size_t n, at = 0; bool ok = true;
+  uint64_t u64() { uint64_t v = 0; if (at + 8 > n) { ok = false; return 0; } memcpy(&v, p + at, 8); at += 8; return v; }
+  void bytes(void* dst, size_t k) { if (at + k > n) { ok = false; return; } memcpy(dst, p + at, k); at += k; }
+};
+constexpr uint64_t kBlobMagic = 0x62323030726c7631ull;   // "b200rlv1"
+}  // namespace
+
+static void write_host_state(b200rl_replay* h, BlobWriter& w) {
+  w.u64(kBlobMagic);
+  w.u64((uint64_t)h->M); w.u64((uint64_t)h->S); w.u64((uint64_t)h->cfg.obs_bytes); w.u64((uint64_t)h->cfg.act_bytes);
+  w.u64(h->slot_head); w.u64(h->item_head); w.u64(h->item_tail);
+  w.u64(h->item_start_seq.size());
+  w.bytes(h->item_start_seq.data(), h->item_start_seq.size() * 8);
+  w.u64(h->start_min.size());
+  for (auto& e : h->start_min) { w.u64(e.first); w.u64(e.second); }
+  w.u64(h->writers.size());
+  for (auto& wr : h->writers) {
+    w.u64(wr.in_use ? 1 : 0); w.u64((uint64_t)wr.k); w.u64(wr.has_pending ? 1 : 0);
+    uint32_t f[2]; memcpy(&f[0], &wr.pending_rew, 4); memcpy(&f[1], &wr.pending_disc, 4);
+    w.u64(((uint64_t)f[1] << 32) | f[0]);
+    w.u64(wr.hist.size());
+    for (uint64_t s : wr.hist) w.u64(s);
+    w.u64(wr.pending_act.size());
+    w.bytes(wr.pending_act.data(), wr.pending_act.size());
+  }
+}
+
+// Host bookkeeping (key counters, FIFO bounds, every open writer's episode window) as one blob.  Staged steps are
+// flushed first, so the device arrays read afterwards are complete.  blob == NULL: only the size is returned.
+extern "C" int b200rl_replay_host_state(b200rl_replay* h, void* blob, int64_t capacity, int64_t* size, void* stream) {
+  B200RL_REQUIRE(h && size, "null argument");
+  B200RL_LOCK(h);
+  int rc = ensure_device(h);
+  if (rc) return rc;
+  rc = flush_impl(h, as_stream(stream));
+  if (rc) return rc;
+  BlobWriter w;
+  write_host_state(h, w);
+  *size = (int64_t)w.b.size();
+  if (blob) {
+    B200RL_REQUIRE(capacity >= *size, "blob buffer too small: need %lld bytes", (long long)*size);
+    memcpy(blob, w.b.data(), w.b.size());
+  }
+  return B200RL_OK;
+}
+
+// Inverse of b200rl_replay_host_state: the handle must have the geometry the blob was saved from; the caller restores
+// the device arrays (b200rl_replay_segment) around this call, in any order, before the next sample / append.
+extern "C" int b200rl_replay_set_host_state(b200rl_replay* h, const void* blob, int64_t size) {
+  B200RL_REQUIRE(h && blob && size >= 64, "bad argument");
+  B200RL_LOCK(h);
+  BlobReader r{(const uint8_t*)blob, (size_t)size};
+  B200RL_REQUIRE(r.u64() == kBlobMagic, "not a b200rl replay state blob");
+  const uint64_t M = r.u64(), S = r.u64(), ob = r.u64(), ab = r.u64();
+  B200RL_REQUIRE((int64_t)M == h->M && (int64_t)S == h->S && (int64_t)ob == h->cfg.obs_bytes && (int64_t)ab == h->cfg.act_bytes,
+                 "replay geometry differs from the saved one (max_items %llu, slots %llu, obs %llu B, act %llu B)",
+                 (unsigned long long)M, (unsigned long long)S, (unsigned long long)ob, (unsigned long long)ab);
+  h->n_obs = h->n_fill = h->n_item = 0;
+  h->slot_head = r.u64(); h->item_head = r.u64(); h->item_tail = r.u64();
+  uint64_t n = r.u64();
+  B200RL_REQUIRE(r.ok && n <= (uint64_t)h->M, "corrupt blob");
+  h->item_start_seq.assign(n, 0);
+  r.bytes(h->item_start_seq.data(), n * 8);
+  n = r.u64();
+  B200RL_REQUIRE(r.ok && n <= (uint64_t)h->M, "corrupt blob");
+  h->start_min.clear();
+  for (uint64_t i = 0; i < n; ++i) { uint64_t a = r.u64(), b = r.u64(); h->start_min.emplace_back(a, b); }
+  n = r.u64();
+  B200RL_REQUIRE(r.ok && n <= 65536, "corrupt blob");
+  h->writers.assign(n, Writer());
+  for (auto& wr : h->writers) {
+    wr.in_use = r.u64() != 0; wr.k = (int64_t)r.u64(); wr.has_pending = r.u64() != 0;
+    const uint64_t f = r.u64();
+    uint32_t lo = (uint32_t)f, hi = (uint32_t)(f >> 32);
+    memcpy(&wr.pending_rew, &lo, 4); memcpy(&wr.pending_disc, &hi, 4);
+    uint64_t k = r.u64();
+    B200RL_REQUIRE(r.ok && k <= 1024, "corrupt blob");
+    for (uint64_t i = 0; i < k; ++i) wr.hist.push_back(r.u64());
+    k = r.u64();
+    B200RL_REQUIRE(r.ok && k <= (1u << 20), "corrupt blob");
+    wr.pending_act.resize(k);
+    r.bytes(wr.pending_act.data(), k);
+  }
+  B200RL_REQUIRE(r.ok, "truncated blob");
+  h->state_dirty = false;      // d_state is one of the restored segments
+  return B200RL_OK;
+}
+
 // ----------------------------------------------------------------------------- sample path
 extern "C" int b200rl_replay_sample(b200rl_replay* h, int32_t B, const float* u_dev, int stratified,
                                     int64_t* idx_dev, uint64_t* keys_dev, float* prob_dev, void* stream) {
@@ -760,6 +947,27 @@ extern "C" int b200rl_replay_gather(b200rl_replay* h, int32_t B, const int64_t* 
     gather_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(h->ring, (const long long*)idx_dev, (uint8_t*)o_tm1, (uint8_t*)a_tm1, R, D, (uint8_t*)o_t);
   else
     gather_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(h->ring, (const long long*)idx_dev, (uint8_t*)o_tm1, (uint8_t*)a_tm1, R, D, (uint8_t*)o_t);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_replay_gather_rows(b200rl_replay* h, int32_t B, const int64_t* idx_dev, void* o_tm1, void* a_tm1, float* R,
+                                         float* D, void* o_t, void* rows_tm1, void* rows_t, const b200rl_conv_geom* g,
+                                         void* stream) {
+  B200RL_REQUIRE(h && idx_dev && o_tm1 && a_tm1 && R && D && o_t && rows_tm1 && rows_t && g, "null argument");
+  B200RL_LOCK(h);
+  B200RL_REQUIRE(B >= 1, "batch must be >= 1");
+  B200RL_REQUIRE(g->C == 4 && g->W % 4 == 0 && h->cfg.obs_bytes == g->H * g->W * g->C,
+                 "gather_rows: the table's observations are not [H][W][4] uint8 frames of this geometry");
+  B200RL_REQUIRE(g->pad_left % 2 == 0, "gather_rows: pad_left must be even (16-byte aligned pixel pairs)");
+  int Hp = 0, row_elems = 0;
+  B200RL_REQUIRE(h_rows_layout(*g, &Hp, &row_elems) == 0, "gather_rows: geometry not eligible for a row image");
+  B200RL_REQUIRE(((((uintptr_t)o_tm1 | (uintptr_t)o_t | (uintptr_t)rows_tm1 | (uintptr_t)rows_t)) & 15) == 0, "buffers must be 16-byte aligned");
+  int rc = ensure_device(h);
+  if (rc) return rc;
+  gather_rows_kernel<<<dim3(B, 2), 256, 0, as_stream(stream)>>>(h->ring, (const long long*)idx_dev, (uint8_t*)o_tm1, (uint8_t*)a_tm1, R, D,
+                                                               (uint8_t*)o_t, (uint4*)rows_tm1, (uint4*)rows_t, g->W / 4, g->pad_left,
+                                                               g->pad_top, Hp, row_elems / 8);
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }

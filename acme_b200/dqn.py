@@ -146,6 +146,14 @@ class DQNLearner(core.Learner, core.Saveable):
     self._obs_shape = tuple(obs_spec.shape)
     self._obs_dtype = np.dtype(obs_spec.dtype)
     self._act_dtype = np.dtype(t.signature[1].dtype)
+    # bf16 dataflow on uint8 frames: K3 writes the first conv layer's row image itself (no conversion pass)
+    self._gather_rows = None
+    if (self._fused and getattr(network, 'flow', False) and self._obs_dtype == np.uint8 and
+        os.environ.get('B200RL_GATHER_ROWS', '1') != '0'):
+      buf = network.rows_buffer(2 * B, 'all')
+      fb = network.rows_frame_bytes()
+      if buf is not None and fb:
+        self._gather_rows = (buf.data_ptr(), buf.data_ptr() + B * fb, network.geom(0, 1))
 
   # ------------------------------------------------------------------ one update on the device
   def _obs_view(self, rows):
@@ -241,7 +249,11 @@ class DQNLearner(core.Learner, core.Saveable):
     main = torch.cuda.current_stream()
     rows_all = rows_t = None
     self._rows_tm1 = None
-    if hasattr(net, 'prepare_frames'):
+    if self._gather_rows is not None:
+      rows_all = net.rows_buffer(2 * B, 'all')               # written by K3 (b200rl_replay_gather_rows)
+      self._rows_tm1 = rows_all
+      rows_t = rows_all[B * net.rows_frame_bytes():]
+    elif hasattr(net, 'prepare_frames'):
       rows_all = net.prepare_frames(o_all, 'all')            # one row image of the 2B frames
       if rows_all is not None:
         self._rows_tm1 = rows_all                            # its first B frames: conv1's weight gradient
@@ -547,7 +559,7 @@ class DQNLearner(core.Learner, core.Saveable):
     """The gradient half of a step: K1, K3, forwards, K4, backward, K2."""
     self._stamp(0)
     self._sample(uniforms)
-    self._dataset.gather_only()
+    self._dataset.gather_only(self._gather_rows)
     self._forwards()
     self._loss_backward()
     self._stamp(4)
@@ -627,7 +639,7 @@ class DQNLearner(core.Learner, core.Saveable):
     lib = _capi.load()
     n0 = lib.b200rl_launch_count()
     self._sample(uniforms)
-    self._dataset.gather_only()
+    self._dataset.gather_only(self._gather_rows)
     self._forward_loss()
     if self._px is None:
       self._dp.sum_(self._net.params.grad)   # all-reduce(SUM); Adam multiplies by 1/R (mean), then applies
@@ -661,7 +673,7 @@ class DQNLearner(core.Learner, core.Saveable):
         def whole():
           self._stamp(0)
           self._sample()
-          self._dataset.gather_only()
+          self._dataset.gather_only(self._gather_rows)
           self._forward_loss()
           self._apply()
         self._graphs = [self._capture(whole)]
@@ -670,7 +682,7 @@ class DQNLearner(core.Learner, core.Saveable):
           dist.barrier(group=self._dp.group)    # every rank has its graph before anyone spins on a peer
       else:
         def second():
-          self._dataset.gather_only()
+          self._dataset.gather_only(self._gather_rows)
           self._forwards()
         if self._concurrent and hasattr(self._net, 'grad_buckets'):
           self._graphs = [self._capture(self._sample), self._capture(second),

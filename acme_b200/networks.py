@@ -298,6 +298,19 @@ class DQNAtariNetwork(Network):
     import ctypes
     return int(_capi.load().b200rl_conv2d_rows_bf16_bytes(ctypes.byref(self.geom(0, 1)))) if self.flow else 0
 
+  def rows_buffer(self, B: int, slot: str = 'x'):
+    """The (cached, zero-initialised) row-image buffer of B frames; None if the geometry has no row image.  Zeroed because
+    `b200rl_replay_gather_rows` writes only the frames' interior and relies on the padding staying zero."""
+    import ctypes
+    import torch
+    cache = self.__dict__.setdefault('_rows', {})
+    if (slot, B) not in cache:
+      lib = _capi.load()
+      fn = lib.b200rl_conv2d_rows_bf16_bytes if self.flow else lib.b200rl_conv2d_rows_bytes
+      nbytes = int(fn(ctypes.byref(self.geom(0, B))))
+      cache[(slot, B)] = (torch.zeros(nbytes, dtype=torch.uint8, device=torch.device('cuda', self.device)) if nbytes > 0 else None)
+    return cache[(slot, B)]
+
   def prepare_frames(self, obs, slot: str = 'x'):
     """uint8 frames -> the row image that first-layer calls accept, built ONCE for all the passes over the same frames
     (two networks on o_t; forward + weight gradient on o_tm1).  Precision 1: zero-padded fp32 rows x/255
@@ -309,13 +322,7 @@ class DQNAtariNetwork(Network):
     if self.precision == _capi.PRECISION_FP32 or obs.dtype != torch.uint8:
       return None
     B = obs.shape[0]
-    cache = self.__dict__.setdefault('_rows', {})
-    lib = _capi.load()
-    if (slot, B) not in cache:
-      fn = lib.b200rl_conv2d_rows_bf16_bytes if self.flow else lib.b200rl_conv2d_rows_bytes
-      nbytes = int(fn(ctypes.byref(self.geom(0, B))))
-      cache[(slot, B)] = (torch.empty(nbytes, dtype=torch.uint8, device=obs.device) if nbytes > 0 else None)
-    buf = cache[(slot, B)]
+    buf = self.rows_buffer(B, slot)
     if buf is None:
       if self.flow:
         raise ValueError('the bf16 dataflow needs the Atari first-layer geometry (C = 4, kw * C = 32)')
@@ -417,7 +424,15 @@ class DQNAtariNetwork(Network):
       _linear_dgrad(B, 1024, self.flat_dim, gbufs['dh'].data_ptr(), 1024, P.p('fc1.w'), gbufs['dy3'].data_ptr(), self.flat_dim,
                     bufs['y3'].data_ptr(), ACT_RELU, self)
 
-  def _conv_wgrad(self, i, obs, bufs, gbufs, rows):
+  def _conv_bias_grad(self, i, bufs, gbufs):
+    """bf16 dataflow: db of conv layer i+1 = column sums of dy, as its own launch (so it can sit on another stream)."""
+    B, P = bufs['B'], self.params
+    ws, wsb = self.ws
+    _, _, _, co, _, oh, _ = self.convs[i]
+    _capi.call('b200rl_colsum_bf16', B * oh * oh, co, gbufs[f'dy{i + 1}'].data_ptr(), co, P.g(f'conv{i + 1}.b'), ws, wsb,
+               _capi.current_stream())
+
+  def _conv_wgrad(self, i, obs, bufs, gbufs, rows, bias: bool = True):
     import torch
     B, P = bufs['B'], self.params
     ws, wsb = self.ws
@@ -430,8 +445,8 @@ class DQNAtariNetwork(Network):
         if rows is None:
           rows = self.prepare_frames(obs, 'bwd')
         x, x_rows = rows.data_ptr(), 1
-      _capi.call('b200rl_conv2d_wgrad_bf16', x, x_rows, dy, P.g(f'conv{i + 1}.w'), P.g(f'conv{i + 1}.b'), g, ws, wsb,
-                 _capi.current_stream())
+      _capi.call('b200rl_conv2d_wgrad_bf16', x, x_rows, dy, P.g(f'conv{i + 1}.w'), P.g(f'conv{i + 1}.b') if bias else None, g,
+                 ws, wsb, _capi.current_stream())
       return
     if i > 0:
       x, x_u8 = bufs[f'y{i}'].data_ptr(), 0
@@ -518,7 +533,15 @@ class DQNAtariNetwork(Network):
         self.lane(0)
         self._conv_dgrad(i, bufs, gbufs)
       else:   # conv1 has no data gradient: its weight gradient finishes the main chain
-        self._conv_wgrad(0, obs, bufs, gbufs, rows)
+        if self.flow:   # ... and its bias gradient runs beside it
+          ev = torch.cuda.Event()
+          ev.record(main)
+          side.wait_event(ev)
+          with torch.cuda.stream(side):
+            self.lane(1)
+            self._conv_bias_grad(0, bufs, gbufs)
+          self.lane(0)
+        self._conv_wgrad(0, obs, bufs, gbufs, rows, bias=not self.flow)
     ev = torch.cuda.Event()
     ev.record(side)
     main.wait_event(ev)

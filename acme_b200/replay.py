@@ -251,9 +251,60 @@ class Table:
     _capi.call('b200rl_replay_gather', self.handle, idx.shape[0], _capi.ptr(idx), _capi.ptr(o_tm1),
                _capi.ptr(a_tm1), _capi.ptr(R), _capi.ptr(D), _capi.ptr(o_t), _capi.current_stream())
 
+  def gather_rows_into(self, idx, o_tm1, a_tm1, R, D, o_t, rows_tm1_ptr: int, rows_t_ptr: int, geom):
+    """K3 that also writes the first conv layer's bf16 row images (`b200rl_replay_gather_rows`)."""
+    _capi.call('b200rl_replay_gather_rows', self.handle, idx.shape[0], _capi.ptr(idx), _capi.ptr(o_tm1), _capi.ptr(a_tm1),
+               _capi.ptr(R), _capi.ptr(D), _capi.ptr(o_t), rows_tm1_ptr, rows_t_ptr, geom, _capi.current_stream())
+
   def update_priorities_device(self, keys, priorities):
     _capi.call('b200rl_replay_update_priorities', self.handle, keys.shape[0], _capi.ptr(keys),
                _capi.ptr(priorities), _capi.current_stream())
+
+  # -- core.Saveable: the whole shard (SURVEY §8f-4).  The reference's checkpointers save learner state only
+  # (`acme/tf/savers.py:76-167`); a table restored here continues exactly where the saved one stopped: same keys, same
+  # FIFO position, same priorities, open writers keep their episode windows.
+  _SEGMENTS = ('obs', 'act', 'rew', 'disc', 'next', 'item_start', 'item_end', 'item_len', 'tree', 'key_range')
+
+  def _segment(self, which: int):
+    import torch
+    p, n = C.c_void_p(), C.c_int64()
+    _capi.call('b200rl_replay_segment', self.handle, which, C.byref(p), C.byref(n))
+    if not n.value:
+      return None
+    return torch.as_tensor(_RawBytes(p.value, n.value), device=torch.device('cuda', self.device))
+
+  def save(self):
+    """Host copy of the shard: {'host': bookkeeping blob, 'segments': {name: uint8 array}, 'geometry': ...}.  Staged
+    steps are flushed first.  The observation ring is copied whole (28 KB per Atari slot): size the table accordingly."""
+    import torch
+    st = _capi.current_stream()
+    size = C.c_int64()
+    _capi.call('b200rl_replay_host_state', self.handle, None, 0, C.byref(size), st)
+    blob = np.empty(size.value, np.uint8)
+    _capi.call('b200rl_replay_host_state', self.handle, blob.ctypes.data, size.value, C.byref(size), st)
+    torch.cuda.current_stream().synchronize()
+    segs = {}
+    for which, name in enumerate(self._SEGMENTS):
+      t = self._segment(which)
+      if t is not None:
+        segs[name] = t.cpu().numpy()
+    return dict(host=blob[:size.value].copy(), segments=segs,
+                geometry=dict(max_size=self.max_size, slot_capacity=self.slot_capacity, alpha=self.alpha,
+                              obs_bytes=self.obs_packer.nbytes, act_bytes=self.act_packer.nbytes))
+
+  def restore(self, state):
+    import torch
+    geo = state['geometry']
+    if (geo['max_size'], geo['slot_capacity'], geo['obs_bytes'], geo['act_bytes']) != (
+        self.max_size, self.slot_capacity, self.obs_packer.nbytes, self.act_packer.nbytes):
+      raise ValueError(f'table geometry differs from the saved one: {geo}')
+    blob = np.ascontiguousarray(state['host'], np.uint8)
+    _capi.call('b200rl_replay_set_host_state', self.handle, blob.ctypes.data, blob.size)
+    for which, name in enumerate(self._SEGMENTS):
+      t = self._segment(which)
+      if t is not None:
+        t.copy_(torch.as_tensor(np.ascontiguousarray(state['segments'][name], np.uint8)))
+    torch.cuda.current_stream().synchronize()
 
   def set_weights(self, weights):
     """Priorities-only table (sampling/update sweeps): leaves <- weights (device f32 [n])."""
@@ -384,6 +435,13 @@ TFClient = Client
 
 
 # ----------------------------------------------------------------------------- dataset
+class _RawBytes:
+  """A device byte range dressed up for torch.as_tensor (zero copy)."""
+
+  def __init__(self, ptr: int, n: int):
+    self.__cuda_array_interface__ = {'shape': (n,), 'typestr': '|u1', 'data': (ptr, False), 'version': 2}
+
+
 class _MassView:
   """The tree's root mass (one device float) as a zero-copy array for torch.as_tensor."""
 
@@ -434,9 +492,13 @@ class ReplayDataset:
       self.u.copy_(uniforms)
     self.table.sample_into(self.u, self.idx, self.keys, self.prob, self.stratified)
 
-  def gather_only(self):
-    """K3: the sampled items' transitions (n-step return and discount built on the fly)."""
-    self.table.gather_into(self.idx, self.o_tm1, self.a_tm1, self.R, self.D, self.o_t)
+  def gather_only(self, rows=None):
+    """K3: the sampled items' transitions (n-step return and discount built on the fly).  rows = (rows_tm1_ptr,
+    rows_t_ptr, conv geometry): the frames are also written into the first conv layer's bf16 row images."""
+    if rows is not None:
+      self.table.gather_rows_into(self.idx, self.o_tm1, self.a_tm1, self.R, self.D, self.o_t, *rows)
+    else:
+      self.table.gather_into(self.idx, self.o_tm1, self.a_tm1, self.R, self.D, self.o_t)
 
   def as_sample(self, table_size: Optional[int] = None) -> ReplaySample:
     import torch

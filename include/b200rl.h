@@ -119,6 +119,25 @@ int b200rl_replay_tree_read_prefix(b200rl_replay* h, int32_t level, float* host_
 /* Device address of the root mass (one float) for cross-shard normalisation. */
 int b200rl_replay_mass_ptr(b200rl_replay* h, float** mass_dev);
 
+/* K3 with the first layer's input fused in (bf16 dataflow): as b200rl_replay_gather, and the frames ([H][W][4] uint8) are
+ * also written into the zero-padded bf16 row images that b200rl_conv2d_fwd_bf16(x_rows = 1) reads (layout:
+ * b200rl_conv2d_rows_bf16_bytes(g with B = 1) bytes per frame; the images must be zero-initialised once -- the padding is
+ * never written).  Replaces gather + b200rl_conv2d_rows_bf16_from_u8. */
+struct b200rl_conv_geom;   /* defined with the network layers below */
+int b200rl_replay_gather_rows(b200rl_replay* h, int32_t B, const int64_t* idx_dev, void* o_tm1, void* a_tm1, float* R,
+                              float* D, void* o_t, void* rows_tm1, void* rows_t, const struct b200rl_conv_geom* g,
+                              void* stream);
+
+/* Checkpoint / resume of a replay shard (the reference's checkpointers, acme/tf/savers.py:76-167, never save
+ * replay contents).  host_state serialises the host bookkeeping (key counters, FIFO bounds, every open writer's episode
+ * window) after flushing staged steps; blob == NULL only reports the size.  segment(which) exposes the device arrays to
+ * copy out / in: 0 obs slots, 1 actions, 2 rewards, 3 discounts, 4 next links, 5-7 item start / end / length, 8 sum
+ * tree (values + prefix lines), 9 live key range.  Restore = set_host_state + writing every segment back, on a handle
+ * created with the same geometry. */
+int b200rl_replay_host_state(b200rl_replay* h, void* blob, int64_t capacity, int64_t* size, void* stream);
+int b200rl_replay_set_host_state(b200rl_replay* h, const void* blob, int64_t size);
+int b200rl_replay_segment(b200rl_replay* h, int32_t which, void** dev_ptr, int64_t* bytes);
+
 /* Stand-alone sum-tree (priorities only) for the sampling/update sweep (BASELINE config 4). */
 int b200rl_replay_set_weights(b200rl_replay* h, int64_t n, const float* weights_dev, void* stream);
 
@@ -311,6 +330,9 @@ int b200rl_linear_fwd_bf16(int32_t M, int32_t N, int32_t K, const void* x_bf16, 
 int b200rl_linear_dgrad_bf16(int32_t M, int32_t N, int32_t K, const void* dy_bf16, int32_t lddy, const void* w_bf16,
                              void* dx, int32_t lddx, int dx_bf16, const void* mask_y, int mask_bf16, int mask_act,
                              void* ws, int64_t ws_bytes, void* stream);
+/* out[n] = sum_m x[m, n] over bf16 rows (a bias gradient issued on its own stream; N a power of two in [4, 1024]) */
+int b200rl_colsum_bf16(int32_t M, int32_t N, const void* x_bf16, int32_t ld, float* out, void* ws, int64_t ws_bytes,
+                       void* stream);
 int b200rl_linear_wgrad_bf16(int32_t M, int32_t N, int32_t K, const void* dy_bf16, int32_t lddy, const void* x_bf16,
                              int32_t ldx, float* dw, float* db, void* ws, int64_t ws_bytes, void* stream);
 

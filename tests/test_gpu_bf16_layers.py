@@ -235,3 +235,36 @@ def test_fused_head_td_matches_unfused_kernels():
   for x, y in zip(gw2, gw):
     assert torch.equal(x, y)
   np.testing.assert_allclose(mean.cpu().numpy()[0], lps.cpu().numpy().astype(np.float64).mean(), rtol=1e-6)
+
+
+@pytest.mark.parametrize('hw', [84, 20])
+def test_gather_rows_equals_gather_plus_conversion(hw):
+  """b200rl_replay_gather_rows == b200rl_replay_gather followed by b200rl_conv2d_rows_bf16_from_u8, byte for byte."""
+  import ctypes
+  import torch
+  import helpers
+  from acme_b200 import _capi, replay
+  rng = np.random.default_rng(hw)
+  shape, A, n, B = (hw, hw, 4), 4, 3, 32
+  spec, table, server, adder, oracle = helpers.make_pair(shape, np.uint8, A, n, 0.99, 0.6, max_size=200)
+  for ep in range(5):
+    helpers.feed_episode(rng, adder, oracle, int(rng.integers(5, 30)), n, shape, np.uint8, A)
+  table.flush()
+  g1, oh, pad = _geom(1, hw, 4, 8, 4, 32)
+  g2, _, _ = _geom(2 * B, hw, 4, 8, 4, 32)
+  fb = int(_capi.load().b200rl_conv2d_rows_bf16_bytes(ctypes.byref(g1)))
+  assert fb > 0 and fb % 128 == 0
+  ds = replay.ReplayDataset(table, B, seed=1)
+  ds.sample_only(torch.as_tensor(rng.random(B, dtype=np.float32)).cuda())
+  rows = torch.zeros(2 * B * fb, dtype=torch.uint8, device='cuda')
+  ds.gather_only((rows.data_ptr(), rows.data_ptr() + B * fb, g1))
+  torch.cuda.synchronize()
+  o_both, R, D, a = ds.o_both.clone(), ds.R.clone(), ds.D.clone(), ds.a_tm1.clone()
+  ds.o_both.zero_()
+  ds.gather_only()
+  want = torch.full((2 * B * fb,), 0xAB, dtype=torch.uint8, device='cuda')
+  _capi.call('b200rl_conv2d_rows_bf16_from_u8', ds.o_both.data_ptr(), g2, want.data_ptr(), want.numel(), _capi.current_stream())
+  torch.cuda.synchronize()
+  assert torch.equal(ds.o_both, o_both) and torch.equal(ds.R, R) and torch.equal(ds.D, D) and torch.equal(ds.a_tm1, a)
+  assert torch.equal(rows, want)
+  server.stop()

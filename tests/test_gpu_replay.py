@@ -292,3 +292,64 @@ def test_philox_uniforms_are_reproducible():
   _capi.call('b200rl_uniform', out.data_ptr(), 4096, 1234, step.data_ptr(), 1, _capi.current_stream())
   b = out.cpu().numpy()
   assert (a != b).mean() > 0.99 and a.min() >= 0 and a.max() < 1 and abs(a.mean() - 0.5) < 0.03
+
+
+def test_table_save_restore_resumes_exactly():
+  """a table restored from save() continues exactly like the uninterrupted one -- same keys, FIFO position,
+  priorities and n-step windows, including an episode that is open across the checkpoint."""
+  torch = _torch()
+  import helpers
+  from acme_b200 import dm_env, replay
+  rng = np.random.default_rng(12)
+  shape, dtype, A, n = (8, 8, 4), np.uint8, 4, 3
+  spec, t1, s1, adder1, _ = helpers.make_pair(shape, dtype, A, n, 0.99, 0.6, max_size=120)
+  _, t2, s2, adder2, _ = helpers.make_pair(shape, dtype, A, n, 0.99, 0.6, max_size=120)
+
+  class Null:   # the helper feeds an oracle as well; not needed here
+    def writer(self): return None
+    def append(self, *a): pass
+    def create_item(self, *a): pass
+    def close(self, *a): pass
+
+  for ep in range(12):     # > max_size items: the FIFO has wrapped
+    helpers.feed_episode(rng, adder1, Null(), int(rng.integers(3, 25)), n, shape, dtype, A)
+  # an episode left open across the checkpoint
+  obs = [helpers.random_obs(rng, shape, dtype) for _ in range(12)]
+  adder1.add_first(dm_env.restart(obs[0]))
+  for k in range(1, 5):
+    adder1.add(np.int32(k % A), dm_env.transition(np.float32(k), obs[k], np.float32(1.)))
+  keys = np.arange(t1.info()['tail_key'], t1.info()['head_key'], dtype=np.uint64)
+  replay.Client(s1).update_priorities(t1.name, keys, np.abs(rng.standard_normal(keys.shape[0])))
+  state = t1.save()
+  t2.restore(state)
+  assert t2.info() == t1.info()
+  # the second adder continues the open episode: give it the same writer state by construction
+  adder2._buffer = adder1._buffer.__class__(adder1._buffer, maxlen=adder1._buffer.maxlen)
+  w1, w2 = adder1._writer, adder2._writer            # the property creates adder2's writer (lazily, one per episode)
+  w2._ids = dict(w1._ids)                            # same writer slot in the restored table: its window came with the blob
+  w2._started = set(w1._started)
+  for k in range(5, 11):
+    for ad in (adder1, adder2):
+      last = k == 10
+      ts = dm_env.TimeStep(dm_env.StepType.LAST if last else dm_env.StepType.MID, np.float32(k), np.float32(0. if last else 1.), obs[k])
+      ad.add(np.int32(k % A), ts)
+  rng2 = np.random.default_rng(5)
+  for ep in range(3):
+    T = int(rng2.integers(3, 20))
+    seeds = int(rng2.integers(1 << 30))
+    for ad in (adder1, adder2):
+      helpers.feed_episode(np.random.default_rng(seeds), ad, Null(), T, n, shape, dtype, A)
+  t1.flush(); t2.flush()
+  assert t2.info() == t1.info()
+  L = t1.tree_levels()[0]
+  for l in range(L + 1):
+    np.testing.assert_array_equal(t2.read_tree_level(l), t1.read_tree_level(l))
+  B = 64
+  d1, d2 = replay.ReplayDataset(t1, B), replay.ReplayDataset(t2, B)
+  u = torch.as_tensor(rng.random(B, dtype=np.float32)).cuda()
+  d1.sample_raw(u); d2.sample_raw(u)
+  torch.cuda.synchronize()
+  for a, b in ((d1.idx, d2.idx), (d1.prob, d2.prob), (d1.o_both, d2.o_both), (d1.a_tm1, d2.a_tm1), (d1.R, d2.R), (d1.D, d2.D)):
+    assert torch.equal(a, b)
+  assert torch.equal(d1.keys.view(torch.int64), d2.keys.view(torch.int64))
+  s1.stop(); s2.stop()

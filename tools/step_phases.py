@@ -20,12 +20,12 @@ table = replay.Table(replay.DEFAULT_PRIORITY_TABLE, replay.selectors.Prioritized
                      discount=0.99, slot_capacity=items + 4096, stage_slots=4096, device=rank, shard_count=world, shard_rank=rank)
 server = replay.Server([table])
 bench.fill_replay(table, items, 3, seed=1 + rank)
-prec = 1 if (len(sys.argv) < 2 or sys.argv[1] != 'fp32') else 0
+prec = {'fp32': 0, 'tf32': 1, 'bf16': 2}[sys.argv[1] if len(sys.argv) > 1 else 'bf16']
 net = networks.DQNAtariNetwork(18, precision=prec, seed=1, device=rank)
 tgt = net.clone()
 ds = replay.ReplayDataset(table, 256, seed=1 + rank)
 L = dqn.DQNLearner(net, tgt, 0.99, 0.2, 1e-3, 100, ds, replay_client=replay.Client(server), logger=loggers.NoOpLogger(), process_group=pg)
-names = ['k1 sample + k3 gather', 'forwards x3 (3 streams)', 'k4 td/loss', 'backward (2 streams)', 'k7 adam', 'k2 priorities + copy + inc']
+names = ['k1 sample + k3 gather', 'forwards (target || batched online)', 'heads + k4 td/loss', 'backward (2 streams)', 'k7 adam', 'k2 priorities + copy + inc']
 for _ in range(10): L.step(fetch_loss=False)
 late = int(os.environ.get('B200RL_PHASES_AFTER', '0'))   # measure after this many extra steps (drift over long runs)
 for _ in range(late): L.step(fetch_loss=False)
