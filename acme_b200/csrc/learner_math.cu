@@ -469,21 +469,39 @@ __device__ __forceinline__ float head_q(const float* __restrict__ hrow, const fl
       ha[j] = hrow[H + lane + 32 * j];
     }
   }
-  float sv = 0.f;
+  // All A + 1 dot products first, then their butterfly reductions INTERLEAVED (A + 1 independent shuffles per level):
+  // a warp owns one sample, so one reduction after another would expose 5 shuffle latencies per dot product.  Every sum
+  // is formed in the same order as in duelling_head_fwd_kernel, so the values are identical.
+  float s[33];
 #pragma unroll
-  for (int j = 0; j < HPL; ++j) sv = fmaf(hv[j], sw[lane + 32 * j], sv);
-  for (int d = 16; d > 0; d >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, d);
-  sv += bv[0];
+  for (int a = 0; a < 33; ++a) {
+    s[a] = 0.f;
+    if (a <= A) {
+      const float* w = sw + (size_t)a * H;
+      if (a == 0) {
+#pragma unroll
+        for (int j = 0; j < HPL; ++j) s[a] = fmaf(hv[j], w[lane + 32 * j], s[a]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < HPL; ++j) s[a] = fmaf(ha[j], w[lane + 32 * j], s[a]);
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+#pragma unroll
+    for (int a = 0; a < 33; ++a)
+      if (a <= A) s[a] += __shfl_xor_sync(0xffffffffu, s[a], d);
+  }
+  const float sv = s[0] + bv[0];
   float total = 0.f, mine = 0.f;
-  for (int a = 0; a < A; ++a) {
-    const float* w = sw + (size_t)(a + 1) * H;
-    float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < HPL; ++j) s = fmaf(ha[j], w[lane + 32 * j], s);
-    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-    s += ba[a];
-    total += s;
-    if (lane == a) mine = s;
+  for (int a = 0; a < 32; ++a) {
+    if (a < A) {
+      const float t = s[a + 1] + ba[a];
+      total += t;
+      if (lane == a) mine = t;
+    }
   }
   const float mean = total / (float)A;
   val_out = sv;

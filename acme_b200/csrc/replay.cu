@@ -175,7 +175,8 @@ gather_rows_kernel(RingView r, const long long* __restrict__ idx, uint8_t* __res
   int4* d4 = reinterpret_cast<int4*>((which == 0 ? o_tm1 : o_t) + (size_t)b * r.obs_bytes);
   uint4* rows = (which == 0 ? rows_tm1 : rows_t) + (size_t)b * Hp * row_v16;
   const int nv = r.obs_bytes >> 4;
-  for (int i = threadIdx.x; i < nv; i += 256) {
+  // gridDim.z CTAs share a frame (a frame is only 1764 vectors: one CTA per frame leaves the stores latency-bound)
+  for (int i = blockIdx.z * 256 + threadIdx.x; i < nv; i += 256 * gridDim.z) {
     const int4 v = __ldg(s4 + i);
     d4[i] = v;
     const int y = i / W4, xv = i - y * W4;
@@ -193,7 +194,7 @@ gather_rows_kernel(RingView r, const long long* __restrict__ idx, uint8_t* __res
     dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
     dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
   }
-  if (which == 0) {
+  if (which == 0 && blockIdx.z == 0) {
     const uint8_t* as = r.act + (size_t)slot * r.act_stride;
     uint8_t* ad = a_tm1 + (size_t)b * r.act_bytes;
     for (int i = threadIdx.x; i < r.act_bytes; i += 256) ad[i] = as[i];
@@ -965,7 +966,8 @@ extern "C" int b200rl_replay_gather_rows(b200rl_replay* h, int32_t B, const int6
   B200RL_REQUIRE(((((uintptr_t)o_tm1 | (uintptr_t)o_t | (uintptr_t)rows_tm1 | (uintptr_t)rows_t)) & 15) == 0, "buffers must be 16-byte aligned");
   int rc = ensure_device(h);
   if (rc) return rc;
-  gather_rows_kernel<<<dim3(B, 2), 256, 0, as_stream(stream)>>>(h->ring, (const long long*)idx_dev, (uint8_t*)o_tm1, (uint8_t*)a_tm1, R, D,
+  const int zsplit = std::max(1, std::min(4, (h->cfg.obs_bytes >> 4) / 256));
+  gather_rows_kernel<<<dim3(B, 2, zsplit), 256, 0, as_stream(stream)>>>(h->ring, (const long long*)idx_dev, (uint8_t*)o_tm1, (uint8_t*)a_tm1, R, D,
                                                                (uint8_t*)o_t, (uint4*)rows_tm1, (uint4*)rows_t, g->W / 4, g->pad_left,
                                                                g->pad_top, Hp, row_elems / 8);
   B200RL_LAUNCH_OK();

@@ -105,7 +105,7 @@ class DQNLearner(core.Learner, core.Saveable):
     # With a peer exchange on >= 4 ranks the bucket's kernel is NVLink-bound (1/R of the Adam work) and does hide
     # behind the convolution backward.
     split_default = '0'   # measured on 8 GPUs: 0.540 ms split vs 0.522 ms unsplit (more barriers, contention)
-    self._split_adam = (self._concurrent and hasattr(network, 'grad_buckets') and not self._fused and
+    self._split_adam = (self._concurrent and hasattr(network, 'grad_buckets') and
                         os.environ.get('B200RL_SPLIT_ADAM', split_default) == '1')
     self._tail_done = None
     self._side = [torch.cuda.Stream(device=dev) for _ in range(5)] if self._concurrent else None
@@ -421,8 +421,20 @@ class DQNLearner(core.Learner, core.Saveable):
         self._early_done.record(side)
       net.backward_conv_part(o_tm1, bt, gb, self._side[0], **self._rows_kw())
     elif self._concurrent:
-      net.backward_dense_part(bt, gb, None, self._side[0])
-      net.backward_conv_part(o_tm1, bt, gb, self._side[0], **self._rows_kw())
+      hook = None
+      if self._split_adam and (self._world == 1 or self._px is not None):
+        # fc1 + heads are 99% of the parameters and final long before the torso's gradients: their optimizer update can
+        # run underneath the convolution backward (B200RL_SPLIT_ADAM=1; `_apply` then only updates the torso bucket)
+        def hook(events):
+          side = self._side[3]
+          for ev in events:
+            side.wait_event(ev)
+          with torch.cuda.stream(side):
+            (o1, n1), _ = net.grad_buckets()
+            self._adam(o1, n1, bucket=0)
+            self._tail_done = torch.cuda.Event()
+            self._tail_done.record(side)
+      net.backward_after_head(o_tm1, bt, gb, self._side[0], self._side[1], on_dense_done=hook, **self._rows_kw())
     else:
       net.head_wgrad(bt, gb)
       net._fc1_wgrad(bt, gb)

@@ -404,12 +404,18 @@ class DQNAtariNetwork(Network):
                bufs['h'].data_ptr(), 1024, P.g('v2.w'), P.g('v2.b'), P.g('a2.w'), P.g('a2.b'), ws, wsb, _capi.current_stream())
 
   # layer calls of the backward pass in either dataflow
-  def _fc1_wgrad(self, bufs, gbufs):
+  def _fc1_bias_grad(self, bufs, gbufs):
+    """bf16 dataflow: d fc1.b = column sums of dh, as its own launch."""
+    B, P = bufs['B'], self.params
+    ws, wsb = self.ws
+    _capi.call('b200rl_colsum_bf16', B, 1024, gbufs['dh'].data_ptr(), 1024, P.g('fc1.b'), ws, wsb, _capi.current_stream())
+
+  def _fc1_wgrad(self, bufs, gbufs, bias: bool = True):
     B, P = bufs['B'], self.params
     ws, wsb = self.ws
     if self.flow:
       _capi.call('b200rl_linear_wgrad_bf16', B, 1024, self.flat_dim, gbufs['dh'].data_ptr(), 1024, bufs['y3'].data_ptr(),
-                 self.flat_dim, P.g('fc1.w'), P.g('fc1.b'), ws, wsb, _capi.current_stream())
+                 self.flat_dim, P.g('fc1.w'), P.g('fc1.b') if bias else None, ws, wsb, _capi.current_stream())
     else:
       _linear_wgrad(B, 1024, self.flat_dim, gbufs['dh'].data_ptr(), 1024, bufs['y3'].data_ptr(), self.flat_dim, P.g('fc1.w'),
                     P.g('fc1.b'), self)
@@ -489,6 +495,62 @@ class DQNAtariNetwork(Network):
   def _backward_two_streams(self, obs, bufs, gbufs, dq, side, rows=None):
     self.backward_dense_part(bufs, gbufs, dq, side)
     self.backward_conv_part(obs, bufs, gbufs, side, rows)
+
+  def backward_after_head(self, obs, bufs, gbufs, s1, s2, rows=None, on_dense_done=None):
+    """Everything behind the fused head + TD kernel (which has produced gbufs['dh'] / ['dval'] / ['dadv']), scheduled on
+    three streams: the data-gradient chain fc1 -> conv3 -> conv2 (+ conv1's weight gradient) on the current stream, the
+    weight-gradient GEMMs on `s1`, the head's parameter gradients and (bf16 dataflow) the bias-gradient column sums on
+    `s2`.  Workspace lanes 0 / 1 / 2.  `on_dense_done(event_list)` is called once fc1's and the head's gradients have
+    been issued, with the events that mark their completion (a caller may start their optimizer update there)."""
+    import torch
+    main = torch.cuda.current_stream()
+    flow = self.flow
+
+    def fork(*streams):
+      ev = torch.cuda.Event()
+      ev.record(main)
+      for st in streams:
+        st.wait_event(ev)
+
+    fork(s1, s2)
+    with torch.cuda.stream(s1):
+      self.lane(1)
+      self._fc1_wgrad(bufs, gbufs, bias=not flow)
+      ev_w = torch.cuda.Event()
+      ev_w.record(s1)
+    with torch.cuda.stream(s2):
+      self.lane(2)
+      self.head_wgrad(bufs, gbufs)
+      if flow:
+        self._fc1_bias_grad(bufs, gbufs)
+      ev_h = torch.cuda.Event()
+      ev_h.record(s2)
+    if on_dense_done is not None:
+      on_dense_done([ev_w, ev_h])
+    self.lane(0)
+    self._fc1_dgrad(bufs, gbufs)
+    for i in (2, 1):
+      fork(s1, s2) if flow else fork(s1)
+      with torch.cuda.stream(s1):
+        self.lane(1)
+        self._conv_wgrad(i, obs, bufs, gbufs, rows, bias=not flow)
+      if flow:
+        with torch.cuda.stream(s2):
+          self.lane(2)
+          self._conv_bias_grad(i, bufs, gbufs)
+      self.lane(0)
+      self._conv_dgrad(i, bufs, gbufs)
+    if flow:
+      fork(s2)
+      with torch.cuda.stream(s2):
+        self.lane(2)
+        self._conv_bias_grad(0, bufs, gbufs)
+    self.lane(0)
+    self._conv_wgrad(0, obs, bufs, gbufs, rows, bias=not flow)
+    for st in (s1, s2):
+      ev = torch.cuda.Event()
+      ev.record(st)
+      main.wait_event(ev)
 
   def grad_buckets(self):
     """(offset, count) in floats of the gradient regions that become final after backward_dense_part

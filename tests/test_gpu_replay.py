@@ -325,6 +325,7 @@ def test_table_save_restore_resumes_exactly():
   assert t2.info() == t1.info()
   # the second adder continues the open episode: give it the same writer state by construction
   adder2._buffer = adder1._buffer.__class__(adder1._buffer, maxlen=adder1._buffer.maxlen)
+  adder2._next_observation, adder2._start_of_episode = adder1._next_observation, adder1._start_of_episode
   w1, w2 = adder1._writer, adder2._writer            # the property creates adder2's writer (lazily, one per episode)
   w2._ids = dict(w1._ids)                            # same writer slot in the restored table: its window came with the blob
   w2._started = set(w1._started)
