@@ -62,6 +62,7 @@ PROTOTYPES = {
     'b200rl_replay_host_state': (c_int, [c_vp, c_vp, c_i64, C.POINTER(c_i64), c_vp]),
     'b200rl_replay_set_host_state': (c_int, [c_vp, c_vp, c_i64]),
     'b200rl_replay_segment': (c_int, [c_vp, c_i32, C.POINTER(c_vp), C.POINTER(c_i64)]),
+    'b200rl_replay_set_global_mass': (c_int, [c_vp, c_vp]),
     'b200rl_replay_set_weights': (c_int, [c_vp, c_i64, c_vp, c_vp]),
     'b200rl_uniform': (c_int, [c_vp, c_i32, c_u64, c_vp, c_i64, c_vp]),
     'b200rl_dqn_td': (c_int, [c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_f32,

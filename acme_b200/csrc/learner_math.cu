@@ -451,62 +451,56 @@ duelling_head_fwd_kernel(int B, int A, const float* __restrict__ h, int ldh, con
 }
 
 // ------------------------------------------------------------------------------ K4 fused into the duelling head
-// One warp per sample: the three duelling heads (online(o_tm1), target(o_t), online(o_t); duelling.py:37-59), the
-// double-Q TD error / Huber / importance weight / priority (learning.py:127-154) and the head's data gradient
-// dh = [dval * wv, dadv @ wa] * relu'(h) in ONE launch -- three head kernels, the single-CTA TD kernel and the
-// head-backward kernel of the unfused path sat back to back on the step's critical path.  The arithmetic of every
-// piece is the unfused kernels', operation for operation (same dot-product order, same __f*_rn sequence), so the two
-// paths agree bit for bit.  Needs A <= 32 and the batch-max importance weight precomputed (b200rl_is_weight_max).
+// The three duelling heads (online(o_tm1), target(o_t), online(o_t); duelling.py:37-59), the double-Q TD error / Huber /
+// importance weight / priority (learning.py:127-154) and the head's data gradient dh = [dval * wv, dadv @ wa] * relu'(h)
+// in ONE launch -- three head kernels, the single-CTA TD kernel and the head-backward kernel of the unfused path sat
+// back to back on the step's critical path.  Three warps per sample (one per head) so the 3 x (A + 1) dot products of a
+// sample are not one serial chain; the warp that owns the o_tm1 head keeps its hidden row in registers and finishes the
+// sample (TD, dq, dh) once the other two have published their q rows in shared memory.  The arithmetic of every piece
+// is the unfused kernels', operation for operation (same dot-product order, same __f*_rn sequence), so the two paths
+// agree bit for bit.  Needs A <= 32 and the batch-max importance weight precomputed (b200rl_is_weight_max).
+constexpr int kHeadSamples = 4;                       // samples per CTA
+constexpr int kHeadThreads = 96 * kHeadSamples;       // 3 warps per sample
+
+// q row of one head from a hidden row held in registers; lane a < A returns q[a].  Dot products run four at a time
+// (their shuffle reductions interleave), each one in the order of duelling_head_fwd_kernel.
 template <int HPL>
-__device__ __forceinline__ float head_q(const float* __restrict__ hrow, const float* __restrict__ sw, const float* __restrict__ bv,
-                                        const float* __restrict__ ba, int A, int lane, float (&hv)[HPL], float (&ha)[HPL],
-                                        float& val_out, float& adv_out) {
+__device__ __forceinline__ float head_q(const float* __restrict__ sw, const float* __restrict__ bv, const float* __restrict__ ba,
+                                        int A, int lane, const float (&hv)[HPL], const float (&ha)[HPL]) {
   constexpr int H = 32 * HPL;
-  if (hrow) {
+  float sv = 0.f;
 #pragma unroll
-    for (int j = 0; j < HPL; ++j) {
-      hv[j] = hrow[lane + 32 * j];
-      ha[j] = hrow[H + lane + 32 * j];
+  for (int j = 0; j < HPL; ++j) sv = fmaf(hv[j], sw[lane + 32 * j], sv);
+  for (int d = 16; d > 0; d >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, d);
+  sv += bv[0];
+  float total = 0.f, mine = 0.f;
+  for (int a0 = 0; a0 < A; a0 += 4) {
+    float s[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      s[q] = 0.f;
+      if (a0 + q < A) {
+        const float* w = sw + (size_t)(a0 + q + 1) * H;
+#pragma unroll
+        for (int j = 0; j < HPL; ++j) s[q] = fmaf(ha[j], w[lane + 32 * j], s[q]);
+      }
     }
-  }
-  // All A + 1 dot products first, then their butterfly reductions INTERLEAVED (A + 1 independent shuffles per level):
-  // a warp owns one sample, so one reduction after another would expose 5 shuffle latencies per dot product.  Every sum
-  // is formed in the same order as in duelling_head_fwd_kernel, so the values are identical.
-  float s[33];
 #pragma unroll
-  for (int a = 0; a < 33; ++a) {
-    s[a] = 0.f;
-    if (a <= A) {
-      const float* w = sw + (size_t)a * H;
-      if (a == 0) {
+    for (int d = 16; d > 0; d >>= 1) {
 #pragma unroll
-        for (int j = 0; j < HPL; ++j) s[a] = fmaf(hv[j], w[lane + 32 * j], s[a]);
-      } else {
+      for (int q = 0; q < 4; ++q) s[q] += __shfl_xor_sync(0xffffffffu, s[q], d);
+    }
 #pragma unroll
-        for (int j = 0; j < HPL; ++j) s[a] = fmaf(ha[j], w[lane + 32 * j], s[a]);
+    for (int q = 0; q < 4; ++q) {
+      if (a0 + q < A) {
+        const float t = s[q] + ba[a0 + q];
+        total += t;
+        if (lane == a0 + q) mine = t;
       }
     }
   }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-#pragma unroll
-    for (int a = 0; a < 33; ++a)
-      if (a <= A) s[a] += __shfl_xor_sync(0xffffffffu, s[a], d);
-  }
-  const float sv = s[0] + bv[0];
-  float total = 0.f, mine = 0.f;
-#pragma unroll
-  for (int a = 0; a < 32; ++a) {
-    if (a < A) {
-      const float t = s[a + 1] + ba[a];
-      total += t;
-      if (lane == a) mine = t;
-    }
-  }
   const float mean = total / (float)A;
-  val_out = sv;
-  adv_out = mine;
-  return sv + (mine - mean);   // lane a < A holds q[a]
+  return sv + (mine - mean);
 }
 
 struct HeadTdArgs {
@@ -522,16 +516,16 @@ struct HeadTdArgs {
   void* dh;
 };
 
-constexpr int kHeadThreads = 256;
 template <int HPL>
 __global__ void __launch_bounds__(kHeadThreads)
 dqn_head_td_kernel(HeadTdArgs p) {
   constexpr int H = 32 * HPL;
-  extern __shared__ __align__(128) float sw[];   // online [A + 1][H], then target [A + 1][H]
+  extern __shared__ __align__(16) float sw[];   // online [A + 1][H], then target [A + 1][H]
   __shared__ __align__(8) unsigned long long bar;
+  __shared__ float q_other[kHeadSamples][2][32];  // [sample][0 = target(o_t), 1 = online(o_t)][action]
   float* swt = sw + (size_t)(p.A + 1) * H;
   // the four weight blocks arrive by bulk async copies (one instruction each, completion on an mbarrier) while the
-  // warps below already fetch their hidden rows
+  // warps already fetch their hidden rows
   if (threadIdx.x == 0) {
     const uint32_t b32 = (uint32_t)__cvta_generic_to_shared(&bar);
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b32) : "memory");
@@ -549,18 +543,18 @@ dqn_head_td_kernel(HeadTdArgs p) {
                    : "memory");
   }
   __syncthreads();   // the barrier is initialised before anyone waits on it
-  const int lane = threadIdx.x & 31;
-  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (b >= p.B) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sl = warp / 3, head = warp - 3 * sl;           // head: 0 = online(o_tm1), 1 = target(o_t), 2 = online(o_t)
+  const int b = blockIdx.x * kHeadSamples + sl;
+  const bool valid = b < p.B;
   const int A = p.A;
-  float hv[HPL], ha[HPL], tv[HPL], ta[HPL], sv_[HPL], sa_[HPL], val, adv;
-  {   // the three hidden rows of this sample: in flight while the weights land
-    const float *r0 = p.h_tm1 + (size_t)b * p.ldh, *r1 = p.h_tgt + (size_t)b * p.ldh, *r2 = p.h_sel + (size_t)b * p.ldh;
+  float hv[HPL], ha[HPL];
+  if (valid) {
+    const float* row = (head == 0 ? p.h_tm1 : (head == 1 ? p.h_tgt : p.h_sel)) + (size_t)b * p.ldh;
 #pragma unroll
     for (int j = 0; j < HPL; ++j) {
-      hv[j] = r0[lane + 32 * j]; ha[j] = r0[H + lane + 32 * j];
-      tv[j] = r1[lane + 32 * j]; ta[j] = r1[H + lane + 32 * j];
-      sv_[j] = r2[lane + 32 * j]; sa_[j] = r2[H + lane + 32 * j];
+      hv[j] = row[lane + 32 * j];
+      ha[j] = row[H + lane + 32 * j];
     }
   }
   {
@@ -574,16 +568,16 @@ dqn_head_td_kernel(HeadTdArgs p) {
           : "memory");
     } while (!ok);
   }
-  // learning.py:124-125: the target network and the online network on o_t
-  const float q_tv = head_q<HPL>(nullptr, swt, p.tbv, p.tba, A, lane, tv, ta, val, adv);
-  const float q_ts = head_q<HPL>(nullptr, sw, p.bv, p.ba, A, lane, sv_, sa_, val, adv);
-  // learning.py:123: the online network on o_tm1 (its hidden row stays in registers for the backward)
-  const float q_tm1 = head_q<HPL>(nullptr, sw, p.bv, p.ba, A, lane, hv, ha, val, adv);
-  if (lane < A) {
-    if (p.q_tm1) p.q_tm1[(size_t)b * A + lane] = q_tm1;
-    if (p.q_tv) p.q_tv[(size_t)b * A + lane] = q_tv;
-    if (p.q_ts) p.q_ts[(size_t)b * A + lane] = q_ts;
+  float q = 0.f;
+  if (valid) {
+    q = head == 1 ? head_q<HPL>(swt, p.tbv, p.tba, A, lane, hv, ha) : head_q<HPL>(sw, p.bv, p.ba, A, lane, hv, ha);
+    float* qout = head == 0 ? p.q_tm1 : (head == 1 ? p.q_tv : p.q_ts);
+    if (qout && lane < A) qout[(size_t)b * A + lane] = q;
+    if (head != 0) q_other[sl][head - 1][lane] = q;
   }
+  __syncthreads();
+  if (!valid || head != 0) return;
+  const float q_tm1 = q, q_tv = q_other[sl][0][lane], q_ts = q_other[sl][1][lane];
   // trfl.double_qlearning: first maximum of the selector wins
   int best = 0;
   float bvv = __shfl_sync(0xffffffffu, q_ts, 0);
@@ -1074,7 +1068,7 @@ extern "C" int b200rl_dqn_head_td(int32_t B, int32_t A, int32_t H, const float* 
     B200RL_CUDA_OK(cudaFuncSetAttribute(dqn_head_td_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
-  const int blocks = ceil_div(B * 32, kHeadThreads);
+  const int blocks = ceil_div(B, kHeadSamples);
   cudaStream_t st = as_stream(stream);
   switch (H) {
     case 512: dqn_head_td_kernel<16><<<blocks, kHeadThreads, smem, st>>>(p); break;

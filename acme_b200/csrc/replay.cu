@@ -36,7 +36,7 @@ void set_error(const char* fmt, ...) {
 // from sumtree.cu
 int tree_staged_levels(const TreeView& t, int64_t budget_bytes);
 int tree_sample(const TreeView& t, const ReplayState* st_dev, int64_t M, int B, const float* u,
-                int stratified, int shard_count, int64_t* idx, uint64_t* keys, float* prob,
+                int stratified, int shard_count, const float* denom_dev, int64_t* idx, uint64_t* keys, float* prob,
                 cudaStream_t stream, int* staged_out);
 int tree_rebuild(const TreeView& t, cudaStream_t stream);
 int tree_scatter_positions(const TreeView& t, int64_t M, int n, const int64_t* pos_dev,
@@ -285,6 +285,7 @@ struct b200rl_replay {
   // learner thread that flushes / samples; ctypes drops the GIL during calls, so every entry point takes this lock
   // (Reverb's table is thread-safe too: acme runs actors and learner against one server).
   std::recursive_mutex mu;
+  const float* global_mass_dev = nullptr;   // sum of all shards' masses (caller-owned device float), or NULL
 };
 #define B200RL_LOCK(h) std::lock_guard<std::recursive_mutex> _guard((h)->mu)
 
@@ -927,7 +928,7 @@ extern "C" int b200rl_replay_sample(b200rl_replay* h, int32_t B, const float* u_
   }
   int rc = ensure_device(h);
   if (rc) return rc;
-  return tree_sample(h->tree, h->d_state, h->M, B, u_dev, stratified, h->cfg.shard_count, idx_dev,
+  return tree_sample(h->tree, h->d_state, h->M, B, u_dev, stratified, h->cfg.shard_count, h->global_mass_dev, idx_dev,
                      keys_dev, prob_dev, as_stream(stream), nullptr);
 }
 
@@ -1032,6 +1033,15 @@ extern "C" int b200rl_replay_tree_read_prefix(b200rl_replay* h, int32_t level, f
   if (rc) return rc;
   B200RL_CUDA_OK(cudaMemcpyAsync(host_out, h->tree.pre[level], n * 4, cudaMemcpyDeviceToHost, as_stream(stream)));
   B200RL_CUDA_OK(cudaStreamSynchronize(as_stream(stream)));
+  return B200RL_OK;
+}
+
+// Global-priority-mass normalisation: every rank all-reduces its shard mass (b200rl_replay_mass_ptr) into
+// one device float and installs it here; K1 then reports weight / sum_r M_r.  NULL restores weight / (R * M_r).
+extern "C" int b200rl_replay_set_global_mass(b200rl_replay* h, const float* global_mass_dev) {
+  B200RL_REQUIRE(h, "null handle");
+  B200RL_LOCK(h);
+  h->global_mass_dev = global_mass_dev;
   return B200RL_OK;
 }
 

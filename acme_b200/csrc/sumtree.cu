@@ -69,7 +69,7 @@ __device__ __forceinline__ void group_descend(const float* __restrict__ line, in
 template <int SPG>   // samples interleaved per 4-lane group (memory-level parallelism for large batches)
 __global__ void __launch_bounds__(kSampleThreads)
 sample_kernel(TreeView t, int S, const ReplayState* __restrict__ st, long long M, int B,
-              const float* __restrict__ u, int stratified, float shards_f,
+              const float* __restrict__ u, int stratified, float shards_f, const float* __restrict__ denom_dev,
               long long* __restrict__ idx, unsigned long long* __restrict__ keys,
               float* __restrict__ prob) {
   extern __shared__ __align__(16) float staged[];
@@ -93,7 +93,9 @@ sample_kernel(TreeView t, int S, const ReplayState* __restrict__ st, long long M
   const long long group_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
   const long long total_groups = ((long long)gridDim.x * blockDim.x) >> 2;
   const float mass = t.lvl[0][0];
-  const float denom = __fmul_rn(shards_f, mass);
+  // reported probability = weight / (R * M_r): the item's true inclusion probability when each of R shards draws the
+  // same number of items; with a global mass installed (b200rl_replay_set_global_mass) = weight / sum_r M_r instead
+  const float denom = denom_dev ? *denom_dev : __fmul_rn(shards_f, mass);
   const unsigned long long tail = st->item_tail;
   const unsigned long long key_base = tail - tail % (unsigned long long)M;
   const long long rounds = ((long long)B + total_groups * SPG - 1) / (total_groups * SPG);
@@ -149,7 +151,7 @@ static int64_t staged_bytes(const TreeView& t, int S) {
 }
 
 int tree_sample(const TreeView& t, const ReplayState* st_dev, int64_t M, int B, const float* u,
-                int stratified, int shard_count, int64_t* idx, uint64_t* keys, float* prob,
+                int stratified, int shard_count, const float* denom_dev, int64_t* idx, uint64_t* keys, float* prob,
                 cudaStream_t stream, int* staged_out) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -166,13 +168,13 @@ int tree_sample(const TreeView& t, const ReplayState* st_dev, int64_t M, int B, 
     const int threads = 128;                                    // 32 samples per CTA
     int blocks = (int)ceil_div<int64_t>((int64_t)B * 4, threads);
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-    sample_kernel<1><<<blocks, threads, smem, stream>>>(t, S, st_dev, M, B, u, stratified, (float)shard_count,
+    sample_kernel<1><<<blocks, threads, smem, stream>>>(t, S, st_dev, M, B, u, stratified, (float)shard_count, denom_dev,
                                                         (long long*)idx, (unsigned long long*)keys, prob);
   } else {
     const bool fat = smem > 100 * 1024;   // one 1024-thread CTA per SM when the staged levels are big
     int threads = fat ? 1024 : 512;
     int blocks = kNumSMs * (fat ? 1 : 4);
-    sample_kernel<2><<<blocks, threads, smem, stream>>>(t, S, st_dev, M, B, u, stratified, (float)shard_count,
+    sample_kernel<2><<<blocks, threads, smem, stream>>>(t, S, st_dev, M, B, u, stratified, (float)shard_count, denom_dev,
                                                         (long long*)idx, (unsigned long long*)keys, prob);
   }
   B200RL_LAUNCH_OK();

@@ -56,6 +56,20 @@ class DataParallel:
     dist.all_gather_into_tensor(out, scalar_tensor.reshape(1), group=self.group)
     return out
 
+  def refresh_global_mass(self, table, total=None):
+    """Global-priority-mass normalisation: all-reduce(SUM) of the shards' masses into `total` (device float
+    [1], allocated on first use) and install it in the table, whose K1 then reports weight / sum_r M_r.  Call after
+    priority updates / inserts, whenever the reported probabilities should track the global mass."""
+    import torch
+    if total is None:
+      total = torch.empty(1, dtype=torch.float32, device=torch.device('cuda', table.device))
+    total.copy_(table.mass_tensor())
+    if self.enabled:
+      import torch.distributed as dist
+      dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.group)
+    table.set_global_mass(total)
+    return total
+
   def assert_replicated(self, tensor, what: str = 'parameters'):
     """Raises if ranks have diverged (cheap: two scalar all-reduces of a checksum)."""
     if not self.enabled:

@@ -242,6 +242,17 @@ class Table:
     _capi.call('b200rl_replay_mass_ptr', self.handle, C.byref(p))
     return p.value
 
+  def mass_tensor(self):
+    """The shard's total mass M_r as a zero-copy device tensor [1] (the tree's root)."""
+    import torch
+    return torch.as_tensor(_MassView(self.mass_ptr()), device=torch.device('cuda', self.device))
+
+  def set_global_mass(self, total):
+    """Installs sum_r M_r (device float tensor [1], kept alive by the table) so that K1 reports weight / sum_r M_r
+    (global-priority-mass normalisation); None restores weight / (R * M_r)."""
+    self._global_mass = total
+    _capi.call('b200rl_replay_set_global_mass', self.handle, None if total is None else total.data_ptr())
+
   # -- device path (torch tensors are only memory handles here)
   def sample_into(self, u, idx, keys, prob, stratified=True):
     _capi.call('b200rl_replay_sample', self.handle, u.shape[0], _capi.ptr(u), int(stratified),

@@ -366,9 +366,13 @@ def run_ours(args):
     # the network group exactly as the step runs it: target pass beside the batched online pass, then the fused
     # head + K4 kernel and the backward (weight gradients beside data gradients), recorded into ONE graph and replayed,
     # so the figure is the in-step time of the group, not a sum of serialised eager launches
+    def join_tail():     # B200RL_SPLIT_ADAM=1 forks the fc1 + head optimizer update inside the backward: rejoin for the capture
+      if getattr(learner, '_tail_done', None) is not None:
+        torch.cuda.current_stream().wait_event(learner._tail_done)
+        learner._tail_done = None
     g_fwd = learner._capture(learner._forwards)
-    g_bwd = learner._capture(learner._loss_backward)
-    g_net = learner._capture(lambda: (learner._forwards(), learner._loss_backward()))
+    g_bwd = learner._capture(lambda: (learner._loss_backward(), join_tail()))
+    g_net = learner._capture(lambda: (learner._forwards(), learner._loss_backward(), join_tail()))
     stages['k6_forwards_in_graph'] = time_stage(g_fwd.replay, it, torch)
     stages['k4_k6_loss_backward_in_graph'] = time_stage(g_bwd.replay, it, torch)
     stages['k6_network_group_in_graph'] = time_stage(g_net.replay, it, torch)

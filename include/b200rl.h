@@ -118,6 +118,10 @@ int b200rl_replay_tree_read(b200rl_replay* h, int32_t level, float* host_out, in
 int b200rl_replay_tree_read_prefix(b200rl_replay* h, int32_t level, float* host_out, int64_t n, void* stream);
 /* Device address of the root mass (one float) for cross-shard normalisation. */
 int b200rl_replay_mass_ptr(b200rl_replay* h, float** mass_dev);
+/* Global-priority-mass normalisation for sharded replay (north_star "each rank sampling locally with
+ * global-priority-mass normalisation"): global_mass_dev = caller-owned device float holding sum_r M_r (all-reduce of
+ * every shard's *mass_dev); K1 then reports weight / sum_r M_r instead of weight / (R * M_r).  NULL switches it off. */
+int b200rl_replay_set_global_mass(b200rl_replay* h, const float* global_mass_dev);
 
 /* K3 with the first layer's input fused in (bf16 dataflow): as b200rl_replay_gather, and the frames ([H][W][4] uint8) are
  * also written into the zero-padded bf16 row images that b200rl_conv2d_fwd_bf16(x_rows = 1) reads (layout:

@@ -8,6 +8,5 @@ run default X=1
 run split B200RL_SPLIT_ADAM=1
 run split_c2 B200RL_SPLIT_ADAM=1 B200RL_ADAM_CTAS_PER_SM=2
 run split_c4 B200RL_SPLIT_ADAM=1 B200RL_ADAM_CTAS_PER_SM=4
-run adam_c16 B200RL_ADAM_CTAS_PER_SM=16
-run adam_c4 B200RL_ADAM_CTAS_PER_SM=4
+run split_c1 B200RL_SPLIT_ADAM=1 B200RL_ADAM_CTAS_PER_SM=1
 timeout 300 python tools/step_phases.py bf16 > gpurun_out/run5_phases.log 2>&1; echo "phases rc=$?"; tail -9 gpurun_out/run5_phases.log
