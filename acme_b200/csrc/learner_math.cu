@@ -268,6 +268,9 @@ __device__ __forceinline__ float adam_one(float& p, float g, float& m, float& v,
 }
 // 8 elements (two float4 per array = 8 independent 16-byte loads) per thread per iteration: enough bytes in
 // flight to run at HBM speed; p/m/v are read-modify-write, g is read once (streamed through the read-only path).
+// VPT = float4 vectors per array per thread per iteration: 2 for the full-occupancy launch, 4 for launches limited to a
+// few CTAs per SM (an update running beside other kernels): fewer threads, the same bytes in flight.
+template <int VPT>
 __global__ void __launch_bounds__(256)
 adam_kernel(long long n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
             float* __restrict__ v, const long long* __restrict__ step_dev, float lr, double b1,
@@ -286,20 +289,21 @@ adam_kernel(long long n, float* __restrict__ p, const float* __restrict__ g, flo
   c.b1f = (float)b1; c.b2f = (float)b2; c.omb1 = (float)(1.0 - b1); c.omb2 = (float)(1.0 - b2);
   c.gs = gscale_dev ? *gscale_dev : 1.f;
   c.k1 = sqrtf(c.bc2) / c.bc1; c.lr = lr; c.eps = eps; c.eps_mode = eps_mode;
-  const long long n8 = n & ~7ll;
-  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
-  const long long stride = (long long)gridDim.x * blockDim.x * 8;
+  constexpr int EPT = 4 * VPT;                       // elements per thread per iteration
+  const long long n8 = n - n % EPT;
+  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * EPT;
+  const long long stride = (long long)gridDim.x * blockDim.x * EPT;
   for (; i < n8; i += stride) {
-    float4 pq[2], gq[2], mq[2], vq[2];
+    float4 pq[VPT], gq[VPT], mq[VPT], vq[VPT];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < VPT; ++h) {
       pq[h] = *reinterpret_cast<const float4*>(p + i + 4 * h);
       gq[h] = __ldg(reinterpret_cast<const float4*>(g + i + 4 * h));
       mq[h] = *reinterpret_cast<const float4*>(m + i + 4 * h);
       vq[h] = *reinterpret_cast<const float4*>(v + i + 4 * h);
     }
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < VPT; ++h) {
       adam_one(pq[h].x, gq[h].x, mq[h].x, vq[h].x, c);
       adam_one(pq[h].y, gq[h].y, mq[h].y, vq[h].y, c);
       adam_one(pq[h].z, gq[h].z, mq[h].z, vq[h].z, c);
@@ -309,15 +313,18 @@ adam_kernel(long long n, float* __restrict__ p, const float* __restrict__ g, flo
       *reinterpret_cast<float4*>(v + i + 4 * h) = vq[h];
     }
     if (shadow) {
-      uint4 pk;
-      __nv_bfloat162 t0 = __floats2bfloat162_rn(pq[0].x, pq[0].y), t1 = __floats2bfloat162_rn(pq[0].z, pq[0].w);
-      __nv_bfloat162 t2 = __floats2bfloat162_rn(pq[1].x, pq[1].y), t3 = __floats2bfloat162_rn(pq[1].z, pq[1].w);
-      pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-      pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-      *reinterpret_cast<uint4*>(shadow + i) = pk;
+#pragma unroll
+      for (int h = 0; h < VPT; h += 2) {
+        uint4 pk;
+        __nv_bfloat162 t0 = __floats2bfloat162_rn(pq[h].x, pq[h].y), t1 = __floats2bfloat162_rn(pq[h].z, pq[h].w);
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(pq[h + 1].x, pq[h + 1].y), t3 = __floats2bfloat162_rn(pq[h + 1].z, pq[h + 1].w);
+        pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+        pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+        *reinterpret_cast<uint4*>(shadow + i + 4 * h) = pk;
+      }
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x < (int)(n - n8)) {   // ragged tail (< 8 elements)
+  if (blockIdx.x == 0 && threadIdx.x < (int)(n - n8)) {   // ragged tail (< EPT elements)
     const long long j = n8 + threadIdx.x;
     float pv = p[j], mv = m[j], vv = v[j];
     adam_one(pv, g[j], mv, vv, c);
@@ -920,9 +927,17 @@ extern "C" int b200rl_adam(int64_t n, float* param, const float* grad, float* m,
   B200RL_REQUIRE((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "buffers must be 16-byte aligned");
   if (n == 0) return B200RL_OK;
   static const int per_sm = getenv("B200RL_ADAM_CTAS_PER_SM") ? atoi(getenv("B200RL_ADAM_CTAS_PER_SM")) : 8;   // 0 = one pass, no loop
-  int blocks = grid1d((n + 7) / 8, 256, per_sm > 0 ? kNumSMs * per_sm : (1 << 30));
-  adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(n, param, grad, m, v, (const long long*)step_dev, lr, b1, b2, eps,
-                                                    eps_mode, grad_scale_dev, (__nv_bfloat16*)bf16_shadow);
+  static const int wide = getenv("B200RL_ADAM_WIDE") ? atoi(getenv("B200RL_ADAM_WIDE")) : -1;                 // -1 = by CTA count
+  const bool use_wide = wide >= 0 ? wide != 0 : (per_sm > 0 && per_sm <= 4);
+  if (use_wide) {
+    int blocks = grid1d((n + 15) / 16, 256, per_sm > 0 ? kNumSMs * per_sm : (1 << 30));
+    adam_kernel<4><<<blocks, 256, 0, as_stream(stream)>>>(n, param, grad, m, v, (const long long*)step_dev, lr, b1, b2, eps,
+                                                         eps_mode, grad_scale_dev, (__nv_bfloat16*)bf16_shadow);
+  } else {
+    int blocks = grid1d((n + 7) / 8, 256, per_sm > 0 ? kNumSMs * per_sm : (1 << 30));
+    adam_kernel<2><<<blocks, 256, 0, as_stream(stream)>>>(n, param, grad, m, v, (const long long*)step_dev, lr, b1, b2, eps,
+                                                         eps_mode, grad_scale_dev, (__nv_bfloat16*)bf16_shadow);
+  }
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }

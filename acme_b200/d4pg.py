@@ -16,7 +16,7 @@ from typing import List, Optional
 
 import numpy as np
 
-from acme_b200 import _capi, actors, adders, agent, core, counting, loggers, networks, replay, specs
+from acme_b200 import _capi, actors, adders, agent, core, counting, loggers, networks, parallel, replay, specs
 
 
 class D4PGLearner(core.Learner, core.Saveable):
@@ -26,9 +26,13 @@ class D4PGLearner(core.Learner, core.Saveable):
                discount: float, target_update_period: int, dataset: replay.ReplayDataset,
                policy_lr: float = 1e-4, critic_lr: float = 1e-4, clipping: bool = True,
                counter: counting.Counter = None, logger: loggers.Logger = None, checkpoint: bool = True,
-               eps_mode: int = 0, use_cuda_graph: bool = True):
+               eps_mode: int = 0, use_cuda_graph: bool = True, process_group=None):
+    """`process_group`: data-parallel learner over per-rank replay shards -- both gradient sets are all-reduced (mean) over
+    NCCL between the gradient half and the optimizer half of the step, then clipped and applied identically on every rank
+    (the ordering of the reference's only multi-replica learner, `crr/recurrent_learning.py:346-359`)."""
     import torch
     self._torch = torch
+    self._dp = parallel.DataParallel(process_group)
     self._policy, self._critic = policy_network, critic_network
     self._tpolicy, self._tcritic = target_policy_network, target_critic_network
     self._dataset = dataset
@@ -60,6 +64,9 @@ class D4PGLearner(core.Learner, core.Saveable):
     self._norm_ws = f32(1024)
     self._pscale, self._cscale, self.policy_norm, self.critic_norm = f32(1), f32(1), f32(1), f32(1)
     self._loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+    self._loss_ring = torch.zeros(2, 2, dtype=torch.float32).pin_memory()      # fetch_loss='async': two slots
+    self._loss_events = [torch.cuda.Event(), torch.cuda.Event()]
+    self._loss_pending = None
     self._obs_dim, self._act_dim = critic_network.obs_dim, critic_network.act_dim
 
   def _views(self):
@@ -70,6 +77,24 @@ class D4PGLearner(core.Learner, core.Saveable):
     return o0, a0, o1
 
   def _device_step_eager(self, uniforms=None):
+    self._gradient_half(uniforms)
+    self._exchange()
+    self._apply_half()
+
+  def _exchange(self):
+    """Data parallel: mean of both gradient sets over the ranks (NCCL all-reduce; not capturable, sits between graphs)."""
+    if not self._dp.enabled:
+      return
+    import torch.distributed as dist
+    for net in (self._policy, self._critic):
+      g = net.params.grad
+      if dist.get_backend(self._dp.group) == 'nccl':
+        dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self._dp.group)
+      else:
+        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self._dp.group)
+        g.mul_(1.0 / self._dp.world)
+
+  def _gradient_half(self, uniforms=None):
     st = _capi.current_stream()
     P, C, TP, TC = self._policy, self._critic, self._tpolicy, self._tcritic
     ds, B = self._dataset, self.B
@@ -98,7 +123,11 @@ class D4PGLearner(core.Learner, core.Saveable):
     _capi.call('b200rl_dpg_action_grad', B, self._act_dim, _capi.ptr(self.dqda), 1.0 if self._clipping else 0.0,
                int(self._clipping), 1.0 / B, _capi.ptr(self.da), _capi.ptr(self.policy_loss_ps), _capi.ptr(self.policy_loss), st)
     P.backward_action(o1, self._p_online, self._pg, self.da)
-    # clip each gradient set by its global norm (learning.py:235-237), then the two Adams (240-241)
+
+  def _apply_half(self):
+    """clip each gradient set by its global norm (learning.py:235-237), then the two Adams (240-241), step counter."""
+    st = _capi.current_stream()
+    P, C = self._policy, self._critic
     pscale = cscale = None
     if self._clipping:
       _capi.call('b200rl_global_norm_scale', P.params.size, _capi.ptr(P.params.grad), 40.0, _capi.ptr(self._norm_ws),
@@ -117,12 +146,20 @@ class D4PGLearner(core.Learner, core.Saveable):
       self._device_step_eager(uniforms)
       return
     if self._graph is None:
-      g = torch.cuda.CUDAGraph()
-      torch.cuda.synchronize()
-      with torch.cuda.graph(g):
-        self._device_step_eager(None)
-      self._graph = g
-    self._graph.replay()
+      def capture(fn):
+        g = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g):
+          fn()
+        return g
+      if self._dp.enabled:     # the all-reduces sit between two graphs
+        self._graph = (capture(lambda: self._gradient_half(None)), capture(self._apply_half))
+      else:
+        self._graph = (capture(lambda: self._device_step_eager(None)),)
+    self._graph[0].replay()
+    if self._dp.enabled:
+      self._exchange()
+      self._graph[1].replay()
 
   def step(self, uniforms=None, fetch_loss: bool = True):
     table = self._dataset.table
@@ -132,7 +169,16 @@ class D4PGLearner(core.Learner, core.Saveable):
     self._device_step(uniforms)
     self._steps_done += 1
     result = {}
-    if fetch_loss:
+    if fetch_loss == 'async':   # copy to pinned memory now, consume when the next step has been issued (or at drain())
+      slot = self._steps_done & 1
+      self._loss_ring[slot, 0:1].copy_(self.critic_loss, non_blocking=True)
+      self._loss_ring[slot, 1:2].copy_(self.policy_loss, non_blocking=True)
+      self._loss_events[slot].record()
+      previous, self._loss_pending = self._loss_pending, slot
+      if previous is not None:
+        self._loss_events[previous].synchronize()
+        result = {'critic_loss': float(self._loss_ring[previous, 0]), 'policy_loss': float(self._loss_ring[previous, 1])}
+    elif fetch_loss:
       self._loss_host[0:1].copy_(self.critic_loss, non_blocking=True)
       self._loss_host[1:2].copy_(self.policy_loss, non_blocking=True)
       self._torch.cuda.current_stream().synchronize()
@@ -142,6 +188,16 @@ class D4PGLearner(core.Learner, core.Saveable):
     self._timestamp = timestamp
     result.update(self._counter.increment(steps=1, walltime=elapsed))
     self._logger.write(result)
+
+  def drain(self):
+    """The losses still in flight from a `fetch_loss='async'` step (or None)."""
+    if self._loss_pending is None:
+      return None
+    slot, self._loss_pending = self._loss_pending, None
+    self._loss_events[slot].synchronize()
+    out = {'critic_loss': float(self._loss_ring[slot, 0]), 'policy_loss': float(self._loss_ring[slot, 1])}
+    self._logger.write(out)
+    return out
 
   def get_variables(self, names: List[str]) -> List[List[np.ndarray]]:
     nets = {'critic': self._tcritic, 'policy': self._tpolicy}   # learning.py:133-140: target networks

@@ -112,8 +112,35 @@ class ParamStore:
     return self.view(name, grad).detach().cpu().numpy().copy()
 
 
+class Marks:
+  """tools/step_phases.py: global-timer stamps issued between kernels (also inside a captured step); name -> slot."""
+
+  def __init__(self, device: int, slots: int = 128):
+    import torch
+    self.buf = torch.zeros(slots, dtype=torch.int64, device=torch.device('cuda', device))
+    self.slots = {}
+
+  def mark(self, name: str):
+    import ctypes
+    slot = self.slots.setdefault(name, len(self.slots))
+    if slot < self.buf.numel():
+      _capi.load().b200rl_debug_stamp(ctypes.c_void_p(self.buf.data_ptr()), slot, ctypes.c_void_p(_capi.current_stream()))
+
+  def timeline(self):
+    t = self.buf.cpu().numpy()
+    ev = sorted((int(t[s]), n) for n, s in self.slots.items() if s < len(t) and t[s] > 0)
+    t0 = ev[0][0] if ev else 0
+    return [(n, (x - t0) / 1e3) for x, n in ev]
+
+
 class Network:
   """Common plumbing: parameter store, workspace, precision."""
+  marks: Optional[Marks] = None
+  mark_prefix = ''
+
+  def _mark(self, name: str):
+    if self.marks is not None:
+      self.marks.mark(self.mark_prefix + name)
 
   def __init__(self, device: int = 0, precision: int = _capi.PRECISION_FP32):
     self.device = device
@@ -347,15 +374,18 @@ class DQNAtariNetwork(Network):
           raise ValueError('the bf16 dataflow reads uint8 frames')
         rows = self.prepare_frames(obs, 'fwd')
       x, x_rows = rows.data_ptr(), 1
+      self._mark(f'fwd{B}.start')
       for i in range(3):
         y = bufs[f'y{i + 1}']
         _capi.call('b200rl_conv2d_fwd_bf16', x, x_rows, P.sp(f'conv{i + 1}.w'), P.p(f'conv{i + 1}.b'), y.data_ptr(), 1,
                    self.geom(i, B), ACT_RELU, ws, wsb, st)
+        self._mark(f'fwd{B}.conv{i + 1}')
         x, x_rows = y.data_ptr(), 0
       if before_fc1 is not None:
         before_fc1()
       _capi.call('b200rl_linear_fwd_bf16', B, 1024, self.flat_dim, x, self.flat_dim, P.sp('fc1.w'), P.p('fc1.b'),
                  bufs['h'].data_ptr(), 1024, 0, ACT_RELU, ws, wsb, st)
+      self._mark(f'fwd{B}.fc1')
       return bufs['h']
     x, x_u8 = obs.data_ptr(), int(obs.dtype == torch.uint8)
     if rows is not None:              # the frames' row image from prepare_frames()
@@ -512,10 +542,12 @@ class DQNAtariNetwork(Network):
       for st in streams:
         st.wait_event(ev)
 
+    self._mark('bwd.start')
     fork(s1, s2)
     with torch.cuda.stream(s1):
       self.lane(1)
       self._fc1_wgrad(bufs, gbufs, bias=not flow)
+      self._mark('bwd.s1.fc1_wgrad')
       ev_w = torch.cuda.Event()
       ev_w.record(s1)
     with torch.cuda.stream(s2):
@@ -523,23 +555,28 @@ class DQNAtariNetwork(Network):
       self.head_wgrad(bufs, gbufs)
       if flow:
         self._fc1_bias_grad(bufs, gbufs)
+      self._mark('bwd.s2.head_wgrad+fc1_db')
       ev_h = torch.cuda.Event()
       ev_h.record(s2)
     if on_dense_done is not None:
       on_dense_done([ev_w, ev_h])
     self.lane(0)
     self._fc1_dgrad(bufs, gbufs)
+    self._mark('bwd.fc1_dgrad')
     for i in (2, 1):
       fork(s1, s2) if flow else fork(s1)
       with torch.cuda.stream(s1):
         self.lane(1)
         self._conv_wgrad(i, obs, bufs, gbufs, rows, bias=not flow)
+        self._mark(f'bwd.s1.conv{i + 1}_wgrad')
       if flow:
         with torch.cuda.stream(s2):
           self.lane(2)
           self._conv_bias_grad(i, bufs, gbufs)
+          self._mark(f'bwd.s2.conv{i + 1}_db')
       self.lane(0)
       self._conv_dgrad(i, bufs, gbufs)
+      self._mark(f'bwd.conv{i + 1}_dgrad')
     if flow:
       fork(s2)
       with torch.cuda.stream(s2):
@@ -547,6 +584,7 @@ class DQNAtariNetwork(Network):
         self._conv_bias_grad(0, bufs, gbufs)
     self.lane(0)
     self._conv_wgrad(0, obs, bufs, gbufs, rows, bias=not flow)
+    self._mark('bwd.conv1_wgrad')
     for st in (s1, s2):
       ev = torch.cuda.Event()
       ev.record(st)

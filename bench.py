@@ -106,6 +106,32 @@ def fill_replay(table, steps, n_step, seed, chunk=32768):
   return info
 
 
+def fill_replay_control(table, steps, n_step, seed, obs_dim, act_dim, chunk=65536):
+  """C3: obs f32[obs_dim] ~ N(0,1), act f32[act_dim] ~ U(-1,1), reward ~ U(0,1), env discount 1 except 0
+  w.p. 1/1000, ~1000-step episodes; observations generated on the device (set-up, not timed)."""
+  import ctypes as C
+  import torch
+  from acme_b200 import _capi
+  stream = SynthStream(seed)
+  wid = C.c_int32()
+  _capi.call('b200rl_writer_open', table.handle, C.byref(wid))
+  gen = torch.Generator(device='cuda')
+  gen.manual_seed(seed)
+  rng = np.random.default_rng(seed)
+  done = 0
+  while done < steps:
+    n = min(chunk, steps - done)
+    _, _, disc, first, last = stream.chunk(n)
+    act = rng.uniform(-1, 1, (n, act_dim)).astype(np.float32)
+    rew = rng.random(n, dtype=np.float32)
+    obs = torch.randn((n, obs_dim), dtype=torch.float32, device='cuda', generator=gen)
+    _capi.call('b200rl_writer_append_stream', table.handle, wid.value, n, obs.data_ptr(), 1, act.ctypes.data, rew.ctypes.data,
+               disc.ctypes.data, first.ctypes.data, last.ctypes.data, n_step, 1.0, _capi.current_stream())
+    torch.cuda.synchronize()
+    done += n
+  return table.info()
+
+
 # ------------------------------------------------------------------------------ clocks sampler
 class ClockSampler:
   """nvidia-smi sampler (the recipe's clocks line).  It is started before the warm-up and samples every 50 ms;
@@ -198,6 +224,103 @@ class CpuReferencePath:
     out = self.learner.step(self.obs[s], self.act[s], R, D, self.obs[s + self.n], prob.astype(np.float32))
     self.tree.set(idx, out['priority']**0.6)              # update_priorities
     return float(out['loss'])
+
+
+D4PG_METRIC = 'learner_updates_per_sec_d4pg_control_b256'
+D4PG_UNIT = 'updates/s (one update = 256 transitions; N ranks do N x 256 per data-parallel step)'
+D4PG_WORKLOAD = 'D4PG control-suite humanoid-shaped 67-d obs / 21-d act, C51 critic (51 atoms), uniform replay 1M items, batch 256, n=5 (BASELINE configs[2])'
+OBS_DIM, ACT_DIM, ATOMS = 67, 21, 51
+# MACs per sample: critic 451,328, policy 153,600; step = 3 critic fwd + 2 policy fwd + critic bwd (2x) +
+# critic dgrad-only (1x) + policy bwd (2x)
+D4PG_STEP_FLOPS = 2 * (3 * 451_328 + 2 * 153_600 + 2 * 451_328 + 451_328 + 2 * 153_600) * 256
+TREE_METRIC = 'per_samples_per_sec_sumtree_sweep'
+TREE_UNIT = 'prioritized samples/s (K1 draws, whole job; one step = one stratified draw of B per rank + the priority update of the drawn items)'
+
+
+class CpuD4PGPath:
+  """The reference's CPU path of C3 restated: NumPy gather + n-step over a host ring, PyTorch-CPU D4PG learner
+  (oracle.learner.D4PGOracleLearner: dense l2_project, CE, DPG with dq/da clipping, global-norm clip, two Adams)."""
+
+  def __init__(self, ring=65536, batch=256, n_step=5, seed=0, threads=None):
+    import torch
+    from oracle import learner as olearner
+    from oracle import nets as onets
+    self.threads = threads or os.cpu_count()
+    torch.set_num_threads(self.threads)
+    rng = np.random.default_rng(seed)
+    self.rng, self.B, self.n, self.ring = rng, batch, n_step, ring
+    self.obs = rng.standard_normal((ring, OBS_DIM)).astype(np.float32)
+    self.act = rng.uniform(-1, 1, (ring, ACT_DIM)).astype(np.float32)
+    self.rew = rng.random(ring, dtype=np.float32)
+    self.disc = np.where(rng.random(ring) < 1e-3, 0., 1.).astype(np.float32)
+    pol, cri = onets.D4PGPolicy(OBS_DIM, ACT_DIM, seed=seed), onets.D4PGCritic(OBS_DIM, ACT_DIM, seed=seed + 1)
+    tp, tc = onets.D4PGPolicy(OBS_DIM, ACT_DIM, seed=seed), onets.D4PGCritic(OBS_DIM, ACT_DIM, seed=seed + 1)
+    self.learner = olearner.D4PGOracleLearner(pol, cri, tp, tc, 0.99, 100)
+    self.g = np.float32(0.99)
+
+  def step(self):
+    s = self.rng.integers(0, self.ring - self.n - 1, self.B)       # uniform table
+    R, D = self.rew[s].copy(), self.disc[s].copy()
+    for j in range(1, self.n):
+      D = D * self.g
+      R = R + self.rew[s + j] * D
+      D = D * self.disc[s + j]
+    out = self.learner.step(self.obs[s], self.act[s], R, D, self.obs[s + self.n])
+    return float(out['critic_loss'])
+
+
+class CpuTreePath:
+  """Reverb-Prioritized-like binary f64 sum tree on the host: B root-to-leaf walks + B leaf updates per step."""
+
+  def __init__(self, items, batch, seed=0):
+    from oracle import sumtree
+    self.rng = np.random.default_rng(seed)
+    self.tree = sumtree.BinarySumTreeF64(items)
+    self.tree.build(np.abs(self.rng.standard_normal(items))**0.6)
+    self.B = batch
+    self.threads = 1
+
+  def step(self):
+    idx, _ = self.tree.sample(self.rng.random(self.B))
+    self.tree.set(idx, np.abs(self.rng.standard_normal(self.B))**0.6)
+
+
+def _cpu_model():
+  cpu = open('/proc/cpuinfo').read()
+  return next((l.split(':', 1)[1].strip() for l in cpu.splitlines() if l.startswith('model name')), 'unknown')
+
+
+def run_reference_other(args):
+  """Reference arm of the d4pg / sumtree workloads (rank 0 only): the CPU restatement on the host cores."""
+  if int(os.environ.get('RANK', '0')) != 0:
+    return
+  t0 = time.time()
+  if args.workload == 'd4pg':
+    ref, metric, unit, workload, per_step = CpuD4PGPath(seed=1234), D4PG_METRIC, D4PG_UNIT, D4PG_WORKLOAD, 1.0
+    sample = (f'{args.steps} full D4PG learner updates (B=256, critic (512,512,256)+51 atoms, policy (256,256,256)), NumPy n-step over a '
+              f'{ref.ring}-step host ring, PyTorch-CPU, {ref.threads} threads, {_cpu_model()}')
+  else:
+    Bt = min(args.tree_batch, 1 << 16)      # bounded sample: the host tree walks ~1e5 samples/s
+    ref, metric, unit, per_step = CpuTreePath(min(args.items, 4_000_000), Bt, seed=1234), TREE_METRIC, TREE_UNIT, float(Bt)
+    workload = f'sum-tree sweep point: {args.items:,} items per rank, {args.tree_batch:,} draws + updates per step (BASELINE configs[3])'
+    sample = (f'{args.steps} steps of {Bt:,} draws + {Bt:,} updates on a binary f64 NumPy sum tree over {ref.tree.n if hasattr(ref.tree, "n") else min(args.items, 4_000_000):,} '
+              f'priorities (bounded: the GPU arm uses {args.items:,} items and {args.tree_batch:,} draws per step), 1 thread, {_cpu_model()}')
+  for _ in range(args.warmup):
+    ref.step()
+  t1 = time.time()
+  for _ in range(args.steps):
+    ref.step()
+  dt = (time.time() - t1) / max(args.steps, 1)
+  value = per_step / dt
+  print(json.dumps({
+      'impl': 'reference', 'metric': metric, 'value': value, 'unit': unit, 'n_gpus': args.gpus, 'steps': args.steps,
+      'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+      'dtype': 'f32' if args.workload == 'd4pg' else 'f64', 'data': 'synthetic',
+      'config': {'workload': workload, 'note': 'reference arm = CPU restatement (oracle port); Acme TF/JAX + Reverb are not installable offline'},
+      'cpu_baseline': {'value': value, 'unit': unit.split(' (')[0], 'cores': ref.threads, 'kind': 'port', 'sample': sample},
+      'e2e': {'value': value, 'unit': unit.split(' (')[0], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+      'setup_s': t1 - t0,
+  }))
 
 
 def run_reference(args):
@@ -475,6 +598,297 @@ def run_ours(args):
     dist.destroy_process_group()
 
 
+def _dist_setup():
+  import torch
+  import torch.distributed as dist
+  rank, world, local = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('LOCAL_RANK', '0'))
+  torch.cuda.set_device(local)
+  pg = None
+  if world > 1:
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    pg = dist.group.WORLD
+  return rank, world, local, pg
+
+
+def _max_over_ranks(x, world):
+  import torch
+  import torch.distributed as dist
+  if world == 1:
+    return x
+  t = torch.tensor([x], device='cuda')
+  dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  return float(t)
+
+
+def run_d4pg(args):
+  """BASELINE configs[2]: D4PG learner updates/s on control-suite-humanoid-shaped transitions."""
+  import torch
+  import torch.distributed as dist
+  from acme_b200 import _capi, adders, d4pg, dm_env, loggers, networks, replay, specs
+  rank, world, local, pg = _dist_setup()
+  _capi.require_device(local)
+  P = peaks()
+  B, n_step, items = 256, 5, args.items
+  spec = specs.EnvironmentSpec(specs.Array((OBS_DIM,), np.float32), specs.BoundedArray((ACT_DIM,), np.float32, -1., 1.),
+                               specs.Array((), np.float32), specs.BoundedArray((), np.float32, 0., 1.))
+  table = replay.Table(replay.DEFAULT_PRIORITY_TABLE, replay.selectors.Uniform(), replay.selectors.Fifo(), max_size=items,
+                       rate_limiter=replay.rate_limiters.MinSize(1), signature=adders.NStepTransitionAdder.signature(spec),
+                       max_window=n_step, discount=0.99, device=local, slot_capacity=items + 4096, shard_count=world,
+                       shard_rank=rank, stage_slots=4096)
+  server = replay.Server([table])
+  t_setup = time.time()
+  info = fill_replay_control(table, items, n_step, 1234 + rank, OBS_DIM, ACT_DIM)
+  precision = _capi.PRECISION_FP32 if args.precision == 'fp32' else _capi.PRECISION_TC
+  policy = networks.D4PGPolicy(OBS_DIM, ACT_DIM, device=local, precision=precision, seed=1)
+  critic = networks.D4PGCritic(OBS_DIM, ACT_DIM, device=local, precision=precision, seed=2)
+  ds = replay.ReplayDataset(table, B, seed=1234 + rank, stratified=False)
+  client = replay.Client(server)
+  learner = d4pg.D4PGLearner(policy, critic, policy.clone(), critic.clone(), 0.99, 100, ds, logger=loggers.NoOpLogger(),
+                             process_group=pg, use_cuda_graph=not args.no_graph)
+  adder = adders.NStepTransitionAdder(client, n_step=n_step, discount=0.99)
+  t_setup = time.time() - t_setup
+  lib = _capi.load()
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  clocks = ClockSampler(local)
+  for _ in range(max(args.warmup, 3)):
+    learner.step(fetch_loss=False)
+  barrier()
+  launches0 = lib.b200rl_launch_count()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  barrier()
+  clocks.mark()
+  e0.record()
+  for _ in range(args.steps):
+    learner.step(fetch_loss=False)
+  e1.record()
+  barrier()
+  clocks.mark()
+  clk = clocks.stop()
+  dev_s = _max_over_ranks(e0.elapsed_time(e1) * 1e-3, world)
+  value = world * args.steps / dev_s
+  gpu_launches = int(lib.b200rl_launch_count() - launches0) if args.no_graph else None
+
+  # ---- end to end: 8 adder.add() from host numpy per update (batch 256 / samples_per_insert 32, d4pg/agent.py:176-180)
+  rng = np.random.default_rng(99 + rank)
+  host_obs = rng.standard_normal((64, OBS_DIM)).astype(np.float32)
+  host_act = rng.uniform(-1, 1, (64, ACT_DIM)).astype(np.float32)
+  inserts = 8
+  adder.add_first(dm_env.restart(host_obs[0]))
+
+  def e2e_step(i):
+    for j in range(inserts):
+      k = (i * inserts + j + 1) % 64
+      adder.add(host_act[k], dm_env.transition(np.float32(0.5), host_obs[k], np.float32(1.)))
+    learner.step(fetch_loss='async')
+
+  for i in range(3):
+    e2e_step(i)
+  barrier()
+  t0 = time.perf_counter()
+  e2e_steps = max(args.steps, 10)
+  for i in range(e2e_steps):
+    e2e_step(i + 3)
+  last = learner.drain()
+  assert last is not None and np.isfinite(last['critic_loss'])
+  barrier()
+  e2e_s = _max_over_ranks(time.perf_counter() - t0, world)
+  e2e_value = world * e2e_steps / e2e_s
+  h2d = inserts * (OBS_DIM * 4 + ACT_DIM * 4 + 4 + 4 + 4) + inserts * 24 + 16
+  d2h = 8
+
+  stages, k5 = {}, None
+  if rank == 0:
+    it = 30
+    stages['k1_sample_uniform'] = time_stage(ds.sample_only, it, torch)
+    stages['k3_gather_nstep'] = time_stage(ds.gather_only, it, torch)
+    g_half = torch.cuda.CUDAGraph()
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g_half):
+      learner._gradient_half(None)
+    stages['gradient_half_in_graph (K1, K3, 5 MLP passes, K5, DPG)'] = time_stage(g_half.replay, it, torch)
+    K = critic.K
+    t5 = time_stage(lambda: _capi.call(
+        'b200rl_c51_loss', B, K, critic.vmin, critic.vmax, learner._c_train['out'].data_ptr(), learner._c_tgt['out'].data_ptr(),
+        ds.R.data_ptr(), ds.D.data_ptr(), 0.99, 1.0 / B, learner.target.data_ptr(), learner.critic_loss_ps.data_ptr(),
+        learner.dlogits.data_ptr(), None, _capi.current_stream()), it, torch)
+    stages['k5_c51_project_ce'] = t5
+    k5 = {'alg_bytes': B * 828, 'us': t5 * 1e6, 'GBps': B * 828 / t5 / 1e9, 'frac_of_hbm_peak': B * 828 / t5 / 1e9 / P['hbm'],
+          'note': 'launch-latency bound at B = 256 (212 KB per launch); the HBM regime is tools/ncu_hbm_kernels.py (B = 65,536)'}
+
+  cpu_baseline = None
+  if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    ref = CpuD4PGPath(seed=1234)
+    ref.step()
+    t0 = time.time()
+    n_cpu = 0
+    while n_cpu < 3 or (time.time() - t0 < 12 and n_cpu < 200):
+      ref.step()
+      n_cpu += 1
+    cdt = (time.time() - t0) / n_cpu
+    cpu_baseline = {'value': 1.0 / cdt, 'unit': 'updates/s', 'cores': ref.threads, 'kind': 'port',
+                    'sample': f'{n_cpu} full D4PG learner updates of the same workload on the host (oracle port: NumPy n-step over a '
+                              f'{ref.ring}-step ring, PyTorch-CPU critic/policy, dense l2_project, B=256)'}
+  if rank == 0:
+    grp = stages.get('gradient_half_in_graph (K1, K3, 5 MLP passes, K5, DPG)', 0)
+    achieved = D4PG_STEP_FLOPS / grp / 1e12 if grp else None
+    print(json.dumps({
+        'metric': D4PG_METRIC, 'value': value, 'unit': D4PG_UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+        'ms_per_step': dev_s / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32 (dense layers below 0.13 GFLOP take the exact FFMA path; larger ones tf32/bf16 tensor-core operands)' if precision else 'f32',
+        'data': 'synthetic',
+        'config': {'workload': D4PG_WORKLOAD, 'items_per_rank': info['size'], 'batch_per_rank': B, 'n_step': n_step,
+                   'networks': 'critic LayerNormMLP(512,512,256) + DiscreteValuedHead(51), policy LayerNormMLP(256,256,256) + tanh',
+                   'optimizer': 'Adam 1e-4 x2, global-norm clip 40',
+                   'parallelism': f'dp{world}: per-rank replay shard, NCCL all-reduce(mean) of both gradient sets' if world > 1 else 'single GPU',
+                   'cuda_graph': not args.no_graph,
+                   'l2_policy': 'the 628 MB transition ring is sampled uniformly at random; parameters and activations (< 10 MB) are L2-resident by nature of the workload'},
+        'clocks': clk,
+        'e2e': {'value': e2e_value, 'unit': 'updates/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': e2e_steps,
+                'what': f"{inserts} adder.add() calls from host numpy (pinned staging -> H2D) + learner.step(fetch_loss='async') per update, "
+                        'both losses copied to pinned host memory every update'},
+        'gpu_launches': gpu_launches if gpu_launches is not None else 'captured graph (count with --no-graph)',
+        'roofline': {'kernel': 'critic / policy MLP group of the gradient half (3 critic + 2 policy forwards, critic backward, dq/da, policy backward)',
+                     'bound': 'tensor', 'achieved': achieved, 'peak': P['tf_sustained'], 'unit': 'TFLOP/s',
+                     'frac': achieved / P['tf_sustained'] if achieved else None, 'traffic': None,
+                     'peak_source': f"{P['src']} (sustained bf16 dense peak)", 'alg_flops_per_launch_group': D4PG_STEP_FLOPS,
+                     'group_seconds': grp,
+                     'note': '1.7 GFLOP per step over ~100 small launches: launch- and latency-bound, not tensor-bound'},
+        'hbm_kernels': {'k5_c51_project_ce': k5},
+        'cpu_baseline': cpu_baseline,
+        'stages_us': {k: v * 1e6 for k, v in stages.items()},
+        'setup_s': t_setup,
+    }))
+  server.stop()
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def run_sumtree(args):
+  """BASELINE configs[3]: prioritized sampling / update sweep point, one shard of `--items` priorities per rank, each rank
+  drawing `--tree-batch` items locally per step; probabilities normalised by the GLOBAL priority mass (all-reduce of the
+  shard masses)."""
+  import torch
+  import torch.distributed as dist
+  from acme_b200 import _capi, parallel, replay
+  rank, world, local, pg = _dist_setup()
+  _capi.require_device(local)
+  P = peaks()
+  N, B = args.items, args.tree_batch
+  gen = torch.Generator(device='cuda')
+  gen.manual_seed(1234 + rank)
+  table = replay.Table.priorities_only('t', 0.6, N, device=local, shard_count=world, shard_rank=rank)
+  w = torch.randn(N, device='cuda', generator=gen).abs_() * (1.0 + 0.1 * rank)      # shards of unequal mass
+  table.set_weights(w)
+  del w
+  dp = parallel.DataParallel(pg)
+  total = dp.refresh_global_mass(table)
+  L, F, S_small = table.tree_levels()
+  u = torch.rand(B, device='cuda', generator=gen)
+  idx = torch.empty(B, dtype=torch.int64, device='cuda')
+  keys = torch.empty(B, dtype=torch.uint64, device='cuda')
+  prob = torch.empty(B, device='cuda')
+  pr = torch.randn(B, device='cuda', generator=gen).abs_()
+
+  def step():
+    table.sample_into(u, idx, keys, prob, True)            # K1: local draws, probabilities = weight / sum_r M_r
+    table.update_priorities_device(keys, pr)               # K2
+    dp.refresh_global_mass(table, total)                   # one scalar all-reduce(SUM): the new global mass
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  clocks = ClockSampler(local)
+  for _ in range(max(args.warmup, 3)):
+    step()
+  barrier()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  barrier()
+  clocks.mark()
+  e0.record()
+  for _ in range(args.steps):
+    step()
+  e1.record()
+  barrier()
+  clocks.mark()
+  clk = clocks.stop()
+  dev_s = _max_over_ranks(e0.elapsed_time(e1) * 1e-3, world)
+  value = world * args.steps * B / dev_s
+  # sanity: with the global mass installed the probabilities of ALL shards' items sum to one
+  masses = dp.gather_scalars(table.mass_tensor())
+  ts = time_stage(lambda: table.sample_into(u, idx, keys, prob, True), 10, torch)
+  tu = time_stage(lambda: table.update_priorities_device(keys, pr), 10, torch)
+  # end to end: uniforms from pinned host memory in, sampled keys + probabilities back to pinned host memory, every step
+  hu = torch.rand(B).pin_memory()
+  hk, hp = torch.empty(B, dtype=torch.int64).pin_memory(), torch.empty(B).pin_memory()
+  barrier()
+  t0 = time.perf_counter()
+  e2e_steps = max(args.steps // 2, 5)
+  for _ in range(e2e_steps):
+    u.copy_(hu, non_blocking=True)
+    step()
+    hk.copy_(keys.view(torch.int64), non_blocking=True)
+    hp.copy_(prob, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+  barrier()
+  e2e_s = _max_over_ranks(time.perf_counter() - t0, world)
+  staged = 0
+  used = 0
+  budget = (160 if B >= 16384 else 16) * 1024
+  for l in range(1, L + 1):
+    wl = len(table.read_tree_level(l)) * 4 if l < L else N * 4
+    if used + wl > budget:
+      break
+    used += wl
+    staged = l
+  sample_bytes = (L - staged) * F * 4 + 28
+  cpu_baseline = None
+  if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    Bt = min(B, 1 << 15)
+    ref = CpuTreePath(min(N, 4_000_000), Bt, seed=1234)
+    t0 = time.time()
+    n_cpu = 0
+    while n_cpu < 2 or (time.time() - t0 < 10 and n_cpu < 50):
+      ref.step()
+      n_cpu += 1
+    cdt = (time.time() - t0) / n_cpu
+    cpu_baseline = {'value': Bt / cdt, 'unit': 'samples/s', 'cores': 1, 'kind': 'port',
+                    'sample': f'{n_cpu} steps of {Bt:,} draws + {Bt:,} updates on a binary f64 NumPy sum tree over {min(N, 4_000_000):,} priorities'}
+  if rank == 0:
+    m = masses.cpu().numpy().astype(np.float64)
+    print(json.dumps({
+        'metric': TREE_METRIC, 'value': value, 'unit': TREE_UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+        'ms_per_step': dev_s / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic',
+        'config': {'workload': f'sum-tree sweep point: {N:,} items per rank, {B:,} draws + updates per step (BASELINE configs[3])',
+                   'levels': L, 'fanout': F, 'staged_levels': staged, 'alpha': 0.6,
+                   'parallelism': (f'{world} shards, one per GPU; local sampling; global-priority-mass normalisation by one scalar '
+                                   'all-reduce(SUM) per step') if world > 1 else 'single shard',
+                   'l2_policy': f'tree of {N:,} leaves = {8 * N / 1e6:.0f} MB of values + prefix lines, sampled at random (larger than L2 for N >= 2^24)'},
+        'clocks': clk,
+        'shard_masses': m.tolist(), 'mass_imbalance_max_over_mean': float(m.max() / m.mean()), 'global_mass': float(total.item()),
+        'e2e': {'value': world * e2e_steps * B / e2e_s, 'unit': 'samples/s', 'h2d_bytes_per_step': 4 * B, 'd2h_bytes_per_step': 12 * B,
+                'steps': e2e_steps, 'what': 'uniforms from pinned host memory, sampled keys and probabilities copied back to pinned host memory, every step'},
+        'gpu_launches': 'see stages',
+        'roofline': {'kernel': 'k1 sample_kernel', 'bound': 'hbm', 'achieved': B * sample_bytes / ts / 1e9, 'peak': P['hbm'], 'unit': 'GB/s',
+                     'frac': B * sample_bytes / ts / 1e9 / P['hbm'], 'traffic': None, 'peak_source': P['src'],
+                     'alg_bytes_per_sample': sample_bytes,
+                     'note': 'algorithmic bytes per SURVEY §8d: (L - S) * 128 + 28; DRAM bytes of the N = 1e8, B = 2^20 point are in profiles/ncu_full_r02_hbm_kernels.csv'},
+        'stages_us': {'k1_sample': ts * 1e6, 'k2_update': tu * 1e6},
+        'update': {'updates_per_sec_per_gpu': B / tu, 'alg_bytes_per_item': 4 + L * (F * 4 + 4) + 12},
+        'cpu_baseline': cpu_baseline,
+    }))
+  table.close()
+  if world > 1:
+    dist.destroy_process_group()
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
@@ -484,15 +898,26 @@ def main():
   ap.add_argument('--precision', default=os.environ.get('B200RL_PRECISION', 'bf16'), choices=['fp32', 'tf32', 'tc', 'bf16'],
                   help="'bf16' (default): bf16 dataflow on tcgen05 (kind::f16); 'tf32' ('tc'): fp32 tensors with tf32 operands; "
                        "both with the stated tolerances of tests/test_gpu_learner.py; 'fp32': SIMT FFMA, 1e-5 parity with the oracle")
-  ap.add_argument('--items', type=int, default=1_000_000)
+  ap.add_argument('--workload', default='dqn', choices=['dqn', 'd4pg', 'sumtree'],
+                  help='dqn (default): BASELINE configs[1], the headline metric; d4pg: configs[2]; sumtree: a point of the configs[3] sweep')
+  ap.add_argument('--items', type=int, default=None, help='items per rank (default 1M; sumtree: 100M)')
+  ap.add_argument('--tree-batch', type=int, default=1 << 20, help='sumtree: draws (and updates) per rank per step')
   ap.add_argument('--no-graph', action='store_true')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--profile', action='store_true', help='only warm-up + timed steps (for ncu captures)')
   args = ap.parse_args()
+  if args.items is None:
+    args.items = 100_000_000 if args.workload == 'sumtree' else 1_000_000
+  if args.workload == 'sumtree' and args.steps == 2000 and args.warmup == 50:
+    args.steps, args.warmup = 100, 5          # a step is 2^20 draws + updates: keep the default run short
   if args.impl == 'reference':
-    if args.steps == 100 and args.warmup == 10:      # defaults sized for the GPU arm; bound the CPU run
-      args.steps, args.warmup = 10, 2
-    run_reference(args)
+    if args.steps >= 100:                     # defaults sized for the GPU arm; bound the CPU run
+      args.steps, args.warmup = (10, 2) if args.workload != 'sumtree' else (3, 1)
+    (run_reference if args.workload == 'dqn' else run_reference_other)(args)
+  elif args.workload == 'd4pg':
+    run_d4pg(args)
+  elif args.workload == 'sumtree':
+    run_sumtree(args)
   else:
     run_ours(args)
 

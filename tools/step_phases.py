@@ -25,6 +25,11 @@ net = networks.DQNAtariNetwork(18, precision=prec, seed=1, device=rank)
 tgt = net.clone()
 ds = replay.ReplayDataset(table, 256, seed=1 + rank)
 L = dqn.DQNLearner(net, tgt, 0.99, 0.2, 1e-3, 100, ds, replay_client=replay.Client(server), logger=loggers.NoOpLogger(), process_group=pg)
+FINE = os.environ.get('B200RL_FINE', '0') == '1'
+if FINE:
+  marks = networks.Marks(rank)
+  net.marks = tgt.marks = marks
+  net.mark_prefix, tgt.mark_prefix = 'on.', 'tgt.'
 names = ['k1 sample + k3 gather', 'forwards (target || batched online)', 'heads + k4 td/loss', 'backward (2 streams)', 'k7 adam', 'k2 priorities + copy + inc']
 for _ in range(10): L.step(fetch_loss=False)
 late = int(os.environ.get('B200RL_PHASES_AFTER', '0'))   # measure after this many extra steps (drift over long runs)
@@ -37,6 +42,11 @@ for _ in range(n):
 if rank == 0:
   for nm, v in zip(names, tot / n): print(f'{nm:28s} {v:8.1f} us')
 if rank == 0: print('sum', round(float((tot / n).sum()), 1), '(each stamp kernel adds ~2 us)')
+if FINE and rank == 0:
+  print('--- fine timeline of the last step (us since the first mark; prefix on. = online net, tgt. = target net; s1 / s2 = side streams)')
+  prev = {}
+  for name, t in marks.timeline():
+    print(f'{t:9.1f}  {name}')
 if L._px is not None:
   import ctypes
   st = np.zeros(8, np.int64)
