@@ -20,7 +20,7 @@ class ReplayCfg(C.Structure):
   _fields_ = [('max_items', c_i64), ('slot_capacity', c_i64), ('obs_bytes', c_i32),
               ('act_bytes', c_i32), ('max_window', c_i32), ('shard_count', c_i32),
               ('shard_rank', c_i32), ('device', c_i32), ('stage_slots', c_i32),
-              ('reserved', c_i32), ('gamma', c_f32), ('reserved_f', c_f32), ('alpha', c_f64)]
+              ('frame_stack', c_i32), ('gamma', c_f32), ('reserved_f', c_f32), ('alpha', c_f64)]
 
 
 class DpCfg(C.Structure):

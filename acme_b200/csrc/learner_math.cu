@@ -928,7 +928,9 @@ extern "C" int b200rl_adam(int64_t n, float* param, const float* grad, float* m,
   if (n == 0) return B200RL_OK;
   static const int per_sm = getenv("B200RL_ADAM_CTAS_PER_SM") ? atoi(getenv("B200RL_ADAM_CTAS_PER_SM")) : 8;   // 0 = one pass, no loop
   static const int wide = getenv("B200RL_ADAM_WIDE") ? atoi(getenv("B200RL_ADAM_WIDE")) : -1;                 // -1 = by CTA count
-  const bool use_wide = wide >= 0 ? wide != 0 : (per_sm > 0 && per_sm <= 4);
+  // measured on B200: the 4-vector variant is SLOWER (0.347 vs 0.318 ms per step at full occupancy, no gain beside other
+  // kernels): more registers per thread cost more than the extra loads in flight bring.  Kept behind B200RL_ADAM_WIDE=1.
+  const bool use_wide = wide > 0;
   if (use_wide) {
     int blocks = grid1d((n + 15) / 16, 256, per_sm > 0 ? kNumSMs * per_sm : (1 << 30));
     adam_kernel<4><<<blocks, 256, 0, as_stream(stream)>>>(n, param, grad, m, v, (const long long*)step_dev, lr, b1, b2, eps,

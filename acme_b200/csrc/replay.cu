@@ -53,12 +53,16 @@ struct SlotFill {   // scalars of one finished step, scattered into the slot arr
   float rew;
   float disc;
 };
+constexpr int kMaxFrameStack = 8;
 struct ItemRec {    // one new item (len > 0) or a tree-only update (len == 0, e.g. eviction)
   int64_t pos;
   int32_t start;
   int32_t end;
   int32_t len;
   float weight;
+  // frame-deduplicated rings: slots of the F-1 observations before `start` / before `end` in the same episode, nearest
+  // first; -1 = before the episode's first observation (the frame stacker's blank frames)
+  int32_t prev[2][kMaxFrameStack - 1];
 };
 
 struct RingView {
@@ -71,10 +75,16 @@ struct RingView {
   int32_t* item_end;
   int32_t* item_len;
   int64_t obs_stride;
-  int32_t obs_bytes;
+  int32_t obs_bytes;      // bytes of one observation as the table's signature (and a gathered batch row) has it
   int32_t act_stride;
   int32_t act_bytes;
   float gamma;
+  // frame deduplication: observations are stacks of F single-byte-element frames on their LAST axis
+  // (acme/wrappers/frame_stacking.py:64-88); a slot stores only the newest frame (slot_bytes = obs_bytes / F) and
+  // item_prev holds, per item, the slots of the older frames of its two observations
+  int32_t frame_stack;    // F (1 = off)
+  int32_t slot_bytes;
+  int32_t* item_prev;     // [M][2][F - 1]
 };
 
 __global__ void scatter_fills_kernel(RingView r, const SlotFill* __restrict__ fills,
@@ -99,6 +109,11 @@ __global__ void scatter_items_kernel(RingView r, const ItemRec* __restrict__ rec
     r.item_start[it.pos] = it.start;
     r.item_end[it.pos] = it.end;
     r.item_len[it.pos] = it.len;
+    if (r.frame_stack > 1) {
+      const int fm = r.frame_stack - 1;
+      for (int w = 0; w < 2; ++w)
+        for (int j = 0; j < fm; ++j) r.item_prev[((size_t)it.pos * 2 + w) * fm + j] = it.prev[w][j];
+    }
   }
   pos_out[i] = it.pos;
   w_out[i] = it.weight;
@@ -216,6 +231,90 @@ gather_rows_kernel(RingView r, const long long* __restrict__ idx, uint8_t* __res
   }
 }
 
+// K3 on a frame-deduplicated ring: a stack [H*W][F] is rebuilt from F single frames (the item's own slot = newest
+// frame = channel F-1, item_prev = the older ones, missing ones read as zero: FrameStacker's blank frames).  F = 4,
+// uint8: thread i loads bytes [4i, 4i+4) of each frame (coalesced), transposes 4x4 bytes and stores 16 bytes = 4 pixels
+// x 4 channels of the batch row; with ROWS it also writes conv1's bf16 row image like gather_rows_kernel.
+template <bool ROWS>
+__global__ void __launch_bounds__(256)
+gather_frames4_kernel(RingView r, const long long* __restrict__ idx, uint8_t* __restrict__ o_tm1, uint8_t* __restrict__ a_tm1,
+                      float* __restrict__ R, float* __restrict__ D, uint8_t* __restrict__ o_t, uint4* __restrict__ rows_tm1,
+                      uint4* __restrict__ rows_t, int W4, int pad_left, int pad_top, int Hp, int row_v16) {
+  const int b = blockIdx.x;
+  const long long pos = idx[b];
+  const int which = blockIdx.y;
+  const int slot = which == 0 ? r.item_start[pos] : r.item_end[pos];
+  const int32_t* pv = r.item_prev + ((size_t)pos * 2 + which) * 3;
+  const uint32_t* f[4];   // channel c = frame of observation k - (3 - c)
+  f[3] = reinterpret_cast<const uint32_t*>(r.obs + (size_t)slot * r.obs_stride);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int ps = pv[j];
+    f[2 - j] = ps >= 0 ? reinterpret_cast<const uint32_t*>(r.obs + (size_t)ps * r.obs_stride) : nullptr;
+  }
+  int4* d4 = reinterpret_cast<int4*>((which == 0 ? o_tm1 : o_t) + (size_t)b * r.obs_bytes);
+  uint4* rows = ROWS ? (which == 0 ? rows_tm1 : rows_t) + (size_t)b * Hp * row_v16 : nullptr;
+  const int nv = r.obs_bytes >> 4;
+  for (int i = blockIdx.z * 256 + threadIdx.x; i < nv; i += 256 * gridDim.z) {
+    uint32_t w[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) w[c] = f[c] ? __ldg(f[c] + i) : 0u;
+    uint32_t px[4];   // pixel p of the vector: bytes (w0.p, w1.p, w2.p, w3.p)
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+      px[p] = ((w[0] >> (8 * p)) & 0xffu) | (((w[1] >> (8 * p)) & 0xffu) << 8) | (((w[2] >> (8 * p)) & 0xffu) << 16) |
+              (((w[3] >> (8 * p)) & 0xffu) << 24);
+    d4[i] = make_int4((int)px[0], (int)px[1], (int)px[2], (int)px[3]);
+    if (ROWS) {
+      const int y = i / W4, xv = i - y * W4;
+      uint32_t o[8];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn((float)(px[p] & 0xffu), (float)((px[p] >> 8) & 0xffu));
+        const __nv_bfloat162 hi = __floats2bfloat162_rn((float)((px[p] >> 16) & 0xffu), (float)(px[p] >> 24));
+        o[2 * p] = *reinterpret_cast<const uint32_t*>(&lo);
+        o[2 * p + 1] = *reinterpret_cast<const uint32_t*>(&hi);
+      }
+      uint4* dst = rows + (size_t)(y + pad_top) * row_v16 + ((4 * xv + pad_left) >> 1);
+      dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+      dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+  }
+  if (which == 0 && blockIdx.z == 0) {
+    const uint8_t* as = r.act + (size_t)slot * r.act_stride;
+    uint8_t* ad = a_tm1 + (size_t)b * r.act_bytes;
+    for (int i = threadIdx.x; i < r.act_bytes; i += 256) ad[i] = as[i];
+    if (threadIdx.x == 0) {
+      // acme/adders/reverb/transition.py:135-145, fp32, every op rounded separately (no FMA)
+      int cur = slot;
+      const int len = r.item_len[pos];
+      float Rv = r.rew[cur], Dv = r.disc[cur];
+      cur = r.next[cur];
+      for (int j = 1; j < len; ++j) {
+        Dv = __fmul_rn(Dv, r.gamma);
+        Rv = __fadd_rn(Rv, __fmul_rn(r.rew[cur], Dv));
+        Dv = __fmul_rn(Dv, r.disc[cur]);
+        cur = r.next[cur];
+      }
+      R[b] = Rv;
+      D[b] = Dv;
+    }
+  }
+}
+
+// device observations that arrive as full stacks [n][frame_bytes][F]: keep the newest frame (last axis index F-1)
+__global__ void extract_newest_frame_kernel(const uint8_t* __restrict__ stacks, uint8_t* __restrict__ ring, long long first_slot,
+                                            long long S, long long obs_stride, int frame_bytes, int F, long long n) {
+  const long long total = n * frame_bytes;
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; e < total; e += stride) {
+    const long long j = e / frame_bytes;
+    const int i = (int)(e - j * frame_bytes);
+    ring[((first_slot + j) % S) * obs_stride + i] = stacks[(j * frame_bytes + i) * (long long)F + (F - 1)];
+  }
+}
+
 __global__ void fill_float_kernel(float* p, long long n, float v) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
@@ -256,6 +355,8 @@ struct b200rl_replay {
   int64_t M = 0, S = 0;
   int64_t obs_stride = 0;
   int32_t act_stride = 0;
+  int32_t F = 1;              // frame_stack (1 = off)
+  int32_t slot_bytes = 0;     // bytes stored per observation slot: obs_bytes, or one frame when F > 1
   RingView ring{};
   float* d_tree = nullptr;
   int64_t tree_floats = 0;
@@ -329,7 +430,7 @@ extern "C" int b200rl_replay_destroy(b200rl_replay* h) {
   cudaSetDevice(h->cfg.device);
   cudaFree(h->ring.obs); cudaFree(h->ring.act); cudaFree(h->ring.rew); cudaFree(h->ring.disc);
   cudaFree(h->ring.next); cudaFree(h->ring.item_start); cudaFree(h->ring.item_end);
-  cudaFree(h->ring.item_len); cudaFree(h->d_tree); cudaFree(h->d_stamp); cudaFree(h->d_epoch);
+  cudaFree(h->ring.item_len); cudaFree(h->ring.item_prev); cudaFree(h->d_tree); cudaFree(h->d_stamp); cudaFree(h->d_epoch);
   cudaFree(h->d_state);
   free_stage(h->stage[0]);
   free_stage(h->stage[1]);
@@ -344,8 +445,11 @@ extern "C" int b200rl_replay_create(b200rl_replay** out, const b200rl_replay_cfg
   B200RL_REQUIRE(cfg->max_window >= 1 && cfg->max_window <= 64, "max_window must be in [1,64]");
   B200RL_REQUIRE(cfg->shard_count >= 1, "shard_count must be >= 1");
   const bool payload = cfg->obs_bytes > 0;
-  B200RL_REQUIRE(!payload || (cfg->slot_capacity >= cfg->max_window + 2 && cfg->slot_capacity < (1ll << 31)),
-                 "slot_capacity must be >= max_window + 2");
+  const int F = cfg->frame_stack > 1 ? cfg->frame_stack : 1;
+  B200RL_REQUIRE(F <= kMaxFrameStack, "frame_stack must be <= %d", kMaxFrameStack);
+  B200RL_REQUIRE(F == 1 || (payload && cfg->obs_bytes % F == 0), "frame_stack must divide obs_bytes (stacks of single-byte elements)");
+  B200RL_REQUIRE(!payload || (cfg->slot_capacity >= cfg->max_window + 1 + F && cfg->slot_capacity < (1ll << 31)),
+                 "slot_capacity must be >= max_window + 1 + frame_stack");
   int rc = b200rl_device_check(cfg->device);
   if (rc) return rc;
   B200RL_CUDA_OK(cudaSetDevice(cfg->device));
@@ -354,7 +458,9 @@ extern "C" int b200rl_replay_create(b200rl_replay** out, const b200rl_replay_cfg
   h->cfg = *cfg;
   h->M = cfg->max_items;
   h->S = payload ? cfg->slot_capacity : 0;
-  h->obs_stride = round_up(cfg->obs_bytes, 16);
+  h->F = F;
+  h->slot_bytes = cfg->obs_bytes / F;
+  h->obs_stride = round_up(h->slot_bytes, 16);
   h->act_stride = (int32_t)round_up(std::max(cfg->act_bytes, 1), 4);
   RingView& r = h->ring;
   r.obs_stride = h->obs_stride;
@@ -362,6 +468,9 @@ extern "C" int b200rl_replay_create(b200rl_replay** out, const b200rl_replay_cfg
   r.act_stride = h->act_stride;
   r.act_bytes = cfg->act_bytes;
   r.gamma = cfg->gamma;
+  r.frame_stack = F;
+  r.slot_bytes = h->slot_bytes;
+  r.item_prev = nullptr;
 
 #define ALLOC(ptr, bytes)                                                        \
   do {                                                                           \
@@ -382,6 +491,10 @@ extern "C" int b200rl_replay_create(b200rl_replay** out, const b200rl_replay_cfg
     ALLOC(r.item_start, h->M * 4);
     ALLOC(r.item_end, h->M * 4);
     ALLOC(r.item_len, h->M * 4);
+    if (F > 1) {
+      ALLOC(r.item_prev, h->M * 2 * (F - 1) * 4);
+      cudaMemset(r.item_prev, 0xff, h->M * 2 * (F - 1) * 4);
+    }
     cudaMemset(r.next, 0xff, h->S * 4);
     cudaMemset(r.item_len, 0, h->M * 4);
   }
@@ -467,11 +580,11 @@ static int flush_impl(b200rl_replay* h, cudaStream_t stream) {
     // staged observations occupy consecutive slot sequence numbers -> at most two runs in the ring
     int64_t first = (int64_t)(h->obs_first_seq % (uint64_t)h->S);
     int64_t run0 = std::min<int64_t>(h->n_obs, h->S - first);
-    B200RL_CUDA_OK(cudaMemcpy2DAsync(r.obs + first * r.obs_stride, r.obs_stride, s.h_obs, r.obs_bytes,
-                                     r.obs_bytes, run0, cudaMemcpyHostToDevice, stream));
+    B200RL_CUDA_OK(cudaMemcpy2DAsync(r.obs + first * r.obs_stride, r.obs_stride, s.h_obs, r.slot_bytes,
+                                     r.slot_bytes, run0, cudaMemcpyHostToDevice, stream));
     if (run0 < h->n_obs)
-      B200RL_CUDA_OK(cudaMemcpy2DAsync(r.obs, r.obs_stride, s.h_obs + run0 * (int64_t)r.obs_bytes,
-                                       r.obs_bytes, r.obs_bytes, h->n_obs - run0,
+      B200RL_CUDA_OK(cudaMemcpy2DAsync(r.obs, r.obs_stride, s.h_obs + run0 * (int64_t)r.slot_bytes,
+                                       r.slot_bytes, r.slot_bytes, h->n_obs - run0,
                                        cudaMemcpyHostToDevice, stream));
   }
   if (h->n_fill > 0) {
@@ -538,12 +651,19 @@ static int alloc_slot(b200rl_replay* h, const void* obs_host, uint64_t* seq_out)
   if (obs_host && !h->stage[h->cur].h_obs) {  // host-observation staging is allocated on first use
     for (int i = 0; i < 2; ++i)
       B200RL_CUDA_OK(cudaMallocHost((void**)&h->stage[i].h_obs,
-                                    (size_t)(h->stage_slots * std::max<int64_t>(h->cfg.obs_bytes, 1))));
+                                    (size_t)(h->stage_slots * std::max<int64_t>(h->slot_bytes, 1))));
   }
   uint64_t seq = h->slot_head++;
   if (obs_host) {
     if (h->n_obs == 0) h->obs_first_seq = seq;
-    memcpy(h->stage[h->cur].h_obs + h->n_obs * (int64_t)h->cfg.obs_bytes, obs_host, h->cfg.obs_bytes);
+    uint8_t* dst = h->stage[h->cur].h_obs + h->n_obs * (int64_t)h->slot_bytes;
+    if (h->F == 1) {
+      memcpy(dst, obs_host, h->slot_bytes);
+    } else {   // the newest frame of the stack: last-axis index F - 1
+      const uint8_t* src = (const uint8_t*)obs_host + (h->F - 1);
+      const int F = h->F, nb = h->slot_bytes;
+      for (int i = 0; i < nb; ++i) dst[i] = src[(size_t)i * F];
+    }
     h->n_obs++;
   }
   if (h->slot_head > (uint64_t)h->S) {
@@ -586,9 +706,12 @@ static int make_item(b200rl_replay* h, Writer& w, int32_t num_timesteps, double 
   B200RL_REQUIRE(num_timesteps >= 1 && (int64_t)w.hist.size() >= (int64_t)num_timesteps + 1,
                  "create_item(%d): only %d steps appended in this episode", num_timesteps,
                  (int)w.hist.size() - 1);
-  uint64_t start_seq = w.hist[w.hist.size() - 1 - num_timesteps];
+  const int64_t i_end = (int64_t)w.hist.size() - 1, i_start = i_end - num_timesteps;
+  uint64_t start_seq = w.hist[i_start];
   uint64_t end_seq = w.hist.back();
-  B200RL_REQUIRE(h->slot_head <= (uint64_t)h->S || start_seq >= h->slot_head - (uint64_t)h->S,
+  // with frame deduplication the item also needs the F-1 slots before its first observation
+  const uint64_t oldest_seq = w.hist[std::max<int64_t>(0, i_start - (h->F - 1))];
+  B200RL_REQUIRE(h->slot_head <= (uint64_t)h->S || oldest_seq >= h->slot_head - (uint64_t)h->S,
                  "item window was already overwritten in the slot ring (slot_capacity too small)");
   if (h->item_start_seq.empty()) h->item_start_seq.assign(h->M, 0);
   // never stage two records for one tree position (tiny tables): cap the window at M items
@@ -600,14 +723,19 @@ static int make_item(b200rl_replay* h, Writer& w, int32_t num_timesteps, double 
   if (h->item_head - h->item_tail > (uint64_t)h->M) h->item_tail++;  // Fifo remover: same tree position
   while (!h->start_min.empty() && h->start_min.front().first < h->item_tail) h->start_min.pop_front();
   int64_t pos = (int64_t)(key % (uint64_t)h->M);
-  h->item_start_seq[pos] = start_seq;
-  while (!h->start_min.empty() && h->start_min.back().second >= start_seq) h->start_min.pop_back();
-  h->start_min.emplace_back(key, start_seq);
+  h->item_start_seq[pos] = oldest_seq;
+  while (!h->start_min.empty() && h->start_min.back().second >= oldest_seq) h->start_min.pop_back();
+  h->start_min.emplace_back(key, oldest_seq);
   ItemRec& it = h->stage[h->cur].h_item[h->n_item++];
   it.pos = pos;
   it.start = (int32_t)(start_seq % (uint64_t)h->S);
   it.end = (int32_t)(end_seq % (uint64_t)h->S);
   it.len = num_timesteps;
+  for (int j = 0; j < kMaxFrameStack - 1; ++j) {
+    const int64_t a = i_start - 1 - j, b = i_end - 1 - j;
+    it.prev[0][j] = (j < h->F - 1 && a >= 0) ? (int32_t)(w.hist[a] % (uint64_t)h->S) : -1;
+    it.prev[1][j] = (j < h->F - 1 && b >= 0) ? (int32_t)(w.hist[b] % (uint64_t)h->S) : -1;
+  }
   float wt = (float)std::pow(priority, h->cfg.alpha);
   it.weight = (wt > 0.f && wt < 3.0e38f) ? wt : 0.f;
   h->state_dirty = true;
@@ -642,7 +770,7 @@ extern "C" int b200rl_writer_open(b200rl_replay* h, int32_t* writer_id) {
 
 static void push_hist(b200rl_replay* h, Writer& w, uint64_t seq) {
   w.hist.push_back(seq);
-  while ((int64_t)w.hist.size() > h->cfg.max_window + 1) w.hist.pop_front();
+  while ((int64_t)w.hist.size() > h->cfg.max_window + 1 + (h->F - 1)) w.hist.pop_front();
 }
 
 extern "C" int b200rl_writer_append(b200rl_replay* h, int32_t writer, const void* obs, const void* act,
@@ -708,6 +836,9 @@ extern "C" int b200rl_writer_append_stream(b200rl_replay* h, int32_t writer, int
   cudaStream_t stream = as_stream(stream_);
   cudaStream_t saved = g_implicit_stream;
   g_implicit_stream = stream;
+  // obs_on_device: 0 = host observations as the signature has them; 1 = device observations as the signature has them;
+  // 2 = device SINGLE FRAMES [n][obs_bytes / frame_stack] (frame-deduplicated tables: what the ring stores)
+  B200RL_REQUIRE(obs_on_device != 2 || h->F > 1, "obs_on_device = 2 (single frames) needs a frame-deduplicated table");
   const int32_t ob = h->cfg.obs_bytes;
   if (obs_on_device) {
     // pending host-staged observations must land first (slot order), then one or two D2D runs
@@ -716,12 +847,22 @@ extern "C" int b200rl_writer_append_stream(b200rl_replay* h, int32_t writer, int
     int64_t firsti = (int64_t)(h->slot_head % (uint64_t)h->S);
     int64_t run0 = std::min<int64_t>(n, h->S - firsti);
     RingView& r = h->ring;
-    if (run0 > 0)
-      B200RL_CUDA_OK(cudaMemcpy2DAsync(r.obs + firsti * r.obs_stride, r.obs_stride, obs, ob, ob, run0,
-                                       cudaMemcpyDeviceToDevice, stream));
-    if (run0 < n)
-      B200RL_CUDA_OK(cudaMemcpy2DAsync(r.obs, r.obs_stride, (const uint8_t*)obs + run0 * (int64_t)ob, ob, ob,
-                                       n - run0, cudaMemcpyDeviceToDevice, stream));
+    if (h->F > 1 && obs_on_device == 1) {
+      if (n > 0) {
+        const long long total = n * (long long)h->slot_bytes;
+        extract_newest_frame_kernel<<<(int)std::min<long long>(ceil_div<long long>(total, 256), kNumSMs * 16), 256, 0, stream>>>(
+            (const uint8_t*)obs, r.obs, firsti, h->S, r.obs_stride, h->slot_bytes, h->F, n);
+        B200RL_LAUNCH_OK();
+      }
+    } else {
+      const int32_t sb = h->slot_bytes;
+      if (run0 > 0)
+        B200RL_CUDA_OK(cudaMemcpy2DAsync(r.obs + firsti * r.obs_stride, r.obs_stride, obs, sb, sb, run0,
+                                         cudaMemcpyDeviceToDevice, stream));
+      if (run0 < n)
+        B200RL_CUDA_OK(cudaMemcpy2DAsync(r.obs, r.obs_stride, (const uint8_t*)obs + run0 * (int64_t)sb, sb, sb,
+                                         n - run0, cudaMemcpyDeviceToDevice, stream));
+    }
   }
   const uint8_t* acts = (const uint8_t*)act;
   for (int64_t i = 0; i < n && rc == 0; ++i) {
@@ -794,7 +935,7 @@ extern "C" int b200rl_replay_reset(b200rl_replay* h, void* stream_) {
 // The reference never checkpoints replay contents (acme/tf/savers.py:76-167 saves learner state only); a resumed
 // run there starts from an empty table.  Here the whole shard can be saved: its device arrays are exposed one by one
 // (the host side copies them with any D2H mechanism) and the host bookkeeping is serialised into one blob.
-enum { SEG_OBS = 0, SEG_ACT, SEG_REW, SEG_DISC, SEG_NEXT, SEG_ITEM_START, SEG_ITEM_END, SEG_ITEM_LEN, SEG_TREE, SEG_STATE, SEG_COUNT };
+enum { SEG_OBS = 0, SEG_ACT, SEG_REW, SEG_DISC, SEG_NEXT, SEG_ITEM_START, SEG_ITEM_END, SEG_ITEM_LEN, SEG_TREE, SEG_STATE, SEG_ITEM_PREV, SEG_COUNT };
 
 extern "C" int b200rl_replay_segment(b200rl_replay* h, int32_t which, void** dev_ptr, int64_t* bytes) {
   B200RL_REQUIRE(h && dev_ptr && bytes, "null argument");
@@ -814,6 +955,7 @@ extern "C" int b200rl_replay_segment(b200rl_replay* h, int32_t which, void** dev
     case SEG_ITEM_LEN: p = r.item_len; n = payload ? h->M * 4 : 0; break;
     case SEG_TREE: p = h->d_tree; n = h->tree_floats * 4; break;
     case SEG_STATE: p = h->d_state; n = sizeof(ReplayState); break;
+    case SEG_ITEM_PREV: p = r.item_prev; n = h->F > 1 ? h->M * 2 * (h->F - 1) * 4 : 0; break;
     default: set_error("unknown replay segment %d (0..%d)", which, SEG_COUNT - 1); return B200RL_EINVAL;
   }
   *dev_ptr = p;
@@ -940,6 +1082,15 @@ extern "C" int b200rl_replay_gather(b200rl_replay* h, int32_t B, const int64_t* 
   B200RL_REQUIRE(B >= 1, "batch must be >= 1");
   int rc = ensure_device(h);
   if (rc) return rc;
+  if (h->F > 1) {
+    B200RL_REQUIRE(h->F == 4 && h->cfg.obs_bytes % 16 == 0 && (((uintptr_t)o_tm1 | (uintptr_t)o_t) % 16 == 0),
+                   "frame-deduplicated gather is implemented for stacks of 4 uint8 frames with 16-byte aligned rows");
+    const int zsplit = std::max(1, std::min(4, (h->cfg.obs_bytes >> 4) / 256));
+    gather_frames4_kernel<false><<<dim3(B, 2, zsplit), 256, 0, as_stream(stream)>>>(
+        h->ring, (const long long*)idx_dev, (uint8_t*)o_tm1, (uint8_t*)a_tm1, R, D, (uint8_t*)o_t, nullptr, nullptr, 1, 0, 0, 0, 0);
+    B200RL_LAUNCH_OK();
+    return B200RL_OK;
+  }
   dim3 grid(B, 2);
   const bool a16 = (h->cfg.obs_bytes % 16 == 0) && (((uintptr_t)o_tm1 | (uintptr_t)o_t) % 16 == 0);
   const bool a4 = (h->cfg.obs_bytes % 4 == 0) && (((uintptr_t)o_tm1 | (uintptr_t)o_t) % 4 == 0);
@@ -968,6 +1119,14 @@ extern "C" int b200rl_replay_gather_rows(b200rl_replay* h, int32_t B, const int6
   int rc = ensure_device(h);
   if (rc) return rc;
   const int zsplit = std::max(1, std::min(4, (h->cfg.obs_bytes >> 4) / 256));
+  if (h->F > 1) {
+    B200RL_REQUIRE(h->F == 4, "frame-deduplicated gather is implemented for stacks of 4 frames");
+    gather_frames4_kernel<true><<<dim3(B, 2, zsplit), 256, 0, as_stream(stream)>>>(
+        h->ring, (const long long*)idx_dev, (uint8_t*)o_tm1, (uint8_t*)a_tm1, R, D, (uint8_t*)o_t, (uint4*)rows_tm1, (uint4*)rows_t,
+        g->W / 4, g->pad_left, g->pad_top, Hp, row_elems / 8);
+    B200RL_LAUNCH_OK();
+    return B200RL_OK;
+  }
   gather_rows_kernel<<<dim3(B, 2, zsplit), 256, 0, as_stream(stream)>>>(h->ring, (const long long*)idx_dev, (uint8_t*)o_tm1, (uint8_t*)a_tm1, R, D,
                                                                (uint8_t*)o_t, (uint4*)rows_tm1, (uint4*)rows_t, g->W / 4, g->pad_left,
                                                                g->pad_top, Hp, row_elems / 8);

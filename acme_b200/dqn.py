@@ -819,13 +819,15 @@ class DQN(agent.Agent):
                importance_sampling_exponent: float = 0.2, priority_exponent: float = 0.6, n_step: int = 5,
                epsilon: Optional[float] = None, learning_rate: float = 1e-3, discount: float = 0.99,
                logger: loggers.Logger = None, checkpoint: bool = False, checkpoint_subpath: str = '~/acme/',
-               seed: int = 0, use_cuda_graph: bool = True, slot_capacity: Optional[int] = None):
+               seed: int = 0, use_cuda_graph: bool = True, slot_capacity: Optional[int] = None, frame_stack: int = 0):
+    """frame_stack: see `replay.Table` -- store one frame per step when the observations are AtariWrapper frame stacks."""
     table = replay.Table(
         name=replay.DEFAULT_PRIORITY_TABLE, sampler=replay.selectors.Prioritized(priority_exponent),
         remover=replay.selectors.Fifo(), max_size=max_replay_size,
         rate_limiter=replay.rate_limiters.MinSize(1),
         signature=adders.NStepTransitionAdder.signature(environment_spec),
-        max_window=max(n_step, 1), discount=discount, device=network.device, slot_capacity=slot_capacity)
+        max_window=max(n_step, 1), discount=discount, device=network.device, slot_capacity=slot_capacity,
+        frame_stack=frame_stack)
     self._server = replay.Server([table], port=None)
     address = f'localhost:{self._server.port}'
     adder = adders.NStepTransitionAdder(client=replay.Client(address), n_step=n_step, discount=discount)

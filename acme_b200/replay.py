@@ -121,7 +121,13 @@ class Table:
 
   def __init__(self, name: str, sampler, remover, max_size: int, rate_limiter, signature=None,
                slot_capacity: Optional[int] = None, max_window: int = 8, discount: float = 0.99,
-               device: int = 0, shard_count: int = 1, shard_rank: int = 0, stage_slots: int = 0):
+               device: int = 0, shard_count: int = 1, shard_rank: int = 0, stage_slots: int = 0, frame_stack: int = 0):
+    """frame_stack = F > 1: the observation is a uint8 stack of F frames on its LAST axis, as
+    `FrameStacker` / `AtariWrapper` produce it (`acme/wrappers/frame_stacking.py:64-88`, `atari_wrapper.py:277-308`: the
+    newest frame last, blank frames before the episode's first observation).  The HBM ring then stores ONE frame per
+    step and K3 rebuilds the stacks when it gathers: obs_bytes / F bytes per step (7,056 instead of 28,224 for Atari)
+    and F times less host-to-device traffic per insert.  The caller's observations must really be such stacks: the
+    older F-1 frames of every observation are taken from the previous observations of the same episode."""
     if not isinstance(remover, selectors.Fifo):
       raise NotImplementedError('only the Fifo remover is implemented (the one the hot path uses)')
     self.name = name
@@ -134,9 +140,10 @@ class Table:
     self.device = device
     self.shard_count, self.shard_rank = shard_count, shard_rank
     self.stage_slots = stage_slots
+    self.frame_stack = int(frame_stack) if frame_stack and frame_stack > 1 else 0
     # one slot per observation; an episode of T steps uses T+1 slots and yields >= T items, so
     # 2*max_size (+window) slots can never evict a live item before the Fifo remover does.
-    self.slot_capacity = int(slot_capacity) if slot_capacity else 2 * self.max_size + self.max_window + 2
+    self.slot_capacity = int(slot_capacity) if slot_capacity else 2 * self.max_size + self.max_window + 2 + self.frame_stack
     self._handle = None
     self._lock = threading.Lock()
     if signature is not None:
@@ -162,6 +169,11 @@ class Table:
     self.act_packer = _Packer((sig[1], extras_spec) if extras_spec != () else sig[1])
     self.has_extras = extras_spec != ()
     self.signature = sig
+    if self.frame_stack:
+      leaves = tree.flatten(sig[0])
+      if len(leaves) != 1 or np.dtype(leaves[0].dtype) != np.uint8 or tuple(leaves[0].shape)[-1:] != (self.frame_stack,):
+        raise ValueError(f'frame_stack={self.frame_stack} needs a single uint8 observation whose last axis is the frame stack; '
+                         f'got {sig[0]}')
 
   def _ensure(self):
     if self._handle is not None:
@@ -173,7 +185,8 @@ class Table:
                           obs_bytes=self.obs_packer.nbytes, act_bytes=self.act_packer.nbytes,
                           max_window=self.max_window, shard_count=self.shard_count,
                           shard_rank=self.shard_rank, device=self.device,
-                          stage_slots=self.stage_slots, gamma=float(self.discount), alpha=self.alpha)
+                          stage_slots=self.stage_slots, frame_stack=self.frame_stack, gamma=float(self.discount),
+                          alpha=self.alpha)
     h = C.c_void_p()
     _capi.call('b200rl_replay_create', C.byref(h), C.byref(cfg))
     self._handle = h
@@ -274,7 +287,7 @@ class Table:
   # -- core.Saveable: the whole shard.  The reference's checkpointers save learner state only
   # (`acme/tf/savers.py:76-167`); a table restored here continues exactly where the saved one stopped: same keys, same
   # FIFO position, same priorities, open writers keep their episode windows.
-  _SEGMENTS = ('obs', 'act', 'rew', 'disc', 'next', 'item_start', 'item_end', 'item_len', 'tree', 'key_range')
+  _SEGMENTS = ('obs', 'act', 'rew', 'disc', 'next', 'item_start', 'item_end', 'item_len', 'tree', 'key_range', 'item_prev')
 
   def _segment(self, which: int):
     import torch
@@ -301,13 +314,14 @@ class Table:
         segs[name] = t.cpu().numpy()
     return dict(host=blob[:size.value].copy(), segments=segs,
                 geometry=dict(max_size=self.max_size, slot_capacity=self.slot_capacity, alpha=self.alpha,
-                              obs_bytes=self.obs_packer.nbytes, act_bytes=self.act_packer.nbytes))
+                              obs_bytes=self.obs_packer.nbytes, act_bytes=self.act_packer.nbytes,
+                              frame_stack=self.frame_stack))
 
   def restore(self, state):
     import torch
     geo = state['geometry']
-    if (geo['max_size'], geo['slot_capacity'], geo['obs_bytes'], geo['act_bytes']) != (
-        self.max_size, self.slot_capacity, self.obs_packer.nbytes, self.act_packer.nbytes):
+    if (geo['max_size'], geo['slot_capacity'], geo['obs_bytes'], geo['act_bytes'], geo.get('frame_stack', 0)) != (
+        self.max_size, self.slot_capacity, self.obs_packer.nbytes, self.act_packer.nbytes, self.frame_stack):
       raise ValueError(f'table geometry differs from the saved one: {geo}')
     blob = np.ascontiguousarray(state['host'], np.uint8)
     _capi.call('b200rl_replay_set_host_state', self.handle, blob.ctypes.data, blob.size)

@@ -75,7 +75,7 @@ class SynthStream:
     return act, rew, disc, first, last
 
 
-def fill_replay(table, steps, n_step, seed, chunk=32768):
+def fill_replay(table, steps, n_step, seed, chunk=32768, single_frames=False):
   """Fills the HBM ring with `steps` synthetic timesteps (observations generated on the device:
   setup only, not timed) and then sets priorities to |N(0,1)| like SURVEY §8d."""
   import ctypes as C
@@ -90,8 +90,10 @@ def fill_replay(table, steps, n_step, seed, chunk=32768):
   while done < steps:
     n = min(chunk, steps - done)
     act, rew, disc, first, last = stream.chunk(n)
-    obs = torch.randint(0, 256, (n,) + OBS_SHAPE, dtype=torch.uint8, device='cuda', generator=gen)
-    _capi.call('b200rl_writer_append_stream', table.handle, wid.value, n, obs.data_ptr(), 1, act.ctypes.data,
+    # frame-deduplicated table: the ring stores one 84x84 frame per step; feed it single frames (obs_on_device = 2)
+    shape = (n, OBS_SHAPE[0] * OBS_SHAPE[1]) if single_frames else (n,) + OBS_SHAPE
+    obs = torch.randint(0, 256, shape, dtype=torch.uint8, device='cuda', generator=gen)
+    _capi.call('b200rl_writer_append_stream', table.handle, wid.value, n, obs.data_ptr(), 2 if single_frames else 1, act.ctypes.data,
                rew.ctypes.data, disc.ctypes.data, first.ctypes.data, last.ctypes.data, n_step, 1.0,
                _capi.current_stream())
     torch.cuda.synchronize()
@@ -388,10 +390,11 @@ def run_ours(args):
   table = replay.Table(replay.DEFAULT_PRIORITY_TABLE, replay.selectors.Prioritized(0.6), replay.selectors.Fifo(),
                        max_size=items, rate_limiter=replay.rate_limiters.MinSize(1),
                        signature=adders.NStepTransitionAdder.signature(spec), max_window=n_step, discount=0.99,
-                       device=local, slot_capacity=items + 4096, shard_count=world, shard_rank=rank, stage_slots=4096)
+                       device=local, slot_capacity=items + 4096, shard_count=world, shard_rank=rank, stage_slots=4096,
+                       frame_stack=4 if args.frame_dedup else 0)
   server = replay.Server([table])
   t_setup = time.time()
-  info = fill_replay(table, items, n_step, seed=1234 + rank)
+  info = fill_replay(table, items, n_step, seed=1234 + rank, single_frames=args.frame_dedup)
   net = networks.DQNAtariNetwork(NUM_ACTIONS, device=local, precision=precision, seed=1234)   # replicated init
   tgt = net.clone()
   ds = replay.ReplayDataset(table, B, seed=1234 + rank)
@@ -476,7 +479,8 @@ def run_ours(args):
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     e2e_s = float(tt)
   e2e_value = world * e2e_steps / e2e_s
-  h2d = inserts_per_step * (int(np.prod(OBS_SHAPE)) + 4 + 4 + 4 + 4) + inserts_per_step * 24 + 16
+  obs_h2d = int(np.prod(OBS_SHAPE)) // (4 if args.frame_dedup else 1)       # a frame-deduplicated table uploads one frame per step
+  h2d = inserts_per_step * (obs_h2d + 4 + 4 + 4 + 4) + inserts_per_step * 24 + 16
   d2h = 4
 
   # ---- per-stage device times (eager launches, CUDA events) and the roofline of the dominant kernel
@@ -563,6 +567,9 @@ def run_ours(args):
         'config': {'workload': 'DQN Atari-shaped 84x84x4 uint8, PER 1M items, batch 256, n=3 (BASELINE configs[1])',
                    'items_per_rank': info['size'], 'batch_per_rank': B, 'n_step': n_step, 'alpha': 0.6, 'beta': 0.2,
                    'network': 'DQNAtariNetwork(18), 8,018,611 params', 'optimizer': 'Adam 1e-3',
+                   'replay_ring': ('frame-deduplicated: one 84x84 uint8 frame per step, stacks rebuilt by K3 '
+                                   f'({(items + 4096) * 7056 / 1e9:.1f} GB)') if args.frame_dedup else
+                                  f'one 84x84x4 uint8 stack per step ({(items + 4096) * 28224 / 1e9:.1f} GB)',
                    'parallelism': (f'dp{world}: per-rank replay shard; gradient mean + Adam + parameter broadcast fused over '
                                    'NVLink peer memory (NCCL for set-up only)') if world > 1 else 'single GPU',
                    'cuda_graph': not args.no_graph,
@@ -902,6 +909,8 @@ def main():
                   help='dqn (default): BASELINE configs[1], the headline metric; d4pg: configs[2]; sumtree: a point of the configs[3] sweep')
   ap.add_argument('--items', type=int, default=None, help='items per rank (default 1M; sumtree: 100M)')
   ap.add_argument('--tree-batch', type=int, default=1 << 20, help='sumtree: draws (and updates) per rank per step')
+  ap.add_argument('--frame-dedup', action='store_true',
+                  help='dqn: store one frame per step in the HBM ring and rebuild the 4-stacks at gather time (SURVEY 8f-1)')
   ap.add_argument('--no-graph', action='store_true')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--profile', action='store_true', help='only warm-up + timed steps (for ncu captures)')

@@ -57,7 +57,10 @@ typedef struct b200rl_replay_cfg {
   int32_t shard_rank;
   int32_t device;
   int32_t stage_slots;   /* pinned-host staging capacity in slots (0 = default)             */
-  int32_t reserved;
+  int32_t frame_stack;   /* F > 1: observations are stacks of F single-byte-element frames on their LAST axis
+                            (acme/wrappers/frame_stacking.py:64-88, atari_wrapper.py:277-308) and the ring stores one
+                            frame per slot, rebuilding stacks (zero frames before the episode start) at gather time:
+                            obs_bytes / F bytes of HBM per step instead of obs_bytes.  0 / 1 = off                  */
   float gamma;           /* agent discount, np.float32(discount): transition.py:111         */
   float reserved_f;
   double alpha;          /* priority exponent: stored weight = priority^alpha               */
@@ -136,7 +139,7 @@ int b200rl_replay_gather_rows(b200rl_replay* h, int32_t B, const int64_t* idx_de
  * replay contents).  host_state serialises the host bookkeeping (key counters, FIFO bounds, every open writer's episode
  * window) after flushing staged steps; blob == NULL only reports the size.  segment(which) exposes the device arrays to
  * copy out / in: 0 obs slots, 1 actions, 2 rewards, 3 discounts, 4 next links, 5-7 item start / end / length, 8 sum
- * tree (values + prefix lines), 9 live key range.  Restore = set_host_state + writing every segment back, on a handle
+ * tree (values + prefix lines), 9 live key range, 10 older-frame slots of every item (frame-deduplicated tables).  Restore = set_host_state + writing every segment back, on a handle
  * created with the same geometry. */
 int b200rl_replay_host_state(b200rl_replay* h, void* blob, int64_t capacity, int64_t* size, void* stream);
 int b200rl_replay_set_host_state(b200rl_replay* h, const void* blob, int64_t size);

@@ -147,3 +147,23 @@ class Table:
     w = sumtree.weight_from_priority(priorities, self.alpha)
     live = (keys >= self.item_tail) & (keys < self.item_head)
     self.tree.set_leaves(keys[live] % self.M, w[live])
+
+
+class FrameStacker:
+  """`acme/wrappers/frame_stacking.py:64-88` restated: the last `num_frames` frames stacked on a new LAST axis, newest
+  last, blank (zero) frames before the first frame after `reset()`.  Used by the tests to produce the observation stream
+  whose stacks the frame-deduplicated ring must rebuild bit for bit."""
+
+  def __init__(self, num_frames: int):
+    self.num_frames = num_frames
+    self.reset()
+
+  def reset(self):
+    self._stack = []
+
+  def step(self, frame):
+    frame = np.asarray(frame)
+    if not self._stack:
+      self._stack = [np.zeros_like(frame)] * (self.num_frames - 1)
+    self._stack = (self._stack + [frame])[-self.num_frames:]
+    return np.stack(self._stack, axis=-1)

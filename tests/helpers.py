@@ -8,7 +8,7 @@ from oracle import replay as oreplay
 
 
 def make_pair(obs_shape=(8, 8, 4), obs_dtype=np.uint8, num_actions=4, n_step=3, discount=0.99, alpha=0.6,
-              max_size=500, slot_capacity=None, stage_slots=0, act_dim=None):
+              max_size=500, slot_capacity=None, stage_slots=0, act_dim=None, frame_stack=0):
   """num_actions discrete actions, or (act_dim given) a float32 action vector in [-1, 1]."""
   aspec = (specs.DiscreteArray(num_actions) if act_dim is None else
            specs.BoundedArray((act_dim,), np.float32, -1., 1.))
@@ -17,7 +17,7 @@ def make_pair(obs_shape=(8, 8, 4), obs_dtype=np.uint8, num_actions=4, n_step=3, 
   table = replay.Table(replay.DEFAULT_PRIORITY_TABLE, replay.selectors.Prioritized(alpha), replay.selectors.Fifo(),
                        max_size=max_size, rate_limiter=replay.rate_limiters.MinSize(1),
                        signature=adders.NStepTransitionAdder.signature(spec), max_window=n_step,
-                       discount=discount, slot_capacity=slot_capacity, stage_slots=stage_slots)
+                       discount=discount, slot_capacity=slot_capacity, stage_slots=stage_slots, frame_stack=frame_stack)
   server = replay.Server([table])
   adder = adders.NStepTransitionAdder(replay.Client(server), n_step=n_step, discount=discount)
   oracle = oreplay.Table(max_size, table.slot_capacity, obs_shape, obs_dtype, () if act_dim is None else (act_dim,),
@@ -44,6 +44,30 @@ def feed_episode(rng, adder, oracle, T, n_step, obs_shape, obs_dtype, num_action
     o2 = random_obs(rng, obs_shape, obs_dtype)
     ts = dm_env.TimeStep(dm_env.StepType.LAST if last else dm_env.StepType.MID, r, d, o2)
     adder.add(a, ts)
+    oracle.append(w, o, a, r, d, o2)
+    oracle.create_item(w, min(k, n_step), 1.0)
+    if last:
+      m = min(n_step, T)
+      for j in range(1, m):
+        oracle.create_item(w, m - j, 1.0)
+      oracle.close(w)
+    o = o2
+
+
+def feed_stacked_episode(rng, adder, oracle, T, n_step, frame_shape, num_frames, num_actions, terminal=True):
+  """One episode whose observations are FrameStacker stacks (oracle.replay.FrameStacker <- frame_stacking.py:64-88) of
+  random uint8 frames: what AtariWrapper hands to the adder.  The oracle table stores the stacks whole."""
+  stacker = oreplay.FrameStacker(num_frames)
+  o = stacker.step(rng.integers(0, 256, frame_shape, dtype=np.uint8))
+  adder.add_first(dm_env.restart(o))
+  w = oracle.writer()
+  for k in range(1, T + 1):
+    a = np.int32(rng.integers(num_actions))
+    r = np.float32(rng.choice([-1., 0., 1., 0.5]))
+    last = k == T
+    d = np.float32(0. if (last and terminal) else 1.)
+    o2 = stacker.step(rng.integers(0, 256, frame_shape, dtype=np.uint8))
+    adder.add(a, dm_env.TimeStep(dm_env.StepType.LAST if last else dm_env.StepType.MID, r, d, o2))
     oracle.append(w, o, a, r, d, o2)
     oracle.create_item(w, min(k, n_step), 1.0)
     if last:

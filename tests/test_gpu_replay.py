@@ -354,3 +354,57 @@ def test_table_save_restore_resumes_exactly():
     assert torch.equal(a, b)
   assert torch.equal(d1.keys.view(torch.int64), d2.keys.view(torch.int64))
   s1.stop(); s2.stop()
+
+
+@pytest.mark.parametrize('hw,n_step,max_size', [(84, 3, 400), (20, 5, 150), (8, 1, 64)])
+def test_frame_dedup_ring_rebuilds_stacks(hw, n_step, max_size):
+  """a table with frame_stack=4 stores one frame per step; K3 must hand back exactly the stacks the
+  FrameStacker (frame_stacking.py:64-88) produced -- including the blank frames at episode starts, items whose two
+  observations straddle short episodes, and after the item FIFO has wrapped.  Checked against the oracle table, which
+  stores every stack whole, for both gather forms (plain, and with conv1's bf16 row image where the geometry has one)."""
+  import ctypes
+  torch = _torch()
+  import helpers
+  from acme_b200 import _capi, replay
+  rng = np.random.default_rng(hw + n_step)
+  shape, A = (hw, hw, 4), 4
+  spec, table, server, adder, oracle = helpers.make_pair(shape, np.uint8, A, n_step, 0.99, 0.6, max_size, frame_stack=4)
+  for ep in range(30):
+    helpers.feed_stacked_episode(rng, adder, oracle, int(rng.integers(1, 40)), n_step, (hw, hw), 4, A, terminal=ep % 3 != 0)
+  table.flush()
+  info = table.info()
+  assert (info['size'], info['head_key'], info['tail_key']) == (oracle.size, oracle.item_head, oracle.item_tail)
+  helpers.sync_oracle_leaves(table, oracle)
+  B = 128
+  ds = replay.ReplayDataset(table, B)
+  for trial in range(3):
+    u = rng.random(B, dtype=np.float32)
+    ds.sample_raw(torch.as_tensor(u).cuda())
+    torch.cuda.synchronize()
+    keys, pos, prob = oracle.sample(u, True)
+    np.testing.assert_array_equal(ds.idx.cpu().numpy(), pos)
+    o0, a, R, D, o1 = oracle.gather(pos)
+    s = ds.as_sample().data
+    np.testing.assert_array_equal(s[0].cpu().numpy(), o0)          # stacks rebuilt from single frames: bit-exact
+    np.testing.assert_array_equal(s[4].cpu().numpy(), o1)
+    np.testing.assert_array_equal(s[1].cpu().numpy(), a)
+    np.testing.assert_array_equal(s[2].cpu().numpy().view(np.uint32), R.view(np.uint32))
+    np.testing.assert_array_equal(s[3].cpu().numpy().view(np.uint32), D.view(np.uint32))
+  assert (o0[..., 0] == 0).all(axis=(1, 2)).any(), 'no episode-start stack in the sample: the blank-frame case was not exercised'
+  if hw in (84, 20):        # geometries with a conv1 row image: the fused form writes the same image as gather + conversion
+    from acme_b200 import networks
+    oh, pad = networks.tf_same_pad(hw, 8, 4)
+    g = lambda b: _capi.ConvGeom(B=b, H=hw, W=hw, C=4, kh=8, kw=8, stride=4, pad_top=pad, pad_left=pad, OH=oh, OW=oh, Cout=32)
+    fb = int(_capi.load().b200rl_conv2d_rows_bf16_bytes(ctypes.byref(g(1))))
+    rows = torch.zeros(2 * B * fb, dtype=torch.uint8, device='cuda')
+    both = ds.o_both.clone()
+    ds.o_both.zero_()
+    ds.gather_only((rows.data_ptr(), rows.data_ptr() + B * fb, g(1)))
+    want = torch.zeros(2 * B * fb, dtype=torch.uint8, device='cuda')
+    _capi.call('b200rl_conv2d_rows_bf16_from_u8', both.data_ptr(), g(2 * B), want.data_ptr(), want.numel(), _capi.current_stream())
+    torch.cuda.synchronize()
+    assert torch.equal(ds.o_both, both) and torch.equal(rows, want)
+  # the ring really is four times smaller
+  seg = table._segment(0)
+  assert seg.numel() == table.slot_capacity * (-(-(hw * hw) // 16) * 16)
+  server.stop()
