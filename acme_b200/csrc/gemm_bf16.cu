@@ -15,6 +15,7 @@
 // and a second one the convolutions' data gradient (one stride-1 sub-problem per stride phase, as in gemm_tma.cu).
 // Roles per CTA (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warps 2-5 = epilogue.
 #include <algorithm>
+#include <cstdlib>
 
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -233,6 +234,183 @@ hgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   if (warp == 1) tmem_dealloc(tmem_d, TMEM_COLS);
 }
 
+// ------------------------------------------------------------------------------ persistent variant (A K-major)
+// Same tiles, but a CTA walks a static list of them (tile t = blockIdx.x + i * gridDim.x) with TWO accumulators in TMEM:
+// the epilogue of tile i (TMEM -> shared-memory slab -> global) overlaps the loads and MMAs of tile i + 1, and barrier
+// set-up, TMEM allocation and tensor-map fetch are paid once per CTA instead of once per tile.  For problems of hundreds
+// of small tiles (conv1: 1764 tiles of 8 k-blocks; a conv data gradient: 882 tiles of 4) those fixed costs dominate.
+// RESB (convolutions: the whole weight matrix is K * BN * 2 <= 72 KB): B is loaded ONCE per CTA and stays in shared
+// memory; the ring then carries A only, which cuts the L2 -> shared-memory fill -- the bound of these kernels -- by
+// the B share (20-33%).
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int KE, int BM, int BN, int STAGES, bool RESB>
+__global__ void __launch_bounds__(H_THREADS)
+hgemm_pers_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, Epilogue epi, int M, int N,
+                  int K, int kblocks_per_split, int splits, ConvA conv) {
+  constexpr int A_BYTES = HBM_ROWS * KE * 2, B_BYTES = BN * KE * 2, STAGE = RESB ? A_BYTES : A_BYTES + B_BYTES;
+  constexpr int B_WB = BM == 1 ? 64 : 32, B_BOX = B_WB * KE * 2, B_NBOX = BN / B_WB;
+  constexpr int SLAB = HBM_ROWS * BN * 4;
+  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // [ring stages][epilogue slab][resident B]
+  uint8_t* const smem_al = smem_raw + (base - smem_u32(smem_raw));
+  __shared__ __align__(8) uint64_t bar_full[STAGES], bar_empty[STAGES], acc_full[2], acc_empty[2], bar_b;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tiles_m = (M + HBM_ROWS - 1) / HBM_ROWS, tiles_n = (N + BN - 1) / BN, tiles_mn = tiles_m * tiles_n;
+  const int total = tiles_mn * splits;
+  const int total_kblocks = (K + KE - 1) / KE;
+  const uint32_t res_b = base + STAGES * STAGE + SLAB;                 // resident B: total_kblocks tiles of B_BYTES
+
+  if (tid == 0) {
+    prefetch_tensormap(&map_a);
+    prefetch_tensormap(&map_b);
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+#pragma unroll
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+    mbar_init(&bar_b, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_smem;
+
+  if (warp == 0 && lane == 0) {
+    // ---------------- TMA producer
+    if (RESB) {   // the whole weight matrix, once (conv: splits == 1, tiles_n == 1)
+      mbar_expect_tx(&bar_b, (uint32_t)(total_kblocks * B_BYTES));
+      for (int kb = 0; kb < total_kblocks; ++kb) tma_load_2d(res_b + kb * B_BYTES, &map_b, kb * KE, 0, &bar_b);
+    }
+    int it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      const int split = t / tiles_mn, mn = t - split * tiles_mn, m_t = mn / tiles_n, n_t = mn - m_t * tiles_n;
+      const int row0 = m_t * HBM_ROWS, col0 = n_t * BN;
+      const int kb_begin = split * kblocks_per_split;
+      const int nkb = min(total_kblocks, kb_begin + kblocks_per_split) - kb_begin;
+      int ax = 0, ay = 0, an = 0, f_c0 = 0, f_tx = 0, f_ty = 0;
+      if (conv.enabled) {
+        const int ox = row0 % conv.OW, q = row0 / conv.OW;
+        ax = ox * conv.stride_w - conv.pad_left;
+        ay = (q % conv.OH) * conv.stride_h - conv.pad_top;
+        an = q / conv.OH;
+        const int cb = conv.C / KE, tap = kb_begin / cb;
+        f_c0 = (kb_begin % cb) * KE; f_tx = tap % conv.kw; f_ty = tap / conv.kw;
+      }
+      for (int i = 0; i < nkb; ++i, ++it) {
+        const int s = it % STAGES;
+        if (it >= STAGES) mbar_wait(&bar_empty[s], ((it / STAGES) - 1) & 1);
+        const uint32_t sa = base + s * STAGE, sb = sa + A_BYTES;
+        const int k0 = (kb_begin + i) * KE;
+        mbar_expect_tx(&bar_full[s], STAGE);
+        if (conv.enabled) {
+          tma_load_im2col(sa, &map_a, f_c0, ax, ay, an, (uint16_t)f_tx, (uint16_t)f_ty, &bar_full[s]);
+          f_c0 += KE;
+          if (f_c0 == conv.C) {
+            f_c0 = 0;
+            if (++f_tx == conv.kw) { f_tx = 0; ++f_ty; }
+          }
+        } else {
+          tma_load_2d(sa, &map_a, k0, row0, &bar_full[s]);
+        }
+        if (!RESB) {
+          if (BM != 0) {
+#pragma unroll
+            for (int j = 0; j < B_NBOX; ++j) tma_load_2d(sb + j * B_BOX, &map_b, col0 + B_WB * j, k0, &bar_full[s]);
+          } else {
+            tma_load_2d(sb, &map_b, k0, col0, &bar_full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---------------- MMA issuer
+    constexpr uint32_t idesc = idesc_bf16(HBM_ROWS, BN, false, BM != 0);
+    if (RESB) { mbar_wait(&bar_b, 0); tc_fence_after(); }
+    int it = 0, ti = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
+      const int split = t / tiles_mn;
+      const int kb_begin = split * kblocks_per_split;
+      const int nkb = min(total_kblocks, kb_begin + kblocks_per_split) - kb_begin;
+      const int ab = ti & 1;
+      mbar_wait(&acc_empty[ab], ((ti >> 1) & 1) ^ 1);     // the epilogue has drained this accumulator (first use: free)
+      tc_fence_after();
+      const uint32_t acc = tmem_d + (uint32_t)(ab * BN);
+      for (int i = 0; i < nkb; ++i, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&bar_full[s], (it / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t sa = base + s * STAGE;
+        const uint32_t sb = RESB ? res_b + (kb_begin + i) * B_BYTES : sa + A_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < KE / 16; ++kk)
+          umma_bf16(acc, operand_desc<0, KE>(sa, kk), operand_desc<BM, KE>(sb, kk), idesc, (i > 0 || kk > 0) ? 1u : 0u);
+        umma_commit(&bar_empty[s]);
+      }
+      umma_commit(&acc_full[ab]);
+    }
+  } else if (warp >= 2) {
+    // ---------------- epilogue: warp w reads TMEM lanes 32 * (w % 4) ..; private slab per warp
+    const int lane_base = (warp & 3) * 32;
+    float* slab = reinterpret_cast<float*>(smem_al + STAGES * STAGE) + (warp & 3) * 32 * BN;
+    int ti = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
+      const int split = t / tiles_mn, mn = t - split * tiles_mn, m_t = mn / tiles_n, n_t = mn - m_t * tiles_n;
+      const int row0 = m_t * HBM_ROWS, col0 = n_t * BN;
+      const int ab = ti & 1;
+      mbar_wait(&acc_full[ab], (ti >> 1) & 1);
+      tc_fence_after();
+      Epilogue e = epi;
+      if (e.partial) e.partial += (size_t)split * M * N;       // the helpers add blockIdx.z (= 0 here)
+      stage_accumulator<BN>(tmem_d + ((uint32_t)lane_base << 16) + (uint32_t)(ab * BN), slab, lane, true);
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(&acc_empty[ab]);              // TMEM reads done: the MMA warp may overwrite this accumulator
+      const int first = row0 + lane_base;
+      store_staged_rows<BN>(e, slab, lane, col0, N, M, [&](int r) -> long long { return first + r < M ? first + r : -1; });
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_d, TMEM_COLS);
+}
+
+int g_h_persistent = -1;   // -1 = read B200RL_PERSISTENT once (default on), else 0 / 1
+
+static bool use_persistent() {
+  if (g_h_persistent < 0) {
+    const char* e = getenv("B200RL_PERSISTENT");
+    g_h_persistent = e ? atoi(e) : 1;
+  }
+  return g_h_persistent != 0;
+}
+
+template <int KE, int BM, int BN, bool RESB>
+static int launch_h_pers(const CUtensorMap& ma, const CUtensorMap& mb, Epilogue epi, int M, int N, int K, int kps, int splits,
+                         int res_b_bytes, cudaStream_t stream, const ConvA& conv) {
+  constexpr int STAGE = RESB ? HBM_ROWS * KE * 2 : HBM_ROWS * KE * 2 + BN * KE * 2;
+  constexpr int STAGES = STAGE >= 24 * 1024 ? 3 : 4;
+  const int smem = STAGES * STAGE + HBM_ROWS * BN * 4 + (RESB ? res_b_bytes : 0) + 1024;
+  const int total = ceil_div(M, HBM_ROWS) * ceil_div(N, BN) * splits;
+  int occ = std::min(std::min(4, (227 * 1024) / (smem + 1024)), 512 / (2 * BN < 32 ? 32 : 2 * BN));
+  occ = std::max(occ, 1);
+  const int grid = std::min(total, kNumSMs * occ);
+  static int attr = 0;
+  if (attr < smem) {
+    B200RL_CUDA_OK(cudaFuncSetAttribute(hgemm_pers_kernel<KE, BM, BN, STAGES, RESB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = smem;
+  }
+  hgemm_pers_kernel<KE, BM, BN, STAGES, RESB><<<grid, H_THREADS, smem, stream>>>(ma, mb, epi, M, N, K, kps, splits, conv);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+
 template <int KE, int AM, int BM, int BN>
 static int launch_h(const CUtensorMap& ma, const CUtensorMap& mb, Epilogue epi, int M, int N, int K, void* ws, int64_t ws_bytes,
                     cudaStream_t stream, const ConvA& conv, bool allow_split = true) {
@@ -250,6 +428,18 @@ static int launch_h(const CUtensorMap& ma, const CUtensorMap& mb, Epilogue epi, 
   const int kps = ceil_div(kblocks, splits);
   splits = ceil_div(kblocks, kps);
   epi.partial = splits > 1 ? (float*)ws : nullptr;
+  if (AM == 0 && use_persistent() && !epi.transpose_out && tiles * splits >= 3 * kNumSMs / 2) {
+    // many small tiles: walk them with persistent CTAs; convolution weights (<= 80 KB) stay resident in shared memory
+    const int res_b = ceil_div(K, KE) * BN * KE * 2;
+    int rc;
+    if (BM == 0 && conv.enabled && splits == 1 && ceil_div(N, BN) == 1 && res_b <= 80 * 1024)
+      rc = launch_h_pers<KE, BM, BN, true>(ma, mb, epi, M, N, K, kps, splits, res_b, stream, conv);
+    else
+      rc = launch_h_pers<KE, BM, BN, false>(ma, mb, epi, M, N, K, kps, splits, 0, stream, conv);
+    if (rc) return rc;
+    if (splits > 1) return launch_splitk_finish(epi, M, N, splits, stream);
+    return B200RL_OK;
+  }
   dim3 grid(ceil_div(N, BN), ceil_div(M, HBM_ROWS), splits);
   constexpr int smem = STAGES * STAGE + 1024;
   static bool attr = false;
@@ -639,3 +829,5 @@ int h_f32_to_bf16(int64_t n, const float* src, bf16* dst, cudaStream_t s) {
 }
 
 }  // namespace b200rl
+
+extern "C" int b200rl_debug_set_persistent(int on) { b200rl::g_h_persistent = on; return 0; }
