@@ -391,16 +391,9 @@ static bool use_persistent() {
   return g_h_persistent != 0;
 }
 
-template <int KE, int BM, int BN, bool RESB>
-static int launch_h_pers(const CUtensorMap& ma, const CUtensorMap& mb, Epilogue epi, int M, int N, int K, int kps, int splits,
-                         int res_b_bytes, cudaStream_t stream, const ConvA& conv) {
-  constexpr int STAGE = RESB ? HBM_ROWS * KE * 2 : HBM_ROWS * KE * 2 + BN * KE * 2;
-  constexpr int STAGES = STAGE >= 24 * 1024 ? 3 : 4;
-  const int smem = STAGES * STAGE + HBM_ROWS * BN * 4 + (RESB ? res_b_bytes : 0) + 1024;
-  const int total = ceil_div(M, HBM_ROWS) * ceil_div(N, BN) * splits;
-  int occ = std::min(std::min(4, (227 * 1024) / (smem + 1024)), 512 / (2 * BN < 32 ? 32 : 2 * BN));
-  occ = std::max(occ, 1);
-  const int grid = std::min(total, kNumSMs * occ);
+template <int KE, int BM, int BN, bool RESB, int STAGES>
+static int launch_h_pers_s(const CUtensorMap& ma, const CUtensorMap& mb, const Epilogue& epi, int M, int N, int K, int kps, int splits,
+                           int smem, int grid, cudaStream_t stream, const ConvA& conv) {
   static int attr = 0;
   if (attr < smem) {
     B200RL_CUDA_OK(cudaFuncSetAttribute(hgemm_pers_kernel<KE, BM, BN, STAGES, RESB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -409,6 +402,34 @@ static int launch_h_pers(const CUtensorMap& ma, const CUtensorMap& mb, Epilogue 
   hgemm_pers_kernel<KE, BM, BN, STAGES, RESB><<<grid, H_THREADS, smem, stream>>>(ma, mb, epi, M, N, K, kps, splits, conv);
   B200RL_LAUNCH_OK();
   return B200RL_OK;
+}
+
+template <int KE, int BM, int BN, bool RESB>
+static int launch_h_pers(const CUtensorMap& ma, const CUtensorMap& mb, Epilogue epi, int M, int N, int K, int kps, int splits,
+                         int res_b_bytes, cudaStream_t stream, const ConvA& conv) {
+  constexpr int STAGE = RESB ? HBM_ROWS * KE * 2 : HBM_ROWS * KE * 2 + BN * KE * 2;
+  constexpr int S0 = STAGE >= 24 * 1024 ? 3 : 4;
+  const int fixed = HBM_ROWS * BN * 4 + (RESB ? res_b_bytes : 0) + 1024;
+  const int total = ceil_div(M, HBM_ROWS) * ceil_div(N, BN) * splits;
+  const int tmem_occ = 512 / (2 * BN < 32 ? 32 : 2 * BN);
+  auto occ_of = [&](int stages) { return std::max(0, std::min(std::min(4, (227 * 1024) / (stages * STAGE + fixed + 1024)), tmem_occ)); };
+  // What hides the L2 latency is the bytes in flight per SM = co-resident CTAs x ring depth x stage size.  Shallow rings
+  // with several CTAs per SM when the fixed part (slab + resident weights) is small; one CTA per SM with a deep ring when
+  // the resident weights take most of the shared memory (measured: conv2 with a 4 x 8 KB ring and one CTA per SM ran at
+  // 26 us against 16 us for three co-resident one-tile CTAs).
+  int stages = S0;
+  if (occ_of(S0) < 2) {
+    for (int cand : {12, 8, 6}) if (cand > S0 && occ_of(cand) >= 1) { stages = cand; break; }
+  }
+  const int occ = std::max(1, occ_of(stages));
+  const int smem = stages * STAGE + fixed;
+  const int grid = std::min(total, kNumSMs * occ);
+  switch (stages) {
+    case 12: return launch_h_pers_s<KE, BM, BN, RESB, 12>(ma, mb, epi, M, N, K, kps, splits, smem, grid, stream, conv);
+    case 8: return launch_h_pers_s<KE, BM, BN, RESB, 8>(ma, mb, epi, M, N, K, kps, splits, smem, grid, stream, conv);
+    case 6: return launch_h_pers_s<KE, BM, BN, RESB, 6>(ma, mb, epi, M, N, K, kps, splits, smem, grid, stream, conv);
+    default: return launch_h_pers_s<KE, BM, BN, RESB, S0>(ma, mb, epi, M, N, K, kps, splits, smem, grid, stream, conv);
+  }
 }
 
 template <int KE, int AM, int BM, int BN>
@@ -745,6 +766,162 @@ hconv_dgrad_kernel(const __grid_constant__ HDgradMaps maps, const __grid_constan
   if (warp == 1) tmem_dealloc(tmem_d, TMEM_COLS);
 }
 
+// persistent data-gradient kernel: static tile walk over all phases, two TMEM accumulators, the WHOLE weight matrix
+// resident in shared memory (box (tap, co-block) at a fixed offset), so the ring carries the dy tiles only
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(H_THREADS)
+hconv_dgrad_pers_kernel(const __grid_constant__ HDgradMaps maps, const __grid_constant__ CUtensorMap map_w, HDgradParams P, Epilogue epi,
+                        int total_tiles, int kh) {
+  constexpr int KE = 64, BM = BN == 32 ? 2 : 1;
+  constexpr int A_BYTES = HBM_ROWS * KE * 2, B_BYTES = BN * KE * 2;
+  constexpr int B_WB = BN == 32 ? 32 : 64, B_BOX = B_WB * KE * 2, B_NBOX = BN / B_WB;
+  constexpr int SLAB = HBM_ROWS * BN * 4;
+  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* const smem_al = smem_raw + (base - smem_u32(smem_raw));
+  __shared__ __align__(8) uint64_t bar_full[STAGES], bar_empty[STAGES], acc_full[2], acc_empty[2], bar_b;
+  __shared__ uint32_t tmem_base_smem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cb = P.Cout / KE;
+  const uint32_t res_b = base + STAGES * A_BYTES + SLAB;     // box ((ky * kw + kx) * cb + co-block)
+
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if (i < P.nphase) prefetch_tensormap(&maps.m[i]);
+    prefetch_tensormap(&map_w);
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+#pragma unroll
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+    mbar_init(&bar_b, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_smem;
+
+  auto phase_of = [&](int t) {
+    int ph = 0;
+#pragma unroll
+    for (int i = 1; i < 4; ++i) if (i < P.nphase && t >= P.ph[i].tile_begin) ph = i;
+    return ph;
+  };
+
+  if (warp == 0 && lane == 0) {
+    const int K = P.kw * P.C, taps = kh * P.kw;
+    mbar_expect_tx(&bar_b, (uint32_t)(taps * cb * B_BYTES));
+    for (int tap = 0; tap < taps; ++tap)
+      for (int c = 0; c < cb; ++c)
+#pragma unroll
+        for (int j = 0; j < B_NBOX; ++j)
+          tma_load_2d(res_b + (tap * cb + c) * B_BYTES + j * B_BOX, &map_w, (tap / P.kw) * K + (tap % P.kw) * P.C + B_WB * j, c * KE, &bar_b);
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int phase = phase_of(t);
+      const HDgradPhase& ph = P.ph[phase];
+      const int row0 = (t - ph.tile_begin) * HBM_ROWS;
+      const int jx = row0 % ph.cnt_x, q = row0 / ph.cnt_x;
+      const int ax = ph.lower_x + jx, ay = ph.lower_y + q % ph.cnt_y, an = q / ph.cnt_y;
+      const int nkb = ph.Ty * ph.Tx * cb;
+      int co0 = 0, off_x = 0, off_y = 0;
+      for (int i = 0; i < nkb; ++i, ++it) {
+        const int s = it % STAGES;
+        if (it >= STAGES) mbar_wait(&bar_empty[s], ((it / STAGES) - 1) & 1);
+        mbar_expect_tx(&bar_full[s], A_BYTES);
+        tma_load_im2col(base + s * A_BYTES, &maps.m[phase], co0, ax, ay, an, (uint16_t)off_x, (uint16_t)off_y, &bar_full[s]);
+        co0 += KE;
+        if (co0 == P.Cout) {
+          co0 = 0;
+          if (++off_x == ph.Tx) { off_x = 0; ++off_y; }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    constexpr uint32_t idesc = idesc_bf16(HBM_ROWS, BN, false, true);
+    mbar_wait(&bar_b, 0);
+    tc_fence_after();
+    int it = 0, ti = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+      const HDgradPhase& ph = P.ph[phase_of(t)];
+      const int nkb = ph.Ty * ph.Tx * cb;
+      const int ab = ti & 1;
+      mbar_wait(&acc_empty[ab], ((ti >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_d + (uint32_t)(ab * BN);
+      int c = 0, off_x = 0, off_y = 0;
+      for (int i = 0; i < nkb; ++i, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&bar_full[s], (it / STAGES) & 1);
+        tc_fence_after();
+        const int ky = ph.py + P.stride * (ph.Ty - 1 - off_y), kx = ph.px + P.stride * (ph.Tx - 1 - off_x);
+        const uint32_t sa = base + s * A_BYTES, sb = res_b + ((ky * P.kw + kx) * cb + c) * B_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < KE / 16; ++kk)
+          umma_bf16(acc, operand_desc<0, KE>(sa, kk), operand_desc<BM, KE>(sb, kk), idesc, (i > 0 || kk > 0) ? 1u : 0u);
+        umma_commit(&bar_empty[s]);
+        if (++c == cb) {
+          c = 0;
+          if (++off_x == ph.Tx) { off_x = 0; ++off_y; }
+        }
+      }
+      umma_commit(&acc_full[ab]);
+    }
+  } else if (warp >= 2) {
+    const int lane_base = (warp & 3) * 32;
+    float* slab = reinterpret_cast<float*>(smem_al + STAGES * A_BYTES) + (warp & 3) * 32 * BN;
+    int ti = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+      const HDgradPhase& ph = P.ph[phase_of(t)];
+      const int row = (t - ph.tile_begin) * HBM_ROWS + lane_base + lane;
+      const int Mp = P.B * ph.cnt_y * ph.cnt_x;
+      long long orow = -1;
+      if (row < Mp) {
+        const int jx = row % ph.cnt_x, q = row / ph.cnt_x;
+        const int jy = q % ph.cnt_y, b = q / ph.cnt_y;
+        orow = ((long long)b * P.H + (ph.iy0 + P.stride * jy)) * P.W + (ph.ix0 + P.stride * jx);
+      }
+      const int ab = ti & 1;
+      mbar_wait(&acc_full[ab], (ti >> 1) & 1);
+      tc_fence_after();
+      stage_accumulator<BN>(tmem_d + ((uint32_t)lane_base << 16) + (uint32_t)(ab * BN), slab, lane, true);
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(&acc_empty[ab]);
+      store_staged_rows<BN>(epi, slab, lane, 0, P.C, 0, [&](int r) -> long long { return __shfl_sync(0xffffffffu, orow, r); });
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_d, TMEM_COLS);
+}
+
+template <int BN, int STAGES>
+static int launch_hdgrad_pers_s(const HDgradMaps& maps, const CUtensorMap& mw, const HDgradParams& P, int tiles, const Epilogue& e,
+                                int kh, int smem, cudaStream_t s) {
+  static int attr = 0;
+  if (attr < smem) {
+    B200RL_CUDA_OK(cudaFuncSetAttribute(hconv_dgrad_pers_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = smem;
+  }
+  hconv_dgrad_pers_kernel<BN, STAGES><<<std::min(tiles, kNumSMs), H_THREADS, smem, s>>>(maps, mw, P, e, tiles, kh);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+template <int BN>
+static int launch_hdgrad_pers(const HDgradMaps& maps, const CUtensorMap& mw, const HDgradParams& P, int tiles, const Epilogue& e,
+                              int kh, cudaStream_t s) {
+  const int res_b = kh * P.kw * (P.Cout / 64) * BN * 64 * 2;
+  const int fixed = HBM_ROWS * BN * 4 + res_b + 1024, A = HBM_ROWS * 64 * 2;
+  // one CTA per SM (the resident weights take 64-72 KB): the ring gets the rest of the shared memory
+  if (8 * A + fixed <= 224 * 1024) return launch_hdgrad_pers_s<BN, 8>(maps, mw, P, tiles, e, kh, 8 * A + fixed, s);
+  if (6 * A + fixed <= 224 * 1024) return launch_hdgrad_pers_s<BN, 6>(maps, mw, P, tiles, e, kh, 6 * A + fixed, s);
+  if (4 * A + fixed <= 224 * 1024) return launch_hdgrad_pers_s<BN, 4>(maps, mw, P, tiles, e, kh, 4 * A + fixed, s);
+  return 1;
+}
+
 template <int BN>
 static int launch_hdgrad(const HDgradMaps& maps, const CUtensorMap& mw, const HDgradParams& P, int tiles, const Epilogue& e,
                          cudaStream_t s) {
@@ -800,6 +977,10 @@ int h_conv_dgrad(const bf16* dy, const bf16* w, void* dx, const b200rl_conv_geom
   const int WB = g.C == 32 ? 32 : 64;
   if (!make_map_h(&mw, w, g.Cout, K, K, WB, 64)) return 1;
   Epilogue e = make_epi(dx, g.C, nullptr, 0, mask, g.C, mask_act, 0, out_bf16, mask_bf16, 0.f);
+  if (use_persistent() && tiles > kNumSMs && (g.C == 32 || g.C == 64)) {
+    const int rc = g.C == 32 ? launch_hdgrad_pers<32>(maps, mw, P, tiles, e, g.kh, s) : launch_hdgrad_pers<64>(maps, mw, P, tiles, e, g.kh, s);
+    if (rc != 1) return rc;     // 1 = weights too large to stay resident: one tile per CTA instead
+  }
   if (g.C == 32) return launch_hdgrad<32>(maps, mw, P, tiles, e, s);
   if (g.C == 64) return launch_hdgrad<64>(maps, mw, P, tiles, e, s);
   return launch_hdgrad<128>(maps, mw, P, tiles, e, s);
