@@ -189,6 +189,21 @@ __global__ void c51_loss_kernel(int K, float vmin, float vmax, const float* __re
   if (i == 0 && loss_ps) loss_ps[b] = loss;
 }
 
+// trfl.td_learning as called at acme/agents/tf/ddpg/learning.py:193 (public trfl formula; trfl is not in the tree):
+// target = r + pcont * v_t (stop-gradient), td = target - v_tm1, loss = 0.5 td^2; d(mean loss)/d v_tm1 = -td / B.
+__global__ void td_learning_kernel(int B, const float* __restrict__ v_tm1, const float* __restrict__ v_t,
+                                   const float* __restrict__ R, const float* __restrict__ D, float gamma, float grad_scale,
+                                   float* __restrict__ td_out, float* __restrict__ loss_ps, float* __restrict__ dv) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float pcont = __fmul_rn(gamma, D[b]);                        // discount * d_t, learning.py:169,193
+  const float target = __fadd_rn(R[b], __fmul_rn(pcont, v_t[b]));
+  const float td = __fsub_rn(target, v_tm1[b]);
+  if (td_out) td_out[b] = td;
+  loss_ps[b] = __fmul_rn(0.5f, __fmul_rn(td, td));
+  if (dv) dv[b] = -td * grad_scale;
+}
+
 __global__ void __launch_bounds__(1024) mean_kernel(const float* __restrict__ x, int n, float* __restrict__ out) {
   __shared__ float scratch[32];
   float s = 0.f;
@@ -873,6 +888,18 @@ extern "C" int b200rl_c51_loss(int32_t B, int32_t K, float vmin, float vmax, con
   int threads = ((K + 31) / 32) * 32;
   c51_loss_kernel<<<B, threads, 3 * K * sizeof(float), as_stream(stream)>>>(K, vmin, vmax, logits_tm1, logits_t, R, D, gamma,
                                                                            grad_scale, target, loss_ps, dlogits);
+  B200RL_LAUNCH_OK();
+  if (loss_mean) {
+    mean_kernel<<<1, 256, 0, as_stream(stream)>>>(loss_ps, B, loss_mean);
+    B200RL_LAUNCH_OK();
+  }
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_td_learning(int32_t B, const float* v_tm1, const float* v_t, const float* R, const float* D, float gamma,
+                                  float grad_scale, float* td, float* loss_ps, float* dv_tm1, float* loss_mean, void* stream) {
+  B200RL_REQUIRE(v_tm1 && v_t && R && D && loss_ps && B >= 1, "bad argument");
+  td_learning_kernel<<<ceil_div(B, 128), 128, 0, as_stream(stream)>>>(B, v_tm1, v_t, R, D, gamma, grad_scale, td, loss_ps, dv_tm1);
   B200RL_LAUNCH_OK();
   if (loss_mean) {
     mean_kernel<<<1, 256, 0, as_stream(stream)>>>(loss_ps, B, loss_mean);

@@ -108,21 +108,32 @@ class D4PGLearner(core.Learner, core.Saveable):
     logits_tm1 = C.logits(o0, a0, self._c_train)
     a_targ = TP.action(o1, self._p_tgt)
     logits_t = TC.logits(o1, a_targ, self._c_tgt)
-    _capi.call('b200rl_c51_loss', B, C.K, C.vmin, C.vmax, _capi.ptr(logits_tm1), _capi.ptr(logits_t), _capi.ptr(ds.R),
-               _capi.ptr(ds.D), self._discount, 1.0 / B, _capi.ptr(self.target), _capi.ptr(self.critic_loss_ps),
-               _capi.ptr(self.dlogits), _capi.ptr(self.critic_loss), st)
+    self._critic_loss(logits_tm1, logits_t)
     C.backward_flat(self._c_train['x'].data_ptr(), self._c_train, self._cg_train, self.dlogits.data_ptr(),
                     param_grads=True, input_grad=False)
     # actor learning (learning.py:206-218): dq/da through the online critic, parameters untouched
     a_t = P.action(o1, self._p_online)
     logits_pi = C.logits(o1, a_t, self._c_pi)
-    _capi.call('b200rl_c51_mean_bwd', B, C.K, C.vmin, C.vmax, _capi.ptr(logits_pi), None, _capi.ptr(self.dlogits_pi), st)
+    self._dq_dlogits(logits_pi)
     C.backward_flat(self._c_pi['x'].data_ptr(), self._c_pi, self._cg_pi, self.dlogits_pi.data_ptr(),
                     param_grads=False, input_grad=True)
     _capi.call('b200rl_split_second', B, self._obs_dim, self._act_dim, _capi.ptr(self._cg_pi['dx']), _capi.ptr(self.dqda), st)
     _capi.call('b200rl_dpg_action_grad', B, self._act_dim, _capi.ptr(self.dqda), 1.0 if self._clipping else 0.0,
                int(self._clipping), 1.0 / B, _capi.ptr(self.da), _capi.ptr(self.policy_loss_ps), _capi.ptr(self.policy_loss), st)
     P.backward_action(o1, self._p_online, self._pg, self.da)
+
+  def _critic_loss(self, logits_tm1, logits_t):
+    """K5: losses.categorical (distributional.py:22-37) and its gradient w.r.t. logits_tm1 (learning.py:202-203)."""
+    C, ds, B = self._critic, self._dataset, self.B
+    _capi.call('b200rl_c51_loss', B, C.K, C.vmin, C.vmax, _capi.ptr(logits_tm1), _capi.ptr(logits_t), _capi.ptr(ds.R),
+               _capi.ptr(ds.D), self._discount, 1.0 / B, _capi.ptr(self.target), _capi.ptr(self.critic_loss_ps),
+               _capi.ptr(self.dlogits), _capi.ptr(self.critic_loss), _capi.current_stream())
+
+  def _dq_dlogits(self, logits_pi):
+    """d mean(Z) / d logits of the critic's output at (o_t, policy(o_t)) (distributions.py:64-66; learning.py:206-208)."""
+    C, B = self._critic, self.B
+    _capi.call('b200rl_c51_mean_bwd', B, C.K, C.vmin, C.vmax, _capi.ptr(logits_pi), None, _capi.ptr(self.dlogits_pi),
+               _capi.current_stream())
 
   def _apply_half(self):
     """clip each gradient set by its global norm (learning.py:235-237), then the two Adams (240-241), step counter."""
@@ -222,6 +233,28 @@ class D4PGLearner(core.Learner, core.Saveable):
     self._pm.copy_(t(state['policy_opt'][0])); self._pv.copy_(t(state['policy_opt'][1]))
     self._cm.copy_(t(state['critic_opt'][0])); self._cv.copy_(t(state['critic_opt'][1]))
     self._num_steps.fill_(int(state['num_steps']))
+
+
+class DDPGLearner(D4PGLearner):
+  """`acme/agents/tf/ddpg/learning.py:140-237`: the D4PG step with a scalar critic -- critic loss = trfl.td_learning
+  (0.5 td^2, line 193) instead of the categorical projection, dq/da through the scalar output directly; same target-copy
+  timing (before the update, 157-160), DPG loss with dq/da norm clipping, global-norm clip 40, two Adams."""
+
+  def __init__(self, policy_network, critic_network, target_policy_network, target_critic_network, *args, **kwargs):
+    super().__init__(policy_network, critic_network, target_policy_network, target_critic_network, *args, **kwargs)
+    torch = self._torch
+    dev = self.dlogits.device
+    self.td = torch.zeros(self.B, dtype=torch.float32, device=dev)
+    self._ones = torch.ones((self.B, 1), dtype=torch.float32, device=dev)
+
+  def _critic_loss(self, q_tm1, q_t):
+    ds, B = self._dataset, self.B
+    _capi.call('b200rl_td_learning', B, _capi.ptr(q_tm1), _capi.ptr(q_t), _capi.ptr(ds.R), _capi.ptr(ds.D), self._discount,
+               1.0 / B, _capi.ptr(self.td), _capi.ptr(self.critic_loss_ps), _capi.ptr(self.dlogits), _capi.ptr(self.critic_loss),
+               _capi.current_stream())
+
+  def _dq_dlogits(self, q_pi):
+    self.dlogits_pi.copy_(self._ones)      # d q / d q = 1: the action gradient flows through the scalar output itself
 
 
 class GaussianNoisePolicy:

@@ -838,6 +838,22 @@ class D4PGCritic(LayerNormMLP):
     return self.forward_flat(bufs['x'].data_ptr(), bufs)
 
 
+class DDPGCritic(LayerNormMLP):
+  """CriticMultiplexer(critic_network=LayerNormMLP(sizes + [1])) (`acme/agents/tf/ddpg/agent_test.py:46-47`): the scalar
+  critic of DDPG -- the same torso as the D4PG critic with one linear output instead of the 51 atoms."""
+
+  def __init__(self, obs_dim: int, act_dim: int, sizes=(512, 512, 256), device: int = 0,
+               precision: int = _capi.PRECISION_FP32, seed: int = 0):
+    super().__init__(obs_dim + act_dim, sizes, 1, 'q', None, device, precision, seed)
+    self.obs_dim, self.act_dim, self.K = int(obs_dim), int(act_dim), 1
+
+  def logits(self, obs, act, bufs):
+    """q(obs, act) [B, 1] (named like D4PGCritic.logits so both critics drive the same learner plumbing)."""
+    _capi.call('b200rl_concat2', bufs['B'], self.obs_dim, self.act_dim, obs.data_ptr(), act.data_ptr(),
+               bufs['x'].data_ptr(), _capi.current_stream())
+    return self.forward_flat(bufs['x'].data_ptr(), bufs)
+
+
 class D4PGPolicy(LayerNormMLP):
   """LayerNormMLP(sizes, activate_final=True) -> NearZeroInitializedLinear(A) -> TanhToSpec."""
 

@@ -178,6 +178,10 @@ int b200rl_c51_loss(int32_t B, int32_t K, float vmin, float vmax, const float* l
                     const float* logits_t, const float* R, const float* D, float gamma,
                     float grad_scale, float* target, float* loss_per_sample, float* dlogits_tm1,
                     float* loss_mean, void* stream);
+/* DDPG critic loss (acme/agents/tf/ddpg/learning.py:193, trfl.td_learning): td = (R + gamma * D * v_t) - v_tm1,
+ * loss = 0.5 td^2, dv_tm1 = -td * grad_scale.  td, dv_tm1, loss_mean nullable. */
+int b200rl_td_learning(int32_t B, const float* v_tm1, const float* v_t, const float* R, const float* D, float gamma,
+                       float grad_scale, float* td, float* loss_per_sample, float* dv_tm1, float* loss_mean, void* stream);
 /* mean of a discrete-valued distribution and its logit gradient (distributions.py:64-66):
  * q = sum softmax(l)_i z_i;  dlogits_i = p_i (z_i - q) * dq. */
 int b200rl_c51_mean_fwd(int32_t B, int32_t K, float vmin, float vmax, const float* logits, float* q,

@@ -134,6 +134,12 @@ class D4PGOracleLearner:
     self.copt = Adam(critic_lr, eps_mode=eps_mode)
     self.num_steps = 0
 
+  def _critic_loss(self, logits_tm1, logits_t, Rn, Dg):
+    """losses.categorical (distributional.py:22-37) through autograd; `ref` carries the NumPy restatement's outputs."""
+    ref = L.categorical(logits_tm1.detach().numpy(), logits_t.numpy(), self.critic.values.numpy(), Rn, Dg)
+    target = torch.tensor(ref['target'])
+    return ref, (-(target * torch.log_softmax(logits_tm1, dim=-1)).sum(dim=-1)).mean()
+
   def step(self, o_tm1, a_tm1, R, D, o_t):
     if self.num_steps % self.period == 0:
       self.tpolicy.copy_from(self.policy)
@@ -148,9 +154,7 @@ class D4PGOracleLearner:
     logits_tm1 = self.critic.logits(o0, a0)
     with torch.no_grad():
       logits_t = self.tcritic.logits(o1, self.tpolicy.action(o1))
-    ref = L.categorical(logits_tm1.detach().numpy(), logits_t.numpy(), self.critic.values.numpy(), Rn, Dg)
-    target = torch.tensor(ref['target'])
-    critic_loss = (-(target * torch.log_softmax(logits_tm1, dim=-1)).sum(dim=-1)).mean()
+    ref, critic_loss = self._critic_loss(logits_tm1, logits_t, Rn, Dg)
 
     a_t = self.policy.action(o1)
     a_leaf = a_t.detach().clone().requires_grad_(True)
@@ -174,6 +178,16 @@ class D4PGOracleLearner:
     self.policy.load(self.popt.apply(pg, self.policy.numpy()))
     self.critic.load(self.copt.apply(cg, self.critic.numpy()))
     return dict(critic_loss=np.float32(critic_loss.item()), policy_loss=policy_loss,
-                target=ref['target'], per_sample=ref['loss'], dlogits_tm1=ref['dlogits_tm1'],
+                target=ref.get('target'), per_sample=ref['loss'], dlogits_tm1=ref.get('dlogits_tm1'), td=ref.get('td'),
                 logits_tm1=logits_tm1.detach().numpy(), logits_t=logits_t.numpy(),
                 dqda=dqda, critic_grads=cg, policy_grads=pg, critic_norm=cnorm, policy_norm=pnorm)
+
+
+class DDPGOracleLearner(D4PGOracleLearner):
+  """acme/agents/tf/ddpg/learning.py:140-237: D4PG's step with a scalar critic and trfl.td_learning (line 193)."""
+
+  def _critic_loss(self, q_tm1, q_t, Rn, Dg):
+    ref = L.td_learning(q_tm1.detach().numpy()[:, 0], Rn, Dg, q_t.numpy()[:, 0])
+    target = torch.tensor(Rn) + torch.tensor(Dg) * q_t[:, 0]
+    td = target - q_tm1[:, 0]
+    return ref, (0.5 * td * td).mean()

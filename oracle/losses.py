@@ -118,3 +118,12 @@ def clip_by_global_norm(grads, clip):
   norm = np.sqrt(sq)
   scale = f32(clip / max(norm, clip))
   return [np.asarray(g, f32) * scale for g in grads], f32(norm)
+
+
+def td_learning(v_tm1, r_t, pcont_t, v_t):
+  """trfl.td_learning as called at acme/agents/tf/ddpg/learning.py:193 (public trfl formula; UNPINNED): target =
+  r + pcont * v_t (stop-gradient), td = target - v_tm1, loss = 0.5 td^2.  Returns dict(td, loss[B], dv_tm1 of the mean)."""
+  v_tm1, v_t = np.asarray(v_tm1, f32), np.asarray(v_t, f32)
+  target = (np.asarray(r_t, f32) + np.asarray(pcont_t, f32) * v_t).astype(f32)
+  td = (target - v_tm1).astype(f32)
+  return dict(td=td, loss=(f32(0.5) * td * td).astype(f32), dv_tm1=(-td / f32(td.shape[0])).astype(f32))

@@ -192,6 +192,21 @@ class D4PGCritic(LayerNormMLP):
     return (torch.softmax(self.logits(obs, act), dim=-1) * self.values).sum(dim=-1)
 
 
+class DDPGCritic(LayerNormMLP):
+  """CriticMultiplexer(critic_network=LayerNormMLP(sizes + [1])) (acme/agents/tf/ddpg/agent_test.py:46-47): the hidden
+  sizes are activated (ELU), the last layer of width 1 is not -- the same as a torso with `activate_final` plus a linear
+  output."""
+
+  def __init__(self, obs_dim, act_dim, sizes=(512, 512, 256), seed=0):
+    super().__init__(obs_dim + act_dim, sizes, head_dim=1, head_name='q', seed=seed)
+
+  def logits(self, obs, act):
+    return self(torch.cat([obs.reshape(obs.shape[0], -1), act.reshape(act.shape[0], -1)], dim=-1))
+
+  def mean(self, obs, act):
+    return self.logits(obs, act)[:, 0]
+
+
 class D4PGPolicy(LayerNormMLP):
   """LayerNormMLP(sizes, activate_final) -> NearZeroInitializedLinear(A) -> TanhToSpec."""
 

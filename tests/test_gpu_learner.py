@@ -673,3 +673,58 @@ def test_dqn_learner_jax_variants():
     assert torch.equal(tgt.params.flat, frozen), f'target network wrong after update {step}'
     helpers.sync_oracle_leaves_loose(table, oracle)
   server.stop()
+
+
+@pytest.mark.parametrize('use_graph', [False, True])
+def test_ddpg_learner_steps_match_oracle(use_graph):
+  """`acme/agents/tf/ddpg/learning.py:140-237` (scalar critic, trfl.td_learning at 193, DPG with dq/da norm
+  clipping, global-norm clip, two Adams, target copy before the update) against oracle.learner.DDPGOracleLearner."""
+  import torch
+  import helpers
+  from acme_b200 import _capi, d4pg, loggers, networks, replay
+  from oracle import learner as olearner
+  from oracle import nets as onets
+  rng = np.random.default_rng(6)
+  OBS, ACT, n, B = 17, 6, 5, 32
+  spec, table, server, adder, oracle = helpers.make_pair((OBS,), np.float32, 0, n, 0.99, 0.0, max_size=400, act_dim=ACT)
+  for ep in range(10):
+    helpers.feed_episode(rng, adder, oracle, int(rng.integers(3, 40)), n, (OBS,), np.float32, 0, act_dim=ACT)
+  table.flush()
+  helpers.sync_oracle_leaves(table, oracle)
+  sizes = (64, 64)
+  policy = networks.D4PGPolicy(OBS, ACT, sizes=sizes, seed=1)
+  critic = networks.DDPGCritic(OBS, ACT, sizes=sizes, seed=2)
+  pv = policy.variables()
+  pv['out/w'] = (np.random.default_rng(3).standard_normal(pv['out/w'].shape) * 0.05).astype(np.float32)
+  policy.load_variables(pv)
+  opol, ocri = onets.D4PGPolicy(OBS, ACT, sizes), onets.DDPGCritic(OBS, ACT, sizes)
+  otp, otc = onets.D4PGPolicy(OBS, ACT, sizes), onets.DDPGCritic(OBS, ACT, sizes)
+  for o, n_ in ((opol, policy), (otp, policy), (ocri, critic), (otc, critic)):
+    o.load(n_.variables())
+  ds = replay.ReplayDataset(table, B, seed=11, stratified=False)
+  learner = d4pg.DDPGLearner(policy, critic, policy.clone(), critic.clone(), 0.99, target_update_period=2, dataset=ds,
+                             logger=loggers.NoOpLogger(), use_cuda_graph=use_graph)
+  ol = olearner.DDPGOracleLearner(opol, ocri, otp, otc, 0.99, 2)
+  counter = torch.zeros(1, dtype=torch.int64, device='cuda')
+  u_dev = torch.empty(B, device='cuda')
+  lr = 1e-4
+  for step in range(4):
+    _capi.call('b200rl_uniform', u_dev.data_ptr(), B, 11, counter.data_ptr(), step, _capi.current_stream())
+    keys, pos, prob = oracle.sample(u_dev.cpu().numpy(), False)
+    ref = ol.step(*oracle.gather(pos))
+    learner.step()
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(ds.idx.cpu().numpy(), pos)
+    close(learner.td.cpu().numpy(), ref['td'], atol_scale=2e-5, name=f'td step {step}')
+    close(learner.critic_loss_ps.cpu().numpy(), ref['per_sample'], rtol=1e-4, atol_scale=2e-5, name='0.5 td^2')
+    close(learner.critic_loss.cpu().numpy()[0], ref['critic_loss'], rtol=1e-4)
+    close(learner.dqda.cpu().numpy(), ref['dqda'], rtol=1e-3, atol_scale=1e-4, name='dq/da')
+    close(learner.policy_loss.cpu().numpy()[0], ref['policy_loss'], rtol=1e-3)
+    if step < 2:
+      for net, onet, what in ((critic, ocri, 'critic'), (policy, opol, 'policy')):
+        got = net.variables()
+        for k, v in onet.numpy().items():
+          bad = ~np.isclose(got[k], v, rtol=1e-4, atol=0.02 * lr)
+          assert bad.mean() < 2e-3, f'{what} {k} step {step}: {bad.sum()} of {bad.size} outside 2% of lr'
+  assert learner.num_steps == 4
+  server.stop()
