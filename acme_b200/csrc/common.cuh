@@ -60,6 +60,25 @@ struct ReplayState {
   unsigned long long item_tail;  // oldest live key
 };
 
+// Philox4x32-10 uniform in [0,1) for (element i, draw counter `step`) keyed by `seed`: the learner's device-side uniform
+// stream (b200rl_uniform) and K1's built-in draws (b200rl_replay_sample_philox) are the same function.
+#ifdef __CUDACC__
+__device__ __forceinline__ float philox_uniform(unsigned int i, unsigned long long seed, unsigned long long step) {
+  unsigned int c0 = i, c1 = 0u, c2 = (unsigned int)step, c3 = (unsigned int)(step >> 32);
+  unsigned int k0 = (unsigned int)seed, k1 = (unsigned int)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const unsigned int n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return (float)(c0 >> 8) * (1.0f / 16777216.0f);  // 24 bits -> [0,1), exact in fp32
+}
+#endif
+
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 template <typename T>

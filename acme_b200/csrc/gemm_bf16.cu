@@ -30,6 +30,16 @@ namespace b200rl {
 typedef __nv_bfloat16 bf16;
 constexpr int HBM_ROWS = 128, H_THREADS = 192;
 
+// tools/h_timeline.py: global-timer stamps of one CTA's life (set-up, first operands, last MMA, epilogue, exit)
+__device__ unsigned long long* g_h_timeline = nullptr;
+__device__ __forceinline__ void h_mark(int slot, int cta) {
+  if (g_h_timeline && (int)(blockIdx.x + blockIdx.y * gridDim.x) == cta && blockIdx.z == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_h_timeline[slot] = t;
+  }
+}
+
 // ---- tensor maps over bf16 tensors
 static CUtensorMapSwizzle sw_mode(int row_bytes) { return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B; }
 
@@ -386,7 +396,11 @@ int g_h_persistent = -1;   // -1 = read B200RL_PERSISTENT once (default on), els
 static bool use_persistent() {
   if (g_h_persistent < 0) {
     const char* e = getenv("B200RL_PERSISTENT");
-    g_h_persistent = e ? atoi(e) : 1;
+    // Measured on B200 (round 2): correct, but SLOWER inside the learner step (0.331-0.366 vs 0.314 ms).  The step runs the
+    // target pass beside the online pass and weight gradients beside data gradients on separate streams; a persistent
+    // CTA with resident weights takes 130-190 KB of shared memory, so two such kernels cannot share an SM and the
+    // streams serialise, while one-tile CTAs of 40-100 KB interleave.  Off by default; B200RL_PERSISTENT=1 enables it.
+    g_h_persistent = e ? atoi(e) : 0;
   }
   return g_h_persistent != 0;
 }
@@ -698,6 +712,8 @@ hconv_dgrad_kernel(const __grid_constant__ HDgradMaps maps, const __grid_constan
   const int Mp = P.B * ph.cnt_y * ph.cnt_x;
   const int cb = P.Cout / KE;
   const int nkb = ph.Ty * ph.Tx * cb;
+  const int mark_cta = gridDim.x / 2;
+  if (tid == 0) h_mark(0, mark_cta);
 
   if (tid == 0) {
     prefetch_tensormap(&maps.m[phase]);
@@ -712,6 +728,7 @@ hconv_dgrad_kernel(const __grid_constant__ HDgradMaps maps, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = tmem_base_smem;
+  if (tid == 0) h_mark(1, mark_cta);
 
   if (warp == 0 && lane == 0) {
     const int jx = row0 % ph.cnt_x, t = row0 / ph.cnt_x;
@@ -738,6 +755,8 @@ hconv_dgrad_kernel(const __grid_constant__ HDgradMaps maps, const __grid_constan
     for (int i = 0; i < nkb; ++i) {
       const int s = i % D_STAGES;
       mbar_wait(&bar_full[s], (i / D_STAGES) & 1);
+      if (i == 0) h_mark(2, mark_cta);
+      if (i == nkb - 1) h_mark(3, mark_cta);
       tc_fence_after();
       const uint32_t sa = base + s * STAGE, sb = sa + A_BYTES;
 #pragma unroll
@@ -748,6 +767,7 @@ hconv_dgrad_kernel(const __grid_constant__ HDgradMaps maps, const __grid_constan
     }
   } else if (warp >= 2) {
     mbar_wait(&bar_done, 0);
+    if (tid == 64) h_mark(4, mark_cta);
     tc_fence_after();
     const int lane_base = (warp & 3) * 32;
     const int row = row0 + lane_base + lane;
@@ -759,11 +779,14 @@ hconv_dgrad_kernel(const __grid_constant__ HDgradMaps maps, const __grid_constan
     }
     float* slab = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw))) + (warp & 3) * 32 * BN;
     stage_accumulator<BN>(tmem_d + ((uint32_t)lane_base << 16), slab, lane, true);
+    if (tid == 64) h_mark(5, mark_cta);
     store_staged_rows<BN>(epi, slab, lane, 0, P.C, 0, [&](int r) -> long long { return __shfl_sync(0xffffffffu, orow, r); });
+    if (tid == 64) h_mark(6, mark_cta);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_d, TMEM_COLS);
+  if (tid == 32) h_mark(7, mark_cta);
 }
 
 // persistent data-gradient kernel: static tile walk over all phases, two TMEM accumulators, the WHOLE weight matrix
@@ -1012,3 +1035,7 @@ int h_f32_to_bf16(int64_t n, const float* src, bf16* dst, cudaStream_t s) {
 }  // namespace b200rl
 
 extern "C" int b200rl_debug_set_persistent(int on) { b200rl::g_h_persistent = on; return 0; }
+extern "C" int b200rl_debug_h_timeline(unsigned long long* buf_dev) {
+  cudaError_t e = cudaMemcpyToSymbol(b200rl::g_h_timeline, &buf_dev, sizeof(buf_dev));
+  return e == cudaSuccess ? 0 : -2;
+}

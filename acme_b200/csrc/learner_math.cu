@@ -11,28 +11,13 @@
 
 namespace b200rl {
 
-// ------------------------------------------------------------------------------ Philox4x32-10
-__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-  uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
-  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
-}
-
+// ------------------------------------------------------------------------------ Philox4x32-10 (common.cuh)
 __global__ void uniform_kernel(float* __restrict__ out, int n, unsigned long long seed,
                                const long long* __restrict__ step_dev, long long step_offset) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  unsigned long long step = (unsigned long long)((step_dev ? *step_dev : 0) + step_offset);
-  uint32_t c[4] = {(uint32_t)i, 0u, (uint32_t)step, (uint32_t)(step >> 32)};
-  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    philox_round(c, k0, k1);
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
-  }
-  out[i] = (float)(c[0] >> 8) * (1.0f / 16777216.0f);  // 24 bits -> [0,1), exact in fp32
+  const unsigned long long step = (unsigned long long)((step_dev ? *step_dev : 0) + step_offset);
+  out[i] = philox_uniform((unsigned int)i, seed, step);
 }
 
 // ------------------------------------------------------------------------------ block reductions
@@ -379,6 +364,31 @@ __global__ void copy_if_period_kernel(long long n16, int4* __restrict__ dst, con
   for (; i < n16; i += stride) dst[i] = __ldg(src + i);
 }
 __global__ void step_increment_kernel(long long* step) { *step += 1; }
+
+// The end of a learner step in one launch: target <- online (parameters and, if given, their bf16 shadow) when
+// (*step + phase) % period == 0, then *step += 1 and (if given) *counter2 += 1.  Every CTA reads *step when it starts;
+// the increments are done by the CTA that finishes LAST (ticket), i.e. after every CTA has taken its decision.
+__device__ unsigned int g_tail_ticket[8];
+__global__ void __launch_bounds__(256)
+learner_tail_kernel(long long n16_a, int4* __restrict__ dst_a, const int4* __restrict__ src_a, long long n16_b,
+                    int4* __restrict__ dst_b, const int4* __restrict__ src_b, long long* __restrict__ step_dev, long long period,
+                    long long phase, long long* __restrict__ counter2, int ticket) {
+  const bool due = period > 0 && ((*step_dev) + phase) % period == 0;
+  if (due) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16_a; i += stride) dst_a[i] = __ldg(src_a + i);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16_b; i += stride) dst_b[i] = __ldg(src_b + i);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&g_tail_ticket[ticket], 1u) == gridDim.x - 1) {
+      g_tail_ticket[ticket] = 0;
+      *step_dev += 1;
+      if (counter2) *counter2 += 1;
+    }
+  }
+}
 
 // ------------------------------------------------------------------------------ element-wise
 __device__ __forceinline__ float act_grad_from_output(float y, int act) {
@@ -946,14 +956,25 @@ extern "C" int b200rl_debug_stamp(unsigned long long* buf, int slot, void* strea
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
+extern "C" int b200rl_adam_throttled(int64_t n, float* param, const float* grad, float* m, float* v, const int64_t* step_dev,
+                                     float lr, double b1, double b2, float eps, int eps_mode, const float* grad_scale_dev,
+                                     void* bf16_shadow, int32_t ctas_per_sm, void* stream);
 extern "C" int b200rl_adam(int64_t n, float* param, const float* grad, float* m, float* v, const int64_t* step_dev,
                            float lr, double b1, double b2, float eps, int eps_mode, const float* grad_scale_dev,
                            void* bf16_shadow, void* stream) {
+  return b200rl_adam_throttled(n, param, grad, m, v, step_dev, lr, b1, b2, eps, eps_mode, grad_scale_dev, bf16_shadow, 0, stream);
+}
+// ctas_per_sm > 0 limits the grid to that many CTAs per SM: an update that runs BESIDE other kernels (the fc1 + head
+// bucket under the convolution backward) must leave them SM slots; 0 = the default (8, or B200RL_ADAM_CTAS_PER_SM)
+extern "C" int b200rl_adam_throttled(int64_t n, float* param, const float* grad, float* m, float* v, const int64_t* step_dev,
+                                     float lr, double b1, double b2, float eps, int eps_mode, const float* grad_scale_dev,
+                                     void* bf16_shadow, int32_t ctas_per_sm, void* stream) {
   B200RL_REQUIRE(param && grad && m && v && step_dev, "null argument");
   B200RL_REQUIRE(n >= 0 && (eps_mode == 0 || eps_mode == 1), "bad argument");
   B200RL_REQUIRE((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "buffers must be 16-byte aligned");
   if (n == 0) return B200RL_OK;
-  static const int per_sm = getenv("B200RL_ADAM_CTAS_PER_SM") ? atoi(getenv("B200RL_ADAM_CTAS_PER_SM")) : 8;   // 0 = one pass, no loop
+  static const int per_sm_env = getenv("B200RL_ADAM_CTAS_PER_SM") ? atoi(getenv("B200RL_ADAM_CTAS_PER_SM")) : 8;   // 0 = one pass, no loop
+  const int per_sm = ctas_per_sm > 0 ? ctas_per_sm : per_sm_env;
   static const int wide = getenv("B200RL_ADAM_WIDE") ? atoi(getenv("B200RL_ADAM_WIDE")) : -1;                 // -1 = by CTA count
   // measured on B200: the 4-vector variant is SLOWER (0.347 vs 0.318 ms per step at full occupancy, no gain beside other
   // kernels): more registers per thread cost more than the extra loads in flight bring.  Kept behind B200RL_ADAM_WIDE=1.
@@ -988,6 +1009,21 @@ extern "C" int b200rl_copy_if_period(int64_t n_bytes, void* dst, const void* src
   B200RL_REQUIRE(n_bytes % 16 == 0 && (((uintptr_t)dst | (uintptr_t)src) & 15) == 0, "copy must be 16-byte aligned/sized");
   copy_if_period_kernel<<<grid1d(n_bytes / 16, 256, kNumSMs * 8), 256, 0, as_stream(stream)>>>(
       n_bytes / 16, (int4*)dst, (const int4*)src, (const long long*)step_dev, period, phase);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_learner_tail(int64_t n_bytes_a, void* dst_a, const void* src_a, int64_t n_bytes_b, void* dst_b,
+                                   const void* src_b, int64_t* step_dev, int64_t period, int64_t phase, int64_t* counter2,
+                                   void* stream) {
+  B200RL_REQUIRE(step_dev && period >= 0, "bad argument");
+  B200RL_REQUIRE(n_bytes_a >= 0 && n_bytes_b >= 0 && n_bytes_a % 16 == 0 && n_bytes_b % 16 == 0, "copies must be multiples of 16 bytes");
+  B200RL_REQUIRE((n_bytes_a == 0 || (dst_a && src_a)) && (n_bytes_b == 0 || (dst_b && src_b)), "null buffer");
+  B200RL_REQUIRE(((((uintptr_t)dst_a | (uintptr_t)src_a | (uintptr_t)dst_b | (uintptr_t)src_b)) & 15) == 0, "buffers must be 16-byte aligned");
+  // one ticket per call site is enough: calls on one stream never overlap, and a learner has one tail per step
+  learner_tail_kernel<<<kNumSMs * 4, 256, 0, as_stream(stream)>>>(n_bytes_a / 16, (int4*)dst_a, (const int4*)src_a, n_bytes_b / 16,
+                                                                  (int4*)dst_b, (const int4*)src_b, (long long*)step_dev, period, phase,
+                                                                  (long long*)counter2, 0);
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }

@@ -35,9 +35,9 @@ void set_error(const char* fmt, ...) {
 
 // from sumtree.cu
 int tree_staged_levels(const TreeView& t, int64_t budget_bytes);
-int tree_sample(const TreeView& t, const ReplayState* st_dev, int64_t M, int B, const float* u,
-                int stratified, int shard_count, const float* denom_dev, int64_t* idx, uint64_t* keys, float* prob,
-                cudaStream_t stream, int* staged_out);
+int tree_sample(const TreeView& t, const ReplayState* st_dev, int64_t M, int B, const float* u, const int64_t* philox_counter,
+                uint64_t philox_seed, float* u_out, int stratified, int shard_count, const float* denom_dev, int64_t* idx,
+                uint64_t* keys, float* prob, cudaStream_t stream, int* staged_out);
 int tree_rebuild(const TreeView& t, cudaStream_t stream);
 int tree_scatter_positions(const TreeView& t, int64_t M, int n, const int64_t* pos_dev,
                            const float* w_dev, const ReplayState* st_dev, unsigned long long* stamp,
@@ -1070,8 +1070,25 @@ extern "C" int b200rl_replay_sample(b200rl_replay* h, int32_t B, const float* u_
   }
   int rc = ensure_device(h);
   if (rc) return rc;
-  return tree_sample(h->tree, h->d_state, h->M, B, u_dev, stratified, h->cfg.shard_count, h->global_mass_dev, idx_dev,
-                     keys_dev, prob_dev, as_stream(stream), nullptr);
+  return tree_sample(h->tree, h->d_state, h->M, B, u_dev, nullptr, 0, nullptr, stratified, h->cfg.shard_count, h->global_mass_dev,
+                     idx_dev, keys_dev, prob_dev, as_stream(stream), nullptr);
+}
+
+// K1 with built-in uniform draws: u_b = Philox(seed, *counter_dev)[b] -- exactly what b200rl_uniform(seed, counter_dev)
+// would have written -- so a captured step needs no separate draw kernel.  u_out (nullable) receives the draws.
+extern "C" int b200rl_replay_sample_philox(b200rl_replay* h, int32_t B, uint64_t seed, const int64_t* counter_dev, int stratified,
+                                           float* u_out_dev, int64_t* idx_dev, uint64_t* keys_dev, float* prob_dev, void* stream) {
+  B200RL_REQUIRE(h && counter_dev && idx_dev && prob_dev, "null argument");
+  B200RL_LOCK(h);
+  B200RL_REQUIRE(B >= 1, "batch must be >= 1");
+  if (h->item_head == h->item_tail) {
+    set_error("replay is empty (MinSize(1) not met)");
+    return B200RL_EAGAIN;
+  }
+  int rc = ensure_device(h);
+  if (rc) return rc;
+  return tree_sample(h->tree, h->d_state, h->M, B, nullptr, counter_dev, seed, u_out_dev, stratified, h->cfg.shard_count,
+                     h->global_mass_dev, idx_dev, keys_dev, prob_dev, as_stream(stream), nullptr);
 }
 
 extern "C" int b200rl_replay_gather(b200rl_replay* h, int32_t B, const int64_t* idx_dev, void* o_tm1,

@@ -69,7 +69,8 @@ __device__ __forceinline__ void group_descend(const float* __restrict__ line, in
 template <int SPG>   // samples interleaved per 4-lane group (memory-level parallelism for large batches)
 __global__ void __launch_bounds__(kSampleThreads)
 sample_kernel(TreeView t, int S, const ReplayState* __restrict__ st, long long M, int B,
-              const float* __restrict__ u, int stratified, float shards_f, const float* __restrict__ denom_dev,
+              const float* __restrict__ u, const long long* __restrict__ philox_counter, unsigned long long philox_seed,
+              float* __restrict__ u_out, int stratified, float shards_f, const float* __restrict__ denom_dev,
               long long* __restrict__ idx, unsigned long long* __restrict__ keys,
               float* __restrict__ prob) {
   extern __shared__ __align__(16) float staged[];
@@ -106,7 +107,15 @@ sample_kernel(TreeView t, int S, const ReplayState* __restrict__ st, long long M
 #pragma unroll
     for (int s = 0; s < SPG; ++s) {
       b[s] = (r * SPG + s) * total_groups + group_global;
-      const float ub = (b[s] < B) ? __ldg(u + b[s]) : 0.f;
+      float ub = 0.f;
+      if (b[s] < B) {
+        if (philox_counter) {   // built-in draws: the same Philox stream as b200rl_uniform(seed, *counter)
+          ub = philox_uniform((unsigned int)b[s], philox_seed, (unsigned long long)*philox_counter);
+          if (u_out && gl == 0) u_out[b[s]] = ub;
+        } else {
+          ub = __ldg(u + b[s]);
+        }
+      }
       tg[s] = stratified ? __fmul_rn(__fdiv_rn(__fadd_rn((float)b[s], ub), (float)B), mass) : __fmul_rn(ub, mass);
       node[s] = 0;
     }
@@ -150,9 +159,9 @@ static int64_t staged_bytes(const TreeView& t, int S) {
   return used;
 }
 
-int tree_sample(const TreeView& t, const ReplayState* st_dev, int64_t M, int B, const float* u,
-                int stratified, int shard_count, const float* denom_dev, int64_t* idx, uint64_t* keys, float* prob,
-                cudaStream_t stream, int* staged_out) {
+int tree_sample(const TreeView& t, const ReplayState* st_dev, int64_t M, int B, const float* u, const int64_t* philox_counter,
+                uint64_t philox_seed, float* u_out, int stratified, int shard_count, const float* denom_dev, int64_t* idx,
+                uint64_t* keys, float* prob, cudaStream_t stream, int* staged_out) {
   static bool attr_set = false;
   if (!attr_set) {
     B200RL_CUDA_OK(cudaFuncSetAttribute(sample_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -168,13 +177,15 @@ int tree_sample(const TreeView& t, const ReplayState* st_dev, int64_t M, int B, 
     const int threads = 128;                                    // 32 samples per CTA
     int blocks = (int)ceil_div<int64_t>((int64_t)B * 4, threads);
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-    sample_kernel<1><<<blocks, threads, smem, stream>>>(t, S, st_dev, M, B, u, stratified, (float)shard_count, denom_dev,
+    sample_kernel<1><<<blocks, threads, smem, stream>>>(t, S, st_dev, M, B, u, (const long long*)philox_counter, (unsigned long long)philox_seed, u_out, stratified,
+                                                        (float)shard_count, denom_dev,
                                                         (long long*)idx, (unsigned long long*)keys, prob);
   } else {
     const bool fat = smem > 100 * 1024;   // one 1024-thread CTA per SM when the staged levels are big
     int threads = fat ? 1024 : 512;
     int blocks = kNumSMs * (fat ? 1 : 4);
-    sample_kernel<2><<<blocks, threads, smem, stream>>>(t, S, st_dev, M, B, u, stratified, (float)shard_count, denom_dev,
+    sample_kernel<2><<<blocks, threads, smem, stream>>>(t, S, st_dev, M, B, u, (const long long*)philox_counter, (unsigned long long)philox_seed, u_out, stratified,
+                                                        (float)shard_count, denom_dev,
                                                         (long long*)idx, (unsigned long long*)keys, prob);
   }
   B200RL_LAUNCH_OK();

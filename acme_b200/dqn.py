@@ -104,9 +104,16 @@ class DQNLearner(core.Learner, core.Saveable):
     # 200 MB and takes the SM slots the latency-bound conv kernels need), so it is off unless asked for
     # With a peer exchange on >= 4 ranks the bucket's kernel is NVLink-bound (1/R of the Adam work) and does hide
     # behind the convolution backward.
-    split_default = '0'   # measured on 8 GPUs: 0.540 ms split vs 0.522 ms unsplit (more barriers, contention)
+    # Single GPU, fused path (round 2): with the update of the fc1 + head bucket limited to 2 CTAs per SM it does hide
+    # under the convolution backward: 0.300 vs 0.318 ms per step (8 CTAs per SM: 0.319; 1, 3, 4: 0.329 / 0.337 / 0.316).
+    # Data parallel (measured on 8 GPUs in round 1): 0.540 ms split vs 0.522 unsplit (more barriers, contention): off.
+    split_default = '1' if (self._world == 1 and self._fused) else '0'
     self._split_adam = (self._concurrent and hasattr(network, 'grad_buckets') and
                         os.environ.get('B200RL_SPLIT_ADAM', split_default) == '1')
+    self._tail_ctas = int(os.environ.get('B200RL_TAIL_ADAM_CTAS', '2'))
+    # one launch ends the step (target copy of parameters + shadow, both counters): single GPU only, where the whole step
+    # is one graph and the counters are bumped in one place
+    self._fuse_tail = self._world == 1 and os.environ.get('B200RL_FUSE_TAIL', '1') != '0'
     self._tail_done = None
     self._side = [torch.cuda.Stream(device=dev) for _ in range(5)] if self._concurrent else None
     self._wmax_done = None
@@ -301,7 +308,8 @@ class DQNLearner(core.Learner, core.Saveable):
     """K1, and in data-parallel mode the local max importance weight: its all-reduce(MAX) (one f64) is issued right
     after this and hides behind the gather and the forward passes."""
     ds = self._dataset
-    ds.sample_only(uniforms)
+    self._bump_in_tail = self._fuse_tail and uniforms is None
+    ds.sample_only(uniforms, bump=not self._fuse_tail)
     if self._world > 1 or self._fused:
       torch = self._torch
       aux = self._side[2] if (self._concurrent and (self._px is not None or self._world == 1)) else None
@@ -466,9 +474,10 @@ class DQNLearner(core.Learner, core.Saveable):
       return
     P, b = self._net.params, 4 * off
     shadow = (P.shadow.data_ptr() + 2 * off) if P.shadow is not None else None      # bf16 dataflow: weights' bf16 copy
-    _capi.call('b200rl_adam', n, _capi.ptr(P.flat) + b, _capi.ptr(P.grad) + b, _capi.ptr(self._m) + b, _capi.ptr(self._v) + b,
-               _capi.ptr(self._num_steps), self._lr, 0.9, 0.999, self._adam_eps, self._eps_mode,
-               _capi.ptr(self._gscale) if self._world > 1 else None, shadow, _capi.current_stream())
+    throttle = self._tail_ctas if (self._split_adam and bucket == 0 and n < P.size) else 0   # beside the conv backward
+    _capi.call('b200rl_adam_throttled', n, _capi.ptr(P.flat) + b, _capi.ptr(P.grad) + b, _capi.ptr(self._m) + b,
+               _capi.ptr(self._v) + b, _capi.ptr(self._num_steps), self._lr, 0.9, 0.999, self._adam_eps, self._eps_mode,
+               _capi.ptr(self._gscale) if self._world > 1 else None, shadow, throttle, _capi.current_stream())
 
   def _adam_tail_async(self):
     """Adam on the fc1 + head bucket on side stream 1 (B200RL_SPLIT_ADAM=1)."""
@@ -515,8 +524,15 @@ class DQNLearner(core.Learner, core.Saveable):
     elif self._replay_client is not None:                       # learning.py:151-154
       self._dataset.table.update_priorities_device(self._dataset.keys, self.priority)
     # learning.py:157-161: copy when num_steps % period == 0, evaluated before the increment
-    self._target_copy()
-    _capi.call('b200rl_step_increment', _capi.ptr(self._num_steps), st)
+    if self._fuse_tail:
+      T = tgt.params
+      sh = P.shadow is not None and T.shadow is not None
+      _capi.call('b200rl_learner_tail', P.size * 4, _capi.ptr(T.flat), _capi.ptr(P.flat), P.size * 2 if sh else 0,
+                 _capi.ptr(T.shadow) if sh else None, _capi.ptr(P.shadow) if sh else None, _capi.ptr(self._num_steps),
+                 self._period, self._copy_phase, _capi.ptr(self._dataset.counter) if self._bump_in_tail else None, st)
+    else:
+      self._target_copy()
+      _capi.call('b200rl_step_increment', _capi.ptr(self._num_steps), st)
     self._stamp(6)
 
   def _target_copy(self):

@@ -530,8 +530,9 @@ class DQNAtariNetwork(Network):
     """Everything behind the fused head + TD kernel (which has produced gbufs['dh'] / ['dval'] / ['dadv']), scheduled on
     three streams: the data-gradient chain fc1 -> conv3 -> conv2 (+ conv1's weight gradient) on the current stream, the
     weight-gradient GEMMs on `s1`, the head's parameter gradients and (bf16 dataflow) the bias-gradient column sums on
-    `s2`.  Workspace lanes 0 / 1 / 2.  `on_dense_done(event_list)` is called once fc1's and the head's gradients have
-    been issued, with the events that mark their completion (a caller may start their optimizer update there)."""
+    `s2`.  Workspace lanes 0 / 1 / 2.  `on_dense_done(event_list)` is called once fc1's and the head's gradients and fc1's
+    data gradient (the last reader of fc1's weights) have been issued, with the events that mark their completion: a
+    caller may start the optimizer update of that bucket there, underneath the convolution backward."""
     import torch
     main = torch.cuda.current_stream()
     flow = self.flow
@@ -558,11 +559,14 @@ class DQNAtariNetwork(Network):
       self._mark('bwd.s2.head_wgrad+fc1_db')
       ev_h = torch.cuda.Event()
       ev_h.record(s2)
-    if on_dense_done is not None:
-      on_dense_done([ev_w, ev_h])
     self.lane(0)
     self._fc1_dgrad(bufs, gbufs)
     self._mark('bwd.fc1_dgrad')
+    if on_dense_done is not None:
+      # fc1's data gradient READS fc1's weights: an optimizer update of that bucket must wait for it too
+      ev_d = torch.cuda.Event()
+      ev_d.record(main)
+      on_dense_done([ev_w, ev_h, ev_d])
     for i in (2, 1):
       fork(s1, s2) if flow else fork(s1)
       with torch.cuda.stream(s1):

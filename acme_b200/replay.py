@@ -507,14 +507,18 @@ class ReplayDataset:
     self.sample_only(uniforms)
     self.gather_only()
 
-  def sample_only(self, uniforms=None):
-    """K1: uniforms -> item indices, keys and probabilities (static buffers)."""
+  def sample_only(self, uniforms=None, bump: bool = True):
+    """K1: uniforms -> item indices, keys and probabilities (static buffers).  Without `uniforms` the draws are K1's own
+    Philox stream keyed by (seed, call counter) -- the values `b200rl_uniform` would write, also stored in `self.u` -- and
+    the counter advances afterwards (`bump=False`: the caller advances it, e.g. fused into the end of a learner step)."""
     stream = _capi.current_stream()
     if uniforms is None:
-      _capi.call('b200rl_uniform', _capi.ptr(self.u), self.B, self.seed, _capi.ptr(self.counter), 0, stream)
-      _capi.call('b200rl_step_increment', _capi.ptr(self.counter), stream)
-    else:
-      self.u.copy_(uniforms)
+      _capi.call('b200rl_replay_sample_philox', self.table.handle, self.B, self.seed, _capi.ptr(self.counter),
+                 int(self.stratified), _capi.ptr(self.u), _capi.ptr(self.idx), _capi.ptr(self.keys), _capi.ptr(self.prob), stream)
+      if bump:
+        _capi.call('b200rl_step_increment', _capi.ptr(self.counter), stream)
+      return
+    self.u.copy_(uniforms)
     self.table.sample_into(self.u, self.idx, self.keys, self.prob, self.stratified)
 
   def gather_only(self, rows=None):

@@ -103,6 +103,10 @@ int b200rl_replay_sample(b200rl_replay* h, int32_t B, const float* u_dev, int st
                          int64_t* idx_dev, uint64_t* keys_dev, float* prob_dev, void* stream);
 /* K3.  Gather (o_tm1, a_tm1, R, D, o_t) for B tree positions; R, D built from the ring with the
  * arithmetic of transition.py:135-145 (fp32, unfused). */
+/* K1 with built-in draws: u_b = Philox4x32-10(seed, *counter_dev)[b], the value b200rl_uniform(seed, counter_dev) writes,
+ * so a captured learner step has no separate draw kernel; u_out_dev (nullable) receives the draws. */
+int b200rl_replay_sample_philox(b200rl_replay* h, int32_t B, uint64_t seed, const int64_t* counter_dev, int stratified,
+                                float* u_out_dev, int64_t* idx_dev, uint64_t* keys_dev, float* prob_dev, void* stream);
 int b200rl_replay_gather(b200rl_replay* h, int32_t B, const int64_t* idx_dev, void* o_tm1_dev,
                          void* a_tm1_dev, float* R_dev, float* D_dev, void* o_t_dev, void* stream);
 /* K2.  TFClient.update_priorities(table, keys, priorities) (dqn/learning.py:151-154): weight =
@@ -200,6 +204,10 @@ int b200rl_dpg_action_grad(int32_t B, int32_t A, const float* dqda, float clip, 
 int b200rl_adam(int64_t n, float* param, const float* grad, float* m, float* v,
                 const int64_t* step_dev, float lr, double b1, double b2, float eps, int eps_mode,
                 const float* grad_scale_dev, void* bf16_shadow, void* stream);
+/* b200rl_adam on a grid limited to ctas_per_sm CTAs per SM (0 = default): for an update issued BESIDE other kernels */
+int b200rl_adam_throttled(int64_t n, float* param, const float* grad, float* m, float* v, const int64_t* step_dev,
+                          float lr, double b1, double b2, float eps, int eps_mode, const float* grad_scale_dev,
+                          void* bf16_shadow, int32_t ctas_per_sm, void* stream);
 /* tf.clip_by_global_norm (d4pg/learning.py:235-237): *scale_out = clip / max(||g||, clip). */
 int b200rl_global_norm_scale(int64_t n, const float* grad, float clip, float* partial_ws,
                              float* scale_out_dev, float* norm_out_dev, void* stream);
@@ -207,6 +215,11 @@ int b200rl_global_norm_scale(int64_t n, const float* grad, float clip, float* pa
 int b200rl_copy_if_period(int64_t n_bytes, void* dst, const void* src, const int64_t* step_dev,
                           int64_t period, int64_t phase, void* stream);
 int b200rl_step_increment(int64_t* step_dev, void* stream);
+/* End of a learner step in ONE launch (dqn/learning.py:157-161): if ((*step_dev + phase) % period == 0) dst_a <- src_a and
+ * dst_b <- src_b (online -> target parameters and their bf16 shadow; n_bytes_b may be 0), then *step_dev += 1 and, if
+ * counter2 != NULL, *counter2 += 1 (the dataset's draw counter).  period = 0: increments only. */
+int b200rl_learner_tail(int64_t n_bytes_a, void* dst_a, const void* src_a, int64_t n_bytes_b, void* dst_b, const void* src_b,
+                        int64_t* step_dev, int64_t period, int64_t phase, int64_t* counter2, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K6.  Network layers (acme/tf/networks/atari.py:36-69, duelling.py:37-59, continuous.py:37-68).
