@@ -215,11 +215,15 @@ hgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     }
   } else if (warp >= 2) {
     // ---------------- epilogue: warp w reads TMEM lanes 32 * (w % 4) ..
+    const int lane_base = (warp & 3) * 32;
+    const int first = row0 + lane_base;
+    auto row_of = [&](int r) -> long long { return first + r < M ? first + r : -1; };
+    uint2 pm[32 / (32 / (BN / 4))];
+    const bool have_pm = !epi.transpose_out && prefetch_relu_mask<BN>(epi, lane, col0, N, row_of, pm);
     if (nkb > 0) {
       mbar_wait(&bar_done, 0);
       tc_fence_after();
     }
-    const int lane_base = (warp & 3) * 32;
     if (epi.transpose_out && !epi.partial) {
       const int row = row0 + lane_base + lane;
 #pragma unroll 1
@@ -235,8 +239,7 @@ hgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     } else {
       float* slab = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw))) + (warp & 3) * 32 * BN;
       stage_accumulator<BN>(tmem_d + ((uint32_t)lane_base << 16), slab, lane, nkb > 0);
-      const int first = row0 + lane_base;
-      store_staged_rows<BN>(epi, slab, lane, col0, N, M, [&](int r) -> long long { return first + r < M ? first + r : -1; });
+      store_staged_rows<BN>(epi, slab, lane, col0, N, M, row_of, have_pm ? pm : nullptr);
     }
   }
   tc_fence_before();
@@ -766,9 +769,6 @@ hconv_dgrad_kernel(const __grid_constant__ HDgradMaps maps, const __grid_constan
       if (i == nkb - 1) umma_commit(&bar_done);
     }
   } else if (warp >= 2) {
-    mbar_wait(&bar_done, 0);
-    if (tid == 64) h_mark(4, mark_cta);
-    tc_fence_after();
     const int lane_base = (warp & 3) * 32;
     const int row = row0 + lane_base + lane;
     long long orow = -1;
@@ -777,10 +777,16 @@ hconv_dgrad_kernel(const __grid_constant__ HDgradMaps maps, const __grid_constan
       const int jy = t % ph.cnt_y, b = t / ph.cnt_y;
       orow = ((long long)b * P.H + (ph.iy0 + P.stride * jy)) * P.W + (ph.ix0 + P.stride * jx);
     }
+    auto row_of = [&](int r) -> long long { return __shfl_sync(0xffffffffu, orow, r); };
+    uint2 pm[32 / (32 / (BN / 4))];
+    const bool have_pm = prefetch_relu_mask<BN>(epi, lane, 0, P.C, row_of, pm);   // in flight while the MMAs run
+    mbar_wait(&bar_done, 0);
+    if (tid == 64) h_mark(4, mark_cta);
+    tc_fence_after();
     float* slab = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw))) + (warp & 3) * 32 * BN;
     stage_accumulator<BN>(tmem_d + ((uint32_t)lane_base << 16), slab, lane, true);
     if (tid == 64) h_mark(5, mark_cta);
-    store_staged_rows<BN>(epi, slab, lane, 0, P.C, 0, [&](int r) -> long long { return __shfl_sync(0xffffffffu, orow, r); });
+    store_staged_rows<BN>(epi, slab, lane, 0, P.C, 0, row_of, have_pm ? pm : nullptr);
     if (tid == 64) h_mark(6, mark_cta);
   }
   tc_fence_before();

@@ -222,9 +222,31 @@ __device__ __forceinline__ float4 staged_chunk(const float* slab, int r, int c) 
 // Row-wise epilogue over a staged slab: lane -> (row lane, 16-byte column chunk); four rows are in flight at a time
 // (their shared-memory reads and mask loads are issued before any is consumed: one warp per scheduler has nothing
 // else to hide latency with).  dst_row(r) -> destination row of slab row r, or < 0 to skip; it is called by all lanes.
+// The ReLU-derivative mask of a data gradient is the producer layer's OUTPUT: it does not depend on the accumulator, so the
+// epilogue warps fetch it into registers BEFORE they wait for the MMAs (a CTA's timeline showed the masked store phase
+// taking 3-5 us of a 6-10 us tile: four rounds of dependent mask loads).  bf16 masks, ReLU only; `pm[it]` belongs to the
+// same (row, column chunk) that iteration `it` of store_staged_rows handles.  Returns false (warp-uniform) if the
+// fast-path conditions do not hold: store_staged_rows then loads the mask itself.
+template <int BN, class RowFn>
+__device__ __forceinline__ bool prefetch_relu_mask(const Epilogue& e, int lane, int col0, int N, RowFn dst_row,
+                                                   uint2 (&pm)[32 / (32 / (BN / 4))]) {
+  constexpr int CPR = BN / 4, RPI = 32 / CPR, ITERS = 32 / RPI;
+  const int c = lane % CPR, rl = lane / CPR, col = col0 + 4 * c;
+  const bool ok = e.mask && e.mask_bf16 && !e.partial && e.mask_act == B200RL_ACT_RELU && col + 3 < N && (e.ldmask & 3) == 0 &&
+                  ((uintptr_t)e.mask & 7) == 0;
+  if (!__all_sync(0xffffffffu, ok)) return false;
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const long long row = dst_row(it * RPI + rl);
+    pm[it] = row >= 0 ? __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(e.mask) + (size_t)row * e.ldmask + col))
+                      : make_uint2(0u, 0u);
+  }
+  return true;
+}
+
 template <int BN, class RowFn>
 __device__ __forceinline__ void store_staged_rows(const Epilogue& e, const float* slab, int lane, int col0, int N, int M,
-                                                  RowFn dst_row) {
+                                                  RowFn dst_row, const uint2* pm = nullptr) {
   constexpr int CPR = BN / 4, RPI = 32 / CPR, ITERS = 32 / RPI, G = 4;
   const int c = lane % CPR, rl = lane / CPR, col = col0 + 4 * c;
   float* const base = e.partial ? e.partial + (size_t)blockIdx.z * M * N : e.out;
@@ -264,7 +286,15 @@ __device__ __forceinline__ void store_staged_rows(const Epilogue& e, const float
       rows[g] = dst_row(r);
       a[g] = staged_chunk<BN>(slab, r, c);
     }
-    if (use_mask) {
+    if (use_mask && pm) {   // fetched ahead of the accumulator (prefetch_relu_mask)
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const uint2 t = pm[it + g];
+        const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+        const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+        m[g] = make_float4(lo.x, lo.y, hi.x, hi.y);
+      }
+    } else if (use_mask) {
 #pragma unroll
       for (int g = 0; g < G; ++g) {
         if (rows[g] < 0) continue;

@@ -104,10 +104,12 @@ class DQNLearner(core.Learner, core.Saveable):
     # 200 MB and takes the SM slots the latency-bound conv kernels need), so it is off unless asked for
     # With a peer exchange on >= 4 ranks the bucket's kernel is NVLink-bound (1/R of the Adam work) and does hide
     # behind the convolution backward.
-    # Single GPU, fused path (round 2): with the update of the fc1 + head bucket limited to 2 CTAs per SM it does hide
-    # under the convolution backward: 0.300 vs 0.318 ms per step (8 CTAs per SM: 0.319; 1, 3, 4: 0.329 / 0.337 / 0.316).
-    # Data parallel (measured on 8 GPUs in round 1): 0.540 ms split vs 0.522 unsplit (more barriers, contention): off.
-    split_default = '1' if (self._world == 1 and self._fused) else '0'
+    # Round 2, single GPU, fused path: the update of the fc1 + head bucket throttled to 2 CTAs per SM underneath the
+    # convolution backward (it must start after fc1's data gradient, the last reader of fc1's weights): 0.336 ms per step
+    # against 0.317 unsplit (3 CTAs per SM: 0.322; 1: 0.384) -- the throttled update is slow and still takes SM slots
+    # and L2 bandwidth from the latency-bound conv kernels.  (A first measurement of 0.300 ms started the update BEFORE
+    # fc1's data gradient had finished -- a race -- and is void.)  Data parallel, 8 GPUs (round 1): 0.540 split vs 0.522.
+    split_default = '0'
     self._split_adam = (self._concurrent and hasattr(network, 'grad_buckets') and
                         os.environ.get('B200RL_SPLIT_ADAM', split_default) == '1')
     self._tail_ctas = int(os.environ.get('B200RL_TAIL_ADAM_CTAS', '2'))

@@ -66,20 +66,26 @@ def _worker(rank, world, port, q):
 
     # ---- whole learner: peer exchange vs NCCL path, same seeds
     import helpers
-    losses = {}
-    for mode in (True, False):
-      pair = helpers.make_dqn_dp_learner(rank, world, dist.group.WORLD, peer_exchange=mode)
-      ls = []
-      for _ in range(6):
-        pair.step(fetch_loss=False)
-        ls.append(float(pair.loss))
-      dp.assert_replicated(pair._net.params.flat)
-      if pair._px is not None:
-        pair._px.check()
-      losses[mode] = ls
-      if pair._px is not None:
-        pair._px.close()
-    np.testing.assert_allclose(losses[True], losses[False], rtol=2e-3)
+    for precision in (0, 2):      # fp32 parity mode and the benchmarked bf16 dataflow (fused head, batched online pass, shadows)
+      losses = {}
+      for mode in (True, False):
+        pair = helpers.make_dqn_dp_learner(rank, world, dist.group.WORLD, peer_exchange=mode, precision=precision)
+        ls = []
+        for _ in range(6):
+          pair.step(fetch_loss=False)
+          ls.append(float(pair.loss))
+        pair.flush()                # pipelined exchange: apply the update still in flight (collective)
+        torch.cuda.synchronize()
+        dp.assert_replicated(pair._net.params.flat)
+        if precision == 2:          # every rank's bf16 weight shadow follows the exchanged parameters
+          P = pair._net.params
+          assert torch.equal(P.shadow, P.flat.to(torch.bfloat16)), 'bf16 shadow out of step with the parameters'
+        if pair._px is not None:
+          pair._px.check()
+        losses[mode] = ls
+        if pair._px is not None:
+          pair._px.close()
+      np.testing.assert_allclose(losses[True], losses[False], rtol=2e-3 if precision == 0 else 2e-2)
     q.put((rank, 'ok'))
   except Exception as e:   # pragma: no cover
     import traceback
