@@ -92,9 +92,18 @@ __device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, con
   v = __fadd_rn(__fmul_rn(c.b2, v), __fmul_rn(c.omb2, __fmul_rn(gj, gj)));
   m = fabsf(m) < 1.17549435e-38f ? 0.f : m;   // subnormal moments: see adam_one in learner_math.cu
   v = v < 1.17549435e-38f ? 0.f : v;
+  // exact zeros: harmless substitute operands + selects instead of the IEEE slow paths (see adam_one)
+  const bool vz = v == 0.f, mz = m == 0.f;
+  const float v_in = vz ? 1.f : v, m_in = mz ? 1.f : m;
   float upd;
-  if (c.eps_mode == 0) upd = __fdiv_rn(__fdiv_rn(m, c.bc1), __fadd_rn(__fsqrt_rn(__fdiv_rn(v, c.bc2)), c.eps));
-  else upd = __fdiv_rn(__fmul_rn(c.k1, m), __fadd_rn(__fsqrt_rn(v), c.eps));
+  if (c.eps_mode == 0) {
+    const float root = vz ? 0.f : __fsqrt_rn(__fdiv_rn(v_in, c.bc2));
+    upd = __fdiv_rn(__fdiv_rn(m_in, c.bc1), __fadd_rn(root, c.eps));
+  } else {
+    const float root = vz ? 0.f : __fsqrt_rn(v_in);
+    upd = __fdiv_rn(__fmul_rn(c.k1, m_in), __fadd_rn(root, c.eps));
+  }
+  upd = mz ? 0.f : upd;
   p = __fsub_rn(p, __fmul_rn(c.lr, upd));
 }
 

@@ -466,6 +466,17 @@ static int launch_h(const CUtensorMap& ma, const CUtensorMap& mb, Epilogue epi, 
   const int kps = ceil_div(kblocks, splits);
   splits = ceil_div(kblocks, kps);
   epi.partial = splits > 1 ? (float*)ws : nullptr;
+  {
+    // The one case where the persistent kernel wins inside the step (measured): a convolution with SMALL resident
+    // weights and thousands of tiles -- conv1: 16 KB of weights, 1764 / 882 tiles of 8 k-blocks; its persistent CTAs
+    // need ~65 KB of shared memory, three fit on an SM and still leave room for the other streams' kernels
+    // (target-pass conv1: 15-16 us against 26-28 us).  B200RL_PERSISTENT_SMALL=0 switches it off.
+    static const int small_on = getenv("B200RL_PERSISTENT_SMALL") ? atoi(getenv("B200RL_PERSISTENT_SMALL")) : 1;
+    const int res_b = ceil_div(K, KE) * BN * KE * 2;
+    if (AM == 0 && BM == 0 && small_on && conv.enabled && splits == 1 && ceil_div(N, BN) == 1 && !epi.transpose_out &&
+        tiles >= 4 * kNumSMs && 4 * HBM_ROWS * KE * 2 + HBM_ROWS * BN * 4 + res_b <= 72 * 1024)
+      return launch_h_pers<KE, BM, BN, true>(ma, mb, epi, M, N, K, kps, splits, res_b, stream, conv);
+  }
   if (AM == 0 && use_persistent() && !epi.transpose_out && tiles * splits >= 3 * kNumSMs / 2) {
     // many small tiles: walk them with persistent CTAs; convolution weights (<= 80 KB) stay resident in shared memory
     const int res_b = ceil_div(K, KE) * BN * KE * 2;

@@ -260,9 +260,21 @@ __device__ __forceinline__ float adam_one(float& p, float g, float& m, float& v,
   // 55 to 88 us after 3000 updates).  Flushing |m|, v < FLT_MIN to zero changes the update by < 1e-30.
   m = fabsf(m) < 1.17549435e-38f ? 0.f : m;
   v = v < 1.17549435e-38f ? 0.f : v;
+  // Exact zeros (weights of dead units keep g = m = v = 0 for good) would send the IEEE square root and division down
+  // their slow paths -- a warp takes the slow path if ANY lane needs it; measured: 62.7 us for the 8M-parameter pass with
+  // 70% zero moments against 41.9 us without (tools/adam_micro.py).  Substitute harmless operands and select the exact
+  // results afterwards (sqrt(0) = 0, 0 / x = 0): bit-identical values, no slow path.
+  const bool vz = v == 0.f, mz = m == 0.f;
+  const float v_in = vz ? 1.f : v, m_in = mz ? 1.f : m;
   float upd;
-  if (c.eps_mode == 0) upd = __fdiv_rn(__fdiv_rn(m, c.bc1), __fadd_rn(__fsqrt_rn(__fdiv_rn(v, c.bc2)), c.eps));
-  else upd = __fdiv_rn(__fmul_rn(c.k1, m), __fadd_rn(__fsqrt_rn(v), c.eps));
+  if (c.eps_mode == 0) {
+    const float root = vz ? 0.f : __fsqrt_rn(__fdiv_rn(v_in, c.bc2));
+    upd = __fdiv_rn(__fdiv_rn(m_in, c.bc1), __fadd_rn(root, c.eps));
+  } else {
+    const float root = vz ? 0.f : __fsqrt_rn(v_in);
+    upd = __fdiv_rn(__fmul_rn(c.k1, m_in), __fadd_rn(root, c.eps));
+  }
+  upd = mz ? 0.f : upd;
   p = __fsub_rn(p, __fmul_rn(c.lr, upd));
   return p;
 }

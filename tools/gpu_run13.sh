@@ -1,0 +1,9 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+echo "--- adam"; timeout 120 python tools/adam_micro.py 2>&1 | tail -7
+timeout 600 python -m pytest tests/test_gpu_bf16_layers.py tests/test_gpu_learner.py -q --tb=short -k "bf16 or c2_shape or atari_network or learner_steps or adam" > gpurun_out/run13_tests.log 2>&1; echo "tests rc=$?"; tail -6 gpurun_out/run13_tests.log
+run() { name=$1; shift; env "$@" timeout 600 python bench.py --steps 1000 --warmup 20 --precision bf16 --no-cpu-baseline > gpurun_out/run13_bench_$name.json 2> gpurun_out/run13_bench_$name.err; echo "bench $name rc=$? $(python -c "import json;d=json.load(open('gpurun_out/run13_bench_$name.json'));print(round(d['value'],1), round(d['ms_per_step'],4), round(d['e2e']['value'],1), {k:round(v,1) for k,v in d['stages_us'].items()})" 2>&1 | tail -1)"; tail -2 gpurun_out/run13_bench_$name.err; }
+run default X=1
+run nosmallpers B200RL_PERSISTENT_SMALL=0
+B200RL_FINE=1 timeout 300 python tools/step_phases.py bf16 > gpurun_out/run13_phases.log 2>&1; tail -32 gpurun_out/run13_phases.log
