@@ -408,3 +408,62 @@ def test_frame_dedup_ring_rebuilds_stacks(hw, n_step, max_size):
   seg = table._segment(0)
   assert seg.numel() == table.slot_capacity * (-(-(hw * hw) // 16) * 16)
   server.stop()
+
+
+def test_concurrent_actor_threads_feed_one_table():
+  """SURVEY §8f-4 (async actor feed): several actor threads, each with its own adder / writer, insert into ONE table
+  while the learner thread flushes and samples -- Reverb's server is thread-safe and Acme runs actors against it
+  concurrently; here every C entry point takes the shard's lock.  Observations encode (actor, episode, t), so every
+  gathered n-step window can be checked: same actor, same episode, o_t exactly `len` steps after o_tm1, R / D the n-step
+  values of that stretch."""
+  import threading
+  torch = _torch()
+  import helpers
+  from acme_b200 import adders, dm_env, replay
+  n_step, A, actors, episodes, T = 3, 4, 3, 25, 17
+  spec, table, server, adder0, _ = helpers.make_pair((4,), np.float32, A, n_step, 0.5, 0.6, max_size=5000)
+  errors = []
+
+  def actor(aid):
+    try:
+      ad = adders.NStepTransitionAdder(replay.Client(server), n_step=n_step, discount=0.5)
+      for ep in range(episodes):
+        ad.add_first(dm_env.restart(np.array([aid, ep, 0, 0], np.float32)))
+        for t in range(1, T + 1):
+          last = t == T
+          ts = dm_env.TimeStep(dm_env.StepType.LAST if last else dm_env.StepType.MID, np.float32(t), np.float32(0. if last else 1.),
+                               np.array([aid, ep, t, 0], np.float32))
+          ad.add(np.int32(t % A), ts)
+    except Exception as e:   # pragma: no cover
+      errors.append(e)
+
+  threads = [threading.Thread(target=actor, args=(i,)) for i in range(actors)]
+  for th in threads:
+    th.start()
+  B = 64
+  ds = None
+  seen = 0
+  while any(th.is_alive() for th in threads) or seen < 20:
+    table.flush()
+    if table.size >= 1:
+      ds = ds or replay.ReplayDataset(table, B, seed=3)
+      ds.sample_raw()
+      torch.cuda.synchronize()
+      o0 = ds.o_tm1.view(torch.float32).view(B, 4).cpu().numpy()
+      o1 = ds.o_t.view(torch.float32).view(B, 4).cpu().numpy()
+      R, D = ds.R.cpu().numpy(), ds.D.cpu().numpy()
+      np.testing.assert_array_equal(o0[:, :2], o1[:, :2])                       # same actor, same episode
+      length = (o1[:, 2] - o0[:, 2]).astype(int)
+      assert ((length >= 1) & (length <= n_step)).all()
+      for b in range(B):   # n-step return of rewards t0+1 .. t0+len with discount 0.5 and env discounts 1 (0 at the end)
+        t0, ln = int(o0[b, 2]), int(length[b])
+        want_R = sum((0.5**j) * (t0 + 1 + j) for j in range(ln))
+        want_D = (0.5**(ln - 1)) * (0. if t0 + ln == T else 1.)
+        assert abs(R[b] - want_R) < 1e-5 and abs(D[b] - want_D) < 1e-7, (b, t0, ln, R[b], want_R, D[b], want_D)
+      seen += 1
+  for th in threads:
+    th.join()
+  assert not errors, errors
+  table.flush()
+  assert table.size == actors * episodes * (T + n_step - 1)
+  server.stop()
