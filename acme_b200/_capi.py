@@ -52,6 +52,7 @@ PROTOTYPES = {
     'b200rl_replay_sample_philox': (c_int, [c_vp, c_i32, c_u64, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'b200rl_replay_gather': (c_int, [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'b200rl_replay_gather_rows': (c_int, [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.POINTER(ConvGeom), c_vp]),
+    'b200rl_replay_gather_sequences': (c_int, [c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'b200rl_replay_update_priorities': (c_int, [c_vp, c_i32, c_vp, c_vp, c_vp]),
     'b200rl_replay_info': (c_int, [c_vp, C.POINTER(c_i64), C.POINTER(c_u64), C.POINTER(c_u64),
                                    C.POINTER(c_f32), c_vp]),
@@ -69,6 +70,8 @@ PROTOTYPES = {
     'b200rl_dqn_td': (c_int, [c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_f32,
                               c_f64, c_f32, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp]),
     'b200rl_is_weight_max': (c_int, [c_i32, c_vp, c_f64, c_vp, c_i32, c_vp]),
+    'b200rl_seq_priority': (c_int, [c_i32, c_i32, c_vp, C.c_float, c_vp, c_vp]),
+    'b200rl_seq_is_weights': (c_int, [c_i32, c_vp, c_f64, c_f64, c_vp, c_vp]),
     'b200rl_c51_loss': (c_int, [c_i32, c_i32, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_f32, c_f32,
                                 c_vp, c_vp, c_vp, c_vp, c_vp]),
     'b200rl_td_learning': (c_int, [c_i32, c_vp, c_vp, c_vp, c_vp, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -134,6 +137,9 @@ PROTOTYPES = {
     'b200rl_dp_max_f64': (c_int, [c_vp, c_vp, c_vp, c_vp]),
     'b200rl_dp_adam': (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, C.c_float, C.c_double, C.c_double, C.c_float, c_int,
                                c_i32, c_i32, c_vp]),
+    'b200rl_dp_reduce_adam_ce': (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, C.c_float, C.c_double, C.c_double, C.c_float, c_int,
+                                 c_i32, c_vp, c_i32, c_vp]),
+    'b200rl_dp_broadcast_ce': (c_int, [c_vp, c_i64, c_i64, c_vp, c_i32, c_i32, c_vp]),
     'b200rl_dp_status': (c_int, [c_vp]),
 }
 

@@ -1,5 +1,9 @@
 """Adders: the actor-side insert seam (`acme/adders/base.py:24-82`).
 
+`SequenceAdder` (`acme/adders/reverb/sequence.py:29-127`) uses the same ring: every step is appended once
+and an item is "the last `sequence_length` steps"; the episode's final step and its zero padding are appended as
+ordinary steps, and K3's sequence form (`b200rl_replay_gather_sequences`) copies the T rows of a sampled item.
+
 `NStepTransitionAdder` keeps the reference's constructor, `add_first / add / reset` protocol,
 error behaviour and item bookkeeping (`acme/adders/reverb/base.py:62-176`,
 `acme/adders/reverb/transition.py:87-190`), but it does NOT materialise transitions on the host:
@@ -205,3 +209,80 @@ class NStepTransitionAdder(ReverbAdder):
     if extras_spec:
       sig.append(extras_spec)
     return tuple(sig)
+
+
+class SequenceAdder(ReverbAdder):
+  """`acme/adders/reverb/sequence.py:29-127`: fixed-length (possibly overlapping) sequences for recurrent learners."""
+
+  def __init__(self, client, sequence_length: int, period: int, delta_encoded: bool = False,
+               chunk_length: Optional[int] = None, priority_fns: Optional[PriorityFnMapping] = None,
+               pad_end_of_episode: bool = True):
+    super().__init__(client=client, buffer_size=sequence_length, max_sequence_length=sequence_length,
+                     delta_encoded=delta_encoded, chunk_length=chunk_length, priority_fns=priority_fns)
+    self._period = period
+    self._step = 0
+    self._pad_end_of_episode = pad_end_of_episode
+    for name in self._priority_fns:
+      server = getattr(self._client, 'server', None)
+      t = getattr(server, 'tables', {}).get(name) if server is not None else None
+      if t is not None and t.max_window < sequence_length:
+        raise ValueError(f'table {name!r} supports windows up to {t.max_window} < sequence_length {sequence_length}')
+
+  def reset(self):
+    self._step = 0
+    super().reset()
+
+  def _append_step(self, step: Step, next_observation):
+    self._writer.append_step(step.observation, step.action, step.reward, step.discount, next_observation,
+                             extras=step.extras, tables=list(self._priority_fns),
+                             start_of_episode=step.start_of_episode)
+
+  def _write(self):
+    # the step itself went into the ring in _append_step (sequence.py:77-81)
+    self._step += 1
+    self._maybe_add_priorities()
+
+  def _write_last(self):
+    # sequence.py:83-108: the final observation becomes a step of its own with zero action / reward / discount /
+    # extras, then (optionally) all-zero steps up to the next point at which a sequence is due
+    first = self._buffer[0]
+    zeros = lambda x: tree.map_structure(lambda v: np.zeros_like(np.asarray(v)), x)
+    final = Step(self._next_observation, zeros(first.action), zeros(first.reward), zeros(first.discount), False,
+                 zeros(first.extras))
+    zero_obs = zeros(self._next_observation)
+    self._buffer.append(final)
+    self._append_step(final, zero_obs)
+    self._step += 1
+    if self._pad_end_of_episode:
+      zero_step = final._replace(observation=zero_obs)
+      if self._step <= self._max_sequence_length:
+        padding = self._max_sequence_length - self._step
+      else:
+        padding = self._period - (self._step - self._max_sequence_length)
+      for _ in range(padding):
+        self._buffer.append(zero_step)
+        self._append_step(zero_step, zero_obs)
+        self._step += 1
+    self._maybe_add_priorities()
+
+  def _maybe_add_priorities(self):
+    # sequence.py:110-127
+    L = self._max_sequence_length
+    if not (self._step == L or (self._step > L and (self._step - L) % self._period == 0)):
+      return
+    steps = list(self._buffer)
+    if self._default_priorities:
+      priorities = {t: 1. for t in self._priority_fns}
+    else:
+      fn_input = PriorityFnInput(*[_stack([s[i] for s in steps]) for i in range(6)])
+      priorities = {t: float(fn(fn_input)) for t, fn in self._priority_fns.items()}
+    for table, priority in priorities.items():
+      self._writer.create_item(table=table, num_timesteps=len(steps), priority=priority)
+
+  @classmethod
+  def signature(cls, environment_spec: specs.EnvironmentSpec, extras_spec=()):
+    """The per-step spec of a sequence table: a `Step` of specs (what later Acme versions' SequenceAdder.signature
+    returns, minus the leading time axis)."""
+    return Step(observation=environment_spec.observations, action=environment_spec.actions,
+                reward=environment_spec.rewards, discount=environment_spec.discounts,
+                start_of_episode=specs.Array((), np.bool_), extras=extras_spec)

@@ -23,6 +23,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace b200rl {
@@ -53,6 +55,8 @@ struct DpState {
   size_t region_bytes;
   void* opened[kMaxRanks];   // peer regions from cudaIpcOpenMemHandle
   DpPeers peers;
+  float* scratch;            // copy-engine exchange: the peers' gradient shards land here ([world][chunk], lazily allocated)
+  size_t scratch_floats;
 };
 
 static size_t params_bytes(int64_t n) { return ((size_t)n * 4 + 255) & ~(size_t)255; }
@@ -215,6 +219,82 @@ dp_adam_kernel(DpPeers peers, int world, int rank, long long off, long long n, l
   }
 }
 
+// ---- Copy-engine form of the exchange.  The SM-issued kernel above needs ~450 resident CTAs to keep NVLink busy, and
+// while they are resident the latency-bound GEMM / convolution kernels of the step cannot get their SM slots (measured
+// on 2 GPUs: the target forward stalls from 15 to 94 us while the exchange runs).  Here the bulk bytes move by DMA
+// (cudaMemcpyAsync between the peer-mapped regions: graph memcpy nodes, no SM), and the SMs only run
+//   dp_flag_kernel       one warp: announce (grads_ready / params_done) to every peer, optionally wait for all peers
+//   dp_adam_local_kernel the owner's shard: sum of R gradient shards in rank order (own one in place, the others from the
+//                        landing buffer), x 1/R, Adam, bf16 shadow -- the same arithmetic, in the same order, as
+//                        dp_adam_kernel, so both forms produce bit-identical parameters.
+__global__ void dp_flag_kernel(DpPeers peers, int world, int rank, const long long* __restrict__ step_dev, int bucket,
+                               int which, int wait) {
+  if (threadIdx.x != 0) return;
+  Mailbox* mine = peers.mail[rank];
+  const long long epoch = *step_dev + 1;
+  __threadfence_system();
+  for (int j = 0; j < world; ++j) {
+    if (which == 0) peers.mail[j]->grads_ready[bucket][rank] = epoch;
+    else peers.mail[j]->params_done[bucket][rank] = epoch;
+  }
+  if (wait) wait_all(which == 0 ? mine->grads_ready[bucket] : mine->params_done[bucket], world, epoch, &mine->error);
+  __threadfence_system();
+}
+
+template <int W>
+__global__ void __launch_bounds__(256)
+dp_adam_local_kernel(float* __restrict__ params, const float* __restrict__ grads, const float* __restrict__ landing,
+                     int world, int rank, long long s0, long long len, long long chunk, float* __restrict__ m,
+                     float* __restrict__ v, __nv_bfloat16* __restrict__ shadow, const long long* __restrict__ step_dev,
+                     float lr, double b1, double b2, float eps, int eps_mode) {
+  __shared__ AdamC c;
+  if (threadIdx.x == 0) {
+    const double t = (double)(*step_dev + 1);
+    c.bc1 = (float)(1.0 - pow(b1, t)); c.bc2 = (float)(1.0 - pow(b2, t));
+    c.b1 = (float)b1; c.b2 = (float)b2; c.omb1 = (float)(1.0 - b1); c.omb2 = (float)(1.0 - b2);
+    c.k1 = sqrtf(c.bc2) / c.bc1; c.lr = lr; c.eps = eps; c.gs = 1.f / (float)world; c.eps_mode = eps_mode;
+  }
+  __syncthreads();
+  const long long lenv = len & ~3ll;
+  for (long long k = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; k < lenv; k += (long long)gridDim.x * blockDim.x * 4) {
+    const long long i = s0 + k;
+    float4 g;
+#pragma unroll
+    for (int j = 0; j < W; ++j)
+      if (j < world) {
+        const float4 x = j == rank ? *reinterpret_cast<const float4*>(grads + i)
+                                   : *reinterpret_cast<const float4*>(landing + (long long)j * chunk + k);
+        if (j == 0) g = x;
+        else { g.x = __fadd_rn(g.x, x.x); g.y = __fadd_rn(g.y, x.y); g.z = __fadd_rn(g.z, x.z); g.w = __fadd_rn(g.w, x.w); }
+      }
+    float4 p = *reinterpret_cast<const float4*>(params + i);
+    float4 mm = *reinterpret_cast<const float4*>(m + i), vv = *reinterpret_cast<const float4*>(v + i);
+    adam1(p.x, g.x, mm.x, vv.x, c); adam1(p.y, g.y, mm.y, vv.y, c);
+    adam1(p.z, g.z, mm.z, vv.z, c); adam1(p.w, g.w, mm.w, vv.w, c);
+    *reinterpret_cast<float4*>(m + i) = mm;
+    *reinterpret_cast<float4*>(v + i) = vv;
+    *reinterpret_cast<float4*>(params + i) = p;
+    if (shadow) {
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(p.x, p.y), hi = __floats2bfloat162_rn(p.z, p.w);
+      uint2 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&lo); o.y = *reinterpret_cast<const uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(shadow + i) = o;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (int)(len - lenv)) {   // ragged end of the bucket (< 4 floats)
+    const long long k = lenv + threadIdx.x, i = s0 + k;
+    float g = 0.f;
+    for (int j = 0; j < world; ++j) {
+      const float x = j == rank ? grads[i] : landing[(long long)j * chunk + k];
+      g = j == 0 ? x : __fadd_rn(g, x);
+    }
+    float p = params[i], mm = m[i], vv = v[i];
+    adam1(p, g, mm, vv, c);
+    m[i] = mm; v[i] = vv; params[i] = p;
+    if (shadow) shadow[i] = __float2bfloat16_rn(p);
+  }
+}
+
 // all-reduce(MAX) of one double per rank: each rank drops (value, epoch) into every peer's mailbox
 __global__ void dp_max_kernel(DpPeers peers, int world, int rank, double* __restrict__ value, const long long* __restrict__ step_dev) {
   if (threadIdx.x != 0) return;
@@ -249,6 +329,9 @@ extern "C" int b200rl_dp_create(b200rl_dp_t* out, const b200rl_dp_cfg* cfg) {
   cudaError_t e = cudaMalloc(&s->region, s->region_bytes);
   if (e != cudaSuccess) { delete s; set_error("cudaMalloc(%zu): %s", s->region_bytes, cudaGetErrorString(e)); return B200RL_ECUDA; }
   B200RL_CUDA_OK(cudaMemset(s->region, 0, s->region_bytes));
+  // landing buffer of the copy-engine exchange: R shards of ceil(n / R) floats rounded up to 4, for any bucket
+  s->scratch_floats = (size_t)s->n + 4 * kMaxRanks;
+  B200RL_CUDA_OK(cudaMalloc((void**)&s->scratch, s->scratch_floats * 4));
   B200RL_CUDA_OK(cudaDeviceSynchronize());
   s->peers.params[s->rank] = (float*)s->region;
   s->peers.grads[s->rank] = (float*)((char*)s->region + pb);
@@ -264,6 +347,7 @@ extern "C" int b200rl_dp_destroy(b200rl_dp_t h) {
   for (int j = 0; j < s->world; ++j)
     if (s->opened[j]) cudaIpcCloseMemHandle(s->opened[j]);
   if (s->region) cudaFree(s->region);
+  if (s->scratch) cudaFree(s->scratch);
   delete s;
   return B200RL_OK;
 }
@@ -343,6 +427,71 @@ extern "C" int b200rl_dp_adam(b200rl_dp_t h, int64_t off, int64_t n, float* m, f
   }
   if (s->world <= 2) DP_LAUNCH(2, 2) else if (s->world <= 4) DP_LAUNCH(4, 2) else DP_LAUNCH(8, 2)
 #undef DP_LAUNCH
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+
+// ---- copy-engine exchange (see dp_flag_kernel)
+static void dp_shard(const DpState* s, int64_t off, int64_t n, int r, long long* chunk_out, long long* s0, long long* len) {
+  long long chunk = (n + s->world - 1) / s->world;
+  chunk = (chunk + 3) & ~3ll;
+  *chunk_out = chunk;
+  *s0 = off + (long long)r * chunk;
+  *len = std::max<long long>(0, std::min<long long>(off + n, *s0 + chunk) - *s0);
+}
+
+extern "C" int b200rl_dp_reduce_adam_ce(b200rl_dp_t h, int64_t off, int64_t n, float* m, float* v, const int64_t* step_dev,
+                                        float lr, double b1, double b2, float eps, int eps_mode, int32_t bucket,
+                                        void* shadow_bf16, int32_t max_ctas, void* stream) {
+  DpState* s = (DpState*)h;
+  B200RL_REQUIRE(s && m && v && step_dev, "null argument");
+  B200RL_REQUIRE(off >= 0 && n >= 1 && off + n <= s->n && off % 4 == 0, "bad bucket range");
+  B200RL_REQUIRE(bucket >= 0 && bucket < kBuckets && (eps_mode == 0 || eps_mode == 1), "bad argument");
+  B200RL_REQUIRE((((uintptr_t)m | (uintptr_t)v) & 15) == 0 && ((uintptr_t)shadow_bf16 & 7) == 0, "misaligned buffers");
+  if (int rc = dp_ready(s)) return rc;
+  long long chunk, s0, len;
+  dp_shard(s, off, n, s->rank, &chunk, &s0, &len);
+  B200RL_REQUIRE(s->scratch_floats >= (size_t)chunk * s->world, "landing buffer too small");   // sized in dp_create
+  cudaStream_t st = as_stream(stream);
+  dp_flag_kernel<<<1, 32, 0, st>>>(s->peers, s->world, s->rank, (const long long*)step_dev, bucket, 0, 1);
+  B200RL_LAUNCH_OK();
+  if (len > 0) {
+    for (int d = 1; d < s->world; ++d) {   // start with the next rank: the peers' copy engines are hit evenly
+      const int j = (s->rank + d) % s->world;
+      B200RL_CUDA_OK(cudaMemcpyAsync(s->scratch + (size_t)j * chunk, s->peers.grads[j] + s0, (size_t)len * 4,
+                                     cudaMemcpyDeviceToDevice, st));
+    }
+    const long long vec = (len + 3) / 4;
+    int blocks = (int)std::max<long long>(1, std::min<long long>((vec + 255) / 256, 4ll * kNumSMs));
+    if (max_ctas > 0) blocks = std::min(blocks, (int)max_ctas);
+#define DP_LOCAL(W_)                                                                                                    \
+    dp_adam_local_kernel<W_><<<blocks, 256, 0, st>>>(s->peers.params[s->rank], s->peers.grads[s->rank], s->scratch, s->world, \
+                                                    s->rank, s0, len, chunk, m, v, (__nv_bfloat16*)shadow_bf16,           \
+                                                    (const long long*)step_dev, lr, b1, b2, eps, eps_mode)
+    if (s->world <= 2) DP_LOCAL(2); else if (s->world <= 4) DP_LOCAL(4); else DP_LOCAL(8);
+#undef DP_LOCAL
+    B200RL_LAUNCH_OK();
+  }
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_dp_broadcast_ce(b200rl_dp_t h, int64_t off, int64_t n, const int64_t* step_dev, int32_t bucket,
+                                      int32_t final_barrier, void* stream) {
+  DpState* s = (DpState*)h;
+  B200RL_REQUIRE(s && step_dev, "null argument");
+  B200RL_REQUIRE(off >= 0 && n >= 1 && off + n <= s->n && off % 4 == 0, "bad bucket range");
+  B200RL_REQUIRE(bucket >= 0 && bucket < kBuckets, "bad argument");
+  if (int rc = dp_ready(s)) return rc;
+  long long chunk, s0, len;
+  dp_shard(s, off, n, s->rank, &chunk, &s0, &len);
+  cudaStream_t st = as_stream(stream);
+  if (len > 0)
+    for (int d = 1; d < s->world; ++d) {
+      const int j = (s->rank + d) % s->world;
+      B200RL_CUDA_OK(cudaMemcpyAsync(s->peers.params[j] + s0, s->peers.params[s->rank] + s0, (size_t)len * 4,
+                                     cudaMemcpyDeviceToDevice, st));
+    }
+  dp_flag_kernel<<<1, 32, 0, st>>>(s->peers, s->world, s->rank, (const long long*)step_dev, bucket, 1, final_barrier ? 1 : 0);
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }

@@ -857,6 +857,38 @@ __global__ void split_second_kernel(int B, int n0, int n1, const float* __restri
   dx1[i] = dy[(size_t)b * (n0 + n1) + n0 + c];
 }
 
+// ---- recurrent replay: acme/agents/tf/r2d2/learning.py:230-236 and :170-176
+__global__ void seq_priority_kernel(int T, int B, const float* __restrict__ err, float eta, float* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float mx = 0.f, sum = 0.f;
+  for (int t = 0; t < T; ++t) {                 // coalesced over b; tf.reduce_mean = sum / T
+    const float a = fabsf(err[(size_t)t * B + b]);
+    mx = fmaxf(mx, a);
+    sum = __fadd_rn(sum, a);
+  }
+  const float mean = __fdiv_rn(sum, (float)T);
+  out[b] = __fadd_rn(__fmul_rn(eta, mx), __fmul_rn(__fsub_rn(1.f, eta), mean));
+}
+
+__global__ void __launch_bounds__(1024)
+seq_is_weights_kernel(int B, const float* __restrict__ prob, double N, double beta, float* __restrict__ w) {
+  __shared__ double red[32];
+  double m = 0.0;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) m = fmax(m, pow(1.0 / (N * (double)prob[b]), beta));
+  for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x + 31) / 32 ? red[threadIdx.x] : 0.0;
+    for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) red[0] = m;
+  }
+  __syncthreads();
+  const double wmax = red[0];
+  for (int b = threadIdx.x; b < B; b += blockDim.x) w[b] = (float)(pow(1.0 / (N * (double)prob[b]), beta) / wmax);
+}
+
 }  // namespace b200rl
 
 using namespace b200rl;
@@ -873,6 +905,21 @@ extern "C" int b200rl_uniform(float* out, int32_t n, uint64_t seed, const int64_
   B200RL_REQUIRE(out && n >= 0, "bad argument");
   if (n == 0) return B200RL_OK;
   uniform_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(out, n, seed, (const long long*)step_dev, step_offset);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_seq_priority(int32_t T, int32_t B, const float* err_tb, float eta, float* priority_out, void* stream) {
+  B200RL_REQUIRE(err_tb && priority_out && T >= 1 && B >= 1, "bad argument");
+  seq_priority_kernel<<<(B + 127) / 128, 128, 0, as_stream(stream)>>>(T, B, err_tb, eta, priority_out);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_seq_is_weights(int32_t B, const float* prob, double table_size, double is_exponent, float* w_out,
+                                     void* stream) {
+  B200RL_REQUIRE(prob && w_out && B >= 1 && table_size > 0, "bad argument");
+  seq_is_weights_kernel<<<1, B >= 1024 ? 1024 : ((B + 31) / 32) * 32, 0, as_stream(stream)>>>(B, prob, table_size, is_exponent, w_out);
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }

@@ -302,6 +302,69 @@ gather_frames4_kernel(RingView r, const long long* __restrict__ idx, uint8_t* __
   }
 }
 
+// K3 for SEQUENCE items (`acme/adders/reverb/sequence.py:77-127`): an item is T consecutive steps of one
+// episode, each a full (observation, action [+ extras], reward, discount) row -- the final step of an episode and the
+// zero padding after it are ordinary slots whose action / reward / discount bytes are zero.  grid = (T, B): CTA (t, b)
+// copies step t of sampled item b.  A writer's slots are consecutive in the ring unless other writers interleaved, so
+// step t normally sits at (start + t) mod S (recognised by end - start == len); otherwise thread 0 walks t links.
+// Steps beyond the item's own length (never produced by SequenceAdder, possible with hand-made items) read as zeros.
+// time_major = 1 writes [T][B] rows (`tf2_utils.batch_to_sequence`, r2d2/learning.py:115), 0 writes [B][T] rows.
+template <int VEC>
+__global__ void __launch_bounds__(128)
+gather_seq_kernel(RingView r, const long long* __restrict__ idx, int T, int B, long long S, int time_major,
+                  uint8_t* __restrict__ obs_out, uint8_t* __restrict__ act_out, float* __restrict__ rew_out,
+                  float* __restrict__ disc_out) {
+  const int t = blockIdx.x, b = blockIdx.y;
+  const long long pos = idx[b];
+  const int start = r.item_start[pos], end = r.item_end[pos], len = r.item_len[pos];
+  const size_t row = time_major ? (size_t)t * B + b : (size_t)b * T + t;
+  uint8_t* dst = obs_out + row * r.obs_bytes;
+  uint8_t* ad = act_out + row * r.act_bytes;
+  if (t >= len) {   // block-uniform
+    for (int i = threadIdx.x; i < r.obs_bytes; i += 128) dst[i] = 0;
+    for (int i = threadIdx.x; i < r.act_bytes; i += 128) ad[i] = 0;
+    if (threadIdx.x == 0) { rew_out[row] = 0.f; disc_out[row] = 0.f; }
+    return;
+  }
+  __shared__ int s_slot;
+  long long gap = (long long)end - start;
+  if (gap < 0) gap += S;
+  int slot;
+  if (gap == len) {   // block-uniform
+    const long long sl = (long long)start + t;
+    slot = (int)(sl >= S ? sl - S : sl);
+  } else {
+    if (threadIdx.x == 0) {
+      int cur = start;
+      for (int j = 0; j < t; ++j) cur = r.next[cur];
+      s_slot = cur;
+    }
+    __syncthreads();
+    slot = s_slot;
+  }
+  const uint8_t* src = r.obs + (size_t)slot * r.obs_stride;
+  if (VEC == 16) {
+    const int4* s4 = reinterpret_cast<const int4*>(src);
+    int4* d4 = reinterpret_cast<int4*>(dst);
+    const int nv = r.obs_bytes >> 4;
+    int i = threadIdx.x;
+    for (; i + 3 * 128 < nv; i += 4 * 128) {
+      int4 v0 = __ldg(s4 + i), v1 = __ldg(s4 + i + 128), v2 = __ldg(s4 + i + 256), v3 = __ldg(s4 + i + 384);
+      d4[i] = v0; d4[i + 128] = v1; d4[i + 256] = v2; d4[i + 384] = v3;
+    }
+    for (; i < nv; i += 128) d4[i] = __ldg(s4 + i);
+  } else if (VEC == 4) {
+    const int* s1 = reinterpret_cast<const int*>(src);
+    int* d1 = reinterpret_cast<int*>(dst);
+    for (int i = threadIdx.x; i < (r.obs_bytes >> 2); i += 128) d1[i] = __ldg(s1 + i);
+  } else {
+    for (int i = threadIdx.x; i < r.obs_bytes; i += 128) dst[i] = src[i];
+  }
+  const uint8_t* as = r.act + (size_t)slot * r.act_stride;
+  for (int i = threadIdx.x; i < r.act_bytes; i += 128) ad[i] = as[i];
+  if (threadIdx.x == 0) { rew_out[row] = r.rew[slot]; disc_out[row] = r.disc[slot]; }
+}
+
 // device observations that arrive as full stacks [n][frame_bytes][F]: keep the newest frame (last axis index F-1)
 __global__ void extract_newest_frame_kernel(const uint8_t* __restrict__ stacks, uint8_t* __restrict__ ring, long long first_slot,
                                             long long S, long long obs_stride, int frame_bytes, int F, long long n) {
@@ -1147,6 +1210,30 @@ extern "C" int b200rl_replay_gather_rows(b200rl_replay* h, int32_t B, const int6
   gather_rows_kernel<<<dim3(B, 2, zsplit), 256, 0, as_stream(stream)>>>(h->ring, (const long long*)idx_dev, (uint8_t*)o_tm1, (uint8_t*)a_tm1, R, D,
                                                                (uint8_t*)o_t, (uint4*)rows_tm1, (uint4*)rows_t, g->W / 4, g->pad_left,
                                                                g->pad_top, Hp, row_elems / 8);
+  B200RL_LAUNCH_OK();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_replay_gather_sequences(b200rl_replay* h, int32_t B, const int64_t* idx_dev, int32_t T,
+                                              int32_t time_major, void* obs, void* act, float* rew, float* disc,
+                                              void* stream) {
+  B200RL_REQUIRE(h && idx_dev && obs && act && rew && disc, "null argument");
+  B200RL_LOCK(h);
+  B200RL_REQUIRE(h->cfg.obs_bytes > 0, "this replay was created without payload storage");
+  B200RL_REQUIRE(B >= 1 && T >= 1 && T <= h->cfg.max_window, "gather_sequences: need 1 <= T <= max_window (%d), B >= 1",
+                 h->cfg.max_window);
+  B200RL_REQUIRE(h->F == 1, "sequence gather from a frame-deduplicated ring is not implemented");
+  int rc = ensure_device(h);
+  if (rc) return rc;
+  dim3 grid(T, B);
+  cudaStream_t st = as_stream(stream);
+  const bool a16 = (h->cfg.obs_bytes % 16 == 0) && ((uintptr_t)obs % 16 == 0);
+  const bool a4 = (h->cfg.obs_bytes % 4 == 0) && ((uintptr_t)obs % 4 == 0);
+#define SEQ_ARGS h->ring, (const long long*)idx_dev, T, B, (long long)h->S, time_major ? 1 : 0, (uint8_t*)obs, (uint8_t*)act, rew, disc
+  if (a16) gather_seq_kernel<16><<<grid, 128, 0, st>>>(SEQ_ARGS);
+  else if (a4) gather_seq_kernel<4><<<grid, 128, 0, st>>>(SEQ_ARGS);
+  else gather_seq_kernel<1><<<grid, 128, 0, st>>>(SEQ_ARGS);
+#undef SEQ_ARGS
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }

@@ -117,7 +117,7 @@ class DQNLearner(core.Learner, core.Saveable):
     # is one graph and the counters are bumped in one place
     self._fuse_tail = self._world == 1 and os.environ.get('B200RL_FUSE_TAIL', '1') != '0'
     self._tail_done = None
-    self._side = [torch.cuda.Stream(device=dev) for _ in range(5)] if self._concurrent else None
+    self._side = [torch.cuda.Stream(device=dev) for _ in range(6)] if self._concurrent else None
     self._wmax_done = None
     self._params_ready = None      # pipelined exchange: event the online forwards wait for
     # data parallel: gradients and parameters live in a peer-mapped region and the exchange is fused with Adam
@@ -140,8 +140,14 @@ class DQNLearner(core.Learner, core.Saveable):
     # covers both, and is the only thing the online forwards wait for.
     # Measured on 8 GPUs: 0.500 ms/step with it vs 0.486-0.505 without (same box pool, 500-2000 steps): no clear gain,
     # the exchange contends with the convolution backward for SM slots and L2 -- kept as an option, off by default.
-    early_default = '0'
+    # Round 2: with the bulk bytes moved by the copy engines (B200RL_DP_CE=1: `b200rl_dp_reduce_adam_ce` under the
+    # convolution backward of step t, `b200rl_dp_broadcast_ce` beside K1 / K3 / the torso forwards of step t+1) the
+    # exchange of the big bucket holds no SM slots at all.
+    self._dp_ce = self._pipeline and os.environ.get('B200RL_DP_CE', '0') == '1'
+    self._ce_ctas = int(os.environ.get('B200RL_DP_CE_CTAS', '0'))
+    early_default = '1' if self._dp_ce else '0'
     self._early_tail = self._pipeline and os.environ.get('B200RL_DP_EARLY_TAIL', early_default) == '1'
+    self._dp_ce = self._dp_ce and self._early_tail
     self._early_tail_now = False     # true while a graph that contains the early tail exchange is being captured
     self._tail_in_flight = False     # the pending update's fc1 + head bucket has already been exchanged
     self._pending = False            # gradients computed, update not applied yet
@@ -182,6 +188,11 @@ class DQNLearner(core.Learner, core.Saveable):
     """tools/step_phases.py: global-timer stamps between the phases of the (captured) step; off by default."""
     if self._stamps is not None:
       _capi.load().b200rl_debug_stamp(ctypes.c_void_p(self._stamps.data_ptr()), slot, ctypes.c_void_p(_capi.current_stream()))
+
+  def _mk(self, name: str):
+    """tools/step_phases.py (B200RL_FINE=1): a named global-timer mark on the current stream; off by default."""
+    if getattr(self._net, 'marks', None) is not None:
+      self._net.marks.mark('step.' + name)
 
   def _forwards(self):
     """K1 sample, K3 gather, the three forward passes (learning.py:117-125) [+ local IS-weight max]."""
@@ -373,9 +384,7 @@ class DQNLearner(core.Learner, core.Saveable):
       ev.record(main)
       side.wait_event(ev)
       with torch.cuda.stream(side):
-        (o1, n1), _ = net.grad_buckets()
-        self._px.adam(o1, n1, self._m, self._v, self._num_steps, self._lr, 0.9, 0.999, self._adam_eps, self._eps_mode, 0,
-                      final_barrier=False)
+        self._early_tail_exchange()
         self._early_done = torch.cuda.Event()
         self._early_done.record(side)
       net.backward_conv_part(o_tm1, self._bufs_train, self._gbufs, self._side[0], **self._rows_kw())
@@ -417,22 +426,20 @@ class DQNLearner(core.Learner, core.Saveable):
     bt = self._bufs_train
     if part == 'dense':
       net.backward_dense_part(bt, gb, None, self._side[0])
-    elif self._concurrent and self._early_tail_now:
-      net.backward_dense_part(bt, gb, None, self._side[0])
-      main, side = torch.cuda.current_stream(), self._side[4]
-      ev = torch.cuda.Event()
-      ev.record(main)
-      side.wait_event(ev)
-      with torch.cuda.stream(side):
-        (o1, n1), _ = net.grad_buckets()
-        self._px.adam(o1, n1, self._m, self._v, self._num_steps, self._lr, 0.9, 0.999, self._adam_eps, self._eps_mode, 0,
-                      final_barrier=False)
-        self._early_done = torch.cuda.Event()
-        self._early_done.record(side)
-      net.backward_conv_part(o_tm1, bt, gb, self._side[0], **self._rows_kw())
     elif self._concurrent:
       hook = None
-      if self._split_adam and (self._world == 1 or self._px is not None):
+      if self._early_tail_now:
+        # data parallel: the fc1 + head bucket is exchanged as soon as its gradients (and fc1's data gradient, the last
+        # reader of its weights) are done, underneath the convolution backward
+        def hook(events):
+          side = self._side[4]
+          for ev in events:
+            side.wait_event(ev)
+          with torch.cuda.stream(side):
+            self._early_tail_exchange()
+            self._early_done = torch.cuda.Event()
+            self._early_done.record(side)
+      elif self._split_adam and (self._world == 1 or self._px is not None):
         # fc1 + heads are 99% of the parameters and final long before the torso's gradients: their optimizer update can
         # run underneath the convolution backward (B200RL_SPLIT_ADAM=1; `_apply` then only updates the torso bucket)
         def hook(events):
@@ -463,6 +470,19 @@ class DQNLearner(core.Learner, core.Saveable):
       self._dp.global_max_(self._wmax)
     self._loss_backward()
     self._stamp(4)
+
+  def _early_tail_exchange(self):
+    """The fc1 + head bucket of this step, exchanged underneath the convolution backward (current stream = a side stream
+    that waited for the dense backward)."""
+    (o1, n1), _ = self._net.grad_buckets()
+    args = (self._m, self._v, self._num_steps, self._lr, 0.9, 0.999, self._adam_eps, self._eps_mode)
+    if self._dp_ce:
+      P = self._net.params
+      self._mk('ce.start')
+      self._px.reduce_adam_ce(o1, n1, *args, 0, P.shadow.data_ptr() if P.shadow is not None else None, self._ce_ctas)
+      self._mk('ce.done')
+    else:
+      self._px.adam(o1, n1, *args, 0, final_barrier=False)
 
   def _adam(self, off: int, n: int, bucket: int = 0):
     """K7 over params[off : off + n] (snt.optimizers.Adam.apply, dqn/learning.py:147-149); with a peer exchange the
@@ -562,12 +582,35 @@ class DQNLearner(core.Learner, core.Saveable):
       px, args = self._px, (self._m, self._v, self._num_steps, self._lr, 0.9, 0.999, self._adam_eps, self._eps_mode)
       # torso bucket first (0.3 MB: one barrier round trip), then fc1 + heads (NVLink-bound).  Running the two
       # concurrently was measured slower on 2 GPUs (0.463 vs 0.436 ms): the big kernel delays the small one
+      ev_tail = None
+      if tail_done and self._dp_ce:
+        # second half of the copy-engine exchange: DMA pushes + barrier on their own stream, beside the torso bucket
+        cur, side = torch.cuda.current_stream(), self._side[5]
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        side.wait_event(ev)
+        with torch.cuda.stream(side):
+          self._mk('push.start')
+          px.broadcast_ce(o1, n1, self._num_steps, 0, final_barrier=True)
+          self._mk('push.done')
+          self._net.params.refresh_shadow(o1, n1)
+          self._mk('push.shadow')
+          ev_tail = torch.cuda.Event()
+          ev_tail.record(side)
+      self._mk('torso.start')
       px.adam(o0, n0, *args, 1, final_barrier=True)
+      self._mk('torso.done')
       self._net.params.refresh_shadow(o0, n0)
       ev_conv = torch.cuda.Event()
       ev_conv.record(torch.cuda.current_stream())
-      ev_tail = ev_conv
-      if not tail_done:
+      if ev_tail is not None:
+        torch.cuda.current_stream().wait_event(ev_tail)     # the counter below must not move under the pushes' barrier
+      elif tail_done:
+        # SM-issued early exchange: the torso bucket's barrier covered its stores; the bf16 shadow follows here
+        self._net.params.refresh_shadow(o1, n1)
+        ev_tail = torch.cuda.Event()
+        ev_tail.record(torch.cuda.current_stream())
+      else:
         px.adam(o1, n1, *args, 0, final_barrier=True)
         self._net.params.refresh_shadow(o1, n1)
         ev_tail = torch.cuda.Event()
@@ -588,11 +631,15 @@ class DQNLearner(core.Learner, core.Saveable):
   def _compute(self, uniforms=None):
     """The gradient half of a step: K1, K3, forwards, K4, backward, K2."""
     self._stamp(0)
+    self._mk('start')
     self._sample(uniforms)
+    self._mk('k1')
     self._dataset.gather_only(self._gather_rows)
+    self._mk('k3')
     self._forwards()
     self._loss_backward()
     self._stamp(4)
+    self._mk('bwd.done')
     if self._replay_client is not None:
       self._dataset.table.update_priorities_device(self._dataset.keys, self.priority)
     self._stamp(5)

@@ -140,6 +140,20 @@ class PeerExchange:
     _capi.call('b200rl_dp_adam', self._h, off, n, _capi.ptr(m), _capi.ptr(v), _capi.ptr(step), lr, b1, b2, eps, eps_mode,
                bucket, int(final_barrier), _capi.current_stream())
 
+  def reduce_adam_ce(self, off: int, n: int, m, v, step, lr: float, b1: float, b2: float, eps: float, eps_mode: int,
+                     bucket: int, shadow_ptr=None, max_ctas: int = 0):
+    """First half of the copy-engine exchange (`b200rl_dp_reduce_adam_ce`): wait for the peers' gradients, pull the owned
+    shard by DMA, Adam on it (parameters + bf16 shadow of this rank only)."""
+    from acme_b200 import _capi
+    _capi.call('b200rl_dp_reduce_adam_ce', self._h, off, n, _capi.ptr(m), _capi.ptr(v), _capi.ptr(step), lr, b1, b2, eps,
+               eps_mode, bucket, shadow_ptr, max_ctas, _capi.current_stream())
+
+  def broadcast_ce(self, off: int, n: int, step, bucket: int, final_barrier: bool = True):
+    """Second half: push the owned shard of the new parameters to every peer by DMA, then the barrier."""
+    from acme_b200 import _capi
+    _capi.call('b200rl_dp_broadcast_ce', self._h, off, n, _capi.ptr(step), bucket, int(final_barrier),
+               _capi.current_stream())
+
   def check(self):
     from acme_b200 import _capi
     _capi.call('b200rl_dp_status', self._h)

@@ -105,14 +105,14 @@ class _Packer:
     return row
 
   def unpack_batch(self, rows):
-    """rows: torch uint8 [B, nbytes] -> nest of torch tensors [B, *shape] (views)."""
+    """rows: torch uint8 [..., nbytes] -> nest of torch tensors [..., *shape] (views)."""
     import torch
     out = []
-    B = rows.shape[0]
+    lead = tuple(rows.shape[:-1])
     for shape, dt, off, n in self.leaves:
       tdt = getattr(torch, dt.name) if dt.name != 'bool' else torch.bool
-      out.append(rows[:, off:off + n].view(tdt).reshape((B,) + shape) if n else
-                 torch.empty((B,) + shape, dtype=tdt, device=rows.device))
+      out.append(rows[..., off:off + n].view(tdt).reshape(lead + shape) if n else
+                 torch.empty(lead + shape, dtype=tdt, device=rows.device))
     return tree.unflatten_as(self.structure, out)
 
 
@@ -146,6 +146,7 @@ class Table:
     self.slot_capacity = int(slot_capacity) if slot_capacity else 2 * self.max_size + self.max_window + 2 + self.frame_stack
     self._handle = None
     self._lock = threading.Lock()
+    self.is_sequence = False
     if signature is not None:
       self._bind(signature)
 
@@ -159,10 +160,22 @@ class Table:
     t.signature = ()
     t.obs_packer = t.act_packer = _Packer(())
     t.has_extras = False
+    t.is_sequence = False
     return t
 
   # -- lifecycle
   def _bind(self, signature):
+    # a `Step` of specs (adders.SequenceAdder.signature): items are sequences of whole steps; the row
+    # stored beside each observation is (action, start_of_episode, extras)
+    self.is_sequence = 'start_of_episode' in getattr(signature, '_fields', ())
+    if self.is_sequence:
+      self.obs_packer = _Packer(signature.observation)
+      self.act_packer = _Packer((signature.action, signature.start_of_episode, signature.extras))
+      self.has_extras = True
+      self.signature = signature
+      if self.frame_stack:
+        raise ValueError('frame_stack is not supported for sequence tables')
+      return
     sig = tuple(signature)
     extras_spec = sig[5] if len(sig) > 5 else ()
     self.obs_packer = _Packer(sig[0])
@@ -388,7 +401,7 @@ class Writer:
     return self._ids[table.name]
 
   def append_step(self, observation, action, reward, discount, next_observation, extras=(),
-                  tables: Optional[Sequence[str]] = None):
+                  tables: Optional[Sequence[str]] = None, start_of_episode: bool = False):
     if self.closed:
       raise RuntimeError('writer is closed')
     for name in (tables or self._client.server.tables):
@@ -397,7 +410,10 @@ class Writer:
       # (later it is the previous call's next_observation, already in the ring; the C layer ignores the pointer)
       obs = None if name in self._started else t.obs_packer.pack(observation)
       nxt = t.obs_packer.pack(next_observation)
-      act = t.act_packer.pack((action, extras) if t.has_extras else action)
+      if t.is_sequence:
+        act = t.act_packer.pack((action, np.bool_(start_of_episode), extras))
+      else:
+        act = t.act_packer.pack((action, extras) if t.has_extras else action)
       _capi.call('b200rl_writer_append', t.handle, self._wid(t), None if obs is None else obs.ctypes.data,
                  act.ctypes.data, float(np.float32(reward)), float(np.float32(discount)), nxt.ctypes.data)
       self._started.add(name)
@@ -483,7 +499,7 @@ class ReplayDataset:
   """
 
   def __init__(self, table: Table, batch_size: int, seed: int = 0, stratified: bool = True,
-               sequence_length=None):
+               sequence_length=None, time_major: bool = False):
     import torch
     self.table, self.B, self.seed, self.stratified = table, int(batch_size), int(seed), bool(stratified)
     dev = torch.device('cuda', table.device)
@@ -496,6 +512,20 @@ class ReplayDataset:
     self.prob = torch.empty(B, dtype=torch.float32, device=dev)
     # o_tm1 and o_t are the two halves of ONE [2B, obs_bytes] buffer: a learner can run its network over both batches
     # in a single pass (the online network sees o_tm1 and o_t, dqn/learning.py:123,125)
+    self.sequence_length = int(sequence_length) if sequence_length else None
+    self.time_major = bool(time_major)
+    if table.is_sequence:
+      # items are sequences: [B][T] rows of whole steps ([T][B] with time_major, the layout
+      # `tf2_utils.batch_to_sequence` produces for the recurrent learners, r2d2/learning.py:115)
+      if not self.sequence_length:
+        raise ValueError('a sequence table needs make_reverb_dataset(sequence_length=...)')
+      T = self.sequence_length
+      lead = (T, B) if self.time_major else (B, T)
+      self.seq_obs = torch.empty(lead + (max(table.obs_packer.nbytes, 1),), dtype=torch.uint8, device=dev)
+      self.seq_act = torch.empty(lead + (max(table.act_packer.nbytes, 1),), dtype=torch.uint8, device=dev)
+      self.seq_rew = torch.empty(lead, dtype=torch.float32, device=dev)
+      self.seq_disc = torch.empty(lead, dtype=torch.float32, device=dev)
+      return
     self.o_both = torch.empty((2 * B, max(table.obs_packer.nbytes, 1)), dtype=torch.uint8, device=dev)
     self.o_tm1, self.o_t = self.o_both[:B], self.o_both[B:]
     self.a_tm1 = torch.empty((B, max(table.act_packer.nbytes, 1)), dtype=torch.uint8, device=dev)
@@ -524,14 +554,42 @@ class ReplayDataset:
   def gather_only(self, rows=None):
     """K3: the sampled items' transitions (n-step return and discount built on the fly).  rows = (rows_tm1_ptr,
     rows_t_ptr, conv geometry): the frames are also written into the first conv layer's bf16 row images."""
+    if self.table.is_sequence:
+      _capi.call('b200rl_replay_gather_sequences', self.table.handle, self.B, _capi.ptr(self.idx), self.sequence_length,
+                 int(self.time_major), _capi.ptr(self.seq_obs), _capi.ptr(self.seq_act), _capi.ptr(self.seq_rew),
+                 _capi.ptr(self.seq_disc), _capi.current_stream())
+      return
     if rows is not None:
       self.table.gather_rows_into(self.idx, self.o_tm1, self.a_tm1, self.R, self.D, self.o_t, *rows)
     else:
       self.table.gather_into(self.idx, self.o_tm1, self.a_tm1, self.R, self.D, self.o_t)
 
+  def _sequence_sample(self, table_size: Optional[int] = None) -> ReplaySample:
+    """data = the table's `Step` nest with leaves [B, T, ...] ([T, B, ...] when time_major); info fields are tiled over
+    the time axis like `reverb.ReplayDataset(sequence_length=T)` does (r2d2/learning.py:172-173 reads `keys[:, 0]`)."""
+    import torch
+    t, T = self.table, self.sequence_length
+    action, start, extras = t.act_packer.unpack_batch(self.seq_act)
+    data = type(t.signature)(observation=t.obs_packer.unpack_batch(self.seq_obs), action=action, reward=self.seq_rew,
+                             discount=self.seq_disc, start_of_episode=start, extras=extras)
+    tile = (lambda x: x.unsqueeze(0).expand(T, -1)) if self.time_major else (lambda x: x.unsqueeze(1).expand(-1, T))
+    prob64 = self.prob.to(torch.float64)
+    if t.alpha > 0:
+      mass = torch.as_tensor(_MassView(t.mass_ptr()), device=self.prob.device).to(torch.float64)
+      priority = (prob64 * (t.shard_count * mass)).pow(1.0 / t.alpha)
+    else:
+      priority = torch.ones_like(prob64)
+    size = t.size if table_size is None else table_size
+    info = SampleInfo(key=tile(self.keys), probability=tile(prob64),
+                      table_size=tile(torch.full((self.B,), size, dtype=torch.int64, device=self.prob.device)),
+                      priority=tile(priority))
+    return ReplaySample(info=info, data=data)
+
   def as_sample(self, table_size: Optional[int] = None) -> ReplaySample:
     import torch
     t = self.table
+    if t.is_sequence:
+      return self._sequence_sample(table_size)
     act = t.act_packer.unpack_batch(self.a_tm1)
     extras = None
     if t.has_extras:
@@ -570,7 +628,7 @@ class ReplayDataset:
 def make_reverb_dataset(server_address=None, client: Optional[Client] = None, batch_size: int = 256,
                         prefetch_size: Optional[int] = None, sequence_length: Optional[int] = None,
                         extra_spec=None, environment_spec=None, table: str = DEFAULT_PRIORITY_TABLE,
-                        seed: int = 0, stratified: bool = True, **unused) -> ReplayDataset:
+                        seed: int = 0, stratified: bool = True, time_major: bool = False, **unused) -> ReplayDataset:
   """acme/datasets/reverb.py:36-139.  `prefetch_size` is accepted and ignored: batches are built
   synchronously in HBM, so samples are never stale with respect to priorities."""
   if client is None:
@@ -578,4 +636,4 @@ def make_reverb_dataset(server_address=None, client: Optional[Client] = None, ba
       raise ValueError('either client or server_address must be given')
     client = Client(server_address)
   return ReplayDataset(client.table(table), batch_size, seed=seed, stratified=stratified,
-                       sequence_length=sequence_length)
+                       sequence_length=sequence_length, time_major=time_major)

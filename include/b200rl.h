@@ -139,6 +139,15 @@ int b200rl_replay_gather_rows(b200rl_replay* h, int32_t B, const int64_t* idx_de
                               float* D, void* o_t, void* rows_tm1, void* rows_t, const struct b200rl_conv_geom* g,
                               void* stream);
 
+/* K3 for SEQUENCE items: the T steps of every sampled item as full rows, for recurrent learners.  Stands in
+ * for reverb.ReplayDataset(sequence_length=T) + tf2_utils.batch_to_sequence (acme/datasets/reverb.py:100-121,
+ * acme/agents/tf/r2d2/learning.py:112-121) over items made by SequenceAdder (acme/adders/reverb/sequence.py:77-127:
+ * create_item(num_timesteps = T) over the trailing T appended steps; the episode's final step and its zero padding are
+ * ordinary steps).  obs [.][.][obs_bytes], act [.][.][act_bytes] (action + extras row), rew / disc f32 [.][.]; the two
+ * leading axes are [B][T], or [T][B] with time_major = 1.  Steps past an item's own length read as zeros. */
+int b200rl_replay_gather_sequences(b200rl_replay* h, int32_t B, const int64_t* idx_dev, int32_t T, int32_t time_major,
+                                   void* obs, void* act, float* rew, float* disc, void* stream);
+
 /* Checkpoint / resume of a replay shard (the reference's checkpointers, acme/tf/savers.py:76-167, never save
  * replay contents).  host_state serialises the host bookkeeping (key counters, FIFO bounds, every open writer's episode
  * window) after flushing staged steps; blob == NULL only reports the size.  segment(which) exposes the device arrays to
@@ -173,6 +182,12 @@ int b200rl_dqn_td(int32_t B, int32_t A, const float* q_tm1, const float* q_t_val
  * (acme/agents/jax/dqn/learning.py:94-96: 1/probs cast to f32, power and max in f32) instead of the TF learner's
  * f64 power / max / divide followed by a cast (acme/agents/tf/dqn/learning.py:138-143). */
 #define B200RL_TD_IS_WEIGHTS_F32 1
+/* Recurrent replay (acme/agents/tf/r2d2/learning.py):
+ *   seq_priority    :230-236  priority[b] = eta * max_t |err[t][b]| + (1 - eta) * mean_t |err[t][b]|, err f32 [T][B]
+ *                   (time-major, as the learner holds it); the mean is a sequential fp32 sum over t divided by T
+ *   seq_is_weights  :170-176  w[b] = (1 / (table_size * prob[b]))^beta / max_b(...), f64 then cast to f32 */
+int b200rl_seq_priority(int32_t T, int32_t B, const float* err_tb, float eta, float* priority_out, void* stream);
+int b200rl_seq_is_weights(int32_t B, const float* prob, double table_size, double is_exponent, float* w_out, void* stream);
 int b200rl_is_weight_max(int32_t B, const float* prob, double is_exponent, double* wmax_out_dev,
                          int32_t flags, void* stream);
 
@@ -391,6 +406,23 @@ int b200rl_dp_max_f64(b200rl_dp_t h, double* value_dev, const int64_t* step_dev,
 int b200rl_dp_adam(b200rl_dp_t h, int64_t off, int64_t n, float* m, float* v, const int64_t* step_dev, float lr,
                    double b1, double b2, float eps, int eps_mode, int32_t bucket, int32_t final_barrier, void* stream);
 int b200rl_dp_status(b200rl_dp_t h);
+/* The same exchange with the bulk bytes moved by the copy engines (DMA over NVLink, graph memcpy nodes) instead of SM
+ * loads / stores, in two halves that a pipelined step places where they hide: the exchange keeps no SM slots, so the
+ * step's latency-bound GEMM kernels run beside it undisturbed.  Bit-identical parameters to b200rl_dp_adam.
+ *   reduce_adam_ce   announce "my gradients of [off, off+n) are final", wait for every peer's announcement, pull the
+ *                    owned shard of every peer's gradients into a landing buffer, then Adam on the shard (sum in rank
+ *                    order, x 1/R) into this rank's own parameter buffer; shadow_bf16 (NULL or this rank's bf16 copy
+ *                    of the flat parameters) receives the rounded shard; max_ctas > 0 caps the Adam kernel's grid
+ *                    (0 = fill the GPU) so that it can run underneath other kernels.
+ *   broadcast_ce     push the owned shard of the new parameters into every peer's buffer, announce "done", and with
+ *                    final_barrier wait until every peer has announced: then all of [off, off+n) is in place here.
+ * Same ordering rules as b200rl_dp_adam (same calls, same order on every rank; `bucket` names the mailbox slot; both
+ * halves read *step_dev before the step counter is advanced). */
+int b200rl_dp_reduce_adam_ce(b200rl_dp_t h, int64_t off, int64_t n, float* m, float* v, const int64_t* step_dev, float lr,
+                             double b1, double b2, float eps, int eps_mode, int32_t bucket, void* shadow_bf16,
+                             int32_t max_ctas, void* stream);
+int b200rl_dp_broadcast_ce(b200rl_dp_t h, int64_t off, int64_t n, const int64_t* step_dev, int32_t bucket,
+                           int32_t final_barrier, void* stream);
 
 /* bytes of split-K workspace that lets every layer call on outputs of up to max_out_elems
  * elements use its preferred split count (smaller workspaces only reduce the split count) */

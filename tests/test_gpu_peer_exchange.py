@@ -28,12 +28,16 @@ def _worker(rank, world, port, q):
     dp = parallel.DataParallel(dist.group.WORLD)
     n = 100_003 * 4
     px = parallel.PeerExchange(dp, n, rank)
+    px_ce = parallel.PeerExchange(dp, n, rank)       # the copy-engine form of the same exchange, fed the same gradients
     gen = torch.Generator(device='cuda').manual_seed(7)            # same parameters everywhere
     p0 = torch.randn(n, device='cuda', generator=gen)
     gen_r = torch.Generator(device='cuda').manual_seed(100 + rank)  # rank-specific gradients
     step = torch.zeros(1, dtype=torch.int64, device='cuda')
     px.params.copy_(p0)
+    px_ce.params.copy_(p0)
     m, v = torch.zeros(n, device='cuda'), torch.zeros(n, device='cuda')
+    m_ce, v_ce = torch.zeros(n, device='cuda'), torch.zeros(n, device='cuda')
+    shadow_ce = torch.zeros(n, dtype=torch.bfloat16, device='cuda')
     p_ref, m_ref, v_ref = p0.clone(), torch.zeros(n, device='cuda'), torch.zeros(n, device='cuda')
     gscale = torch.full((1,), 1.0 / world, device='cuda')
     for it in range(3):
@@ -48,6 +52,15 @@ def _worker(rank, world, port, q):
       cut = 40_000
       px.adam(cut, n - cut, m, v, step, 1e-3, 0.9, 0.999, 1e-8, 0, 0)
       px.adam(0, cut, m, v, step, 1e-3, 0.9, 0.999, 1e-8, 0, 1)
+      # copy-engine form: reduce + Adam half, then the broadcast half; bit-identical to the SM-issued kernel
+      px_ce.grads.copy_(g)
+      for (o, k, bucket) in ((cut, n - cut, 0), (0, cut, 1)):
+        px_ce.reduce_adam_ce(o, k, m_ce, v_ce, step, 1e-3, 0.9, 0.999, 1e-8, 0, bucket, shadow_ce.data_ptr(), 64 if bucket == 0 else 0)
+      for (o, k, bucket) in ((cut, n - cut, 0), (0, cut, 1)):
+        px_ce.broadcast_ce(o, k, step, bucket, final_barrier=True)
+      torch.cuda.synchronize()
+      px_ce.check()
+      assert torch.equal(px_ce.params, px.params), (it, (px_ce.params - px.params).abs().max().item())
       w = torch.tensor([float(rank * 10 + it)], dtype=torch.float64, device='cuda')
       px.max_f64_(w, step)
       torch.cuda.synchronize()
@@ -61,17 +74,22 @@ def _worker(rank, world, port, q):
       lo = cut + rank * chunk
       hi = min(n, lo + chunk)
       assert torch.allclose(m[lo:hi], m_ref[lo:hi], rtol=1e-5, atol=1e-7)   # owner keeps the moments of its shard
+      assert torch.equal(m_ce[lo:hi], m[lo:hi]) and torch.equal(v_ce[lo:hi], v[lo:hi])
+      assert torch.equal(shadow_ce[lo:hi], px_ce.params[lo:hi].to(torch.bfloat16))   # the owner's shard of the shadow
       step += 1
     px.close()
+    px_ce.close()
 
     # ---- whole learner: peer exchange vs NCCL path, same seeds
     import helpers
     for precision in (0, 2):      # fp32 parity mode and the benchmarked bf16 dataflow (fused head, batched online pass, shadows)
       losses = {}
-      for mode in (True, False):
-        pair = helpers.make_dqn_dp_learner(rank, world, dist.group.WORLD, peer_exchange=mode, precision=precision)
+      for mode in (True, 'ce', False):
+        os.environ['B200RL_DP_CE'] = '1' if mode == 'ce' else '0'
+        pair = helpers.make_dqn_dp_learner(rank, world, dist.group.WORLD, peer_exchange=bool(mode), precision=precision)
+        assert pair._dp_ce == (mode == 'ce')
         ls = []
-        for _ in range(6):
+        for _ in range(8):
           pair.step(fetch_loss=False)
           ls.append(float(pair.loss))
         pair.flush()                # pipelined exchange: apply the update still in flight (collective)
@@ -86,6 +104,7 @@ def _worker(rank, world, port, q):
         if pair._px is not None:
           pair._px.close()
       np.testing.assert_allclose(losses[True], losses[False], rtol=2e-3 if precision == 0 else 2e-2)
+      assert losses['ce'] == losses[True], (losses['ce'], losses[True])   # same sums in the same order: identical
     q.put((rank, 'ok'))
   except Exception as e:   # pragma: no cover
     import traceback
