@@ -410,7 +410,7 @@ class Writer:
       # (later it is the previous call's next_observation, already in the ring; the C layer ignores the pointer)
       obs = None if name in self._started else t.obs_packer.pack(observation)
       nxt = t.obs_packer.pack(next_observation)
-      if t.is_sequence:
+      if getattr(t, 'is_sequence', False):
         act = t.act_packer.pack((action, np.bool_(start_of_episode), extras))
       else:
         act = t.act_packer.pack((action, extras) if t.has_extras else action)
