@@ -139,6 +139,14 @@ PROTOTYPES = {
                                c_i32, c_i32, c_vp]),
     'b200rl_dp_reduce_adam_ce': (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, C.c_float, C.c_double, C.c_double, C.c_float, c_int,
                                  c_i32, c_vp, c_i32, c_vp]),
+    'b200rl_dp_region_bytes': (c_i64, [c_i64]),
+    'b200rl_dp_create_external': (c_int, [C.POINTER(c_vp), C.POINTER(DpCfg), C.POINTER(c_vp), c_vp]),
+    'b200rl_dp_has_multicast': (c_int, [c_vp]),
+    'b200rl_dp_adam_mc': (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, C.c_float, C.c_double, C.c_double, C.c_float, c_int,
+                          c_i32, c_i32, c_i32, c_vp]),
+    'b200rl_dp_reduce_adam_mc': (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, C.c_float, C.c_double, C.c_double, C.c_float, c_int,
+                                 c_i32, c_vp, c_i32, c_vp]),
+    'b200rl_dp_broadcast_mc': (c_int, [c_vp, c_i64, c_i64, c_vp, c_i32, c_i32, c_i32, c_vp]),
     'b200rl_dp_broadcast_ce': (c_int, [c_vp, c_i64, c_i64, c_vp, c_i32, c_i32, c_vp]),
     'b200rl_dp_status': (c_int, [c_vp]),
 }

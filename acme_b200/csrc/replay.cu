@@ -707,7 +707,8 @@ static int stage_tree_only(b200rl_replay* h, int64_t pos, float w) {
 
 // Allocate the next slot; evict items whose first slot is about to be overwritten.
 static int alloc_slot(b200rl_replay* h, const void* obs_host, uint64_t* seq_out) {
-  if (obs_host && h->n_obs >= h->stage_slots) {
+  // staged observations must fit the ring once around (tiny rings: flush before they lap it)
+  if (obs_host && h->n_obs >= std::min<int64_t>(h->stage_slots, h->S)) {
     int rc = flush_impl(h, g_implicit_stream);
     if (rc) return rc;
   }

@@ -11,6 +11,7 @@ The reference's D4PG has no importance weights and never writes priorities (unif
 
 from __future__ import annotations
 
+import os
 import time
 from typing import List, Optional
 
@@ -47,6 +48,9 @@ class D4PGLearner(core.Learner, core.Saveable):
     self._use_graph, self._graph, self._steps_done = bool(use_cuda_graph), None, 0
 
     dev = torch.device('cuda', critic_network.device)
+    # the three independent chains of the step on three streams (see _gradient_half); B200RL_D4PG_STREAMS=0: one stream
+    self._concurrent = os.environ.get('B200RL_D4PG_STREAMS', '1') != '0'
+    self._side = [torch.cuda.Stream(device=dev) for _ in range(2)] if self._concurrent else None
     B = self.B = dataset.B
     K, A = critic_network.K, policy_network.act_dim
     f32 = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
@@ -61,7 +65,7 @@ class D4PGLearner(core.Learner, core.Saveable):
     self._pm, self._pv = torch.zeros_like(policy_network.params.flat), torch.zeros_like(policy_network.params.flat)
     self._cm, self._cv = torch.zeros_like(critic_network.params.flat), torch.zeros_like(critic_network.params.flat)
     self._num_steps = torch.zeros(1, dtype=torch.int64, device=dev)
-    self._norm_ws = f32(1024)
+    self._norm_ws, self._norm_ws2 = f32(1024), f32(1024)
     self._pscale, self._cscale, self.policy_norm, self.critic_norm = f32(1), f32(1), f32(1), f32(1)
     self._loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
     self._loss_ring = torch.zeros(2, 2, dtype=torch.float32).pin_memory()      # fetch_loss='async': two slots
@@ -104,23 +108,54 @@ class D4PGLearner(core.Learner, core.Saveable):
                  _capi.ptr(self._num_steps), self._period, 0, st)
     ds.sample_raw(uniforms)
     o0, a0, o1 = self._views()
+    # The step is ~100 small launch-bound kernels; its three chains are independent until the critic loss, so they run
+    # on three streams (fork / join by events, also inside the captured graph; one workspace lane per stream):
+    #   main  critic(o_tm1, a_tm1)                         -> [join target] critic loss -> critic backward
+    #   s1    target policy(o_t) -> target critic(o_t, .)
+    #   s2    policy(o_t) -> critic(o_t, .) -> dq/da -> DPG loss -> policy backward
+    torch = self._torch
+    main = torch.cuda.current_stream()
+    fork = self._concurrent
+    if fork:
+      s1, s2 = self._side
+      ev = torch.cuda.Event()
+      ev.record(main)
+      s1.wait_event(ev)
+      s2.wait_event(ev)
+    else:
+      s1 = s2 = main
+    with torch.cuda.stream(s1):
+      a_targ = TP.lane(1).action(o1, self._p_tgt)
+      logits_t = TC.lane(1).logits(o1, a_targ, self._c_tgt)
+      if fork:
+        tgt_done = torch.cuda.Event()
+        tgt_done.record(s1)
+    with torch.cuda.stream(s2):
+      # actor learning (learning.py:206-218): dq/da through the online critic, parameters untouched
+      st2 = _capi.current_stream()
+      a_t = P.lane(2).action(o1, self._p_online)
+      logits_pi = C.lane(2).logits(o1, a_t, self._c_pi)
+      self._dq_dlogits(logits_pi)
+      C.backward_flat(self._c_pi['x'].data_ptr(), self._c_pi, self._cg_pi, self.dlogits_pi.data_ptr(),
+                      param_grads=False, input_grad=True)
+      _capi.call('b200rl_split_second', B, self._obs_dim, self._act_dim, _capi.ptr(self._cg_pi['dx']), _capi.ptr(self.dqda), st2)
+      _capi.call('b200rl_dpg_action_grad', B, self._act_dim, _capi.ptr(self.dqda), 1.0 if self._clipping else 0.0,
+                 int(self._clipping), 1.0 / B, _capi.ptr(self.da), _capi.ptr(self.policy_loss_ps), _capi.ptr(self.policy_loss), st2)
+      P.backward_action(o1, self._p_online, self._pg, self.da)
+      if fork:
+        pi_done = torch.cuda.Event()
+        pi_done.record(s2)
     # critic learning (learning.py:198-203)
-    logits_tm1 = C.logits(o0, a0, self._c_train)
-    a_targ = TP.action(o1, self._p_tgt)
-    logits_t = TC.logits(o1, a_targ, self._c_tgt)
+    logits_tm1 = C.lane(0).logits(o0, a0, self._c_train)
+    if fork:
+      main.wait_event(tgt_done)
     self._critic_loss(logits_tm1, logits_t)
     C.backward_flat(self._c_train['x'].data_ptr(), self._c_train, self._cg_train, self.dlogits.data_ptr(),
                     param_grads=True, input_grad=False)
-    # actor learning (learning.py:206-218): dq/da through the online critic, parameters untouched
-    a_t = P.action(o1, self._p_online)
-    logits_pi = C.logits(o1, a_t, self._c_pi)
-    self._dq_dlogits(logits_pi)
-    C.backward_flat(self._c_pi['x'].data_ptr(), self._c_pi, self._cg_pi, self.dlogits_pi.data_ptr(),
-                    param_grads=False, input_grad=True)
-    _capi.call('b200rl_split_second', B, self._obs_dim, self._act_dim, _capi.ptr(self._cg_pi['dx']), _capi.ptr(self.dqda), st)
-    _capi.call('b200rl_dpg_action_grad', B, self._act_dim, _capi.ptr(self.dqda), 1.0 if self._clipping else 0.0,
-               int(self._clipping), 1.0 / B, _capi.ptr(self.da), _capi.ptr(self.policy_loss_ps), _capi.ptr(self.policy_loss), st)
-    P.backward_action(o1, self._p_online, self._pg, self.da)
+    if fork:
+      main.wait_event(pi_done)
+    for net in (P, C, TP, TC):
+      net.lane(0)
 
   def _critic_loss(self, logits_tm1, logits_t):
     """K5: losses.categorical (distributional.py:22-37) and its gradient w.r.t. logits_tm1 (learning.py:202-203)."""
@@ -137,19 +172,36 @@ class D4PGLearner(core.Learner, core.Saveable):
 
   def _apply_half(self):
     """clip each gradient set by its global norm (learning.py:235-237), then the two Adams (240-241), step counter."""
-    st = _capi.current_stream()
+    torch = self._torch
     P, C = self._policy, self._critic
-    pscale = cscale = None
-    if self._clipping:
-      _capi.call('b200rl_global_norm_scale', P.params.size, _capi.ptr(P.params.grad), 40.0, _capi.ptr(self._norm_ws),
-                 _capi.ptr(self._pscale), _capi.ptr(self.policy_norm), st)
-      _capi.call('b200rl_global_norm_scale', C.params.size, _capi.ptr(C.params.grad), 40.0, _capi.ptr(self._norm_ws),
-                 _capi.ptr(self._cscale), _capi.ptr(self.critic_norm), st)
-      pscale, cscale = _capi.ptr(self._pscale), _capi.ptr(self._cscale)
-    for net, m, v, lr, gs in ((P, self._pm, self._pv, self._plr, pscale), (C, self._cm, self._cv, self._clr, cscale)):
+    main = torch.cuda.current_stream()
+
+    def update(net, m, v, lr, ws, scale, norm):
+      st = _capi.current_stream()
+      gs = None
+      if self._clipping:
+        _capi.call('b200rl_global_norm_scale', net.params.size, _capi.ptr(net.params.grad), 40.0, _capi.ptr(ws),
+                   _capi.ptr(scale), _capi.ptr(norm), st)
+        gs = _capi.ptr(scale)
       _capi.call('b200rl_adam', net.params.size, _capi.ptr(net.params.flat), _capi.ptr(net.params.grad), _capi.ptr(m),
                  _capi.ptr(v), _capi.ptr(self._num_steps), lr, 0.9, 0.999, 1e-8, self._eps_mode, gs, None, st)
-    _capi.call('b200rl_step_increment', _capi.ptr(self._num_steps), st)
+
+    # the two networks' clip + Adam are independent: policy on a side stream beside the critic
+    if self._concurrent:
+      side = self._side[0]
+      ev = torch.cuda.Event()
+      ev.record(main)
+      side.wait_event(ev)
+      with torch.cuda.stream(side):
+        update(P, self._pm, self._pv, self._plr, self._norm_ws2, self._pscale, self.policy_norm)
+        done = torch.cuda.Event()
+        done.record(side)
+      update(C, self._cm, self._cv, self._clr, self._norm_ws, self._cscale, self.critic_norm)
+      main.wait_event(done)
+    else:
+      update(P, self._pm, self._pv, self._plr, self._norm_ws2, self._pscale, self.policy_norm)
+      update(C, self._cm, self._cv, self._clr, self._norm_ws, self._cscale, self.critic_norm)
+    _capi.call('b200rl_step_increment', _capi.ptr(self._num_steps), _capi.current_stream())
 
   def _device_step(self, uniforms=None):
     torch = self._torch

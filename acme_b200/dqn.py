@@ -140,14 +140,44 @@ class DQNLearner(core.Learner, core.Saveable):
     # covers both, and is the only thing the online forwards wait for.
     # Measured on 8 GPUs: 0.500 ms/step with it vs 0.486-0.505 without (same box pool, 500-2000 steps): no clear gain,
     # the exchange contends with the convolution backward for SM slots and L2 -- kept as an option, off by default.
-    # Round 2: with the bulk bytes moved by the copy engines (B200RL_DP_CE=1: `b200rl_dp_reduce_adam_ce` under the
-    # convolution backward of step t, `b200rl_dp_broadcast_ce` beside K1 / K3 / the torso forwards of step t+1) the
-    # exchange of the big bucket holds no SM slots at all.
-    self._dp_ce = self._pipeline and os.environ.get('B200RL_DP_CE', '0') == '1'
+    # Round 2: with the bulk bytes moved by the copy engines (default; B200RL_DP_CE=0 restores the SM-issued kernel:
+    # `b200rl_dp_reduce_adam_ce` under the convolution backward of step t, `b200rl_dp_broadcast_ce` beside K1 / K3 / the
+    # torso forwards of step t+1) the exchange of the big bucket holds no SM slots at all.  2 GPUs, bf16 dataflow:
+    # 0.310 ms per step against 0.341 (one-GPU step 0.295).
+    # Measured: the DMA engines move ~310 GB/s per GPU whatever the number of peers or parallel copies (2 GPUs: 53 us per
+    # 16 MB phase, step 0.310 ms against 0.341 with the SM kernel; 8 GPUs: 102 + 112 us per step for 2 x 28 MB, step
+    # 0.376-0.404 against 0.383), so it only pays where the bucket's shard is big and the peers few.
+    # In-switch reduction (B200RL_DP_MC, default where the exchange has a multicast mapping): `b200rl_dp_adam_mc` as the
+    # early tail -- the SMs issue one multimem.ld_reduce and one multimem.st per 16 bytes of the OWNED shard (1/R of the
+    # bucket), so few resident warps suffice and the links carry 32 MB per direction instead of 56 MB at R = 8.
+    # B200RL_DP_REDUCE = sm | ce | mc | mcfused and B200RL_DP_BCAST = ce | mc choose the two halves of the fc1 + head
+    # bucket's exchange (mcfused / sm do both in one kernel).  Defaults by world size, from the measurements in DESIGN §6.
+    mc_ok = self._px is not None and self._px.multicast
+    red = os.environ.get('B200RL_DP_REDUCE', '')
+    if not red:
+      if os.environ.get('B200RL_DP_CE') == '0' and os.environ.get('B200RL_DP_MC', '0') == '0':
+        red = 'sm'
+      elif os.environ.get('B200RL_DP_MC') == '1' and mc_ok:
+        red = 'mcfused'
+      else:
+        red = 'ce'
+    if red in ('mc', 'mcfused') and not mc_ok:
+      red = 'ce'
+    bc = os.environ.get('B200RL_DP_BCAST', 'ce')
+    if bc == 'mc' and not mc_ok:
+      bc = 'ce'
+    if not self._pipeline:
+      red = 'sm'
+    self._dp_reduce, self._dp_bcast = red, (bc if red in ('ce', 'mc') else None)
+    self._dp_ce = red == 'ce'          # kept: tests and tools read these
+    self._dp_mc = red in ('mc', 'mcfused')
     self._ce_ctas = int(os.environ.get('B200RL_DP_CE_CTAS', '0'))
-    early_default = '1' if self._dp_ce else '0'
+    self._mc_ctas = int(os.environ.get('B200RL_DP_MC_CTAS', '148'))
+    early_default = '1' if red != 'sm' else '0'
     self._early_tail = self._pipeline and os.environ.get('B200RL_DP_EARLY_TAIL', early_default) == '1'
-    self._dp_ce = self._dp_ce and self._early_tail
+    if not self._early_tail:
+      self._dp_reduce, self._dp_bcast, self._dp_ce, self._dp_mc = 'sm', None, False, False
+    self._inc_done = None            # event: the step counter has been advanced (the early tail reads it)
     self._early_tail_now = False     # true while a graph that contains the early tail exchange is being captured
     self._tail_in_flight = False     # the pending update's fc1 + head bucket has already been exchanged
     self._pending = False            # gradients computed, update not applied yet
@@ -383,6 +413,9 @@ class DQNLearner(core.Learner, core.Saveable):
       ev = torch.cuda.Event()
       ev.record(main)
       side.wait_event(ev)
+      if self._inc_done is not None:
+        side.wait_event(self._inc_done)
+        self._inc_done = None
       with torch.cuda.stream(side):
         self._early_tail_exchange()
         self._early_done = torch.cuda.Event()
@@ -435,6 +468,9 @@ class DQNLearner(core.Learner, core.Saveable):
           side = self._side[4]
           for ev in events:
             side.wait_event(ev)
+          if self._inc_done is not None:      # the exchange reads the step counter: after the previous update's increment
+            side.wait_event(self._inc_done)
+            self._inc_done = None
           with torch.cuda.stream(side):
             self._early_tail_exchange()
             self._early_done = torch.cuda.Event()
@@ -476,10 +512,19 @@ class DQNLearner(core.Learner, core.Saveable):
     that waited for the dense backward)."""
     (o1, n1), _ = self._net.grad_buckets()
     args = (self._m, self._v, self._num_steps, self._lr, 0.9, 0.999, self._adam_eps, self._eps_mode)
-    if self._dp_ce:
-      P = self._net.params
+    P = self._net.params
+    shadow = P.shadow.data_ptr() if P.shadow is not None else None
+    if self._dp_reduce == 'mcfused':
+      self._mk('mc.start')
+      self._px.adam_mc(o1, n1, *args, 0, final_barrier=False, max_ctas=self._mc_ctas)
+      self._mk('mc.done')
+    elif self._dp_reduce == 'mc':
+      self._mk('mc.start')
+      self._px.reduce_adam_mc(o1, n1, *args, 0, shadow, self._mc_ctas)
+      self._mk('mc.done')
+    elif self._dp_reduce == 'ce':
       self._mk('ce.start')
-      self._px.reduce_adam_ce(o1, n1, *args, 0, P.shadow.data_ptr() if P.shadow is not None else None, self._ce_ctas)
+      self._px.reduce_adam_ce(o1, n1, *args, 0, shadow, self._ce_ctas)
       self._mk('ce.done')
     else:
       self._px.adam(o1, n1, *args, 0, final_barrier=False)
@@ -583,15 +628,19 @@ class DQNLearner(core.Learner, core.Saveable):
       # torso bucket first (0.3 MB: one barrier round trip), then fc1 + heads (NVLink-bound).  Running the two
       # concurrently was measured slower on 2 GPUs (0.463 vs 0.436 ms): the big kernel delays the small one
       ev_tail = None
-      if tail_done and self._dp_ce:
-        # second half of the copy-engine exchange: DMA pushes + barrier on their own stream, beside the torso bucket
+      if tail_done and self._dp_bcast is not None:
+        # second half of a two-part exchange: DMA pushes (or multicast stores) + barrier on their own stream, beside the
+        # torso bucket
         cur, side = torch.cuda.current_stream(), self._side[5]
         ev = torch.cuda.Event()
         ev.record(cur)
         side.wait_event(ev)
         with torch.cuda.stream(side):
           self._mk('push.start')
-          px.broadcast_ce(o1, n1, self._num_steps, 0, final_barrier=True)
+          if self._dp_bcast == 'mc':
+            px.broadcast_mc(o1, n1, self._num_steps, 0, final_barrier=True, max_ctas=self._mc_ctas)
+          else:
+            px.broadcast_ce(o1, n1, self._num_steps, 0, final_barrier=True)
           self._mk('push.done')
           self._net.params.refresh_shadow(o1, n1)
           self._mk('push.shadow')
@@ -622,10 +671,9 @@ class DQNLearner(core.Learner, core.Saveable):
       self._target_copy()
     _capi.call('b200rl_step_increment', _capi.ptr(self._num_steps), st)
     if tail_done and events is not None:
-      # the early tail exchange of THIS graph reads the step counter: everything downstream must see the increment
-      ev = self._torch.cuda.Event()
-      ev.record(self._torch.cuda.current_stream())
-      events = (ev, ev)
+      # the early tail exchange of THIS graph reads the step counter: it (not the forwards) waits for the increment
+      self._inc_done = self._torch.cuda.Event()
+      self._inc_done.record(self._torch.cuda.current_stream())
     return events
 
   def _compute(self, uniforms=None):
@@ -652,6 +700,7 @@ class DQNLearner(core.Learner, core.Saveable):
 
     def body():
       self._early_tail_now = self._early_tail
+      self._inc_done = None
       if variant == 'copy':          # the target network changes in this update: strict order
         self._apply_update(copy=True, tail_done=self._early_tail)
       elif variant == 'norm':        # update on a side stream; only the online forwards wait for it

@@ -12,6 +12,7 @@ Works on any backend: `nccl` on GPUs (NVLink / NVSwitch), `gloo` in the CPU test
 
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 
@@ -107,22 +108,45 @@ class PeerExchange:
     assert dp.enabled
     self.dp, self.n = dp, int(n_params)
     self._h = ctypes.c_void_p()
-    _capi.call('b200rl_dp_create', ctypes.byref(self._h),
-               ctypes.byref(_capi.DpCfg(world=dp.world, rank=dp.rank, device=device, reserved=0, n_params=self.n)))
+    dev = torch.device('cuda', device)
+    cfg = _capi.DpCfg(world=dp.world, rank=dp.rank, device=device, reserved=0, n_params=self.n)
+    self._symm = None
+    self.multicast = False
+    if os.environ.get('B200RL_DP_SYMM', '1') != '0':
+      # Symmetric allocation with an NVSwitch multicast mapping (torch symmetric memory supplies the allocation and the
+      # rendezvous, nothing on the data path): enables the in-switch reduction of `adam_mc`.
+      try:
+        import torch.distributed._symmetric_memory as symm
+        nbytes = int(_capi.load().b200rl_dp_region_bytes(self.n))
+        buf = symm.empty(nbytes, dtype=torch.uint8, device=dev)
+        hdl = symm.rendezvous(buf, dp.group.group_name if dp.group is not None else dist.group.WORLD.group_name)
+        bases = (ctypes.c_void_p * dp.world)(*[int(p) for p in hdl.buffer_ptrs])
+        mc = int(hdl.multicast_ptr) if getattr(hdl, 'multicast_ptr', 0) else None
+        _capi.call('b200rl_dp_create_external', ctypes.byref(self._h), ctypes.byref(cfg), bases, mc)
+        self._symm = (buf, hdl)
+        self.multicast = bool(_capi.load().b200rl_dp_has_multicast(self._h))
+      except Exception as e:  # noqa: BLE001 -- no symmetric memory on this box / torch build: CUDA-IPC region instead
+        if os.environ.get('B200RL_DP_SYMM') == '1':
+          raise
+        self._symm, self._h = None, ctypes.c_void_p()
+        self._symm_error = repr(e)
+    if self._symm is None:
+      _capi.call('b200rl_dp_create', ctypes.byref(self._h), ctypes.byref(cfg))
     p, g = ctypes.c_void_p(), ctypes.c_void_p()
     _capi.call('b200rl_dp_buffers', self._h, ctypes.byref(p), ctypes.byref(g))
-    dev = torch.device('cuda', device)
     self.params = torch.as_tensor(_RawDeviceArray(p.value, self.n), device=dev)
     self.grads = torch.as_tensor(_RawDeviceArray(g.value, self.n), device=dev)
     self._max_epoch = torch.zeros(1, dtype=torch.int64, device=dev)
-    mine = ctypes.create_string_buffer(64)
-    _capi.call('b200rl_dp_export', self._h, mine)
-    handles = [None] * dp.world
-    dist.all_gather_object(handles, bytes(mine.raw), group=dp.group)
-    for r, hb in enumerate(handles):
-      if r != dp.rank:
-        _capi.call('b200rl_dp_import', self._h, r, ctypes.create_string_buffer(hb, 64))
-    dist.barrier(group=dp.group)
+    if self._symm is None:
+      mine = ctypes.create_string_buffer(64)
+      _capi.call('b200rl_dp_export', self._h, mine)
+      handles = [None] * dp.world
+      dist.all_gather_object(handles, bytes(mine.raw), group=dp.group)
+      for r, hb in enumerate(handles):
+        if r != dp.rank:
+          _capi.call('b200rl_dp_import', self._h, r, ctypes.create_string_buffer(hb, 64))
+    torch.cuda.synchronize()
+    dist.barrier(group=dp.group)       # every region is zeroed and mapped before anyone's first exchange
 
   def max_f64_(self, value, step=None):
     """all-reduce(MAX) of one f64 through the peers' mailboxes.  The barrier epoch is a device counter owned by this
@@ -139,6 +163,24 @@ class PeerExchange:
     from acme_b200 import _capi
     _capi.call('b200rl_dp_adam', self._h, off, n, _capi.ptr(m), _capi.ptr(v), _capi.ptr(step), lr, b1, b2, eps, eps_mode,
                bucket, int(final_barrier), _capi.current_stream())
+
+  def adam_mc(self, off: int, n: int, m, v, step, lr: float, b1: float, b2: float, eps: float, eps_mode: int, bucket: int,
+              final_barrier: bool = True, max_ctas: int = 0):
+    """`adam` with the reduction done inside the NVSwitch (`b200rl_dp_adam_mc`); needs `self.multicast`."""
+    from acme_b200 import _capi
+    _capi.call('b200rl_dp_adam_mc', self._h, off, n, _capi.ptr(m), _capi.ptr(v), _capi.ptr(step), lr, b1, b2, eps, eps_mode,
+               bucket, int(final_barrier), max_ctas, _capi.current_stream())
+
+  def reduce_adam_mc(self, off: int, n: int, m, v, step, lr: float, b1: float, b2: float, eps: float, eps_mode: int,
+                     bucket: int, shadow_ptr=None, max_ctas: int = 0):
+    from acme_b200 import _capi
+    _capi.call('b200rl_dp_reduce_adam_mc', self._h, off, n, _capi.ptr(m), _capi.ptr(v), _capi.ptr(step), lr, b1, b2, eps,
+               eps_mode, bucket, shadow_ptr, max_ctas, _capi.current_stream())
+
+  def broadcast_mc(self, off: int, n: int, step, bucket: int, final_barrier: bool = True, max_ctas: int = 0):
+    from acme_b200 import _capi
+    _capi.call('b200rl_dp_broadcast_mc', self._h, off, n, _capi.ptr(step), bucket, int(final_barrier), max_ctas,
+               _capi.current_stream())
 
   def reduce_adam_ce(self, off: int, n: int, m, v, step, lr: float, b1: float, b2: float, eps: float, eps_mode: int,
                      bucket: int, shadow_ptr=None, max_ctas: int = 0):
@@ -168,3 +210,4 @@ class PeerExchange:
       self.params = self.grads = None
       _capi.call('b200rl_dp_destroy', self._h)
       self._h = None
+      self._symm = None

@@ -570,8 +570,10 @@ def run_ours(args):
                    'replay_ring': ('frame-deduplicated: one 84x84 uint8 frame per step, stacks rebuilt by K3 '
                                    f'({(items + 4096) * 7056 / 1e9:.1f} GB)') if args.frame_dedup else
                                   f'one 84x84x4 uint8 stack per step ({(items + 4096) * 28224 / 1e9:.1f} GB)',
-                   'parallelism': (f'dp{world}: per-rank replay shard; gradient mean + Adam + parameter broadcast fused over '
-                                   'NVLink peer memory (NCCL for set-up only)') if world > 1 else 'single GPU',
+                   'parallelism': (f'dp{world}: per-rank replay shard; gradient mean + Adam + parameter broadcast over NVLink '
+                                   f'peer memory (torso bucket: one fused SM kernel; fc1 + head bucket: reduce='
+                                   f'{getattr(learner, "_dp_reduce", "sm")}, broadcast={getattr(learner, "_dp_bcast", None) or "same kernel"}; '
+                                   'NCCL for set-up only)') if world > 1 else 'single GPU',
                    'cuda_graph': not args.no_graph,
                    'l2_policy': 'inputs larger than L2: 28 GB ring sampled at random + 160 MB of params/moments/grads per step'},
         'clocks': clk,

@@ -409,15 +409,35 @@ int b200rl_dp_status(b200rl_dp_t h);
 /* The same exchange with the bulk bytes moved by the copy engines (DMA over NVLink, graph memcpy nodes) instead of SM
  * loads / stores, in two halves that a pipelined step places where they hide: the exchange keeps no SM slots, so the
  * step's latency-bound GEMM kernels run beside it undisturbed.  Bit-identical parameters to b200rl_dp_adam.
- *   reduce_adam_ce   announce "my gradients of [off, off+n) are final", wait for every peer's announcement, pull the
- *                    owned shard of every peer's gradients into a landing buffer, then Adam on the shard (sum in rank
- *                    order, x 1/R) into this rank's own parameter buffer; shadow_bf16 (NULL or this rank's bf16 copy
+ *   reduce_adam_ce   push, for every peer, the shard that peer owns of this rank's gradients of [off, off+n) into the
+ *                    peer's landing buffer (part of its region), announce "landed", wait for every peer's
+ *                    announcement, then Adam on the owned shard (sum in rank order, x 1/R) into this rank's own
+ *                    parameter buffer; shadow_bf16 (NULL or this rank's bf16 copy
  *                    of the flat parameters) receives the rounded shard; max_ctas > 0 caps the Adam kernel's grid
  *                    (0 = fill the GPU) so that it can run underneath other kernels.
  *   broadcast_ce     push the owned shard of the new parameters into every peer's buffer, announce "done", and with
  *                    final_barrier wait until every peer has announced: then all of [off, off+n) is in place here.
  * Same ordering rules as b200rl_dp_adam (same calls, same order on every rank; `bucket` names the mailbox slot; both
  * halves read *step_dev before the step counter is advanced). */
+/* NVSwitch multicast form.  create_external adopts a SYMMETRIC allocation the caller made on every rank (for example
+ * torch.distributed._symmetric_memory: the only plumbing it supplies is the allocation and the rendezvous):
+ * b200rl_dp_region_bytes(n) bytes per rank, bases[r] = this process's mapping of rank r's region, multicast_base = the
+ * multicast mapping of the same regions (NULL = none).  adam_mc is b200rl_dp_adam with the reduce-scatter done by the
+ * switch (one multimem.ld_reduce per 16 bytes of the owned shard) and the all-gather by one multimem.st that the switch
+ * replicates into every rank's parameter buffer; max_ctas > 0 caps the grid so that it runs beside other kernels.  The
+ * in-switch sum replaces the rank-order sum (ulp-level difference in the mean gradient); replicas stay bit-identical. */
+int64_t b200rl_dp_region_bytes(int64_t n_params);
+int b200rl_dp_create_external(b200rl_dp_t* out, const b200rl_dp_cfg* cfg, void* const* bases, void* multicast_base);
+int b200rl_dp_has_multicast(b200rl_dp_t h);
+int b200rl_dp_adam_mc(b200rl_dp_t h, int64_t off, int64_t n, float* m, float* v, const int64_t* step_dev, float lr,
+                      double b1, double b2, float eps, int eps_mode, int32_t bucket, int32_t final_barrier,
+                      int32_t max_ctas, void* stream);
+/* the two halves of adam_mc on their own, interchangeable with the copy-engine halves below (same flags, same shard) */
+int b200rl_dp_reduce_adam_mc(b200rl_dp_t h, int64_t off, int64_t n, float* m, float* v, const int64_t* step_dev, float lr,
+                             double b1, double b2, float eps, int eps_mode, int32_t bucket, void* shadow_bf16,
+                             int32_t max_ctas, void* stream);
+int b200rl_dp_broadcast_mc(b200rl_dp_t h, int64_t off, int64_t n, const int64_t* step_dev, int32_t bucket,
+                           int32_t final_barrier, int32_t max_ctas, void* stream);
 int b200rl_dp_reduce_adam_ce(b200rl_dp_t h, int64_t off, int64_t n, float* m, float* v, const int64_t* step_dev, float lr,
                              double b1, double b2, float eps, int eps_mode, int32_t bucket, void* shadow_bf16,
                              int32_t max_ctas, void* stream);

@@ -29,12 +29,19 @@ def _worker(rank, world, port, q):
     n = 100_003 * 4
     px = parallel.PeerExchange(dp, n, rank)
     px_ce = parallel.PeerExchange(dp, n, rank)       # the copy-engine form of the same exchange, fed the same gradients
+    px_mc = parallel.PeerExchange(dp, n, rank)       # the multicast (in-switch reduction) form, where the box has NVLS
+    if not px_mc.multicast:
+      px_mc.close()
+      px_mc = None
     gen = torch.Generator(device='cuda').manual_seed(7)            # same parameters everywhere
     p0 = torch.randn(n, device='cuda', generator=gen)
     gen_r = torch.Generator(device='cuda').manual_seed(100 + rank)  # rank-specific gradients
     step = torch.zeros(1, dtype=torch.int64, device='cuda')
     px.params.copy_(p0)
     px_ce.params.copy_(p0)
+    if px_mc is not None:
+      px_mc.params.copy_(p0)
+      m_mc, v_mc = torch.zeros(n, device='cuda'), torch.zeros(n, device='cuda')
     m, v = torch.zeros(n, device='cuda'), torch.zeros(n, device='cuda')
     m_ce, v_ce = torch.zeros(n, device='cuda'), torch.zeros(n, device='cuda')
     shadow_ce = torch.zeros(n, dtype=torch.bfloat16, device='cuda')
@@ -61,6 +68,17 @@ def _worker(rank, world, port, q):
       torch.cuda.synchronize()
       px_ce.check()
       assert torch.equal(px_ce.params, px.params), (it, (px_ce.params - px.params).abs().max().item())
+      # in-switch reduction (multimem): the sum order differs from rank order by an ulp of the gradient sum
+      if px_mc is not None:
+        px_mc.grads.copy_(g)
+        torch.cuda.synchronize(); dist.barrier()
+        px_mc.adam_mc(cut, n - cut, m_mc, v_mc, step, 1e-3, 0.9, 0.999, 1e-8, 0, 0, final_barrier=False, max_ctas=16)
+        px_mc.adam_mc(0, cut, m_mc, v_mc, step, 1e-3, 0.9, 0.999, 1e-8, 0, 1, final_barrier=True)
+        torch.cuda.synchronize(); dist.barrier()
+        px_mc.check()
+        err = (px_mc.params - p_ref).abs().max().item()
+        assert err <= 2e-6, ('multicast', it, err)
+        dp.assert_replicated(px_mc.params)
       w = torch.tensor([float(rank * 10 + it)], dtype=torch.float64, device='cuda')
       px.max_f64_(w, step)
       torch.cuda.synchronize()
@@ -79,15 +97,25 @@ def _worker(rank, world, port, q):
       step += 1
     px.close()
     px_ce.close()
+    if px_mc is not None:
+      px_mc.close()
 
     # ---- whole learner: peer exchange vs NCCL path, same seeds
     import helpers
     for precision in (0, 2):      # fp32 parity mode and the benchmarked bf16 dataflow (fused head, batched online pass, shadows)
       losses = {}
-      for mode in (True, 'ce', False):
-        os.environ['B200RL_DP_CE'] = '1' if mode == 'ce' else '0'
+      # True = the SM-issued fused kernel; the other modes pick the halves of the fc1 + head bucket's exchange
+      modes = {True: ('sm', 'ce'), 'ce': ('ce', 'ce'), 'mc': ('mcfused', 'ce'), 'mc+ce': ('mc', 'ce'), 'ce+mc': ('ce', 'mc'), False: None}
+      for mode, halves in modes.items():
+        if halves is not None:
+          os.environ['B200RL_DP_REDUCE'], os.environ['B200RL_DP_BCAST'] = halves
         pair = helpers.make_dqn_dp_learner(rank, world, dist.group.WORLD, peer_exchange=bool(mode), precision=precision)
-        assert pair._dp_ce == (mode == 'ce')
+        if halves is not None and 'mc' in ''.join(halves) and not pair._px.multicast:   # no multicast mapping on this box
+          pair._px.close()
+          losses[mode] = None
+          continue
+        if halves is not None:
+          assert pair._dp_reduce == halves[0], (pair._dp_reduce, halves)
         ls = []
         for _ in range(8):
           pair.step(fetch_loss=False)
@@ -105,6 +133,10 @@ def _worker(rank, world, port, q):
           pair._px.close()
       np.testing.assert_allclose(losses[True], losses[False], rtol=2e-3 if precision == 0 else 2e-2)
       assert losses['ce'] == losses[True], (losses['ce'], losses[True])   # same sums in the same order: identical
+      assert losses['ce+mc'] is None or losses['ce+mc'] == losses[True]     # only the broadcast differs: identical values
+      for mode in ('mc', 'mc+ce'):                                            # in-switch sum: ulp-level differences
+        if losses[mode] is not None:
+          np.testing.assert_allclose(losses[mode], losses[True], rtol=2e-3 if precision == 0 else 2e-2)
     q.put((rank, 'ok'))
   except Exception as e:   # pragma: no cover
     import traceback
@@ -124,7 +156,7 @@ def test_peer_exchange_two_gpus():
   procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
   for p in procs:
     p.start()
-  results = [q.get(timeout=300) for _ in procs]
+  results = [q.get(timeout=600) for _ in procs]
   for p in procs:
     p.join(timeout=60)
   for rank, msg in results:

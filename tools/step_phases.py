@@ -30,6 +30,11 @@ if FINE:
   marks = networks.Marks(rank)
   net.marks = tgt.marks = marks
   net.mark_prefix, tgt.mark_prefix = 'on.', 'tgt.'
+ce_marks = None
+if FINE and world > 1:
+  import ctypes
+  ce_marks = torch.zeros(8, dtype=torch.int64, device=torch.device('cuda', rank))
+  _capi.load().b200rl_debug_dp_ce_marks(ctypes.c_void_p(ce_marks.data_ptr()))
 names = ['k1 sample + k3 gather', 'forwards (target || batched online)', 'heads + k4 td/loss', 'backward (2 streams)', 'k7 adam', 'k2 priorities + copy + inc']
 for _ in range(10): L.step(fetch_loss=False)
 late = int(os.environ.get('B200RL_PHASES_AFTER', '0'))   # measure after this many extra steps (drift over long runs)
@@ -47,6 +52,11 @@ if FINE and rank == 0:
   prev = {}
   for name, t in marks.timeline():
     print(f'{t:9.1f}  {name}')
+if ce_marks is not None and rank == 0:
+  t = ce_marks.cpu().numpy().astype(np.float64) / 1e3
+  if t[0] > 0:
+    print(f'copy-engine exchange (rank 0, last step): DMA push of gradient shards {t[1]-t[0]:.1f} us, wait for the peers\' {t[2]-t[1]:.1f}, '
+          f'Adam on the shard {t[3]-t[2]:.1f} | DMA push {t[5]-t[4]:.1f}, barrier {t[6]-t[5]:.1f} us')
 if L._px is not None:
   import ctypes
   st = np.zeros(8, np.int64)
