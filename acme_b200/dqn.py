@@ -153,6 +153,13 @@ class DQNLearner(core.Learner, core.Saveable):
     # B200RL_DP_REDUCE = sm | ce | mc | mcfused and B200RL_DP_BCAST = ce | mc choose the two halves of the fc1 + head
     # bucket's exchange (mcfused / sm do both in one kernel).  Defaults by world size, from the measurements in DESIGN §6.
     mc_ok = self._px is not None and self._px.multicast
+    # Measured (bf16 dataflow, 500 steps, one-GPU step 0.296 ms; reduce+broadcast -> ms per step):
+    #   2 GPUs: ce+ce 0.295 | mc+ce 0.311 | ce+mc 0.333 | mcfused 0.330-0.384 | sm (round-1 kernel) 0.341
+    #   4 GPUs: ce+ce 0.316 | mc+mc 0.339
+    #   8 GPUs: mc+ce 0.328 | ce+ce 0.334 | mc+mc 0.344 | mcfused 0.355 | ce+mc 0.360 | sm 0.383
+    # DMA moves ~310 GB/s per GPU however many peers or parallel copies (2 x 28 MB = 214 us per step at 8 GPUs: more than
+    # the windows it has to hide in), the in-switch reduction needs few bytes through the SMs but its kernel still holds
+    # slots under the convolution backward: the DMA broadcast with the multicast reduce wins at 8, DMA for both below.
     red = os.environ.get('B200RL_DP_REDUCE', '')
     if not red:
       if os.environ.get('B200RL_DP_CE') == '0' and os.environ.get('B200RL_DP_MC', '0') == '0':
@@ -160,7 +167,7 @@ class DQNLearner(core.Learner, core.Saveable):
       elif os.environ.get('B200RL_DP_MC') == '1' and mc_ok:
         red = 'mcfused'
       else:
-        red = 'ce'
+        red = 'mc' if (self._world > 4 and mc_ok) else 'ce'
     if red in ('mc', 'mcfused') and not mc_ok:
       red = 'ce'
     bc = os.environ.get('B200RL_DP_BCAST', 'ce')
