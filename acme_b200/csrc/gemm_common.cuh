@@ -18,6 +18,7 @@ struct Epilogue {
   int out_bf16;        // `out` holds __nv_bfloat16 (bf16 activation / gradient dataflow), else fp32
   int mask_bf16;       // `mask` holds __nv_bfloat16
   float scale;         // accumulator multiplier applied before the bias; 0 means 1 (conv1 on integer-valued frames: 1/255)
+  const int* row_map;  // nullable: GEMM row r is output / mask row row_map[r] (phase-ordered conv data gradient, fp32 path)
 };
 __device__ __forceinline__ float epi_scale(const Epilogue& e) { return e.scale == 0.f ? 1.f : e.scale; }
 
@@ -38,6 +39,7 @@ __device__ __forceinline__ float act_grad_out(float y, int act) {
   }
 }
 __device__ __forceinline__ void finish(const Epilogue& e, int row, int col, float acc) {
+  if (e.row_map) row = e.row_map[row];
   acc *= epi_scale(e);
   if (e.bias) acc += e.bias[col];
   acc = apply_act(acc, e.act);

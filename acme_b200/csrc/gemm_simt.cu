@@ -7,6 +7,7 @@
 // tcgen05 path in gemm_tc.cu.  C[row, col] = sum_red A(row, red) * B(red, col).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -110,79 +111,144 @@ struct DgradWeights {  // B(red = (ky,kx,co), outer = ci) = w[co][ky][kx][ci]; 4
   }
 };
 
-template <class AL, class BL>
+// CTA tile (16 TM) x (16 TN) with TM, TN in {4, 8}: thread (ty, tx) of the 16 x 16 grid owns rows ty*4 .. ty*4+3 (and, for
+// TM = 8, the same rows + 64) and likewise columns -- the two float4 fragments of an 8-wide micro-tile sit 64 apart so
+// that the shared-memory reads of a quarter-warp stay conflict-free.  128 x 128 tiles do 64 FFMA per 4 LDS.128 (the
+// 64 x 64 tile of round 1: 16 per 2, LDS-bound at 16 TFLOP/s); the k order inside a thread is the same for every
+// tile shape, so results only depend on the split-K count.
+// conv dgrad of a strided convolution, one STRIDE PHASE at a time: with n = i + pad = s q + p an input pixel only meets
+// the taps k = p + s t, so in the gather form above (all taps for every pixel) (s^2 - 1) / s^2 of the products are zeros
+// (conv2, stride 2: 606 us for 1.85 useful GFLOP).  Rows of phase (py, px) are its pixels in (b, iy, ix) order (row_map,
+// built per call into the workspace), the reduction runs over (ty, tx, co) with ky = py + s ty, kx = px + s tx.
+struct DgradPhaseRows {
+  static constexpr bool kRedContig = true;
+  const float* dy; b200rl_conv_geom g; const int* row_map; int Mp; int Rp; int py, px, ntx;
+  __device__ __forceinline__ float4 load(int m, int r) const {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m >= Mp || r >= Rp) return v;
+    const int pix = row_map[m];
+    const int ix = pix % g.W; int t = pix / g.W; const int iy = t % g.H; const int b = t / g.H;
+    const int co = r % g.Cout; int t2 = r / g.Cout; const int kx = px + g.stride * (t2 % ntx), ky = py + g.stride * (t2 / ntx);
+    const int ny = iy + g.pad_top - ky, nx = ix + g.pad_left - kx;
+    if (ny < 0 || nx < 0) return v;
+    const int oy = ny / g.stride, ox = nx / g.stride;      // exact: the pixel is of this phase
+    if (oy >= g.OH || ox >= g.OW) return v;
+    return __ldg(reinterpret_cast<const float4*>(dy + (((size_t)b * g.OH + oy) * g.OW + ox) * g.Cout + co));
+  }
+};
+struct DgradPhaseWeights {
+  static constexpr bool kRedContig = false;
+  const float* w; b200rl_conv_geom g; int Rp; int py, px, ntx;
+  __device__ __forceinline__ float4 load(int ci, int r) const {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ci >= g.C || r >= Rp) return v;
+    const int co = r % g.Cout; int t2 = r / g.Cout; const int kx = px + g.stride * (t2 % ntx), ky = py + g.stride * (t2 / ntx);
+    return __ldg(reinterpret_cast<const float4*>(w + (((size_t)co * g.kh + ky) * g.kw + kx) * g.C + ci));
+  }
+};
+// row_map[base(phase) + rank of the pixel inside its phase] = pixel, for all s^2 phases at once
+__global__ void dgrad_row_map_kernel(b200rl_conv_geom g, int* __restrict__ map) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= g.B * g.H * g.W) return;
+  const int s = g.stride;
+  const int ix = pix % g.W; int t = pix / g.W; const int iy = t % g.H; const int b = t / g.H;
+  const int py = (iy + g.pad_top) % s, px = (ix + g.pad_left) % s;
+  auto first = [&](int p, int pad) { return ((p - pad) % s + s) % s; };          // first index of the phase
+  auto count = [&](int p, int pad, int n) { const int f = first(p, pad); return f < n ? (n - f + s - 1) / s : 0; };
+  int base = 0;
+  for (int q = 0; q < py * s + px; ++q) base += g.B * count(q / s, g.pad_top, g.H) * count(q % s, g.pad_left, g.W);
+  const int hy = count(py, g.pad_top, g.H), wx = count(px, g.pad_left, g.W);
+  const int qy = (iy - first(py, g.pad_top)) / s, qx = (ix - first(px, g.pad_left)) / s;
+  map[base + (b * hy + qy) * wx + qx] = pix;
+}
+
+template <class AL, class BL, int TM, int TN>
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_kernel(AL a, BL b, Epilogue epi, int M, int N, int K, int k_per_split) {
-  __shared__ __align__(16) float As[2][BK][BM + 4];
-  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+  constexpr int TBM = 16 * TM, TBN = 16 * TN, LA = TM / 4, LB = TN / 4;
+  __shared__ __align__(16) float As[2][BK][TBM + 4];
+  __shared__ __align__(16) float Bs[2][BK][TBN + 4];
   const int tid = threadIdx.x;
-  const int row0 = blockIdx.y * BM, col0 = blockIdx.x * BN;
+  const int row0 = blockIdx.y * TBM, col0 = blockIdx.x * TBN;
   const int k_begin = blockIdx.z * k_per_split;
   const int k_end = min(K, k_begin + k_per_split);
   const int tx = tid & 15, ty = tid >> 4;
 
-  // per-thread load coordinates inside a tile (each thread moves one float4 of A and one of B)
-  const int a_outer = AL::kRedContig ? (tid >> 2) : ((tid & 15) << 2);
-  const int a_red = AL::kRedContig ? ((tid & 3) << 2) : (tid >> 4);
-  const int b_outer = BL::kRedContig ? (tid >> 2) : ((tid & 15) << 2);
-  const int b_red = BL::kRedContig ? ((tid & 3) << 2) : (tid >> 4);
+  // per-thread load coordinates inside a tile: L float4 per operand; load l of a red-contiguous operand takes rows
+  // + 64 l, of an outer-contiguous one (two loads) reduction rows + 8 l
+  auto coord = [&](bool red_contig, int loads, int l, int& outer, int& red) {
+    if (red_contig) { outer = (tid >> 2) + 64 * l; red = (tid & 3) << 2; }
+    else if (loads == 1) { outer = (tid & 15) << 2; red = tid >> 4; }
+    else { outer = (tid & 31) << 2; red = (tid >> 5) + 8 * l; }
+  };
 
-  float acc[4][4];
+  float acc[TM][TN];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-  auto stash = [&](int buf, float4 av, float4 bv) {
-    if (AL::kRedContig) {
-      As[buf][a_red + 0][a_outer] = av.x; As[buf][a_red + 1][a_outer] = av.y;
-      As[buf][a_red + 2][a_outer] = av.z; As[buf][a_red + 3][a_outer] = av.w;
-    } else {
-      *reinterpret_cast<float4*>(&As[buf][a_red][a_outer]) = av;
+  auto fetch = [&](int k0, float4 (&av)[LA], float4 (&bv)[LB]) {
+#pragma unroll
+    for (int l = 0; l < LA; ++l) { int o, r; coord(AL::kRedContig, LA, l, o, r); av[l] = a.load(row0 + o, k0 + r); }
+#pragma unroll
+    for (int l = 0; l < LB; ++l) { int o, r; coord(BL::kRedContig, LB, l, o, r); bv[l] = b.load(col0 + o, k0 + r); }
+  };
+  auto stash = [&](int buf, const float4 (&av)[LA], const float4 (&bv)[LB]) {
+#pragma unroll
+    for (int l = 0; l < LA; ++l) {
+      int o, r; coord(AL::kRedContig, LA, l, o, r);
+      if (AL::kRedContig) { As[buf][r + 0][o] = av[l].x; As[buf][r + 1][o] = av[l].y; As[buf][r + 2][o] = av[l].z; As[buf][r + 3][o] = av[l].w; }
+      else *reinterpret_cast<float4*>(&As[buf][r][o]) = av[l];
     }
-    if (BL::kRedContig) {
-      Bs[buf][b_red + 0][b_outer] = bv.x; Bs[buf][b_red + 1][b_outer] = bv.y;
-      Bs[buf][b_red + 2][b_outer] = bv.z; Bs[buf][b_red + 3][b_outer] = bv.w;
-    } else {
-      *reinterpret_cast<float4*>(&Bs[buf][b_red][b_outer]) = bv;
+#pragma unroll
+    for (int l = 0; l < LB; ++l) {
+      int o, r; coord(BL::kRedContig, LB, l, o, r);
+      if (BL::kRedContig) { Bs[buf][r + 0][o] = bv[l].x; Bs[buf][r + 1][o] = bv[l].y; Bs[buf][r + 2][o] = bv[l].z; Bs[buf][r + 3][o] = bv[l].w; }
+      else *reinterpret_cast<float4*>(&Bs[buf][r][o]) = bv[l];
     }
   };
 
   int buf = 0;
   {
-    float4 av = a.load(row0 + a_outer, k_begin + a_red);
-    float4 bv = b.load(col0 + b_outer, k_begin + b_red);
+    float4 av[LA], bv[LB];
+    fetch(k_begin, av, bv);
     stash(0, av, bv);
   }
   __syncthreads();
   for (int k0 = k_begin; k0 < k_end; k0 += BK) {
     const bool more = k0 + BK < k_end;
-    float4 av, bv;
-    if (more) {
-      av = a.load(row0 + a_outer, k0 + BK + a_red);
-      bv = b.load(col0 + b_outer, k0 + BK + b_red);
-    }
+    float4 av[LA], bv[LB];
+    if (more) fetch(k0 + BK, av, bv);
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
-      const float4 ar = *reinterpret_cast<const float4*>(&As[buf][kk][ty << 2]);
-      const float4 br = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx << 2]);
-      const float af[4] = {ar.x, ar.y, ar.z, ar.w}, bf[4] = {br.x, br.y, br.z, br.w};
+      float af[TM], bf[TN];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int l = 0; l < LA; ++l) {
+        const float4 t = *reinterpret_cast<const float4*>(&As[buf][kk][(ty << 2) + 64 * l]);
+        af[4 * l] = t.x; af[4 * l + 1] = t.y; af[4 * l + 2] = t.z; af[4 * l + 3] = t.w;
+      }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(af[i], bf[j], acc[i][j]);
+      for (int l = 0; l < LB; ++l) {
+        const float4 t = *reinterpret_cast<const float4*>(&Bs[buf][kk][(tx << 2) + 64 * l]);
+        bf[4 * l] = t.x; bf[4 * l + 1] = t.y; bf[4 * l + 2] = t.z; bf[4 * l + 3] = t.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(af[i], bf[j], acc[i][j]);
     }
     if (more) stash(buf ^ 1, av, bv);
     __syncthreads();
     buf ^= 1;
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int row = row0 + (ty << 2) + i;
+  for (int i = 0; i < TM; ++i) {
+    const int row = row0 + (ty << 2) + (i & 3) + 64 * (i >> 2);
     if (row >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int col = col0 + (tx << 2) + j;
+    for (int j = 0; j < TN; ++j) {
+      const int col = col0 + (tx << 2) + (j & 3) + 64 * (j >> 2);
       if (col >= N) continue;
       if (epi.partial) epi.partial[((size_t)blockIdx.z * M + row) * N + col] = acc[i][j];
       else finish(epi, row, col, acc[i][j]);
@@ -261,7 +327,13 @@ int launch_splitk_finish(const Epilogue& epi, int M, int N, int splits, cudaStre
 template <class AL, class BL>
 static int launch_gemm(const AL& a, const BL& b, Epilogue epi, int M, int N, int K, void* ws, int64_t ws_bytes,
                        cudaStream_t stream) {
-  const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
+  // tile shape: 128 x 128 where that still fills the GPU, 128 x 64 for the narrow (conv) outputs, else 64 x 64
+  static const int big_env = getenv("B200RL_SIMT_BIG") ? atoi(getenv("B200RL_SIMT_BIG")) : 1;
+  int tm = 4, tn = 4;
+  if (big_env && M >= 128 && N >= 128 && ceil_div(M, 128) * ceil_div(N, 128) >= kNumSMs) { tm = 8; tn = 8; }
+  else if (big_env && M >= 128 && ceil_div(M, 128) * ceil_div(N, 64) >= kNumSMs) { tm = 8; tn = 4; }
+  const int bm = 16 * tm, bn = 16 * tn;
+  const int tiles = ceil_div(M, bm) * ceil_div(N, bn);
   int splits = 1;
   if (tiles < 2 * kNumSMs && K >= 4 * BK) {
     splits = ceil_div(2 * kNumSMs, tiles);
@@ -273,9 +345,11 @@ static int launch_gemm(const AL& a, const BL& b, Epilogue epi, int M, int N, int
   }
   int k_per_split = ceil_div(ceil_div(K, splits), BK) * BK;
   splits = ceil_div(K, k_per_split);
-  dim3 grid(ceil_div(N, BN), ceil_div(M, BM), splits);
+  dim3 grid(ceil_div(N, bn), ceil_div(M, bm), splits);
   if (splits > 1) epi.partial = (float*)ws; else epi.partial = nullptr;
-  gemm_kernel<AL, BL><<<grid, GEMM_THREADS, 0, stream>>>(a, b, epi, M, N, K, k_per_split);
+  if (tm == 8 && tn == 8) gemm_kernel<AL, BL, 8, 8><<<grid, GEMM_THREADS, 0, stream>>>(a, b, epi, M, N, K, k_per_split);
+  else if (tm == 8) gemm_kernel<AL, BL, 8, 4><<<grid, GEMM_THREADS, 0, stream>>>(a, b, epi, M, N, K, k_per_split);
+  else gemm_kernel<AL, BL, 4, 4><<<grid, GEMM_THREADS, 0, stream>>>(a, b, epi, M, N, K, k_per_split);
   B200RL_LAUNCH_OK();
   if (splits > 1) {
     splitk_finish_kernel<<<(int)ceil_div<long long>((long long)M * N, 256), 256, 0, stream>>>(epi, M, N, splits);
@@ -470,6 +544,33 @@ int simt_conv_wgrad(const void* x, int x_u8, const float* dy, float* dw, float* 
 int simt_conv_dgrad(const float* dy, const float* w, float* dx, const b200rl_conv_geom& g, const float* mask,
                     int mask_act, void* ws, int64_t wsb, cudaStream_t s) {
   const int Min = g.B * g.H * g.W, R = g.kh * g.kw * g.Cout;
+  static const int phases_env = getenv("B200RL_SIMT_DGRAD_PHASES") ? atoi(getenv("B200RL_SIMT_DGRAD_PHASES")) : 1;
+  const int st = g.stride;
+  const int64_t map_bytes = ((int64_t)Min * 4 + 255) & ~(int64_t)255;
+  if (phases_env && st > 1 && st <= g.kh && st <= g.kw && ws && wsb > map_bytes) {
+    int* map = (int*)ws;
+    dgrad_row_map_kernel<<<ceil_div(Min, 256), 256, 0, s>>>(g, map);
+    B200RL_LAUNCH_OK();
+    auto first = [&](int p, int pad) { return ((p - pad) % st + st) % st; };
+    auto count = [&](int p, int pad, int n) { const int f = first(p, pad); return f < n ? (n - f + st - 1) / st : 0; };
+    int base = 0;
+    for (int py = 0; py < st; ++py)
+      for (int px = 0; px < st; ++px) {
+        const int Mp = g.B * count(py, g.pad_top, g.H) * count(px, g.pad_left, g.W);
+        const int nty = (g.kh - py + st - 1) / st, ntx = (g.kw - px + st - 1) / st;
+        const int Rp = nty * ntx * g.Cout;
+        if (Mp > 0) {
+          DgradPhaseRows a{dy, g, map + base, Mp, Rp, py, px, ntx};
+          DgradPhaseWeights b{w, g, Rp, py, px, ntx};
+          Epilogue e{dx, g.C, nullptr, 0, mask, g.C, mask_act, nullptr, 0};
+          e.row_map = map + base;
+          int rc = launch_gemm(a, b, e, Mp, g.C, Rp, (char*)ws + map_bytes, wsb - map_bytes, s);
+          if (rc) return rc;
+        }
+        base += Mp;
+      }
+    return B200RL_OK;
+  }
   DgradRows a{dy, g, Min, R};
   DgradWeights b{w, g, R};
   Epilogue e{dx, g.C, nullptr, 0, mask, g.C, mask_act, nullptr, 0};

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
+#include <cstdlib>
 #include <deque>
 #include <mutex>
 #include <vector>
@@ -100,9 +101,13 @@ __global__ void scatter_fills_kernel(RingView r, const SlotFill* __restrict__ fi
   for (int b = 0; b < r.act_bytes; ++b) dst[b] = src[b];
 }
 
+// The staged item records arrive in one blob behind the new key range (item_head / item_tail): thread 0 publishes the
+// range (K1 / K2 read it from `state_dst`, after this kernel in stream order), the others scatter the item records.
 __global__ void scatter_items_kernel(RingView r, const ItemRec* __restrict__ recs, int n,
-                                     long long* __restrict__ pos_out, float* __restrict__ w_out) {
+                                     long long* __restrict__ pos_out, float* __restrict__ w_out,
+                                     const ReplayState* __restrict__ state_src, ReplayState* __restrict__ state_dst) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && state_src) *state_dst = *state_src;
   if (i >= n) return;
   ItemRec it = recs[i];
   if (it.len > 0) {
@@ -402,8 +407,10 @@ struct Stage {   // one pinned staging set + its device mirror; two sets alterna
   uint8_t* h_obs = nullptr;
   SlotFill* h_fill = nullptr;
   uint8_t* h_act = nullptr;
-  ItemRec* h_item = nullptr;
-  ReplayState* h_state = nullptr;
+  uint8_t* h_blob = nullptr;     // [ReplayState, padded to one ItemRec | stage_items x ItemRec]: one H2D copy per flush
+  uint8_t* d_blob = nullptr;
+  ItemRec* h_item = nullptr;     // = h_blob + sizeof(ItemRec)
+  ReplayState* h_state = nullptr;   // = h_blob
   SlotFill* d_fill = nullptr;
   uint8_t* d_act = nullptr;
   ItemRec* d_item = nullptr;
@@ -443,6 +450,15 @@ struct b200rl_replay {
   int64_t n_obs = 0, n_fill = 0, n_item = 0;
   uint64_t obs_first_seq = 0;
   bool state_dirty = false;
+  // Split flush (b200rl_replay_flush): the bulk of an insert -- observation rows H2D, per-slot scalars -- goes on an
+  // internal stream and overlaps whatever the caller's stream is still running (the previous learner step); only the
+  // item records, the key range and the tree insert, which must not race with sampling / priority updates, are ordered
+  // on the caller's stream.  Not used when this flush evicts live items from the slot ring (their slots may still be
+  // read by work in flight) or for implicit flushes.
+  cudaStream_t payload_stream = nullptr;
+  cudaEvent_t payload_done = nullptr;
+  bool async_payload = true;
+  bool stage_has_eviction = false;
   cudaStream_t last_flush_stream = nullptr;  // flushes on different streams are chained by event
   cudaEvent_t last_flush_event = nullptr;
   // Host bookkeeping (staging sets, writer histories, key counters) is shared by actor threads that append and the
@@ -481,9 +497,8 @@ extern "C" int b200rl_device_check(int device) {
 }
 
 static void free_stage(Stage& s) {
-  cudaFreeHost(s.h_obs); cudaFreeHost(s.h_fill); cudaFreeHost(s.h_act); cudaFreeHost(s.h_item);
-  cudaFreeHost(s.h_state);
-  cudaFree(s.d_fill); cudaFree(s.d_act); cudaFree(s.d_item); cudaFree(s.d_pos); cudaFree(s.d_w);
+  cudaFreeHost(s.h_obs); cudaFreeHost(s.h_fill); cudaFreeHost(s.h_act); cudaFreeHost(s.h_blob);
+  cudaFree(s.d_fill); cudaFree(s.d_act); cudaFree(s.d_blob); cudaFree(s.d_pos); cudaFree(s.d_w);
   if (s.done) cudaEventDestroy(s.done);
   s = Stage{};
 }
@@ -497,6 +512,8 @@ extern "C" int b200rl_replay_destroy(b200rl_replay* h) {
   cudaFree(h->d_state);
   free_stage(h->stage[0]);
   free_stage(h->stage[1]);
+  if (h->payload_stream) cudaStreamDestroy(h->payload_stream);
+  if (h->payload_done) cudaEventDestroy(h->payload_done);
   delete h;
   return B200RL_OK;
 }
@@ -610,9 +627,14 @@ extern "C" int b200rl_replay_create(b200rl_replay** out, const b200rl_replay_cfg
       ok = ok && cudaMalloc((void**)&s.d_fill, h->stage_slots * sizeof(SlotFill)) == cudaSuccess;
       ok = ok && cudaMalloc((void**)&s.d_act, h->stage_slots * (size_t)h->act_stride) == cudaSuccess;
     }
-    ok = ok && cudaMallocHost((void**)&s.h_item, h->stage_items * sizeof(ItemRec)) == cudaSuccess;
-    ok = ok && cudaMallocHost((void**)&s.h_state, sizeof(ReplayState)) == cudaSuccess;
-    ok = ok && cudaMalloc((void**)&s.d_item, h->stage_items * sizeof(ItemRec)) == cudaSuccess;
+    static_assert(sizeof(ReplayState) <= sizeof(ItemRec), "blob header");
+    ok = ok && cudaMallocHost((void**)&s.h_blob, (h->stage_items + 1) * sizeof(ItemRec)) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&s.d_blob, (h->stage_items + 1) * sizeof(ItemRec)) == cudaSuccess;
+    if (ok) {
+      s.h_state = (ReplayState*)s.h_blob;
+      s.h_item = (ItemRec*)(s.h_blob + sizeof(ItemRec));
+      s.d_item = (ItemRec*)(s.d_blob + sizeof(ItemRec));
+    }
     ok = ok && cudaMalloc((void**)&s.d_pos, h->stage_items * 8) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&s.d_w, h->stage_items * 4) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) == cudaSuccess;
@@ -623,13 +645,19 @@ extern "C" int b200rl_replay_create(b200rl_replay** out, const b200rl_replay_cfg
     }
   }
 #undef ALLOC
+  if (payload) {
+    const char* e = getenv("B200RL_ASYNC_INSERT");
+    h->async_payload = !(e && atoi(e) == 0);
+    B200RL_CUDA_OK(cudaStreamCreateWithFlags(&h->payload_stream, cudaStreamNonBlocking));
+    B200RL_CUDA_OK(cudaEventCreateWithFlags(&h->payload_done, cudaEventDisableTiming));
+  }
   B200RL_CUDA_OK(cudaDeviceSynchronize());
   *out = h;
   return B200RL_OK;
 }
 
 // ----------------------------------------------------------------------------------- flush
-static int flush_impl(b200rl_replay* h, cudaStream_t stream) {
+static int flush_impl(b200rl_replay* h, cudaStream_t stream, bool allow_split = false) {
   // Order `stream` after the previous flush even when nothing is staged now: an implicit flush (staging full) runs on
   // g_implicit_stream, and the sample / gather kernels the caller is about to issue on `stream` must see its copies.
   if (h->last_flush_event && h->last_flush_stream != stream) {
@@ -639,32 +667,41 @@ static int flush_impl(b200rl_replay* h, cudaStream_t stream) {
   if (h->n_obs == 0 && h->n_fill == 0 && h->n_item == 0 && !h->state_dirty) return B200RL_OK;
   Stage& s = h->stage[h->cur];
   RingView& r = h->ring;
+  const bool split = allow_split && h->async_payload && h->payload_stream && !h->stage_has_eviction &&
+                     (h->n_obs > 0 || h->n_fill > 0);
+  cudaStream_t ps = split ? h->payload_stream : stream;
+  if (split && h->last_flush_event)   // payload copies of this flush after the previous flush's (shared device staging)
+    B200RL_CUDA_OK(cudaStreamWaitEvent(ps, h->last_flush_event, 0));
   if (h->n_obs > 0) {
     // staged observations occupy consecutive slot sequence numbers -> at most two runs in the ring
     int64_t first = (int64_t)(h->obs_first_seq % (uint64_t)h->S);
     int64_t run0 = std::min<int64_t>(h->n_obs, h->S - first);
     B200RL_CUDA_OK(cudaMemcpy2DAsync(r.obs + first * r.obs_stride, r.obs_stride, s.h_obs, r.slot_bytes,
-                                     r.slot_bytes, run0, cudaMemcpyHostToDevice, stream));
+                                     r.slot_bytes, run0, cudaMemcpyHostToDevice, ps));
     if (run0 < h->n_obs)
       B200RL_CUDA_OK(cudaMemcpy2DAsync(r.obs, r.obs_stride, s.h_obs + run0 * (int64_t)r.slot_bytes,
                                        r.slot_bytes, r.slot_bytes, h->n_obs - run0,
-                                       cudaMemcpyHostToDevice, stream));
+                                       cudaMemcpyHostToDevice, ps));
   }
   if (h->n_fill > 0) {
-    B200RL_CUDA_OK(cudaMemcpyAsync(s.d_fill, s.h_fill, h->n_fill * sizeof(SlotFill), cudaMemcpyHostToDevice, stream));
-    B200RL_CUDA_OK(cudaMemcpyAsync(s.d_act, s.h_act, h->n_fill * (size_t)r.act_stride, cudaMemcpyHostToDevice, stream));
-    scatter_fills_kernel<<<(int)ceil_div<int64_t>(h->n_fill, 128), 128, 0, stream>>>(r, s.d_fill, s.d_act, (int)h->n_fill);
+    B200RL_CUDA_OK(cudaMemcpyAsync(s.d_fill, s.h_fill, h->n_fill * sizeof(SlotFill), cudaMemcpyHostToDevice, ps));
+    B200RL_CUDA_OK(cudaMemcpyAsync(s.d_act, s.h_act, h->n_fill * (size_t)r.act_stride, cudaMemcpyHostToDevice, ps));
+    scatter_fills_kernel<<<(int)ceil_div<int64_t>(h->n_fill, 128), 128, 0, ps>>>(r, s.d_fill, s.d_act, (int)h->n_fill);
     B200RL_LAUNCH_OK();
   }
-  // publish the key range BEFORE the tree update so that its kernels see the new tail/head
+  if (split) {
+    B200RL_CUDA_OK(cudaEventRecord(h->payload_done, ps));
+    B200RL_CUDA_OK(cudaStreamWaitEvent(stream, h->payload_done, 0));
+  }
+  // the key range and the item records travel in one copy; the range is published BEFORE the tree update so that its
+  // kernels see the new tail / head
   s.h_state->item_head = h->item_head;
   s.h_state->item_tail = h->item_tail;
-  B200RL_CUDA_OK(cudaMemcpyAsync(h->d_state, s.h_state, sizeof(ReplayState), cudaMemcpyHostToDevice, stream));
+  B200RL_CUDA_OK(cudaMemcpyAsync(s.d_blob, s.h_blob, (size_t)(h->n_item + 1) * sizeof(ItemRec), cudaMemcpyHostToDevice, stream));
+  scatter_items_kernel<<<(int)std::max<int64_t>(1, ceil_div<int64_t>(h->n_item, 128)), 128, 0, stream>>>(
+      r, s.d_item, (int)h->n_item, s.d_pos, s.d_w, (const ReplayState*)s.d_blob, h->d_state);
+  B200RL_LAUNCH_OK();
   if (h->n_item > 0) {
-    B200RL_CUDA_OK(cudaMemcpyAsync(s.d_item, s.h_item, h->n_item * sizeof(ItemRec), cudaMemcpyHostToDevice, stream));
-    scatter_items_kernel<<<(int)ceil_div<int64_t>(h->n_item, 128), 128, 0, stream>>>(r, s.d_item, (int)h->n_item, s.d_pos, s.d_w);
-    B200RL_LAUNCH_OK();
-    // large flushes go through the stamp path in <=1024-entry pieces? no: one call, any size
     int rc = tree_scatter_positions(h->tree, h->M, (int)h->n_item, (const int64_t*)s.d_pos, s.d_w,
                                     h->d_state, h->d_stamp, h->d_epoch, stream);
     if (rc) return rc;
@@ -675,6 +712,7 @@ static int flush_impl(b200rl_replay* h, cudaStream_t stream) {
   h->last_flush_stream = stream;
   h->n_obs = h->n_fill = h->n_item = 0;
   h->state_dirty = false;
+  h->stage_has_eviction = false;
   h->cur ^= 1;
   Stage& nxt = h->stage[h->cur];
   if (nxt.in_flight) {  // the set we are about to overwrite: wait for its copies (2 flushes ago)
@@ -689,7 +727,7 @@ extern "C" int b200rl_replay_flush(b200rl_replay* h, void* stream) {
   B200RL_LOCK(h);
   int rc = ensure_device(h);
   if (rc) return rc;
-  return flush_impl(h, as_stream(stream));
+  return flush_impl(h, as_stream(stream), /*allow_split=*/true);
 }
 
 // the stream used by implicit flushes triggered from the host-only writer calls
@@ -741,6 +779,7 @@ static int alloc_slot(b200rl_replay* h, const void* obs_host, uint64_t* seq_out)
       if (rc) return rc;
       h->item_tail++;
       h->state_dirty = true;
+      h->stage_has_eviction = true;   // live slots are being recycled: this flush stays on one stream
     }
   }
   *seq_out = seq;
