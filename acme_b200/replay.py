@@ -191,6 +191,12 @@ class Table:
   def _ensure(self):
     if self._handle is not None:
       return
+    with self._lock:      # actor threads and the learner thread may all touch a fresh table first (ctypes drops the GIL)
+      self._ensure_locked()
+
+  def _ensure_locked(self):
+    if self._handle is not None:
+      return
     if self.signature is None:
       raise ValueError(f'table {self.name!r} has no signature; pass signature=Adder.signature(spec)')
     _capi.require_device(self.device)
