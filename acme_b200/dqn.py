@@ -201,7 +201,7 @@ class DQNLearner(core.Learner, core.Saveable):
     # bf16 dataflow on uint8 frames: K3 writes the first conv layer's row image itself (no conversion pass)
     self._gather_rows = None
     if (self._fused and getattr(network, 'flow', False) and self._obs_dtype == np.uint8 and
-        os.environ.get('B200RL_GATHER_ROWS', '1') != '0'):
+        getattr(dataset, 'supports_gather_rows', True) and os.environ.get('B200RL_GATHER_ROWS', '1') != '0'):
       buf = network.rows_buffer(2 * B, 'all')
       fb = network.rows_frame_bytes()
       if buf is not None and fb:

@@ -148,6 +148,18 @@ int b200rl_replay_gather_rows(b200rl_replay* h, int32_t B, const int64_t* idx_de
 int b200rl_replay_gather_sequences(b200rl_replay* h, int32_t B, const int64_t* idx_dev, int32_t T, int32_t time_major,
                                    void* obs, void* act, float* rew, float* disc, void* stream);
 
+/* DQfD demonstration mixing (acme/agents/tf/dqfd/agent.py:111-122: sample_from_datasets([replay, demonstrations],
+ * [1 - ratio, ratio]); :160-219: _n_step_transition_from_episode).  The demonstration episodes are flat device arrays
+ * (obs [steps][obs_bytes], act [steps][act_bytes], rew / disc f32 [steps], episode_offsets i64 [num_episodes + 1]; every
+ * episode has >= 3 steps).  Called after sample + gather: batch row b is REPLACED by a demonstration transition when
+ * uniforms3[3b] < ratio (episode = floor(uniforms3[3b+1] * num_episodes), first step = floor(uniforms3[3b+2] *
+ * (max_index - 1))), with the reference's arithmetic for its n-step reward / discount, key 0 and probability 1;
+ * is_demo (nullable) receives the mask. */
+int b200rl_demo_mix(int32_t B, const void* obs, int32_t obs_bytes, const void* act, int32_t act_bytes, const float* rew,
+                    const float* disc, const int64_t* episode_offsets, int32_t num_episodes, int32_t n_step, float gamma,
+                    const float* uniforms3, float ratio, void* o_tm1, void* a_tm1, float* R, float* D, void* o_t,
+                    uint64_t* keys, float* prob, int32_t* is_demo, void* stream);
+
 /* Checkpoint / resume of a replay shard (the reference's checkpointers, acme/tf/savers.py:76-167, never save
  * replay contents).  host_state serialises the host bookkeeping (key counters, FIFO bounds, every open writer's episode
  * window) after flushing staged steps; blob == NULL only reports the size.  segment(which) exposes the device arrays to
