@@ -21,6 +21,9 @@ import numpy as np
 
 from acme_b200 import _capi, actors, adders, agent, core, counting, loggers, networks, parallel, replay, specs
 
+# Single-GPU pipelined update (see DQNLearner.__init__): '1' once measured faster than the one-graph serial step.
+PIPELINE_1GPU_DEFAULT = '0'
+
 
 class DQNLearner(core.Learner, core.Saveable):
 
@@ -120,6 +123,7 @@ class DQNLearner(core.Learner, core.Saveable):
     self._side = [torch.cuda.Stream(device=dev) for _ in range(6)] if self._concurrent else None
     self._wmax_done = None
     self._params_ready = None      # pipelined exchange: event the online forwards wait for
+    self._k2_done = False          # K2 of this step was already issued beside the backward
     # data parallel: gradients and parameters live in a peer-mapped region and the exchange is fused with Adam
     # (parallel.PeerExchange); peer_exchange=False keeps the NCCL all-reduce + replicated Adam path
     if peer_exchange is None:
@@ -134,6 +138,16 @@ class DQNLearner(core.Learner, core.Saveable):
     # critical path.  `flush()` applies the update still in flight (collective: every rank must call it).
     self._pipeline = (self._px is not None and self._concurrent and bool(use_cuda_graph) and
                       os.environ.get('B200RL_DP_PIPELINE', '1') != '0')
+    # The same pipeline on ONE GPU (B200RL_PIPELINE_1GPU): Adam of step t (HBM-bound, 225 MB) is issued at the start of
+    # step t+1's graph on a side stream, torso bucket first; K1 / K3 / the target forward never wait for it, the online
+    # pass waits for the torso bucket before conv1 and for the fc1 + head bucket before fc1.  Same values as the serial
+    # order (K1 of step t+1 still follows K2 of step t); `flush()` applies the update still in flight.
+    self._pipeline1 = (self._px is None and self._world == 1 and self._concurrent and self._fused and bool(use_cuda_graph) and
+                       hasattr(network, 'grad_buckets') and os.environ.get('B200RL_PIPELINE_1GPU', PIPELINE_1GPU_DEFAULT) == '1')
+    if self._pipeline1:
+      self._pipeline = True
+      self._fuse_tail = False          # the pipelined update ends with its own target copy + increment
+    self._pipe_adam_ctas = int(os.environ.get('B200RL_PIPE_ADAM_CTAS', '0'))
     # Early tail (>= 4 ranks, where the exchange is NVLink-bound rather than HBM-bound): the fc1 + head bucket of step
     # t is exchanged as soon as step t's dense backward has produced it, underneath the convolution backward, without
     # waiting for the peers' stores; the torso bucket's exchange at the start of step t+1 ends with the barrier that
@@ -173,7 +187,7 @@ class DQNLearner(core.Learner, core.Saveable):
     bc = os.environ.get('B200RL_DP_BCAST', 'ce')
     if bc == 'mc' and not mc_ok:
       bc = 'ce'
-    if not self._pipeline:
+    if not self._pipeline or self._px is None:
       red = 'sm'
     self._dp_reduce, self._dp_bcast = red, (bc if red in ('ce', 'mc') else None)
     self._dp_ce = red == 'ce'          # kept: tests and tools read these
@@ -181,7 +195,8 @@ class DQNLearner(core.Learner, core.Saveable):
     self._ce_ctas = int(os.environ.get('B200RL_DP_CE_CTAS', '0'))
     self._mc_ctas = int(os.environ.get('B200RL_DP_MC_CTAS', '148'))
     early_default = '1' if red != 'sm' else '0'
-    self._early_tail = self._pipeline and os.environ.get('B200RL_DP_EARLY_TAIL', early_default) == '1'
+    self._early_tail = (self._pipeline and self._px is not None and
+                        os.environ.get('B200RL_DP_EARLY_TAIL', early_default) == '1')
     if not self._early_tail:
       self._dp_reduce, self._dp_bcast, self._dp_ce, self._dp_mc = 'sm', None, False, False
     self._inc_done = None            # event: the step counter has been advanced (the early tail reads it)
@@ -458,6 +473,10 @@ class DQNLearner(core.Learner, core.Saveable):
       aux.wait_event(ev)
       with torch.cuda.stream(aux):
         _capi.call('b200rl_mean', B, _capi.ptr(self.loss_ps), _capi.ptr(self.loss), _capi.current_stream())
+        if self._pipeline1 and self._replay_client is not None:
+          # K2 (learning.py:151-154) only needs K4's priorities: beside the backward instead of after it
+          ds.table.update_priorities_device(ds.keys, self.priority)
+          self._k2_done = True
         self._loss_done = torch.cuda.Event()
         self._loss_done.record(aux)
     else:
@@ -549,6 +568,8 @@ class DQNLearner(core.Learner, core.Saveable):
     P, b = self._net.params, 4 * off
     shadow = (P.shadow.data_ptr() + 2 * off) if P.shadow is not None else None      # bf16 dataflow: weights' bf16 copy
     throttle = self._tail_ctas if (self._split_adam and bucket == 0 and n < P.size) else 0   # beside the conv backward
+    if self._pipeline1 and bucket == 0 and n < P.size:
+      throttle = self._pipe_adam_ctas                                                       # beside the next step's torso
     _capi.call('b200rl_adam_throttled', n, _capi.ptr(P.flat) + b, _capi.ptr(P.grad) + b, _capi.ptr(self._m) + b,
                _capi.ptr(self._v) + b, _capi.ptr(self._num_steps), self._lr, 0.9, 0.999, self._adam_eps, self._eps_mode,
                _capi.ptr(self._gscale) if self._world > 1 else None, shadow, throttle, _capi.current_stream())
@@ -672,6 +693,16 @@ class DQNLearner(core.Learner, core.Saveable):
         ev_tail = torch.cuda.Event()
         ev_tail.record(torch.cuda.current_stream())
       events = (ev_conv, ev_tail)
+    elif self._pipeline1:
+      torch = self._torch
+      (o1, n1), (o0, n0) = self._net.grad_buckets()
+      self._adam(o0, n0, bucket=1)       # torso: 0.3 MB, what conv1 of the next online pass waits for
+      ev_conv = torch.cuda.Event()
+      ev_conv.record(torch.cuda.current_stream())
+      self._adam(o1, n1, bucket=0)       # fc1 + heads: 99% of the bytes, needed only before fc1
+      ev_tail = torch.cuda.Event()
+      ev_tail.record(torch.cuda.current_stream())
+      events = (ev_conv, ev_tail)
     else:
       self._adam(0, P.size)
     if copy:
@@ -695,8 +726,9 @@ class DQNLearner(core.Learner, core.Saveable):
     self._loss_backward()
     self._stamp(4)
     self._mk('bwd.done')
-    if self._replay_client is not None:
+    if self._replay_client is not None and not self._k2_done:
       self._dataset.table.update_priorities_device(self._dataset.keys, self.priority)
+    self._k2_done = False
     self._stamp(5)
     if self._early_tail_now:
       self._torch.cuda.current_stream().wait_event(self._early_done)
@@ -728,8 +760,9 @@ class DQNLearner(core.Learner, core.Saveable):
         torch.cuda.current_stream().wait_event(self._update_done)
       self._early_tail_now = False
     g = self._capture(body)
-    import torch.distributed as dist
-    dist.barrier(group=self._dp.group)      # every rank has the graph before anyone spins on a peer
+    if self._px is not None:
+      import torch.distributed as dist
+      dist.barrier(group=self._dp.group)      # every rank has the graph before anyone spins on a peer
     return g
 
   def _pipelined_step(self, uniforms):

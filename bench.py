@@ -575,6 +575,9 @@ def run_ours(args):
                                    f'{getattr(learner, "_dp_reduce", "sm")}, broadcast={getattr(learner, "_dp_bcast", None) or "same kernel"}; '
                                    'NCCL for set-up only)') if world > 1 else 'single GPU',
                    'cuda_graph': not args.no_graph,
+                   'update_order': ('pipelined: the optimizer half of update t is issued at the start of step t+1\'s graph beside '
+                                    'K1 / K3 / the target forward (same values as the serial order; the last update is flushed '
+                                    'inside the timed region)') if getattr(learner, '_pipeline', False) else 'serial (one graph per step)',
                    'l2_policy': 'inputs larger than L2: 28 GB ring sampled at random + 160 MB of params/moments/grads per step'},
         'clocks': clk,
         'e2e': {'value': e2e_value, 'unit': 'updates/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,

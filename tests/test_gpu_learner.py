@@ -391,11 +391,15 @@ def test_variable_export_roundtrip():
     np.testing.assert_array_equal(x, v[k])
 
 
-@pytest.mark.parametrize('use_graph', [False, True])
-def test_dqn_learner_steps_match_oracle(use_graph):
+@pytest.mark.parametrize('mode', ['eager', 'graph', 'pipelined'])
+def test_dqn_learner_steps_match_oracle(mode, monkeypatch):
   """Full update (sample -> gather -> 3 forwards -> TD -> backward -> Adam -> priorities -> target copy)
-  against oracle.learner.DQNOracleLearner fed by oracle.replay on the same uniform draws."""
+  against oracle.learner.DQNOracleLearner fed by oracle.replay on the same uniform draws.  'pipelined' = the
+  single-GPU form whose optimizer half runs at the start of the next step's graph (B200RL_PIPELINE_1GPU=1): same
+  values, `flush()` applies the update still in flight."""
   import torch
+  use_graph = mode != 'eager'
+  monkeypatch.setenv('B200RL_PIPELINE_1GPU', '1' if mode == 'pipelined' else '0')
   import helpers
   from acme_b200 import dqn, networks, replay
   from oracle import learner as olearner
@@ -420,7 +424,9 @@ def test_dqn_learner_steps_match_oracle(use_graph):
   counter = torch.zeros(1, dtype=torch.int64, device='cuda')
   u_dev = torch.empty(B, device='cuda')
   from acme_b200 import _capi
-  for step in range(5):
+  assert learner._pipeline == (mode == 'pipelined')
+  steps = 9 if mode == 'pipelined' else 5      # pipelined: two eager steps, then all three graph variants several times
+  for step in range(steps):
     # the uniforms the learner is about to draw (device Philox keyed by (seed, call counter))
     _capi.call('b200rl_uniform', u_dev.data_ptr(), B, 7, counter.data_ptr(), step, _capi.current_stream())
     u = u_dev.cpu().numpy()
@@ -441,6 +447,9 @@ def test_dqn_learner_steps_match_oracle(use_graph):
     # trajectories then drift apart chaotically.  The Adam kernel itself is pinned to 1e-5 in
     # test_adam_and_global_norm and the gradients in test_dqn_atari_network_forward_backward; here the
     # first two updates must agree to 2% of one learning-rate step for all but <1e-3 of the parameters.
+    if mode == 'pipelined' and step in (0, 1, 4, 5, 8):
+      learner.flush()            # also leaves some updates pending across steps (2-3, 6-7): both orders are exercised
+    pending = learner._pending
     if step < 2:
       got = net.variables()
       for k, v in onet.numpy().items():
@@ -449,11 +458,12 @@ def test_dqn_learner_steps_match_oracle(use_graph):
         np.testing.assert_allclose(got[k], v, rtol=1e-4, atol=0.5 * lr, err_msg=f'param {k} step {step}')
     # target copy timing (learning.py:157-161): target == online right after updates 0, 2, 4 (period 2) and
     # stays frozen in between -- exact on the device.
-    if step % 2 == 0:
-      frozen = net.params.flat.clone()
-    assert torch.equal(tgt.params.flat, frozen), f'target network wrong after update {step}'
+    if not pending:
+      if step % 2 == 0:
+        frozen = net.params.flat.clone()
+      assert torch.equal(tgt.params.flat, frozen), f'target network wrong after update {step}'
     helpers.sync_oracle_leaves_loose(table, oracle)
-  assert learner.num_steps == 5
+  assert learner.num_steps == steps
   server.stop()
 
 
