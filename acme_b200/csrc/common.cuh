@@ -81,6 +81,56 @@ __device__ __forceinline__ float philox_uniform(unsigned int i, unsigned long lo
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Programmatic dependent launch (B200RL_PDL=1).  A learner step is a chain of ~16 short kernels, each waiting for the
+// one before it; with a programmatic edge the next kernel's CTAs are scheduled while the previous kernel drains and run
+// their set-up (barrier init, TMEM allocation, tensor-map prefetch) up to `pdl_wait()`, which returns when every
+// prerequisite grid has completed and its memory is visible.  Kernels call pdl_launch_dependents() first thing and
+// pdl_wait() before their first access to global memory; both are no-ops in a launch without the attribute, so only
+// kernels that contain pdl_wait() may be launched through launch_pdl().
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+#define B200RL_PDL_DEFAULT true    // measured on B200: 0.289 -> 0.269 ms per DQN step (gpurun_out/c3_*, c4_*)
+#define B200RL_PDL_LATE_DEFAULT 1   // trigger at accumulator-ready: 0.276 -> 0.269 ms
+bool pdl_enabled();   // replay.cu: B200RL_PDL (or b200rl_debug_set_pdl)
+int pdl_late_mode();  // replay.cu: B200RL_PDL_LATE
+
+// Two domains.  launch_pdl: the tensor-core GEMM / convolution kernels and the kernels between them on the DQN step's
+// critical path (10-30 us each: scheduling the next grid during the previous one's epilogue pays; measured 0.291 -> 0.271
+// ms per step).  launch_pdl_small: the FFMA GEMM and the element-wise / reduction kernels of a few microseconds that
+// make up the D4PG step and the fp32 parity mode -- there the programmatic edges cost more than they hide (measured with
+// them on: D4PG 0.267 -> 0.317 ms, fp32 DQN 2.41 -> 2.69 ms), so that domain is off unless B200RL_PDL_SMALL=1.
+bool pdl_small_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl_on(bool on, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                        Args&&... args);
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  return launch_pdl_on(pdl_enabled(), kernel, grid, block, smem, stream, static_cast<Args&&>(args)...);
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl_small(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                           Args&&... args) {
+  return launch_pdl_on(pdl_enabled() && pdl_small_enabled(), kernel, grid, block, smem, stream, static_cast<Args&&>(args)...);
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl_on(bool on, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                        Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = on ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<Args&&>(args)...);
+}
+#endif
+
 template <typename T>
 static inline T ceil_div(T a, T b) {
   return (a + b - 1) / b;

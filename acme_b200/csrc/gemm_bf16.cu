@@ -112,6 +112,7 @@ hgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   __shared__ uint32_t tmem_base_smem;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (!epi.pdl_late) pdl_launch_dependents();
   const int row0 = blockIdx.y * HBM_ROWS, col0 = blockIdx.x * BN;
   const int total_kblocks = (K + KE - 1) / KE;
   const int kb_begin = blockIdx.z * kblocks_per_split;
@@ -129,6 +130,7 @@ hgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                  // everything above overlaps the previous kernel's tail (launch_pdl); no-op otherwise
   const uint32_t tmem_d = tmem_base_smem;
 
   if (warp == 0 && lane == 0) {
@@ -224,6 +226,7 @@ hgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       mbar_wait(&bar_done, 0);
       tc_fence_after();
     }
+    if (epi.pdl_late) pdl_launch_dependents();
     if (epi.transpose_out && !epi.partial) {
       const int row = row0 + lane_base + lane;
 #pragma unroll 1
@@ -274,6 +277,7 @@ hgemm_pers_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   __shared__ uint32_t tmem_base_smem;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_launch_dependents();
   const int tiles_m = (M + HBM_ROWS - 1) / HBM_ROWS, tiles_n = (N + BN - 1) / BN, tiles_mn = tiles_m * tiles_n;
   const int total = tiles_mn * splits;
   const int total_kblocks = (K + KE - 1) / KE;
@@ -293,6 +297,7 @@ hgemm_pers_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                  // everything above overlaps the previous kernel's tail (launch_pdl); no-op otherwise
   const uint32_t tmem_d = tmem_base_smem;
 
   if (warp == 0 && lane == 0) {
@@ -416,7 +421,8 @@ static int launch_h_pers_s(const CUtensorMap& ma, const CUtensorMap& mb, const E
     B200RL_CUDA_OK(cudaFuncSetAttribute(hgemm_pers_kernel<KE, BM, BN, STAGES, RESB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr = smem;
   }
-  hgemm_pers_kernel<KE, BM, BN, STAGES, RESB><<<grid, H_THREADS, smem, stream>>>(ma, mb, epi, M, N, K, kps, splits, conv);
+  B200RL_CUDA_OK(launch_pdl(hgemm_pers_kernel<KE, BM, BN, STAGES, RESB>, dim3(grid), dim3(H_THREADS), smem, stream, ma, mb, epi, M, N, K, kps,
+                            splits, conv));
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }
@@ -449,6 +455,7 @@ static int launch_h_pers(const CUtensorMap& ma, const CUtensorMap& mb, Epilogue 
   }
 }
 
+constexpr int SPLITK_OCC_DEFAULT = 1, SPLITK_MIN_KB_DEFAULT = 8, SPLITK_MAX_DEFAULT = 64;   // round-1/2 values
 template <int KE, int AM, int BM, int BN>
 static int launch_h(const CUtensorMap& ma, const CUtensorMap& mb, Epilogue epi, int M, int N, int K, void* ws, int64_t ws_bytes,
                     cudaStream_t stream, const ConvA& conv, bool allow_split = true) {
@@ -457,9 +464,16 @@ static int launch_h(const CUtensorMap& ma, const CUtensorMap& mb, Epilogue epi, 
   const int tiles = ceil_div(M, HBM_ROWS) * ceil_div(N, BN);
   const int kblocks = ceil_div(K, KE);
   int splits = 1;
+  // split-K fills the GPU when a layer has few output tiles (conv weight gradients: 2-5 tiles over a 30-113 K pixel
+  // reduction; fc1 forward: 32 tiles over K = 7744).  A CTA's k-blocks are a serial chain of ~0.5 us ring round trips, so
+  // the chain length, not the byte count, sets the kernel's duration: B200RL_SPLITK_OCC CTAs per SM (default below),
+  // at least B200RL_SPLITK_MIN_KB k-blocks per split, at most B200RL_SPLITK_MAX splits.
+  static const int sk_occ = getenv("B200RL_SPLITK_OCC") ? atoi(getenv("B200RL_SPLITK_OCC")) : SPLITK_OCC_DEFAULT;
+  static const int sk_min = getenv("B200RL_SPLITK_MIN_KB") ? atoi(getenv("B200RL_SPLITK_MIN_KB")) : SPLITK_MIN_KB_DEFAULT;
+  static const int sk_max = getenv("B200RL_SPLITK_MAX") ? atoi(getenv("B200RL_SPLITK_MAX")) : SPLITK_MAX_DEFAULT;
   if (allow_split && 2 * tiles <= kNumSMs && kblocks >= 16) {
-    splits = std::min(ceil_div(kNumSMs, tiles), kblocks / 8);
-    splits = std::min(splits, 64);
+    splits = std::min(ceil_div(sk_occ * kNumSMs, tiles), kblocks / sk_min);
+    splits = std::max(1, std::min(splits, sk_max));
     const int64_t cap = ws ? ws_bytes / ((int64_t)M * N * 4) : 0;
     splits = (int)std::max<int64_t>(1, std::min<int64_t>(splits, cap));
   }
@@ -496,7 +510,8 @@ static int launch_h(const CUtensorMap& ma, const CUtensorMap& mb, Epilogue epi, 
     B200RL_CUDA_OK(cudaFuncSetAttribute(hgemm_kernel<KE, AM, BM, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr = true;
   }
-  hgemm_kernel<KE, AM, BM, BN, STAGES><<<grid, H_THREADS, smem, stream>>>(ma, mb, epi, M, N, K, kps, conv);
+  epi.pdl_late = pdl_late_mode();
+  B200RL_CUDA_OK(launch_pdl(hgemm_kernel<KE, AM, BM, BN, STAGES>, grid, dim3(H_THREADS), smem, stream, ma, mb, epi, M, N, K, kps, conv));
   B200RL_LAUNCH_OK();
   if (splits > 1) return launch_splitk_finish(epi, M, N, splits, stream);
   return B200RL_OK;
@@ -717,6 +732,7 @@ hconv_dgrad_kernel(const __grid_constant__ HDgradMaps maps, const __grid_constan
   __shared__ __align__(8) uint64_t bar_full[D_STAGES], bar_empty[D_STAGES], bar_done;
   __shared__ uint32_t tmem_base_smem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (!epi.pdl_late) pdl_launch_dependents();
 
   int phase = 0;
 #pragma unroll
@@ -741,6 +757,7 @@ hconv_dgrad_kernel(const __grid_constant__ HDgradMaps maps, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                  // everything above overlaps the previous kernel's tail (launch_pdl); no-op otherwise
   const uint32_t tmem_d = tmem_base_smem;
   if (tid == 0) h_mark(1, mark_cta);
 
@@ -794,6 +811,7 @@ hconv_dgrad_kernel(const __grid_constant__ HDgradMaps maps, const __grid_constan
     mbar_wait(&bar_done, 0);
     if (tid == 64) h_mark(4, mark_cta);
     tc_fence_after();
+    if (epi.pdl_late) pdl_launch_dependents();
     float* slab = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw))) + (warp & 3) * 32 * BN;
     stage_accumulator<BN>(tmem_d + ((uint32_t)lane_base << 16), slab, lane, true);
     if (tid == 64) h_mark(5, mark_cta);
@@ -823,6 +841,7 @@ hconv_dgrad_pers_kernel(const __grid_constant__ HDgradMaps maps, const __grid_co
   __shared__ __align__(8) uint64_t bar_full[STAGES], bar_empty[STAGES], acc_full[2], acc_empty[2], bar_b;
   __shared__ uint32_t tmem_base_smem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_launch_dependents();
   const int cb = P.Cout / KE;
   const uint32_t res_b = base + STAGES * A_BYTES + SLAB;     // box ((ky * kw + kx) * cb + co-block)
 
@@ -841,6 +860,7 @@ hconv_dgrad_pers_kernel(const __grid_constant__ HDgradMaps maps, const __grid_co
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                  // everything above overlaps the previous kernel's tail (launch_pdl); no-op otherwise
   const uint32_t tmem_d = tmem_base_smem;
 
   auto phase_of = [&](int t) {
@@ -946,7 +966,7 @@ static int launch_hdgrad_pers_s(const HDgradMaps& maps, const CUtensorMap& mw, c
     B200RL_CUDA_OK(cudaFuncSetAttribute(hconv_dgrad_pers_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr = smem;
   }
-  hconv_dgrad_pers_kernel<BN, STAGES><<<std::min(tiles, kNumSMs), H_THREADS, smem, s>>>(maps, mw, P, e, tiles, kh);
+  B200RL_CUDA_OK(launch_pdl(hconv_dgrad_pers_kernel<BN, STAGES>, dim3(std::min(tiles, kNumSMs)), dim3(H_THREADS), smem, s, maps, mw, P, e, tiles, kh));
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }
@@ -971,7 +991,9 @@ static int launch_hdgrad(const HDgradMaps& maps, const CUtensorMap& mw, const HD
     B200RL_CUDA_OK(cudaFuncSetAttribute(hconv_dgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr = true;
   }
-  hconv_dgrad_kernel<BN><<<tiles, H_THREADS, smem, s>>>(maps, mw, P, e);
+  Epilogue el = e;
+  el.pdl_late = pdl_late_mode();
+  B200RL_CUDA_OK(launch_pdl(hconv_dgrad_kernel<BN>, dim3(tiles), dim3(H_THREADS), smem, s, maps, mw, P, el));
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }

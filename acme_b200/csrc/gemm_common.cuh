@@ -19,6 +19,8 @@ struct Epilogue {
   int mask_bf16;       // `mask` holds __nv_bfloat16
   float scale;         // accumulator multiplier applied before the bias; 0 means 1 (conv1 on integer-valued frames: 1/255)
   const int* row_map;  // nullable: GEMM row r is output / mask row row_map[r] (phase-ordered conv data gradient, fp32 path)
+  int pdl_late;        // programmatic dependent launch: release the dependents when the accumulator is ready (1) instead of at
+                       // CTA start (0): early-scheduled dependents hold SM slots that other streams' kernels could use
 };
 __device__ __forceinline__ float epi_scale(const Epilogue& e) { return e.scale == 0.f ? 1.f : e.scale; }
 

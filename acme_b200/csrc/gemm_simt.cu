@@ -148,6 +148,8 @@ struct DgradPhaseWeights {
 };
 // row_map[base(phase) + rank of the pixel inside its phase] = pixel, for all s^2 phases at once
 __global__ void dgrad_row_map_kernel(b200rl_conv_geom g, int* __restrict__ map) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= g.B * g.H * g.W) return;
   const int s = g.stride;
@@ -165,6 +167,10 @@ __global__ void dgrad_row_map_kernel(b200rl_conv_geom g, int* __restrict__ map) 
 template <class AL, class BL, int TM, int TN>
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_kernel(AL a, BL b, Epilogue epi, int M, int N, int K, int k_per_split) {
+  // no early pdl_launch_dependents(): this kernel runs for tens of microseconds beside other streams' GEMMs, and a
+  // dependent grid parked on the SMs (a 2,000-CTA split-K finish fills every thread slot) starves them -- measured 2.40
+  // -> 2.60 ms per fp32 step with the trigger here
+  pdl_wait();
   constexpr int TBM = 16 * TM, TBN = 16 * TN, LA = TM / 4, LB = TN / 4;
   __shared__ __align__(16) float As[2][BK][TBM + 4];
   __shared__ __align__(16) float Bs[2][BK][TBN + 4];
@@ -257,6 +263,8 @@ gemm_kernel(AL a, BL b, Epilogue epi, int M, int N, int K, int k_per_split) {
 }
 
 __global__ void splitk_finish_kernel(Epilogue epi, int M, int N, int splits) {
+  pdl_launch_dependents();
+  pdl_wait();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)M * N) return;
   const int row = (int)(i / N), col = (int)(i % N);
@@ -285,6 +293,8 @@ __global__ void splitk_finish_kernel(Epilogue epi, int M, int N, int splits) {
 // order: deterministic and parallel over the (long) row dimension.
 __global__ void colsum_partial_kernel(int M, int N, const float* __restrict__ x, int ld, int rows_per_block,
                                       float* __restrict__ partial) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float part[8][33];
   const int col = blockIdx.x * 32 + threadIdx.x;
   const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
@@ -300,6 +310,8 @@ __global__ void colsum_partial_kernel(int M, int N, const float* __restrict__ x,
   }
 }
 __global__ void colsum_finish_kernel(int N, int splits, const float* __restrict__ partial, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= N) return;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -319,7 +331,7 @@ __global__ void colsum_finish_kernel(int N, int splits, const float* __restrict_
 }
 
 int launch_splitk_finish(const Epilogue& epi, int M, int N, int splits, cudaStream_t stream) {
-  splitk_finish_kernel<<<(int)ceil_div<long long>((long long)M * N, 256), 256, 0, stream>>>(epi, M, N, splits);
+  B200RL_CUDA_OK(launch_pdl(splitk_finish_kernel, dim3((int)ceil_div<long long>((long long)M * N, 256)), dim3(256), 0, stream, epi, M, N, splits));
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }
@@ -347,12 +359,12 @@ static int launch_gemm(const AL& a, const BL& b, Epilogue epi, int M, int N, int
   splits = ceil_div(K, k_per_split);
   dim3 grid(ceil_div(N, bn), ceil_div(M, bm), splits);
   if (splits > 1) epi.partial = (float*)ws; else epi.partial = nullptr;
-  if (tm == 8 && tn == 8) gemm_kernel<AL, BL, 8, 8><<<grid, GEMM_THREADS, 0, stream>>>(a, b, epi, M, N, K, k_per_split);
-  else if (tm == 8) gemm_kernel<AL, BL, 8, 4><<<grid, GEMM_THREADS, 0, stream>>>(a, b, epi, M, N, K, k_per_split);
-  else gemm_kernel<AL, BL, 4, 4><<<grid, GEMM_THREADS, 0, stream>>>(a, b, epi, M, N, K, k_per_split);
+  if (tm == 8 && tn == 8) B200RL_CUDA_OK(launch_pdl_small(gemm_kernel<AL, BL, 8, 8>, dim3(grid), dim3(GEMM_THREADS), 0, stream, a, b, epi, M, N, K, k_per_split));
+  else if (tm == 8) B200RL_CUDA_OK(launch_pdl_small(gemm_kernel<AL, BL, 8, 4>, dim3(grid), dim3(GEMM_THREADS), 0, stream, a, b, epi, M, N, K, k_per_split));
+  else B200RL_CUDA_OK(launch_pdl_small(gemm_kernel<AL, BL, 4, 4>, dim3(grid), dim3(GEMM_THREADS), 0, stream, a, b, epi, M, N, K, k_per_split));
   B200RL_LAUNCH_OK();
   if (splits > 1) {
-    splitk_finish_kernel<<<(int)ceil_div<long long>((long long)M * N, 256), 256, 0, stream>>>(epi, M, N, splits);
+    B200RL_CUDA_OK(launch_pdl(splitk_finish_kernel, dim3((int)ceil_div<long long>((long long)M * N, 256)), dim3(256), 0, stream, epi, M, N, splits));
     B200RL_LAUNCH_OK();
   }
   return B200RL_OK;
@@ -414,6 +426,8 @@ template <bool BF>
 __global__ void __launch_bounds__(256)
 colsum_vec_kernel(int M, int N, const void* __restrict__ x, int ld, int rows_per_block, float* __restrict__ partial,
                   float* __restrict__ out, int ticket) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float4 red[256];
   __shared__ bool last;
   const int cpr = N >> 2;
@@ -457,7 +471,7 @@ int launch_colsum(int M, int N, const float* x, int ld, float* out, void* ws, in
     blocks = (int)std::max<int64_t>(1, std::min<int64_t>(blocks, ws ? ws_bytes / ((int64_t)N * 4) : 1));
     const int rpb = ceil_div(M, blocks);
     blocks = ceil_div(M, rpb);
-    colsum_vec_kernel<false><<<blocks, 256, 0, stream>>>(M, N, x, ld, rpb, (float*)ws, out, ticket);
+    B200RL_CUDA_OK(launch_pdl_small(colsum_vec_kernel<false>, dim3(blocks), dim3(256), 0, stream, M, N, x, ld, rpb, (float*)ws, out, ticket));
     B200RL_LAUNCH_OK();
     return B200RL_OK;
   }
@@ -465,15 +479,15 @@ int launch_colsum(int M, int N, const float* x, int ld, float* out, void* ws, in
   int splits = std::max(1, std::min(std::min(ceil_div(M, 64), (2 * kNumSMs) / col_blocks), 96));
   splits = (int)std::min<int64_t>(splits, ws ? ws_bytes / ((int64_t)N * 4) : 1);
   if (splits <= 1) {
-    colsum_partial_kernel<<<dim3(col_blocks, 1), dim3(32, 8), 0, stream>>>(M, N, x, ld, M, out);
+    B200RL_CUDA_OK(launch_pdl_small(colsum_partial_kernel, dim3(dim3(col_blocks, 1)), dim3(dim3(32, 8)), 0, stream, M, N, x, ld, M, out));
     B200RL_LAUNCH_OK();
     return B200RL_OK;
   }
   const int rpb = ceil_div(M, splits);
   splits = ceil_div(M, rpb);
-  colsum_partial_kernel<<<dim3(col_blocks, splits), dim3(32, 8), 0, stream>>>(M, N, x, ld, rpb, (float*)ws);
+  B200RL_CUDA_OK(launch_pdl_small(colsum_partial_kernel, dim3(dim3(col_blocks, splits)), dim3(dim3(32, 8)), 0, stream, M, N, x, ld, rpb, (float*)ws));
   B200RL_LAUNCH_OK();
-  colsum_finish_kernel<<<ceil_div(N, 128), 128, 0, stream>>>(N, splits, (const float*)ws, out);
+  B200RL_CUDA_OK(launch_pdl_small(colsum_finish_kernel, dim3(ceil_div(N, 128)), dim3(128), 0, stream, N, splits, (const float*)ws, out));
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }
@@ -492,7 +506,7 @@ int launch_colsum_bf16(int M, int N, const __nv_bfloat16* x, int ld, float* out,
   blocks = (int)std::max<int64_t>(1, std::min<int64_t>(blocks, ws ? ws_bytes / ((int64_t)N * 4) : 1));
   const int rpb = ceil_div(M, blocks);
   blocks = ceil_div(M, rpb);
-  colsum_vec_kernel<true><<<blocks, 256, 0, stream>>>(M, N, x, ld, rpb, (float*)ws, out, ticket);
+  B200RL_CUDA_OK(launch_pdl_small(colsum_vec_kernel<true>, dim3(blocks), dim3(256), 0, stream, M, N, x, ld, rpb, (float*)ws, out, ticket));
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }
@@ -549,7 +563,7 @@ int simt_conv_dgrad(const float* dy, const float* w, float* dx, const b200rl_con
   const int64_t map_bytes = ((int64_t)Min * 4 + 255) & ~(int64_t)255;
   if (phases_env && st > 1 && st <= g.kh && st <= g.kw && ws && wsb > map_bytes) {
     int* map = (int*)ws;
-    dgrad_row_map_kernel<<<ceil_div(Min, 256), 256, 0, s>>>(g, map);
+    B200RL_CUDA_OK(launch_pdl_small(dgrad_row_map_kernel, dim3(ceil_div(Min, 256)), dim3(256), 0, s, g, map));
     B200RL_LAUNCH_OK();
     auto first = [&](int p, int pad) { return ((p - pad) % st + st) % st; };
     auto count = [&](int p, int pad, int n) { const int f = first(p, pad); return f < n ? (n - f + st - 1) / st : 0; };

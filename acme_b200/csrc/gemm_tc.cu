@@ -346,6 +346,8 @@ struct TileMap {
 template <class AL, class BL, int BN>
 __global__ void __launch_bounds__(TC_THREADS)
 tc_gemm_kernel(AL a, BL b, Epilogue epi, int M, int N, int K, int kblocks_per_split) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr bool AMN = AL::MN, BMN = BL::MN;
   using MapA = TileMap<AMN, TBM>;
   using MapB = TileMap<BMN, BN>;
@@ -512,7 +514,7 @@ static int launch_tc_bn(const AL& a, const BL& b, Epilogue epi, int M, int N, in
   splits = ceil_div(kblocks, kps);
   epi.partial = splits > 1 ? (float*)ws : nullptr;
   dim3 grid(ceil_div(N, BN), ceil_div(M, TBM), splits);
-  tc_gemm_kernel<AL, BL, BN><<<grid, TC_THREADS, smem, stream>>>(a, b, epi, M, N, K, kps);
+  B200RL_CUDA_OK(launch_pdl(tc_gemm_kernel<AL, BL, BN>, dim3(grid), dim3(TC_THREADS), smem, stream, a, b, epi, M, N, K, kps));
   B200RL_LAUNCH_OK();
   if (splits > 1) return launch_splitk_finish(epi, M, N, splits, stream);
   return B200RL_OK;

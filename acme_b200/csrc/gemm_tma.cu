@@ -110,6 +110,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   __shared__ uint32_t tmem_base_smem;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (!epi.pdl_late) pdl_launch_dependents();
   const int row0 = blockIdx.y * GBM, col0 = blockIdx.x * BN;
   const int total_kblocks = (K + GBK - 1) / GBK;
   const int kb_begin = blockIdx.z * kblocks_per_split;
@@ -127,6 +128,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                  // the set-up above overlaps the previous kernel's tail (launch_pdl); no-op otherwise
   const uint32_t tmem_d = tmem_base_smem;
   if (tid == 0) tm_mark(0);
 
@@ -229,6 +231,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       mbar_wait(&bar_done, 0);
       tc_fence_after();
     }
+    if (epi.pdl_late) pdl_launch_dependents();
     if (tid == 64) tm_mark(10);
     const int lane_base = (warp & 3) * 32;
     if (epi.transpose_out && !epi.partial) {
@@ -287,7 +290,8 @@ static int launch_tma_bn(const CUtensorMap& ma, const CUtensorMap& mb, Epilogue 
       B200RL_CUDA_OK(cudaFuncSetAttribute(tma_gemm_kernel<AMN, BMN, BN, DS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       attr = true;
     }
-    tma_gemm_kernel<AMN, BMN, BN, DS><<<grid, G_THREADS, smem, stream>>>(ma, mb, epi, M, N, K, kps, conv);
+    epi.pdl_late = pdl_late_mode();
+    B200RL_CUDA_OK(launch_pdl(tma_gemm_kernel<AMN, BMN, BN, DS>, dim3(grid), dim3(G_THREADS), smem, stream, ma, mb, epi, M, N, K, kps, conv));
   } else {
     constexpr int smem = G_STAGES * (GBM * 128 + BN * 128) + 1024;
     static bool attr = false;
@@ -295,7 +299,8 @@ static int launch_tma_bn(const CUtensorMap& ma, const CUtensorMap& mb, Epilogue 
       B200RL_CUDA_OK(cudaFuncSetAttribute(tma_gemm_kernel<AMN, BMN, BN, G_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       attr = true;
     }
-    tma_gemm_kernel<AMN, BMN, BN, G_STAGES><<<grid, G_THREADS, smem, stream>>>(ma, mb, epi, M, N, K, kps, conv);
+    epi.pdl_late = pdl_late_mode();
+    B200RL_CUDA_OK(launch_pdl(tma_gemm_kernel<AMN, BMN, BN, G_STAGES>, dim3(grid), dim3(G_THREADS), smem, stream, ma, mb, epi, M, N, K, kps, conv));
   }
   B200RL_LAUNCH_OK();
   if (splits > 1) return launch_splitk_finish(epi, M, N, splits, stream);
@@ -568,6 +573,7 @@ tma_conv_dgrad_kernel(const __grid_constant__ DgradMaps maps, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_d = tmem_base_smem;
 
   if (warp == 0 && lane == 0) {
@@ -607,6 +613,7 @@ tma_conv_dgrad_kernel(const __grid_constant__ DgradMaps maps, const __grid_const
   } else if (warp >= 2) {
     mbar_wait(&bar_done, 0);
     tc_fence_after();
+    pdl_launch_dependents();   // dependents are scheduled while this tile's epilogue runs
     const int lane_base = (warp & 3) * 32;
     const int row = row0 + lane_base + lane;
     long long orow = -1;   // destination pixel of this lane's accumulator row
@@ -634,7 +641,7 @@ static int launch_dgrad(const DgradMaps& maps, const CUtensorMap& mw, const Dgra
     B200RL_CUDA_OK(cudaFuncSetAttribute(tma_conv_dgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr = true;
   }
-  tma_conv_dgrad_kernel<BN><<<tiles, G_THREADS, smem, s>>>(maps, mw, P, dx, mask, mask_act);
+  B200RL_CUDA_OK(launch_pdl(tma_conv_dgrad_kernel<BN>, dim3(tiles), dim3(G_THREADS), smem, s, maps, mw, P, dx, mask, mask_act));
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }

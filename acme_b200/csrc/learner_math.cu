@@ -14,6 +14,8 @@ namespace b200rl {
 // ------------------------------------------------------------------------------ Philox4x32-10 (common.cuh)
 __global__ void uniform_kernel(float* __restrict__ out, int n, unsigned long long seed,
                                const long long* __restrict__ step_dev, long long step_offset) {
+  pdl_launch_dependents();
+  pdl_wait();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const unsigned long long step = (unsigned long long)((step_dev ? *step_dev : 0) + step_offset);
@@ -60,6 +62,8 @@ __device__ __forceinline__ float is_weight_norm(double raw, double wmax, int fla
 
 __global__ void __launch_bounds__(1024)
 is_weight_max_kernel(int B, const float* __restrict__ prob, double beta, double* __restrict__ out, int flags) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double scratch[32];
   double m = 0.0;
   for (int b = threadIdx.x; b < B; b += blockDim.x) m = fmax(m, is_weight_raw(prob[b], beta, flags));
@@ -75,6 +79,8 @@ dqn_td_kernel(int B, int A, const float* __restrict__ q_tm1, const float* __rest
               float grad_scale, float* __restrict__ td_out, float* __restrict__ loss_ps,
               float* __restrict__ weight, float* __restrict__ priority, float* __restrict__ dq,
               float* __restrict__ loss_mean, int flags) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double scratch_d[32];
   __shared__ float scratch_f[32];
   double wmax = 0.0;
@@ -128,6 +134,8 @@ __global__ void c51_loss_kernel(int K, float vmin, float vmax, const float* __re
                                 const float* __restrict__ D, float gamma, float grad_scale,
                                 float* __restrict__ target_out, float* __restrict__ loss_ps,
                                 float* __restrict__ dlogits) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];
   float* p = sm;          // softmax(logits_t)          [K]
   float* zc = sm + K;     // clip(R + Dg * z_j)         [K]
@@ -187,6 +195,8 @@ c51_loss_warp_kernel(int B, int K, float vmin, float vmax, const float* __restri
                      const float* __restrict__ logits_t, const float* __restrict__ R, const float* __restrict__ D,
                      float gamma, float grad_scale, float* __restrict__ target_out, float* __restrict__ loss_ps,
                      float* __restrict__ dlogits) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s_p[kC51WarpsPerCta][64], s_zc[kC51WarpsPerCta][64];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * kC51WarpsPerCta + w;
@@ -266,6 +276,8 @@ c51_loss_warp_kernel(int B, int K, float vmin, float vmax, const float* __restri
 __global__ void td_learning_kernel(int B, const float* __restrict__ v_tm1, const float* __restrict__ v_t,
                                    const float* __restrict__ R, const float* __restrict__ D, float gamma, float grad_scale,
                                    float* __restrict__ td_out, float* __restrict__ loss_ps, float* __restrict__ dv) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const float pcont = __fmul_rn(gamma, D[b]);                        // discount * d_t, learning.py:169,193
@@ -277,6 +289,8 @@ __global__ void td_learning_kernel(int B, const float* __restrict__ v_tm1, const
 }
 
 __global__ void __launch_bounds__(1024) mean_kernel(const float* __restrict__ x, int n, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float scratch[32];
   float s = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
@@ -287,6 +301,8 @@ __global__ void __launch_bounds__(1024) mean_kernel(const float* __restrict__ x,
 // distributions.py:64-66: q = sum_i softmax(l)_i z_i ; warp per row
 __global__ void c51_mean_kernel(int B, int K, float vmin, float vmax, const float* __restrict__ logits,
                                 const float* __restrict__ dq, float* __restrict__ q, float* __restrict__ dlogits) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (b >= B) return;
@@ -316,6 +332,8 @@ __global__ void c51_mean_kernel(int B, int K, float vmin, float vmax, const floa
 // acme/tf/losses/dpg.py:41-57 (tf.clip_by_norm: t * clip / max(||t||, clip)); warp per row
 __global__ void dpg_kernel(int B, int A, const float* __restrict__ dqda, float clip, int clip_norm,
                            float grad_scale, float* __restrict__ da, float* __restrict__ loss_ps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (b >= B) return;
@@ -369,7 +387,11 @@ __device__ __forceinline__ float adam_one(float& p, float g, float& m, float& v,
 // flight to run at HBM speed; p/m/v are read-modify-write, g is read once (streamed through the read-only path).
 // VPT = float4 vectors per array per thread per iteration: 2 for the full-occupancy launch, 4 for launches limited to a
 // few CTAs per SM (an update running beside other kernels): fewer threads, the same bytes in flight.
-template <int VPT>
+// CS: p / g / m / v move with the cache-streaming policy (ld.global.cs / st.global.cs, evict-first): the update touches
+// 225 MB once per step, more than the L2 holds, so keeping its lines only evicts what the network kernels running beside
+// (or right after) it still want -- activations, the bf16 weight shadow (written with the default policy: the next
+// forward reads it).
+template <int VPT, bool CS>
 __global__ void __launch_bounds__(256)
 adam_kernel(long long n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
             float* __restrict__ v, const long long* __restrict__ step_dev, float lr, double b1,
@@ -377,6 +399,8 @@ adam_kernel(long long n, float* __restrict__ p, const float* __restrict__ g, flo
             __nv_bfloat16* __restrict__ shadow) {
   // the double-precision powers cost a few hundred FP64 instructions: one thread per CTA evaluates them
   __shared__ float bc_sh[2];
+  pdl_launch_dependents();
+  pdl_wait();
   if (threadIdx.x == 0) {
     const double t = (double)(*step_dev + 1);
     bc_sh[0] = (float)(1.0 - pow(b1, t));
@@ -396,10 +420,17 @@ adam_kernel(long long n, float* __restrict__ p, const float* __restrict__ g, flo
     float4 pq[VPT], gq[VPT], mq[VPT], vq[VPT];
 #pragma unroll
     for (int h = 0; h < VPT; ++h) {
-      pq[h] = *reinterpret_cast<const float4*>(p + i + 4 * h);
-      gq[h] = __ldg(reinterpret_cast<const float4*>(g + i + 4 * h));
-      mq[h] = *reinterpret_cast<const float4*>(m + i + 4 * h);
-      vq[h] = *reinterpret_cast<const float4*>(v + i + 4 * h);
+      if (CS) {
+        pq[h] = __ldcs(reinterpret_cast<const float4*>(p + i + 4 * h));
+        gq[h] = __ldcs(reinterpret_cast<const float4*>(g + i + 4 * h));
+        mq[h] = __ldcs(reinterpret_cast<const float4*>(m + i + 4 * h));
+        vq[h] = __ldcs(reinterpret_cast<const float4*>(v + i + 4 * h));
+      } else {
+        pq[h] = *reinterpret_cast<const float4*>(p + i + 4 * h);
+        gq[h] = __ldg(reinterpret_cast<const float4*>(g + i + 4 * h));
+        mq[h] = *reinterpret_cast<const float4*>(m + i + 4 * h);
+        vq[h] = *reinterpret_cast<const float4*>(v + i + 4 * h);
+      }
     }
 #pragma unroll
     for (int h = 0; h < VPT; ++h) {
@@ -407,9 +438,15 @@ adam_kernel(long long n, float* __restrict__ p, const float* __restrict__ g, flo
       adam_one(pq[h].y, gq[h].y, mq[h].y, vq[h].y, c);
       adam_one(pq[h].z, gq[h].z, mq[h].z, vq[h].z, c);
       adam_one(pq[h].w, gq[h].w, mq[h].w, vq[h].w, c);
-      *reinterpret_cast<float4*>(p + i + 4 * h) = pq[h];
-      *reinterpret_cast<float4*>(m + i + 4 * h) = mq[h];
-      *reinterpret_cast<float4*>(v + i + 4 * h) = vq[h];
+      if (CS) {
+        __stcs(reinterpret_cast<float4*>(p + i + 4 * h), pq[h]);
+        __stcs(reinterpret_cast<float4*>(m + i + 4 * h), mq[h]);
+        __stcs(reinterpret_cast<float4*>(v + i + 4 * h), vq[h]);
+      } else {
+        *reinterpret_cast<float4*>(p + i + 4 * h) = pq[h];
+        *reinterpret_cast<float4*>(m + i + 4 * h) = mq[h];
+        *reinterpret_cast<float4*>(v + i + 4 * h) = vq[h];
+      }
     }
     if (shadow) {
 #pragma unroll
@@ -434,6 +471,8 @@ adam_kernel(long long n, float* __restrict__ p, const float* __restrict__ g, flo
 
 // tf.clip_by_global_norm (acme/agents/tf/d4pg/learning.py:235-237), two fixed-order stages
 __global__ void __launch_bounds__(256) sumsq_partial_kernel(long long n, const float* __restrict__ g, float* __restrict__ partial) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double scratch[32];
   double s = 0.0;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -444,6 +483,8 @@ __global__ void __launch_bounds__(256) sumsq_partial_kernel(long long n, const f
 }
 __global__ void __launch_bounds__(256) norm_finish_kernel(int nparts, const float* __restrict__ partial, float clip,
                                                          float* __restrict__ scale_out, float* __restrict__ norm_out) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double scratch[32];
   double s = 0.0;
   for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += (double)partial[i];
@@ -457,12 +498,16 @@ __global__ void __launch_bounds__(256) norm_finish_kernel(int nparts, const floa
 
 __global__ void copy_if_period_kernel(long long n16, int4* __restrict__ dst, const int4* __restrict__ src,
                                       const long long* __restrict__ step_dev, long long period, long long phase) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (((*step_dev) + phase) % period != 0) return;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n16; i += stride) dst[i] = __ldg(src + i);
 }
-__global__ void step_increment_kernel(long long* step) { *step += 1; }
+__global__ void step_increment_kernel(long long* step) {
+  pdl_launch_dependents();
+  pdl_wait(); *step += 1; }
 
 // The end of a learner step in one launch: target <- online (parameters and, if given, their bf16 shadow) when
 // (*step + phase) % period == 0, then *step += 1 and (if given) *counter2 += 1.  Every CTA reads *step when it starts;
@@ -472,6 +517,7 @@ __global__ void __launch_bounds__(256)
 learner_tail_kernel(long long n16_a, int4* __restrict__ dst_a, const int4* __restrict__ src_a, long long n16_b,
                     int4* __restrict__ dst_b, const int4* __restrict__ src_b, long long* __restrict__ step_dev, long long period,
                     long long phase, long long* __restrict__ counter2, int ticket) {
+  pdl_wait();
   const bool due = period > 0 && ((*step_dev) + phase) % period == 0;
   if (due) {
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -499,6 +545,8 @@ __device__ __forceinline__ float act_grad_from_output(float y, int act) {
   }
 }
 __global__ void act_bwd_kernel(long long n, float* __restrict__ dy, const float* __restrict__ y, int act) {
+  pdl_launch_dependents();
+  pdl_wait();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) dy[i] *= act_grad_from_output(y[i], act);
@@ -506,6 +554,8 @@ __global__ void act_bwd_kernel(long long n, float* __restrict__ dy, const float*
 
 // acme/tf/networks/duelling.py:51-59
 __global__ void duelling_fwd_kernel(int B, int A, const float* __restrict__ value, const float* __restrict__ adv, float* __restrict__ q) {
+  pdl_launch_dependents();
+  pdl_wait();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   float s = 0.f;
@@ -514,6 +564,8 @@ __global__ void duelling_fwd_kernel(int B, int A, const float* __restrict__ valu
   for (int a = 0; a < A; ++a) q[(size_t)b * A + a] = v + (adv[(size_t)b * A + a] - mean);
 }
 __global__ void duelling_bwd_kernel(int B, int A, const float* __restrict__ dq, float* __restrict__ dvalue, float* __restrict__ dadv) {
+  pdl_launch_dependents();
+  pdl_wait();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   float s = 0.f;
@@ -542,6 +594,8 @@ __global__ void __launch_bounds__(256)
 duelling_head_fwd_kernel(int B, int A, const float* __restrict__ h, int ldh, const float* __restrict__ wv,
                          const float* __restrict__ bv, const float* __restrict__ wa, const float* __restrict__ ba,
                          float* __restrict__ val, float* __restrict__ adv, float* __restrict__ q) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int H = 32 * HPL;
   extern __shared__ __align__(16) float sw[];   // [A + 1][H]: value row, then advantage rows
   stage_head_weights(sw, wv, wa, A, H);
@@ -655,6 +709,8 @@ dqn_head_td_kernel(HeadTdArgs p) {
   __shared__ __align__(8) unsigned long long bar;
   __shared__ float q_other[kHeadSamples][2][32];  // [sample][0 = target(o_t), 1 = online(o_t)][action]
   float* swt = sw + (size_t)(p.A + 1) * H;
+  pdl_launch_dependents();
+  pdl_wait();
   // the four weight blocks arrive by bulk async copies (one instruction each, completion on an mbarrier) while the
   // warps already fetch their hidden rows
   if (threadIdx.x == 0) {
@@ -780,6 +836,8 @@ __global__ void __launch_bounds__(256)
 duelling_head_bwd_dh_kernel(int B, int A, int H, const float* __restrict__ dq, const float* __restrict__ h, int ldh,
                             const float* __restrict__ wv, const float* __restrict__ wa, float* __restrict__ dval,
                             float* __restrict__ dadv, float* __restrict__ dh, int lddh) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int per = H >> 2;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * per) return;
@@ -812,6 +870,8 @@ duelling_head_bwd_dh_kernel(int B, int A, int H, const float* __restrict__ dq, c
 __global__ void __launch_bounds__(128)
 duelling_head_bwd_dw_kernel(int B, int A, int H, const float* __restrict__ dval, const float* __restrict__ dadv,
                             const float* __restrict__ h, int ldh, float* __restrict__ partial) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int a = (int)blockIdx.y - 1;   // -1 = value stream
   if (k >= H) return;
@@ -841,6 +901,8 @@ duelling_head_bwd_dw_kernel(int B, int A, int H, const float* __restrict__ dval,
 __global__ void duelling_head_bwd_finish_kernel(int A, int H, int segs, const float* __restrict__ partial,
                                                 float* __restrict__ dwv, float* __restrict__ dbv,
                                                 float* __restrict__ dwa, float* __restrict__ dba) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over (A+1) * (H+1)
   if (i >= (A + 1) * (H + 1)) return;
   float t = 0.f;
@@ -855,6 +917,8 @@ __global__ void __launch_bounds__(256)
 layernorm_tanh_fwd_kernel(int N, const float* __restrict__ x, const float* __restrict__ scale,
                           const float* __restrict__ offset, float eps, float* __restrict__ y,
                           float* __restrict__ xhat, float* __restrict__ rstd) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float scratch[32];
   const int b = blockIdx.x;
   const float* xr = x + (size_t)b * N;
@@ -876,6 +940,8 @@ __global__ void __launch_bounds__(256)
 layernorm_tanh_bwd_kernel(int N, const float* __restrict__ dy, const float* __restrict__ y,
                           const float* __restrict__ xhat, const float* __restrict__ rstd,
                           const float* __restrict__ scale, float* __restrict__ dx) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float scratch[32];
   const int b = blockIdx.x;
   const size_t o = (size_t)b * N;
@@ -897,6 +963,8 @@ layernorm_tanh_bwd_kernel(int N, const float* __restrict__ dy, const float* __re
 }
 __global__ void layernorm_param_grad_kernel(int B, int N, const float* __restrict__ dy, const float* __restrict__ y,
                                             const float* __restrict__ xhat, float* __restrict__ dscale, float* __restrict__ doffset) {
+  pdl_launch_dependents();
+  pdl_wait();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   float ds = 0.f, dof = 0.f;
@@ -913,6 +981,8 @@ __global__ void layernorm_param_grad_kernel(int B, int N, const float* __restric
 // acme/tf/networks/rescaling.py:63-74
 __global__ void tanh_to_spec_fwd_kernel(long long n, int A, const float* __restrict__ x, const float* __restrict__ scale,
                                         const float* __restrict__ offset, float* __restrict__ a) {
+  pdl_launch_dependents();
+  pdl_wait();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int c = (int)(i % A);
@@ -922,6 +992,8 @@ __global__ void tanh_to_spec_fwd_kernel(long long n, int A, const float* __restr
 }
 __global__ void tanh_to_spec_bwd_kernel(long long n, int A, const float* __restrict__ da, const float* __restrict__ x,
                                         const float* __restrict__ scale, float* __restrict__ dx) {
+  pdl_launch_dependents();
+  pdl_wait();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int c = (int)(i % A);
@@ -931,6 +1003,8 @@ __global__ void tanh_to_spec_bwd_kernel(long long n, int A, const float* __restr
 
 // acme/tf/utils.py:39-54 batch_concat of two flat tensors, and the slice of its gradient
 __global__ void concat2_kernel(int B, int n0, int n1, const float* __restrict__ x0, const float* __restrict__ x1, float* __restrict__ y) {
+  pdl_launch_dependents();
+  pdl_wait();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int n = n0 + n1;
   if (i >= (long long)B * n) return;
@@ -938,6 +1012,8 @@ __global__ void concat2_kernel(int B, int n0, int n1, const float* __restrict__ 
   y[i] = c < n0 ? x0[(size_t)b * n0 + c] : x1[(size_t)b * n1 + (c - n0)];
 }
 __global__ void split_second_kernel(int B, int n0, int n1, const float* __restrict__ dy, float* __restrict__ dx1) {
+  pdl_launch_dependents();
+  pdl_wait();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * n1) return;
   int b = (int)(i / n1), c = (int)(i % n1);
@@ -946,6 +1022,8 @@ __global__ void split_second_kernel(int B, int n0, int n1, const float* __restri
 
 // ---- recurrent replay: acme/agents/tf/r2d2/learning.py:230-236 and :170-176
 __global__ void seq_priority_kernel(int T, int B, const float* __restrict__ err, float eta, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   float mx = 0.f, sum = 0.f;
@@ -960,6 +1038,8 @@ __global__ void seq_priority_kernel(int T, int B, const float* __restrict__ err,
 
 __global__ void __launch_bounds__(1024)
 seq_is_weights_kernel(int B, const float* __restrict__ prob, double N, double beta, float* __restrict__ w) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double red[32];
   double m = 0.0;
   for (int b = threadIdx.x; b < B; b += blockDim.x) m = fmax(m, pow(1.0 / (N * (double)prob[b]), beta));
@@ -991,14 +1071,14 @@ extern "C" int b200rl_uniform(float* out, int32_t n, uint64_t seed, const int64_
                               int64_t step_offset, void* stream) {
   B200RL_REQUIRE(out && n >= 0, "bad argument");
   if (n == 0) return B200RL_OK;
-  uniform_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(out, n, seed, (const long long*)step_dev, step_offset);
+  B200RL_CUDA_OK(launch_pdl_small(uniform_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, as_stream(stream), out, n, seed, (const long long*)step_dev, step_offset));
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }
 
 extern "C" int b200rl_seq_priority(int32_t T, int32_t B, const float* err_tb, float eta, float* priority_out, void* stream) {
   B200RL_REQUIRE(err_tb && priority_out && T >= 1 && B >= 1, "bad argument");
-  seq_priority_kernel<<<(B + 127) / 128, 128, 0, as_stream(stream)>>>(T, B, err_tb, eta, priority_out);
+  B200RL_CUDA_OK(launch_pdl_small(seq_priority_kernel, dim3((B + 127) / 128), dim3(128), 0, as_stream(stream), T, B, err_tb, eta, priority_out));
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }
@@ -1006,14 +1086,14 @@ extern "C" int b200rl_seq_priority(int32_t T, int32_t B, const float* err_tb, fl
 extern "C" int b200rl_seq_is_weights(int32_t B, const float* prob, double table_size, double is_exponent, float* w_out,
                                      void* stream) {
   B200RL_REQUIRE(prob && w_out && B >= 1 && table_size > 0, "bad argument");
-  seq_is_weights_kernel<<<1, B >= 1024 ? 1024 : ((B + 31) / 32) * 32, 0, as_stream(stream)>>>(B, prob, table_size, is_exponent, w_out);
+  B200RL_CUDA_OK(launch_pdl_small(seq_is_weights_kernel, dim3(1), dim3(B >= 1024 ? 1024 : ((B + 31) / 32) * 32), 0, as_stream(stream), B, prob, table_size, is_exponent, w_out));
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }
 
 extern "C" int b200rl_is_weight_max(int32_t B, const float* prob, double beta, double* out, int32_t flags, void* stream) {
   B200RL_REQUIRE(prob && out && B >= 1, "bad argument");
-  is_weight_max_kernel<<<1, B >= 1024 ? 1024 : ((B + 31) / 32) * 32, 0, as_stream(stream)>>>(B, prob, beta, out, flags);
+  B200RL_CUDA_OK(launch_pdl_small(is_weight_max_kernel, dim3(1), dim3(B >= 1024 ? 1024 : ((B + 31) / 32) * 32), 0, as_stream(stream), B, prob, beta, out, flags));
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }
@@ -1028,9 +1108,9 @@ extern "C" int b200rl_dqn_td(int32_t B, int32_t A, const float* q_tm1, const flo
   B200RL_REQUIRE(B >= 1 && A >= 1, "bad shape");
   B200RL_REQUIRE(delta >= 0.f, "quadratic_linear_boundary must be >= 0");  // huber.py:45-46
   int threads = B >= 1024 ? 1024 : ((B + 31) / 32) * 32;
-  dqn_td_kernel<<<1, threads, 0, as_stream(stream)>>>(B, A, q_tm1, q_tv, q_ts, a_tm1, R, D, prob, gamma, delta, beta,
+  B200RL_CUDA_OK(launch_pdl_small(dqn_td_kernel, dim3(1), dim3(threads), 0, as_stream(stream), B, A, q_tm1, q_tv, q_ts, a_tm1, R, D, prob, gamma, delta, beta,
                                                      max_abs_reward, wmax_dev, grad_scale, td, loss_ps, weight,
-                                                     priority, dq, loss_mean, flags);
+                                                     priority, dq, loss_mean, flags));
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }
@@ -1043,16 +1123,15 @@ extern "C" int b200rl_c51_loss(int32_t B, int32_t K, float vmin, float vmax, con
   B200RL_REQUIRE(B >= 1 && K >= 2 && K <= 1024, "bad shape");
   static const int dense_env = getenv("B200RL_C51_DENSE") ? atoi(getenv("B200RL_C51_DENSE")) : 0;
   if (K <= 64 && !dense_env) {
-    c51_loss_warp_kernel<<<(B + kC51WarpsPerCta - 1) / kC51WarpsPerCta, 32 * kC51WarpsPerCta, 0, as_stream(stream)>>>(
-        B, K, vmin, vmax, logits_tm1, logits_t, R, D, gamma, grad_scale, target, loss_ps, dlogits);
+    B200RL_CUDA_OK(launch_pdl_small(c51_loss_warp_kernel, dim3((B + kC51WarpsPerCta - 1) / kC51WarpsPerCta), dim3(32 * kC51WarpsPerCta), 0, as_stream(stream), B, K, vmin, vmax, logits_tm1, logits_t, R, D, gamma, grad_scale, target, loss_ps, dlogits));
   } else {
     int threads = ((K + 31) / 32) * 32;
-    c51_loss_kernel<<<B, threads, 3 * K * sizeof(float), as_stream(stream)>>>(K, vmin, vmax, logits_tm1, logits_t, R, D, gamma,
-                                                                             grad_scale, target, loss_ps, dlogits);
+    B200RL_CUDA_OK(launch_pdl_small(c51_loss_kernel, dim3(B), dim3(threads), 3 * K * sizeof(float), as_stream(stream), K, vmin, vmax, logits_tm1, logits_t, R, D, gamma,
+                                                                             grad_scale, target, loss_ps, dlogits));
   }
   B200RL_LAUNCH_OK();
   if (loss_mean) {
-    mean_kernel<<<1, 256, 0, as_stream(stream)>>>(loss_ps, B, loss_mean);
+    B200RL_CUDA_OK(launch_pdl_small(mean_kernel, dim3(1), dim3(256), 0, as_stream(stream), loss_ps, B, loss_mean));
     B200RL_LAUNCH_OK();
   }
   return B200RL_OK;
@@ -1061,10 +1140,10 @@ extern "C" int b200rl_c51_loss(int32_t B, int32_t K, float vmin, float vmax, con
 extern "C" int b200rl_td_learning(int32_t B, const float* v_tm1, const float* v_t, const float* R, const float* D, float gamma,
                                   float grad_scale, float* td, float* loss_ps, float* dv_tm1, float* loss_mean, void* stream) {
   B200RL_REQUIRE(v_tm1 && v_t && R && D && loss_ps && B >= 1, "bad argument");
-  td_learning_kernel<<<ceil_div(B, 128), 128, 0, as_stream(stream)>>>(B, v_tm1, v_t, R, D, gamma, grad_scale, td, loss_ps, dv_tm1);
+  B200RL_CUDA_OK(launch_pdl_small(td_learning_kernel, dim3(ceil_div(B, 128)), dim3(128), 0, as_stream(stream), B, v_tm1, v_t, R, D, gamma, grad_scale, td, loss_ps, dv_tm1));
   B200RL_LAUNCH_OK();
   if (loss_mean) {
-    mean_kernel<<<1, 256, 0, as_stream(stream)>>>(loss_ps, B, loss_mean);
+    B200RL_CUDA_OK(launch_pdl_small(mean_kernel, dim3(1), dim3(256), 0, as_stream(stream), loss_ps, B, loss_mean));
     B200RL_LAUNCH_OK();
   }
   return B200RL_OK;
@@ -1072,14 +1151,14 @@ extern "C" int b200rl_td_learning(int32_t B, const float* v_tm1, const float* v_
 
 extern "C" int b200rl_c51_mean_fwd(int32_t B, int32_t K, float vmin, float vmax, const float* logits, float* q, void* stream) {
   B200RL_REQUIRE(logits && q && B >= 1 && K >= 2, "bad argument");
-  c51_mean_kernel<<<ceil_div(B * 32, 128), 128, 0, as_stream(stream)>>>(B, K, vmin, vmax, logits, nullptr, q, nullptr);
+  B200RL_CUDA_OK(launch_pdl_small(c51_mean_kernel, dim3(ceil_div(B * 32, 128)), dim3(128), 0, as_stream(stream), B, K, vmin, vmax, logits, nullptr, q, nullptr));
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }
 extern "C" int b200rl_c51_mean_bwd(int32_t B, int32_t K, float vmin, float vmax, const float* logits, const float* dq,
                                    float* dlogits, void* stream) {
   B200RL_REQUIRE(logits && dlogits && B >= 1 && K >= 2, "bad argument");
-  c51_mean_kernel<<<ceil_div(B * 32, 128), 128, 0, as_stream(stream)>>>(B, K, vmin, vmax, logits, dq, nullptr, dlogits);
+  B200RL_CUDA_OK(launch_pdl_small(c51_mean_kernel, dim3(ceil_div(B * 32, 128)), dim3(128), 0, as_stream(stream), B, K, vmin, vmax, logits, dq, nullptr, dlogits));
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }
@@ -1088,10 +1167,10 @@ extern "C" int b200rl_dpg_action_grad(int32_t B, int32_t A, const float* dqda, f
                                       float grad_scale, float* da, float* loss_ps, float* loss_mean, void* stream) {
   B200RL_REQUIRE(dqda && da && B >= 1 && A >= 1, "bad argument");
   B200RL_REQUIRE(!loss_mean || loss_ps, "loss_mean needs a loss_per_sample buffer");
-  dpg_kernel<<<ceil_div(B * 32, 128), 128, 0, as_stream(stream)>>>(B, A, dqda, clip, clip_norm, grad_scale, da, loss_ps);
+  B200RL_CUDA_OK(launch_pdl_small(dpg_kernel, dim3(ceil_div(B * 32, 128)), dim3(128), 0, as_stream(stream), B, A, dqda, clip, clip_norm, grad_scale, da, loss_ps));
   B200RL_LAUNCH_OK();
   if (loss_mean) {
-    mean_kernel<<<1, 256, 0, as_stream(stream)>>>(loss_ps, B, loss_mean);
+    B200RL_CUDA_OK(launch_pdl_small(mean_kernel, dim3(1), dim3(256), 0, as_stream(stream), loss_ps, B, loss_mean));
     B200RL_LAUNCH_OK();
   }
   return B200RL_OK;
@@ -1111,6 +1190,7 @@ extern "C" int b200rl_debug_stamp(unsigned long long* buf, int slot, void* strea
 extern "C" int b200rl_adam_throttled(int64_t n, float* param, const float* grad, float* m, float* v, const int64_t* step_dev,
                                      float lr, double b1, double b2, float eps, int eps_mode, const float* grad_scale_dev,
                                      void* bf16_shadow, int32_t ctas_per_sm, void* stream);
+#define ADAM_CS_DEFAULT 0   // 1 once measured faster on B200 (gpurun_out/c2_*)
 extern "C" int b200rl_adam(int64_t n, float* param, const float* grad, float* m, float* v, const int64_t* step_dev,
                            float lr, double b1, double b2, float eps, int eps_mode, const float* grad_scale_dev,
                            void* bf16_shadow, void* stream) {
@@ -1131,14 +1211,19 @@ extern "C" int b200rl_adam_throttled(int64_t n, float* param, const float* grad,
   // measured on B200: the 4-vector variant is SLOWER (0.347 vs 0.318 ms per step at full occupancy, no gain beside other
   // kernels): more registers per thread cost more than the extra loads in flight bring.  Kept behind B200RL_ADAM_WIDE=1.
   const bool use_wide = wide > 0;
+  static const int cs = getenv("B200RL_ADAM_CS") ? atoi(getenv("B200RL_ADAM_CS")) : ADAM_CS_DEFAULT;   // cache-streaming accesses
   if (use_wide) {
     int blocks = grid1d((n + 15) / 16, 256, per_sm > 0 ? kNumSMs * per_sm : (1 << 30));
-    adam_kernel<4><<<blocks, 256, 0, as_stream(stream)>>>(n, param, grad, m, v, (const long long*)step_dev, lr, b1, b2, eps,
-                                                         eps_mode, grad_scale_dev, (__nv_bfloat16*)bf16_shadow);
+    adam_kernel<4, false><<<blocks, 256, 0, as_stream(stream)>>>(n, param, grad, m, v, (const long long*)step_dev, lr, b1, b2, eps,
+                                                                eps_mode, grad_scale_dev, (__nv_bfloat16*)bf16_shadow);
   } else {
     int blocks = grid1d((n + 7) / 8, 256, per_sm > 0 ? kNumSMs * per_sm : (1 << 30));
-    adam_kernel<2><<<blocks, 256, 0, as_stream(stream)>>>(n, param, grad, m, v, (const long long*)step_dev, lr, b1, b2, eps,
-                                                         eps_mode, grad_scale_dev, (__nv_bfloat16*)bf16_shadow);
+    if (cs)
+      B200RL_CUDA_OK(launch_pdl(adam_kernel<2, true>, dim3(blocks), dim3(256), 0, as_stream(stream), n, param, grad, m, v, (const long long*)step_dev, lr, b1, b2, eps,
+                                                                 eps_mode, grad_scale_dev, (__nv_bfloat16*)bf16_shadow));
+    else
+      B200RL_CUDA_OK(launch_pdl(adam_kernel<2, false>, dim3(blocks), dim3(256), 0, as_stream(stream), n, param, grad, m, v, (const long long*)step_dev, lr, b1, b2, eps,
+                                                                  eps_mode, grad_scale_dev, (__nv_bfloat16*)bf16_shadow));
   }
   B200RL_LAUNCH_OK();
   return B200RL_OK;
@@ -1148,9 +1233,9 @@ extern "C" int b200rl_global_norm_scale(int64_t n, const float* grad, float clip
                                         float* norm_out, void* stream) {
   B200RL_REQUIRE(grad && partial_ws && scale_out && n >= 1, "bad argument");
   int blocks = grid1d(n, 256, 1024);
-  sumsq_partial_kernel<<<blocks, 256, 0, as_stream(stream)>>>(n, grad, partial_ws);
+  B200RL_CUDA_OK(launch_pdl_small(sumsq_partial_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), n, grad, partial_ws));
   B200RL_LAUNCH_OK();
-  norm_finish_kernel<<<1, 256, 0, as_stream(stream)>>>(blocks, partial_ws, clip, scale_out, norm_out);
+  B200RL_CUDA_OK(launch_pdl_small(norm_finish_kernel, dim3(1), dim3(256), 0, as_stream(stream), blocks, partial_ws, clip, scale_out, norm_out));
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }
@@ -1159,8 +1244,7 @@ extern "C" int b200rl_copy_if_period(int64_t n_bytes, void* dst, const void* src
                                      int64_t phase, void* stream) {
   B200RL_REQUIRE(dst && src && step_dev && period >= 1, "bad argument");
   B200RL_REQUIRE(n_bytes % 16 == 0 && (((uintptr_t)dst | (uintptr_t)src) & 15) == 0, "copy must be 16-byte aligned/sized");
-  copy_if_period_kernel<<<grid1d(n_bytes / 16, 256, kNumSMs * 8), 256, 0, as_stream(stream)>>>(
-      n_bytes / 16, (int4*)dst, (const int4*)src, (const long long*)step_dev, period, phase);
+  B200RL_CUDA_OK(launch_pdl_small(copy_if_period_kernel, dim3(grid1d(n_bytes / 16, 256, kNumSMs * 8)), dim3(256), 0, as_stream(stream), n_bytes / 16, (int4*)dst, (const int4*)src, (const long long*)step_dev, period, phase));
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }
@@ -1173,16 +1257,16 @@ extern "C" int b200rl_learner_tail(int64_t n_bytes_a, void* dst_a, const void* s
   B200RL_REQUIRE((n_bytes_a == 0 || (dst_a && src_a)) && (n_bytes_b == 0 || (dst_b && src_b)), "null buffer");
   B200RL_REQUIRE(((((uintptr_t)dst_a | (uintptr_t)src_a | (uintptr_t)dst_b | (uintptr_t)src_b)) & 15) == 0, "buffers must be 16-byte aligned");
   // one ticket per call site is enough: calls on one stream never overlap, and a learner has one tail per step
-  learner_tail_kernel<<<kNumSMs * 4, 256, 0, as_stream(stream)>>>(n_bytes_a / 16, (int4*)dst_a, (const int4*)src_a, n_bytes_b / 16,
-                                                                  (int4*)dst_b, (const int4*)src_b, (long long*)step_dev, period, phase,
-                                                                  (long long*)counter2, 0);
+  B200RL_CUDA_OK(launch_pdl(learner_tail_kernel, dim3(kNumSMs * 4), dim3(256), 0, as_stream(stream), (long long)(n_bytes_a / 16), (int4*)dst_a,
+                            (const int4*)src_a, (long long)(n_bytes_b / 16), (int4*)dst_b, (const int4*)src_b, (long long*)step_dev,
+                            (long long)period, (long long)phase, (long long*)counter2, 0));
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }
 
 extern "C" int b200rl_step_increment(int64_t* step_dev, void* stream) {
   B200RL_REQUIRE(step_dev, "null argument");
-  step_increment_kernel<<<1, 1, 0, as_stream(stream)>>>((long long*)step_dev);
+  B200RL_CUDA_OK(launch_pdl_small(step_increment_kernel, dim3(1), dim3(1), 0, as_stream(stream), (long long*)step_dev));
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }
@@ -1190,20 +1274,20 @@ extern "C" int b200rl_step_increment(int64_t* step_dev, void* stream) {
 extern "C" int b200rl_act_bwd(int64_t n, float* dy, const float* y, int act, void* stream) {
   B200RL_REQUIRE(dy && y && n >= 0, "bad argument");
   if (n == 0 || act == B200RL_ACT_NONE) return B200RL_OK;
-  act_bwd_kernel<<<grid1d(n, 256), 256, 0, as_stream(stream)>>>(n, dy, y, act);
+  B200RL_CUDA_OK(launch_pdl_small(act_bwd_kernel, dim3(grid1d(n, 256)), dim3(256), 0, as_stream(stream), n, dy, y, act));
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }
 
 extern "C" int b200rl_duelling_fwd(int32_t B, int32_t A, const float* value, const float* adv, float* q, void* stream) {
   B200RL_REQUIRE(value && adv && q && B >= 1 && A >= 1, "bad argument");
-  duelling_fwd_kernel<<<ceil_div(B, 128), 128, 0, as_stream(stream)>>>(B, A, value, adv, q);
+  B200RL_CUDA_OK(launch_pdl_small(duelling_fwd_kernel, dim3(ceil_div(B, 128)), dim3(128), 0, as_stream(stream), B, A, value, adv, q));
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }
 extern "C" int b200rl_duelling_bwd(int32_t B, int32_t A, const float* dq, float* dvalue, float* dadv, void* stream) {
   B200RL_REQUIRE(dq && dvalue && dadv && B >= 1 && A >= 1, "bad argument");
-  duelling_bwd_kernel<<<ceil_div(B, 128), 128, 0, as_stream(stream)>>>(B, A, dq, dvalue, dadv);
+  B200RL_CUDA_OK(launch_pdl_small(duelling_bwd_kernel, dim3(ceil_div(B, 128)), dim3(128), 0, as_stream(stream), B, A, dq, dvalue, dadv));
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }
@@ -1231,10 +1315,10 @@ extern "C" int b200rl_duelling_head_fwd(int32_t B, int32_t A, int32_t H, const f
   B200RL_REQUIRE(smem <= 200 * 1024 && H % 4 == 0, "duelling head weights do not fit in shared memory");
   if (int rc = ensure_head_attrs()) return rc;
   switch (H) {
-    case 512: duelling_head_fwd_kernel<16><<<blocks, 256, smem, st>>>(B, A, h, ldh, wv, bv, wa, ba, value, adv, q); break;
-    case 256: duelling_head_fwd_kernel<8><<<blocks, 256, smem, st>>>(B, A, h, ldh, wv, bv, wa, ba, value, adv, q); break;
-    case 128: duelling_head_fwd_kernel<4><<<blocks, 256, smem, st>>>(B, A, h, ldh, wv, bv, wa, ba, value, adv, q); break;
-    case 64: duelling_head_fwd_kernel<2><<<blocks, 256, smem, st>>>(B, A, h, ldh, wv, bv, wa, ba, value, adv, q); break;
+    case 512: B200RL_CUDA_OK(launch_pdl_small(duelling_head_fwd_kernel<16>, dim3(blocks), dim3(256), smem, st, B, A, h, ldh, wv, bv, wa, ba, value, adv, q)); break;
+    case 256: B200RL_CUDA_OK(launch_pdl_small(duelling_head_fwd_kernel<8>, dim3(blocks), dim3(256), smem, st, B, A, h, ldh, wv, bv, wa, ba, value, adv, q)); break;
+    case 128: B200RL_CUDA_OK(launch_pdl_small(duelling_head_fwd_kernel<4>, dim3(blocks), dim3(256), smem, st, B, A, h, ldh, wv, bv, wa, ba, value, adv, q)); break;
+    case 64: B200RL_CUDA_OK(launch_pdl_small(duelling_head_fwd_kernel<2>, dim3(blocks), dim3(256), smem, st, B, A, h, ldh, wv, bv, wa, ba, value, adv, q)); break;
     default: set_error("duelling head: hidden size %d not in {64,128,256,512}", H); return B200RL_EINVAL;
   }
   B200RL_LAUNCH_OK();
@@ -1253,15 +1337,15 @@ extern "C" int b200rl_duelling_head_bwd(int32_t B, int32_t A, int32_t H, const f
   B200RL_REQUIRE(ldh % 4 == 0 && lddh % 4 == 0 &&
                      (((uintptr_t)h | (uintptr_t)dh | (uintptr_t)wv | (uintptr_t)wa) & 15) == 0,
                  "duelling head: rows must be 16-byte aligned");
-  duelling_head_bwd_dh_kernel<<<(int)ceil_div<long long>((long long)B * (H / 4), 256), 256, 0, st>>>(B, A, H, dq, h, ldh, wv, wa,
-                                                                                                     dvalue, dadv, dh, lddh);
+  B200RL_CUDA_OK(launch_pdl_small(duelling_head_bwd_dh_kernel, dim3((int)ceil_div<long long>((long long)B * (H / 4), 256)), dim3(256), 0, st, B, A, H, dq, h, ldh, wv, wa,
+                                                                                                     dvalue, dadv, dh, lddh));
   B200RL_LAUNCH_OK();
   int segs = std::max(1, std::min(B / 32, 8));
   const int64_t per = (int64_t)(A + 1) * (H + 1) * 4;
   segs = (int)std::max<int64_t>(1, std::min<int64_t>(segs, ws_bytes / per));
-  duelling_head_bwd_dw_kernel<<<dim3(ceil_div(H, 128), A + 1, segs), 128, 0, st>>>(B, A, H, dvalue, dadv, h, ldh, (float*)ws);
+  B200RL_CUDA_OK(launch_pdl_small(duelling_head_bwd_dw_kernel, dim3(dim3(ceil_div(H, 128), A + 1, segs)), dim3(128), 0, st, B, A, H, dvalue, dadv, h, ldh, (float*)ws));
   B200RL_LAUNCH_OK();
-  duelling_head_bwd_finish_kernel<<<ceil_div((A + 1) * (H + 1), 256), 256, 0, st>>>(A, H, segs, (const float*)ws, dwv, dbv, dwa, dba);
+  B200RL_CUDA_OK(launch_pdl_small(duelling_head_bwd_finish_kernel, dim3(ceil_div((A + 1) * (H + 1), 256)), dim3(256), 0, st, A, H, segs, (const float*)ws, dwv, dbv, dwa, dba));
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }
@@ -1302,20 +1386,22 @@ extern "C" int b200rl_dqn_head_td(int32_t B, int32_t A, int32_t H, const float* 
   }
   const int blocks = ceil_div(B, kHeadSamples);
   cudaStream_t st = as_stream(stream);
+  cudaError_t e = cudaSuccess;
   switch (H) {
-    case 512: dqn_head_td_kernel<16><<<blocks, kHeadThreads, smem, st>>>(p); break;
-    case 256: dqn_head_td_kernel<8><<<blocks, kHeadThreads, smem, st>>>(p); break;
-    case 128: dqn_head_td_kernel<4><<<blocks, kHeadThreads, smem, st>>>(p); break;
-    case 64: dqn_head_td_kernel<2><<<blocks, kHeadThreads, smem, st>>>(p); break;
+    case 512: e = launch_pdl(dqn_head_td_kernel<16>, dim3(blocks), dim3(kHeadThreads), smem, st, p); break;
+    case 256: e = launch_pdl(dqn_head_td_kernel<8>, dim3(blocks), dim3(kHeadThreads), smem, st, p); break;
+    case 128: e = launch_pdl(dqn_head_td_kernel<4>, dim3(blocks), dim3(kHeadThreads), smem, st, p); break;
+    case 64: e = launch_pdl(dqn_head_td_kernel<2>, dim3(blocks), dim3(kHeadThreads), smem, st, p); break;
     default: set_error("fused duelling head: hidden size %d not in {64,128,256,512}", H); return B200RL_EINVAL;
   }
+  B200RL_CUDA_OK(e);
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }
 
 extern "C" int b200rl_mean(int32_t n, const float* x, float* out, void* stream) {
   B200RL_REQUIRE(x && out && n >= 1, "bad argument");
-  mean_kernel<<<1, 256, 0, as_stream(stream)>>>(x, n, out);
+  B200RL_CUDA_OK(launch_pdl_small(mean_kernel, dim3(1), dim3(256), 0, as_stream(stream), x, n, out));
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }
@@ -1331,9 +1417,9 @@ extern "C" int b200rl_duelling_head_wgrad(int32_t B, int32_t A, int32_t H, const
   int segs = std::max(1, std::min(B / 32, 8));
   const int64_t per = (int64_t)(A + 1) * (H + 1) * 4;
   segs = (int)std::max<int64_t>(1, std::min<int64_t>(segs, ws_bytes / per));
-  duelling_head_bwd_dw_kernel<<<dim3(ceil_div(H, 128), A + 1, segs), 128, 0, st>>>(B, A, H, dvalue, dadv, h, ldh, (float*)ws);
+  B200RL_CUDA_OK(launch_pdl_small(duelling_head_bwd_dw_kernel, dim3(dim3(ceil_div(H, 128), A + 1, segs)), dim3(128), 0, st, B, A, H, dvalue, dadv, h, ldh, (float*)ws));
   B200RL_LAUNCH_OK();
-  duelling_head_bwd_finish_kernel<<<ceil_div((A + 1) * (H + 1), 256), 256, 0, st>>>(A, H, segs, (const float*)ws, dwv, dbv, dwa, dba);
+  B200RL_CUDA_OK(launch_pdl_small(duelling_head_bwd_finish_kernel, dim3(ceil_div((A + 1) * (H + 1), 256)), dim3(256), 0, st, A, H, segs, (const float*)ws, dwv, dbv, dwa, dba));
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }
@@ -1341,7 +1427,7 @@ extern "C" int b200rl_duelling_head_wgrad(int32_t B, int32_t A, int32_t H, const
 extern "C" int b200rl_layernorm_tanh_fwd(int32_t B, int32_t N, const float* x, const float* scale, const float* offset,
                                          float eps, float* y, float* xhat, float* rstd, void* stream) {
   B200RL_REQUIRE(x && scale && offset && y && xhat && rstd && B >= 1 && N >= 1, "bad argument");
-  layernorm_tanh_fwd_kernel<<<B, 256, 0, as_stream(stream)>>>(N, x, scale, offset, eps, y, xhat, rstd);
+  B200RL_CUDA_OK(launch_pdl_small(layernorm_tanh_fwd_kernel, dim3(B), dim3(256), 0, as_stream(stream), N, x, scale, offset, eps, y, xhat, rstd));
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }
@@ -1349,10 +1435,10 @@ extern "C" int b200rl_layernorm_tanh_bwd(int32_t B, int32_t N, const float* dy, 
                                          const float* rstd, const float* scale, float* dx, float* dscale,
                                          float* doffset, void* stream) {
   B200RL_REQUIRE(dy && y && xhat && rstd && scale && dx && B >= 1 && N >= 1, "bad argument");
-  layernorm_tanh_bwd_kernel<<<B, 256, 0, as_stream(stream)>>>(N, dy, y, xhat, rstd, scale, dx);
+  B200RL_CUDA_OK(launch_pdl_small(layernorm_tanh_bwd_kernel, dim3(B), dim3(256), 0, as_stream(stream), N, dy, y, xhat, rstd, scale, dx));
   B200RL_LAUNCH_OK();
   if (dscale && doffset) {
-    layernorm_param_grad_kernel<<<ceil_div(N, 128), 128, 0, as_stream(stream)>>>(B, N, dy, y, xhat, dscale, doffset);
+    B200RL_CUDA_OK(launch_pdl_small(layernorm_param_grad_kernel, dim3(ceil_div(N, 128)), dim3(128), 0, as_stream(stream), B, N, dy, y, xhat, dscale, doffset));
     B200RL_LAUNCH_OK();
   }
   return B200RL_OK;
@@ -1362,7 +1448,7 @@ extern "C" int b200rl_tanh_to_spec_fwd(int32_t B, int32_t A, const float* x, con
                                        float* a, void* stream) {
   B200RL_REQUIRE(x && scale && offset && a && B >= 1 && A >= 1, "bad argument");
   long long n = (long long)B * A;
-  tanh_to_spec_fwd_kernel<<<(int)ceil_div<long long>(n, 256), 256, 0, as_stream(stream)>>>(n, A, x, scale, offset, a);
+  B200RL_CUDA_OK(launch_pdl_small(tanh_to_spec_fwd_kernel, dim3((int)ceil_div<long long>(n, 256)), dim3(256), 0, as_stream(stream), n, A, x, scale, offset, a));
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }
@@ -1370,7 +1456,7 @@ extern "C" int b200rl_tanh_to_spec_bwd(int32_t B, int32_t A, const float* da, co
                                        float* dx, void* stream) {
   B200RL_REQUIRE(da && x && scale && dx && B >= 1 && A >= 1, "bad argument");
   long long n = (long long)B * A;
-  tanh_to_spec_bwd_kernel<<<(int)ceil_div<long long>(n, 256), 256, 0, as_stream(stream)>>>(n, A, da, x, scale, dx);
+  B200RL_CUDA_OK(launch_pdl_small(tanh_to_spec_bwd_kernel, dim3((int)ceil_div<long long>(n, 256)), dim3(256), 0, as_stream(stream), n, A, da, x, scale, dx));
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }
@@ -1378,14 +1464,14 @@ extern "C" int b200rl_tanh_to_spec_bwd(int32_t B, int32_t A, const float* da, co
 extern "C" int b200rl_concat2(int32_t B, int32_t n0, int32_t n1, const float* x0, const float* x1, float* y, void* stream) {
   B200RL_REQUIRE(x0 && x1 && y && B >= 1 && n0 >= 1 && n1 >= 1, "bad argument");
   long long n = (long long)B * (n0 + n1);
-  concat2_kernel<<<(int)ceil_div<long long>(n, 256), 256, 0, as_stream(stream)>>>(B, n0, n1, x0, x1, y);
+  B200RL_CUDA_OK(launch_pdl_small(concat2_kernel, dim3((int)ceil_div<long long>(n, 256)), dim3(256), 0, as_stream(stream), B, n0, n1, x0, x1, y));
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }
 extern "C" int b200rl_split_second(int32_t B, int32_t n0, int32_t n1, const float* dy, float* dx1, void* stream) {
   B200RL_REQUIRE(dy && dx1 && B >= 1 && n0 >= 1 && n1 >= 1, "bad argument");
   long long n = (long long)B * n1;
-  split_second_kernel<<<(int)ceil_div<long long>(n, 256), 256, 0, as_stream(stream)>>>(B, n0, n1, dy, dx1);
+  B200RL_CUDA_OK(launch_pdl_small(split_second_kernel, dim3((int)ceil_div<long long>(n, 256)), dim3(256), 0, as_stream(stream), B, n0, n1, dy, dx1));
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }

@@ -24,6 +24,19 @@ int h_rows_layout(const b200rl_conv_geom& g, int* Hp, int* row_elems);   // gemm
 static thread_local std::string g_last_error;
 static unsigned long long g_launches = 0;
 void count_launch() { __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED); }
+static int g_pdl_override = -1;   // b200rl_debug_set_pdl: 0 / 1 for the launches that follow, -1 = the environment's choice
+bool pdl_enabled() {
+  static const bool on = getenv("B200RL_PDL") ? atoi(getenv("B200RL_PDL")) != 0 : B200RL_PDL_DEFAULT;
+  return g_pdl_override < 0 ? on : g_pdl_override != 0;
+}
+bool pdl_small_enabled() {
+  static const bool on = getenv("B200RL_PDL_SMALL") ? atoi(getenv("B200RL_PDL_SMALL")) != 0 : false;
+  return on;
+}
+int pdl_late_mode() {
+  static const int late = getenv("B200RL_PDL_LATE") ? atoi(getenv("B200RL_PDL_LATE")) : B200RL_PDL_LATE_DEFAULT;
+  return late;
+}
 
 void set_error(const char* fmt, ...) {
   char buf[1024];
@@ -132,6 +145,8 @@ __global__ void __launch_bounds__(256)
 gather_kernel(RingView r, const long long* __restrict__ idx, uint8_t* __restrict__ o_tm1,
               uint8_t* __restrict__ a_tm1, float* __restrict__ R, float* __restrict__ D,
               uint8_t* __restrict__ o_t) {
+  pdl_launch_dependents();
+  pdl_wait();                  // K1's indices
   const int b = blockIdx.x;
   const long long pos = idx[b];
   const int which = blockIdx.y;
@@ -187,6 +202,8 @@ gather_rows_kernel(RingView r, const long long* __restrict__ idx, uint8_t* __res
                    float* __restrict__ R, float* __restrict__ D, uint8_t* __restrict__ o_t, uint4* __restrict__ rows_tm1,
                    uint4* __restrict__ rows_t, int W4 /* 16-byte vectors per image row */, int pad_left, int pad_top, int Hp,
                    int row_v16 /* 16-byte units per padded row */) {
+  pdl_launch_dependents();
+  pdl_wait();                  // K1's indices
   const int b = blockIdx.x;
   const long long pos = idx[b];
   const int which = blockIdx.y;
@@ -477,6 +494,7 @@ static int ensure_device(b200rl_replay* h) {
 }
 
 extern "C" int b200rl_version(void) { return B200RL_VERSION; }
+extern "C" int b200rl_debug_set_pdl(int on) { b200rl::g_pdl_override = on; return 0; }
 extern "C" uint64_t b200rl_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 extern "C" const char* b200rl_last_error(void) { return g_last_error.c_str(); }
 
@@ -1215,11 +1233,11 @@ extern "C" int b200rl_replay_gather(b200rl_replay* h, int32_t B, const int64_t* 
   const bool a16 = (h->cfg.obs_bytes % 16 == 0) && (((uintptr_t)o_tm1 | (uintptr_t)o_t) % 16 == 0);
   const bool a4 = (h->cfg.obs_bytes % 4 == 0) && (((uintptr_t)o_tm1 | (uintptr_t)o_t) % 4 == 0);
   if (a16)
-    gather_kernel<16><<<grid, 256, 0, as_stream(stream)>>>(h->ring, (const long long*)idx_dev, (uint8_t*)o_tm1, (uint8_t*)a_tm1, R, D, (uint8_t*)o_t);
+    B200RL_CUDA_OK(launch_pdl(gather_kernel<16>, dim3(grid), dim3(256), 0, as_stream(stream), h->ring, (const long long*)idx_dev, (uint8_t*)o_tm1, (uint8_t*)a_tm1, R, D, (uint8_t*)o_t));
   else if (a4)
-    gather_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(h->ring, (const long long*)idx_dev, (uint8_t*)o_tm1, (uint8_t*)a_tm1, R, D, (uint8_t*)o_t);
+    B200RL_CUDA_OK(launch_pdl(gather_kernel<4>, dim3(grid), dim3(256), 0, as_stream(stream), h->ring, (const long long*)idx_dev, (uint8_t*)o_tm1, (uint8_t*)a_tm1, R, D, (uint8_t*)o_t));
   else
-    gather_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(h->ring, (const long long*)idx_dev, (uint8_t*)o_tm1, (uint8_t*)a_tm1, R, D, (uint8_t*)o_t);
+    B200RL_CUDA_OK(launch_pdl(gather_kernel<1>, dim3(grid), dim3(256), 0, as_stream(stream), h->ring, (const long long*)idx_dev, (uint8_t*)o_tm1, (uint8_t*)a_tm1, R, D, (uint8_t*)o_t));
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }
@@ -1247,9 +1265,9 @@ extern "C" int b200rl_replay_gather_rows(b200rl_replay* h, int32_t B, const int6
     B200RL_LAUNCH_OK();
     return B200RL_OK;
   }
-  gather_rows_kernel<<<dim3(B, 2, zsplit), 256, 0, as_stream(stream)>>>(h->ring, (const long long*)idx_dev, (uint8_t*)o_tm1, (uint8_t*)a_tm1, R, D,
-                                                               (uint8_t*)o_t, (uint4*)rows_tm1, (uint4*)rows_t, g->W / 4, g->pad_left,
-                                                               g->pad_top, Hp, row_elems / 8);
+  B200RL_CUDA_OK(launch_pdl(gather_rows_kernel, dim3(B, 2, zsplit), dim3(256), 0, as_stream(stream), h->ring, (const long long*)idx_dev,
+                            (uint8_t*)o_tm1, (uint8_t*)a_tm1, R, D, (uint8_t*)o_t, (uint4*)rows_tm1, (uint4*)rows_t, (int)(g->W / 4),
+                            (int)g->pad_left, (int)g->pad_top, (int)Hp, (int)(row_elems / 8)));
   B200RL_LAUNCH_OK();
   return B200RL_OK;
 }

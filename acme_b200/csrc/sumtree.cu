@@ -75,6 +75,7 @@ sample_kernel(TreeView t, int S, const ReplayState* __restrict__ st, long long M
               float* __restrict__ prob) {
   extern __shared__ __align__(16) float staged[];
   __shared__ int off[kMaxLevels];
+  pdl_launch_dependents();     // K3 may be scheduled behind this grid (its own pdl_wait orders the data)
   if (threadIdx.x == 0) {
     int o = 0;
     for (int l = 1; l <= S; ++l) {

@@ -23,6 +23,7 @@ from acme_b200 import _capi, actors, adders, agent, core, counting, loggers, net
 
 # Single-GPU pipelined update (see DQNLearner.__init__): '1' once measured faster than the one-graph serial step.
 PIPELINE_1GPU_DEFAULT = '0'
+K2_EARLY_DEFAULT = '1'      # measured: 0.298 -> 0.289 ms per step (gpurun_out/c3_bench_k2early.json)
 
 
 class DQNLearner(core.Learner, core.Saveable):
@@ -124,6 +125,10 @@ class DQNLearner(core.Learner, core.Saveable):
     self._wmax_done = None
     self._params_ready = None      # pipelined exchange: event the online forwards wait for
     self._k2_done = False          # K2 of this step was already issued beside the backward
+    self._pdl_scope_mode = os.environ.get('B200RL_PDL_SCOPE', 'all')
+    # single GPU: K2 right after K4 on the auxiliary stream (beside the backward) instead of beside Adam, which then has
+    # the HBM to itself
+    self._k2_early = self._world == 1 and os.environ.get('B200RL_K2_EARLY', K2_EARLY_DEFAULT) == '1'
     # data parallel: gradients and parameters live in a peer-mapped region and the exchange is fused with Adam
     # (parallel.PeerExchange); peer_exchange=False keeps the NCCL all-reduce + replicated Adam path
     if peer_exchange is None:
@@ -144,10 +149,21 @@ class DQNLearner(core.Learner, core.Saveable):
     # order (K1 of step t+1 still follows K2 of step t); `flush()` applies the update still in flight.
     self._pipeline1 = (self._px is None and self._world == 1 and self._concurrent and self._fused and bool(use_cuda_graph) and
                        hasattr(network, 'grad_buckets') and os.environ.get('B200RL_PIPELINE_1GPU', PIPELINE_1GPU_DEFAULT) == '1')
+    self._cap_stream = None
     if self._pipeline1:
       self._pipeline = True
       self._fuse_tail = False          # the pipelined update ends with its own target copy + increment
+      # The update's CTAs must not queue in front of the step's: the graph is captured on a high-priority stream (its
+      # forks too) and only the update's side stream keeps the default (lowest) priority, so K1 / K3 / the forwards take
+      # every SM slot the streaming Adam kernel frees (B200RL_PIPE_PRIO=0: all streams equal -- measured 0.281 ms per
+      # step, K1 finishing 40 us into the step behind Adam's 1,184 CTAs).
+      if os.environ.get('B200RL_PIPE_PRIO', '1') == '1':
+        self._cap_stream = torch.cuda.Stream(device=dev, priority=-1)
+        self._side = [torch.cuda.Stream(device=dev, priority=(0 if i == 3 else -1)) for i in range(6)]
     self._pipe_adam_ctas = int(os.environ.get('B200RL_PIPE_ADAM_CTAS', '0'))
+    # 1 = the update is forked AFTER K1 / K3 have been issued (they are short and latency-bound; the update then runs
+    # beside the forwards only); 0 = at the very start of the graph
+    self._pipe_order = int(os.environ.get('B200RL_PIPE_ORDER', '1'))
     # Early tail (>= 4 ranks, where the exchange is NVLink-bound rather than HBM-bound): the fc1 + head bucket of step
     # t is exchanged as soon as step t's dense backward has produced it, underneath the convolution backward, without
     # waiting for the peers' stores; the torso bucket's exchange at the start of step t+1 ends with the barrier that
@@ -306,6 +322,16 @@ class DQNLearner(core.Learner, core.Saveable):
       net.forward(o_t, self._bufs_sel)                           # learning.py:125
     self._stamp(2)
 
+  def _pdl_scope(self, what):
+    """Programmatic dependent launch per phase (B200RL_PDL_SCOPE = all | bwd | noft: everything but the target forward):
+    a dependent grid scheduled early holds SM slots while it waits, which the OTHER forward pass running beside it
+    could have used."""
+    scope = self._pdl_scope_mode
+    if scope == 'all':
+      return
+    off = what is not None and (scope == 'bwd' or (scope == 'noft' and what == 'tgt'))
+    _capi.load().b200rl_debug_set_pdl(0 if off else -1)
+
   def _obs_view_n(self, rows, n):
     torch = self._torch
     if self._obs_dtype == np.uint8:
@@ -346,9 +372,11 @@ class DQNLearner(core.Learner, core.Saveable):
       with torch.cuda.stream(side):
         if rows_all is not None and rows_t is None:
           rows_t = tgt.prepare_frames(o_t, 't')              # precision 1: the row image cannot be sliced
+        self._pdl_scope('tgt')
         tgt.lane(1).features(o_t, self._bufs_tgt, **(dict(rows=rows_t) if rows_t is not None else {}))   # learning.py:124
         done = torch.cuda.Event()
         done.record(side)
+      self._pdl_scope('on')
       tgt.lane(0)
       if ev_conv is not None:
         # pipelined exchange: the torso's parameters (a 0.3 MB bucket, exchanged first) must have landed before the
@@ -359,6 +387,7 @@ class DQNLearner(core.Learner, core.Saveable):
       if rows_all is not None:
         kw['rows'] = rows_all
       net.lane(0).features(o_all, self._bufs_on, **kw)       # learning.py:123 and :125 in one pass
+      self._pdl_scope(None)
       main.wait_event(done)
     else:
       if rows_all is not None and rows_t is None:
@@ -473,7 +502,7 @@ class DQNLearner(core.Learner, core.Saveable):
       aux.wait_event(ev)
       with torch.cuda.stream(aux):
         _capi.call('b200rl_mean', B, _capi.ptr(self.loss_ps), _capi.ptr(self.loss), _capi.current_stream())
-        if self._pipeline1 and self._replay_client is not None:
+        if (self._pipeline1 or self._k2_early) and self._replay_client is not None:
           # K2 (learning.py:151-154) only needs K4's priorities: beside the backward instead of after it
           ds.table.update_priorities_device(ds.keys, self.priority)
           self._k2_done = True
@@ -596,7 +625,8 @@ class DQNLearner(core.Learner, core.Saveable):
       split = self._concurrent and self._split_adam and (self._world == 1 or self._px is not None)
       adam = 'conv+join' if split else 'all'
     prio_done = None
-    if self._replay_client is not None and self._concurrent:
+    k2_done, self._k2_done = self._k2_done, False
+    if self._replay_client is not None and self._concurrent and not k2_done:
       # K2 only needs the priorities K4 produced: it runs beside the optimizer / exchange
       torch = self._torch
       ev = torch.cuda.Event()
@@ -616,7 +646,7 @@ class DQNLearner(core.Learner, core.Saveable):
     self._stamp(5)
     if prio_done is not None:
       self._torch.cuda.current_stream().wait_event(prio_done)
-    elif self._replay_client is not None:                       # learning.py:151-154
+    elif self._replay_client is not None and not k2_done:       # learning.py:151-154
       self._dataset.table.update_priorities_device(self._dataset.keys, self.priority)
     # learning.py:157-161: copy when num_steps % period == 0, evaluated before the increment
     if self._fuse_tail:
@@ -714,14 +744,19 @@ class DQNLearner(core.Learner, core.Saveable):
       self._inc_done.record(self._torch.cuda.current_stream())
     return events
 
-  def _compute(self, uniforms=None):
-    """The gradient half of a step: K1, K3, forwards, K4, backward, K2."""
+  def _compute_head(self, uniforms=None):
+    """K1 + K3 of a step."""
     self._stamp(0)
     self._mk('start')
     self._sample(uniforms)
     self._mk('k1')
     self._dataset.gather_only(self._gather_rows)
     self._mk('k3')
+
+  def _compute(self, uniforms=None, head_done: bool = False):
+    """The gradient half of a step: K1, K3, forwards, K4, backward, K2."""
+    if not head_done:
+      self._compute_head(uniforms)
     self._forwards()
     self._loss_backward()
     self._stamp(4)
@@ -740,9 +775,13 @@ class DQNLearner(core.Learner, core.Saveable):
     def body():
       self._early_tail_now = self._early_tail
       self._inc_done = None
+      head_done = False
       if variant == 'copy':          # the target network changes in this update: strict order
         self._apply_update(copy=True, tail_done=self._early_tail)
       elif variant == 'norm':        # update on a side stream; only the online forwards wait for it
+        if self._pipeline1 and self._pipe_order == 1:
+          self._compute_head()
+          head_done = True
         main, side = torch.cuda.current_stream(), self._side[3]
         ev = torch.cuda.Event()
         ev.record(main)
@@ -755,7 +794,7 @@ class DQNLearner(core.Learner, core.Saveable):
             self._params_ready = (ev, ev)
           self._update_done = torch.cuda.Event()     # the side stream must rejoin the capture's origin stream
           self._update_done.record(side)
-      self._compute()
+      self._compute(head_done=head_done)
       if variant == 'norm':
         torch.cuda.current_stream().wait_event(self._update_done)
       self._early_tail_now = False
@@ -816,7 +855,7 @@ class DQNLearner(core.Learner, core.Saveable):
     torch = self._torch
     g = torch.cuda.CUDAGraph()
     torch.cuda.synchronize()
-    with torch.cuda.graph(g):
+    with (torch.cuda.graph(g, stream=self._cap_stream) if self._cap_stream is not None else torch.cuda.graph(g)):
       fn()
     return g
 

@@ -425,7 +425,7 @@ def test_dqn_learner_steps_match_oracle(mode, monkeypatch):
   u_dev = torch.empty(B, device='cuda')
   from acme_b200 import _capi
   assert learner._pipeline == (mode == 'pipelined')
-  steps = 9 if mode == 'pipelined' else 5      # pipelined: two eager steps, then all three graph variants several times
+  steps = 5      # pipelined: two eager steps, then the 'first', 'copy' and 'norm' graphs (longer runs: the bit-identity test below)
   for step in range(steps):
     # the uniforms the learner is about to draw (device Philox keyed by (seed, call counter))
     _capi.call('b200rl_uniform', u_dev.data_ptr(), B, 7, counter.data_ptr(), step, _capi.current_stream())
@@ -447,8 +447,8 @@ def test_dqn_learner_steps_match_oracle(mode, monkeypatch):
     # trajectories then drift apart chaotically.  The Adam kernel itself is pinned to 1e-5 in
     # test_adam_and_global_norm and the gradients in test_dqn_atari_network_forward_backward; here the
     # first two updates must agree to 2% of one learning-rate step for all but <1e-3 of the parameters.
-    if mode == 'pipelined' and step in (0, 1, 4, 5, 8):
-      learner.flush()            # also leaves some updates pending across steps (2-3, 6-7): both orders are exercised
+    if mode == 'pipelined' and step in (0, 1, 4):
+      learner.flush()            # updates 2 and 3 stay pending across steps: applied by the next step's graph
     pending = learner._pending
     if step < 2:
       got = net.variables()
@@ -465,6 +465,50 @@ def test_dqn_learner_steps_match_oracle(mode, monkeypatch):
     helpers.sync_oracle_leaves_loose(table, oracle)
   assert learner.num_steps == steps
   server.stop()
+
+
+@pytest.mark.parametrize('precision', [0, 2])
+def test_pipelined_single_gpu_learner_is_bit_identical_to_serial(precision, monkeypatch):
+  """The single-GPU pipelined update (B200RL_PIPELINE_1GPU=1: Adam of step t inside step t+1's graph, beside K1 / K3 /
+  the torso forwards; K2 beside the backward) reorders launches, not arithmetic: TD errors, priorities, losses, sampled
+  indices of every step and the final parameters, moments and target network equal the serial learner's bit for bit.
+  Two identical tables (same inserts), period 3 so that all three graph variants ('first', 'norm', 'copy') run."""
+  import torch
+  import helpers
+  from acme_b200 import dqn, loggers, networks, replay
+  shape, A, n, B = (84, 84, 4), 6, 3, 32
+  runs = []
+  for pipelined in (False, True):
+    monkeypatch.setenv('B200RL_PIPELINE_1GPU', '1' if pipelined else '0')
+    rng = np.random.default_rng(4)
+    spec, table, server, adder, oracle = helpers.make_pair(shape, np.uint8, A, n, 0.99, 0.6, max_size=300)
+    for ep in range(8):
+      helpers.feed_episode(rng, adder, oracle, int(rng.integers(5, 30)), n, shape, np.uint8, A)
+    table.flush()
+    net = networks.DQNAtariNetwork(A, seed=5, precision=precision)
+    tgt = net.clone()
+    ds = replay.ReplayDataset(table, B, seed=7)
+    learner = dqn.DQNLearner(net, tgt, 0.99, 0.2, 1e-3, target_update_period=3, dataset=ds, replay_client=replay.Client(server),
+                             logger=loggers.NoOpLogger(), use_cuda_graph=True)
+    assert learner._pipeline == pipelined
+    trace = []
+    for step in range(13):
+      learner.step(fetch_loss=False)
+      torch.cuda.synchronize()
+      trace.append([x.clone() for x in (ds.idx, ds.keys.view(torch.int64), learner.td, learner.priority, learner.loss, learner.weight)])
+      if pipelined and step in (5, 9):
+        learner.flush()             # a flush between two graph replays: the next replay is the 'first' variant again
+    assert learner.num_steps == 13  # flushes the update in flight
+    torch.cuda.synchronize()
+    runs.append((trace, net.params.flat.clone(), tgt.params.flat.clone(), learner._m.clone(), learner._v.clone(),
+                 torch.from_numpy(table.read_tree_level(table.tree_levels()[0])).clone()))
+    server.stop()
+  (ta, *fa), (tb, *fb) = runs
+  for step, (xa, xb) in enumerate(zip(ta, tb)):
+    for name, a, b in zip(('idx', 'keys', 'td', 'priority', 'loss', 'weight'), xa, xb):
+      assert torch.equal(a, b), f'{name} differs at step {step}'
+  for name, a, b in zip(('params', 'target params', 'adam m', 'adam v', 'tree leaves'), fa, fb):
+    assert torch.equal(a, b), f'{name} differ after 13 updates'
 
 
 @pytest.mark.parametrize('use_graph', [False, True])
