@@ -23,6 +23,7 @@ from acme_b200 import _capi, actors, adders, agent, core, counting, loggers, net
 
 # Single-GPU pipelined update (see DQNLearner.__init__): '1' once measured faster than the one-graph serial step.
 PIPELINE_1GPU_DEFAULT = '0'
+STREAM_PRIO_DEFAULT = '0'
 K2_EARLY_DEFAULT = '1'      # measured: 0.298 -> 0.289 ms per step (gpurun_out/c3_bench_k2early.json)
 
 
@@ -160,10 +161,14 @@ class DQNLearner(core.Learner, core.Saveable):
       if os.environ.get('B200RL_PIPE_PRIO', '1') == '1':
         self._cap_stream = torch.cuda.Stream(device=dev, priority=-1)
         self._side = [torch.cuda.Stream(device=dev, priority=(0 if i == 3 else -1)) for i in range(6)]
+    elif self._world == 1 and self._concurrent and os.environ.get('B200RL_STREAM_PRIO', STREAM_PRIO_DEFAULT) == '1':
+      # the step's critical chain (K1, K3, online pass, head, data gradients) is captured on a high-priority stream; the
+      # forks (target pass, weight gradients, bias gradients, K2) keep the default priority and fill the slots left over
+      self._cap_stream = torch.cuda.Stream(device=dev, priority=-1)
     self._pipe_adam_ctas = int(os.environ.get('B200RL_PIPE_ADAM_CTAS', '0'))
     # 1 = the update is forked AFTER K1 / K3 have been issued (they are short and latency-bound; the update then runs
     # beside the forwards only); 0 = at the very start of the graph
-    self._pipe_order = int(os.environ.get('B200RL_PIPE_ORDER', '1'))
+    self._pipe_order = int(os.environ.get('B200RL_PIPE_ORDER', '0'))   # measured: 0.282 (0) vs 0.291 (1)
     # Early tail (>= 4 ranks, where the exchange is NVLink-bound rather than HBM-bound): the fc1 + head bucket of step
     # t is exchanged as soon as step t's dense backward has produced it, underneath the convolution backward, without
     # waiting for the peers' stores; the torso bucket's exchange at the start of step t+1 ends with the barrier that
