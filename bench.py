@@ -462,11 +462,11 @@ def run_ours(args):
     # (logged) when update i+1 has been issued, so the host-side inserts overlap the device step
     learner.step(fetch_loss='async')
 
-  for i in range(3):
+  for i in range(10):   # warm-up: pinned staging, both staging sets, the async-loss ring
     e2e_step(i)
   barrier()
   t0 = time.perf_counter()
-  e2e_steps = max(args.steps // 2, 10)
+  e2e_steps = max(args.steps, 200)       # at least as long as the value leg; short driver runs still time 200 updates (~70 ms)
   for i in range(e2e_steps):
     e2e_step(i + 3)
   learner.flush()
@@ -702,7 +702,7 @@ def run_d4pg(args):
     e2e_step(i)
   barrier()
   t0 = time.perf_counter()
-  e2e_steps = max(args.steps, 10)
+  e2e_steps = max(args.steps, 200)
   for i in range(e2e_steps):
     e2e_step(i + 3)
   last = learner.drain()

@@ -11,7 +11,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, 'acme_b200', 'lib', 'libb200rl.so')
-OPS = ['UTCHMMA', 'UTCQMMA', 'UTCMMA', 'LDTM', 'STTM', 'UTMALDG', 'UTMASTG', 'UTCBAR', 'UBLKCP', 'LDGMC', 'STGMC', 'SYNCS', 'HMMA', 'FFMA', 'MUFU']
+OPS = ['UTCHMMA', 'UTCQMMA', 'UTCMMA', 'LDTM', 'STTM', 'UTMALDG', 'UTMASTG', 'UTCBAR', 'UBLKCP', 'LDGMC', 'STGMC', 'SYNCS', 'HMMA', 'FFMA', 'MUFU',
+       'ACQBULK', 'PREEXIT']   # griddepcontrol.wait / griddepcontrol.launch_dependents (programmatic dependent launch)
 
 
 def main():
