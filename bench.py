@@ -551,7 +551,7 @@ def run_ours(args):
                 'gradients, TMA-fed: im2col for the convolutions incl. conv1 on uint8 frames via an integer-valued bf16 row image)'}[precision]
     achieved = STEP_FLOPS / net_s / 1e12 if net_s > 0 else None
     traffic = None    # dram bytes of the same kernel group from the committed `ncu --set full` capture (tensor-core mode)
-    prof_name = {1: 'ncu_full_r01_tc_layers_summary.json', 2: 'ncu_full_r02_bf16_step_summary.json'}.get(precision)
+    prof_name = {1: 'ncu_full_r01_tc_layers_summary.json', 2: 'ncu_full_r02c_bf16_step_summary.json'}.get(precision)
     prof = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', prof_name or 'none')
     traffic_source = None
     if os.path.exists(prof):
