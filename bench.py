@@ -287,6 +287,29 @@ class CpuTreePath:
     self.tree.set(idx, np.abs(self.rng.standard_normal(self.B))**0.6)
 
 
+def parity_record(precision: int):
+  """The bench line's `parity` object: which arithmetic mode was timed, the tolerance stated (and asserted) for it by
+  `tests/test_gpu_learner.py::test_dqn_learner_c2_shape_parity` against the fp32 oracle at the benchmarked shapes (B=256,
+  A=18, three updates on injected uniforms), and the largest error that test measured on B200 (committed
+  `profiles/parity_c2_<mode>.json`, written by the test itself; not re-measured in this run -- bench.py's own arm never
+  executes the oracle)."""
+  mode = {0: 'fp32', 1: 'tf32', 2: 'bf16'}[precision]
+  rec = {'mode': mode, 'oracle': 'oracle/learner.py (fp32 restatement of dqn/learning.py:121-154)',
+         'sampled_indices_and_nstep_bookkeeping': 'bit-exact (all modes)', 'tol': None, 'max_rel_err_td': None, 'source': None}
+  path = os.path.join(ROOT, 'profiles', f'parity_c2_{mode}.json')
+  try:
+    d = json.load(open(path))
+    runs = d['measured']
+    worst = lambda k: max(float(r[k]) for r in runs)
+    rec.update(tol=d['tolerances'], max_rel_err_td=worst('td'), max_rel_err_loss=worst('loss'), max_rel_err_priority=worst('priority'),
+               max_grad_rel_l2=max(max(float(v) for v in r['grad_rel_l2'].values()) for r in runs),
+               shape={'B': d['B'], 'A': d['A'], 'updates': len(runs)},
+               source=f'profiles/parity_c2_{mode}.json (tests/test_gpu_learner.py, measured on B200; errors are relative to the tensor scale)')
+  except (OSError, KeyError, ValueError, TypeError):
+    pass
+  return rec
+
+
 def _cpu_model():
   cpu = open('/proc/cpuinfo').read()
   return next((l.split(':', 1)[1].strip() for l in cpu.splitlines() if l.startswith('model name')), 'unknown')
@@ -592,6 +615,7 @@ def run_ours(args):
                      'traffic_source': traffic_source, 'alg_flops_per_launch_group': STEP_FLOPS, 'group_seconds': net_s,
                      'group_timing': 'CUDA events around replays of the captured network group (forwards + head/K4 + backward)'},
         'cpu_baseline': cpu_baseline,
+        'parity': parity_record(precision),
         'stages_us': {k: v * 1e6 for k, v in stages.items()},
         'hbm_kernels': {
             'k3_gather_nstep': {'alg_bytes': B * 112_944, 'GBps': B * 112_944 / stages['k3_gather_nstep'] / 1e9,

@@ -34,3 +34,22 @@ def test_product_path_refuses_to_run_without_a_gpu():
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
   assert out.returncode != 0
   assert not any(l.startswith('{"metric"') for l in out.stdout.splitlines())
+
+
+def test_parity_record_states_the_tested_tolerance():
+  """The `parity` object of our arm's line: every arithmetic mode names its stated tolerance and the committed B200
+  measurement it comes from; a missing profile degrades to nulls instead of breaking the bench line."""
+  sys.path.insert(0, ROOT)
+  import bench
+  for precision, mode, td_tol in ((0, 'fp32', 2e-5), (1, 'tf32', 1e-2), (2, 'bf16', 2e-2)):
+    rec = bench.parity_record(precision)
+    assert rec['mode'] == mode and rec['tol']['td'] == td_tol
+    assert 0 <= rec['max_rel_err_td'] <= td_tol and rec['max_rel_err_priority'] <= rec['tol']['priority']
+    assert rec['shape'] == {'B': 256, 'A': 18, 'updates': 3} and rec['source'].startswith(f'profiles/parity_c2_{mode}.json')
+    json.dumps(rec)
+  old_root, bench.ROOT = bench.ROOT, os.path.join(ROOT, 'does-not-exist')
+  try:
+    rec = bench.parity_record(2)
+  finally:
+    bench.ROOT = old_root
+  assert rec['mode'] == 'bf16' and rec['tol'] is None and rec['max_rel_err_td'] is None
