@@ -749,7 +749,8 @@ extern "C" int b200rl_replay_flush(b200rl_replay* h, void* stream) {
 }
 
 // the stream used by implicit flushes triggered from the host-only writer calls
-static cudaStream_t g_implicit_stream = nullptr;
+// (thread-local: b200rl_writer_append_stream redirects it to the caller's stream for the duration of its own call only)
+static thread_local cudaStream_t g_implicit_stream = nullptr;
 
 static int stage_tree_only(b200rl_replay* h, int64_t pos, float w) {
   if (h->n_item >= h->stage_items) {
