@@ -30,6 +30,36 @@ def test_run_episodes_and_steps():
     loop.run(num_episodes=1, num_steps=1)
 
 
+def test_episode_report_carries_counter_totals_and_call_order():
+  """Per step the actor sees select_action -> observe -> update after one observe_first; the report merges the shared
+  counter's running totals (environment_loop.py:68-104)."""
+  env = testing.DiscreteEnvironment(episode_length=3)
+  calls = []
+
+  class Spy(testing.Actor):
+    def select_action(self, observation):
+      calls.append('select')
+      return super().select_action(observation)
+    def observe_first(self, timestep):
+      calls.append('first')
+      super().observe_first(timestep)
+    def observe(self, action, next_timestep):
+      calls.append('observe')
+      super().observe(action, next_timestep)
+    def update(self):
+      calls.append('update')
+      super().update()
+
+  counter = counting.Counter()
+  loop = environment_loop.EnvironmentLoop(env, Spy(specs.make_environment_spec(env)), counter=counter, logger=loggers.NoOpLogger())
+  first = loop.run_episode()
+  second = loop.run_episode()
+  assert calls[:7] == ['first', 'select', 'observe', 'update', 'select', 'observe', 'update'] and calls.count('first') == 2
+  assert (first['episodes'], first['steps'], second['episodes'], second['steps']) == (1, 3, 2, 6)
+  assert second['episode_length'] == 3 and second['steps_per_second'] > 0
+  assert counter.get_counts() == {'episodes': 2, 'steps': 6}
+
+
 class CountingLearner:
 
   def __init__(self):
