@@ -329,6 +329,8 @@ class GaussianNoisePolicy:
 class D4PG(agent.Agent):
   """`acme/agents/tf/d4pg/agent.py:36-180`: uniform table, n-step adder, dataset, actor, learner."""
 
+  _learner_cls = D4PGLearner
+
   def __init__(self, environment_spec: specs.EnvironmentSpec, policy_network: networks.D4PGPolicy,
                critic_network: networks.D4PGCritic, discount: float = 0.99, batch_size: int = 256,
                prefetch_size: int = 4, target_update_period: int = 100, min_replay_size: int = 1000,
@@ -348,9 +350,17 @@ class D4PG(agent.Agent):
                                          seed=seed, stratified=False)
     aspec = environment_spec.actions
     actor = actors.FeedForwardActor(GaussianNoisePolicy(policy_network, sigma, aspec.minimum, aspec.maximum, seed), adder)
-    learner = D4PGLearner(policy_network, critic_network, policy_network.clone(), critic_network.clone(), discount,
-                          target_update_period, dataset, clipping=clipping, logger=logger, checkpoint=checkpoint,
-                          use_cuda_graph=use_cuda_graph)
+    learner = self._learner_cls(policy_network, critic_network, policy_network.clone(), critic_network.clone(), discount,
+                                target_update_period, dataset, clipping=clipping, logger=logger, checkpoint=checkpoint,
+                                use_cuda_graph=use_cuda_graph)
     self._table = table
     super().__init__(actor=actor, learner=learner, min_observations=max(batch_size, min_replay_size),
                      observations_per_step=float(batch_size) / samples_per_insert)
+
+
+class DDPG(D4PG):
+  """`acme/agents/tf/ddpg/agent.py:36-176`: the same single-process wiring (uniform table, n-step adder with constant
+  priorities, Gaussian-noise behaviour policy clipped to the action spec, two Adams at 1e-4) around `DDPGLearner`;
+  `critic_network` is a scalar critic (`networks.DDPGCritic`)."""
+
+  _learner_cls = DDPGLearner

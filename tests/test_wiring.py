@@ -140,3 +140,53 @@ def test_counter_shared_counts():
   child2 = counting.Counter(parent, 'child2')
   child1.increment(foo=1)
   assert child2.increment(foo=2) == {'child1_foo': 1, 'child2_foo': 2}
+
+
+def test_ddpg_and_d4pg_agents_share_the_wiring_and_differ_in_the_learner(monkeypatch):
+  """`ddpg/agent.py:36-176` and `d4pg/agent.py:36-180` build the same pieces (uniform table, n-step adder, dataset,
+  noisy behaviour policy, cadence batch/samples_per_insert after max(batch, min_replay) observations) around their
+  own learner.  Device objects are replaced by fakes: this checks the host wiring only."""
+  from acme_b200 import d4pg, replay
+  built = []
+
+  class FakeLearner:
+    def __init__(self, policy, critic, target_policy, target_critic, discount, period, dataset, **kwargs):
+      built.append((type(self).__name__, policy, critic, target_policy, target_critic, discount, period, dataset, kwargs))
+      self.steps = 0
+    def step(self):
+      self.steps += 1
+    def get_variables(self, names):
+      return [[] for _ in names]
+
+  class FakeD4PGLearner(FakeLearner):
+    pass
+
+  class FakeDDPGLearner(FakeLearner):
+    pass
+
+  class Net:
+    device = 0
+    def clone(self):
+      return Net()
+
+  monkeypatch.setattr(d4pg.D4PG, '_learner_cls', FakeD4PGLearner)
+  monkeypatch.setattr(d4pg.DDPG, '_learner_cls', FakeDDPGLearner)
+  monkeypatch.setattr(replay, 'make_reverb_dataset', lambda **kw: ('dataset', kw))
+  monkeypatch.setattr(d4pg, 'GaussianNoisePolicy', lambda policy, sigma, lo, hi, seed: (lambda observation: lo))
+  assert d4pg.DDPG.__mro__[1] is d4pg.D4PG
+
+  env = testing.ContinuousEnvironment(action_dim=2, observation_dim=3, bounded=True, episode_length=10)
+  spec = specs.make_environment_spec(env)
+  for cls, expected in ((d4pg.D4PG, 'FakeD4PGLearner'), (d4pg.DDPG, 'FakeDDPGLearner')):
+    built.clear()
+    policy, critic = Net(), Net()
+    a = cls(spec, policy, critic, batch_size=4, min_replay_size=2, samples_per_insert=2.0, n_step=3, discount=0.9,
+            target_update_period=7)
+    name, p, c, tp, tc, discount, period, dataset, kwargs = built[0]
+    assert name == expected and p is policy and c is critic and tp is not policy and tc is not critic
+    assert (discount, period) == (0.9, 7) and dataset[0] == 'dataset' and dataset[1]['batch_size'] == 4
+    assert dataset[1]['stratified'] is False            # Reverb's Uniform selector draws i.i.d.
+    table = a._table
+    assert table.alpha == 0.0 and table.max_window == 3 and table.min_size == 1
+    assert a._schedule.period == 2 and a._schedule.burst == 1   # 4 / 2.0 observations per learner step
+    a._server.stop()
