@@ -370,6 +370,11 @@ def run_reference(args):
       'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
       'dtype': 'f32', 'data': 'synthetic',
       'config': {'workload': 'DQN Atari-shaped 84x84x4 uint8, PER 1M items, batch 256, n=3 (BASELINE configs[1])',
+                 'items_per_rank': ref.items, 'batch_per_rank': ref.B, 'n_step': ref.n, 'alpha': 0.6, 'beta': 0.2,
+                 'network': 'DQNAtariNetwork(18), 8,018,611 params', 'optimizer': 'Adam 1e-3',
+                 'replay_ring': f'host ring of {ref.ring} uint8 84x84x4 steps under the 1M-priority tree (bounded sample: a 1M-step '
+                                'host ring would be 28 GB)',
+                 'parallelism': 'host cores of rank 0', 'cuda_graph': False,
                  'note': 'reference arm = CPU restatement (oracle port); Acme TF/JAX + Reverb are not installable offline'},
       'cpu_baseline': {'value': value, 'unit': 'updates/s', 'cores': ref.threads, 'kind': 'port', 'sample': sample},
       'e2e': {'value': value, 'unit': 'updates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
