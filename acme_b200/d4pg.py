@@ -359,7 +359,7 @@ class D4PG(agent.Agent):
 
 
 class DDPG(D4PG):
-  """`acme/agents/tf/ddpg/agent.py:36-176`: the same single-process wiring (uniform table, n-step adder with constant
+  """`acme/agents/tf/ddpg/agent.py:36-173`: the same single-process wiring (uniform table, n-step adder with constant
   priorities, Gaussian-noise behaviour policy clipped to the action spec, two Adams at 1e-4) around `DDPGLearner`;
   `critic_network` is a scalar critic (`networks.DDPGCritic`)."""
 

@@ -1,4 +1,4 @@
-"""DQfD: a DQN learner whose batches mix replay with demonstrations (`acme/agents/tf/dqfd/agent.py:37-219`).
+"""DQfD: a DQN learner whose batches mix replay with demonstrations (`acme/agents/tf/dqfd/agent.py:37-217`).
 
 The reference builds `sample_from_datasets([replay dataset, demonstrations.map(_n_step_transition_from_episode)],
 [1 - ratio, ratio])` and hands the result to the unchanged `DQNLearner`.  Here the demonstration episodes are uploaded

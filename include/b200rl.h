@@ -149,7 +149,7 @@ int b200rl_replay_gather_sequences(b200rl_replay* h, int32_t B, const int64_t* i
                                    void* obs, void* act, float* rew, float* disc, void* stream);
 
 /* DQfD demonstration mixing (acme/agents/tf/dqfd/agent.py:111-122: sample_from_datasets([replay, demonstrations],
- * [1 - ratio, ratio]); :160-219: _n_step_transition_from_episode).  The demonstration episodes are flat device arrays
+ * [1 - ratio, ratio]); :160-217: _n_step_transition_from_episode).  The demonstration episodes are flat device arrays
  * (obs [steps][obs_bytes], act [steps][act_bytes], rew / disc f32 [steps], episode_offsets i64 [num_episodes + 1]; every
  * episode has >= 3 steps).  Called after sample + gather: batch row b is REPLACED by a demonstration transition when
  * uniforms3[3b] < ratio (episode = floor(uniforms3[3b+1] * num_episodes), first step = floor(uniforms3[3b+2] *

@@ -1,7 +1,7 @@
 """DQfD demonstration mixing, CPU restatement.  TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
 
 Follows `acme/agents/tf/dqfd/agent.py`:
-  * `:160-219` `_n_step_transition_from_episode`: one n-step transition out of a whole demonstration episode, with ITS
+  * `:160-217` `_n_step_transition_from_episode`: one n-step transition out of a whole demonstration episode, with ITS
     arithmetic (a cumulative product of the environment discounts times powers of the agent discount, then one sum) --
     not the adder's running update (`acme/adders/reverb/transition.py:135-145`), so the two may differ in the last ulp;
   * `:111-122` `sample_from_datasets([replay, demonstrations], [1 - ratio, ratio])`: every batch ELEMENT comes from the

@@ -1,4 +1,4 @@
-"""oracle.dqfd (CPU): `_n_step_transition_from_episode` (`acme/agents/tf/dqfd/agent.py:160-219`) against an independent
+"""oracle.dqfd (CPU): `_n_step_transition_from_episode` (`acme/agents/tf/dqfd/agent.py:160-217`) against an independent
 exact evaluation, and the draw rule's ranges.  Parity of this oracle is UNPINNED (no vectors in the reference, TF absent);
 these are closed-form checks."""
 from fractions import Fraction

@@ -143,7 +143,7 @@ def test_counter_shared_counts():
 
 
 def test_ddpg_and_d4pg_agents_share_the_wiring_and_differ_in_the_learner(monkeypatch):
-  """`ddpg/agent.py:36-176` and `d4pg/agent.py:36-180` build the same pieces (uniform table, n-step adder, dataset,
+  """`ddpg/agent.py:36-173` and `d4pg/agent.py:36-180` build the same pieces (uniform table, n-step adder, dataset,
   noisy behaviour policy, cadence batch/samples_per_insert after max(batch, min_replay) observations) around their
   own learner.  Device objects are replaced by fakes: this checks the host wiring only."""
   from acme_b200 import d4pg, replay
